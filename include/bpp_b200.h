@@ -1,0 +1,206 @@
+/*
+ * bpp_b200.h — C ABI of the B200-native self-play hot path (bin-packing MCTS).
+ *
+ * The reference (Wang-Xiaoyang/resource_packing_self_play) is pure Python and has no FFI; its plug-in boundary is
+ * the duck-typed Game / MCTS / NeuralNet API (xw_mcts/Game.py:14-113, xw_mcts/NeuralNet.py:14-50) as specialised by
+ *   xw_mcts/binpacking/BinPackingGame.py:8-285, xw_mcts/binpacking/BinPackingLogic.py:19-109,
+ *   xw_mcts/MCTS_bpp.py:11-139, xw_mcts/binpacking/pytorch/NNet.py:69-85.
+ * Each entry point below names the reference method(s) it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative BPP_E_* code on failure; bpp_last_error() returns a
+ *     thread-local, NUL-terminated description of the last failure;
+ *   - no C++ types, exceptions or torch types cross this boundary: plain pointers, sizes and scalars;
+ *   - pointer arguments named *_dev are CALLER-OWNED DEVICE pointers (e.g. torch.Tensor.data_ptr()); pointer arguments
+ *     named *_host are host pointers (copied with cudaMemcpyAsync on `stream`; pass pinned memory for overlap);
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); 0 = legacy default stream;
+ *   - a handle is bound to one CUDA device and is NOT thread-safe; use one handle per device/process.
+ *
+ * Compact state layout ("record"): 32 little-endian uint32 words per state,
+ *   word r (0 <= r < H)  occupancy of bin row r, bit x = column x        (plane 0 of the reference state tensor)
+ *   word 28              remaining-items mask, bit i = item i not yet placed (planes 1..N non-zero)
+ *   words 29..31         tree bookkeeping inside the engine; ignored on input, zero on output of the env ops
+ * which, together with the per-episode item list (w_i, h_i), is bijective with the reference's (N+1, H, W) int64
+ * state tensor (BinPackingGame.py:118-120).  Limits: W <= 32, H <= 28, N <= 16.
+ */
+#ifndef BPP_B200_H
+#define BPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPP_REC_WORDS 32
+#define BPP_REC_REM 28
+#define BPP_MAX_ITEMS 16
+
+#define BPP_OK 0
+#define BPP_E_INVALID (-1)  /* bad argument / configuration */
+#define BPP_E_CUDA (-2)     /* CUDA runtime error */
+#define BPP_E_NOMEM (-3)    /* device allocation failed */
+#define BPP_E_CAPACITY (-4) /* a game's node/edge pool overflowed (sticky, see bpp_engine_check) */
+#define BPP_E_STATE (-5)    /* call sequence error */
+
+/* stub leaf evaluators computed inside the kernels (definitions: tests/golden/make_golden.py) */
+#define BPP_STUB_U 1
+#define BPP_STUB_V 2
+#define BPP_STUB_H 3
+#define BPP_STUB_D 4
+
+#define BPP_DTYPE_F32 0
+#define BPP_DTYPE_F64 1
+
+/* action choice after a search (bpp_engine_choose) */
+#define BPP_CHOOSE_ARGMAX_FIRST 0 /* first maximum of the visit counts (deterministic; parity tests) */
+#define BPP_CHOOSE_SAMPLE 1       /* a ~ counts / sum(counts)   (CoachBPP.py:86-87, greedy=False) */
+#define BPP_CHOOSE_GREEDY 2       /* uniformly random arg-max     (MCTS_bpp.py:43-49, greedy_a=0) */
+
+const char *bpp_last_error(void);
+/* library/ABI version: major*10000 + minor*100 + patch */
+int bpp_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stateless, batched environment ops (one warp per state).
+ * n states; recs_dev: uint32 [n][32]; items_wh_dev: int32 [n][N][2] = (w, h) of every item of that state's episode.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* BinPackingGame.getValidMoves (BinPackingGame.py:78-92) + Bin.get_moves_for_square / get_adjacency
+ * (BinPackingLogic.py:47-93).  valid_out_dev: uint8 [n][W*N], 1 = legal.  Unlike the reference it does not assert
+ * on "no legal move": the row is all-zero (that is has_valid_moves == False, BinPackingGame.py:94-107). */
+int bpp_env_valid_moves(int W, int H, int N, int n, const uint32_t *recs_dev, const int32_t *items_wh_dev,
+                        uint8_t *valid_out_dev, void *stream);
+
+/* BinPackingGame.getNextState (BinPackingGame.py:58-76) + Bin.execute_move (BinPackingLogic.py:95-109), including
+ * the silent truncation when fewer than h strip rows are empty.  actions_dev: int32 [n] (item*W + x; the item must
+ * be remaining).  recs_out_dev: uint32 [n][32]. */
+int bpp_env_next_state(int W, int H, int N, int n, const uint32_t *recs_dev, const int32_t *items_wh_dev,
+                       const int32_t *actions_dev, uint32_t *recs_out_dev, void *stream);
+
+/* BinPackingGame.getGameEnded + getRankedReward + get_minimal_bin_height (BinPackingGame.py:109-116,181-212).
+ * total_area_dev, max_h_dev: int32 [n]; bl_dev: float64 [n] ranked-reward threshold
+ * sorted(rewards)[floor(len*alpha)-1], NaN = empty rewards list (always +1); tie_dev: int8 [n] value returned on
+ * r == bl (the reference draws it from numpy's global RNG, BinPackingGame.py:212), may be NULL (=+1).
+ * ended_out_dev: int32 [n] in {0,+1,-1}; score_out_dev: float64 [n] raw reward r (undefined where ended == 0). */
+int bpp_env_game_ended(int W, int H, int N, int n, const uint32_t *recs_dev, const int32_t *items_wh_dev,
+                       const int32_t *total_area_dev, const int32_t *max_h_dev, const double *bl_dev,
+                       const int8_t *tie_dev, int32_t *ended_out_dev, double *score_out_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Search engine: G lockstep games, each with its own device-resident search graph (replaces the six dicts of
+ * MCTS.__init__, MCTS_bpp.py:16-26).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct bpp_engine bpp_engine;
+
+typedef struct bpp_config {
+    int32_t W, H, N;      /* virtual bin width/height, items per episode */
+    int32_t G;            /* games resident on this device */
+    int32_t num_sims;     /* args.numMCTSSims */
+    double cpuct;         /* args.cpuct */
+    int32_t node_cap;     /* nodes per game; 0 = num_sims*N + 2 (the per-episode worst case) */
+    int64_t edge_cap;     /* 8-byte edge units per game; 0 = auto (worst case if it fits in free memory) */
+    int32_t device;       /* CUDA device ordinal */
+} bpp_config;
+
+int bpp_engine_create(const bpp_config *cfg, bpp_engine **out);
+int bpp_engine_destroy(bpp_engine *e);
+/* bytes of device memory held by the handle */
+int64_t bpp_engine_device_bytes(const bpp_engine *e);
+
+/* New episode for every game (a fresh MCTS object, CoachBPP.py:124, plus getInitBoard/getInitItems,
+ * BinPackingGame.py:24-51).  items_wh: int32 [G][N][2]; total_area: int32 [G]; bl: float64 [G] (NaN = empty
+ * rewards list); tie: int8 [G] or NULL.  max_h (hidden state of the reference Game, BinPackingGame.py:48-50) is
+ * derived from the items. */
+int bpp_engine_reset(bpp_engine *e, const int32_t *items_wh_dev, const int32_t *total_area_dev, const double *bl_dev,
+                     const int8_t *tie_dev, void *stream);
+int bpp_engine_reset_host(bpp_engine *e, const int32_t *items_wh_host, const int32_t *total_area_host,
+                          const double *bl_host, const int8_t *tie_host, void *stream);
+
+/* Overwrite the root state of every game (drop-in single-state use: MCTS.getActionProb(state, ...) on an arbitrary
+ * state).  roots_dev: uint32 [G][32] records.  Keeps the search graph. */
+int bpp_engine_set_roots(bpp_engine *e, const uint32_t *roots_dev, void *stream);
+
+/* Begin a getActionProb call: zero the per-move simulation counters (MCTS_bpp.py:37). */
+int bpp_engine_begin_move(bpp_engine *e, void *stream);
+
+/* One lockstep step of MCTS.search (MCTS_bpp.py:56-139) for every game that still owes simulations this move:
+ * runs simulations (PUCT descent :107-125, terminal hits :78-83 with backup :130-139) until the game reaches an
+ * unexpanded non-terminal state, then parks that leaf for evaluation.  After it returns, the leaf batch is
+ * (leaf_count, leaf records); feed an evaluator and call bpp_engine_expand_backup. */
+int bpp_engine_select(bpp_engine *e, void *stream);
+/* number of parked leaves (synchronises `stream`) */
+int bpp_engine_leaf_count(bpp_engine *e, int32_t *count_host, void *stream);
+/* device-side leaf batch for a device evaluator: count int32[1], game index int32 [<=G], records uint32 [<=G][32]
+ * (row b = leaf b).  Pointers stay valid for the life of the handle. */
+int bpp_engine_leaf_buffers(bpp_engine *e, const int32_t **count_dev, const int32_t **game_dev,
+                            const uint32_t **recs_dev);
+/* Dense evaluator input, the reference's NNet.predict argument (getBinItem, BinPackingGame.py:118-120):
+ * planes_out_dev float32 [leaf_count][N+1][H][W]. */
+int bpp_engine_leaf_planes(bpp_engine *e, float *planes_out_dev, void *stream);
+/* Leaf expansion (MCTS_bpp.py:85-104: mask by valid moves, renormalise with numpy's pairwise summation order,
+ * uniform fallback) and path backup (:130-139) for every parked leaf.
+ * policy_dev: [leaf_count][A] of policy_dtype; value_dev: [leaf_count] of value_dtype. */
+int bpp_engine_expand_backup(bpp_engine *e, const void *policy_dev, int policy_dtype, const void *value_dev,
+                             int value_dtype, void *stream);
+
+/* Whole getActionProb simulation loop (MCTS_bpp.py:37-38) in ONE launch with an in-kernel stub evaluator:
+ * every game runs simulations until its per-move counter reaches num_sims. */
+int bpp_engine_search_stub(bpp_engine *e, int stub_kind, void *stream);
+
+/* counts[a] = Nsa[(root, a)] (MCTS_bpp.py:40-41).  counts_out_dev: int32 [G][A]. */
+int bpp_engine_root_counts(bpp_engine *e, int32_t *counts_out_dev, void *stream);
+int bpp_engine_root_counts_host(bpp_engine *e, int32_t *counts_out_host, void *stream);
+/* choose an action per game from the root visit counts; actions_out_dev int32 [G] (-1 for finished games) */
+int bpp_engine_choose(bpp_engine *e, int mode, uint64_t seed, int32_t *actions_out_dev, void *stream);
+/* Play actions_dev[g] in every unfinished game (CoachBPP.py:88-98): root <- getNextState(root, a); evaluates
+ * getGameEnded on the new root and latches (r, score) when the episode ends.  Starts the next move. */
+int bpp_engine_advance(bpp_engine *e, const int32_t *actions_dev, void *stream);
+/* Per-game episode status: done int32 [G] (0 running, 1 ended), r int32 [G] (+1/-1), score float64 [G],
+ * moves int32 [G].  Any pointer may be NULL. */
+int bpp_engine_status(bpp_engine *e, int32_t *done_out_dev, int32_t *r_out_dev, double *score_out_dev,
+                      int32_t *moves_out_dev, void *stream);
+/* current root records uint32 [G][32] (word 28 = remaining mask) */
+int bpp_engine_roots(bpp_engine *e, uint32_t *roots_out_dev, void *stream);
+
+/* Whole self-play episodes in one call with an in-kernel stub evaluator: reset must have been called; loops
+ * search_stub -> choose(mode, seed) -> advance until every game has ended.  counts_out_dev (may be NULL):
+ * int32 [max_moves][G][A] per-move visit counts; actions_out_dev (may be NULL): int32 [max_moves][G].
+ * moves_run_host receives the number of move rounds executed. */
+int bpp_engine_play_stub(bpp_engine *e, int stub_kind, int choose_mode, uint64_t seed, int max_moves,
+                         int32_t *counts_out_dev, int32_t *actions_out_dev, int32_t *moves_run_host, void *stream);
+
+/* Counters since creation (or the last bpp_engine_stats with reset != 0), copied to the host (synchronises):
+ * [0] simulations, [1] edges traversed, [2] expansions, [3] terminal hits, [4] nodes created, [5] hash probes,
+ * [6] kernels launched by this handle, [7] reserved. */
+int bpp_engine_stats(bpp_engine *e, uint64_t stats_host[8], int reset, void *stream);
+/* Synchronises and returns BPP_E_CAPACITY if any game overflowed its pools (the search of that game stopped). */
+int bpp_engine_check(bpp_engine *e, void *stream);
+/* per-game graph sizes: nodes int32 [G], edge units int32 [G] (either may be NULL) */
+int bpp_engine_graph_sizes(bpp_engine *e, int32_t *nodes_out_dev, int32_t *units_out_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Batched policy/value network forward (NNetWrapper.predict, NNet.py:69-85, over BinPackingNNet.forward,
+ * BinpackingNNet.py:72-81) in bf16 with fp32 accumulation.  Declared in bpp_net section of the library.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct bpp_net bpp_net;
+
+/* Create for board H x W, N items (in_channels = N + 1), action size A = W*N. */
+int bpp_net_create(int W, int H, int N, int max_batch, int device, bpp_net **out);
+int bpp_net_destroy(bpp_net *n);
+/* Load one parameter tensor by its reference state_dict name (e.g. "conv_seqs.0.res_block1.conv0.weight"),
+ * fp32, host pointer, PyTorch layout (OIHW for conv, [out][in] for linear). */
+int bpp_net_set_param(bpp_net *n, const char *name, const float *data_host, int64_t numel);
+/* commit parameters (converts/re-lays-out to the device formats the kernels use) */
+int bpp_net_commit(bpp_net *n, void *stream);
+/* Forward for B compact states.  recs_dev uint32 [B][32], game_dev int32 [B] (index into items_wh_dev rows; may be
+ * NULL for identity), items_wh_dev int32 [*][N][2]; if count_dev != NULL the batch size is read from device memory
+ * (*count_dev <= B).  policy_out_dev float32 [B][A] = exp(log_softmax(logits)); value_out_dev float32 [B]. */
+int bpp_net_forward(bpp_net *n, int B, const int32_t *count_dev, const uint32_t *recs_dev, const int32_t *game_dev,
+                    const int32_t *items_wh_dev, float *policy_out_dev, float *value_out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPP_B200_H */

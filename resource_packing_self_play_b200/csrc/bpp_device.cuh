@@ -1,0 +1,286 @@
+// bpp_device.cuh — warp-cooperative device primitives of the bin-packing self-play hot path (sm_100a).
+//
+// One warp owns one game / one state.  The occupancy grid lives as one 32-bit row mask per lane (lane r = bin row r),
+// mirrored into a 32-word shared-memory strip per warp for the broadcast sweeps of the valid-move computation.
+// Every function here is warp-collective: all 32 lanes must call it convergently.
+//
+// Reference semantics implemented (paths relative to /root/reference/xw_mcts):
+//   valid_words      BinPackingGame.getValidMoves :78-92, Bin.get_moves_for_square / get_adjacency
+//                    (binpacking/BinPackingLogic.py:47-93)
+//   apply_move       BinPackingGame.getNextState :58-76, Bin.execute_move (BinPackingLogic.py:95-109)
+//   terminal_value   BinPackingGame.getRankedReward :188-212, get_minimal_bin_height :181-186
+//   np_pairwise_sum  numpy's pairwise float64 add-reduction (np.sum at MCTS_bpp.py:90,100)
+//   puct_select      MCTS.search PUCT loop (MCTS_bpp.py:107-121), first-max tie-break
+//   backup_path      MCTS.search backup (MCTS_bpp.py:130-139)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bpp {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int REC_WORDS = 32;
+constexpr int REC_REM = 28;   // remaining-items mask
+constexpr int REC_NS = 29;    // Ns[s]
+constexpr int REC_OFF = 30;   // edge block offset (8-byte units) in the game's edge pool
+constexpr int REC_META = 31;  // nvalid | kind << 16
+constexpr int KIND_NEW = 0;   // key known, never visited by search (Es/Ps not computed yet)
+constexpr int KIND_EXP = 1;   // expanded (Ps, Vs, Ns exist)
+constexpr int KIND_TPOS = 2;  // terminal, Es = +1
+constexpr int KIND_TNEG = 3;  // terminal, Es = -1
+constexpr int MAX_AW = 16;    // valid-mask words (A <= 512)
+constexpr int MAX_LEAVES = 16;
+constexpr int MAX_PROG = 32;
+
+// numpy pairwise-sum plan for a length-A float64 reduction (host-built, see build_sum_plan in bpp_engine.cu)
+struct SumPlan {
+    int n_leaves;
+    int prog_len;
+    short leaf_base[MAX_LEAVES];
+    short leaf_n[MAX_LEAVES];
+    signed char prog[MAX_PROG];  // postfix: >= 0 push leaf, -1 add the two on top (left + right)
+};
+
+struct Geom {
+    int W, H, N, A, AW;
+    unsigned wmask;  // low W bits
+};
+
+__device__ __forceinline__ bool state_lane(int lane, int H) { return lane < H || lane == REC_REM; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// key hash: murmur-style per-lane mix, XOR-reduced with REDUX
+__device__ __forceinline__ uint32_t hash_state(uint32_t rec, int lane, int H) {
+    uint32_t v = state_lane(lane, H) ? rec : 0u;
+    uint32_t h = v + 0x9E3779B9u * (uint32_t)(lane + 1);
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    h = __reduce_xor_sync(FULL, h);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+
+__device__ __forceinline__ uint32_t strip_mask(int w, int x, unsigned wmask) {
+    uint32_t m = (w >= 32) ? 0xffffffffu : ((1u << w) - 1u);
+    return (m << x) & wmask;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Valid-move mask.  s_occ[0..H) = occupancy rows (shared, this warp's strip), s_items[i] = w | h << 8.
+// Action a = item*W + x is handled by lane a % 32 in round a / 32; the ballot of a round IS word a/32 of the mask.
+// Returns word k in lane k (0 elsewhere); also stores the words to s_vw[0..AW).
+__device__ __forceinline__ uint32_t valid_words(const Geom& g, const uint32_t* s_occ, const uint16_t* s_items,
+                                                uint32_t rem, int lane, uint32_t* s_vw) {
+    uint32_t mine = 0;
+    for (int k = 0; k < g.AW; ++k) {
+        const int a0 = k * 32;
+        const int i0 = a0 / g.W;
+        int i1 = (a0 + 31) / g.W;
+        if (i1 > g.N - 1) i1 = g.N - 1;
+        const uint32_t range = ((2u << i1) - 1u) & ~((1u << i0) - 1u);
+        uint32_t b = 0;
+        if (rem & range) {  // warp-uniform: skip rounds whose items are all placed
+            const int a = a0 + lane;
+            const int i = a / g.W;
+            const int x = a - i * g.W;
+            bool ok = false;
+            if (a < g.A && ((rem >> i) & 1u)) {
+                const int w = s_items[i] & 0xff, h = s_items[i] >> 8;
+                if (x + w <= g.W) {
+                    const uint32_t m = strip_mask(w, x, g.wmask);
+                    int cnt = 0, t = -1;
+                    for (int r = 0; r < g.H; ++r) {
+                        const uint32_t c = s_occ[r] & m;
+                        cnt += __popc(c);
+                        if (c == 0 && t < 0) t = r;
+                    }
+                    if (t < 0) t = g.H - 1;  // BinPackingLogic.py:66-68: the loop variable keeps its last value
+                    // (A) cell-count test, BinPackingLogic.py:89 ; (B) left adjacency, :63-70
+                    ok = (cnt <= w * (g.H - h)) && (x == 0 || ((s_occ[t] >> (x - 1)) & 1u));
+                }
+            }
+            b = __ballot_sync(FULL, ok);
+        }
+        if (lane == k) mine = b;
+    }
+    if (lane < MAX_AW) s_vw[lane] = mine;
+    __syncwarp();
+    return mine;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Placement: fill the strip in the first h strip rows that are completely empty (rows need not be contiguous; fewer
+// than h -> silent truncation).  rec is the lane's word of the state record; returns the new word.
+__device__ __forceinline__ uint32_t apply_move(const Geom& g, uint32_t rec, int lane, int item, int w, int h, int x) {
+    const uint32_t m = strip_mask(w, x, g.wmask);
+    const bool e = (lane < g.H) && ((rec & m) == 0);
+    const uint32_t E = __ballot_sync(FULL, e);
+    const int before = __popc(E & ((1u << lane) - 1u));
+    if (e && before < h) rec |= m;
+    if (lane == REC_REM) rec &= ~(1u << item);
+    return rec;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct RewardCtx {
+    int total_area;  // items_total_area
+    int numer;       // max(ceil(total_area / W), max_h)
+    double bl;       // ranked-reward threshold, NaN = empty rewards list
+    int tie;         // value on r == bl
+};
+
+// returns +1 / -1 and the raw reward r (score)
+__device__ __forceinline__ int terminal_value(const Geom& g, const RewardCtx& rc, uint32_t rec, int lane, double* score) {
+    const uint32_t rowv = lane < g.H ? rec : 0u;
+    const int pop = __reduce_add_sync(FULL, (unsigned)__popc(rowv));
+    const uint32_t ne = __ballot_sync(FULL, rowv != 0u);
+    double r;
+    if (pop != rc.total_area) {
+        r = 0.0;  // some item discarded or truncated, BinPackingGame.py:193-195
+    } else {
+        const int top = ne ? 32 - __clz(ne) : 1;  // get_minimal_bin_height, :181-186
+        r = __ddiv_rn((double)rc.numer, (double)top);
+    }
+    *score = r;
+    if (rc.bl != rc.bl) return 1;  // empty rewards list, :203-204
+    if (r > rc.bl || r == 1.0) return 1;
+    if (r < rc.bl) return -1;
+    return rc.tie;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// numpy float64 pairwise add-reduction over f(0..A), bit-exact: blocks of <= 128 elements use 8 interleaved
+// accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then a sequential tail; longer inputs split
+// recursively at n/2 rounded down to a multiple of 8.  Each 8-lane group of the warp evaluates one block.
+// scratch: >= MAX_LEAVES doubles of this warp's shared memory.  Result is warp-uniform.
+template <typename F>
+__device__ __forceinline__ double np_pairwise_sum(const SumPlan& plan, F f, int lane, double* scratch) {
+    const int j = lane & 7;
+    for (int pass = 0; pass * 4 < plan.n_leaves; ++pass) {
+        const int li = pass * 4 + (lane >> 3);
+        const bool act = li < plan.n_leaves;
+        const int base = act ? plan.leaf_base[li] : 0;
+        const int n = act ? plan.leaf_n[li] : 0;
+        const int lim = n - (n & 7);
+        double r = 0.0;
+        if (n >= 8) {
+            r = f(base + j);
+            for (int i = 8; i < lim; i += 8) r = __dadd_rn(r, f(base + i + j));
+        }
+        double t = __dadd_rn(r, __shfl_xor_sync(FULL, r, 1));
+        t = __dadd_rn(t, __shfl_xor_sync(FULL, t, 2));
+        t = __dadd_rn(t, __shfl_xor_sync(FULL, t, 4));
+        double res;
+        if (n >= 8) {
+            res = t;
+            for (int i = lim; i < n; ++i) res = __dadd_rn(res, f(base + i));
+        } else {
+            res = 0.0;
+            for (int i = 0; i < n; ++i) res = __dadd_rn(res, f(base + i));
+        }
+        if (act && j == 0) scratch[li] = res;
+    }
+    __syncwarp();
+    double st[8];
+    int sp = 0;
+    for (int t = 0; t < plan.prog_len; ++t) {
+        const int op = plan.prog[t];
+        if (op >= 0) {
+            st[sp++] = scratch[op];
+        } else {
+            const double b = st[--sp];
+            const double a = st[--sp];
+            st[sp++] = __dadd_rn(a, b);
+        }
+    }
+    __syncwarp();
+    return st[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Edge block of an expanded node with nv valid actions, nvp = nv rounded up to 4; 8-byte units:
+//   [0, nvp)        Q   float64     Qsa
+//   [nvp, 2nvp)     P   float64     Ps[s][a] (masked + renormalised prior)
+//   [2nvp, 3nvp)    NC  {int32 Nsa, int32 child node (-1 = not resolved yet)}
+//   [3nvp, 3nvp + nvp/4)  ACT uint16 action index, ascending
+struct EdgeBlock {
+    double* Q;
+    double* P;
+    int2* NC;
+    uint16_t* ACT;
+    __device__ __forceinline__ EdgeBlock(unsigned long long* base, int nvp)
+        : Q(reinterpret_cast<double*>(base)),
+          P(reinterpret_cast<double*>(base) + nvp),
+          NC(reinterpret_cast<int2*>(base + 2 * (size_t)nvp)),
+          ACT(reinterpret_cast<uint16_t*>(base + 3 * (size_t)nvp)) {}
+};
+__host__ __device__ __forceinline__ int edge_units(int nv) {
+    const int nvp = (nv + 3) & ~3;
+    return 3 * nvp + (nvp >> 2);
+}
+
+// PUCT arg-max with the reference's exact operation order and first-max tie-break (ascending action == ascending
+// edge index).  u = Q + ((cpuct*P)*sqrt(Ns)) / (1+Nsa) for visited edges, (cpuct*P)*sqrt(Ns+1e-8) otherwise.
+__device__ __forceinline__ int puct_select(const EdgeBlock& eb, int nv, int Ns, double cpuct, int lane) {
+    const double sq = __dsqrt_rn((double)Ns);
+    const double sqe = __dsqrt_rn(__dadd_rn((double)Ns, 1e-8));
+    double bu = __longlong_as_double((long long)0xfff0000000000000ull);  // -inf
+    int be = 0x7fffffff;
+    for (int e = lane; e < nv; e += 32) {
+        const double q = eb.Q[e];
+        const double p = eb.P[e];
+        const int n = eb.NC[e].x;
+        const double cp = __dmul_rn(cpuct, p);
+        double u;
+        if (n > 0)
+            u = __dadd_rn(q, __ddiv_rn(__dmul_rn(cp, sq), (double)(1 + n)));
+        else
+            u = __dmul_rn(cp, sqe);
+        u = __dadd_rn(u, 0.0);  // canonicalise -0.0 (Python's `>` treats it as equal to +0.0)
+        if (u > bu) { bu = u; be = e; }
+    }
+    // order-preserving map double -> uint64, then two 32-bit REDUX max + one REDUX min on the edge index
+    unsigned long long bits = (unsigned long long)__double_as_longlong(bu);
+    bits ^= (bits >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull;
+    const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
+    const uint32_t mh = __reduce_max_sync(FULL, hi);
+    const uint32_t ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    const bool match = (hi == mh) && (lo == ml) && (be != 0x7fffffff);
+    return (int)__reduce_min_sync(FULL, match ? (unsigned)be : 0x7fffffffu);
+}
+
+// One path entry per lane (lane d = depth d).  Paths never revisit a node (every move removes an item), so the
+// lanes update disjoint memory.
+struct PathEntry {
+    int node;
+    int off;   // edge block offset (units)
+    int nvp;
+    int e;
+};
+
+__device__ __forceinline__ void backup_path(uint32_t* nodes, unsigned long long* edges, const PathEntry& pe, int depth,
+                                            double v, int lane) {
+    if (lane < depth) {
+        EdgeBlock eb(edges + pe.off, pe.nvp);
+        const int n = eb.NC[pe.e].x;
+        const double q = eb.Q[pe.e];
+        // MCTS_bpp.py:130-136: Q <- (N*Q + v)/(N+1), first visit Q <- v
+        const double qn = n > 0 ? __ddiv_rn(__dadd_rn(__dmul_rn((double)n, q), v), (double)(n + 1)) : v;
+        eb.Q[pe.e] = qn;
+        eb.NC[pe.e].x = n + 1;
+        nodes[(size_t)pe.node * REC_WORDS + REC_NS] += 1u;  // Ns[s] += 1, :138
+    }
+    __syncwarp();
+}
+
+// stub evaluators (tests/golden/make_golden.py)
+__device__ __forceinline__ double stub_value_of(int pop, int nrem) {
+    return (double)((7 * pop + 3 * nrem) & 15) / 16.0 - 0.5;
+}
+template <int STUB>
+__device__ __forceinline__ double stub_prior(int a, int A, int pop) {
+    if (STUB == 1 || STUB == 2) return __ddiv_rn(1.0, (double)A);
+    if (STUB == 3) return __ddiv_rn(1.0, (double)(a + 3 + pop % 5));
+    return __ddiv_rn((double)((37 * a + 11 + pop) % 64 + 1), 4096.0);
+}
+
+}  // namespace bpp

@@ -1,0 +1,1091 @@
+// bpp_engine.cu — device-resident MCTS for G lockstep bin-packing games + the stateless env ops, behind the C ABI of
+// include/bpp_b200.h.  sm_100a only.
+//
+// Layout in HBM (per game g, struct-of-arrays across games):
+//   nodes  [G][node_cap][32] u32   one 128-byte record per known state: rows 0..H-1, rem, Ns, edge offset, meta
+//   table  [G][table_cap]    u32   open-addressing hash table over the FULL compact state (tag<<20 | node+1)
+//   edges  [G][edge_cap]     8 B   bump-allocated edge blocks (Q f64 | P f64 | {Nsa, child} | action u16), only the
+//                                  VALID actions of a node are stored, in ascending action order
+// This replaces the reference's six Python dicts keyed by 19.8 KB byte strings (MCTS_bpp.py:16-26).  The graph is a
+// DAG (transpositions share Ns/Ps, edges keep their own Nsa/Qsa), exactly like the dict version.
+//
+// Parallelisation: the reference's simulations of one game are strictly sequential (each reads the statistics the
+// previous one wrote), so ONE WARP owns one game and all parallelism is across games; inside the warp the 32 lanes
+// split the actions (PUCT, valid sweep), the bin rows (placement, hashing, key compare) and the path (backup).
+// No atomics are needed on the graph; atomics are only used for the leaf-batch cursor and the statistics.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bpp_b200.h"
+#include "bpp_device.cuh"
+
+using namespace bpp;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+extern "C" const char* bpp_last_error(void) { return g_err; }
+extern "C" int bpp_version(void) { return 100; }
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return set_err(BPP_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct Params {
+    Geom geom;
+    int G, num_sims, node_cap;
+    unsigned table_mask;
+    long long edge_cap;
+    double cpuct;
+    SumPlan plan;
+    // episode constants
+    uint8_t* item_w;   // [G][16]
+    uint8_t* item_h;   // [G][16]
+    int* total_area;   // [G]
+    int* numer;        // [G]
+    double* bl;        // [G]
+    int8_t* tie;       // [G]
+    // per-game state
+    uint32_t* root_rec;  // [G][32]
+    int* root_node;      // [G]
+    int* n_nodes;        // [G]
+    int* n_units;        // [G]
+    int* sims_done;      // [G]
+    int* moves_done;     // [G]
+    int* status;         // [G] 0 running, 1 episode ended, <0 error
+    int* ep_r;           // [G]
+    double* ep_score;    // [G]
+    // parked leaves (lockstep)
+    int* pend_depth;         // [G] -1 = none
+    int* pend_leaf;          // [G]
+    int4* pend_path;         // [G][32]
+    uint32_t* pend_valid;    // [G][16]
+    int* leaf_count;         // [1]
+    int* leaf_game;          // [G]
+    uint32_t* leaf_rec;      // [G][32]
+    // graph
+    uint32_t* nodes;
+    uint32_t* table;
+    unsigned long long* edges;
+    unsigned long long* stats;  // [8]
+};
+
+struct WarpSmem {
+    uint32_t occ[32];
+    uint32_t vw[MAX_AW];
+    uint16_t items[BPP_MAX_ITEMS];
+    double scratch[MAX_LEAVES];
+};
+
+struct Stats {
+    unsigned sims, edges, expansions, terminals, created, probes;
+};
+
+struct GameCtx {
+    int g;
+    uint32_t* nodes;
+    uint32_t* table;
+    unsigned long long* edges;
+    int n_nodes, n_units, root_node, err;
+    RewardCtx rc;
+};
+
+__device__ __forceinline__ void load_ctx(const Params& P, int g, int lane, GameCtx& gm, WarpSmem& sm) {
+    gm.g = g;
+    gm.nodes = P.nodes + (size_t)g * P.node_cap * REC_WORDS;
+    gm.table = P.table + (size_t)g * (P.table_mask + 1u);
+    gm.edges = P.edges + (size_t)g * (size_t)P.edge_cap;
+    gm.n_nodes = P.n_nodes[g];
+    gm.n_units = P.n_units[g];
+    gm.root_node = P.root_node[g];
+    gm.err = 0;
+    gm.rc.total_area = P.total_area[g];
+    gm.rc.numer = P.numer[g];
+    gm.rc.bl = P.bl[g];
+    gm.rc.tie = P.tie[g];
+    if (lane < BPP_MAX_ITEMS)
+        sm.items[lane] = (uint16_t)(P.item_w[g * BPP_MAX_ITEMS + lane] | (P.item_h[g * BPP_MAX_ITEMS + lane] << 8));
+    __syncwarp();
+}
+__device__ __forceinline__ void store_ctx(const Params& P, const GameCtx& gm, int lane) {
+    if (lane == 0) {
+        P.n_nodes[gm.g] = gm.n_nodes;
+        P.n_units[gm.g] = gm.n_units;
+        P.root_node[gm.g] = gm.root_node;
+        if (gm.err) P.status[gm.g] = -gm.err;
+    }
+}
+__device__ __forceinline__ void flush_stats(const Params& P, const Stats& st, int lane) {
+    if (lane == 0) {
+        if (st.sims) atomicAdd(&P.stats[0], (unsigned long long)st.sims);
+        if (st.edges) atomicAdd(&P.stats[1], (unsigned long long)st.edges);
+        if (st.expansions) atomicAdd(&P.stats[2], (unsigned long long)st.expansions);
+        if (st.terminals) atomicAdd(&P.stats[3], (unsigned long long)st.terminals);
+        if (st.created) atomicAdd(&P.stats[4], (unsigned long long)st.created);
+        if (st.probes) atomicAdd(&P.stats[5], (unsigned long long)st.probes);
+    }
+}
+
+// Find the node of a state (full-key equality, like the dict lookup of MCTS_bpp.py:76-85) or create it.
+__device__ __forceinline__ int lookup_or_insert(const Params& P, GameCtx& gm, uint32_t rec, int lane, Stats& st) {
+    const int H = P.geom.H;
+    const uint32_t h = hash_state(rec, lane, H);
+    const uint32_t tag = h >> 20;
+    uint32_t slot = h & P.table_mask;
+    for (;;) {
+        st.probes++;
+        const uint32_t ent = gm.table[slot];
+        if (ent == 0u) {
+            if (gm.n_nodes >= P.node_cap) {
+                gm.err = 4;
+                return -1;
+            }
+            const int idx = gm.n_nodes++;
+            gm.nodes[(size_t)idx * REC_WORDS + lane] = state_lane(lane, H) ? rec : 0u;
+            if (lane == 0) gm.table[slot] = (tag << 20) | (uint32_t)(idx + 1);
+            __syncwarp();
+            st.created++;
+            return idx;
+        }
+        if ((ent >> 20) == tag) {
+            const int cand = (int)(ent & 0xfffffu) - 1;
+            const uint32_t o = gm.nodes[(size_t)cand * REC_WORDS + lane];
+            const bool same = !state_lane(lane, H) || o == rec;
+            if (__all_sync(FULL, same)) return cand;
+        }
+        slot = (slot + 1u) & P.table_mask;
+    }
+}
+
+// Leaf expansion, MCTS_bpp.py:85-104.  sm.vw holds the valid mask.  prior(a) is the evaluator's p[a] as float64.
+template <typename F>
+__device__ __forceinline__ bool expand_node(const Params& P, GameCtx& gm, WarpSmem& sm, int cur, int lane, F prior) {
+    const uint32_t myw = lane < MAX_AW ? sm.vw[lane] : 0u;
+    const int nv = (int)__reduce_add_sync(FULL, (unsigned)__popc(myw));
+    const int nvp = (nv + 3) & ~3;
+    const int units = edge_units(nv);
+    if ((long long)gm.n_units + units > P.edge_cap) {
+        gm.err = 4;
+        return false;
+    }
+    const int off = gm.n_units;
+    gm.n_units += units;
+    EdgeBlock eb(gm.edges + off, nvp);
+    const uint32_t* vw = sm.vw;
+    auto masked = [&](int a) -> double { return ((vw[a >> 5] >> (a & 31)) & 1u) ? prior(a) : 0.0; };
+    const double tot = np_pairwise_sum(P.plan, masked, lane, sm.scratch);
+    const bool fallback = !(tot > 0.0);
+    double tot2 = 1.0;
+    if (fallback) {  // "all valid moves were masked": Ps <- Ps + valids, renormalise (MCTS_bpp.py:93-100)
+        auto bumped = [&](int a) -> double { return ((vw[a >> 5] >> (a & 31)) & 1u) ? __dadd_rn(prior(a), 1.0) : 0.0; };
+        tot2 = np_pairwise_sum(P.plan, bumped, lane, sm.scratch);
+    }
+    int base = 0;
+    for (int k = 0; k < P.geom.AW; ++k) {
+        const uint32_t wk = vw[k];
+        if ((wk >> lane) & 1u) {
+            const int a = k * 32 + lane;
+            const int e = base + __popc(wk & ((1u << lane) - 1u));
+            const double p = prior(a);
+            eb.P[e] = fallback ? __ddiv_rn(__dadd_rn(p, 1.0), tot2) : __ddiv_rn(p, tot);
+            eb.Q[e] = 0.0;
+            eb.NC[e] = make_int2(0, -1);
+            eb.ACT[e] = (uint16_t)a;
+        }
+        base += __popc(wk);
+    }
+    uint32_t* rec = gm.nodes + (size_t)cur * REC_WORDS;
+    if (lane == REC_NS) rec[REC_NS] = 0u;
+    if (lane == REC_OFF) rec[REC_OFF] = (uint32_t)off;
+    if (lane == REC_META) rec[REC_META] = (uint32_t)nv | ((uint32_t)KIND_EXP << 16);
+    __syncwarp();
+    return true;
+}
+
+// One simulation (MCTS.search from the root, MCTS_bpp.py:56-139).
+// Returns 0 = finished and backed up, 1 = parked an unexpanded leaf (STUB == 0 only), -1 = pool overflow.
+template <int STUB>
+__device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& sm, int lane, Stats& st) {
+    const Geom& ge = P.geom;
+    int cur = gm.root_node;
+    if (cur < 0) {
+        const uint32_t rrec = P.root_rec[(size_t)gm.g * REC_WORDS + lane];
+        cur = lookup_or_insert(P, gm, rrec, lane, st);
+        if (cur < 0) return -1;
+        gm.root_node = cur;
+    }
+    PathEntry pe = {0, 0, 0, 0};
+    int depth = 0;
+    double v = 0.0;
+    for (;;) {
+        const uint32_t rec = gm.nodes[(size_t)cur * REC_WORDS + lane];
+        const uint32_t meta = __shfl_sync(FULL, rec, REC_META);
+        const int kind = (int)((meta >> 16) & 0xffu);
+        if (kind == KIND_TPOS || kind == KIND_TNEG) {  // Es[s] != 0, :81-83
+            v = kind == KIND_TPOS ? 1.0 : -1.0;
+            st.terminals++;
+            break;
+        }
+        const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
+        if (kind == KIND_NEW) {
+            // first visit of this state: Es (getGameEnded) then, if not terminal, expansion
+            sm.occ[lane] = rec;
+            __syncwarp();
+            const uint32_t mine = valid_words(ge, sm.occ, sm.items, rem, lane, sm.vw);
+            if (!__any_sync(FULL, mine != 0u)) {
+                double score;
+                const int r = terminal_value(ge, gm.rc, rec, lane, &score);
+                if (lane == REC_META)
+                    gm.nodes[(size_t)cur * REC_WORDS + REC_META] = (uint32_t)(r > 0 ? KIND_TPOS : KIND_TNEG) << 16;
+                __syncwarp();
+                v = (double)r;
+                st.terminals++;
+                break;
+            }
+            if (STUB == 0) {
+                // park the leaf for the batched evaluator
+                int b = 0;
+                if (lane == 0) b = atomicAdd(P.leaf_count, 1);
+                b = __shfl_sync(FULL, b, 0);
+                if (lane == 0) {
+                    P.leaf_game[b] = gm.g;
+                    P.pend_depth[gm.g] = depth;
+                    P.pend_leaf[gm.g] = cur;
+                }
+                P.leaf_rec[(size_t)b * REC_WORDS + lane] = state_lane(lane, ge.H) ? rec : 0u;
+                P.pend_path[(size_t)gm.g * 32 + lane] = make_int4(pe.node, pe.off, pe.nvp, pe.e);
+                if (lane < MAX_AW) P.pend_valid[(size_t)gm.g * MAX_AW + lane] = sm.vw[lane];
+                return 1;
+            } else {
+                const uint32_t rowv = lane < ge.H ? rec : 0u;
+                const int pop = (int)__reduce_add_sync(FULL, (unsigned)__popc(rowv));
+                const int A = ge.A;
+                auto prior = [=](int a) -> double { return stub_prior<STUB>(a, A, pop); };
+                if (!expand_node(P, gm, sm, cur, lane, prior)) return -1;
+                v = STUB == 1 ? 0.0 : stub_value_of(pop, __popc(rem));
+                st.expansions++;
+                break;
+            }
+        }
+        // expanded node: PUCT
+        const int Ns = (int)__shfl_sync(FULL, rec, REC_NS);
+        const int off = (int)__shfl_sync(FULL, rec, REC_OFF);
+        const int nv = (int)(meta & 0xffffu);
+        const int nvp = (nv + 3) & ~3;
+        EdgeBlock eb(gm.edges + off, nvp);
+        const int e = puct_select(eb, nv, Ns, P.cpuct, lane);
+        const int act = eb.ACT[e];
+        int child = eb.NC[e].y;
+        if (lane == depth) {
+            pe.node = cur; pe.off = off; pe.nvp = nvp; pe.e = e;
+        }
+        depth++;
+        st.edges++;
+        if (child < 0) {  // first traversal of this edge: getNextState + key lookup (:125-128)
+            const int item = act / ge.W;
+            const int x = act - item * ge.W;
+            const int w = sm.items[item] & 0xff, h = sm.items[item] >> 8;
+            const uint32_t nrec = apply_move(ge, rec, lane, item, w, h, x);
+            child = lookup_or_insert(P, gm, nrec, lane, st);
+            if (child < 0) return -1;
+            if (lane == 0) eb.NC[e].y = child;
+            __syncwarp();
+        }
+        cur = child;
+    }
+    backup_path(gm.nodes, gm.edges, pe, depth, v, lane);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels: one warp per game, 4 warps per CTA
+constexpr int WARPS_PER_CTA = 4;
+
+template <int STUB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_search(Params P) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    if (g >= P.G) return;
+    if (P.status[g] != 0) return;
+    if (STUB == 0 && P.pend_depth[g] >= 0) return;
+    WarpSmem& sm = smem[wid];
+    GameCtx gm;
+    load_ctx(P, g, lane, gm, sm);
+    Stats st = {0, 0, 0, 0, 0, 0};
+    int done = P.sims_done[g];
+    while (done < P.num_sims) {
+        const int rc = simulate<STUB>(P, gm, sm, lane, st);
+        if (rc != 0) break;  // parked leaf (counted when it is expanded) or overflow
+        done++;
+        st.sims++;
+    }
+    if (lane == 0) P.sims_done[g] = done;
+    store_ctx(P, gm, lane);
+    flush_stats(P, st, lane);
+}
+
+// expansion + backup of the parked leaves; one warp per leaf
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_expand_backup(Params P, const void* policy, int policy_f64, const void* value, int value_f64) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.x * WARPS_PER_CTA + wid;
+    if (b >= *P.leaf_count) return;
+    const int g = P.leaf_game[b];
+    WarpSmem& sm = smem[wid];
+    GameCtx gm;
+    load_ctx(P, g, lane, gm, sm);
+    Stats st = {0, 0, 0, 0, 0, 0};
+    const int cur = P.pend_leaf[g];
+    const int depth = P.pend_depth[g];
+    if (lane < MAX_AW) sm.vw[lane] = P.pend_valid[(size_t)g * MAX_AW + lane];
+    __syncwarp();
+    const int4 pp = P.pend_path[(size_t)g * 32 + lane];
+    PathEntry pe = {pp.x, pp.y, pp.z, pp.w};
+    const int A = P.geom.A;
+    bool ok;
+    if (policy_f64) {
+        const double* pol = reinterpret_cast<const double*>(policy) + (size_t)b * A;
+        ok = expand_node(P, gm, sm, cur, lane, [=](int a) -> double { return pol[a]; });
+    } else {
+        const float* pol = reinterpret_cast<const float*>(policy) + (size_t)b * A;
+        ok = expand_node(P, gm, sm, cur, lane, [=](int a) -> double { return (double)pol[a]; });
+    }
+    if (ok) {
+        const double v = value_f64 ? reinterpret_cast<const double*>(value)[b]
+                                   : (double)reinterpret_cast<const float*>(value)[b];
+        backup_path(gm.nodes, gm.edges, pe, depth, v, lane);
+        st.expansions++;
+        st.sims++;
+        if (lane == 0) P.sims_done[g] += 1;
+    }
+    if (lane == 0) P.pend_depth[g] = -1;
+    store_ctx(P, gm, lane);
+    flush_stats(P, st, lane);
+}
+
+__global__ void k_reset(Params P, const int32_t* items_wh, const int32_t* total_area, const double* bl,
+                        const int8_t* tie) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.G) return;
+    const int N = P.geom.N;
+    int max_h = 0;
+    for (int i = 0; i < BPP_MAX_ITEMS; ++i) {
+        int w = 0, h = 0;
+        if (i < N) {
+            w = items_wh[((size_t)g * N + i) * 2 + 0];
+            h = items_wh[((size_t)g * N + i) * 2 + 1];
+            max_h = h > max_h ? h : max_h;
+        }
+        P.item_w[g * BPP_MAX_ITEMS + i] = (uint8_t)w;
+        P.item_h[g * BPP_MAX_ITEMS + i] = (uint8_t)h;
+    }
+    const int area = total_area[g];
+    const int cdiv = (area + P.geom.W - 1) / P.geom.W;  // np.ceil(items_total_area / bin_width), BinPackingGame.py:198
+    P.total_area[g] = area;
+    P.numer[g] = cdiv > max_h ? cdiv : max_h;
+    P.bl[g] = bl[g];
+    P.tie[g] = tie ? tie[g] : (int8_t)1;
+    for (int r = 0; r < REC_WORDS; ++r) P.root_rec[(size_t)g * REC_WORDS + r] = 0u;
+    P.root_rec[(size_t)g * REC_WORDS + REC_REM] = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+    P.root_node[g] = -1;
+    P.n_nodes[g] = 0;
+    P.n_units[g] = 0;
+    P.sims_done[g] = 0;
+    P.moves_done[g] = 0;
+    P.status[g] = 0;
+    P.ep_r[g] = 0;
+    P.ep_score[g] = 0.0;
+    P.pend_depth[g] = -1;
+}
+
+__global__ void k_set_roots(Params P, const uint32_t* roots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.G * REC_WORDS) return;
+    const int lane = i & 31, g = i >> 5;
+    P.root_rec[i] = state_lane(lane, P.geom.H) ? roots[i] : 0u;
+    if (lane == 0) {
+        P.root_node[g] = -1;
+        P.sims_done[g] = 0;
+        P.pend_depth[g] = -1;
+        if (P.status[g] == 1) P.status[g] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_root_counts(Params P, int32_t* out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    if (g >= P.G) return;
+    const int A = P.geom.A;
+    int32_t* row = out + (size_t)g * A;
+    for (int a = lane; a < A; a += 32) row[a] = 0;
+    __syncwarp();
+    const int root = P.root_node[g];
+    if (root < 0) return;
+    const uint32_t* nodes = P.nodes + (size_t)g * P.node_cap * REC_WORDS;
+    const uint32_t meta = nodes[(size_t)root * REC_WORDS + REC_META];
+    if (((meta >> 16) & 0xffu) != KIND_EXP) return;
+    const int nv = (int)(meta & 0xffffu), nvp = (nv + 3) & ~3;
+    EdgeBlock eb(P.edges + (size_t)g * (size_t)P.edge_cap + nodes[(size_t)root * REC_WORDS + REC_OFF], nvp);
+    for (int e = lane; e < nv; e += 32) row[eb.ACT[e]] = eb.NC[e].x;
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// action choice from the root visit counts (one thread per game; <= A edges)
+__global__ void k_choose(Params P, int mode, unsigned long long seed, int32_t* actions) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.G) return;
+    int act = -1;
+    const int root = P.root_node[g];
+    if (P.status[g] == 0 && root >= 0) {
+        const uint32_t* nodes = P.nodes + (size_t)g * P.node_cap * REC_WORDS;
+        const uint32_t meta = nodes[(size_t)root * REC_WORDS + REC_META];
+        if (((meta >> 16) & 0xffu) == KIND_EXP) {
+            const int nv = (int)(meta & 0xffffu), nvp = (nv + 3) & ~3;
+            EdgeBlock eb(P.edges + (size_t)g * (size_t)P.edge_cap + nodes[(size_t)root * REC_WORDS + REC_OFF], nvp);
+            const unsigned long long rnd =
+                splitmix64(seed ^ splitmix64(((unsigned long long)g << 20) ^ (unsigned long long)P.moves_done[g]));
+            if (mode == BPP_CHOOSE_SAMPLE) {
+                long long tot = 0;
+                for (int e = 0; e < nv; ++e) tot += eb.NC[e].x;
+                if (tot > 0) {
+                    long long t = (long long)(rnd % (unsigned long long)tot);
+                    for (int e = 0; e < nv; ++e) {
+                        t -= eb.NC[e].x;
+                        if (t < 0) { act = eb.ACT[e]; break; }
+                    }
+                }
+            } else {
+                int best = -1, nbest = 0;
+                for (int e = 0; e < nv; ++e) {
+                    const int n = eb.NC[e].x;
+                    if (n > best) { best = n; nbest = 1; act = eb.ACT[e]; }
+                    else if (n == best) nbest++;
+                }
+                if (mode == BPP_CHOOSE_GREEDY && nbest > 1) {
+                    int k = (int)(rnd % (unsigned long long)nbest);
+                    for (int e = 0; e < nv; ++e)
+                        if (eb.NC[e].x == best && k-- == 0) { act = eb.ACT[e]; break; }
+                }
+            }
+        }
+    }
+    actions[g] = act;
+}
+
+// play one real move per game (CoachBPP.py:88-98)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_advance(Params P, const int32_t* actions) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    if (g >= P.G) return;
+    if (P.status[g] != 0) return;
+    const Geom& ge = P.geom;
+    WarpSmem& sm = smem[wid];
+    GameCtx gm;
+    load_ctx(P, g, lane, gm, sm);
+    Stats st = {0, 0, 0, 0, 0, 0};
+    const int a = actions[g];
+    uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
+    const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
+    const int item = a >= 0 ? a / ge.W : -1;
+    if (a < 0 || a >= ge.A || !((rem >> item) & 1u)) {  // reference: assert sum(sum(item)) > 0, BinPackingGame.py:69
+        if (lane == 0) P.status[g] = -1;
+        return;
+    }
+    const int x = a - item * ge.W;
+    rec = apply_move(ge, rec, lane, item, sm.items[item] & 0xff, sm.items[item] >> 8, x);
+    rec = state_lane(lane, ge.H) ? rec : 0u;
+    P.root_rec[(size_t)g * REC_WORDS + lane] = rec;
+    gm.root_node = lookup_or_insert(P, gm, rec, lane, st);
+    // getGameEnded on the new root (CoachBPP.py:91)
+    sm.occ[lane] = rec;
+    __syncwarp();
+    const uint32_t nrem = __shfl_sync(FULL, rec, REC_REM);
+    const uint32_t mine = valid_words(ge, sm.occ, sm.items, nrem, lane, sm.vw);
+    if (!__any_sync(FULL, mine != 0u)) {
+        double score;
+        const int r = terminal_value(ge, gm.rc, rec, lane, &score);
+        if (lane == 0) {
+            P.status[g] = 1;
+            P.ep_r[g] = r;
+            P.ep_score[g] = score;
+        }
+    }
+    if (lane == 0) {
+        P.moves_done[g] += 1;
+        P.sims_done[g] = 0;
+    }
+    if (gm.err) {
+        if (lane == 0) P.status[g] = -gm.err;
+        gm.err = 0;
+    }
+    store_ctx(P, gm, lane);
+    flush_stats(P, st, lane);
+}
+
+// dense evaluator input: planes [B][N+1][H][W] float32 (getBinItem, BinPackingGame.py:118-120)
+__global__ void k_leaf_planes(Params P, float* out) {
+    const int B = *P.leaf_count;
+    const Geom& ge = P.geom;
+    const int per = (ge.N + 1) * ge.H * ge.W;
+    const long long total = (long long)B * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        int r = (int)(i - (long long)b * per);
+        const int c = r / (ge.H * ge.W);
+        r -= c * ge.H * ge.W;
+        const int y = r / ge.W, x = r - y * ge.W;
+        const uint32_t* rec = P.leaf_rec + (size_t)b * REC_WORDS;
+        float v;
+        if (c == 0) {
+            v = (float)((rec[y] >> x) & 1u);
+        } else {
+            const int g = P.leaf_game[b];
+            const int it = c - 1;
+            const bool remaining = (rec[REC_REM] >> it) & 1u;
+            v = (remaining && y < P.item_h[g * BPP_MAX_ITEMS + it] && x < P.item_w[g * BPP_MAX_ITEMS + it]) ? 1.f : 0.f;
+        }
+        out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stateless env kernels (one warp per state)
+struct EnvArgs {
+    Geom geom;
+    int n;
+    const uint32_t* recs;
+    const int32_t* items_wh;
+};
+__device__ __forceinline__ void env_load(const EnvArgs& E, int s, int lane, WarpSmem& sm, uint32_t& rec) {
+    rec = E.recs[(size_t)s * REC_WORDS + lane];
+    rec = state_lane(lane, E.geom.H) ? rec : 0u;
+    sm.occ[lane] = rec;
+    if (lane < BPP_MAX_ITEMS) {
+        int w = 0, h = 0;
+        if (lane < E.geom.N) {
+            w = E.items_wh[((size_t)s * E.geom.N + lane) * 2 + 0];
+            h = E.items_wh[((size_t)s * E.geom.N + lane) * 2 + 1];
+        }
+        sm.items[lane] = (uint16_t)((w & 0xff) | ((h & 0xff) << 8));
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_env_valid(EnvArgs E, uint8_t* out) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int s = blockIdx.x * WARPS_PER_CTA + wid;
+    if (s >= E.n) return;
+    WarpSmem& sm = smem[wid];
+    uint32_t rec;
+    env_load(E, s, lane, sm, rec);
+    const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
+    valid_words(E.geom, sm.occ, sm.items, rem, lane, sm.vw);
+    for (int a = lane; a < E.geom.A; a += 32) out[(size_t)s * E.geom.A + a] = (uint8_t)((sm.vw[a >> 5] >> (a & 31)) & 1u);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_env_next(EnvArgs E, const int32_t* actions, uint32_t* out) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int s = blockIdx.x * WARPS_PER_CTA + wid;
+    if (s >= E.n) return;
+    WarpSmem& sm = smem[wid];
+    uint32_t rec;
+    env_load(E, s, lane, sm, rec);
+    const int a = actions[s];
+    if (a >= 0 && a < E.geom.A) {
+        const int item = a / E.geom.W, x = a - item * E.geom.W;
+        rec = apply_move(E.geom, rec, lane, item, sm.items[item] & 0xff, sm.items[item] >> 8, x);
+    }
+    out[(size_t)s * REC_WORDS + lane] = state_lane(lane, E.geom.H) ? rec : 0u;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_env_ended(EnvArgs E, const int32_t* total_area, const int32_t* max_h, const double* bl, const int8_t* tie,
+            int32_t* ended, double* score_out) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int s = blockIdx.x * WARPS_PER_CTA + wid;
+    if (s >= E.n) return;
+    WarpSmem& sm = smem[wid];
+    uint32_t rec;
+    env_load(E, s, lane, sm, rec);
+    const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
+    const uint32_t mine = valid_words(E.geom, sm.occ, sm.items, rem, lane, sm.vw);
+    int res = 0;
+    double score = 0.0;
+    if (!__any_sync(FULL, mine != 0u)) {
+        RewardCtx rc;
+        rc.total_area = total_area[s];
+        const int cdiv = (rc.total_area + E.geom.W - 1) / E.geom.W;
+        rc.numer = cdiv > max_h[s] ? cdiv : max_h[s];
+        rc.bl = bl[s];
+        rc.tie = tie ? tie[s] : 1;
+        res = terminal_value(E.geom, rc, rec, lane, &score);
+    }
+    if (lane == 0) {
+        ended[s] = res;
+        score_out[s] = score;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+static void build_sum_plan_rec(SumPlan& p, int base, int n) {
+    if (n <= 128) {  // numpy PW_BLOCKSIZE
+        p.leaf_base[p.n_leaves] = (short)base;
+        p.leaf_n[p.n_leaves] = (short)n;
+        p.prog[p.prog_len++] = (signed char)p.n_leaves++;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        build_sum_plan_rec(p, base, n2);
+        build_sum_plan_rec(p, base + n2, n - n2);
+        p.prog[p.prog_len++] = -1;
+    }
+}
+
+static int make_geom(int W, int H, int N, Geom* g) {
+    if (W < 1 || W > 32 || H < 1 || H > 28 || N < 1 || N > BPP_MAX_ITEMS)
+        return set_err(BPP_E_INVALID, "unsupported geometry W=%d H=%d N=%d (limits: W<=32, H<=28, N<=16)", W, H, N);
+    g->W = W; g->H = H; g->N = N; g->A = W * N; g->AW = (W * N + 31) / 32;
+    g->wmask = W >= 32 ? 0xffffffffu : ((1u << W) - 1u);
+    return BPP_OK;
+}
+
+struct bpp_engine {
+    bpp_config cfg;
+    Params P;
+    std::vector<void*> allocs;
+    int64_t bytes = 0;
+    unsigned long long launches = 0;
+    bool leaf_parked = false;
+    int32_t* d_actions = nullptr;  // scratch for play_stub
+    int32_t* d_items = nullptr;    // staging for the *_host entry points
+    int32_t* d_area = nullptr;
+    double* d_bl = nullptr;
+    int8_t* d_tie = nullptr;
+    int32_t* d_counts = nullptr;
+    int* h_status = nullptr;
+};
+
+template <typename T>
+static int dev_alloc(bpp_engine* e, T** p, size_t count) {
+    void* q = nullptr;
+    const size_t bytes = count * sizeof(T);
+    cudaError_t err = cudaMalloc(&q, bytes ? bytes : 1);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(BPP_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(err));
+    }
+    e->allocs.push_back(q);
+    e->bytes += (int64_t)bytes;
+    *p = reinterpret_cast<T*>(q);
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_destroy(bpp_engine* e) {
+    if (!e) return BPP_OK;
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->h_status) cudaFreeHost(e->h_status);
+    delete e;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
+    if (!cfg || !out) return set_err(BPP_E_INVALID, "null argument");
+    *out = nullptr;
+    Geom ge;
+    int rc = make_geom(cfg->W, cfg->H, cfg->N, &ge);
+    if (rc) return rc;
+    if (cfg->G < 1 || cfg->num_sims < 0) return set_err(BPP_E_INVALID, "G=%d num_sims=%d", cfg->G, cfg->num_sims);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    bpp_engine* e = new bpp_engine();
+    e->cfg = *cfg;
+    Params& P = e->P;
+    memset(&P, 0, sizeof(P));
+    P.geom = ge;
+    P.G = cfg->G;
+    P.num_sims = cfg->num_sims;
+    P.cpuct = cfg->cpuct;
+    // every simulation creates at most one node, every real move at most one more (+ the first root)
+    P.node_cap = cfg->node_cap > 0 ? cfg->node_cap : cfg->num_sims * cfg->N + cfg->N + 2;
+    if (P.node_cap >= (1 << 20) - 1) {
+        delete e;
+        return set_err(BPP_E_INVALID, "node_cap %d too large (max 2^20-2)", P.node_cap);
+    }
+    unsigned tc = 64;
+    while (tc < 2u * (unsigned)P.node_cap) tc <<= 1;
+    P.table_mask = tc - 1u;
+    memset(&P.plan, 0, sizeof(P.plan));
+    build_sum_plan_rec(P.plan, 0, ge.A);
+    const size_t G = (size_t)cfg->G;
+#define ALLOC(ptr, count)                          \
+    if ((rc = dev_alloc(e, &(ptr), (count))) != 0) { \
+        bpp_engine_destroy(e);                     \
+        return rc;                                 \
+    }
+    ALLOC(P.item_w, G * BPP_MAX_ITEMS);
+    ALLOC(P.item_h, G * BPP_MAX_ITEMS);
+    ALLOC(P.total_area, G);
+    ALLOC(P.numer, G);
+    ALLOC(P.bl, G);
+    ALLOC(P.tie, G);
+    ALLOC(P.root_rec, G * REC_WORDS);
+    ALLOC(P.root_node, G);
+    ALLOC(P.n_nodes, G);
+    ALLOC(P.n_units, G);
+    ALLOC(P.sims_done, G);
+    ALLOC(P.moves_done, G);
+    ALLOC(P.status, G);
+    ALLOC(P.ep_r, G);
+    ALLOC(P.ep_score, G);
+    ALLOC(P.pend_depth, G);
+    ALLOC(P.pend_leaf, G);
+    ALLOC(P.pend_path, G * 32);
+    ALLOC(P.pend_valid, G * MAX_AW);
+    ALLOC(P.leaf_count, 1);
+    ALLOC(P.leaf_game, G);
+    ALLOC(P.leaf_rec, G * REC_WORDS);
+    ALLOC(P.stats, 8);
+    ALLOC(e->d_actions, G);
+    ALLOC(e->d_items, G * (size_t)ge.N * 2);
+    ALLOC(e->d_area, G);
+    ALLOC(e->d_bl, G);
+    ALLOC(e->d_tie, G);
+    ALLOC(e->d_counts, G * (size_t)ge.A);
+    ALLOC(P.nodes, G * (size_t)P.node_cap * REC_WORDS);
+    ALLOC(P.table, G * (size_t)tc);
+    // edge pool: worst case = every node expanded with all A actions valid; shrink to fit free memory
+    const long long worst = (long long)P.node_cap * edge_units(ge.A);
+    long long cap = cfg->edge_cap > 0 ? cfg->edge_cap : worst;
+    if (cfg->edge_cap <= 0) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const long long fit = (long long)((double)free_b * 0.70 / (double)G / 8.0);
+        if (cap > fit) cap = fit;
+        const long long floor_units = (long long)edge_units(ge.A) * 4;
+        if (cap < floor_units) cap = floor_units;
+    }
+    if (cap > 0x7fffffffll) cap = 0x7fffffffll;
+    P.edge_cap = cap;
+    ALLOC(P.edges, G * (size_t)cap);
+#undef ALLOC
+    CUDA_TRY(cudaMemset(P.stats, 0, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(P.status, 0xff, G * sizeof(int)));  // not reset yet
+    CUDA_TRY(cudaMemset(P.pend_depth, 0xff, G * sizeof(int)));
+    CUDA_TRY(cudaMemset(P.leaf_count, 0, sizeof(int)));
+    CUDA_TRY(cudaMallocHost(&e->h_status, G * sizeof(int)));
+    *out = e;
+    return BPP_OK;
+}
+
+extern "C" int64_t bpp_engine_device_bytes(const bpp_engine* e) { return e ? e->bytes : 0; }
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int grid_warps(int n) { return (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+#define LAUNCH_CHECK(e)                                                                          \
+    do {                                                                                         \
+        (e)->launches++;                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess) return set_err(BPP_E_CUDA, "kernel launch failed: %s (%s:%d)",    \
+                                              cudaGetErrorString(_e), __FILE__, __LINE__);       \
+    } while (0)
+
+extern "C" int bpp_engine_reset(bpp_engine* e, const int32_t* items_wh_dev, const int32_t* total_area_dev,
+                                const double* bl_dev, const int8_t* tie_dev, void* stream) {
+    if (!e || !items_wh_dev || !total_area_dev || !bl_dev) return set_err(BPP_E_INVALID, "null argument");
+    Params& P = e->P;
+    CUDA_TRY(cudaMemsetAsync(P.table, 0, (size_t)P.G * (P.table_mask + 1u) * sizeof(uint32_t), S(stream)));
+    CUDA_TRY(cudaMemsetAsync(P.leaf_count, 0, sizeof(int), S(stream)));
+    k_reset<<<(P.G + 127) / 128, 128, 0, S(stream)>>>(P, items_wh_dev, total_area_dev, bl_dev, tie_dev);
+    LAUNCH_CHECK(e);
+    e->leaf_parked = false;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_reset_host(bpp_engine* e, const int32_t* items_wh_host, const int32_t* total_area_host,
+                                     const double* bl_host, const int8_t* tie_host, void* stream) {
+    if (!e || !items_wh_host || !total_area_host || !bl_host) return set_err(BPP_E_INVALID, "null argument");
+    const size_t G = (size_t)e->P.G, N = (size_t)e->P.geom.N;
+    int32_t* d_items = e->d_items;
+    int32_t* d_area = e->d_area;
+    double* d_bl = e->d_bl;
+    int8_t* d_tie = e->d_tie;
+    CUDA_TRY(cudaMemcpyAsync(d_items, items_wh_host, G * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, S(stream)));
+    CUDA_TRY(cudaMemcpyAsync(d_area, total_area_host, G * sizeof(int32_t), cudaMemcpyHostToDevice, S(stream)));
+    CUDA_TRY(cudaMemcpyAsync(d_bl, bl_host, G * sizeof(double), cudaMemcpyHostToDevice, S(stream)));
+    if (tie_host) CUDA_TRY(cudaMemcpyAsync(d_tie, tie_host, G * sizeof(int8_t), cudaMemcpyHostToDevice, S(stream)));
+    return bpp_engine_reset(e, d_items, d_area, d_bl, tie_host ? d_tie : nullptr, stream);
+}
+
+extern "C" int bpp_engine_set_roots(bpp_engine* e, const uint32_t* roots_dev, void* stream) {
+    if (!e || !roots_dev) return set_err(BPP_E_INVALID, "null argument");
+    const int n = e->P.G * REC_WORDS;
+    k_set_roots<<<(n + 255) / 256, 256, 0, S(stream)>>>(e->P, roots_dev);
+    LAUNCH_CHECK(e);
+    e->leaf_parked = false;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_begin_move(bpp_engine* e, void* stream) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    CUDA_TRY(cudaMemsetAsync(e->P.sims_done, 0, (size_t)e->P.G * sizeof(int), S(stream)));
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_select(bpp_engine* e, void* stream) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    if (e->leaf_parked) return set_err(BPP_E_STATE, "bpp_engine_select called with leaves still parked");
+    CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, sizeof(int), S(stream)));
+    k_search<0><<<grid_warps(e->P.G), WARPS_PER_CTA * 32, 0, S(stream)>>>(e->P);
+    LAUNCH_CHECK(e);
+    e->leaf_parked = true;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_leaf_count(bpp_engine* e, int32_t* count_host, void* stream) {
+    if (!e || !count_host) return set_err(BPP_E_INVALID, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(count_host, e->P.leaf_count, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_leaf_buffers(bpp_engine* e, const int32_t** count_dev, const int32_t** game_dev,
+                                       const uint32_t** recs_dev) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    if (count_dev) *count_dev = e->P.leaf_count;
+    if (game_dev) *game_dev = e->P.leaf_game;
+    if (recs_dev) *recs_dev = e->P.leaf_rec;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_leaf_planes(bpp_engine* e, float* planes_out_dev, void* stream) {
+    if (!e || !planes_out_dev) return set_err(BPP_E_INVALID, "null argument");
+    k_leaf_planes<<<296, 256, 0, S(stream)>>>(e->P, planes_out_dev);
+    LAUNCH_CHECK(e);
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_expand_backup(bpp_engine* e, const void* policy_dev, int policy_dtype,
+                                        const void* value_dev, int value_dtype, void* stream) {
+    if (!e || !policy_dev || !value_dev) return set_err(BPP_E_INVALID, "null argument");
+    if (!e->leaf_parked) return set_err(BPP_E_STATE, "bpp_engine_expand_backup without a preceding bpp_engine_select");
+    k_expand_backup<<<grid_warps(e->P.G), WARPS_PER_CTA * 32, 0, S(stream)>>>(
+        e->P, policy_dev, policy_dtype == BPP_DTYPE_F64, value_dev, value_dtype == BPP_DTYPE_F64);
+    LAUNCH_CHECK(e);
+    e->leaf_parked = false;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_search_stub(bpp_engine* e, int stub_kind, void* stream) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    if (e->leaf_parked) return set_err(BPP_E_STATE, "leaves are parked; call bpp_engine_expand_backup first");
+    const int grid = grid_warps(e->P.G), block = WARPS_PER_CTA * 32;
+    switch (stub_kind) {
+        case BPP_STUB_U: k_search<1><<<grid, block, 0, S(stream)>>>(e->P); break;
+        case BPP_STUB_V: k_search<2><<<grid, block, 0, S(stream)>>>(e->P); break;
+        case BPP_STUB_H: k_search<3><<<grid, block, 0, S(stream)>>>(e->P); break;
+        case BPP_STUB_D: k_search<4><<<grid, block, 0, S(stream)>>>(e->P); break;
+        default: return set_err(BPP_E_INVALID, "unknown stub kind %d", stub_kind);
+    }
+    LAUNCH_CHECK(e);
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_root_counts(bpp_engine* e, int32_t* counts_out_dev, void* stream) {
+    if (!e || !counts_out_dev) return set_err(BPP_E_INVALID, "null argument");
+    k_root_counts<<<grid_warps(e->P.G), WARPS_PER_CTA * 32, 0, S(stream)>>>(e->P, counts_out_dev);
+    LAUNCH_CHECK(e);
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_root_counts_host(bpp_engine* e, int32_t* counts_out_host, void* stream) {
+    if (!e || !counts_out_host) return set_err(BPP_E_INVALID, "null argument");
+    const size_t n = (size_t)e->P.G * e->P.geom.A;
+    int32_t* d_counts = e->d_counts;
+    int rc = bpp_engine_root_counts(e, d_counts, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(counts_out_host, d_counts, n * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_choose(bpp_engine* e, int mode, uint64_t seed, int32_t* actions_out_dev, void* stream) {
+    if (!e || !actions_out_dev) return set_err(BPP_E_INVALID, "null argument");
+    if (mode < 0 || mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", mode);
+    k_choose<<<(e->P.G + 127) / 128, 128, 0, S(stream)>>>(e->P, mode, (unsigned long long)seed, actions_out_dev);
+    LAUNCH_CHECK(e);
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_advance(bpp_engine* e, const int32_t* actions_dev, void* stream) {
+    if (!e || !actions_dev) return set_err(BPP_E_INVALID, "null argument");
+    if (e->leaf_parked) return set_err(BPP_E_STATE, "leaves are parked; call bpp_engine_expand_backup first");
+    k_advance<<<grid_warps(e->P.G), WARPS_PER_CTA * 32, 0, S(stream)>>>(e->P, actions_dev);
+    LAUNCH_CHECK(e);
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_status(bpp_engine* e, int32_t* done_out_dev, int32_t* r_out_dev, double* score_out_dev,
+                                 int32_t* moves_out_dev, void* stream) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    const size_t G = (size_t)e->P.G;
+    if (done_out_dev)
+        CUDA_TRY(cudaMemcpyAsync(done_out_dev, e->P.status, G * sizeof(int), cudaMemcpyDeviceToDevice, S(stream)));
+    if (r_out_dev) CUDA_TRY(cudaMemcpyAsync(r_out_dev, e->P.ep_r, G * sizeof(int), cudaMemcpyDeviceToDevice, S(stream)));
+    if (score_out_dev)
+        CUDA_TRY(cudaMemcpyAsync(score_out_dev, e->P.ep_score, G * sizeof(double), cudaMemcpyDeviceToDevice, S(stream)));
+    if (moves_out_dev)
+        CUDA_TRY(cudaMemcpyAsync(moves_out_dev, e->P.moves_done, G * sizeof(int), cudaMemcpyDeviceToDevice, S(stream)));
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_roots(bpp_engine* e, uint32_t* roots_out_dev, void* stream) {
+    if (!e || !roots_out_dev) return set_err(BPP_E_INVALID, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(roots_out_dev, e->P.root_rec, (size_t)e->P.G * REC_WORDS * sizeof(uint32_t),
+                             cudaMemcpyDeviceToDevice, S(stream)));
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_play_stub(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed, int max_moves,
+                                    int32_t* counts_out_dev, int32_t* actions_out_dev, int32_t* moves_run_host,
+                                    void* stream) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    // every move places exactly one item, so an episode has at most N moves; finished games idle
+    const int moves = max_moves > 0 && max_moves < e->P.geom.N ? max_moves : e->P.geom.N;
+    const size_t GA = (size_t)e->P.G * e->P.geom.A;
+    for (int m = 0; m < moves; ++m) {
+        int rc;
+        if ((rc = bpp_engine_search_stub(e, stub_kind, stream))) return rc;
+        if (counts_out_dev && (rc = bpp_engine_root_counts(e, counts_out_dev + m * GA, stream))) return rc;
+        int32_t* act = actions_out_dev ? actions_out_dev + (size_t)m * e->P.G : e->d_actions;
+        if ((rc = bpp_engine_choose(e, choose_mode, seed, act, stream))) return rc;
+        if ((rc = bpp_engine_advance(e, act, stream))) return rc;
+    }
+    if (moves_run_host) *moves_run_host = moves;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_stats(bpp_engine* e, uint64_t stats_host[8], int reset, void* stream) {
+    if (!e || !stats_host) return set_err(BPP_E_INVALID, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(stats_host, e->P.stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    stats_host[6] = e->launches;
+    if (reset) {
+        CUDA_TRY(cudaMemsetAsync(e->P.stats, 0, 8 * sizeof(uint64_t), S(stream)));
+        e->launches = 0;
+    }
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_check(bpp_engine* e, void* stream) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    const size_t G = (size_t)e->P.G;
+    CUDA_TRY(cudaMemcpyAsync(e->h_status, e->P.status, G * sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    for (size_t g = 0; g < G; ++g) {
+        if (e->h_status[g] == -4)
+            return set_err(BPP_E_CAPACITY, "game %zu overflowed its node/edge pool (node_cap=%d, edge_cap=%lld units)", g,
+                           e->P.node_cap, e->P.edge_cap);
+        if (e->h_status[g] < 0)
+            return set_err(BPP_E_STATE, "game %zu is in error state %d (illegal action or engine not reset)", g,
+                           e->h_status[g]);
+    }
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_graph_sizes(bpp_engine* e, int32_t* nodes_out_dev, int32_t* units_out_dev, void* stream) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    const size_t G = (size_t)e->P.G;
+    if (nodes_out_dev)
+        CUDA_TRY(cudaMemcpyAsync(nodes_out_dev, e->P.n_nodes, G * sizeof(int), cudaMemcpyDeviceToDevice, S(stream)));
+    if (units_out_dev)
+        CUDA_TRY(cudaMemcpyAsync(units_out_dev, e->P.n_units, G * sizeof(int), cudaMemcpyDeviceToDevice, S(stream)));
+    return BPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// env C ABI
+static int env_args(int W, int H, int N, int n, const uint32_t* recs, const int32_t* items, EnvArgs* E) {
+    int rc = make_geom(W, H, N, &E->geom);
+    if (rc) return rc;
+    if (n < 0 || !recs || !items) return set_err(BPP_E_INVALID, "bad env arguments");
+    E->n = n;
+    E->recs = recs;
+    E->items_wh = items;
+    return BPP_OK;
+}
+#define ENV_LAUNCH_CHECK()                                                                                     \
+    do {                                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                                   \
+        if (_e != cudaSuccess) return set_err(BPP_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" int bpp_env_valid_moves(int W, int H, int N, int n, const uint32_t* recs_dev, const int32_t* items_wh_dev,
+                                   uint8_t* valid_out_dev, void* stream) {
+    EnvArgs E;
+    int rc = env_args(W, H, N, n, recs_dev, items_wh_dev, &E);
+    if (rc) return rc;
+    if (!valid_out_dev) return set_err(BPP_E_INVALID, "null output");
+    if (n == 0) return BPP_OK;
+    k_env_valid<<<grid_warps(n), WARPS_PER_CTA * 32, 0, S(stream)>>>(E, valid_out_dev);
+    ENV_LAUNCH_CHECK();
+    return BPP_OK;
+}
+
+extern "C" int bpp_env_next_state(int W, int H, int N, int n, const uint32_t* recs_dev, const int32_t* items_wh_dev,
+                                  const int32_t* actions_dev, uint32_t* recs_out_dev, void* stream) {
+    EnvArgs E;
+    int rc = env_args(W, H, N, n, recs_dev, items_wh_dev, &E);
+    if (rc) return rc;
+    if (!actions_dev || !recs_out_dev) return set_err(BPP_E_INVALID, "null argument");
+    if (n == 0) return BPP_OK;
+    k_env_next<<<grid_warps(n), WARPS_PER_CTA * 32, 0, S(stream)>>>(E, actions_dev, recs_out_dev);
+    ENV_LAUNCH_CHECK();
+    return BPP_OK;
+}
+
+extern "C" int bpp_env_game_ended(int W, int H, int N, int n, const uint32_t* recs_dev, const int32_t* items_wh_dev,
+                                  const int32_t* total_area_dev, const int32_t* max_h_dev, const double* bl_dev,
+                                  const int8_t* tie_dev, int32_t* ended_out_dev, double* score_out_dev, void* stream) {
+    EnvArgs E;
+    int rc = env_args(W, H, N, n, recs_dev, items_wh_dev, &E);
+    if (rc) return rc;
+    if (!total_area_dev || !max_h_dev || !bl_dev || !ended_out_dev || !score_out_dev)
+        return set_err(BPP_E_INVALID, "null argument");
+    if (n == 0) return BPP_OK;
+    k_env_ended<<<grid_warps(n), WARPS_PER_CTA * 32, 0, S(stream)>>>(E, total_area_dev, max_h_dev, bl_dev, tie_dev,
+                                                                    ended_out_dev, score_out_dev);
+    ENV_LAUNCH_CHECK();
+    return BPP_OK;
+}

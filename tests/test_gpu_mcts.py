@@ -1,0 +1,114 @@
+"""-m gpu: per-move MCTS visit counts of the CUDA engine, bit-exact against fixtures produced by the unmodified
+reference (MCTS_bpp.py) under the deterministic stub evaluators."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import bl_of, load_mcts_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_mcts_golden()
+
+
+def _items_wh(case):
+    return np.array([[it[0], it[1]] for it in case["items"]], dtype=np.int32)
+
+
+def _torch_stub(kind, A):
+    """the stub evaluators of tests/golden/make_golden.py on a batch of dense planes (float64 on the device)"""
+    def ev(planes):
+        pop = planes[:, 0].sum(dim=(1, 2)).to(torch.int64)
+        nrem = (planes[:, 1:].sum(dim=(2, 3)) > 0).sum(dim=1).to(torch.int64)
+        B = planes.shape[0]
+        a = torch.arange(A, device=planes.device, dtype=torch.float64)[None, :]
+        v = ((7 * pop + 3 * nrem) % 16).to(torch.float64) / 16 - 0.5
+        if kind == "U":
+            return torch.full((B, A), 1 / A, dtype=torch.float64, device=planes.device), torch.zeros_like(v)
+        if kind == "V":
+            return torch.full((B, A), 1 / A, dtype=torch.float64, device=planes.device), v
+        if kind == "H":
+            return 1.0 / (a + 3 + (pop % 5)[:, None].to(torch.float64)), v
+        ai = torch.arange(A, device=planes.device, dtype=torch.int64)[None, :]
+        return ((37 * ai + 11 + pop[:, None]) % 64 + 1).to(torch.float64) / 4096.0, v
+    return ev
+
+
+def _play(case, mode, G=3):
+    from resource_packing_self_play_b200.engine import SearchEngine
+    W, H, N, A = case["W"], case["H"], case["N"], case["W"] * case["N"]
+    eng = SearchEngine(W, H, N, G, case["sims"], case["cpuct"])
+    items = np.repeat(_items_wh(case)[None], G, axis=0)
+    area = np.full(G, case["genW"] * case["genH"], dtype=np.int32)
+    bl = np.full(G, bl_of(case["rewards"], case["alpha"]))
+    eng.reset(items, area, bl)
+    counts_all = []
+    for mv, a_ref in enumerate(case["actions"]):
+        eng.begin_move()
+        if mode == "fused":
+            eng.search_stub(case["stub"])
+        else:
+            eng.search_with(_torch_stub(case["stub"], A))
+        counts = eng.root_counts().cpu().numpy()
+        counts_all.append(counts)
+        if case["policy"] == "argmax":
+            chosen = eng.choose(0).cpu().numpy()
+            assert (chosen == a_ref).all(), (mv, chosen, a_ref)
+        eng.advance(np.full(G, a_ref, dtype=np.int32))
+    eng.check()
+    st = eng.status()
+    return np.stack(counts_all, axis=1), {k: v.cpu().numpy() for k, v in st.items()}, eng
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_fused_stub_visit_counts_bit_exact(ci):
+    case = CASES[ci]
+    counts, st, eng = _play(case, "fused")
+    want = np.array(case["counts"], dtype=np.int64)
+    for g in range(counts.shape[0]):
+        assert np.array_equal(counts[g], want), f"case {ci} game {g}: visit counts differ"
+    assert (st["done"] == 1).all()
+    assert (st["r"] == case["r"]).all()
+    assert (st["score"] == case["score"]).all()
+    assert (st["moves"] == len(case["actions"])).all()
+    nodes, _ = eng.graph_sizes()
+    # every dict entry of the reference (Es) is a node here; real moves may add the played-to state as well
+    n_ref = case["n_expanded"] + case["n_terminal"]
+    assert ((nodes.cpu().numpy() >= n_ref) & (nodes.cpu().numpy() <= n_ref + len(case["actions"]))).all()
+
+
+@pytest.mark.parametrize("ci", [0, 3, 6, 7, 8, 9, 11, 12, 15, 16, 17, 18])
+def test_lockstep_external_evaluator_visit_counts_bit_exact(ci):
+    case = CASES[ci]
+    counts, st, _ = _play(case, "lockstep", G=2)
+    want = np.array(case["counts"], dtype=np.int64)
+    for g in range(counts.shape[0]):
+        assert np.array_equal(counts[g], want), f"case {ci} game {g}: visit counts differ"
+    assert (st["r"] == case["r"]).all() and (st["score"] == case["score"]).all()
+
+
+def test_many_games_mixed_instances_match_single_game_runs():
+    """4 different instances interleaved in one engine give the same counts as their fixtures."""
+    from resource_packing_self_play_b200.engine import SearchEngine
+    sel = [c for c in CASES if (c["W"], c["H"], c["N"], c["sims"], c["cpuct"], c["stub"], c["policy"]) ==
+           (15, 15, 10, 200, 1, "V", "argmax") and not c["rewards"]]
+    assert len(sel) >= 4
+    G = len(sel) * 5
+    order = [i % len(sel) for i in range(G)]
+    eng = SearchEngine(15, 15, 10, G, 200, 1.0)
+    items = np.stack([np.array([[it[0], it[1]] for it in sel[k]["items"]], dtype=np.int32) for k in order])
+    area = np.array([sel[k]["genW"] * sel[k]["genH"] for k in order], dtype=np.int32)
+    eng.reset(items, area, np.full(G, np.nan))
+    counts, actions = eng.play_stub("V", 0)
+    eng.check()
+    counts, actions = counts.cpu().numpy(), actions.cpu().numpy()
+    for g, k in enumerate(order):
+        want = np.array(sel[k]["counts"])
+        nm = want.shape[0]
+        assert np.array_equal(counts[:nm, g], want)
+        assert list(actions[:nm, g]) == sel[k]["actions"]
+        assert (actions[nm:, g] == -1).all()
+    st = eng.status()
+    assert (st["done"].cpu().numpy() == 1).all()
+    s = eng.stats()
+    assert s["sims"] == sum(200 * len(sel[k]["actions"]) for k in order)
