@@ -1039,7 +1039,7 @@ extern "C" int bpp_engine_graph_sizes(bpp_engine* e, int32_t* nodes_out_dev, int
 static int env_args(int W, int H, int N, int n, const uint32_t* recs, const int32_t* items, EnvArgs* E) {
     int rc = make_geom(W, H, N, &E->geom);
     if (rc) return rc;
-    if (n < 0 || !recs || !items) return set_err(BPP_E_INVALID, "bad env arguments");
+    if (n < 0 || (n > 0 && (!recs || !items))) return set_err(BPP_E_INVALID, "bad env arguments");
     E->n = n;
     E->recs = recs;
     E->items_wh = items;
@@ -1056,8 +1056,8 @@ extern "C" int bpp_env_valid_moves(int W, int H, int N, int n, const uint32_t* r
     EnvArgs E;
     int rc = env_args(W, H, N, n, recs_dev, items_wh_dev, &E);
     if (rc) return rc;
-    if (!valid_out_dev) return set_err(BPP_E_INVALID, "null output");
     if (n == 0) return BPP_OK;
+    if (!valid_out_dev) return set_err(BPP_E_INVALID, "null output");
     k_env_valid<<<grid_warps(n), WARPS_PER_CTA * 32, 0, S(stream)>>>(E, valid_out_dev);
     ENV_LAUNCH_CHECK();
     return BPP_OK;
@@ -1068,8 +1068,8 @@ extern "C" int bpp_env_next_state(int W, int H, int N, int n, const uint32_t* re
     EnvArgs E;
     int rc = env_args(W, H, N, n, recs_dev, items_wh_dev, &E);
     if (rc) return rc;
-    if (!actions_dev || !recs_out_dev) return set_err(BPP_E_INVALID, "null argument");
     if (n == 0) return BPP_OK;
+    if (!actions_dev || !recs_out_dev) return set_err(BPP_E_INVALID, "null argument");
     k_env_next<<<grid_warps(n), WARPS_PER_CTA * 32, 0, S(stream)>>>(E, actions_dev, recs_out_dev);
     ENV_LAUNCH_CHECK();
     return BPP_OK;
@@ -1082,7 +1082,7 @@ extern "C" int bpp_env_game_ended(int W, int H, int N, int n, const uint32_t* re
     int rc = env_args(W, H, N, n, recs_dev, items_wh_dev, &E);
     if (rc) return rc;
     if (!total_area_dev || !max_h_dev || !bl_dev || !ended_out_dev || !score_out_dev)
-        return set_err(BPP_E_INVALID, "null argument");
+        return n == 0 ? BPP_OK : set_err(BPP_E_INVALID, "null argument");
     if (n == 0) return BPP_OK;
     k_env_ended<<<grid_warps(n), WARPS_PER_CTA * 32, 0, S(stream)>>>(E, total_area_dev, max_h_dev, bl_dev, tie_dev,
                                                                     ended_out_dev, score_out_dev);
