@@ -171,6 +171,16 @@ int bpp_engine_roots(bpp_engine *e, uint32_t *roots_out_dev, void *stream);
 int bpp_engine_play_stub(bpp_engine *e, int stub_kind, int choose_mode, uint64_t seed, int max_moves,
                          int32_t *counts_out_dev, int32_t *actions_out_dev, int32_t *moves_run_host, void *stream);
 
+/* The reference-facing batched "executeEpisode" with HOST buffers (CoachBPP.py:50-99 for G games at once): uploads the
+ * instances, resets, plays whole episodes with the in-kernel stub evaluator, downloads the results and synchronises.
+ * counts_out_host int32 [N][G][A] (rows of moves a game did not play stay 0), actions_out_host int32 [N][G] (-1 when
+ * the game had already ended), r_out_host int32 [G], score_out_host float64 [G], moves_out_host int32 [G]; any output
+ * may be NULL.  Fails with BPP_E_CAPACITY if a game overflowed its pools. */
+int bpp_engine_play_stub_host(bpp_engine *e, int stub_kind, int choose_mode, uint64_t seed,
+                              const int32_t *items_wh_host, const int32_t *total_area_host, const double *bl_host,
+                              const int8_t *tie_host, int32_t *counts_out_host, int32_t *actions_out_host,
+                              int32_t *r_out_host, double *score_out_host, int32_t *moves_out_host, void *stream);
+
 /* Counters since creation (or the last bpp_engine_stats with reset != 0), copied to the host (synchronises):
  * [0] simulations, [1] edges traversed, [2] expansions, [3] terminal hits, [4] nodes created, [5] hash probes,
  * [6] kernels launched by this handle, [7] reserved. */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "bpp_engine_status": [_vp, _vp, _vp, _vp, _vp, _vp],
     "bpp_engine_roots": [_vp, _vp, _vp],
     "bpp_engine_play_stub": [_vp, _i32, _i32, _u64, _i32, _vp, _vp, C.POINTER(_i32), _vp],
+    "bpp_engine_play_stub_host": [_vp, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "bpp_engine_stats": [_vp, C.POINTER(_u64), _i32, _vp],
     "bpp_engine_check": [_vp, _vp],
     "bpp_engine_graph_sizes": [_vp, _vp, _vp, _vp],

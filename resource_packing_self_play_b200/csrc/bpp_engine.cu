@@ -695,6 +695,8 @@ struct bpp_engine {
     double* d_bl = nullptr;
     int8_t* d_tie = nullptr;
     int32_t* d_counts = nullptr;
+    int32_t* d_counts_all = nullptr;   // [N][G][A], lazily allocated by play_stub_host
+    int32_t* d_actions_all = nullptr;  // [N][G]
     int* h_status = nullptr;
 };
 
@@ -994,6 +996,40 @@ extern "C" int bpp_engine_play_stub(bpp_engine* e, int stub_kind, int choose_mod
     }
     if (moves_run_host) *moves_run_host = moves;
     return BPP_OK;
+}
+
+extern "C" int bpp_engine_play_stub_host(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed,
+                                         const int32_t* items_wh_host, const int32_t* total_area_host,
+                                         const double* bl_host, const int8_t* tie_host, int32_t* counts_out_host,
+                                         int32_t* actions_out_host, int32_t* r_out_host, double* score_out_host,
+                                         int32_t* moves_out_host, void* stream) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    const size_t G = (size_t)e->P.G, A = (size_t)e->P.geom.A, N = (size_t)e->P.geom.N;
+    int rc;
+    if (counts_out_host && !e->d_counts_all) {
+        if ((rc = dev_alloc(e, &e->d_counts_all, N * G * A))) return rc;
+    }
+    if (!e->d_actions_all && (rc = dev_alloc(e, &e->d_actions_all, N * G))) return rc;
+    if ((rc = bpp_engine_reset_host(e, items_wh_host, total_area_host, bl_host, tie_host, stream))) return rc;
+    CUDA_TRY(cudaMemsetAsync(e->d_actions_all, 0xff, N * G * sizeof(int32_t), S(stream)));
+    if (counts_out_host) CUDA_TRY(cudaMemsetAsync(e->d_counts_all, 0, N * G * A * sizeof(int32_t), S(stream)));
+    if ((rc = bpp_engine_play_stub(e, stub_kind, choose_mode, seed, 0, counts_out_host ? e->d_counts_all : nullptr,
+                                   e->d_actions_all, nullptr, stream)))
+        return rc;
+    if (counts_out_host)
+        CUDA_TRY(cudaMemcpyAsync(counts_out_host, e->d_counts_all, N * G * A * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 S(stream)));
+    if (actions_out_host)
+        CUDA_TRY(cudaMemcpyAsync(actions_out_host, e->d_actions_all, N * G * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 S(stream)));
+    if (r_out_host)
+        CUDA_TRY(cudaMemcpyAsync(r_out_host, e->P.ep_r, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    if (score_out_host)
+        CUDA_TRY(cudaMemcpyAsync(score_out_host, e->P.ep_score, G * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
+    if (moves_out_host)
+        CUDA_TRY(cudaMemcpyAsync(moves_out_host, e->P.moves_done, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    return bpp_engine_check(e, stream);
 }
 
 extern "C" int bpp_engine_stats(bpp_engine* e, uint64_t stats_host[8], int reset, void* stream) {

@@ -251,6 +251,26 @@ class SearchEngine:
              C.c_uint64(seed), 0, _ptr(counts), _ptr(actions), C.byref(moves), _stream())
         return counts, actions
 
+    def play_stub_host(self, kind, items_wh, total_area, bl, choose_mode=_lib.CHOOSE_ARGMAX_FIRST, seed=0, out=None):
+        """HOST-buffer episode batch through the C ABI (uploads, plays, downloads, synchronises).
+        `out` may hold preallocated (ideally pinned) numpy arrays: counts (N,G,A) i32, actions (N,G) i32,
+        r (G,) i32, score (G,) f64, moves (G,) i32."""
+        items = np.ascontiguousarray(items_wh, dtype=np.int32)
+        area = np.ascontiguousarray(total_area, dtype=np.int32)
+        blh = np.ascontiguousarray(bl, dtype=np.float64)
+        if out is None:
+            out = {}
+        out.setdefault("counts", np.empty((self.N, self.G, self.A), dtype=np.int32))
+        out.setdefault("actions", np.empty((self.N, self.G), dtype=np.int32))
+        out.setdefault("r", np.empty(self.G, dtype=np.int32))
+        out.setdefault("score", np.empty(self.G, dtype=np.float64))
+        out.setdefault("moves", np.empty(self.G, dtype=np.int32))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        call("bpp_engine_play_stub_host", self._h, STUB[kind] if isinstance(kind, str) else int(kind), int(choose_mode),
+             C.c_uint64(seed), vp(items), vp(area), vp(blh), C.c_void_p(0), vp(out["counts"]), vp(out["actions"]),
+             vp(out["r"]), vp(out["score"]), vp(out["moves"]), _stream())
+        return out
+
     # -- results ------------------------------------------------------------------------------------------------------
     def root_counts(self):
         out = torch.empty((self.G, self.A), dtype=torch.int32, device=self.device)
