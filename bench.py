@@ -169,7 +169,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -222,7 +222,11 @@ def run_gpu_arm(args):
         first = ((k * world) + rank) * G
         seeds, heights, areas = workload(first, G)
         inst.append((gen.items_batch(seeds, heights), areas))
-    eng = SearchEngine(W, H, N, G, args.sims, CPUCT, device=local)
+    edge_cap = 0
+    if args.edge_frac < 1.0:  # profiling runs: a smaller edge pool keeps ncu's save/restore cheap
+        worst_units_per_node = 3 * ((W * N + 3) // 4 * 4) + ((W * N + 3) // 4 * 4) // 4
+        edge_cap = int((args.sims * N + N + 2) * worst_units_per_node * args.edge_frac)
+    eng = SearchEngine(W, H, N, G, args.sims, CPUCT, device=local, edge_cap=edge_cap)
     nan_bl = np.full(G, np.nan)
     bl_dev = torch.from_numpy(nan_bl).to(dev)
     counts_buf = torch.zeros((N, G, W * N), dtype=torch.int32, device=dev)
@@ -273,6 +277,9 @@ def run_gpu_arm(args):
     st = eng.stats(reset=True)
     done = eng.status()["done"]
     assert bool((done == 1).all()), "some games did not finish their episode"
+    g_nodes, g_units = eng.graph_sizes()
+    graph = {"max_nodes_per_game": int(g_nodes.max()), "max_edge_units_per_game": int(g_units.max()),
+             "mean_edge_units_per_game": float(g_units.double().mean()), "engine_device_bytes": eng.device_bytes}
     search_ms = sum(a.elapsed_time(b) for a, b in search_events)
     n_search = len(search_events)
 
@@ -349,7 +356,7 @@ def run_gpu_arm(args):
                          "kernel_share_of_step": search_ms / (ms if world == 1 else search_ms_max or ms),
                          "note": "latency/issue-bound pointer chasing: one warp per game, strictly sequential "
                                  "simulations; see DESIGN.md"},
-            "clocks": clocks,
+            "clocks": clocks, "graph": graph,
         }
         if world == 1 and not args.no_cpu:
             v, eps, dt = cpu_single_core(args.cpu_seconds, args.sims)
@@ -364,13 +371,14 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--sims", type=int, default=SIMS)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--edge-frac", type=float, default=1.0, help="edge pool as a fraction of the worst case")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -122,6 +122,16 @@ int bpp_engine_reset_host(bpp_engine *e, const int32_t *items_wh_host, const int
  * state).  roots_dev: uint32 [G][32] records.  Keeps the search graph. */
 int bpp_engine_set_roots(bpp_engine *e, const uint32_t *roots_dev, void *stream);
 
+/* Override max_h, the hidden state BinPackingGame.getInitItems leaves on the Game object (BinPackingGame.py:48-50) and
+ * getRankedReward reads (:198); needed when a search starts from a mid-episode state whose placed items' dims are no
+ * longer in the state tensor.  max_h_dev: int32 [G].  Call after bpp_engine_reset. */
+int bpp_engine_set_max_h(bpp_engine *e, const int32_t *max_h_dev, void *stream);
+/* Change the per-move simulation budget (args.numMCTSSims); MCTS.search() is one simulation: budget 1. */
+int bpp_engine_set_num_sims(bpp_engine *e, int num_sims);
+/* v returned by the most recent simulation of each game (the return value of MCTS.search, MCTS_bpp.py:83,104,139).
+ * values_out_dev: float64 [G]. */
+int bpp_engine_last_values(bpp_engine *e, double *values_out_dev, void *stream);
+
 /* Begin a getActionProb call: zero the per-move simulation counters (MCTS_bpp.py:37). */
 int bpp_engine_begin_move(bpp_engine *e, void *stream);
 

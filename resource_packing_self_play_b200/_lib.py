@@ -45,6 +45,9 @@ SIGNATURES = {
     "bpp_engine_reset_host": [_vp, _vp, _vp, _vp, _vp, _vp],
     "bpp_engine_set_roots": [_vp, _vp, _vp],
     "bpp_engine_begin_move": [_vp, _vp],
+    "bpp_engine_set_max_h": [_vp, _vp, _vp],
+    "bpp_engine_set_num_sims": [_vp, _i32],
+    "bpp_engine_last_values": [_vp, _vp, _vp],
     "bpp_engine_select": [_vp, _vp],
     "bpp_engine_leaf_count": [_vp, C.POINTER(_i32), _vp],
     "bpp_engine_leaf_buffers": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],

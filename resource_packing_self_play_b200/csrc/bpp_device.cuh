@@ -30,21 +30,25 @@ constexpr int KIND_TPOS = 2;  // terminal, Es = +1
 constexpr int KIND_TNEG = 3;  // terminal, Es = -1
 constexpr int MAX_AW = 16;    // valid-mask words (A <= 512)
 constexpr int MAX_LEAVES = 16;
-constexpr int MAX_PROG = 32;
 
-// numpy pairwise-sum plan for a length-A float64 reduction (host-built, see build_sum_plan in bpp_engine.cu)
+// numpy pairwise-sum plan for a length-A float64 reduction (host-built, see build_sum_plan_rec in bpp_engine.cu):
+// leaf blocks of <= 128 elements, then the recursion's additions as in-place pair operations s[dst] += s[src]
+// executed in order; the total ends in s[0].
 struct SumPlan {
     int n_leaves;
-    int prog_len;
+    int n_ops;
     short leaf_base[MAX_LEAVES];
     short leaf_n[MAX_LEAVES];
-    signed char prog[MAX_PROG];  // postfix: >= 0 push leaf, -1 add the two on top (left + right)
+    signed char op_dst[MAX_LEAVES];
+    signed char op_src[MAX_LEAVES];
 };
 
 struct Geom {
     int W, H, N, A, AW;
     unsigned wmask;  // low W bits
+    unsigned invW;   // ceil(2^16 / W): a / W == (a * invW) >> 16 for 0 <= a < 512 (W <= 32)
 };
+__device__ __forceinline__ int div_w(const Geom& g, int a) { return (int)(((unsigned)a * g.invW) >> 16); }
 
 __device__ __forceinline__ bool state_lane(int lane, int H) { return lane < H || lane == REC_REM; }
 
@@ -67,20 +71,26 @@ __device__ __forceinline__ uint32_t strip_mask(int w, int x, unsigned wmask) {
 // ---------------------------------------------------------------------------------------------------------------------
 // Valid-move mask.  s_occ[0..H) = occupancy rows (shared, this warp's strip), s_items[i] = w | h << 8.
 // Action a = item*W + x is handled by lane a % 32 in round a / 32; the ballot of a round IS word a/32 of the mask.
-// Returns word k in lane k (0 elsewhere); also stores the words to s_vw[0..AW).
+// (The row loop carries no cross-lane dependency and its shared-memory reads are loop-invariant addresses, so the
+// per-warp latency - which bounds this kernel at ~7 warps per scheduler - stays short; an item-major variant with
+// prefix sums and early-exit votes executed fewer instructions but ran 10 % slower.)
+//   (A) cell-count test (BinPackingLogic.py:89): occupied cells of the strip [:, x:x+w] <= w*(H-h);
+//   (B) left adjacency (BinPackingLogic.py:63-70): x == 0, or the cell left of the strip is occupied in the first strip
+//       row that is completely empty (row H-1 if none: the reference's loop variable keeps its last value).
+// Returns word k in lane k (0 elsewhere); also stores the words to s_vw[0..MAX_AW).
 __device__ __forceinline__ uint32_t valid_words(const Geom& g, const uint32_t* s_occ, const uint16_t* s_items,
                                                 uint32_t rem, int lane, uint32_t* s_vw) {
     uint32_t mine = 0;
     for (int k = 0; k < g.AW; ++k) {
         const int a0 = k * 32;
-        const int i0 = a0 / g.W;
-        int i1 = (a0 + 31) / g.W;
+        const int i0 = div_w(g, a0);
+        int i1 = div_w(g, a0 + 31);
         if (i1 > g.N - 1) i1 = g.N - 1;
         const uint32_t range = ((2u << i1) - 1u) & ~((1u << i0) - 1u);
         uint32_t b = 0;
         if (rem & range) {  // warp-uniform: skip rounds whose items are all placed
             const int a = a0 + lane;
-            const int i = a / g.W;
+            const int i = div_w(g, a);
             const int x = a - i * g.W;
             bool ok = false;
             if (a < g.A && ((rem >> i) & 1u)) {
@@ -93,8 +103,7 @@ __device__ __forceinline__ uint32_t valid_words(const Geom& g, const uint32_t* s
                         cnt += __popc(c);
                         if (c == 0 && t < 0) t = r;
                     }
-                    if (t < 0) t = g.H - 1;  // BinPackingLogic.py:66-68: the loop variable keeps its last value
-                    // (A) cell-count test, BinPackingLogic.py:89 ; (B) left adjacency, :63-70
+                    if (t < 0) t = g.H - 1;
                     ok = (cnt <= w * (g.H - h)) && (x == 0 || ((s_occ[t] >> (x - 1)) & 1u));
                 }
             }
@@ -148,52 +157,60 @@ __device__ __forceinline__ int terminal_value(const Geom& g, const RewardCtx& rc
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// numpy float64 pairwise add-reduction over f(0..A), bit-exact: blocks of <= 128 elements use 8 interleaved
-// accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then a sequential tail; longer inputs split
-// recursively at n/2 rounded down to a multiple of 8.  Each 8-lane group of the warp evaluates one block.
-// scratch: >= MAX_LEAVES doubles of this warp's shared memory.  Result is warp-uniform.
+// numpy float64 pairwise add-reduction (np.sum) of the dense length-A vector whose entry a is f(a) where bit a of the
+// valid mask vw is set and 0.0 elsewhere, bit-exact: blocks of <= 128 elements use 8 interleaved accumulators
+// (accumulator j takes positions j, j+8, ...) combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then a sequential tail;
+// longer inputs split recursively at n/2 rounded down to a multiple of 8 (the SumPlan).  Adding +0.0 never changes a
+// partial sum, so only the VALID positions are visited (in the same ascending order).  Each 8-lane group of the warp
+// evaluates one block.  scratch: >= MAX_LEAVES doubles of this warp's shared memory.  Result is warp-uniform.
 template <typename F>
-__device__ __forceinline__ double np_pairwise_sum(const SumPlan& plan, F f, int lane, double* scratch) {
+__device__ __forceinline__ double np_masked_sum(const SumPlan& plan, const uint32_t* vw, F f, int lane,
+                                                double* scratch) {
     const int j = lane & 7;
+#pragma unroll 1
     for (int pass = 0; pass * 4 < plan.n_leaves; ++pass) {
         const int li = pass * 4 + (lane >> 3);
         const bool act = li < plan.n_leaves;
-        const int base = act ? plan.leaf_base[li] : 0;
+        const int base = act ? plan.leaf_base[li] : 0;  // multiple of 8
         const int n = act ? plan.leaf_n[li] : 0;
-        const int lim = n - (n & 7);
+        const int lim = n >= 8 ? n - (n & 7) : 0;
         double r = 0.0;
-        if (n >= 8) {
-            r = f(base + j);
-            for (int i = 8; i < lim; i += 8) r = __dadd_rn(r, f(base + i + j));
+        if (lim > 0) {
+            const int pend = base + lim;
+            const uint32_t sel = 0x01010101u << j;  // positions == j (mod 8)
+#pragma unroll 1
+            for (int k = base >> 5; k <= (pend - 1) >> 5; ++k) {
+                const int lo = k << 5;
+                uint32_t m = vw[k] & sel;
+                if (lo < base) m &= 0xffffffffu << (base - lo);
+                if (pend - lo < 32) m &= (1u << (pend - lo)) - 1u;
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1u;
+                    r = __dadd_rn(r, f(lo + bit));
+                }
+            }
         }
         double t = __dadd_rn(r, __shfl_xor_sync(FULL, r, 1));
         t = __dadd_rn(t, __shfl_xor_sync(FULL, t, 2));
         t = __dadd_rn(t, __shfl_xor_sync(FULL, t, 4));
-        double res;
-        if (n >= 8) {
-            res = t;
-            for (int i = lim; i < n; ++i) res = __dadd_rn(res, f(base + i));
-        } else {
-            res = 0.0;
-            for (int i = 0; i < n; ++i) res = __dadd_rn(res, f(base + i));
-        }
+        double res = lim > 0 ? t : 0.0;
+#pragma unroll 1
+        for (int a = base + lim; a < base + n; ++a)  // sequential tail (< 8 positions)
+            if ((vw[a >> 5] >> (a & 31)) & 1u) res = __dadd_rn(res, f(a));
         if (act && j == 0) scratch[li] = res;
     }
     __syncwarp();
-    double st[8];
-    int sp = 0;
-    for (int t = 0; t < plan.prog_len; ++t) {
-        const int op = plan.prog[t];
-        if (op >= 0) {
-            st[sp++] = scratch[op];
-        } else {
-            const double b = st[--sp];
-            const double a = st[--sp];
-            st[sp++] = __dadd_rn(a, b);
-        }
+    if (plan.n_ops > 0) {
+        if (lane == 0)
+#pragma unroll 1
+            for (int t = 0; t < plan.n_ops; ++t)
+                scratch[plan.op_dst[t]] = __dadd_rn(scratch[plan.op_dst[t]], scratch[plan.op_src[t]]);
+        __syncwarp();
     }
+    const double total = scratch[0];
     __syncwarp();
-    return st[0];
+    return total;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -221,21 +238,37 @@ __host__ __device__ __forceinline__ int edge_units(int nv) {
 // PUCT arg-max with the reference's exact operation order and first-max tie-break (ascending action == ascending
 // edge index).  u = Q + ((cpuct*P)*sqrt(Ns)) / (1+Nsa) for visited edges, (cpuct*P)*sqrt(Ns+1e-8) otherwise.
 __device__ __forceinline__ int puct_select(const EdgeBlock& eb, int nv, int Ns, double cpuct, int lane) {
-    const double sq = __dsqrt_rn((double)Ns);
-    const double sqe = __dsqrt_rn(__dadd_rn((double)Ns, 1e-8));
     double bu = __longlong_as_double((long long)0xfff0000000000000ull);  // -inf
     int be = 0x7fffffff;
-    for (int e = lane; e < nv; e += 32) {
+    // first round from registers: issue all loads, then decide which square root is needed (the root has every edge
+    // visited, a fresh node none), then the arithmetic
+    const bool in0 = lane < nv;
+    const double q0 = in0 ? eb.Q[lane] : 0.0;
+    const double p0 = in0 ? eb.P[lane] : 0.0;
+    const int n0 = in0 ? eb.NC[lane].x : 0;
+    bool need_sq = in0 && n0 > 0, need_sqe = in0 && n0 <= 0;
+#pragma unroll 1
+    for (int e = lane + 32; e < nv; e += 32) {
+        const int n = eb.NC[e].x;
+        need_sq |= n > 0;
+        need_sqe |= n <= 0;
+    }
+    const double sq = __any_sync(FULL, need_sq) ? __dsqrt_rn((double)Ns) : 0.0;
+    const double sqe = __any_sync(FULL, need_sqe) ? __dsqrt_rn(__dadd_rn((double)Ns, 1e-8)) : 0.0;
+    if (in0) {
+        const double cp = __dmul_rn(cpuct, p0);
+        double u = n0 > 0 ? __dadd_rn(q0, __ddiv_rn(__dmul_rn(cp, sq), (double)(1 + n0))) : __dmul_rn(cp, sqe);
+        bu = __dadd_rn(u, 0.0);  // canonicalise -0.0 (Python's `>` treats it as equal to +0.0)
+        be = lane;
+    }
+#pragma unroll 1
+    for (int e = lane + 32; e < nv; e += 32) {
         const double q = eb.Q[e];
         const double p = eb.P[e];
         const int n = eb.NC[e].x;
         const double cp = __dmul_rn(cpuct, p);
-        double u;
-        if (n > 0)
-            u = __dadd_rn(q, __ddiv_rn(__dmul_rn(cp, sq), (double)(1 + n)));
-        else
-            u = __dmul_rn(cp, sqe);
-        u = __dadd_rn(u, 0.0);  // canonicalise -0.0 (Python's `>` treats it as equal to +0.0)
+        double u = n > 0 ? __dadd_rn(q, __ddiv_rn(__dmul_rn(cp, sq), (double)(1 + n))) : __dmul_rn(cp, sqe);
+        u = __dadd_rn(u, 0.0);
         if (u > bu) { bu = u; be = e; }
     }
     // order-preserving map double -> uint64, then two 32-bit REDUX max + one REDUX min on the edge index

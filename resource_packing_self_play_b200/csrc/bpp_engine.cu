@@ -39,6 +39,7 @@ static int set_err(int code, const char* fmt, ...) {
     return code;
 }
 extern "C" const char* bpp_last_error(void) { return g_err; }
+int bpp_set_error_message(int code, const char* msg) { return set_err(code, "%s", msg); }  // used by bpp_net.cu
 extern "C" int bpp_version(void) { return 100; }
 
 #define CUDA_TRY(expr)                                                                                   \
@@ -74,6 +75,7 @@ struct Params {
     int* status;         // [G] 0 running, 1 episode ended, <0 error
     int* ep_r;           // [G]
     double* ep_score;    // [G]
+    double* last_v;      // [G] value backed up by the most recent simulation (return value of MCTS.search)
     // parked leaves (lockstep)
     int* pend_depth;         // [G] -1 = none
     int* pend_leaf;          // [G]
@@ -146,7 +148,7 @@ __device__ __forceinline__ void flush_stats(const Params& P, const Stats& st, in
 }
 
 // Find the node of a state (full-key equality, like the dict lookup of MCTS_bpp.py:76-85) or create it.
-__device__ __forceinline__ int lookup_or_insert(const Params& P, GameCtx& gm, uint32_t rec, int lane, Stats& st) {
+__device__ __noinline__ int lookup_or_insert(const Params& P, GameCtx& gm, uint32_t rec, int lane, Stats& st) {
     const int H = P.geom.H;
     const uint32_t h = hash_state(rec, lane, H);
     const uint32_t tag = h >> 20;
@@ -191,13 +193,16 @@ __device__ __forceinline__ bool expand_node(const Params& P, GameCtx& gm, WarpSm
     gm.n_units += units;
     EdgeBlock eb(gm.edges + off, nvp);
     const uint32_t* vw = sm.vw;
-    auto masked = [&](int a) -> double { return ((vw[a >> 5] >> (a & 31)) & 1u) ? prior(a) : 0.0; };
-    const double tot = np_pairwise_sum(P.plan, masked, lane, sm.scratch);
-    const bool fallback = !(tot > 0.0);
-    double tot2 = 1.0;
-    if (fallback) {  // "all valid moves were masked": Ps <- Ps + valids, renormalise (MCTS_bpp.py:93-100)
-        auto bumped = [&](int a) -> double { return ((vw[a >> 5] >> (a & 31)) & 1u) ? __dadd_rn(prior(a), 1.0) : 0.0; };
-        tot2 = np_pairwise_sum(P.plan, bumped, lane, sm.scratch);
+    // sum of the masked prior; if it is not positive ("all valid moves were masked", MCTS_bpp.py:93-100) the prior
+    // becomes Ps + valids, i.e. every valid entry is bumped by 1.0, and is renormalised by its own sum.
+    // (p + 0.0 == p, so one code path serves both.)
+    double bump = 0.0, tot;
+#pragma unroll 1
+    for (;;) {
+        auto term = [&](int a) -> double { return __dadd_rn(prior(a), bump); };
+        tot = np_masked_sum(P.plan, vw, term, lane, sm.scratch);
+        if (tot > 0.0 || bump != 0.0) break;
+        bump = 1.0;
     }
     int base = 0;
     for (int k = 0; k < P.geom.AW; ++k) {
@@ -206,7 +211,7 @@ __device__ __forceinline__ bool expand_node(const Params& P, GameCtx& gm, WarpSm
             const int a = k * 32 + lane;
             const int e = base + __popc(wk & ((1u << lane) - 1u));
             const double p = prior(a);
-            eb.P[e] = fallback ? __ddiv_rn(__dadd_rn(p, 1.0), tot2) : __ddiv_rn(p, tot);
+            eb.P[e] = __ddiv_rn(__dadd_rn(p, bump), tot);
             eb.Q[e] = 0.0;
             eb.NC[e] = make_int2(0, -1);
             eb.ACT[e] = (uint16_t)a;
@@ -301,7 +306,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
         depth++;
         st.edges++;
         if (child < 0) {  // first traversal of this edge: getNextState + key lookup (:125-128)
-            const int item = act / ge.W;
+            const int item = div_w(ge, act);
             const int x = act - item * ge.W;
             const int w = sm.items[item] & 0xff, h = sm.items[item] >> 8;
             const uint32_t nrec = apply_move(ge, rec, lane, item, w, h, x);
@@ -313,6 +318,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
         cur = child;
     }
     backup_path(gm.nodes, gm.edges, pe, depth, v, lane);
+    if (lane == 0) P.last_v[gm.g] = v;
     return 0;
 }
 
@@ -375,6 +381,7 @@ k_expand_backup(Params P, const void* policy, int policy_f64, const void* value,
         const double v = value_f64 ? reinterpret_cast<const double*>(value)[b]
                                    : (double)reinterpret_cast<const float*>(value)[b];
         backup_path(gm.nodes, gm.edges, pe, depth, v, lane);
+        if (lane == 0) P.last_v[g] = v;
         st.expansions++;
         st.sims++;
         if (lane == 0) P.sims_done[g] += 1;
@@ -660,18 +667,21 @@ k_env_ended(EnvArgs E, const int32_t* total_area, const int32_t* max_h, const do
 
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
-static void build_sum_plan_rec(SumPlan& p, int base, int n) {
+// returns the index of the leaf slot that will hold the sum of [base, base+n)
+static int build_sum_plan_rec(SumPlan& p, int base, int n) {
     if (n <= 128) {  // numpy PW_BLOCKSIZE
         p.leaf_base[p.n_leaves] = (short)base;
         p.leaf_n[p.n_leaves] = (short)n;
-        p.prog[p.prog_len++] = (signed char)p.n_leaves++;
-    } else {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        build_sum_plan_rec(p, base, n2);
-        build_sum_plan_rec(p, base + n2, n - n2);
-        p.prog[p.prog_len++] = -1;
+        return p.n_leaves++;
     }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const int l = build_sum_plan_rec(p, base, n2);
+    const int r = build_sum_plan_rec(p, base + n2, n - n2);
+    p.op_dst[p.n_ops] = (signed char)l;
+    p.op_src[p.n_ops] = (signed char)r;
+    p.n_ops++;
+    return l;
 }
 
 static int make_geom(int W, int H, int N, Geom* g) {
@@ -679,6 +689,7 @@ static int make_geom(int W, int H, int N, Geom* g) {
         return set_err(BPP_E_INVALID, "unsupported geometry W=%d H=%d N=%d (limits: W<=32, H<=28, N<=16)", W, H, N);
     g->W = W; g->H = H; g->N = N; g->A = W * N; g->AW = (W * N + 31) / 32;
     g->wmask = W >= 32 ? 0xffffffffu : ((1u << W) - 1u);
+    g->invW = (65536u + (unsigned)W - 1u) / (unsigned)W;
     return BPP_OK;
 }
 
@@ -771,6 +782,7 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     ALLOC(P.status, G);
     ALLOC(P.ep_r, G);
     ALLOC(P.ep_score, G);
+    ALLOC(P.last_v, G);
     ALLOC(P.pend_depth, G);
     ALLOC(P.pend_leaf, G);
     ALLOC(P.pend_path, G * 32);
@@ -856,6 +868,33 @@ extern "C" int bpp_engine_set_roots(bpp_engine* e, const uint32_t* roots_dev, vo
     k_set_roots<<<(n + 255) / 256, 256, 0, S(stream)>>>(e->P, roots_dev);
     LAUNCH_CHECK(e);
     e->leaf_parked = false;
+    return BPP_OK;
+}
+
+__global__ void k_set_max_h(Params P, const int32_t* max_h) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.G) return;
+    const int cdiv = (P.total_area[g] + P.geom.W - 1) / P.geom.W;
+    P.numer[g] = cdiv > max_h[g] ? cdiv : max_h[g];
+}
+
+extern "C" int bpp_engine_set_max_h(bpp_engine* e, const int32_t* max_h_dev, void* stream) {
+    if (!e || !max_h_dev) return set_err(BPP_E_INVALID, "null argument");
+    k_set_max_h<<<(e->P.G + 127) / 128, 128, 0, S(stream)>>>(e->P, max_h_dev);
+    LAUNCH_CHECK(e);
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_set_num_sims(bpp_engine* e, int num_sims) {
+    if (!e || num_sims < 0) return set_err(BPP_E_INVALID, "bad argument");
+    e->P.num_sims = num_sims;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_last_values(bpp_engine* e, double* values_out_dev, void* stream) {
+    if (!e || !values_out_dev) return set_err(BPP_E_INVALID, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(values_out_dev, e->P.last_v, (size_t)e->P.G * sizeof(double), cudaMemcpyDeviceToDevice,
+                             S(stream)));
     return BPP_OK;
 }
 

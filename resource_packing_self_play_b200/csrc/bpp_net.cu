@@ -1,9 +1,390 @@
-// bpp_net.cu — batched policy/value forward (placeholder translation unit; the real kernels land next).
+// bpp_net.cu — batched policy/value network forward for the leaf evaluation of the search
+// (NNetWrapper.predict, binpacking/pytorch/NNet.py:69-85, over BinPackingNNet.forward,
+// binpacking/pytorch/BinpackingNNet.py:72-81: three ConvSequences [conv3x3 -> maxpool(3,2,1) -> 2 residual blocks],
+// flatten, relu, fc256, relu, {fc A -> log_softmax, fc 1 -> tanh}; predict returns exp(log_pi) and v).
+//
+// Numerics: weights and inter-layer activations are bf16, every accumulation is fp32 (the tolerance against the fp32
+// torch reference is stated in tests/test_gpu_net.py).  The input planes are never materialised in HBM: they are
+// synthesised in shared memory from the 128-byte compact state record (row masks + remaining mask) and the episode's
+// item list.
+//
+// Kernel v1 (this file): one CTA per leaf, whole network fused in one launch, activations resident in shared memory,
+// weights (341 KB bf16) served from L1/L2.  CUDA-core FMA; the tcgen05 implicit-GEMM version replaces the conv stages
+// ("leaf evaluation").
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
 #include "../../include/bpp_b200.h"
-extern "C" int bpp_net_create(int, int, int, int, int, bpp_net** out) { if (out) *out = nullptr; return BPP_E_STATE; }
-extern "C" int bpp_net_destroy(bpp_net*) { return BPP_OK; }
-extern "C" int bpp_net_set_param(bpp_net*, const char*, const float*, int64_t) { return BPP_E_STATE; }
-extern "C" int bpp_net_commit(bpp_net*, void*) { return BPP_E_STATE; }
-extern "C" int bpp_net_forward(bpp_net*, int, const int32_t*, const uint32_t*, const int32_t*, const int32_t*, float*,
-                               float*, void*) { return BPP_E_STATE; }
+
+namespace {
+
+constexpr int NCONV = 15;   // 3 sequences x (1 + 2*2) convolutions
+constexpr int HIDDEN = 256;
+constexpr int NET_THREADS = 128;
+constexpr int CO_T = 4;     // output channels per thread
+
+struct ConvDesc {
+    int ci, co, h, w;       // input channels, output channels, spatial size
+    long long w_off;        // offset (elements) into the bf16 weight buffer, layout [ci][tap][co]
+    int b_off;              // offset into the fp32 bias buffer
+};
+
+struct NetParams {
+    int W, H, N, Cin, A;
+    int hs[4], ws[4];       // spatial size at the input of sequence s (s = 3: after the last pool)
+    int flat;               // 32 * hs[3] * ws[3]
+    int buf_elems;          // floats per activation buffer
+    ConvDesc conv[NCONV];
+    long long fc_hidden_off, fc_logits_off, fc_value_off;  // bf16, transposed [in][out]
+    int b_hidden_off, b_logits_off, b_value_off;
+    const __nv_bfloat16* wts;
+    const float* bias;
+};
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// out[co][y][x] = bias[co] + sum_{ci,dy,dx} act(in[ci][y+dy-1][x+dx-1]) * w[ci][dy*3+dx][co] (+ residual)
+template <bool RELU_IN>
+__device__ void conv3x3(const NetParams& P, const ConvDesc& d, const float* __restrict__ in, float* __restrict__ out,
+                        const float* residual) {
+    const int hw = d.h * d.w;
+    const int groups = d.co / CO_T;
+    const __nv_bfloat16* wbase = P.wts + d.w_off;
+    for (int idx = threadIdx.x; idx < groups * hw; idx += blockDim.x) {
+        const int cg = idx / hw, p = idx - cg * hw;
+        const int y = p / d.w, x = p - y * d.w;
+        const int co0 = cg * CO_T;
+        float acc[CO_T];
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[j] = P.bias[d.b_off + co0 + j];
+        for (int ci = 0; ci < d.ci; ++ci) {
+            const float* ip = in + ci * hw;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int yy = y + dy - 1;
+                if (yy < 0 || yy >= d.h) continue;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int xx = x + dx - 1;
+                    if (xx < 0 || xx >= d.w) continue;
+                    float v = ip[yy * d.w + xx];
+                    if (RELU_IN) v = fmaxf(v, 0.f);
+                    const uint2 wv = *reinterpret_cast<const uint2*>(wbase + ((size_t)(ci * 9 + dy * 3 + dx) * d.co + co0));
+                    acc[0] = fmaf(v, __uint_as_float(wv.x << 16), acc[0]);
+                    acc[1] = fmaf(v, __uint_as_float(wv.x & 0xffff0000u), acc[1]);
+                    acc[2] = fmaf(v, __uint_as_float(wv.y << 16), acc[2]);
+                    acc[3] = fmaf(v, __uint_as_float(wv.y & 0xffff0000u), acc[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) {
+            float r = acc[j];
+            if (residual) r += residual[(co0 + j) * hw + p];
+            out[(co0 + j) * hw + p] = bf16_round(r);
+        }
+    }
+    __syncthreads();
+}
+
+// max_pool2d(kernel 3, stride 2, padding 1): (h, w) -> ((h+1)/2, (w+1)/2)
+__device__ void maxpool3s2(const float* __restrict__ in, float* __restrict__ out, int c, int h, int w) {
+    const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+    for (int idx = threadIdx.x; idx < c * ho * wo; idx += blockDim.x) {
+        const int ch = idx / (ho * wo), p = idx - ch * ho * wo;
+        const int oy = p / wo, ox = p - oy * wo;
+        float m = -INFINITY;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = 2 * oy + dy;
+            if (yy < 0 || yy >= h) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = 2 * ox + dx;
+                if (xx < 0 || xx >= w) continue;
+                m = fmaxf(m, in[(ch * h + yy) * w + xx]);
+            }
+        }
+        out[idx] = m;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NET_THREADS)
+k_net_forward(NetParams P, int Bmax, const int32_t* __restrict__ count_dev, const uint32_t* __restrict__ recs,
+              const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh, float* __restrict__ policy,
+              float* __restrict__ value) {
+    extern __shared__ float smem[];
+    float* bufA = smem;
+    float* bufB = smem + P.buf_elems;
+    float* bufC = smem + 2 * P.buf_elems;
+    __shared__ float s_red[NET_THREADS / 32 + 1];
+    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        // ---- input planes from the compact record (getBinItem, BinPackingGame.py:118-120)
+        const uint32_t* rec = recs + (size_t)b * 32;
+        const int g = game ? game[b] : b;
+        const int32_t* it = items_wh + (size_t)g * P.N * 2;
+        const uint32_t rem = rec[BPP_REC_REM];
+        const int hw0 = P.H * P.W;
+        for (int idx = threadIdx.x; idx < P.Cin * hw0; idx += blockDim.x) {
+            const int c = idx / hw0, p = idx - c * hw0;
+            const int y = p / P.W, x = p - y * P.W;
+            float v;
+            if (c == 0) v = (float)((rec[y] >> x) & 1u);
+            else v = (((rem >> (c - 1)) & 1u) && y < it[(c - 1) * 2 + 1] && x < it[(c - 1) * 2]) ? 1.f : 0.f;
+            bufA[idx] = v;
+        }
+        __syncthreads();
+        // ---- three ConvSequences (BinpackingNNet.py:29-48)
+        float* x = bufA;
+        float* t1 = bufB;
+        float* t2 = bufC;
+        int li = 0;
+        for (int s = 0; s < 3; ++s) {
+            const ConvDesc& c0 = P.conv[li++];
+            conv3x3<false>(P, c0, x, t1, nullptr);
+            maxpool3s2(t1, x, c0.co, c0.h, c0.w);
+            for (int blk = 0; blk < 2; ++blk) {  // ResidualBlock, BinpackingNNet.py:15-27
+                const ConvDesc& ca = P.conv[li++];
+                const ConvDesc& cb = P.conv[li++];
+                conv3x3<true>(P, ca, x, t1, nullptr);
+                conv3x3<true>(P, cb, t1, t2, x);
+                float* sw = x; x = t2; t2 = sw;
+            }
+        }
+        // ---- heads: flatten -> relu -> fc256 -> relu -> {logits, value} (BinpackingNNet.py:74-81)
+        const __nv_bfloat16* wh = P.wts + P.fc_hidden_off;
+        for (int o = threadIdx.x; o < HIDDEN; o += blockDim.x) {
+            float acc = P.bias[P.b_hidden_off + o];
+            for (int i = 0; i < P.flat; ++i)
+                acc = fmaf(fmaxf(x[i], 0.f), __bfloat162float(wh[(size_t)i * HIDDEN + o]), acc);
+            t1[o] = bf16_round(fmaxf(acc, 0.f));
+        }
+        __syncthreads();
+        const __nv_bfloat16* wl = P.wts + P.fc_logits_off;
+        float lmax = -INFINITY;
+        for (int o = threadIdx.x; o < P.A; o += blockDim.x) {
+            float acc = P.bias[P.b_logits_off + o];
+            for (int i = 0; i < HIDDEN; ++i) acc = fmaf(t1[i], __bfloat162float(wl[(size_t)i * P.A + o]), acc);
+            t2[o] = acc;
+            lmax = fmaxf(lmax, acc);
+        }
+        if (threadIdx.x < 32) {  // value head: one warp
+            const __nv_bfloat16* wv = P.wts + P.fc_value_off;
+            float acc = 0.f;
+            for (int i = threadIdx.x; i < HIDDEN; i += 32) acc = fmaf(t1[i], __bfloat162float(wv[i]), acc);
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (threadIdx.x == 0) value[b] = tanhf(acc + P.bias[P.b_value_off]);
+        }
+        // softmax = exp(log_softmax(logits)) (BinpackingNNet.py:81, NNet.py:85)
+        for (int o = 16; o; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = lmax;
+        __syncthreads();
+        lmax = s_red[0];
+        for (int i = 1; i < NET_THREADS / 32; ++i) lmax = fmaxf(lmax, s_red[i]);
+        __syncthreads();
+        float lsum = 0.f;
+        for (int o = threadIdx.x; o < P.A; o += blockDim.x) lsum += expf(t2[o] - lmax);
+        for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = lsum;
+        __syncthreads();
+        lsum = 0.f;
+        for (int i = 0; i < NET_THREADS / 32; ++i) lsum += s_red[i];
+        const float lse = lmax + logf(lsum);
+        for (int o = threadIdx.x; o < P.A; o += blockDim.x) policy[(size_t)b * P.A + o] = expf(t2[o] - lse);
+        __syncthreads();
+    }
+}
+
+uint16_t f32_to_bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+int bpp_set_error_message(int code, const char* msg);  // defined in bpp_engine.cu
+
+struct bpp_net {
+    NetParams P;
+    int max_batch, device;
+    std::map<std::string, std::vector<float>> host;
+    std::map<std::string, long long> expect;  // name -> numel
+    __nv_bfloat16* d_wts = nullptr;
+    float* d_bias = nullptr;
+    bool committed = false;
+    int smem_bytes = 0;
+};
+
+static const char* kSeqConvNames[5] = {"conv", "res_block0.conv0", "res_block0.conv1", "res_block1.conv0",
+                                       "res_block1.conv1"};
+
+static int nerr(int code, const std::string& msg) { return bpp_set_error_message(code, msg.c_str()); }
+
+extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bpp_net** out) {
+    if (!out) return nerr(BPP_E_INVALID, "null argument");
+    *out = nullptr;
+    if (W < 1 || W > 32 || H < 1 || H > 28 || N < 1 || N > BPP_MAX_ITEMS || max_batch < 1)
+        return nerr(BPP_E_INVALID, "unsupported network geometry");
+    bpp_net* n = new bpp_net();
+    n->max_batch = max_batch;
+    n->device = device;
+    NetParams& P = n->P;
+    memset(&P, 0, sizeof(P));
+    P.W = W; P.H = H; P.N = N; P.Cin = N + 1; P.A = W * N;
+    P.hs[0] = H; P.ws[0] = W;
+    for (int s = 0; s < 3; ++s) {
+        P.hs[s + 1] = (P.hs[s] + 1) / 2;
+        P.ws[s + 1] = (P.ws[s] + 1) / 2;
+    }
+    const int chans[3] = {16, 32, 32};
+    P.flat = 32 * P.hs[3] * P.ws[3];
+    long long woff = 0;
+    int boff = 0, li = 0, cin = P.Cin;
+    int buf = P.Cin * H * W;
+    for (int s = 0; s < 3; ++s) {
+        for (int k = 0; k < 5; ++k) {
+            ConvDesc& d = P.conv[li++];
+            d.ci = k == 0 ? cin : chans[s];
+            d.co = chans[s];
+            d.h = k == 0 ? P.hs[s] : P.hs[s + 1];
+            d.w = k == 0 ? P.ws[s] : P.ws[s + 1];
+            d.w_off = woff;
+            d.b_off = boff;
+            woff += (long long)d.ci * 9 * d.co;
+            boff += d.co;
+            if (d.co * d.h * d.w > buf) buf = d.co * d.h * d.w;
+            const std::string base = "conv_seqs." + std::to_string(s) + "." + kSeqConvNames[k];
+            n->expect[base + ".weight"] = (long long)d.co * d.ci * 9;
+            n->expect[base + ".bias"] = d.co;
+        }
+        cin = chans[s];
+    }
+    if (buf < HIDDEN) buf = HIDDEN;
+    if (buf < P.A) buf = P.A;
+    P.buf_elems = (buf + 3) & ~3;
+    woff = (woff + 7) & ~7ll;
+    P.fc_hidden_off = woff; woff += (long long)P.flat * HIDDEN;
+    P.fc_logits_off = woff; woff += (long long)HIDDEN * P.A;
+    woff = (woff + 7) & ~7ll;
+    P.fc_value_off = woff; woff += HIDDEN;
+    P.b_hidden_off = boff; boff += HIDDEN;
+    P.b_logits_off = boff; boff += P.A;
+    P.b_value_off = boff; boff += 1;
+    n->expect["hidden_fc.weight"] = (long long)HIDDEN * P.flat;
+    n->expect["hidden_fc.bias"] = HIDDEN;
+    n->expect["logits_fc.weight"] = (long long)P.A * HIDDEN;
+    n->expect["logits_fc.bias"] = P.A;
+    n->expect["value_fc.weight"] = HIDDEN;
+    n->expect["value_fc.bias"] = 1;
+    if (cudaSetDevice(device) != cudaSuccess) { delete n; return nerr(BPP_E_CUDA, "cudaSetDevice failed"); }
+    if (cudaMalloc(&n->d_wts, (size_t)woff * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        cudaMalloc(&n->d_bias, (size_t)boff * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        delete n;
+        return nerr(BPP_E_NOMEM, "cudaMalloc of the network parameters failed");
+    }
+    P.wts = n->d_wts;
+    P.bias = n->d_bias;
+    n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
+    if (cudaFuncSetAttribute(k_net_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        delete n;
+        return nerr(BPP_E_CUDA, "cannot reserve shared memory for the forward kernel");
+    }
+    *out = n;
+    return BPP_OK;
+}
+
+extern "C" int bpp_net_destroy(bpp_net* n) {
+    if (!n) return BPP_OK;
+    cudaFree(n->d_wts);
+    cudaFree(n->d_bias);
+    delete n;
+    return BPP_OK;
+}
+
+extern "C" int bpp_net_set_param(bpp_net* n, const char* name, const float* data_host, int64_t numel) {
+    if (!n || !name || !data_host) return nerr(BPP_E_INVALID, "null argument");
+    auto it = n->expect.find(name);
+    if (it == n->expect.end()) return nerr(BPP_E_INVALID, std::string("unknown parameter name: ") + name);
+    if (it->second != numel)
+        return nerr(BPP_E_INVALID, std::string("parameter ") + name + " has " + std::to_string(numel) +
+                                       " elements, expected " + std::to_string(it->second));
+    n->host[name].assign(data_host, data_host + numel);
+    n->committed = false;
+    return BPP_OK;
+}
+
+extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
+    if (!n) return nerr(BPP_E_INVALID, "null argument");
+    for (auto& kv : n->expect)
+        if (!n->host.count(kv.first)) return nerr(BPP_E_STATE, "parameter not set: " + kv.first);
+    const NetParams& P = n->P;
+    const long long nw = P.fc_value_off + HIDDEN;
+    const int nb = P.b_value_off + 1;
+    std::vector<uint16_t> w((size_t)nw, 0);
+    std::vector<float> b((size_t)nb, 0.f);
+    int li = 0;
+    for (int s = 0; s < 3; ++s)
+        for (int k = 0; k < 5; ++k) {
+            const ConvDesc& d = P.conv[li++];
+            const std::string base = "conv_seqs." + std::to_string(s) + "." + kSeqConvNames[k];
+            const std::vector<float>& src = n->host[base + ".weight"];  // OIHW
+            for (int co = 0; co < d.co; ++co)
+                for (int ci = 0; ci < d.ci; ++ci)
+                    for (int t = 0; t < 9; ++t)
+                        w[(size_t)d.w_off + ((size_t)ci * 9 + t) * d.co + co] =
+                            f32_to_bf16_rne(src[((size_t)co * d.ci + ci) * 9 + t]);
+            const std::vector<float>& bs = n->host[base + ".bias"];
+            for (int co = 0; co < d.co; ++co) b[d.b_off + co] = bs[co];
+        }
+    {
+        const std::vector<float>& src = n->host["hidden_fc.weight"];  // [256][flat]
+        for (int o = 0; o < HIDDEN; ++o)
+            for (int i = 0; i < P.flat; ++i)
+                w[(size_t)P.fc_hidden_off + (size_t)i * HIDDEN + o] = f32_to_bf16_rne(src[(size_t)o * P.flat + i]);
+        const std::vector<float>& src2 = n->host["logits_fc.weight"];  // [A][256]
+        for (int o = 0; o < P.A; ++o)
+            for (int i = 0; i < HIDDEN; ++i)
+                w[(size_t)P.fc_logits_off + (size_t)i * P.A + o] = f32_to_bf16_rne(src2[(size_t)o * HIDDEN + i]);
+        const std::vector<float>& src3 = n->host["value_fc.weight"];
+        for (int i = 0; i < HIDDEN; ++i) w[(size_t)P.fc_value_off + i] = f32_to_bf16_rne(src3[i]);
+        memcpy(&b[P.b_hidden_off], n->host["hidden_fc.bias"].data(), HIDDEN * sizeof(float));
+        memcpy(&b[P.b_logits_off], n->host["logits_fc.bias"].data(), (size_t)P.A * sizeof(float));
+        b[P.b_value_off] = n->host["value_fc.bias"][0];
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(n->d_wts, w.data(), w.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(n->d_bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+        return nerr(BPP_E_CUDA, std::string("parameter upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+    n->committed = true;
+    return BPP_OK;
+}
+
+extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, const uint32_t* recs_dev,
+                               const int32_t* game_dev, const int32_t* items_wh_dev, float* policy_out_dev,
+                               float* value_out_dev, void* stream) {
+    if (!n || !recs_dev || !items_wh_dev || !policy_out_dev || !value_out_dev)
+        return B == 0 ? BPP_OK : nerr(BPP_E_INVALID, "null argument");
+    if (!n->committed) return nerr(BPP_E_STATE, "bpp_net_forward before bpp_net_commit");
+    if (B < 0 || B > n->max_batch) return nerr(BPP_E_INVALID, "batch larger than max_batch");
+    if (B == 0) return BPP_OK;
+    int grid = B < 148 * 8 ? B : 148 * 8;
+    k_net_forward<<<grid, NET_THREADS, n->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+        n->P, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return nerr(BPP_E_CUDA, std::string("forward launch failed: ") + cudaGetErrorString(e));
+    return BPP_OK;
+}

@@ -190,6 +190,20 @@ class SearchEngine:
                  torch.int32, self.device).reshape(self.G, REC_WORDS)
         call("bpp_engine_set_roots", self._h, _ptr(t), _stream())
 
+    def set_max_h(self, max_h):
+        t = _dev(max_h, torch.int32, self.device).reshape(self.G)
+        self._keep_mh = t
+        call("bpp_engine_set_max_h", self._h, _ptr(t), _stream())
+
+    def set_num_sims(self, n):
+        call("bpp_engine_set_num_sims", self._h, int(n))
+        self.num_sims = int(n)
+
+    def last_values(self):
+        out = torch.empty(self.G, dtype=torch.float64, device=self.device)
+        call("bpp_engine_last_values", self._h, _ptr(out), _stream())
+        return out
+
     def begin_move(self):
         call("bpp_engine_begin_move", self._h, _stream())
 

@@ -1,0 +1,197 @@
+"""Leaf evaluator with the reference's NeuralNet interface (xw_mcts/NeuralNet.py:14-50 as implemented by
+binpacking/pytorch/NNet.py:17-111).
+
+`predict` / `predict_batch` run the hand-written CUDA forward (csrc/bpp_net.cu) in bf16 with fp32 accumulation.  The
+torch module below has the reference's architecture and parameter names (BinpackingNNet.py:15-81) so that reference
+checkpoints (`{'state_dict': ...}`) load unchanged; it is the parameter container (and the learner's autograd graph,
+SURVEY.md §8(f) rank 1), not the inference path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import call
+from .engine import _ptr, _stream, pack_states
+from .utils import AverageMeter
+
+
+class ResidualBlock(nn.Module):  # BinpackingNNet.py:15-27 (pre-activation residual block)
+    def __init__(self, channels):
+        super().__init__()
+        self.conv0 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+        self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+
+    def forward(self, x):
+        y = self.conv0(F.relu(x))
+        y = self.conv1(F.relu(y))
+        return y + x
+
+
+class ConvSequence(nn.Module):  # BinpackingNNet.py:29-48
+    def __init__(self, input_shape, out_channels):
+        super().__init__()
+        self._input_shape = input_shape
+        self._out_channels = out_channels
+        self.conv = nn.Conv2d(input_shape[0], out_channels, kernel_size=3, padding=1)
+        self.res_block0 = ResidualBlock(out_channels)
+        self.res_block1 = ResidualBlock(out_channels)
+
+    def forward(self, x):
+        x = F.max_pool2d(self.conv(x), kernel_size=3, stride=2, padding=1)
+        return self.res_block1(self.res_block0(x))
+
+    def get_output_shape(self):
+        _c, h, w = self._input_shape
+        return (self._out_channels, (h + 1) // 2, (w + 1) // 2)
+
+
+class BinPackingNNet(nn.Module):  # BinpackingNNet.py:50-81
+    def __init__(self, game, args):
+        super().__init__()
+        self.board_h, self.board_w = game.getBoardSize()
+        self.action_size = game.getActionSize()
+        self.args = args
+        self.in_channels = args.num_items + args.num_bins
+        shape = (self.in_channels, self.board_h, self.board_w)
+        seqs = []
+        for out_channels in (16, 32, 32):
+            seq = ConvSequence(shape, out_channels)
+            shape = seq.get_output_shape()
+            seqs.append(seq)
+        self.conv_seqs = nn.ModuleList(seqs)
+        self.hidden_fc = nn.Linear(shape[0] * shape[1] * shape[2], 256)
+        self.logits_fc = nn.Linear(256, self.action_size)
+        self.value_fc = nn.Linear(256, 1)
+
+    def forward(self, x):
+        for seq in self.conv_seqs:
+            x = seq(x)
+        x = F.relu(torch.flatten(x, start_dim=1))
+        x = F.relu(self.hidden_fc(x))
+        return F.log_softmax(self.logits_fc(x), dim=1), torch.tanh(self.value_fc(x))
+
+
+class DeviceNet:
+    """Handle of the CUDA forward (bpp_net_*)."""
+
+    def __init__(self, W, H, N, max_batch, device=0):
+        _lib.load()
+        self.W, self.H, self.N, self.A = W, H, N, W * N
+        self.max_batch = max_batch
+        self.device = torch.device("cuda", device)
+        h = C.c_void_p()
+        call("bpp_net_create", W, H, N, max_batch, device, C.byref(h))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().bpp_net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, state_dict):
+        for name, t in state_dict.items():
+            a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
+            call("bpp_net_set_param", self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size)
+        with torch.cuda.device(self.device):
+            call("bpp_net_commit", self._h, _stream())
+
+    def forward(self, recs, items_wh, game=None, count_dev=None, policy_out=None, value_out=None):
+        """recs int32/uint32 (B, 32) device, items_wh int32 (*, N, 2) device, game int32 (B,) device or None."""
+        B = recs.shape[0]
+        if policy_out is None:
+            policy_out = torch.empty((B, self.A), dtype=torch.float32, device=self.device)
+        if value_out is None:
+            value_out = torch.empty(B, dtype=torch.float32, device=self.device)
+        call("bpp_net_forward", self._h, B, _ptr(count_dev) if count_dev is not None else C.c_void_p(0), _ptr(recs),
+             _ptr(game) if game is not None else C.c_void_p(0), _ptr(items_wh), _ptr(policy_out), _ptr(value_out),
+             _stream())
+        return policy_out, value_out
+
+
+class NNetWrapper:
+    """Same surface as NNet.py:17-111: predict / train / save_checkpoint / load_checkpoint."""
+
+    def __init__(self, game, args, max_batch=8192, device=0):
+        self.args = args
+        self.game = game
+        self.nnet = BinPackingNNet(game, args)
+        self.board_h, self.board_w = game.getBoardSize()
+        self.action_size = game.getActionSize()
+        self.num_items = args.num_items
+        self.device = torch.device("cuda", device)
+        self.nnet.to(self.device)  # the reference moves the module only if args.cuda; this path is CUDA-only
+        self.dnet = DeviceNet(self.board_w, self.board_h, self.num_items, max_batch, device)
+        self.sync_weights()
+
+    def sync_weights(self):
+        """push the torch parameters into the CUDA forward (after init / load_checkpoint / train)"""
+        self.dnet.load_state_dict(self.nnet.state_dict())
+
+    # ---- inference ---------------------------------------------------------------------------------------------------
+    def predict(self, board):
+        """board: (N+1, H, W) array -> (pi (A,) float32, v (1,) float32), NNet.py:69-85."""
+        recs, items = pack_states(np.asarray(board), self.board_w, self.board_h, self.num_items)
+        recs_t = torch.from_numpy(recs.view(np.int32)).to(self.device)
+        items_t = torch.from_numpy(items).to(self.device)
+        pi, v = self.dnet.forward(recs_t, items_t)
+        return pi[0].cpu().numpy(), v[:1].cpu().numpy()
+
+    def predict_batch(self, recs, items_wh, game=None, count_dev=None):
+        return self.dnet.forward(recs, items_wh, game, count_dev)
+
+    # ---- learner (same semantics as NNet.py:27-67,87-91) --------------------------------------
+    def train(self, examples):
+        optimizer = torch.optim.Adam(self.nnet.parameters())  # re-created per call, default lr (args.lr ignored)
+        for epoch in range(self.args.epochs):
+            self.nnet.train()
+            pi_losses, v_losses = AverageMeter(), AverageMeter()
+            batch_count = int(len(examples) / self.args.batch_size)
+            for _ in range(batch_count):
+                ids = np.random.randint(len(examples), size=self.args.batch_size)
+                boards, pis, vs = list(zip(*[examples[i] for i in ids]))
+                boards = torch.as_tensor(np.array(boards), dtype=torch.float32, device=self.device)
+                target_pis = torch.as_tensor(np.array(pis), dtype=torch.float32, device=self.device)
+                target_vs = torch.as_tensor(np.array(vs).astype(np.float64), dtype=torch.float32, device=self.device)
+                out_pi, out_v = self.nnet(boards)
+                l_pi = self.loss_pi(target_pis, out_pi)
+                l_v = self.loss_v(target_vs, out_v)
+                total = l_pi + l_v
+                pi_losses.update(l_pi.item(), boards.size(0))
+                v_losses.update(l_v.item(), boards.size(0))
+                optimizer.zero_grad()
+                total.backward()
+                optimizer.step()
+        self.nnet.eval()
+        self.sync_weights()
+
+    def loss_pi(self, targets, outputs):  # NNet.py:87-88
+        return -torch.sum(targets * outputs) / targets.size()[0]
+
+    def loss_v(self, targets, outputs):  # NNet.py:90-91
+        return torch.sum((targets - outputs.view(-1)) ** 2) / targets.size()[0]
+
+    # ---- checkpoints (NNet.py:93-111; same {'state_dict': ...} format) ---------------------------------------------------
+    def save_checkpoint(self, folder='checkpoint', filename='checkpoint.pth.tar'):
+        filepath = os.path.join(folder, filename)
+        if not os.path.exists(folder):
+            os.mkdir(folder)
+        torch.save({'state_dict': self.nnet.state_dict()}, filepath)
+
+    def load_checkpoint(self, folder='checkpoint', filename='checkpoint.pth.tar'):
+        filepath = os.path.join(folder, filename)
+        if not os.path.exists(filepath):
+            raise FileNotFoundError("No model in path {}".format(filepath))
+        checkpoint = torch.load(filepath, map_location=self.device)
+        self.nnet.load_state_dict(checkpoint['state_dict'])
+        self.sync_weights()
