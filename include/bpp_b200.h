@@ -214,6 +214,13 @@ int bpp_net_destroy(bpp_net *n);
 int bpp_net_set_param(bpp_net *n, const char *name, const float *data_host, int64_t numel);
 /* commit parameters (converts/re-lays-out to the device formats the kernels use) */
 int bpp_net_commit(bpp_net *n, void *stream);
+/* Arithmetic of the forward.  BPP_NET_BF16 (default): bf16 weights and inter-layer activations, fp32 accumulation - within
+ * 1e-3 of the fp32 reference for freshly initialised networks.  BPP_NET_FP32: fp32 weights and activations - needed for
+ * the reference's TRAINED checkpoints, whose logits span ~3e3 so that bf16 rounding of the weights alone moves the
+ * policy by up to 0.3 (measured, DESIGN.md "leaf evaluation"). */
+#define BPP_NET_BF16 0
+#define BPP_NET_FP32 1
+int bpp_net_set_precision(bpp_net *n, int mode);
 /* Forward for B compact states.  recs_dev uint32 [B][32], game_dev int32 [B] (index into items_wh_dev rows; may be
  * NULL for identity), items_wh_dev int32 [*][N][2]; if count_dev != NULL the batch size is read from device memory
  * (*count_dev <= B).  policy_out_dev float32 [B][A] = exp(log_softmax(logits)); value_out_dev float32 [B]. */

@@ -46,18 +46,27 @@ struct NetParams {
     long long fc_hidden_off, fc_logits_off, fc_value_off;  // bf16, transposed [in][out]
     int b_hidden_off, b_logits_off, b_value_off;
     const __nv_bfloat16* wts;
+    const float* wts32;     // same layout in fp32 (precision mode BPP_NET_FP32)
     const float* bias;
 };
 
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+template <bool F32>
+__device__ __forceinline__ float act_round(float x) {
+    return F32 ? x : __bfloat162float(__float2bfloat16_rn(x));
+}
+template <bool F32>
+__device__ __forceinline__ float wt(const NetParams& P, long long idx) {
+    return F32 ? P.wts32[idx] : __bfloat162float(P.wts[idx]);
+}
 
 // out[co][y][x] = bias[co] + sum_{ci,dy,dx} act(in[ci][y+dy-1][x+dx-1]) * w[ci][dy*3+dx][co] (+ residual)
-template <bool RELU_IN>
+template <bool RELU_IN, bool F32>
 __device__ void conv3x3(const NetParams& P, const ConvDesc& d, const float* __restrict__ in, float* __restrict__ out,
                         const float* residual) {
     const int hw = d.h * d.w;
     const int groups = d.co / CO_T;
     const __nv_bfloat16* wbase = P.wts + d.w_off;
+    const float* wbase32 = P.wts32 + d.w_off;
     for (int idx = threadIdx.x; idx < groups * hw; idx += blockDim.x) {
         const int cg = idx / hw, p = idx - cg * hw;
         const int y = p / d.w, x = p - y * d.w;
@@ -77,11 +86,20 @@ __device__ void conv3x3(const NetParams& P, const ConvDesc& d, const float* __re
                     if (xx < 0 || xx >= d.w) continue;
                     float v = ip[yy * d.w + xx];
                     if (RELU_IN) v = fmaxf(v, 0.f);
-                    const uint2 wv = *reinterpret_cast<const uint2*>(wbase + ((size_t)(ci * 9 + dy * 3 + dx) * d.co + co0));
-                    acc[0] = fmaf(v, __uint_as_float(wv.x << 16), acc[0]);
-                    acc[1] = fmaf(v, __uint_as_float(wv.x & 0xffff0000u), acc[1]);
-                    acc[2] = fmaf(v, __uint_as_float(wv.y << 16), acc[2]);
-                    acc[3] = fmaf(v, __uint_as_float(wv.y & 0xffff0000u), acc[3]);
+                    const size_t wi = (size_t)(ci * 9 + dy * 3 + dx) * d.co + co0;
+                    if (F32) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wbase32 + wi);
+                        acc[0] = fmaf(v, wv.x, acc[0]);
+                        acc[1] = fmaf(v, wv.y, acc[1]);
+                        acc[2] = fmaf(v, wv.z, acc[2]);
+                        acc[3] = fmaf(v, wv.w, acc[3]);
+                    } else {
+                        const uint2 wv = *reinterpret_cast<const uint2*>(wbase + wi);
+                        acc[0] = fmaf(v, __uint_as_float(wv.x << 16), acc[0]);
+                        acc[1] = fmaf(v, __uint_as_float(wv.x & 0xffff0000u), acc[1]);
+                        acc[2] = fmaf(v, __uint_as_float(wv.y << 16), acc[2]);
+                        acc[3] = fmaf(v, __uint_as_float(wv.y & 0xffff0000u), acc[3]);
+                    }
                 }
             }
         }
@@ -89,7 +107,7 @@ __device__ void conv3x3(const NetParams& P, const ConvDesc& d, const float* __re
         for (int j = 0; j < CO_T; ++j) {
             float r = acc[j];
             if (residual) r += residual[(co0 + j) * hw + p];
-            out[(co0 + j) * hw + p] = bf16_round(r);
+            out[(co0 + j) * hw + p] = act_round<F32>(r);
         }
     }
     __syncthreads();
@@ -116,6 +134,7 @@ __device__ void maxpool3s2(const float* __restrict__ in, float* __restrict__ out
     __syncthreads();
 }
 
+template <bool F32>
 __global__ void __launch_bounds__(NET_THREADS)
 k_net_forward(NetParams P, int Bmax, const int32_t* __restrict__ count_dev, const uint32_t* __restrict__ recs,
               const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh, float* __restrict__ policy,
@@ -149,37 +168,34 @@ k_net_forward(NetParams P, int Bmax, const int32_t* __restrict__ count_dev, cons
         int li = 0;
         for (int s = 0; s < 3; ++s) {
             const ConvDesc& c0 = P.conv[li++];
-            conv3x3<false>(P, c0, x, t1, nullptr);
+            conv3x3<false, F32>(P, c0, x, t1, nullptr);
             maxpool3s2(t1, x, c0.co, c0.h, c0.w);
             for (int blk = 0; blk < 2; ++blk) {  // ResidualBlock, BinpackingNNet.py:15-27
                 const ConvDesc& ca = P.conv[li++];
                 const ConvDesc& cb = P.conv[li++];
-                conv3x3<true>(P, ca, x, t1, nullptr);
-                conv3x3<true>(P, cb, t1, t2, x);
+                conv3x3<true, F32>(P, ca, x, t1, nullptr);
+                conv3x3<true, F32>(P, cb, t1, t2, x);
                 float* sw = x; x = t2; t2 = sw;
             }
         }
         // ---- heads: flatten -> relu -> fc256 -> relu -> {logits, value} (BinpackingNNet.py:74-81)
-        const __nv_bfloat16* wh = P.wts + P.fc_hidden_off;
         for (int o = threadIdx.x; o < HIDDEN; o += blockDim.x) {
             float acc = P.bias[P.b_hidden_off + o];
             for (int i = 0; i < P.flat; ++i)
-                acc = fmaf(fmaxf(x[i], 0.f), __bfloat162float(wh[(size_t)i * HIDDEN + o]), acc);
-            t1[o] = bf16_round(fmaxf(acc, 0.f));
+                acc = fmaf(fmaxf(x[i], 0.f), wt<F32>(P, P.fc_hidden_off + (long long)i * HIDDEN + o), acc);
+            t1[o] = act_round<F32>(fmaxf(acc, 0.f));
         }
         __syncthreads();
-        const __nv_bfloat16* wl = P.wts + P.fc_logits_off;
         float lmax = -INFINITY;
         for (int o = threadIdx.x; o < P.A; o += blockDim.x) {
             float acc = P.bias[P.b_logits_off + o];
-            for (int i = 0; i < HIDDEN; ++i) acc = fmaf(t1[i], __bfloat162float(wl[(size_t)i * P.A + o]), acc);
+            for (int i = 0; i < HIDDEN; ++i) acc = fmaf(t1[i], wt<F32>(P, P.fc_logits_off + (long long)i * P.A + o), acc);
             t2[o] = acc;
             lmax = fmaxf(lmax, acc);
         }
         if (threadIdx.x < 32) {  // value head: one warp
-            const __nv_bfloat16* wv = P.wts + P.fc_value_off;
             float acc = 0.f;
-            for (int i = threadIdx.x; i < HIDDEN; i += 32) acc = fmaf(t1[i], __bfloat162float(wv[i]), acc);
+            for (int i = threadIdx.x; i < HIDDEN; i += 32) acc = fmaf(t1[i], wt<F32>(P, P.fc_value_off + i), acc);
             for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (threadIdx.x == 0) value[b] = tanhf(acc + P.bias[P.b_value_off]);
         }
@@ -221,7 +237,9 @@ struct bpp_net {
     std::map<std::string, std::vector<float>> host;
     std::map<std::string, long long> expect;  // name -> numel
     __nv_bfloat16* d_wts = nullptr;
+    float* d_wts32 = nullptr;
     float* d_bias = nullptr;
+    int precision = 0;  // BPP_NET_BF16
     bool committed = false;
     int smem_bytes = 0;
 };
@@ -289,15 +307,20 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
     n->expect["value_fc.bias"] = 1;
     if (cudaSetDevice(device) != cudaSuccess) { delete n; return nerr(BPP_E_CUDA, "cudaSetDevice failed"); }
     if (cudaMalloc(&n->d_wts, (size_t)woff * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        cudaMalloc(&n->d_wts32, (size_t)woff * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&n->d_bias, (size_t)boff * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
         delete n;
         return nerr(BPP_E_NOMEM, "cudaMalloc of the network parameters failed");
     }
     P.wts = n->d_wts;
+    P.wts32 = n->d_wts32;
     P.bias = n->d_bias;
     n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
-    if (cudaFuncSetAttribute(k_net_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_net_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(k_net_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
+            cudaSuccess) {
         cudaGetLastError();
         delete n;
         return nerr(BPP_E_CUDA, "cannot reserve shared memory for the forward kernel");
@@ -309,6 +332,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
 extern "C" int bpp_net_destroy(bpp_net* n) {
     if (!n) return BPP_OK;
     cudaFree(n->d_wts);
+    cudaFree(n->d_wts32);
     cudaFree(n->d_bias);
     delete n;
     return BPP_OK;
@@ -334,7 +358,9 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
     const long long nw = P.fc_value_off + HIDDEN;
     const int nb = P.b_value_off + 1;
     std::vector<uint16_t> w((size_t)nw, 0);
+    std::vector<float> w32((size_t)nw, 0.f);
     std::vector<float> b((size_t)nb, 0.f);
+    auto put = [&](size_t idx, float v) { w[idx] = f32_to_bf16_rne(v); w32[idx] = v; };
     int li = 0;
     for (int s = 0; s < 3; ++s)
         for (int k = 0; k < 5; ++k) {
@@ -344,8 +370,7 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
             for (int co = 0; co < d.co; ++co)
                 for (int ci = 0; ci < d.ci; ++ci)
                     for (int t = 0; t < 9; ++t)
-                        w[(size_t)d.w_off + ((size_t)ci * 9 + t) * d.co + co] =
-                            f32_to_bf16_rne(src[((size_t)co * d.ci + ci) * 9 + t]);
+                        put((size_t)d.w_off + ((size_t)ci * 9 + t) * d.co + co, src[((size_t)co * d.ci + ci) * 9 + t]);
             const std::vector<float>& bs = n->host[base + ".bias"];
             for (int co = 0; co < d.co; ++co) b[d.b_off + co] = bs[co];
         }
@@ -353,23 +378,30 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
         const std::vector<float>& src = n->host["hidden_fc.weight"];  // [256][flat]
         for (int o = 0; o < HIDDEN; ++o)
             for (int i = 0; i < P.flat; ++i)
-                w[(size_t)P.fc_hidden_off + (size_t)i * HIDDEN + o] = f32_to_bf16_rne(src[(size_t)o * P.flat + i]);
+                put((size_t)P.fc_hidden_off + (size_t)i * HIDDEN + o, src[(size_t)o * P.flat + i]);
         const std::vector<float>& src2 = n->host["logits_fc.weight"];  // [A][256]
         for (int o = 0; o < P.A; ++o)
             for (int i = 0; i < HIDDEN; ++i)
-                w[(size_t)P.fc_logits_off + (size_t)i * P.A + o] = f32_to_bf16_rne(src2[(size_t)o * HIDDEN + i]);
+                put((size_t)P.fc_logits_off + (size_t)i * P.A + o, src2[(size_t)o * HIDDEN + i]);
         const std::vector<float>& src3 = n->host["value_fc.weight"];
-        for (int i = 0; i < HIDDEN; ++i) w[(size_t)P.fc_value_off + i] = f32_to_bf16_rne(src3[i]);
+        for (int i = 0; i < HIDDEN; ++i) put((size_t)P.fc_value_off + i, src3[i]);
         memcpy(&b[P.b_hidden_off], n->host["hidden_fc.bias"].data(), HIDDEN * sizeof(float));
         memcpy(&b[P.b_logits_off], n->host["logits_fc.bias"].data(), (size_t)P.A * sizeof(float));
         b[P.b_value_off] = n->host["value_fc.bias"][0];
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (cudaMemcpyAsync(n->d_wts, w.data(), w.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(n->d_wts32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess)
         return nerr(BPP_E_CUDA, std::string("parameter upload failed: ") + cudaGetErrorString(cudaGetLastError()));
     n->committed = true;
+    return BPP_OK;
+}
+
+extern "C" int bpp_net_set_precision(bpp_net* n, int mode) {
+    if (!n || (mode != BPP_NET_BF16 && mode != BPP_NET_FP32)) return nerr(BPP_E_INVALID, "unknown precision mode");
+    n->precision = mode;
     return BPP_OK;
 }
 
@@ -382,8 +414,13 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
     if (B < 0 || B > n->max_batch) return nerr(BPP_E_INVALID, "batch larger than max_batch");
     if (B == 0) return BPP_OK;
     int grid = B < 148 * 8 ? B : 148 * 8;
-    k_net_forward<<<grid, NET_THREADS, n->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(
-        n->P, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n->precision == BPP_NET_FP32)
+        k_net_forward<true><<<grid, NET_THREADS, n->smem_bytes, st>>>(n->P, B, count_dev, recs_dev, game_dev, items_wh_dev,
+                                                                      policy_out_dev, value_out_dev);
+    else
+        k_net_forward<false><<<grid, NET_THREADS, n->smem_bytes, st>>>(n->P, B, count_dev, recs_dev, game_dev,
+                                                                       items_wh_dev, policy_out_dev, value_out_dev);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return nerr(BPP_E_CUDA, std::string("forward launch failed: ") + cudaGetErrorString(e));
     return BPP_OK;

@@ -99,6 +99,11 @@ class DeviceNet:
         except Exception:
             pass
 
+    def set_precision(self, mode):
+        """'bf16' (bf16 weights/activations, fp32 accumulate) or 'fp32'"""
+        call("bpp_net_set_precision", self._h, {"bf16": 0, "fp32": 1}[mode])
+        self.precision = mode
+
     def load_state_dict(self, state_dict):
         for name, t in state_dict.items():
             a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
@@ -122,7 +127,7 @@ class DeviceNet:
 class NNetWrapper:
     """Same surface as NNet.py:17-111: predict / train / save_checkpoint / load_checkpoint."""
 
-    def __init__(self, game, args, max_batch=8192, device=0):
+    def __init__(self, game, args, max_batch=8192, device=0, precision="bf16"):
         self.args = args
         self.game = game
         self.nnet = BinPackingNNet(game, args)
@@ -132,6 +137,7 @@ class NNetWrapper:
         self.device = torch.device("cuda", device)
         self.nnet.to(self.device)  # the reference moves the module only if args.cuda; this path is CUDA-only
         self.dnet = DeviceNet(self.board_w, self.board_h, self.num_items, max_batch, device)
+        self.dnet.set_precision(precision)
         self.sync_weights()
 
     def sync_weights(self):

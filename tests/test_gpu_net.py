@@ -1,0 +1,133 @@
+"""-m gpu: the CUDA policy/value forward (bf16 weights + activations, fp32 accumulate) against
+(a) outputs of the reference's own BinPackingNNet (fp32, CPU) stored in tests/golden/net.npz with the weights used, and
+(b) a plain fp32 torch forward of the same architecture on the device.
+
+Tolerance (stated by SURVEY.md §8(d), config 3): |d pi|_inf <= 2e-2 and |d v| <= 2e-2; the bf16 mode is held to
+it on the seeded random-init 20x20 network.  The shipped TRAINED checkpoint has logits in [-3.2e3, -44]: rounding its
+weights to bf16 alone moves the policy by up to 0.33 and the value by 0.09 (tests/golden/make_golden.py outputs vs a CPU
+emulation of bf16 rounding), so that checkpoint is held to the tolerance in the fp32 mode of the kernel, and the bf16
+mode is only checked to be exactly what bf16 rounding of a fp32 torch forward gives (same arg-max on >= 90 % of the
+states)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL_PI, TOL_V = 2e-2, 2e-2
+
+
+class _Game:
+    def __init__(self, W, H, N):
+        self.W, self.H, self.N = W, H, N
+
+    def getBoardSize(self):
+        return (self.H, self.W)
+
+    def getActionSize(self):
+        return self.W * self.N
+
+
+def _wrapper(W, H, N, weights, precision="bf16"):
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+    net = NNetWrapper(_Game(W, H, N), dotdict(num_items=N, num_bins=1, cuda=True, epochs=1, batch_size=8),
+                      precision=precision)
+    sd = {k: torch.from_numpy(v) for k, v in weights.items()}
+    net.nnet.load_state_dict(sd)
+    net.sync_weights()
+    return net
+
+
+@pytest.mark.parametrize("tag,W,H,N,precision", [("ck", 15, 15, 10, "fp32"), ("r20", 20, 20, 10, "bf16"),
+                                                 ("r20", 20, 20, 10, "fp32")])
+def test_forward_matches_reference_outputs(tag, W, H, N, precision):
+    from resource_packing_self_play_b200.engine import pack_states
+    d = np.load(os.path.join(GOLDEN, "net.npz"))
+    weights = {k[len(tag) + 3:]: d[k] for k in d.files if k.startswith(tag + "_w.")}
+    net = _wrapper(W, H, N, weights, precision)
+    states = d[tag + "_states"].astype(np.int64)
+    recs, items = pack_states(states, W, H, N)
+    dev = net.device
+    pi, v = net.predict_batch(torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev))
+    pi, v = pi.cpu().numpy(), v.cpu().numpy()
+    assert np.abs(pi.sum(axis=1) - 1).max() < 1e-4
+    assert np.abs(pi - d[tag + "_pi"]).max() <= TOL_PI
+    assert np.abs(v - d[tag + "_v"]).max() <= TOL_V
+    # the same states through torch fp32 on the device (plain PyTorch reference of the op)
+    with torch.no_grad():
+        lp, tv = net.nnet(torch.from_numpy(states.astype(np.float32)).to(dev))
+    assert np.abs(pi - lp.exp().cpu().numpy()).max() <= TOL_PI
+    assert np.abs(v - tv.view(-1).cpu().numpy()).max() <= TOL_V
+    # single-state drop-in call: NNetWrapper.predict(board) -> (pi (A,), v (1,))
+    p1, v1 = net.predict(states[3])
+    assert p1.shape == (W * N,) and v1.shape == (1,) and p1.dtype == np.float32
+    assert np.array_equal(p1, pi[3]) and v1[0] == v[3]
+
+
+def test_forward_with_game_index_and_device_count():
+    from resource_packing_self_play_b200.engine import pack_states
+    d = np.load(os.path.join(GOLDEN, "net.npz"))
+    weights = {k[5:]: d[k] for k in d.files if k.startswith("ck_w.")}
+    net = _wrapper(15, 15, 10, weights)
+    states = d["ck_states"].astype(np.int64)
+    recs, items = pack_states(states, 15, 15, 10)
+    dev = net.device
+    recs_t, items_t = torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev)
+    pi_ref, v_ref = net.predict_batch(recs_t, items_t)
+    perm = torch.randperm(len(states), device=dev).to(torch.int32)
+    count = torch.tensor([20], dtype=torch.int32, device=dev)
+    pi = torch.zeros_like(pi_ref)
+    v = torch.zeros_like(v_ref)
+    net.dnet.forward(recs_t[perm.long()].contiguous(), items_t, game=perm, count_dev=count, policy_out=pi, value_out=v)
+    assert torch.equal(pi[:20], pi_ref[perm.long()][:20]) and torch.equal(v[:20], v_ref[perm.long()][:20])
+    assert float(pi[20:].abs().sum()) == 0.0  # rows beyond the device-side count are not touched
+
+
+def test_checkpoint_round_trip(tmp_path):
+    d = np.load(os.path.join(GOLDEN, "net.npz"))
+    weights = {k[5:]: d[k] for k in d.files if k.startswith("ck_w.")}
+    net = _wrapper(15, 15, 10, weights)
+    net.save_checkpoint(str(tmp_path), "x.pth.tar")
+    ck = torch.load(os.path.join(str(tmp_path), "x.pth.tar"), map_location="cpu")
+    assert set(ck.keys()) == {"state_dict"}
+    assert set(ck["state_dict"].keys()) == set(weights.keys())
+    net2 = _wrapper(15, 15, 10, {k: np.zeros_like(v) for k, v in weights.items()})
+    net2.load_checkpoint(str(tmp_path), "x.pth.tar")
+    st = d["ck_states"][:4].astype(np.int64)
+    a, b = net.predict(st[0]), net2.predict(st[0])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_bf16_mode_on_trained_checkpoint_is_plain_bf16_rounding():
+    """documents the precision finding: the bf16 kernel equals a bf16-rounded torch forward, and keeps the arg-max"""
+    import torch.nn.functional as F
+    from resource_packing_self_play_b200.engine import pack_states
+    d = np.load(os.path.join(GOLDEN, "net.npz"))
+    weights = {k[5:]: d[k] for k in d.files if k.startswith("ck_w.")}
+    net = _wrapper(15, 15, 10, weights, "bf16")
+    states = d["ck_states"].astype(np.int64)
+    recs, items = pack_states(states, 15, 15, 10)
+    dev = net.device
+    pi, v = net.predict_batch(torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev))
+    pi = pi.cpu().numpy()
+
+    def bf(t):
+        return t.to(torch.bfloat16).to(torch.float32)
+    Wt = {k: torch.from_numpy(x) for k, x in weights.items()}
+    x = torch.from_numpy(states.astype(np.float32))
+    for s in range(3):
+        p = f"conv_seqs.{s}."
+        x = F.max_pool2d(bf(F.conv2d(x, bf(Wt[p + "conv.weight"]), Wt[p + "conv.bias"], padding=1)), 3, 2, 1)
+        for b in range(2):
+            q = p + f"res_block{b}."
+            y = bf(F.conv2d(F.relu(x), bf(Wt[q + "conv0.weight"]), Wt[q + "conv0.bias"], padding=1))
+            x = bf(F.conv2d(F.relu(y), bf(Wt[q + "conv1.weight"]), Wt[q + "conv1.bias"], padding=1) + x)
+    h = bf(F.relu(F.linear(F.relu(torch.flatten(x, 1)), bf(Wt["hidden_fc.weight"]), Wt["hidden_fc.bias"])))
+    emu = F.softmax(F.linear(h, bf(Wt["logits_fc.weight"]), Wt["logits_fc.bias"]), 1).numpy()
+    assert np.abs(pi - emu).max() < 5e-2          # accumulation-order noise on logits of magnitude 1e2..3e3
+    agree = (pi.argmax(1) == d["ck_pi"].argmax(1)).mean()
+    assert agree >= 0.9, agree
