@@ -140,7 +140,8 @@ int bpp_engine_begin_move(bpp_engine *e, void *stream);
  * unexpanded non-terminal state, then parks that leaf for evaluation.  After it returns, the leaf batch is
  * (leaf_count, leaf records); feed an evaluator and call bpp_engine_expand_backup. */
 int bpp_engine_select(bpp_engine *e, void *stream);
-/* number of parked leaves (synchronises `stream`) */
+/* number of parked leaves (synchronises `stream`); a count of 0 completes the select/expand pairing, i.e. no
+ * bpp_engine_expand_backup call is needed (every game has finished its simulations for this move) */
 int bpp_engine_leaf_count(bpp_engine *e, int32_t *count_host, void *stream);
 /* device-side leaf batch for a device evaluator: count int32[1], game index int32 [<=G], records uint32 [<=G][32]
  * (row b = leaf b).  Pointers stay valid for the life of the handle. */

@@ -918,6 +918,7 @@ extern "C" int bpp_engine_leaf_count(bpp_engine* e, int32_t* count_host, void* s
     if (!e || !count_host) return set_err(BPP_E_INVALID, "null argument");
     CUDA_TRY(cudaMemcpyAsync(count_host, e->P.leaf_count, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    if (*count_host == 0) e->leaf_parked = false;  // nothing to expand: the select/expand pairing is complete
     return BPP_OK;
 }
 

@@ -29,7 +29,11 @@ def _dev(x, dtype, device):
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, C.c_void_p):  # raw device pointer owned by a handle (e.g. the engine's leaf buffers)
+        return t
+    return C.c_void_p(t.data_ptr())
 
 
 def ranked_threshold(rewards_list, alpha):
@@ -241,9 +245,7 @@ class SearchEngine:
         while True:
             self.select()
             n = self.leaf_count()
-            if n == 0:
-                # nothing parked: either all simulations are done or every game is finished
-                call("bpp_engine_expand_backup", self._h, C.c_void_p(8), 0, C.c_void_p(8), 0, _stream())
+            if n == 0:  # nothing parked: all simulations of this move are done (or every game has ended)
                 break
             pol, val = evaluator(self.leaf_planes(n))
             self.expand_backup(pol, val.reshape(-1))

@@ -1,0 +1,146 @@
+"""MCTS with the reference's interface (xw_mcts/MCTS_bpp.py:11-139) on the device-resident search engine.
+
+`MCTS(game, nnet, args)` is a drop-in for CoachBPP.executeEpisode / arena_playing: `getActionProb(state, totalArea,
+rewardsList, greedy_a=1)` and `search(state, totalArea, rewardsList)` take the reference's (N+1, H, W) state tensor.
+The six dicts (Qsa, Nsa, Ns, Ps, Es, Vs) live on the GPU as one search graph per game (csrc/bpp_engine.cu); any
+duck-typed `nnet.predict(board) -> (pi, v)` works as the leaf evaluator (one leaf per step, like the reference),
+while an NNetWrapper of this package is evaluated on the device without leaving it.
+
+`BatchedMCTS` runs G games in lockstep (the fast path).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import REC_REM, SearchEngine, pack_states, ranked_threshold
+
+
+class MCTS:
+    def __init__(self, game, nnet, args, device=0):  # MCTS_bpp.py:16-26
+        self.game = game
+        self.nnet = nnet
+        self.args = args
+        self.device = device
+        self._eng = None
+        self._items = None    # (N, 2) dims known for this episode (0,0 = never seen)
+        self._consts = None   # (total_area, bl, max_h)
+        self._on_device = hasattr(nnet, "dnet") and hasattr(nnet, "predict_batch")
+
+    # ---- engine / episode bookkeeping ----------------------------------------------------------------------------
+    def _engine(self):
+        if self._eng is None:
+            g = self.game
+            self._eng = SearchEngine(g.bin_width, g.bin_height, g.num_items, 1, int(self.args.numMCTSSims),
+                                     float(self.args.cpuct), device=self.device)
+        return self._eng
+
+    def reset(self):
+        """forget the search graph (the reference creates a new MCTS object per episode, CoachBPP.py:124)"""
+        self._items = None
+        self._consts = None
+
+    def _prepare(self, state, totalArea, rewardsList):
+        g = self.game
+        recs, items = pack_states(np.asarray(state), g.bin_width, g.bin_height, g.num_items)
+        rem = int(recs[0, REC_REM])
+        items = items[0]
+        bl = ranked_threshold(rewardsList, self.args.alpha)
+        max_h = int(getattr(g, "max_h", 0)) or int(items[:, 1].max())
+        consts = (int(totalArea), bl, max_h)
+        same = self._items is not None and (consts == self._consts or
+                                            (consts[:1] == self._consts[:1] and consts[2] == self._consts[2] and
+                                             np.isnan(bl) and np.isnan(self._consts[1])))
+        if same:
+            for i in range(g.num_items):
+                if rem >> i & 1 and tuple(items[i]) != tuple(self._items[i]):
+                    same = False  # a remaining item has other dims than this episode's: a different instance
+                    break
+        eng = self._engine()
+        if not same:
+            # new episode: a state key of the reference is the full tensor, so states of another instance never match
+            # the old dict entries; dropping the graph is equivalent (see DESIGN.md for the one exception)
+            self._items = items.copy()
+            self._consts = consts
+            tie = np.array([1 if np.random.random() < 0.5 else -1], dtype=np.int8)  # BinPackingGame.py:212
+            eng.reset(self._items[None], np.array([consts[0]], dtype=np.int32), np.array([bl]), tie)
+            eng.set_max_h(np.array([max_h], dtype=np.int32))
+        eng.set_roots(recs)
+        return eng
+
+    def _run(self, eng, num_sims):
+        eng.set_num_sims(num_sims)
+        eng.begin_move()
+        while True:
+            eng.select()
+            n = eng.leaf_count()
+            if n == 0:
+                return
+            if self._on_device:
+                _, game_ptr, recs_ptr = eng.leaf_buffers()
+                pol, val = self.nnet.dnet.forward(recs_ptr, eng.items_wh, game=game_ptr, batch=n)
+            else:
+                board = eng.leaf_planes(1)[0].cpu().numpy().astype(np.int64)
+                pi, v = self.nnet.predict(board)  # MCTS_bpp.py:87
+                pi = np.asarray(pi)
+                dt = torch.float64 if pi.dtype == np.float64 else torch.float32
+                pol = torch.as_tensor(np.ascontiguousarray(pi), dtype=dt).reshape(1, -1).to(eng.device)
+                val = torch.tensor([float(np.asarray(v).reshape(-1)[0])], dtype=torch.float64, device=eng.device)
+            eng.expand_backup(pol, val)
+
+    # ---- reference API ------------------------------------------------------------------------------------------------
+    def getActionProb(self, canonicalBoard, totalArea, rewardsList, greedy_a=1):  # MCTS_bpp.py:28-54
+        eng = self._prepare(canonicalBoard, totalArea, rewardsList)
+        self._run(eng, int(self.args.numMCTSSims))
+        eng.check()
+        counts = [int(c) for c in eng.root_counts_host()[0]]
+        if greedy_a == 0:
+            bestAs = np.array(np.argwhere(counts == np.max(counts))).flatten()
+            bestA = np.random.choice(bestAs)
+            probs = [0] * len(counts)
+            probs[bestA] = 1
+            return probs
+        counts = [x ** (1. / greedy_a) for x in counts]
+        counts_sum = float(sum(counts))
+        return [x / counts_sum for x in counts]
+
+    def search(self, canonicalBoard, totalArea, rewardsList):  # MCTS_bpp.py:56-139 — one simulation
+        eng = self._prepare(canonicalBoard, totalArea, rewardsList)
+        self._run(eng, 1)
+        return float(eng.last_values()[0].item())
+
+    def root_counts(self):
+        return [int(c) for c in self._engine().root_counts_host()[0]]
+
+
+class BatchedMCTS:
+    """G lockstep games: the batched counterpart of MCTS.getActionProb + CoachBPP.executeEpisode's move loop."""
+
+    def __init__(self, game, nnet, args, G, device=0):
+        self.game, self.nnet, self.args, self.G = game, nnet, args, G
+        self.eng = SearchEngine(game.bin_width, game.bin_height, game.num_items, G, int(args.numMCTSSims),
+                                float(args.cpuct), device=device)
+        self.steps = 0
+
+    def reset(self, items_wh, total_area, rewards_list, tie=None):
+        bl = np.full(self.G, ranked_threshold(rewards_list, self.args.alpha))
+        if tie is None:
+            tie = np.where(np.random.random(self.G) < 0.5, 1, -1).astype(np.int8)
+        self.eng.reset(items_wh, total_area, bl, tie)
+
+    def search(self):
+        """numMCTSSims simulations for every running game; the leaves of a step are evaluated in one batched forward
+        straight from the engine's leaf buffers (no copies, nothing leaves the device but the leaf count)"""
+        eng, net = self.eng, self.nnet.dnet
+        _, game_ptr, recs_ptr = eng.leaf_buffers()
+        pol = torch.empty((self.G, eng.A), dtype=torch.float32, device=eng.device)
+        val = torch.empty(self.G, dtype=torch.float32, device=eng.device)
+        eng.begin_move()
+        while True:
+            eng.select()
+            n = eng.leaf_count()
+            if n == 0:
+                break
+            net.forward(recs_ptr, eng.items_wh, game=game_ptr, policy_out=pol, value_out=val, batch=n)
+            eng.expand_backup(pol, val)
+            self.steps += 1
+        return eng.root_counts()

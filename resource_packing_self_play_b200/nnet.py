@@ -111,9 +111,10 @@ class DeviceNet:
         with torch.cuda.device(self.device):
             call("bpp_net_commit", self._h, _stream())
 
-    def forward(self, recs, items_wh, game=None, count_dev=None, policy_out=None, value_out=None):
-        """recs int32/uint32 (B, 32) device, items_wh int32 (*, N, 2) device, game int32 (B,) device or None."""
-        B = recs.shape[0]
+    def forward(self, recs, items_wh, game=None, count_dev=None, policy_out=None, value_out=None, batch=None):
+        """recs int32/uint32 (B, 32) device, items_wh int32 (*, N, 2) device, game int32 (B,) device or None.
+        recs / game / count_dev may also be raw device pointers (ctypes.c_void_p) with `batch` given."""
+        B = recs.shape[0] if batch is None else int(batch)
         if policy_out is None:
             policy_out = torch.empty((B, self.A), dtype=torch.float32, device=self.device)
         if value_out is None:
