@@ -16,6 +16,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from ._lib import call
+from .distributed import allreduce_gradients
 from .engine import _ptr, _stream, pack_states
 from .utils import AverageMeter
 
@@ -178,6 +179,7 @@ class NNetWrapper:
                 v_losses.update(l_v.item(), boards.size(0))
                 optimizer.zero_grad()
                 total.backward()
+                allreduce_gradients(self.nnet)  # no-op unless torch.distributed is initialised with > 1 rank
                 optimizer.step()
         self.nnet.eval()
         self.sync_weights()

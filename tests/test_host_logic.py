@@ -1,0 +1,99 @@
+"""CPU: host-side logic of the package (no CUDA calls): instance generator, state packing, the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+from helpers import load_items_golden
+from oracle import bpp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from resource_packing_self_play_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "bpp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bpp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/bpp_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.bpp_version() >= 100
+    # error plumbing works without a GPU: bad arguments are rejected before any CUDA call
+    assert lib.bpp_engine_create(None, None) == -1
+    assert b"null" in lib.bpp_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from resource_packing_self_play_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libbpp_b200.so")
+    try:
+        _lib.load()
+        assert False, "expected BppError"
+    except _lib.BppError as e:
+        assert "no CPU fallback" in str(e).lower() or "There is no CPU fallback" in str(e)
+
+
+def test_items_generator_matches_reference_fixtures_and_keeps_global_rng_semantics():
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    for rec in load_items_golden():
+        gen = ItemsGenerator(rec["W"], rec["Hgen"], rec["N"])
+        got = gen.items_generator(rec["seed"])
+        assert [[int(v) for v in it] for it in got] == rec["items"]
+    # like the reference, items_generator re-seeds numpy's global generator (BinPackingGame.py:258) ...
+    gen = ItemsGenerator(15, 9, 10)
+    gen.items_generator(123)
+    a = np.random.randint(1 << 30)
+    O.OracleItemsGenerator(15, 9, 10).items_generator(123)
+    assert a == np.random.randint(1 << 30)
+    # ... while the batched variant leaves it alone and agrees with it
+    np.random.seed(7)
+    x = np.random.randint(1 << 30)
+    np.random.seed(7)
+    batch = gen.items_batch([5, 6, 7], [9, 4, 15])
+    assert x == np.random.randint(1 << 30)
+    for s, h, got in zip([5, 6, 7], [9, 4, 15], batch):
+        want = ItemsGenerator(15, h, 10).items_generator(s)
+        assert [list(map(int, it[:2])) for it in want] == got.tolist()
+    assert gen.bin_height == 9
+
+
+def test_pack_unpack_round_trip_matches_oracle_layout():
+    from resource_packing_self_play_b200.engine import pack_states, ranked_threshold, unpack_states
+    rng = np.random.RandomState(0)
+    for (W, H, N) in [(15, 15, 10), (20, 20, 10), (12, 9, 6), (32, 28, 16)]:
+        g = O.OracleGame(W, H, N, 1)
+        items = [[int(rng.randint(1, W + 1)), int(rng.randint(1, H + 1)), 0, 0] for _ in range(N)]
+        planes = g.getInitItems(items)
+        board = (rng.rand(H, W) < 0.3).astype(np.int64)
+        for i in rng.choice(N, N // 2, replace=False):
+            planes[i] = planes[i] * 0
+        st = g.getBinItem(board, planes)
+        recs, wh = pack_states(st, W, H, N)
+        occ, rem = O.pack_state(st)
+        assert recs[0, :H].tolist() == occ and int(recs[0, 28]) == rem
+        back = unpack_states(recs, wh, W, H, N)[0]
+        assert np.array_equal(back, st)
+    assert np.isnan(ranked_threshold([], 0.75)) and ranked_threshold([0.5, 0.6, 0.7, 0.8001, 0.9], 0.75) == 0.7
+
+
+def test_algorithmic_bytes_formula_matches_survey_figures():
+    from resource_packing_self_play_b200.engine import algorithmic_bytes_per_sim
+    b = algorithmic_bytes_per_sim(15, 15, 10, 4.0, 0.5)  # ~14.4 KB/sim at d=4.0, e=0.5
+    assert 14000 < b < 14800
+    assert 18000 < algorithmic_bytes_per_sim(20, 20, 10, 4.0, 0.5) < 20000
+
+
+def test_dotdict_and_average_meter():
+    from resource_packing_self_play_b200 import AverageMeter, dotdict
+    d = dotdict(a=1)
+    d.b = 2
+    assert d.a == 1 and d["b"] == 2
+    m = AverageMeter()
+    m.update(2.0, 2)
+    m.update(4.0, 2)
+    assert m.avg == 3.0
