@@ -219,8 +219,9 @@ int bpp_net_commit(bpp_net *n, void *stream);
  * 1e-3 of the fp32 reference for freshly initialised networks.  BPP_NET_FP32: fp32 weights and activations - needed for
  * the reference's TRAINED checkpoints, whose logits span ~3e3 so that bf16 rounding of the weights alone moves the
  * policy by up to 0.3 (measured, DESIGN.md "leaf evaluation"). */
-#define BPP_NET_BF16 0
-#define BPP_NET_FP32 1
+#define BPP_NET_BF16 0      /* tcgen05 tensor-core kernel (implicit GEMM, TMEM accumulators) */
+#define BPP_NET_FP32 1      /* CUDA-core kernel, fp32 weights and activations */
+#define BPP_NET_BF16_SIMT 2 /* CUDA-core kernel with the bf16 roundings of mode 0 (cross-check of the tensor-core path) */
 int bpp_net_set_precision(bpp_net *n, int mode);
 /* Forward for B compact states.  recs_dev uint32 [B][32], game_dev int32 [B] (index into items_wh_dev rows; may be
  * NULL for identity), items_wh_dev int32 [*][N][2]; if count_dev != NULL the batch size is read from device memory

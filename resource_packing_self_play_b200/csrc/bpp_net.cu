@@ -18,11 +18,13 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/bpp_b200.h"
+#include "bpp_net_tc.cuh"
 
 namespace {
 
@@ -219,6 +221,173 @@ k_net_forward(NetParams P, int Bmax, const int32_t* __restrict__ count_dev, cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tcgen05 forward: one CTA = S leaves through the whole network (see bpp_net_tc.cuh)
+__global__ void __launch_bounds__(bpptc::TC_THREADS, 1)
+k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__ count_dev,
+                 const uint32_t* __restrict__ recs, const int32_t* __restrict__ game,
+                 const int32_t* __restrict__ items_wh, float* __restrict__ policy, float* __restrict__ value) {
+    using namespace bpptc;
+    extern __shared__ __align__(1024) unsigned char arena[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    unsigned char* regA = arena;
+    unsigned char* regB = arena + T.regA_bytes;
+    unsigned char* wbuf = regB + T.regB_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) mbar_init(smem_u32(&s_bar), 1);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    Ctx cx;
+    cx.tmem = s_tmem;
+    cx.bar = smem_u32(&s_bar);
+    cx.phase = 0;
+    cx.wbuf = wbuf;
+    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
+    const int S = T.S;
+    const int ngroups = (B + S - 1) / S;
+    const int cin16_0 = (P.Cin + 15) / 16;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int nvalid = min(S, B - grp * S);
+        // ---- level-0 operand planes from the compact records (getBinItem, BinPackingGame.py:118-120)
+        const Level& L0 = T.lv[0];
+        zero_bytes(regA, 2 * cin16_0 * L0.RT * 16);
+        __syncthreads();
+        {
+            const int hw = P.H * P.W, nplanes = 2 * cin16_0;
+            for (int idx = tid; idx < nvalid * hw * nplanes; idx += TC_THREADS) {
+                const int p = idx / (nvalid * hw);
+                int r = idx - p * nvalid * hw;
+                const int j = r / hw;
+                r -= j * hw;
+                const int y = r / P.W, x = r - y * P.W;
+                const int b = grp * S + j;
+                const uint32_t* rec = recs + (size_t)b * 32;
+                const int g = game ? game[b] : b;
+                const int32_t* it = items_wh + (size_t)g * P.N * 2;
+                const uint32_t rem = rec[BPP_REC_REM];
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int c = p * 8 + k;
+                    bool on = false;
+                    if (c == 0) on = (rec[y] >> x) & 1u;
+                    else if (c <= P.N) on = ((rem >> (c - 1)) & 1u) && y < it[(c - 1) * 2 + 1] && x < it[(c - 1) * 2];
+                    if (on) w[k >> 1] |= (k & 1) ? 0x3f800000u : 0x00003f80u;  // bf16 1.0
+                }
+                const size_t row = (size_t)L0.guard + (size_t)j * L0.P + (size_t)(y + 1) * L0.wp + (x + 1);
+                *reinterpret_cast<uint4*>(regA + ((size_t)p * L0.RT + row) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        // ---- three ConvSequences
+        const unsigned char* in = regA;
+        int cin16 = cin16_0, li = 0;
+        unsigned char* raw = regA;
+        for (int s = 0; s < 3; ++s) {
+            const Level& La = T.lv[s];
+            const Level& Lb = T.lv[s + 1];
+            const int cout = P.conv[li].co;
+            conv_layer(T, cx, La, nvalid, cin16, cout, T.wts_umma + T.w_off[li], P.bias + P.conv[li].b_off, in, EPI_CONV,
+                       regB, nullptr);
+            ++li;
+            const int planes = cout / 8;
+            const size_t pb = (size_t)planes * Lb.RT * 16;
+            raw = regA;
+            unsigned char* actA = regA + pb;
+            unsigned char* actB = regA + 2 * pb;
+            zero_bytes(regA, (int)(3 * pb));
+            __syncthreads();
+            pool_level(La, Lb, nvalid, planes, regB, raw, actA);
+            for (int blk = 0; blk < 2; ++blk) {
+                conv_layer(T, cx, Lb, nvalid, cout / 16, cout, T.wts_umma + T.w_off[li], P.bias + P.conv[li].b_off, actA,
+                           EPI_RES0, actB, nullptr);
+                ++li;
+                conv_layer(T, cx, Lb, nvalid, cout / 16, cout, T.wts_umma + T.w_off[li], P.bias + P.conv[li].b_off, actB,
+                           EPI_RES1, actA, raw);
+                ++li;
+            }
+            in = raw;
+            cin16 = cout / 16;
+        }
+        // ---- heads on the CUDA cores (1.6 % of the FLOPs): flatten -> relu -> fc256 -> relu -> {logits, value}
+        const Level& L3 = T.lv[3];
+        float* feat = reinterpret_cast<float*>(regB);            // [8][flat]
+        float* hid = feat + 8 * P.flat;                           // [8][256]
+        float* lg = hid + 8 * HIDDEN;                             // [8][A]
+        const int hw3 = L3.h * L3.w;
+        for (int idx = tid; idx < 8 * P.flat; idx += TC_THREADS) {
+            const int j = idx / P.flat, f = idx - j * P.flat;
+            float v = 0.f;
+            if (j < nvalid) {
+                const int c = f / hw3, q = f - c * hw3;
+                const int y = q / L3.w, x = q - y * L3.w;
+                const size_t row = (size_t)L3.guard + (size_t)j * L3.P + (size_t)(y + 1) * L3.wp + (x + 1);
+                const __nv_bfloat16* e =
+                    reinterpret_cast<const __nv_bfloat16*>(raw + ((size_t)(c >> 3) * L3.RT + row) * 16) + (c & 7);
+                v = fmaxf(__bfloat162float(*e), 0.f);
+            }
+            feat[idx] = v;
+        }
+        __syncthreads();
+        for (int o = tid; o < HIDDEN; o += TC_THREADS) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = P.bias[P.b_hidden_off + o];
+            for (int i = 0; i < P.flat; ++i) {
+                const float wv = __bfloat162float(P.wts[P.fc_hidden_off + (long long)i * HIDDEN + o]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(feat[j * P.flat + i], wv, acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hid[j * HIDDEN + o] = act_round<false>(fmaxf(acc[j], 0.f));
+        }
+        __syncthreads();
+        for (int o = tid; o < P.A; o += TC_THREADS) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = P.bias[P.b_logits_off + o];
+            for (int i = 0; i < HIDDEN; ++i) {
+                const float wv = __bfloat162float(P.wts[P.fc_logits_off + (long long)i * P.A + o]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(hid[j * HIDDEN + i], wv, acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lg[j * P.A + o] = acc[j];
+        }
+        __syncthreads();
+        for (int j = warp; j < nvalid; j += TC_THREADS / 32) {  // one warp per leaf: value head + softmax
+            const int b = grp * S + j;
+            float acc = 0.f;
+            for (int i = lane; i < HIDDEN; i += 32)
+                acc = fmaf(hid[j * HIDDEN + i], __bfloat162float(P.wts[P.fc_value_off + i]), acc);
+            float mx = -INFINITY;
+            for (int o = lane; o < P.A; o += 32) mx = fmaxf(mx, lg[j * P.A + o]);
+            for (int o = 16; o; o >>= 1) {
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            float sum = 0.f;
+            for (int o = lane; o < P.A; o += 32) sum += expf(lg[j * P.A + o] - mx);
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float lse = mx + logf(sum);
+            for (int o = lane; o < P.A; o += 32) policy[(size_t)b * P.A + o] = expf(lg[j * P.A + o] - lse);
+            if (lane == 0) value[b] = tanhf(acc + P.bias[P.b_value_off]);
+        }
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"((uint32_t)TMEM_COLS));
+}
+
 uint16_t f32_to_bf16_rne(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -240,6 +409,10 @@ struct bpp_net {
     float* d_wts32 = nullptr;
     float* d_bias = nullptr;
     int precision = 0;  // BPP_NET_BF16
+    bpptc::TcParams T;
+    __nv_bfloat16* d_wts_umma = nullptr;
+    long long umma_elems = 0;
+    bool tc_ok = false;
     bool committed = false;
     int smem_bytes = 0;
 };
@@ -306,6 +479,15 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
     n->expect["value_fc.weight"] = HIDDEN;
     n->expect["value_fc.bias"] = 1;
     if (cudaSetDevice(device) != cudaSuccess) { delete n; return nerr(BPP_E_CUDA, "cudaSetDevice failed"); }
+    {   // UMMA-layout conv weights (size known before the Tc setup below: recompute here)
+        long long u = 0;
+        for (int l = 0; l < NCONV; ++l) u += 9LL * ((P.conv[l].ci + 15) / 16) * 2 * P.conv[l].co * 8;
+        if (cudaMalloc(&n->d_wts_umma, (size_t)u * sizeof(__nv_bfloat16)) != cudaSuccess) {
+            cudaGetLastError();
+            delete n;
+            return nerr(BPP_E_NOMEM, "cudaMalloc of the network parameters failed");
+        }
+    }
     if (cudaMalloc(&n->d_wts, (size_t)woff * sizeof(__nv_bfloat16)) != cudaSuccess ||
         cudaMalloc(&n->d_wts32, (size_t)woff * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&n->d_bias, (size_t)boff * sizeof(float)) != cudaSuccess) {
@@ -316,15 +498,56 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
     P.wts = n->d_wts;
     P.wts32 = n->d_wts32;
     P.bias = n->d_bias;
+    // tensor-core path: pick the largest group size S <= 8 whose buffers fit in shared memory
+    {
+        bpptc::TcParams& T = n->T;
+        memset(&T, 0, sizeof(T));
+        long long uoff = 0;
+        int wmax = 0;
+        for (int l = 0; l < NCONV; ++l) {
+            const int c16 = (P.conv[l].ci + 15) / 16;
+            T.w_off[l] = uoff;
+            const int bytes = 9 * c16 * 2 * P.conv[l].co * 16;
+            uoff += bytes / 2;
+            if (bytes > wmax) wmax = bytes;
+        }
+        n->umma_elems = uoff;
+        const int cin16_0 = (P.Cin + 15) / 16;
+        for (int S = 8; S >= 1 && !n->tc_ok; --S) {
+            for (int l = 0; l < 4; ++l) {
+                bpptc::Level& L = T.lv[l];
+                L.h = P.hs[l]; L.w = P.ws[l]; L.hp = L.h + 2; L.wp = L.w + 2; L.P = L.hp * L.wp;
+                L.guard = (L.wp + 1 + 7) & ~7;
+                L.RT = L.guard + S * L.P + L.guard;
+                L.ntiles = (S * L.P + 127) / 128;
+            }
+            long long a = 2LL * cin16_0 * T.lv[0].RT * 16, b = 0;
+            for (int s2 = 0; s2 < 3; ++s2) {
+                const int planes = chans[s2] / 8;
+                a = std::max(a, 3LL * planes * T.lv[s2 + 1].RT * 16);
+                b = std::max(b, (long long)planes * T.lv[s2].RT * 16);
+            }
+            b = std::max(b, (long long)(8 * (P.flat + HIDDEN + P.A)) * 4);
+            T.S = S;
+            T.regA_bytes = (int)((a + 1023) & ~1023LL);
+            T.regB_bytes = (int)((b + 4096 + 1023) & ~1023LL);  // + slack: the last tile's shifted windows over-read
+            T.wbuf_bytes = (wmax + 1023) & ~1023;
+            T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
+            if (T.smem_bytes <= 200 * 1024 && T.lv[0].RT < 16384) n->tc_ok = true;
+        }
+    }
     n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
     if (cudaFuncSetAttribute(k_net_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
             cudaSuccess ||
         cudaFuncSetAttribute(k_net_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
-            cudaSuccess) {
+            cudaSuccess ||
+        (n->tc_ok && cudaFuncSetAttribute(k_net_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          n->T.smem_bytes) != cudaSuccess)) {
         cudaGetLastError();
         delete n;
         return nerr(BPP_E_CUDA, "cannot reserve shared memory for the forward kernel");
     }
+    n->T.wts_umma = n->d_wts_umma;
     *out = n;
     return BPP_OK;
 }
@@ -333,6 +556,7 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     if (!n) return BPP_OK;
     cudaFree(n->d_wts);
     cudaFree(n->d_wts32);
+    cudaFree(n->d_wts_umma);
     cudaFree(n->d_bias);
     delete n;
     return BPP_OK;
@@ -389,8 +613,30 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
         memcpy(&b[P.b_logits_off], n->host["logits_fc.bias"].data(), (size_t)P.A * sizeof(float));
         b[P.b_value_off] = n->host["value_fc.bias"][0];
     }
+    // conv weights in the UMMA K-major B layout: [tap][kc][k-half][cout][8 cin]
+    std::vector<uint16_t> wu((size_t)n->umma_elems, 0);
+    li = 0;
+    for (int s = 0; s < 3; ++s)
+        for (int k = 0; k < 5; ++k) {
+            const ConvDesc& d = P.conv[li];
+            const std::string base = "conv_seqs." + std::to_string(s) + "." + kSeqConvNames[k];
+            const std::vector<float>& src = n->host[base + ".weight"];  // OIHW
+            const int c16 = (d.ci + 15) / 16;
+            for (int t = 0; t < 9; ++t)
+                for (int kc = 0; kc < c16; ++kc)
+                    for (int kh = 0; kh < 2; ++kh)
+                        for (int co = 0; co < d.co; ++co)
+                            for (int j = 0; j < 8; ++j) {
+                                const int ci = kc * 16 + kh * 8 + j;
+                                const float v = ci < d.ci ? src[((size_t)co * d.ci + ci) * 9 + t] : 0.f;
+                                wu[(size_t)n->T.w_off[li] + ((((size_t)t * c16 + kc) * 2 + kh) * d.co + co) * 8 + j] =
+                                    f32_to_bf16_rne(v);
+                            }
+            ++li;
+        }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (cudaMemcpyAsync(n->d_wts, w.data(), w.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+    if (cudaMemcpyAsync(n->d_wts_umma, wu.data(), wu.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(n->d_wts, w.data(), w.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess)
@@ -400,7 +646,8 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
 }
 
 extern "C" int bpp_net_set_precision(bpp_net* n, int mode) {
-    if (!n || (mode != BPP_NET_BF16 && mode != BPP_NET_FP32)) return nerr(BPP_E_INVALID, "unknown precision mode");
+    if (!n || (mode != BPP_NET_BF16 && mode != BPP_NET_FP32 && mode != BPP_NET_BF16_SIMT))
+        return nerr(BPP_E_INVALID, "unknown precision mode");
     n->precision = mode;
     return BPP_OK;
 }
@@ -415,7 +662,12 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
     if (B == 0) return BPP_OK;
     int grid = B < 148 * 8 ? B : 148 * 8;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (n->precision == BPP_NET_FP32)
+    if (n->precision == BPP_NET_BF16 && n->tc_ok) {
+        const int groups = (B + n->T.S - 1) / n->T.S;
+        const int g2 = groups < 148 ? groups : 148;
+        k_net_forward_tc<<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(n->P, n->T, B, count_dev, recs_dev, game_dev,
+                                                                        items_wh_dev, policy_out_dev, value_out_dev);
+    } else if (n->precision == BPP_NET_FP32)
         k_net_forward<true><<<grid, NET_THREADS, n->smem_bytes, st>>>(n->P, B, count_dev, recs_dev, game_dev, items_wh_dev,
                                                                       policy_out_dev, value_out_dev);
     else

@@ -1,0 +1,250 @@
+// bpp_net_tc.cuh — tcgen05 / TMEM implicit-GEMM forward of the policy/value network (sm_100a).
+//
+// One CTA evaluates a group of S leaves through the WHOLE network without touching HBM in between: activations live
+// in shared memory in the UMMA canonical K-major (no-swizzle) layout, accumulators in tensor memory.
+//
+// Convolution as implicit GEMM without im2col.  At spatial level l every sample is a zero-haloed (h+2) x (w+2) grid and
+// the S grids are concatenated into one long ROW axis (row = one padded pixel).  Activations are stored channels-last
+// in 8-channel planes: plane p holds, for every row, the 16 bytes of channels 8p..8p+7 — exactly the 8-row x 16-byte
+// "core matrix" tiling the tensor core reads for a K-major operand (SBO = 128 B between 8-row groups, LBO = plane
+// stride between the two 8-channel halves of a K=16 slice).  For the 3x3 tap (dy, dx) the A operand of output rows
+// [r0, r0+128) is the SAME buffer shifted by (dy-1)*(w+2) + (dx-1) rows, i.e. only the descriptor's start address
+// changes: 9 (x Cin/16) tcgen05.mma instructions of shape 128 x Cout x 16 accumulate one output tile in TMEM.
+// Rows that are halo or tile padding produce garbage accumulators that the epilogue never stores (halo rows of the
+// activation buffers stay zero, which is the convolution's zero padding).
+//
+// Epilogue (all 128 threads, thread i = TMEM lane i = output row r0+i): tcgen05.ld -> + bias (+ residual) -> bf16 ->
+// 16-byte stores into the next layer's operand planes.  Pooling re-grids level l into level l+1 on the CUDA cores.
+// Weights are pre-arranged on the host in the UMMA B layout and staged per layer into shared memory.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bpptc {
+
+constexpr int TC_THREADS = 128;
+constexpr int TMEM_COLS = 32;
+
+struct Level {
+    int h, w, hp, wp, P, guard, RT, ntiles;  // RT = rows of one plane = guard + S*P + guard
+};
+
+struct TcParams {
+    int S;                 // leaves per CTA
+    Level lv[4];
+    int regA_bytes;        // region A: input planes of level 0, then the {raw, actA, actB} triple of levels 1..3
+    int regB_bytes;        // region B: conv outputs awaiting pooling (T_0..T_2), then the head scratch
+    int wbuf_bytes;        // one layer of weights
+    int smem_bytes;
+    long long w_off[15];   // element offsets of each conv layer in wts_umma
+    const __nv_bfloat16* wts_umma;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading byte
+// offset (between the two 8-element K halves) and stride byte offset (between 8-row groups) in 16-byte units,
+// descriptor version 1 for sm_100.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(lbo16 & 0x3fffu) << 16) |
+           ((uint64_t)(sbo16 & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&b);
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&x);
+    v = __hmax2(v, __floats2bfloat162_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a), y = *reinterpret_cast<__nv_bfloat162*>(&b);
+    x = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&x);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+
+enum { EPI_CONV = 0, EPI_RES0 = 1, EPI_RES1 = 2 };
+
+struct Ctx {
+    uint32_t tmem;      // TMEM base (lane 0, column 0)
+    uint32_t bar;       // mbarrier shared address
+    uint32_t phase;
+    unsigned char* wbuf;
+};
+
+// One 3x3 convolution at level L: in_planes (cin16*2 planes of stride RT*16 bytes) -> epilogue `kind`.
+//   EPI_CONV: out0 <- bf16(acc + bias)                       (raw conv output, to be pooled)
+//   EPI_RES0: out0 <- relu(bf16(acc + bias))
+//   EPI_RES1: v = acc + bias + raw; raw <- bf16(v); out0 <- relu(bf16(v))          (raw is read and updated in place)
+__device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Level& L, int nvalid, int cin16, int cout,
+                                           const __nv_bfloat16* __restrict__ wsrc, const float* __restrict__ bias,
+                                           const unsigned char* in_planes, int kind, unsigned char* out0,
+                                           unsigned char* raw) {
+    const int tid = threadIdx.x;
+    // stage this layer's weights (already in the UMMA B layout) into shared memory
+    const int wbytes = 9 * cin16 * 2 * cout * 16;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(wsrc);
+        uint4* dst = reinterpret_cast<uint4*>(cx.wbuf);
+        for (int i = tid; i < wbytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+    }
+    fence_proxy_async();  // generic-proxy writes (weights, previous epilogue) -> visible to the tensor core's async proxy
+    __syncthreads();
+    const uint32_t idesc = umma_idesc(cout);
+    const uint32_t a_base = smem_u32(in_planes);
+    const uint32_t w_base = smem_u32(cx.wbuf);
+    const uint32_t plane_b = (uint32_t)L.RT * 16u;
+    const int rows_valid = nvalid * L.P;
+    for (int t = 0; t < L.ntiles; ++t) {
+        if (t * 128 >= rows_valid) break;  // whole tile belongs to absent samples (partial last group)
+        if (tid == 0) {
+            tc_fence_after();
+            uint32_t acc = 0;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int off = (tap / 3 - 1) * L.wp + (tap % 3 - 1);
+                for (int kc = 0; kc < cin16; ++kc) {
+                    const uint32_t a_addr = a_base + (uint32_t)(2 * kc) * plane_b + (uint32_t)(L.guard + t * 128 + off) * 16u;
+                    const uint32_t b_addr = w_base + (uint32_t)(tap * cin16 + kc) * (uint32_t)(2 * cout * 16);
+                    umma_bf16(cx.tmem, umma_desc(a_addr, (uint32_t)L.RT, 8u), umma_desc(b_addr, (uint32_t)cout, 8u), idesc,
+                              acc);
+                    acc = 1;
+                }
+            }
+            umma_commit(cx.bar);
+        }
+        mbar_wait(cx.bar, cx.phase);
+        cx.phase ^= 1u;
+        tc_fence_after();
+        // ---- epilogue: thread tid owns output row t*128 + tid
+        const int rl = t * 128 + tid;
+        const int j = rl / L.P, q = rl - j * L.P;
+        const int yp = q / L.wp, xp = q - yp * L.wp;
+        const bool interior = rl < rows_valid && yp >= 1 && yp <= L.h && xp >= 1 && xp <= L.w;
+        const size_t rowb = (size_t)(L.guard + rl) * 16;
+        const uint32_t taddr = cx.tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+        for (int c0 = 0; c0 < cout; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)c0, v);  // warp-collective: executed by every lane
+            if (interior) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += __ldg(bias + c0 + i);
+#pragma unroll
+                for (int hp8 = 0; hp8 < 2; ++hp8) {
+                    const int plane = (c0 >> 3) + hp8;
+                    float* u = v + hp8 * 8;
+                    uint4 o;
+                    if (kind == EPI_RES1) {
+                        uint4* rp = reinterpret_cast<uint4*>(raw + (size_t)plane * plane_b + rowb);
+                        const uint4 rv = *rp;
+                        u[0] += bf16_lo(rv.x); u[1] += bf16_hi(rv.x); u[2] += bf16_lo(rv.y); u[3] += bf16_hi(rv.y);
+                        u[4] += bf16_lo(rv.z); u[5] += bf16_hi(rv.z); u[6] += bf16_lo(rv.w); u[7] += bf16_hi(rv.w);
+                        o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]),
+                                       pack_bf16(u[6], u[7]));
+                        *rp = o;
+                    } else {
+                        o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]),
+                                       pack_bf16(u[6], u[7]));
+                    }
+                    if (kind != EPI_CONV)
+                        o = make_uint4(relu_bf16x2(o.x), relu_bf16x2(o.y), relu_bf16x2(o.z), relu_bf16x2(o.w));
+                    *reinterpret_cast<uint4*>(out0 + (size_t)plane * plane_b + rowb) = o;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // TMEM accumulator is free again; epilogue stores are ordered before the next layer's fence
+    }
+}
+
+// max_pool2d(kernel 3, stride 2, padding 1) from the conv output T (level La) into raw/actA of level Lb
+__device__ __forceinline__ void pool_level(const Level& La, const Level& Lb, int nvalid, int planes,
+                                           const unsigned char* Tbuf, unsigned char* raw, unsigned char* actA) {
+    const uint32_t NEG = 0xff80ff80u;  // bf16 -inf pair
+    const int per = Lb.h * Lb.w;
+    const int total = nvalid * per * planes;
+    for (int idx = threadIdx.x; idx < total; idx += TC_THREADS) {
+        const int p = idx / (nvalid * per);
+        int r = idx - p * nvalid * per;
+        const int j = r / per;
+        r -= j * per;
+        const int oy = r / Lb.w, ox = r - oy * Lb.w;
+        uint4 m = make_uint4(NEG, NEG, NEG, NEG);
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = 2 * oy + dy;
+            if (yy < 0 || yy >= La.h) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = 2 * ox + dx;
+                if (xx < 0 || xx >= La.w) continue;
+                const size_t row = (size_t)La.guard + (size_t)j * La.P + (size_t)(yy + 1) * La.wp + (xx + 1);
+                const uint4 v = *reinterpret_cast<const uint4*>(Tbuf + ((size_t)p * La.RT + row) * 16);
+                m = make_uint4(max_bf16x2(m.x, v.x), max_bf16x2(m.y, v.y), max_bf16x2(m.z, v.z), max_bf16x2(m.w, v.w));
+            }
+        }
+        const size_t orow = (size_t)Lb.guard + (size_t)j * Lb.P + (size_t)(oy + 1) * Lb.wp + (ox + 1);
+        *reinterpret_cast<uint4*>(raw + ((size_t)p * Lb.RT + orow) * 16) = m;
+        *reinterpret_cast<uint4*>(actA + ((size_t)p * Lb.RT + orow) * 16) =
+            make_uint4(relu_bf16x2(m.x), relu_bf16x2(m.y), relu_bf16x2(m.z), relu_bf16x2(m.w));
+    }
+}
+
+__device__ __forceinline__ void zero_bytes(unsigned char* p, int bytes) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    for (int i = threadIdx.x; i < bytes / 16; i += TC_THREADS) q[i] = make_uint4(0, 0, 0, 0);
+}
+
+}  // namespace bpptc

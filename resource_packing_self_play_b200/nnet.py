@@ -101,8 +101,8 @@ class DeviceNet:
             pass
 
     def set_precision(self, mode):
-        """'bf16' (bf16 weights/activations, fp32 accumulate) or 'fp32'"""
-        call("bpp_net_set_precision", self._h, {"bf16": 0, "fp32": 1}[mode])
+        """'bf16' (tcgen05 kernel: bf16 weights/activations, fp32 accumulate), 'fp32', or 'bf16_simt'"""
+        call("bpp_net_set_precision", self._h, {"bf16": 0, "fp32": 1, "bf16_simt": 2}[mode])
         self.precision = mode
 
     def load_state_dict(self, state_dict):

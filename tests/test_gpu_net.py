@@ -131,3 +131,26 @@ def test_bf16_mode_on_trained_checkpoint_is_plain_bf16_rounding():
     assert np.abs(pi - emu).max() < 5e-2          # accumulation-order noise on logits of magnitude 1e2..3e3
     agree = (pi.argmax(1) == d["ck_pi"].argmax(1)).mean()
     assert agree >= 0.9, agree
+
+
+@pytest.mark.parametrize("tag,W,H,N,tol", [("r20", 20, 20, 10, 2e-4), ("ck", 15, 15, 10, 6e-2)])
+def test_tensor_core_kernel_matches_the_simt_kernel_with_the_same_roundings(tag, W, H, N, tol):
+    """tcgen05 path (mode bf16) vs the CUDA-core kernel applying the same bf16 roundings (mode bf16_simt): only the
+    fp32 accumulation order differs.  Odd batch sizes exercise partial groups and tiles."""
+    from resource_packing_self_play_b200.engine import pack_states
+    d = np.load(os.path.join(GOLDEN, "net.npz"))
+    weights = {k[len(tag) + 3:]: d[k] for k in d.files if k.startswith(tag + "_w.")}
+    net = _wrapper(W, H, N, weights, "bf16")
+    states = d[tag + "_states"].astype(np.int64)
+    recs, items = pack_states(states, W, H, N)
+    dev = net.device
+    recs_t, items_t = torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev)
+    for B in (len(states), 1, 7, 13):
+        net.dnet.set_precision("bf16")
+        pi_tc, v_tc = net.predict_batch(recs_t[:B].contiguous(), items_t[:B].contiguous())
+        net.dnet.set_precision("bf16_simt")
+        pi_s, v_s = net.predict_batch(recs_t[:B].contiguous(), items_t[:B].contiguous())
+        torch.cuda.synchronize()
+        assert float((pi_tc.sum(dim=1) - 1).abs().max()) < 1e-4
+        assert float((pi_tc - pi_s).abs().max()) <= tol, (B, float((pi_tc - pi_s).abs().max()))
+        assert float((v_tc - v_s).abs().max()) <= tol
