@@ -223,6 +223,9 @@ int bpp_net_commit(bpp_net *n, void *stream);
 #define BPP_NET_FP32 1      /* CUDA-core kernel, fp32 weights and activations */
 #define BPP_NET_BF16_SIMT 2 /* CUDA-core kernel with the bf16 roundings of mode 0 (cross-check of the tensor-core path) */
 int bpp_net_set_precision(bpp_net *n, int mode);
+/* Phase timers (SM clock cycles, CTA 0 of the last tensor-core forward; synchronises the device):
+ * [0] input planes, [1] weight staging, [2] MMA issue, [3] MMA wait, [4] epilogue, [5] pooling, [6] heads, [7] total. */
+int bpp_net_profile(bpp_net *n, int64_t cycles_host[8]);
 /* Forward for B compact states.  recs_dev uint32 [B][32], game_dev int32 [B] (index into items_wh_dev rows; may be
  * NULL for identity), items_wh_dev int32 [*][N][2]; if count_dev != NULL the batch size is read from device memory
  * (*count_dev <= B).  policy_out_dev float32 [B][A] = exp(log_softmax(logits)); value_out_dev float32 [B]. */

@@ -70,6 +70,7 @@ SIGNATURES = {
     "bpp_net_set_param": [_vp, C.c_char_p, _vp, _i64],
     "bpp_net_commit": [_vp, _vp],
     "bpp_net_set_precision": [_vp, _i32],
+    "bpp_net_profile": [_vp, C.POINTER(_i64)],
     "bpp_net_forward": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"bpp_last_error": C.c_char_p, "bpp_engine_device_bytes": C.c_int64}

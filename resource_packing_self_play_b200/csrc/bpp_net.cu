@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -224,10 +225,11 @@ k_net_forward(NetParams P, int Bmax, const int32_t* __restrict__ count_dev, cons
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 forward: one CTA = S leaves through the whole network (see bpp_net_tc.cuh)
-__global__ void __launch_bounds__(bpptc::TC_THREADS, 1)
+__global__ void __launch_bounds__(bpptc::TC_THREADS, 2)
 k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__ count_dev,
                  const uint32_t* __restrict__ recs, const int32_t* __restrict__ game,
-                 const int32_t* __restrict__ items_wh, float* __restrict__ policy, float* __restrict__ value) {
+                 const int32_t* __restrict__ items_wh, float* __restrict__ policy, float* __restrict__ value,
+                 long long* prof) {
     using namespace bpptc;
     extern __shared__ __align__(1024) unsigned char arena[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -250,12 +252,15 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     cx.bar = smem_u32(&s_bar);
     cx.phase = 0;
     cx.wbuf = wbuf;
+    for (int i = 0; i < 8; ++i) cx.prof[i] = 0;
+    const long long t_start = clock64();
     const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
     const int S = T.S;
     const int ngroups = (B + S - 1) / S;
     const int cin16_0 = (P.Cin + 15) / 16;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const int nvalid = min(S, B - grp * S);
+        long long tq = clock64();
         // ---- level-0 operand planes from the compact records (getBinItem, BinPackingGame.py:118-120)
         const Level& L0 = T.lv[0];
         zero_bytes(regA, 2 * cin16_0 * L0.RT * 16);
@@ -286,6 +291,8 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
                 *reinterpret_cast<uint4*>(regA + ((size_t)p * L0.RT + row) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
+        __syncthreads();
+        TC_PROF(0, tq);
         // ---- three ConvSequences
         const unsigned char* in = regA;
         int cin16 = cin16_0, li = 0;
@@ -297,6 +304,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             conv_layer(T, cx, La, nvalid, cin16, cout, T.wts_umma + T.w_off[li], P.bias + P.conv[li].b_off, in, EPI_CONV,
                        regB, nullptr);
             ++li;
+            tq = clock64();
             const int planes = cout / 8;
             const size_t pb = (size_t)planes * Lb.RT * 16;
             raw = regA;
@@ -305,6 +313,8 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             zero_bytes(regA, (int)(3 * pb));
             __syncthreads();
             pool_level(La, Lb, nvalid, planes, regB, raw, actA);
+            __syncthreads();
+            TC_PROF(5, tq);
             for (int blk = 0; blk < 2; ++blk) {
                 conv_layer(T, cx, Lb, nvalid, cout / 16, cout, T.wts_umma + T.w_off[li], P.bias + P.conv[li].b_off, actA,
                            EPI_RES0, actB, nullptr);
@@ -316,6 +326,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             in = raw;
             cin16 = cout / 16;
         }
+        tq = clock64();
         // ---- heads on the CUDA cores (1.6 % of the FLOPs): flatten -> relu -> fc256 -> relu -> {logits, value}
         const Level& L3 = T.lv[3];
         float* feat = reinterpret_cast<float*>(regB);            // [8][flat]
@@ -340,6 +351,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             float acc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = P.bias[P.b_hidden_off + o];
+#pragma unroll 4
             for (int i = 0; i < P.flat; ++i) {
                 const float wv = __bfloat162float(P.wts[P.fc_hidden_off + (long long)i * HIDDEN + o]);
 #pragma unroll
@@ -353,6 +365,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             float acc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = P.bias[P.b_logits_off + o];
+#pragma unroll 4
             for (int i = 0; i < HIDDEN; ++i) {
                 const float wv = __bfloat162float(P.wts[P.fc_logits_off + (long long)i * P.A + o]);
 #pragma unroll
@@ -381,11 +394,24 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             if (lane == 0) value[b] = tanhf(acc + P.bias[P.b_value_off]);
         }
         __syncthreads();
+        TC_PROF(6, tq);
+    }
+    if (prof && blockIdx.x == 0 && tid == 0) {
+        cx.prof[7] = clock64() - t_start;
+        for (int i = 0; i < 8; ++i) prof[i] = cx.prof[i];
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"((uint32_t)TMEM_COLS));
+}
+
+// shared-memory budget of the tensor-core kernel: ~110 KB lets two CTAs share an SM so that one CTA's epilogue overlaps
+// the other's MMAs (BPP_TC_SMEM_KB overrides, for experiments)
+int tc_smem_cap() {
+    const char* e = getenv("BPP_TC_SMEM_KB");
+    const int kb = e ? atoi(e) : 110;
+    return kb * 1024;
 }
 
 uint16_t f32_to_bf16_rne(float f) {
@@ -412,6 +438,7 @@ struct bpp_net {
     bpptc::TcParams T;
     __nv_bfloat16* d_wts_umma = nullptr;
     long long umma_elems = 0;
+    long long* d_prof = nullptr;  // phase timers of CTA 0 (bpp_net_profile)
     bool tc_ok = false;
     bool committed = false;
     int smem_bytes = 0;
@@ -533,7 +560,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             T.regB_bytes = (int)((b + 4096 + 1023) & ~1023LL);  // + slack: the last tile's shifted windows over-read
             T.wbuf_bytes = (wmax + 1023) & ~1023;
             T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
-            if (T.smem_bytes <= 200 * 1024 && T.lv[0].RT < 16384) n->tc_ok = true;
+            if (T.smem_bytes <= tc_smem_cap() && T.lv[0].RT < 16384) n->tc_ok = true;
         }
     }
     n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
@@ -548,6 +575,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         return nerr(BPP_E_CUDA, "cannot reserve shared memory for the forward kernel");
     }
     n->T.wts_umma = n->d_wts_umma;
+    if (cudaMalloc(&n->d_prof, 8 * sizeof(long long)) == cudaSuccess) cudaMemset(n->d_prof, 0, 8 * sizeof(long long));
     *out = n;
     return BPP_OK;
 }
@@ -557,6 +585,7 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     cudaFree(n->d_wts);
     cudaFree(n->d_wts32);
     cudaFree(n->d_wts_umma);
+    cudaFree(n->d_prof);
     cudaFree(n->d_bias);
     delete n;
     return BPP_OK;
@@ -645,6 +674,13 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
     return BPP_OK;
 }
 
+extern "C" int bpp_net_profile(bpp_net* n, int64_t cycles_host[8]) {
+    if (!n || !cycles_host || !n->d_prof) return nerr(BPP_E_INVALID, "null argument");
+    if (cudaMemcpy(cycles_host, n->d_prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return nerr(BPP_E_CUDA, "profile copy failed");
+    return BPP_OK;
+}
+
 extern "C" int bpp_net_set_precision(bpp_net* n, int mode) {
     if (!n || (mode != BPP_NET_BF16 && mode != BPP_NET_FP32 && mode != BPP_NET_BF16_SIMT))
         return nerr(BPP_E_INVALID, "unknown precision mode");
@@ -664,9 +700,10 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (n->precision == BPP_NET_BF16 && n->tc_ok) {
         const int groups = (B + n->T.S - 1) / n->T.S;
-        const int g2 = groups < 148 ? groups : 148;
+        const int g2 = groups < 296 ? groups : 296;
         k_net_forward_tc<<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(n->P, n->T, B, count_dev, recs_dev, game_dev,
-                                                                        items_wh_dev, policy_out_dev, value_out_dev);
+                                                                        items_wh_dev, policy_out_dev, value_out_dev,
+                                                                        n->d_prof);
     } else if (n->precision == BPP_NET_FP32)
         k_net_forward<true><<<grid, NET_THREADS, n->smem_bytes, st>>>(n->P, B, count_dev, recs_dev, game_dev, items_wh_dev,
                                                                       policy_out_dev, value_out_dev);

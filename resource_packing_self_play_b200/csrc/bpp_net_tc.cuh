@@ -125,7 +125,10 @@ struct Ctx {
     uint32_t bar;       // mbarrier shared address
     uint32_t phase;
     unsigned char* wbuf;
+    long long prof[8];  // optional phase timers (thread 0): 0 input, 1 weights, 2 mma issue, 3 mma wait, 4 epilogue,
+                        // 5 pool+zero, 6 heads, 7 total
 };
+#define TC_PROF(slot, t0) do { if (threadIdx.x == 0) { const long long _t = clock64(); cx.prof[slot] += _t - (t0); (t0) = _t; } } while (0)
 
 // One 3x3 convolution at level L: in_planes (cin16*2 planes of stride RT*16 bytes) -> epilogue `kind`.
 //   EPI_CONV: out0 <- bf16(acc + bias)                       (raw conv output, to be pooled)
@@ -136,6 +139,7 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
                                            const unsigned char* in_planes, int kind, unsigned char* out0,
                                            unsigned char* raw) {
     const int tid = threadIdx.x;
+    long long tp = clock64();
     // stage this layer's weights (already in the UMMA B layout) into shared memory
     const int wbytes = 9 * cin16 * 2 * cout * 16;
     {
@@ -145,6 +149,7 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
     }
     fence_proxy_async();  // generic-proxy writes (weights, previous epilogue) -> visible to the tensor core's async proxy
     __syncthreads();
+    TC_PROF(1, tp);
     const uint32_t idesc = umma_idesc(cout);
     const uint32_t a_base = smem_u32(in_planes);
     const uint32_t w_base = smem_u32(cx.wbuf);
@@ -154,22 +159,29 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         if (t * 128 >= rows_valid) break;  // whole tile belongs to absent samples (partial last group)
         if (tid == 0) {
             tc_fence_after();
+            // descriptors differ only in their 14-bit start-address field (16-byte units): one 64-bit add per MMA
+            const uint64_t a0 = umma_desc(a_base + (uint32_t)(L.guard + t * 128) * 16u, (uint32_t)L.RT, 8u);
+            const uint64_t b0 = umma_desc(w_base, (uint32_t)cout, 8u);
+            const long long a_kc = (long long)(2u * plane_b >> 4), b_blk = (long long)(2 * cout);
             uint32_t acc = 0;
+            long long bi = 0;
+#pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                const int off = (tap / 3 - 1) * L.wp + (tap % 3 - 1);
+                const long long a_tap = (long long)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
                 for (int kc = 0; kc < cin16; ++kc) {
-                    const uint32_t a_addr = a_base + (uint32_t)(2 * kc) * plane_b + (uint32_t)(L.guard + t * 128 + off) * 16u;
-                    const uint32_t b_addr = w_base + (uint32_t)(tap * cin16 + kc) * (uint32_t)(2 * cout * 16);
-                    umma_bf16(cx.tmem, umma_desc(a_addr, (uint32_t)L.RT, 8u), umma_desc(b_addr, (uint32_t)cout, 8u), idesc,
+                    umma_bf16(cx.tmem, (uint64_t)((long long)a0 + a_tap + kc * a_kc), (uint64_t)((long long)b0 + bi), idesc,
                               acc);
                     acc = 1;
+                    bi += b_blk;
                 }
             }
             umma_commit(cx.bar);
         }
+        TC_PROF(2, tp);
         mbar_wait(cx.bar, cx.phase);
         cx.phase ^= 1u;
         tc_fence_after();
+        TC_PROF(3, tp);
         // ---- epilogue: thread tid owns output row t*128 + tid
         const int rl = t * 128 + tid;
         const int j = rl / L.P, q = rl - j * L.P;
@@ -208,6 +220,7 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         }
         tc_fence_before();
         __syncthreads();  // TMEM accumulator is free again; epilogue stores are ordered before the next layer's fence
+        TC_PROF(4, tp);
     }
 }
 

@@ -105,6 +105,12 @@ class DeviceNet:
         call("bpp_net_set_precision", self._h, {"bf16": 0, "fp32": 1, "bf16_simt": 2}[mode])
         self.precision = mode
 
+    def profile(self):
+        arr = (C.c_int64 * 8)()
+        call("bpp_net_profile", self._h, arr)
+        keys = ["input", "weights", "mma_issue", "mma_wait", "epilogue", "pool", "heads", "total"]
+        return {k: int(v) for k, v in zip(keys, arr)}
+
     def load_state_dict(self, state_dict):
         for name, t in state_dict.items():
             a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
