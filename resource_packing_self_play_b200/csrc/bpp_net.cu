@@ -232,13 +232,15 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
                  long long* prof) {
     using namespace bpptc;
     extern __shared__ __align__(1024) unsigned char arena[];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[MAX_BARS];
+    __shared__ uint32_t s_rec[8][32];
+    __shared__ int s_it[8][BPP_MAX_ITEMS][2];
     __shared__ uint32_t s_tmem;
     unsigned char* regA = arena;
     unsigned char* regB = arena + T.regA_bytes;
     unsigned char* wbuf = regB + T.regB_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) mbar_init(smem_u32(&s_bar), 1);
+    if (tid < MAX_BARS) mbar_init(smem_u32(&s_bar[tid]), 1);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "r"((uint32_t)TMEM_COLS));
@@ -249,7 +251,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     tc_fence_after();
     Ctx cx;
     cx.tmem = s_tmem;
-    cx.bar = smem_u32(&s_bar);
+    cx.bar = smem_u32(&s_bar[0]);
     cx.phase = 0;
     cx.wbuf = wbuf;
     for (int i = 0; i < 8; ++i) cx.prof[i] = 0;
@@ -264,6 +266,13 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         // ---- level-0 operand planes from the compact records (getBinItem, BinPackingGame.py:118-120)
         const Level& L0 = T.lv[0];
         zero_bytes(regA, 2 * cin16_0 * L0.RT * 16);
+        for (int i = tid; i < nvalid * 32; i += TC_THREADS) s_rec[i >> 5][i & 31] = recs[(size_t)(grp * S + (i >> 5)) * 32 + (i & 31)];
+        for (int i = tid; i < nvalid * P.N * 2; i += TC_THREADS) {
+            const int j = i / (P.N * 2), r = i - j * P.N * 2;
+            const int b = grp * S + j;
+            const int g = game ? game[b] : b;
+            s_it[j][r >> 1][r & 1] = items_wh[(size_t)g * P.N * 2 + r];
+        }
         __syncthreads();
         {
             const int hw = P.H * P.W, nplanes = 2 * cin16_0;
@@ -273,18 +282,14 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
                 const int j = r / hw;
                 r -= j * hw;
                 const int y = r / P.W, x = r - y * P.W;
-                const int b = grp * S + j;
-                const uint32_t* rec = recs + (size_t)b * 32;
-                const int g = game ? game[b] : b;
-                const int32_t* it = items_wh + (size_t)g * P.N * 2;
-                const uint32_t rem = rec[BPP_REC_REM];
+                const uint32_t rem = s_rec[j][BPP_REC_REM];
                 uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int c = p * 8 + k;
                     bool on = false;
-                    if (c == 0) on = (rec[y] >> x) & 1u;
-                    else if (c <= P.N) on = ((rem >> (c - 1)) & 1u) && y < it[(c - 1) * 2 + 1] && x < it[(c - 1) * 2];
+                    if (c == 0) on = (s_rec[j][y] >> x) & 1u;
+                    else if (c <= P.N) on = ((rem >> (c - 1)) & 1u) && y < s_it[j][c - 1][1] && x < s_it[j][c - 1][0];
                     if (on) w[k >> 1] |= (k & 1) ? 0x3f800000u : 0x00003f80u;  // bf16 1.0
                 }
                 const size_t row = (size_t)L0.guard + (size_t)j * L0.P + (size_t)(y + 1) * L0.wp + (x + 1);
@@ -347,32 +352,53 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             feat[idx] = v;
         }
         __syncthreads();
-        for (int o = tid; o < HIDDEN; o += TC_THREADS) {
-            float acc[8];
+        {   // hidden layer: thread -> outputs 2*tid, 2*tid+1 (one coalesced bf16x2 load per input), 8 leaves at once
+            const int o = 2 * tid;
+            float a0[8], a1[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = P.bias[P.b_hidden_off + o];
-#pragma unroll 4
+            for (int j = 0; j < 8; ++j) { a0[j] = P.bias[P.b_hidden_off + o]; a1[j] = P.bias[P.b_hidden_off + o + 1]; }
+            const uint32_t* wp32 = reinterpret_cast<const uint32_t*>(P.wts + P.fc_hidden_off) + tid;
+#pragma unroll 16
             for (int i = 0; i < P.flat; ++i) {
-                const float wv = __bfloat162float(P.wts[P.fc_hidden_off + (long long)i * HIDDEN + o]);
+                const uint32_t wv = __ldg(wp32 + (size_t)i * (HIDDEN / 2));
+                const float w0 = bf16_lo(wv), w1 = bf16_hi(wv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(feat[j * P.flat + i], wv, acc[j]);
+                for (int j = 0; j < 8; ++j) {
+                    const float f = feat[j * P.flat + i];
+                    a0[j] = fmaf(f, w0, a0[j]);
+                    a1[j] = fmaf(f, w1, a1[j]);
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hid[j * HIDDEN + o] = act_round<false>(fmaxf(acc[j], 0.f));
+            for (int j = 0; j < 8; ++j) {
+                hid[j * HIDDEN + o] = act_round<false>(fmaxf(a0[j], 0.f));
+                hid[j * HIDDEN + o + 1] = act_round<false>(fmaxf(a1[j], 0.f));
+            }
         }
         __syncthreads();
-        for (int o = tid; o < P.A; o += TC_THREADS) {
-            float acc[8];
+        if (2 * tid < T.A_pad) {  // logits: padded [256][A_pad] copy of the weights, outputs 2*tid, 2*tid+1
+            const int o = 2 * tid;
+            float a0[8], a1[8];
+            const float b0 = P.bias[P.b_logits_off + o], b1 = o + 1 < P.A ? P.bias[P.b_logits_off + o + 1] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = P.bias[P.b_logits_off + o];
-#pragma unroll 4
+            for (int j = 0; j < 8; ++j) { a0[j] = b0; a1[j] = b1; }
+            const uint32_t* wp32 = reinterpret_cast<const uint32_t*>(T.wts_logits_pad) + tid;
+#pragma unroll 16
             for (int i = 0; i < HIDDEN; ++i) {
-                const float wv = __bfloat162float(P.wts[P.fc_logits_off + (long long)i * P.A + o]);
+                const uint32_t wv = __ldg(wp32 + (size_t)i * (T.A_pad / 2));
+                const float w0 = bf16_lo(wv), w1 = bf16_hi(wv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(hid[j * HIDDEN + i], wv, acc[j]);
+                for (int j = 0; j < 8; ++j) {
+                    const float f = hid[j * HIDDEN + i];
+                    a0[j] = fmaf(f, w0, a0[j]);
+                    a1[j] = fmaf(f, w1, a1[j]);
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) lg[j * P.A + o] = acc[j];
+            for (int j = 0; j < 8; ++j) {
+                lg[j * P.A + o] = a0[j];
+                if (o + 1 < P.A) lg[j * P.A + o + 1] = a1[j];
+            }
         }
         __syncthreads();
         for (int j = warp; j < nvalid; j += TC_THREADS / 32) {  // one warp per leaf: value head + softmax
@@ -437,6 +463,7 @@ struct bpp_net {
     int precision = 0;  // BPP_NET_BF16
     bpptc::TcParams T;
     __nv_bfloat16* d_wts_umma = nullptr;
+    __nv_bfloat16* d_wts_logits_pad = nullptr;
     long long umma_elems = 0;
     long long* d_prof = nullptr;  // phase timers of CTA 0 (bpp_net_profile)
     bool tc_ok = false;
@@ -558,7 +585,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             T.S = S;
             T.regA_bytes = (int)((a + 1023) & ~1023LL);
             T.regB_bytes = (int)((b + 4096 + 1023) & ~1023LL);  // + slack: the last tile's shifted windows over-read
-            T.wbuf_bytes = (wmax + 1023) & ~1023;
+            T.wbuf_bytes = (wmax + 256 + 1023) & ~1023;  // + the layer's bias behind the weights
             T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
             if (T.smem_bytes <= tc_smem_cap() && T.lv[0].RT < 16384) n->tc_ok = true;
         }
@@ -575,6 +602,13 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         return nerr(BPP_E_CUDA, "cannot reserve shared memory for the forward kernel");
     }
     n->T.wts_umma = n->d_wts_umma;
+    n->T.A_pad = (P.A + 1) & ~1;
+    if (cudaMalloc(&n->d_wts_logits_pad, (size_t)HIDDEN * n->T.A_pad * 2) != cudaSuccess) {
+        cudaGetLastError();
+        delete n;
+        return nerr(BPP_E_NOMEM, "cudaMalloc of the network parameters failed");
+    }
+    n->T.wts_logits_pad = n->d_wts_logits_pad;
     if (cudaMalloc(&n->d_prof, 8 * sizeof(long long)) == cudaSuccess) cudaMemset(n->d_prof, 0, 8 * sizeof(long long));
     *out = n;
     return BPP_OK;
@@ -585,6 +619,7 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     cudaFree(n->d_wts);
     cudaFree(n->d_wts32);
     cudaFree(n->d_wts_umma);
+    cudaFree(n->d_wts_logits_pad);
     cudaFree(n->d_prof);
     cudaFree(n->d_bias);
     delete n;
@@ -663,8 +698,15 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
                             }
             ++li;
         }
+    std::vector<uint16_t> wlp((size_t)HIDDEN * n->T.A_pad, 0);
+    {
+        const std::vector<float>& src2 = n->host["logits_fc.weight"];  // [A][256]
+        for (int o = 0; o < P.A; ++o)
+            for (int i = 0; i < HIDDEN; ++i) wlp[(size_t)i * n->T.A_pad + o] = f32_to_bf16_rne(src2[(size_t)o * HIDDEN + i]);
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (cudaMemcpyAsync(n->d_wts_umma, wu.data(), wu.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+    if (cudaMemcpyAsync(n->d_wts_logits_pad, wlp.data(), wlp.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(n->d_wts_umma, wu.data(), wu.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts, w.data(), w.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||

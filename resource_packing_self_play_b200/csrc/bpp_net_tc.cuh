@@ -24,7 +24,8 @@
 namespace bpptc {
 
 constexpr int TC_THREADS = 128;
-constexpr int TMEM_COLS = 32;
+constexpr int TMEM_COLS = 256;   // two CTAs per SM share the 512 columns; up to 256 / Cout output tiles in flight
+constexpr int MAX_BARS = 16;
 
 struct Level {
     int h, w, hp, wp, P, guard, RT, ntiles;  // RT = rows of one plane = guard + S*P + guard
@@ -39,6 +40,8 @@ struct TcParams {
     int smem_bytes;
     long long w_off[15];   // element offsets of each conv layer in wts_umma
     const __nv_bfloat16* wts_umma;
+    int A_pad;                             // action size rounded up to even
+    const __nv_bfloat16* wts_logits_pad;   // logits weights [256][A_pad] (bf16x2 loads)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -122,8 +125,8 @@ enum { EPI_CONV = 0, EPI_RES0 = 1, EPI_RES1 = 2 };
 
 struct Ctx {
     uint32_t tmem;      // TMEM base (lane 0, column 0)
-    uint32_t bar;       // mbarrier shared address
-    uint32_t phase;
+    uint32_t bar;       // shared address of mbarrier[0] (MAX_BARS barriers, 8 bytes apart)
+    uint32_t phase;     // one parity bit per barrier
     unsigned char* wbuf;
     long long prof[8];  // optional phase timers (thread 0): 0 input, 1 weights, 2 mma issue, 3 mma wait, 4 epilogue,
                         // 5 pool+zero, 6 heads, 7 total
@@ -147,6 +150,8 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         uint4* dst = reinterpret_cast<uint4*>(cx.wbuf);
         for (int i = tid; i < wbytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
     }
+    float* s_bias = reinterpret_cast<float*>(cx.wbuf + wbytes);  // Cout floats right behind the staged weights
+    if (tid < cout) s_bias[tid] = __ldg(bias + tid);
     fence_proxy_async();  // generic-proxy writes (weights, previous epilogue) -> visible to the tensor core's async proxy
     __syncthreads();
     TC_PROF(1, tp);
@@ -155,31 +160,40 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
     const uint32_t w_base = smem_u32(cx.wbuf);
     const uint32_t plane_b = (uint32_t)L.RT * 16u;
     const int rows_valid = nvalid * L.P;
-    for (int t = 0; t < L.ntiles; ++t) {
-        if (t * 128 >= rows_valid) break;  // whole tile belongs to absent samples (partial last group)
-        if (tid == 0) {
-            tc_fence_after();
+    const int nt = min(L.ntiles, (rows_valid + 127) >> 7);  // tiles that hold at least one present sample
+    int tpp = TMEM_COLS / cout;                                // tiles in flight per pass
+    if (tpp > MAX_BARS) tpp = MAX_BARS;
+    for (int t0 = 0; t0 < nt; t0 += tpp) {
+      const int nb = min(tpp, nt - t0);
+      // ---- issue: ONE thread queues the MMAs of all nb tiles (each tile into its own TMEM columns, each followed by a
+      // commit to its own mbarrier); the tensor core drains the queue while the 128 threads run the epilogues below
+      if (tid == 0) {
+        tc_fence_after();
+        const uint64_t b0 = umma_desc(w_base, (uint32_t)cout, 8u);
+        const long long a_kc = (long long)(2u * plane_b >> 4), b_blk = (long long)(2 * cout);
+        for (int b = 0; b < nb; ++b) {
             // descriptors differ only in their 14-bit start-address field (16-byte units): one 64-bit add per MMA
-            const uint64_t a0 = umma_desc(a_base + (uint32_t)(L.guard + t * 128) * 16u, (uint32_t)L.RT, 8u);
-            const uint64_t b0 = umma_desc(w_base, (uint32_t)cout, 8u);
-            const long long a_kc = (long long)(2u * plane_b >> 4), b_blk = (long long)(2 * cout);
+            const uint64_t a0 = umma_desc(a_base + (uint32_t)(L.guard + (t0 + b) * 128) * 16u, (uint32_t)L.RT, 8u);
             uint32_t acc = 0;
             long long bi = 0;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const long long a_tap = (long long)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
                 for (int kc = 0; kc < cin16; ++kc) {
-                    umma_bf16(cx.tmem, (uint64_t)((long long)a0 + a_tap + kc * a_kc), (uint64_t)((long long)b0 + bi), idesc,
-                              acc);
+                    umma_bf16(cx.tmem + (uint32_t)(b * cout), (uint64_t)((long long)a0 + a_tap + kc * a_kc),
+                              (uint64_t)((long long)b0 + bi), idesc, acc);
                     acc = 1;
                     bi += b_blk;
                 }
             }
-            umma_commit(cx.bar);
+            umma_commit(cx.bar + 8u * (uint32_t)b);
         }
-        TC_PROF(2, tp);
-        mbar_wait(cx.bar, cx.phase);
-        cx.phase ^= 1u;
+      }
+      TC_PROF(2, tp);
+      for (int b = 0; b < nb; ++b) {
+        const int t = t0 + b;
+        mbar_wait(cx.bar + 8u * (uint32_t)b, (cx.phase >> b) & 1u);
+        cx.phase ^= 1u << b;
         tc_fence_after();
         TC_PROF(3, tp);
         // ---- epilogue: thread tid owns output row t*128 + tid
@@ -188,13 +202,13 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         const int yp = q / L.wp, xp = q - yp * L.wp;
         const bool interior = rl < rows_valid && yp >= 1 && yp <= L.h && xp >= 1 && xp <= L.w;
         const size_t rowb = (size_t)(L.guard + rl) * 16;
-        const uint32_t taddr = cx.tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+        const uint32_t taddr = cx.tmem + ((uint32_t)((tid >> 5) * 32) << 16) + (uint32_t)(b * cout);
         for (int c0 = 0; c0 < cout; c0 += 16) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);  // warp-collective: executed by every lane
             if (interior) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += __ldg(bias + c0 + i);
+                for (int i = 0; i < 16; ++i) v[i] += s_bias[c0 + i];
 #pragma unroll
                 for (int hp8 = 0; hp8 < 2; ++hp8) {
                     const int plane = (c0 >> 3) + hp8;
@@ -218,9 +232,10 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
                 }
             }
         }
-        tc_fence_before();
-        __syncthreads();  // TMEM accumulator is free again; epilogue stores are ordered before the next layer's fence
         TC_PROF(4, tp);
+      }
+      tc_fence_before();
+      __syncthreads();  // TMEM columns are free again; epilogue stores are ordered before the next layer's proxy fence
     }
 }
 
