@@ -368,6 +368,148 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# secondary workloads (not the headline): lockstep self-play with the REAL policy/value net as leaf evaluator
+# (BASELINE.json configs[2]: 20x20 bin, numMCTSSims = 200, bf16 tensor-core forward; "real15" = the default instance)
+NET_FLOPS = {(15, 15, 10): 4394592, (20, 20, 10): 7249920}
+
+
+def _cpu_real_episode(ep_index, sims, Wb, Hb, net):
+    from oracle import bpp_oracle as O
+    rs = np.random.RandomState(77000 + ep_index // 20)
+    gh = int(rs.randint(2, Hb + 1))
+    items = O.OracleItemsGenerator(Wb, gh, N).items_generator(1000 + ep_index)
+    g = O.OracleGame(Wb, Hb, N, 1)
+    m = O.OracleMCTS(g, net, O.dotdict(numMCTSSims=sims, cpuct=CPUCT, alpha=ALPHA))
+    rng = np.random.RandomState(ep_index)
+    board, planes = g.getInitBoard(), g.getInitItems(items)
+    moves = 0
+    while True:
+        state = g.getBinItem(board, planes)
+        pi = m.getActionProb(state, Wb * gh, [])
+        a = int(rng.choice(len(pi), p=pi))
+        board, planes = g.getNextState(board, a, planes)
+        moves += 1
+        if g.getGameEnded(g.getBinItem(board, planes), Wb * gh, [], ALPHA)[0] != 0:
+            return moves * sims
+
+
+def run_real_arm(args):
+    import torch
+    from resource_packing_self_play_b200 import _lib
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    from resource_packing_self_play_b200.mcts import BatchedMCTS
+    from resource_packing_self_play_b200.nnet import BinPackingNNet, NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+
+    Wb, Hb = (20, 20) if args.workload == "real20" else (15, 15)
+    G = args.games
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+
+    class Gm:
+        bin_width, bin_height, num_items = Wb, Hb, N
+
+        def getBoardSize(self):
+            return (Hb, Wb)
+
+        def getActionSize(self):
+            return Wb * N
+    margs = dotdict(numMCTSSims=args.sims, cpuct=CPUCT, alpha=ALPHA, num_items=N, num_bins=1, cuda=True)
+    torch.manual_seed(0)
+    net = NNetWrapper(Gm(), margs, max_batch=G, precision="bf16")
+    bm = BatchedMCTS(Gm(), net, margs, G)
+    gen = ItemsGenerator(Wb, Hb, N)
+
+    def instances(k):
+        idx = np.arange(k * G, (k + 1) * G)
+        hts = np.array([np.random.RandomState(77000 + int(b)).randint(2, Hb + 1) for b in idx // 20], dtype=np.int32)
+        return gen.items_batch(1000 + idx, hts), (Wb * hts).astype(np.int32)
+    inst = [instances(k) for k in range(args.warmup + args.steps)]
+    fwd_events = []
+    orig_forward = net.dnet.forward
+
+    def timed_forward(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_forward(*a, **kw)
+        e1.record()
+        fwd_events.append((e0, e1))
+        return r
+
+    def step(k, timed):
+        items, area = inst[k]
+        bm.reset(items, area, [])
+        net.dnet.forward = timed_forward if timed else orig_forward
+        out = None
+        for m in range(N):
+            counts = bm.search()
+            act = bm.eng.choose(_lib.CHOOSE_SAMPLE, seed=7 + k)
+            bm.eng.advance(act)
+            out = counts
+        return out
+    for k in range(args.warmup):
+        step(k, False)
+    bm.eng.check()
+    bm.eng.stats(reset=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(args.steps):
+        step(args.warmup + k, True)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    clocks = sampler.stop()
+    bm.eng.check()
+    st = bm.eng.stats(reset=True)
+    fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_events)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    flops = NET_FLOPS[(Wb, Hb, N)]
+    achieved = st["expansions"] * flops / (fwd_ms * 1e-3) / 1e12
+    line = {"metric": METRIC, "value": st["sims"] / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 (net) / f64 (tree)", "data": "synthetic",
+            "config": {"workload": f"configs[2]-style: {Wb}x{Hb} bin, 10 items, numMCTSSims={args.sims}, real "
+                                   f"policy/value net (random init, seed 0) in bf16 on tcgen05, {G} lockstep games",
+                       "games_per_gpu": G},
+            "episodes_per_sec": args.steps * G / (ms * 1e-3), "leaf_evals_per_sec": st["expansions"] / (ms * 1e-3),
+            "lockstep_steps": bm.steps, "gpu_launches": st["launches"] + len(fwd_events),
+            "roofline": {"bound": "tensor", "kernel": "k_net_forward_tc", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "flop_per_eval": flops, "evals_per_launch": st["expansions"] / max(1, len(fwd_events)),
+                         "kernel_share_of_step": fwd_ms / ms,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback"},
+            "clocks": clocks}
+    if not args.no_cpu:
+        cpu_net = BinPackingNNet(Gm(), margs)
+        cpu_net.load_state_dict({k: v.cpu() for k, v in net.nnet.state_dict().items()})
+        cpu_net.eval()
+
+        class CpuNet:
+            def predict(self, board):
+                with torch.no_grad():
+                    lp, v = cpu_net(torch.from_numpy(board.astype(np.float32))[None])
+                return torch.exp(lp)[0].numpy(), v[0].numpy()
+        t = time.perf_counter()
+        n = 0
+        ep = 0
+        while time.perf_counter() - t < args.cpu_seconds:
+            n += _cpu_real_episode(ep, args.sims, Wb, Hb, CpuNet())
+            ep += 1
+        dt = time.perf_counter() - t
+        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{ep} episodes in {dt:.1f} s; oracle port + fp32 torch net on CPU"}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -379,9 +521,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--edge-frac", type=float, default=1.0, help="edge pool as a fraction of the worst case")
+    ap.add_argument("--workload", default="stub", choices=["stub", "real15", "real20"],
+                    help="stub = headline (configs[1]); real15/real20 = real net as leaf evaluator (secondary)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload != "stub":
+        run_real_arm(args)
     else:
         run_gpu_arm(args)
 

@@ -127,20 +127,24 @@ class BatchedMCTS:
             tie = np.where(np.random.random(self.G) < 0.5, 1, -1).astype(np.int8)
         self.eng.reset(items_wh, total_area, bl, tie)
 
-    def search(self):
-        """numMCTSSims simulations for every running game; the leaves of a step are evaluated in one batched forward
-        straight from the engine's leaf buffers (no copies, nothing leaves the device but the leaf count)"""
+    def search(self, chunk=8):
+        """numMCTSSims simulations for every running game.  One lockstep step = select (descents + terminal backups
+        until every game parks one unexpanded leaf) -> ONE batched forward over the parked leaves, read straight
+        from the engine's leaf buffers -> expand + backup.  The leaf count stays on the device (the evaluator and the
+        expansion kernel read it there); the host only polls it every `chunk` steps to learn that the move is done."""
         eng, net = self.eng, self.nnet.dnet
-        _, game_ptr, recs_ptr = eng.leaf_buffers()
-        pol = torch.empty((self.G, eng.A), dtype=torch.float32, device=eng.device)
-        val = torch.empty(self.G, dtype=torch.float32, device=eng.device)
+        count_ptr, game_ptr, recs_ptr = eng.leaf_buffers()
+        if getattr(self, "_pol", None) is None:
+            self._pol = torch.empty((self.G, eng.A), dtype=torch.float32, device=eng.device)
+            self._val = torch.empty(self.G, dtype=torch.float32, device=eng.device)
         eng.begin_move()
         while True:
-            eng.select()
-            n = eng.leaf_count()
-            if n == 0:
+            for _ in range(chunk):
+                eng.select()
+                net.forward(recs_ptr, eng.items_wh, game=game_ptr, count_dev=count_ptr, policy_out=self._pol,
+                            value_out=self._val, batch=self.G)
+                eng.expand_backup(self._pol, self._val)
+                self.steps += 1
+            if eng.leaf_count() == 0:  # the last select parked nothing: every game has done its simulations
                 break
-            net.forward(recs_ptr, eng.items_wh, game=game_ptr, policy_out=pol, value_out=val, batch=n)
-            eng.expand_backup(pol, val)
-            self.steps += 1
         return eng.root_counts()
