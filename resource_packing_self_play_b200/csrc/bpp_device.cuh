@@ -69,51 +69,69 @@ __device__ __forceinline__ uint32_t strip_mask(int w, int x, unsigned wmask) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Valid-move mask.  s_occ[0..H) = occupancy rows (shared, this warp's strip), s_items[i] = w | h << 8.
-// Action a = item*W + x is handled by lane a % 32 in round a / 32; the ballot of a round IS word a/32 of the mask.
-// (The row loop carries no cross-lane dependency and its shared-memory reads are loop-invariant addresses, so the
-// per-warp latency - which bounds this kernel at ~7 warps per scheduler - stays short; an item-major variant with
-// prefix sums and early-exit votes executed fewer instructions but ran 10 % slower.)
+// Valid-move mask.  s_occ[0..H) = occupancy rows (shared, this warp's 16-byte aligned strip), s_items[i] = w | h << 8,
+// s_tab = 16-entry scratch.  The (remaining item, column x) pairs are enumerated densely: pair p = k*W + x, k = rank of
+// the item among the remaining ones, so late in an episode (few items left) only ceil(nrem*W/32) rounds run.
 //   (A) cell-count test (BinPackingLogic.py:89): occupied cells of the strip [:, x:x+w] <= w*(H-h);
 //   (B) left adjacency (BinPackingLogic.py:63-70): x == 0, or the cell left of the strip is occupied in the first strip
 //       row that is completely empty (row H-1 if none: the reference's loop variable keeps its last value).
-// Returns word k in lane k (0 elsewhere); also stores the words to s_vw[0..MAX_AW).
+// HC > 0 = compile-time bin height: the rows are held in registers (vector shared loads) and the row sweep is fully
+// unrolled; HC == 0 = generic.  The sweep carries no cross-lane dependency, which keeps the per-warp latency short
+// (an item-major variant with prefix sums and early-exit votes executed fewer instructions but ran 10 % slower).
+// Returns word k of the A-bit mask in lane k (0 elsewhere); also leaves the words in s_vw[0..MAX_AW).
+template <int HC>
 __device__ __forceinline__ uint32_t valid_words(const Geom& g, const uint32_t* s_occ, const uint16_t* s_items,
-                                                uint32_t rem, int lane, uint32_t* s_vw) {
-    uint32_t mine = 0;
-    for (int k = 0; k < g.AW; ++k) {
-        const int a0 = k * 32;
-        const int i0 = div_w(g, a0);
-        int i1 = div_w(g, a0 + 31);
-        if (i1 > g.N - 1) i1 = g.N - 1;
-        const uint32_t range = ((2u << i1) - 1u) & ~((1u << i0) - 1u);
-        uint32_t b = 0;
-        if (rem & range) {  // warp-uniform: skip rounds whose items are all placed
-            const int a = a0 + lane;
-            const int i = div_w(g, a);
-            const int x = a - i * g.W;
-            bool ok = false;
-            if (a < g.A && ((rem >> i) & 1u)) {
-                const int w = s_items[i] & 0xff, h = s_items[i] >> 8;
-                if (x + w <= g.W) {
-                    const uint32_t m = strip_mask(w, x, g.wmask);
-                    int cnt = 0, t = -1;
-                    for (int r = 0; r < g.H; ++r) {
+                                                uint32_t rem, int lane, uint32_t* s_vw, uint8_t* s_tab) {
+    const int H = HC ? HC : g.H;
+    constexpr int NR = HC ? ((HC + 3) & ~3) : 4;
+    uint32_t occ[NR];
+    if (HC) {
+#pragma unroll
+        for (int r4 = 0; r4 < NR; r4 += 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(s_occ + r4);
+            occ[r4] = v.x; occ[r4 + 1] = v.y; occ[r4 + 2] = v.z; occ[r4 + 3] = v.w;
+        }
+    }
+    rem &= (g.N >= 32) ? 0xffffffffu : ((1u << g.N) - 1u);
+    if (lane < MAX_AW) s_vw[lane] = 0u;
+    if ((rem >> lane) & 1u) s_tab[__popc(rem & ((1u << lane) - 1u))] = (uint8_t)lane;  // rank -> item index
+    __syncwarp();
+    const int npairs = __popc(rem) * g.W;
+    for (int p0 = 0; p0 < npairs; p0 += 32) {
+        const int p = p0 + lane;
+        if (p < npairs) {
+            const int k = div_w(g, p);
+            const int x = p - k * g.W;
+            const int i = s_tab[k];
+            const int w = s_items[i] & 0xff, h = s_items[i] >> 8;
+            if (x + w <= g.W) {
+                const uint32_t m = strip_mask(w, x, g.wmask);
+                int cnt = 0;
+                uint32_t emp = 0;  // bit r: strip row r is completely empty
+                if (HC) {
+#pragma unroll
+                    for (int r = 0; r < HC; ++r) {
+                        const uint32_t c = occ[r] & m;
+                        cnt += __popc(c);
+                        emp |= (c == 0u ? 1u : 0u) << r;
+                    }
+                } else {
+                    for (int r = 0; r < H; ++r) {
                         const uint32_t c = s_occ[r] & m;
                         cnt += __popc(c);
-                        if (c == 0 && t < 0) t = r;
+                        emp |= (c == 0u ? 1u : 0u) << r;
                     }
-                    if (t < 0) t = g.H - 1;
-                    ok = (cnt <= w * (g.H - h)) && (x == 0 || ((s_occ[t] >> (x - 1)) & 1u));
+                }
+                const int t = emp ? __ffs(emp) - 1 : H - 1;
+                if ((cnt <= w * (H - h)) && (x == 0 || ((s_occ[t] >> (x - 1)) & 1u))) {
+                    const int a = i * g.W + x;
+                    atomicOr(&s_vw[a >> 5], 1u << (a & 31));
                 }
             }
-            b = __ballot_sync(FULL, ok);
         }
-        if (lane == k) mine = b;
     }
-    if (lane < MAX_AW) s_vw[lane] = mine;
     __syncwarp();
-    return mine;
+    return lane < MAX_AW ? s_vw[lane] : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

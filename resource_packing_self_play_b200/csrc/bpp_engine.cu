@@ -91,10 +91,11 @@ struct Params {
     unsigned long long* stats;  // [8]
 };
 
-struct WarpSmem {
+struct __align__(16) WarpSmem {
     uint32_t occ[32];
     uint32_t vw[MAX_AW];
     uint16_t items[BPP_MAX_ITEMS];
+    uint8_t tab[16];
     double scratch[MAX_LEAVES];
 };
 
@@ -148,16 +149,18 @@ __device__ __forceinline__ void flush_stats(const Params& P, const Stats& st, in
 }
 
 // Find the node of a state (full-key equality, like the dict lookup of MCTS_bpp.py:76-85) or create it.
-__device__ __noinline__ int lookup_or_insert(const Params& P, GameCtx& gm, uint32_t rec, int lane, Stats& st) {
-    const int H = P.geom.H;
+// (scalars instead of `const Params&`: a reference into kernel-parameter space from a non-inlined function would force
+// a 480-byte local copy of Params in every kernel)
+__device__ __noinline__ int lookup_or_insert(int H, int node_cap, uint32_t table_mask, GameCtx& gm, uint32_t rec, int lane,
+                                             Stats& st) {
     const uint32_t h = hash_state(rec, lane, H);
     const uint32_t tag = h >> 20;
-    uint32_t slot = h & P.table_mask;
+    uint32_t slot = h & table_mask;
     for (;;) {
         st.probes++;
         const uint32_t ent = gm.table[slot];
         if (ent == 0u) {
-            if (gm.n_nodes >= P.node_cap) {
+            if (gm.n_nodes >= node_cap) {
                 gm.err = 4;
                 return -1;
             }
@@ -174,7 +177,7 @@ __device__ __noinline__ int lookup_or_insert(const Params& P, GameCtx& gm, uint3
             const bool same = !state_lane(lane, H) || o == rec;
             if (__all_sync(FULL, same)) return cand;
         }
-        slot = (slot + 1u) & P.table_mask;
+        slot = (slot + 1u) & table_mask;
     }
 }
 
@@ -228,13 +231,13 @@ __device__ __forceinline__ bool expand_node(const Params& P, GameCtx& gm, WarpSm
 
 // One simulation (MCTS.search from the root, MCTS_bpp.py:56-139).
 // Returns 0 = finished and backed up, 1 = parked an unexpanded leaf (STUB == 0 only), -1 = pool overflow.
-template <int STUB>
+template <int STUB, int HC>
 __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& sm, int lane, Stats& st) {
     const Geom& ge = P.geom;
     int cur = gm.root_node;
     if (cur < 0) {
         const uint32_t rrec = P.root_rec[(size_t)gm.g * REC_WORDS + lane];
-        cur = lookup_or_insert(P, gm, rrec, lane, st);
+        cur = lookup_or_insert(ge.H, P.node_cap, P.table_mask, gm, rrec, lane, st);
         if (cur < 0) return -1;
         gm.root_node = cur;
     }
@@ -255,7 +258,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
             // first visit of this state: Es (getGameEnded) then, if not terminal, expansion
             sm.occ[lane] = rec;
             __syncwarp();
-            const uint32_t mine = valid_words(ge, sm.occ, sm.items, rem, lane, sm.vw);
+            const uint32_t mine = valid_words<HC>(ge, sm.occ, sm.items, rem, lane, sm.vw, sm.tab);
             if (!__any_sync(FULL, mine != 0u)) {
                 double score;
                 const int r = terminal_value(ge, gm.rc, rec, lane, &score);
@@ -310,7 +313,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
             const int x = act - item * ge.W;
             const int w = sm.items[item] & 0xff, h = sm.items[item] >> 8;
             const uint32_t nrec = apply_move(ge, rec, lane, item, w, h, x);
-            child = lookup_or_insert(P, gm, nrec, lane, st);
+            child = lookup_or_insert(ge.H, P.node_cap, P.table_mask, gm, nrec, lane, st);
             if (child < 0) return -1;
             if (lane == 0) eb.NC[e].y = child;
             __syncwarp();
@@ -326,8 +329,10 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
 // kernels: one warp per game, 4 warps per CTA
 constexpr int WARPS_PER_CTA = 4;
 
-template <int STUB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_search(Params P) {
+// __launch_bounds__(128, 7): 4,096 games = 1,024 CTAs must all be resident at once on 148 SMs (7 CTAs per SM), which caps
+// the kernel at 72 registers per thread; at 80 registers only 6 fit and a second, almost empty wave appears.
+template <int STUB, int HC>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_search(Params P) {
     __shared__ WarpSmem smem[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = blockIdx.x * WARPS_PER_CTA + wid;
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_search(Params P) {
     Stats st = {0, 0, 0, 0, 0, 0};
     int done = P.sims_done[g];
     while (done < P.num_sims) {
-        const int rc = simulate<STUB>(P, gm, sm, lane, st);
+        const int rc = simulate<STUB, HC>(P, gm, sm, lane, st);
         if (rc != 0) break;  // parked leaf (counted when it is expanded) or overflow
         done++;
         st.sims++;
@@ -530,12 +535,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_advance(Params P, const 
     rec = apply_move(ge, rec, lane, item, sm.items[item] & 0xff, sm.items[item] >> 8, x);
     rec = state_lane(lane, ge.H) ? rec : 0u;
     P.root_rec[(size_t)g * REC_WORDS + lane] = rec;
-    gm.root_node = lookup_or_insert(P, gm, rec, lane, st);
+    gm.root_node = lookup_or_insert(ge.H, P.node_cap, P.table_mask, gm, rec, lane, st);
     // getGameEnded on the new root (CoachBPP.py:91)
     sm.occ[lane] = rec;
     __syncwarp();
     const uint32_t nrem = __shfl_sync(FULL, rec, REC_REM);
-    const uint32_t mine = valid_words(ge, sm.occ, sm.items, nrem, lane, sm.vw);
+    const uint32_t mine = valid_words<0>(ge, sm.occ, sm.items, nrem, lane, sm.vw, sm.tab);
     if (!__any_sync(FULL, mine != 0u)) {
         double score;
         const int r = terminal_value(ge, gm.rc, rec, lane, &score);
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_env_valid(EnvArgs E, uin
     uint32_t rec;
     env_load(E, s, lane, sm, rec);
     const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
-    valid_words(E.geom, sm.occ, sm.items, rem, lane, sm.vw);
+    valid_words<0>(E.geom, sm.occ, sm.items, rem, lane, sm.vw, sm.tab);
     for (int a = lane; a < E.geom.A; a += 32) out[(size_t)s * E.geom.A + a] = (uint8_t)((sm.vw[a >> 5] >> (a & 31)) & 1u);
 }
 
@@ -647,7 +652,7 @@ k_env_ended(EnvArgs E, const int32_t* total_area, const int32_t* max_h, const do
     uint32_t rec;
     env_load(E, s, lane, sm, rec);
     const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
-    const uint32_t mine = valid_words(E.geom, sm.occ, sm.items, rem, lane, sm.vw);
+    const uint32_t mine = valid_words<0>(E.geom, sm.occ, sm.items, rem, lane, sm.vw, sm.tab);
     int res = 0;
     double score = 0.0;
     if (!__any_sync(FULL, mine != 0u)) {
@@ -904,11 +909,22 @@ extern "C" int bpp_engine_begin_move(bpp_engine* e, void* stream) {
     return BPP_OK;
 }
 
+// bin heights with a specialised (fully unrolled, rows-in-registers) valid-move sweep; anything else is generic
+template <int STUB>
+static void launch_search(bpp_engine* e, void* stream) {
+    const int grid = grid_warps(e->P.G), block = WARPS_PER_CTA * 32;
+    switch (e->P.geom.H) {
+        case 15: k_search<STUB, 15><<<grid, block, 0, S(stream)>>>(e->P); break;
+        case 20: k_search<STUB, 20><<<grid, block, 0, S(stream)>>>(e->P); break;
+        default: k_search<STUB, 0><<<grid, block, 0, S(stream)>>>(e->P); break;
+    }
+}
+
 extern "C" int bpp_engine_select(bpp_engine* e, void* stream) {
     if (!e) return set_err(BPP_E_INVALID, "null argument");
     if (e->leaf_parked) return set_err(BPP_E_STATE, "bpp_engine_select called with leaves still parked");
     CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, sizeof(int), S(stream)));
-    k_search<0><<<grid_warps(e->P.G), WARPS_PER_CTA * 32, 0, S(stream)>>>(e->P);
+    launch_search<0>(e, stream);
     LAUNCH_CHECK(e);
     e->leaf_parked = true;
     return BPP_OK;
@@ -952,12 +968,11 @@ extern "C" int bpp_engine_expand_backup(bpp_engine* e, const void* policy_dev, i
 extern "C" int bpp_engine_search_stub(bpp_engine* e, int stub_kind, void* stream) {
     if (!e) return set_err(BPP_E_INVALID, "null argument");
     if (e->leaf_parked) return set_err(BPP_E_STATE, "leaves are parked; call bpp_engine_expand_backup first");
-    const int grid = grid_warps(e->P.G), block = WARPS_PER_CTA * 32;
     switch (stub_kind) {
-        case BPP_STUB_U: k_search<1><<<grid, block, 0, S(stream)>>>(e->P); break;
-        case BPP_STUB_V: k_search<2><<<grid, block, 0, S(stream)>>>(e->P); break;
-        case BPP_STUB_H: k_search<3><<<grid, block, 0, S(stream)>>>(e->P); break;
-        case BPP_STUB_D: k_search<4><<<grid, block, 0, S(stream)>>>(e->P); break;
+        case BPP_STUB_U: launch_search<1>(e, stream); break;
+        case BPP_STUB_V: launch_search<2>(e, stream); break;
+        case BPP_STUB_H: launch_search<3>(e, stream); break;
+        case BPP_STUB_D: launch_search<4>(e, stream); break;
         default: return set_err(BPP_E_INVALID, "unknown stub kind %d", stub_kind);
     }
     LAUNCH_CHECK(e);
