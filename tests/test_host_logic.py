@@ -97,3 +97,34 @@ def test_dotdict_and_average_meter():
     m.update(2.0, 2)
     m.update(4.0, 2)
     assert m.avg == 3.0
+
+
+def test_torch_module_is_the_reference_architecture():
+    """BinPackingNNet (the parameter container / learner graph) reproduces the reference net's outputs on CPU fp32 and
+    has the reference's parameter names and count (170,583 at the default size)."""
+    import torch
+    from resource_packing_self_play_b200.nnet import BinPackingNNet
+    from resource_packing_self_play_b200.utils import dotdict
+    from helpers import GOLDEN
+
+    class G:
+        def __init__(self, W, H, N):
+            self.W, self.H, self.N = W, H, N
+
+        def getBoardSize(self):
+            return (self.H, self.W)
+
+        def getActionSize(self):
+            return self.W * self.N
+    d = np.load(os.path.join(GOLDEN, "net.npz"))
+    for tag, (W, H, N) in (("ck", (15, 15, 10)), ("r20", (20, 20, 10))):
+        net = BinPackingNNet(G(W, H, N), dotdict(num_items=N, num_bins=1))
+        sd = {k[len(tag) + 3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith(tag + "_w.")}
+        net.load_state_dict(sd)  # strict: names and shapes must match the reference checkpoint
+        net.eval()
+        with torch.no_grad():
+            lp, v = net(torch.from_numpy(d[tag + "_states"].astype(np.float32)))
+        assert np.abs(lp.exp().numpy() - d[tag + "_pi"]).max() < 1e-4
+        assert np.abs(v.view(-1).numpy() - d[tag + "_v"]).max() < 1e-4
+        if tag == "ck":
+            assert sum(p.numel() for p in net.parameters()) == 170583
