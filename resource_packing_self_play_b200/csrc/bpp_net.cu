@@ -225,7 +225,8 @@ k_net_forward(NetParams P, int Bmax, const int32_t* __restrict__ count_dev, cons
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 forward: one CTA = S leaves through the whole network (see bpp_net_tc.cuh)
-__global__ void __launch_bounds__(bpptc::TC_THREADS, 2)
+template <int NS>  // leaves per CTA the head accumulators are unrolled for (4 or 8)
+__global__ void __launch_bounds__(bpptc::TC_THREADS, (NS <= 4 ? 2 : 1))
 k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__ count_dev,
                  const uint32_t* __restrict__ recs, const int32_t* __restrict__ game,
                  const int32_t* __restrict__ items_wh, float* __restrict__ policy, float* __restrict__ value,
@@ -233,8 +234,8 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     using namespace bpptc;
     extern __shared__ __align__(1024) unsigned char arena[];
     __shared__ __align__(8) uint64_t s_bar[MAX_BARS];
-    __shared__ uint32_t s_rec[8][32];
-    __shared__ int s_it[8][BPP_MAX_ITEMS][2];
+    __shared__ uint32_t s_rec[NS][32];
+    __shared__ int s_it[NS][BPP_MAX_ITEMS][2];
     __shared__ uint32_t s_tmem;
     unsigned char* regA = arena;
     unsigned char* regB = arena + T.regA_bytes;
@@ -243,7 +244,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     if (tid < MAX_BARS) mbar_init(smem_u32(&s_bar[tid]), 1);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "r"((uint32_t)TMEM_COLS));
+                     "r"((uint32_t)T.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -334,11 +335,12 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         tq = clock64();
         // ---- heads on the CUDA cores (1.6 % of the FLOPs): flatten -> relu -> fc256 -> relu -> {logits, value}
         const Level& L3 = T.lv[3];
-        float* feat = reinterpret_cast<float*>(regB);            // [8][flat]
-        float* hid = feat + 8 * P.flat;                           // [8][256]
-        float* lg = hid + 8 * HIDDEN;                             // [8][A]
+        float* feat = reinterpret_cast<float*>(regB);            // [NS][flat]
+        float* hid = feat + NS * P.flat;                          // [NS][256]
+        float* lg = hid + NS * HIDDEN;                            // [NS][A]
+        float* part = lg + NS * P.A;                              // [2][NS][256] / [2][NS][A] partial sums
         const int hw3 = L3.h * L3.w;
-        for (int idx = tid; idx < 8 * P.flat; idx += TC_THREADS) {
+        for (int idx = tid; idx < NS * P.flat; idx += TC_THREADS) {
             const int j = idx / P.flat, f = idx - j * P.flat;
             float v = 0.f;
             if (j < nvalid) {
@@ -352,53 +354,68 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             feat[idx] = v;
         }
         __syncthreads();
-        {   // hidden layer: thread -> outputs 2*tid, 2*tid+1 (one coalesced bf16x2 load per input), 8 leaves at once
-            const int o = 2 * tid;
-            float a0[8], a1[8];
+        const int hh = tid >> 7, ot = tid & 127;  // input half, output pair
+        {   // hidden layer: thread -> outputs 2*ot, 2*ot+1 over one half of the inputs (coalesced bf16x2 loads)
+            const int o = 2 * ot;
+            float a0[NS], a1[NS];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { a0[j] = P.bias[P.b_hidden_off + o]; a1[j] = P.bias[P.b_hidden_off + o + 1]; }
-            const uint32_t* wp32 = reinterpret_cast<const uint32_t*>(P.wts + P.fc_hidden_off) + tid;
+            for (int j = 0; j < NS; ++j) {
+                a0[j] = hh ? 0.f : P.bias[P.b_hidden_off + o];
+                a1[j] = hh ? 0.f : P.bias[P.b_hidden_off + o + 1];
+            }
+            const uint32_t* wp32 = reinterpret_cast<const uint32_t*>(P.wts + P.fc_hidden_off) + ot;
+            const int i0 = hh * (P.flat / 2), i1 = hh ? P.flat : P.flat / 2;
 #pragma unroll 16
-            for (int i = 0; i < P.flat; ++i) {
+            for (int i = i0; i < i1; ++i) {
                 const uint32_t wv = __ldg(wp32 + (size_t)i * (HIDDEN / 2));
                 const float w0 = bf16_lo(wv), w1 = bf16_hi(wv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < NS; ++j) {
                     const float f = feat[j * P.flat + i];
                     a0[j] = fmaf(f, w0, a0[j]);
                     a1[j] = fmaf(f, w1, a1[j]);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                hid[j * HIDDEN + o] = act_round<false>(fmaxf(a0[j], 0.f));
-                hid[j * HIDDEN + o + 1] = act_round<false>(fmaxf(a1[j], 0.f));
+            for (int j = 0; j < NS; ++j) {
+                part[(hh * NS + j) * HIDDEN + o] = a0[j];
+                part[(hh * NS + j) * HIDDEN + o + 1] = a1[j];
             }
         }
         __syncthreads();
-        if (2 * tid < T.A_pad) {  // logits: padded [256][A_pad] copy of the weights, outputs 2*tid, 2*tid+1
-            const int o = 2 * tid;
-            float a0[8], a1[8];
-            const float b0 = P.bias[P.b_logits_off + o], b1 = o + 1 < P.A ? P.bias[P.b_logits_off + o + 1] : 0.f;
+        for (int idx = tid; idx < NS * HIDDEN; idx += TC_THREADS)
+            hid[idx] = act_round<false>(fmaxf(part[idx] + part[NS * HIDDEN + idx], 0.f));
+        __syncthreads();
+        if (2 * ot < T.A_pad) {  // logits: padded [256][A_pad] copy of the weights, outputs 2*ot, 2*ot+1
+            const int o = 2 * ot;
+            float a0[NS], a1[NS];
+            const float b0 = hh ? 0.f : P.bias[P.b_logits_off + o];
+            const float b1 = (hh || o + 1 >= P.A) ? 0.f : P.bias[P.b_logits_off + o + 1];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { a0[j] = b0; a1[j] = b1; }
-            const uint32_t* wp32 = reinterpret_cast<const uint32_t*>(T.wts_logits_pad) + tid;
+            for (int j = 0; j < NS; ++j) { a0[j] = b0; a1[j] = b1; }
+            const uint32_t* wp32 = reinterpret_cast<const uint32_t*>(T.wts_logits_pad) + ot;
+            const int i0 = hh * (HIDDEN / 2), i1 = i0 + HIDDEN / 2;
 #pragma unroll 16
-            for (int i = 0; i < HIDDEN; ++i) {
+            for (int i = i0; i < i1; ++i) {
                 const uint32_t wv = __ldg(wp32 + (size_t)i * (T.A_pad / 2));
                 const float w0 = bf16_lo(wv), w1 = bf16_hi(wv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < NS; ++j) {
                     const float f = hid[j * HIDDEN + i];
                     a0[j] = fmaf(f, w0, a0[j]);
                     a1[j] = fmaf(f, w1, a1[j]);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                lg[j * P.A + o] = a0[j];
-                if (o + 1 < P.A) lg[j * P.A + o + 1] = a1[j];
+            for (int j = 0; j < NS; ++j) {
+                part[(hh * NS + j) * T.A_pad + o] = a0[j];
+                part[(hh * NS + j) * T.A_pad + o + 1] = a1[j];
             }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NS * P.A; idx += TC_THREADS) {
+            const int j = idx / P.A, o = idx - j * P.A;
+            lg[idx] = part[j * T.A_pad + o] + part[(NS + j) * T.A_pad + o];
         }
         __syncthreads();
         for (int j = warp; j < nvalid; j += TC_THREADS / 32) {  // one warp per leaf: value head + softmax
@@ -429,7 +446,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"((uint32_t)TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"((uint32_t)T.tmem_cols));
 }
 
 // shared-memory budget of the tensor-core kernel: ~110 KB lets two CTAs share an SM so that one CTA's epilogue overlaps
@@ -467,6 +484,7 @@ struct bpp_net {
     long long umma_elems = 0;
     long long* d_prof = nullptr;  // phase timers of CTA 0 (bpp_net_profile)
     bool tc_ok = false;
+    int ctas_per_sm = 1;
     bool committed = false;
     int smem_bytes = 0;
 };
@@ -581,13 +599,21 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                 a = std::max(a, 3LL * planes * T.lv[s2 + 1].RT * 16);
                 b = std::max(b, (long long)planes * T.lv[s2].RT * 16);
             }
-            b = std::max(b, (long long)(8 * (P.flat + HIDDEN + P.A)) * 4);
+            const int NSs = S <= 4 ? 4 : 8;
+            b = std::max(b, (long long)NSs * (P.flat + 4 * HIDDEN + 3 * (P.A + 1)) * 4);
             T.S = S;
             T.regA_bytes = (int)((a + 1023) & ~1023LL);
             T.regB_bytes = (int)((b + 4096 + 1023) & ~1023LL);  // + slack: the last tile's shifted windows over-read
             T.wbuf_bytes = (wmax + 256 + 1023) & ~1023;  // + the layer's bias behind the weights
             T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
             if (T.smem_bytes <= tc_smem_cap() && T.lv[0].RT < 16384) n->tc_ok = true;
+            // CTAs that fit on one SM (227 KB shared memory, 1 KB reserved per CTA) share the 512 TMEM columns
+            int ctas = (227 * 1024) / (T.smem_bytes + 2048);
+            if (ctas > 2) ctas = 2;
+            if (S > 4) ctas = 1;
+            if (ctas < 1) ctas = 1;
+            T.tmem_cols = ctas >= 3 ? 128 : (ctas == 2 ? 256 : 512);
+            n->ctas_per_sm = ctas;
         }
     }
     n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
@@ -595,8 +621,10 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             cudaSuccess ||
         cudaFuncSetAttribute(k_net_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
             cudaSuccess ||
-        (n->tc_ok && cudaFuncSetAttribute(k_net_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          n->T.smem_bytes) != cudaSuccess)) {
+        (n->tc_ok && (cudaFuncSetAttribute(k_net_forward_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           n->T.smem_bytes) != cudaSuccess ||
+                      cudaFuncSetAttribute(k_net_forward_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           n->T.smem_bytes) != cudaSuccess))) {
         cudaGetLastError();
         delete n;
         return nerr(BPP_E_CUDA, "cannot reserve shared memory for the forward kernel");
@@ -742,10 +770,14 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (n->precision == BPP_NET_BF16 && n->tc_ok) {
         const int groups = (B + n->T.S - 1) / n->T.S;
-        const int g2 = groups < 296 ? groups : 296;
-        k_net_forward_tc<<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(n->P, n->T, B, count_dev, recs_dev, game_dev,
-                                                                        items_wh_dev, policy_out_dev, value_out_dev,
-                                                                        n->d_prof);
+        const int cap = 148 * n->ctas_per_sm;
+        const int g2 = groups < cap ? groups : cap;
+        if (n->T.S <= 4)
+            k_net_forward_tc<4><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
+                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
+        else
+            k_net_forward_tc<8><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
+                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
     } else if (n->precision == BPP_NET_FP32)
         k_net_forward<true><<<grid, NET_THREADS, n->smem_bytes, st>>>(n->P, B, count_dev, recs_dev, game_dev, items_wh_dev,
                                                                       policy_out_dev, value_out_dev);

@@ -23,8 +23,7 @@
 
 namespace bpptc {
 
-constexpr int TC_THREADS = 128;
-constexpr int TMEM_COLS = 256;   // two CTAs per SM share the 512 columns; up to 256 / Cout output tiles in flight
+constexpr int TC_THREADS = 256;   // 8 warps: warps w and w+4 own the same TMEM lane quarter and alternate output tiles
 constexpr int MAX_BARS = 16;
 
 struct Level {
@@ -38,6 +37,7 @@ struct TcParams {
     int regB_bytes;        // region B: conv outputs awaiting pooling (T_0..T_2), then the head scratch
     int wbuf_bytes;        // one layer of weights
     int smem_bytes;
+    int tmem_cols;         // TMEM columns allocated per CTA: 512 / (CTAs per SM), a power of two
     long long w_off[15];   // element offsets of each conv layer in wts_umma
     const __nv_bfloat16* wts_umma;
     int A_pad;                             // action size rounded up to even
@@ -65,6 +65,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n\t"
         "}" ::"r"(bar), "r"(parity)
         : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
 }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading byte
@@ -161,48 +172,47 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
     const uint32_t plane_b = (uint32_t)L.RT * 16u;
     const int rows_valid = nvalid * L.P;
     const int nt = min(L.ntiles, (rows_valid + 127) >> 7);  // tiles that hold at least one present sample
-    int tpp = TMEM_COLS / cout;                                // tiles in flight per pass
+    int tpp = T.tmem_cols / cout;                              // tiles in flight per pass
     if (tpp > MAX_BARS) tpp = MAX_BARS;
     for (int t0 = 0; t0 < nt; t0 += tpp) {
       const int nb = min(tpp, nt - t0);
       // ---- issue: ONE thread queues the MMAs of all nb tiles (each tile into its own TMEM columns, each followed by a
       // commit to its own mbarrier); the tensor core drains the queue while the 128 threads run the epilogues below
-      if (tid == 0) {
+      if ((tid >> 5) == 0 && elect_one()) {  // warp-uniform branch + elect.sync: no per-thread serialisation loop
         tc_fence_after();
         const uint64_t b0 = umma_desc(w_base, (uint32_t)cout, 8u);
         const long long a_kc = (long long)(2u * plane_b >> 4), b_blk = (long long)(2 * cout);
+        const long long b_tap = b_blk * cin16;
         for (int b = 0; b < nb; ++b) {
             // descriptors differ only in their 14-bit start-address field (16-byte units): one 64-bit add per MMA
-            const uint64_t a0 = umma_desc(a_base + (uint32_t)(L.guard + (t0 + b) * 128) * 16u, (uint32_t)L.RT, 8u);
-            uint32_t acc = 0;
-            long long bi = 0;
+            const long long a0 =
+                (long long)umma_desc(a_base + (uint32_t)(L.guard + (t0 + b) * 128) * 16u, (uint32_t)L.RT, 8u);
+            const uint32_t d = cx.tmem + (uint32_t)(b * cout);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                const long long a_tap = (long long)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
-                for (int kc = 0; kc < cin16; ++kc) {
-                    umma_bf16(cx.tmem + (uint32_t)(b * cout), (uint64_t)((long long)a0 + a_tap + kc * a_kc),
-                              (uint64_t)((long long)b0 + bi), idesc, acc);
-                    acc = 1;
-                    bi += b_blk;
-                }
+                const long long at = a0 + (long long)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
+                const long long bt = (long long)b0 + tap * b_tap;
+                umma_bf16(d, (uint64_t)at, (uint64_t)bt, idesc, tap > 0 ? 1u : 0u);
+                if (cin16 == 2) umma_bf16(d, (uint64_t)(at + a_kc), (uint64_t)(bt + b_blk), idesc, 1u);
             }
             umma_commit(cx.bar + 8u * (uint32_t)b);
         }
       }
+      __syncwarp();
       TC_PROF(2, tp);
-      for (int b = 0; b < nb; ++b) {
+      const int half = tid >> 7, lt = tid & 127;  // lt = TMEM lane = row inside the tile
+      for (int b = half; b < nb; b += 2) {
         const int t = t0 + b;
         mbar_wait(cx.bar + 8u * (uint32_t)b, (cx.phase >> b) & 1u);
-        cx.phase ^= 1u << b;
         tc_fence_after();
         TC_PROF(3, tp);
         // ---- epilogue: thread tid owns output row t*128 + tid
-        const int rl = t * 128 + tid;
+        const int rl = t * 128 + lt;
         const int j = rl / L.P, q = rl - j * L.P;
         const int yp = q / L.wp, xp = q - yp * L.wp;
         const bool interior = rl < rows_valid && yp >= 1 && yp <= L.h && xp >= 1 && xp <= L.w;
         const size_t rowb = (size_t)(L.guard + rl) * 16;
-        const uint32_t taddr = cx.tmem + ((uint32_t)((tid >> 5) * 32) << 16) + (uint32_t)(b * cout);
+        const uint32_t taddr = cx.tmem + ((uint32_t)(((lt >> 5) & 3) * 32) << 16) + (uint32_t)(b * cout);
         for (int c0 = 0; c0 < cout; c0 += 16) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);  // warp-collective: executed by every lane
@@ -234,6 +244,7 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         }
         TC_PROF(4, tp);
       }
+      cx.phase ^= (1u << nb) - 1u;  // every barrier of this pass completed one phase
       tc_fence_before();
       __syncthreads();  // TMEM columns are free again; epilogue stores are ordered before the next layer's proxy fence
     }
