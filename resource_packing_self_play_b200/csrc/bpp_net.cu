@@ -261,6 +261,10 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     const int S = T.S;
     const int ngroups = (B + S - 1) / S;
     const int cin16_0 = (P.Cin + 15) / 16;
+    WPre pre;
+    auto lay_w = [&](int l) { return T.wts_umma + T.w_off[l]; };
+    auto lay_b = [&](int l) { return P.bias + P.conv[l].b_off; };
+    if ((int)blockIdx.x < ngroups) wpre_load(pre, lay_w(0), T.lay_n16[0], lay_b(0), P.conv[0].co);
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const int nvalid = min(S, B - grp * S);
         long long tq = clock64();
@@ -307,8 +311,8 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             const Level& La = T.lv[s];
             const Level& Lb = T.lv[s + 1];
             const int cout = P.conv[li].co;
-            conv_layer(T, cx, La, nvalid, cin16, cout, T.wts_umma + T.w_off[li], P.bias + P.conv[li].b_off, in, EPI_CONV,
-                       regB, nullptr);
+            conv_layer(T, cx, La, nvalid, cin16, cout, lay_w(li), lay_b(li), in, EPI_CONV, regB, nullptr, pre,
+                       lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co);
             ++li;
             tq = clock64();
             const int planes = cout / 8;
@@ -322,11 +326,14 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             __syncthreads();
             TC_PROF(5, tq);
             for (int blk = 0; blk < 2; ++blk) {
-                conv_layer(T, cx, Lb, nvalid, cout / 16, cout, T.wts_umma + T.w_off[li], P.bias + P.conv[li].b_off, actA,
-                           EPI_RES0, actB, nullptr);
+                conv_layer(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actA, EPI_RES0, actB, nullptr, pre,
+                           lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co);
                 ++li;
-                conv_layer(T, cx, Lb, nvalid, cout / 16, cout, T.wts_umma + T.w_off[li], P.bias + P.conv[li].b_off, actB,
-                           EPI_RES1, actA, raw);
+                {
+                    const int nx = (li + 1) % NCONV;  // after the last layer: layer 0 of this CTA's next group
+                    conv_layer(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actB, EPI_RES1, actA, raw, pre,
+                               lay_w(nx), T.lay_n16[nx], lay_b(nx), P.conv[nx].co);
+                }
                 ++li;
             }
             in = raw;
@@ -579,6 +586,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         for (int l = 0; l < NCONV; ++l) {
             const int c16 = (P.conv[l].ci + 15) / 16;
             T.w_off[l] = uoff;
+            T.lay_n16[l] = 9 * c16 * 2 * P.conv[l].co;
             const int bytes = 9 * c16 * 2 * P.conv[l].co * 16;
             uoff += bytes / 2;
             if (bytes > wmax) wmax = bytes;

@@ -39,6 +39,7 @@ struct TcParams {
     int smem_bytes;
     int tmem_cols;         // TMEM columns allocated per CTA: 512 / (CTAs per SM), a power of two
     long long w_off[15];   // element offsets of each conv layer in wts_umma
+    int lay_n16[15];       // 16-byte chunks of each layer's staged weights (9 * cin16 * 2 * cout)
     const __nv_bfloat16* wts_umma;
     int A_pad;                             // action size rounded up to even
     const __nv_bfloat16* wts_logits_pad;   // logits weights [256][A_pad] (bf16x2 loads)
@@ -99,6 +100,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptors given as (lo, hi) halves: only the 14-bit start-address field in `lo` changes between MMAs of a
+// layer, so the issuing thread needs one 32-bit add per operand instead of 64-bit arithmetic
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -134,6 +150,24 @@ __device__ __forceinline__ float bf16_hi(uint32_t x) { return __uint_as_float(x 
 
 enum { EPI_CONV = 0, EPI_RES0 = 1, EPI_RES1 = 2 };
 
+// Register prefetch of the NEXT layer's weights and bias: the global loads are issued at the start of a layer and are
+// consumed (stored to shared memory) at the start of the next one, so their L2 latency hides behind the layer's MMAs
+// and epilogues without a second shared-memory weight buffer.
+constexpr int WPRE = 5;  // ceil(18,432 B / 16 B / 256 threads)
+struct WPre {
+    uint4 w[WPRE];
+    float b;
+};
+__device__ __forceinline__ void wpre_load(WPre& p, const __nv_bfloat16* wsrc, int n16, const float* bias, int cout) {
+    const uint4* src = reinterpret_cast<const uint4*>(wsrc);
+#pragma unroll
+    for (int k = 0; k < WPRE; ++k) {
+        const int i = threadIdx.x + k * TC_THREADS;
+        if (i < n16) p.w[k] = __ldg(src + i);
+    }
+    if ((int)threadIdx.x < cout) p.b = __ldg(bias + threadIdx.x);
+}
+
 struct Ctx {
     uint32_t tmem;      // TMEM base (lane 0, column 0)
     uint32_t bar;       // shared address of mbarrier[0] (MAX_BARS barriers, 8 bytes apart)
@@ -151,18 +185,23 @@ struct Ctx {
 __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Level& L, int nvalid, int cin16, int cout,
                                            const __nv_bfloat16* __restrict__ wsrc, const float* __restrict__ bias,
                                            const unsigned char* in_planes, int kind, unsigned char* out0,
-                                           unsigned char* raw) {
+                                           unsigned char* raw, WPre& pre, const __nv_bfloat16* next_wsrc, int next_n16,
+                                           const float* next_bias, int next_cout) {
     const int tid = threadIdx.x;
     long long tp = clock64();
-    // stage this layer's weights (already in the UMMA B layout) into shared memory
+    // this layer's weights (already in the UMMA B layout) were prefetched into registers: park them in shared memory
     const int wbytes = 9 * cin16 * 2 * cout * 16;
     {
-        const uint4* src = reinterpret_cast<const uint4*>(wsrc);
         uint4* dst = reinterpret_cast<uint4*>(cx.wbuf);
-        for (int i = tid; i < wbytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+#pragma unroll
+        for (int k = 0; k < WPRE; ++k) {
+            const int i = tid + k * TC_THREADS;
+            if (i < wbytes / 16) dst[i] = pre.w[k];
+        }
     }
     float* s_bias = reinterpret_cast<float*>(cx.wbuf + wbytes);  // Cout floats right behind the staged weights
-    if (tid < cout) s_bias[tid] = __ldg(bias + tid);
+    if (tid < cout) s_bias[tid] = pre.b;
+    wpre_load(pre, next_wsrc, next_n16, next_bias, next_cout);  // in flight during this layer
     fence_proxy_async();  // generic-proxy writes (weights, previous epilogue) -> visible to the tensor core's async proxy
     __syncthreads();
     TC_PROF(1, tp);
@@ -181,19 +220,18 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
       if ((tid >> 5) == 0 && elect_one()) {  // warp-uniform branch + elect.sync: no per-thread serialisation loop
         tc_fence_after();
         const uint64_t b0 = umma_desc(w_base, (uint32_t)cout, 8u);
-        const long long a_kc = (long long)(2u * plane_b >> 4), b_blk = (long long)(2 * cout);
-        const long long b_tap = b_blk * cin16;
+        const uint64_t a00 = umma_desc(a_base + (uint32_t)L.guard * 16u, (uint32_t)L.RT, 8u);
+        const uint32_t ahi = (uint32_t)(a00 >> 32), bhi = (uint32_t)(b0 >> 32), blo0 = (uint32_t)b0;
+        const uint32_t a_kc = 2u * plane_b >> 4, b_blk = (uint32_t)(2 * cout), b_tap = b_blk * (uint32_t)cin16;
         for (int b = 0; b < nb; ++b) {
-            // descriptors differ only in their 14-bit start-address field (16-byte units): one 64-bit add per MMA
-            const long long a0 =
-                (long long)umma_desc(a_base + (uint32_t)(L.guard + (t0 + b) * 128) * 16u, (uint32_t)L.RT, 8u);
+            const uint32_t alo0 = (uint32_t)a00 + (uint32_t)(t0 + b) * 128u;  // +128 rows (16-byte units) per tile
             const uint32_t d = cx.tmem + (uint32_t)(b * cout);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                const long long at = a0 + (long long)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
-                const long long bt = (long long)b0 + tap * b_tap;
-                umma_bf16(d, (uint64_t)at, (uint64_t)bt, idesc, tap > 0 ? 1u : 0u);
-                if (cin16 == 2) umma_bf16(d, (uint64_t)(at + a_kc), (uint64_t)(bt + b_blk), idesc, 1u);
+                const uint32_t at = alo0 + (uint32_t)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
+                const uint32_t bt = blo0 + (uint32_t)tap * b_tap;
+                umma_bf16_lh(d, at, ahi, bt, bhi, idesc, tap > 0 ? 1u : 0u);
+                if (cin16 == 2) umma_bf16_lh(d, at + a_kc, ahi, bt + b_blk, bhi, idesc, 1u);
             }
             umma_commit(cx.bar + 8u * (uint32_t)b);
         }
