@@ -13,7 +13,7 @@ Seeds: generator_seed = 1000 + global episode index.  Scaling is weak: every ran
 value   = simulations/s with the instances already resident in HBM (whole job, all ranks, max-over-ranks time)
 e2e     = the same through the host-buffer C-ABI call bpp_engine_play_stub_host: instances uploaded from pinned host
           memory and visit counts / actions / rewards downloaded inside the timed region
-roofline= dominant kernel k_search<U>: algorithmic bytes (SURVEY.md §8(d) formula with the kernel-counted edges and
+roofline= dominant kernel k_episode<U> (all simulations of a step in one launch): algorithmic bytes (SURVEY.md §8(d) formula with the kernel-counted edges and
           expansions per simulation) / CUDA-event time of that kernel, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline = oracle/bpp_oracle.py (a port that keeps the reference's data structures) on ONE host core, bounded
           sample of the same workload.  `--impl reference` runs that port on all host cores instead of the GPU.
@@ -240,20 +240,20 @@ def run_gpu_arm(args):
     dev_inst = [(torch.from_numpy(i).to(dev), torch.from_numpy(a).to(dev)) for i, a in inst[:n_steps_total]]
     search_events = []
 
+    actions_buf = torch.empty((N, G), dtype=torch.int32, device=dev)
+
     def step_resident(k, timed):
+        """reset + ONE launch of the whole-episode kernel (search -> counts -> choose -> play, N moves)"""
         items, area = dev_inst[k]
         eng.reset(items, area, bl_dev)
-        for m in range(N):
-            if timed:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            eng.search_stub("U")
-            if timed:
-                e1.record()
-                search_events.append((e0, e1))
-            _lib.call("bpp_engine_root_counts", eng._h, counts_buf[m].data_ptr(), eng_stream())
-            act = eng.choose(_lib.CHOOSE_SAMPLE, seed=1234 + k)
-            eng.advance(act)
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.call("bpp_engine_play_stub", eng._h, _lib.STUB["U"], _lib.CHOOSE_SAMPLE, C.c_uint64(1234 + k), 0,
+                  C.c_void_p(counts_buf.data_ptr()), C.c_void_p(actions_buf.data_ptr()), None, eng_stream())
+        if timed:
+            e1.record()
+            search_events.append((e0, e1))
 
     def eng_stream():
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -347,7 +347,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": int(d2h), "episodes_per_sec": episodes / (e2e_ms * 1e-3),
                     "api": "bpp_engine_play_stub_host (pinned host buffers)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_search<STUB_U>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_episode<STUB_U,15> (whole episodes, one launch per step)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                          "traffic": None, "algorithmic_bytes_per_sim": bytes_per_sim,

@@ -444,15 +444,11 @@ __global__ void k_set_roots(Params P, const uint32_t* roots) {
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_root_counts(Params P, int32_t* out) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = blockIdx.x * WARPS_PER_CTA + wid;
-    if (g >= P.G) return;
+// counts[a] = Nsa[(root, a)] for one game (warp-collective)
+__device__ __forceinline__ void root_counts_warp(const Params& P, int g, int root, int lane, int32_t* row) {
     const int A = P.geom.A;
-    int32_t* row = out + (size_t)g * A;
     for (int a = lane; a < A; a += 32) row[a] = 0;
     __syncwarp();
-    const int root = P.root_node[g];
     if (root < 0) return;
     const uint32_t* nodes = P.nodes + (size_t)g * P.node_cap * REC_WORDS;
     const uint32_t meta = nodes[(size_t)root * REC_WORDS + REC_META];
@@ -462,6 +458,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_root_counts(Params P, in
     for (int e = lane; e < nv; e += 32) row[eb.ACT[e]] = eb.NC[e].x;
 }
 
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_root_counts(Params P, int32_t* out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    if (g >= P.G) return;
+    root_counts_warp(P, g, P.root_node[g], lane, out + (size_t)g * P.geom.A);
+}
+
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -469,67 +472,63 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     return x ^ (x >> 31);
 }
 
-// action choice from the root visit counts (one thread per game; <= A edges)
+// action choice from the root visit counts of one game (executed by ONE thread; <= A edges).  The random stream is a
+// pure function of (seed, game, move number), so the per-move kernels and the whole-episode kernel draw the same.
+__device__ __forceinline__ int choose_action(const Params& P, int g, int root, int move_no, int mode,
+                                             unsigned long long seed) {
+    int act = -1;
+    if (root < 0) return act;
+    const uint32_t* nodes = P.nodes + (size_t)g * P.node_cap * REC_WORDS;
+    const uint32_t meta = nodes[(size_t)root * REC_WORDS + REC_META];
+    if (((meta >> 16) & 0xffu) != KIND_EXP) return act;
+    const int nv = (int)(meta & 0xffffu), nvp = (nv + 3) & ~3;
+    EdgeBlock eb(P.edges + (size_t)g * (size_t)P.edge_cap + nodes[(size_t)root * REC_WORDS + REC_OFF], nvp);
+    const unsigned long long rnd =
+        splitmix64(seed ^ splitmix64(((unsigned long long)g << 20) ^ (unsigned long long)move_no));
+    if (mode == BPP_CHOOSE_SAMPLE) {  // a ~ counts / sum(counts), CoachBPP.py:86-87
+        long long tot = 0;
+        for (int e = 0; e < nv; ++e) tot += eb.NC[e].x;
+        if (tot > 0) {
+            long long t = (long long)(rnd % (unsigned long long)tot);
+            for (int e = 0; e < nv; ++e) {
+                t -= eb.NC[e].x;
+                if (t < 0) { act = eb.ACT[e]; break; }
+            }
+        }
+    } else {
+        int best = -1, nbest = 0;
+        for (int e = 0; e < nv; ++e) {
+            const int n = eb.NC[e].x;
+            if (n > best) { best = n; nbest = 1; act = eb.ACT[e]; }
+            else if (n == best) nbest++;
+        }
+        if (mode == BPP_CHOOSE_GREEDY && nbest > 1) {  // uniformly random arg-max, MCTS_bpp.py:43-49
+            int k = (int)(rnd % (unsigned long long)nbest);
+            for (int e = 0; e < nv; ++e)
+                if (eb.NC[e].x == best && k-- == 0) { act = eb.ACT[e]; break; }
+        }
+    }
+    return act;
+}
+
 __global__ void k_choose(Params P, int mode, unsigned long long seed, int32_t* actions) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= P.G) return;
-    int act = -1;
-    const int root = P.root_node[g];
-    if (P.status[g] == 0 && root >= 0) {
-        const uint32_t* nodes = P.nodes + (size_t)g * P.node_cap * REC_WORDS;
-        const uint32_t meta = nodes[(size_t)root * REC_WORDS + REC_META];
-        if (((meta >> 16) & 0xffu) == KIND_EXP) {
-            const int nv = (int)(meta & 0xffffu), nvp = (nv + 3) & ~3;
-            EdgeBlock eb(P.edges + (size_t)g * (size_t)P.edge_cap + nodes[(size_t)root * REC_WORDS + REC_OFF], nvp);
-            const unsigned long long rnd =
-                splitmix64(seed ^ splitmix64(((unsigned long long)g << 20) ^ (unsigned long long)P.moves_done[g]));
-            if (mode == BPP_CHOOSE_SAMPLE) {
-                long long tot = 0;
-                for (int e = 0; e < nv; ++e) tot += eb.NC[e].x;
-                if (tot > 0) {
-                    long long t = (long long)(rnd % (unsigned long long)tot);
-                    for (int e = 0; e < nv; ++e) {
-                        t -= eb.NC[e].x;
-                        if (t < 0) { act = eb.ACT[e]; break; }
-                    }
-                }
-            } else {
-                int best = -1, nbest = 0;
-                for (int e = 0; e < nv; ++e) {
-                    const int n = eb.NC[e].x;
-                    if (n > best) { best = n; nbest = 1; act = eb.ACT[e]; }
-                    else if (n == best) nbest++;
-                }
-                if (mode == BPP_CHOOSE_GREEDY && nbest > 1) {
-                    int k = (int)(rnd % (unsigned long long)nbest);
-                    for (int e = 0; e < nv; ++e)
-                        if (eb.NC[e].x == best && k-- == 0) { act = eb.ACT[e]; break; }
-                }
-            }
-        }
-    }
-    actions[g] = act;
+    actions[g] = P.status[g] == 0 ? choose_action(P, g, P.root_node[g], P.moves_done[g], mode, seed) : -1;
 }
 
-// play one real move per game (CoachBPP.py:88-98)
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_advance(Params P, const int32_t* actions) {
-    __shared__ WarpSmem smem[WARPS_PER_CTA];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = blockIdx.x * WARPS_PER_CTA + wid;
-    if (g >= P.G) return;
-    if (P.status[g] != 0) return;
+// Play one real move in one game (CoachBPP.py:88-98): root <- getNextState(root, a), then getGameEnded on the new root.
+// Warp-collective.  `rec` = the lane's word of the root record (in/out).  Returns the new status (0 running, 1 ended,
+// -1 illegal action) and latches (r, score) when the episode ends.
+__device__ __forceinline__ int advance_game(const Params& P, GameCtx& gm, WarpSmem& sm, int lane, int a, uint32_t& rec,
+                                            Stats& st) {
     const Geom& ge = P.geom;
-    WarpSmem& sm = smem[wid];
-    GameCtx gm;
-    load_ctx(P, g, lane, gm, sm);
-    Stats st = {0, 0, 0, 0, 0, 0};
-    const int a = actions[g];
-    uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
+    const int g = gm.g;
     const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
-    const int item = a >= 0 ? a / ge.W : -1;
+    const int item = a >= 0 ? div_w(ge, a) : -1;
     if (a < 0 || a >= ge.A || !((rem >> item) & 1u)) {  // reference: assert sum(sum(item)) > 0, BinPackingGame.py:69
         if (lane == 0) P.status[g] = -1;
-        return;
+        return -1;
     }
     const int x = a - item * ge.W;
     rec = apply_move(ge, rec, lane, item, sm.items[item] & 0xff, sm.items[item] >> 8, x);
@@ -541,9 +540,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_advance(Params P, const 
     __syncwarp();
     const uint32_t nrem = __shfl_sync(FULL, rec, REC_REM);
     const uint32_t mine = valid_words<0>(ge, sm.occ, sm.items, nrem, lane, sm.vw, sm.tab);
+    int status = 0;
     if (!__any_sync(FULL, mine != 0u)) {
         double score;
         const int r = terminal_value(ge, gm.rc, rec, lane, &score);
+        status = 1;
         if (lane == 0) {
             P.status[g] = 1;
             P.ep_r[g] = r;
@@ -556,7 +557,62 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_advance(Params P, const 
     }
     if (gm.err) {
         if (lane == 0) P.status[g] = -gm.err;
+        status = -gm.err;
         gm.err = 0;
+    }
+    return status;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_advance(Params P, const int32_t* actions) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    if (g >= P.G) return;
+    if (P.status[g] != 0) return;
+    WarpSmem& sm = smem[wid];
+    GameCtx gm;
+    load_ctx(P, g, lane, gm, sm);
+    Stats st = {0, 0, 0, 0, 0, 0};
+    uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
+    if (advance_game(P, gm, sm, lane, actions[g], rec, st) == -1) return;
+    store_ctx(P, gm, lane);
+    flush_stats(P, st, lane);
+}
+
+// Whole self-play episodes in ONE launch (stub evaluators): per game, loop {numMCTSSims simulations -> visit counts out
+// -> choose -> play the move} until the episode ends.  Removes the per-move launch boundaries: a game that needs longer
+// for one move no longer holds back the others (the only tail left is the end of the batch).
+template <int STUB, int HC>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7)
+k_episode(Params P, int mode, unsigned long long seed, int max_moves, int32_t* counts_out, int32_t* actions_out) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    if (g >= P.G) return;
+    if (P.status[g] != 0) return;
+    WarpSmem& sm = smem[wid];
+    GameCtx gm;
+    load_ctx(P, g, lane, gm, sm);
+    Stats st = {0, 0, 0, 0, 0, 0};
+    uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
+    int move_no = P.moves_done[g];
+    int done = P.sims_done[g];
+    const size_t GA = (size_t)P.G * P.geom.A;
+    for (int m = 0; m < max_moves; ++m) {
+        while (done < P.num_sims) {
+            if (simulate<STUB, HC>(P, gm, sm, lane, st) != 0) break;
+            done++;
+            st.sims++;
+        }
+        if (gm.err) break;
+        if (counts_out) root_counts_warp(P, g, gm.root_node, lane, counts_out + m * GA + (size_t)g * P.geom.A);
+        int a = lane == 0 ? choose_action(P, g, gm.root_node, move_no, mode, seed) : 0;
+        a = __shfl_sync(FULL, a, 0);
+        if (actions_out && lane == 0) actions_out[(size_t)m * P.G + g] = a;
+        const int status = advance_game(P, gm, sm, lane, a, rec, st);
+        move_no++;
+        done = 0;
+        if (status != 0) break;
     }
     store_ctx(P, gm, lane);
     flush_stats(P, st, lane);
@@ -1034,21 +1090,38 @@ extern "C" int bpp_engine_roots(bpp_engine* e, uint32_t* roots_out_dev, void* st
     return BPP_OK;
 }
 
+template <int STUB>
+static void launch_episode(bpp_engine* e, int mode, uint64_t seed, int moves, int32_t* counts, int32_t* actions,
+                           void* stream) {
+    const int grid = grid_warps(e->P.G), block = WARPS_PER_CTA * 32;
+    const unsigned long long sd = (unsigned long long)seed;
+    switch (e->P.geom.H) {
+        case 15: k_episode<STUB, 15><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions); break;
+        case 20: k_episode<STUB, 20><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions); break;
+        default: k_episode<STUB, 0><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions); break;
+    }
+}
+
 extern "C" int bpp_engine_play_stub(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed, int max_moves,
                                     int32_t* counts_out_dev, int32_t* actions_out_dev, int32_t* moves_run_host,
                                     void* stream) {
     if (!e) return set_err(BPP_E_INVALID, "null argument");
-    // every move places exactly one item, so an episode has at most N moves; finished games idle
+    if (e->leaf_parked) return set_err(BPP_E_STATE, "leaves are parked; call bpp_engine_expand_backup first");
+    if (choose_mode < 0 || choose_mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", choose_mode);
+    // every move places exactly one item, so an episode has at most N moves
     const int moves = max_moves > 0 && max_moves < e->P.geom.N ? max_moves : e->P.geom.N;
-    const size_t GA = (size_t)e->P.G * e->P.geom.A;
-    for (int m = 0; m < moves; ++m) {
-        int rc;
-        if ((rc = bpp_engine_search_stub(e, stub_kind, stream))) return rc;
-        if (counts_out_dev && (rc = bpp_engine_root_counts(e, counts_out_dev + m * GA, stream))) return rc;
-        int32_t* act = actions_out_dev ? actions_out_dev + (size_t)m * e->P.G : e->d_actions;
-        if ((rc = bpp_engine_choose(e, choose_mode, seed, act, stream))) return rc;
-        if ((rc = bpp_engine_advance(e, act, stream))) return rc;
+    const size_t G = (size_t)e->P.G, GA = G * e->P.geom.A;
+    // rows of moves a game does not play: counts 0, action -1
+    if (counts_out_dev) CUDA_TRY(cudaMemsetAsync(counts_out_dev, 0, (size_t)moves * GA * sizeof(int32_t), S(stream)));
+    if (actions_out_dev) CUDA_TRY(cudaMemsetAsync(actions_out_dev, 0xff, (size_t)moves * G * sizeof(int32_t), S(stream)));
+    switch (stub_kind) {
+        case BPP_STUB_U: launch_episode<1>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, stream); break;
+        case BPP_STUB_V: launch_episode<2>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, stream); break;
+        case BPP_STUB_H: launch_episode<3>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, stream); break;
+        case BPP_STUB_D: launch_episode<4>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, stream); break;
+        default: return set_err(BPP_E_INVALID, "unknown stub kind %d", stub_kind);
     }
+    LAUNCH_CHECK(e);
     if (moves_run_host) *moves_run_host = moves;
     return BPP_OK;
 }
@@ -1066,8 +1139,6 @@ extern "C" int bpp_engine_play_stub_host(bpp_engine* e, int stub_kind, int choos
     }
     if (!e->d_actions_all && (rc = dev_alloc(e, &e->d_actions_all, N * G))) return rc;
     if ((rc = bpp_engine_reset_host(e, items_wh_host, total_area_host, bl_host, tie_host, stream))) return rc;
-    CUDA_TRY(cudaMemsetAsync(e->d_actions_all, 0xff, N * G * sizeof(int32_t), S(stream)));
-    if (counts_out_host) CUDA_TRY(cudaMemsetAsync(e->d_counts_all, 0, N * G * A * sizeof(int32_t), S(stream)));
     if ((rc = bpp_engine_play_stub(e, stub_kind, choose_mode, seed, 0, counts_out_host ? e->d_counts_all : nullptr,
                                    e->d_actions_all, nullptr, stream)))
         return rc;

@@ -112,3 +112,39 @@ def test_many_games_mixed_instances_match_single_game_runs():
     assert (st["done"].cpu().numpy() == 1).all()
     s = eng.stats()
     assert s["sims"] == sum(200 * len(sel[k]["actions"]) for k in order)
+
+
+def test_whole_episode_kernel_equals_the_per_move_kernels():
+    """bpp_engine_play_stub (one launch: search -> counts -> choose -> play for all moves) must reproduce, bit for bit,
+    the per-move sequence search_stub / root_counts / choose / advance with the same sampling seed."""
+    from resource_packing_self_play_b200 import _lib
+    from resource_packing_self_play_b200.engine import SearchEngine
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    W, H, N, G, SIMS = 15, 15, 10, 256, 60
+    heights = (np.arange(G) % 14 + 2).astype(np.int32)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(G) + 77, heights)
+    area = (W * heights).astype(np.int32)
+    bl = np.full(G, 0.6501)
+    for mode in (_lib.CHOOSE_SAMPLE, _lib.CHOOSE_GREEDY, _lib.CHOOSE_ARGMAX_FIRST):
+        a = SearchEngine(W, H, N, G, SIMS, 1.0)
+        a.reset(items, area, bl)
+        counts_a, actions_a = a.play_stub("D", mode, seed=11)
+        a.check()
+        b = SearchEngine(W, H, N, G, SIMS, 1.0)
+        b.reset(items, area, bl)
+        counts_b, actions_b = [], []
+        for mv in range(N):
+            b.begin_move()
+            b.search_stub("D")
+            counts_b.append(b.root_counts())
+            act = b.choose(mode, seed=11)
+            actions_b.append(act)
+            b.advance(act)
+        b.check()
+        assert torch.equal(actions_a, torch.stack(actions_b))
+        played = (actions_a >= 0)[:, :, None]
+        assert torch.equal(counts_a * played, torch.stack(counts_b) * played)
+        sa, sb = a.status(), b.status()
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), k
+        assert a.stats()["sims"] == b.stats()["sims"]
