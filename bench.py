@@ -350,7 +350,10 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "kernel": "k_episode<STUB_U,15> (whole episodes, one launch per step)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
-                         "traffic": None, "algorithmic_bytes_per_sim": bytes_per_sim,
+                         # DRAM read+write bytes of one k_episode launch from the committed ncu --set full capture
+                         # (profiles/r01_k_episode_ncu_summary.txt); only valid for the default configuration
+                         "traffic": 5.225e9 if (G == 4096 and args.sims == 200) else None,
+                         "algorithmic_bytes_per_sim": bytes_per_sim,
                          "edges_per_sim": d_bar, "expansions_per_sim": e_bar, "sims_per_launch": sims_per_launch,
                          "kernel_ms_per_launch": search_ms / n_search,
                          "kernel_share_of_step": search_ms / (ms if world == 1 else search_ms_max or ms),

@@ -73,6 +73,12 @@ int bpp_version(void);
 int bpp_env_valid_moves(int W, int H, int N, int n, const uint32_t *recs_dev, const int32_t *items_wh_dev,
                         uint8_t *valid_out_dev, void *stream);
 
+/* BinPackingGame.getBinItem (BinPackingGame.py:118-120) for compact states: the dense evaluator / learner input
+ * planes_out_dev float32 [n][N+1][H][W] (plane 0 = bin occupancy, plane i+1 = item i's [0:h, 0:w] block while it is
+ * still to be placed). */
+int bpp_env_planes(int W, int H, int N, int n, const uint32_t *recs_dev, const int32_t *items_wh_dev,
+                   float *planes_out_dev, void *stream);
+
 /* BinPackingGame.getNextState (BinPackingGame.py:58-76) + Bin.execute_move (BinPackingLogic.py:95-109), including
  * the silent truncation when fewer than h strip rows are empty.  actions_dev: int32 [n] (item*W + x; the item must
  * be remaining).  recs_out_dev: uint32 [n][32]. */

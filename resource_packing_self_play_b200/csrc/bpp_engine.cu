@@ -726,6 +726,31 @@ k_env_ended(EnvArgs E, const int32_t* total_area, const int32_t* max_h, const do
     }
 }
 
+// dense planes of arbitrary compact states (learner input batches): out float32 [n][N+1][H][W]
+__global__ void k_env_planes(EnvArgs E, float* out) {
+    const Geom& ge = E.geom;
+    const int per = (ge.N + 1) * ge.H * ge.W;
+    const long long total = (long long)E.n * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        int r = (int)(i - (long long)b * per);
+        const int c = r / (ge.H * ge.W);
+        r -= c * ge.H * ge.W;
+        const int y = r / ge.W, x = r - y * ge.W;
+        const uint32_t* rec = E.recs + (size_t)b * REC_WORDS;
+        float v;
+        if (c == 0) {
+            v = (float)((rec[y] >> x) & 1u);
+        } else {
+            const int it = c - 1;
+            const int32_t* wh = E.items_wh + ((size_t)b * ge.N + it) * 2;
+            v = (((rec[REC_REM] >> it) & 1u) && y < wh[1] && x < wh[0]) ? 1.f : 0.f;
+        }
+        out[i] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // returns the index of the leaf slot that will hold the sum of [base, base+n)
@@ -1221,6 +1246,18 @@ extern "C" int bpp_env_valid_moves(int W, int H, int N, int n, const uint32_t* r
     if (n == 0) return BPP_OK;
     if (!valid_out_dev) return set_err(BPP_E_INVALID, "null output");
     k_env_valid<<<grid_warps(n), WARPS_PER_CTA * 32, 0, S(stream)>>>(E, valid_out_dev);
+    ENV_LAUNCH_CHECK();
+    return BPP_OK;
+}
+
+extern "C" int bpp_env_planes(int W, int H, int N, int n, const uint32_t* recs_dev, const int32_t* items_wh_dev,
+                              float* planes_out_dev, void* stream) {
+    EnvArgs E;
+    int rc = env_args(W, H, N, n, recs_dev, items_wh_dev, &E);
+    if (rc) return rc;
+    if (n == 0) return BPP_OK;
+    if (!planes_out_dev) return set_err(BPP_E_INVALID, "null output");
+    k_env_planes<<<592, 256, 0, S(stream)>>>(E, planes_out_dev);
     ENV_LAUNCH_CHECK();
     return BPP_OK;
 }

@@ -100,6 +100,15 @@ class EnvOps:
         call("bpp_env_valid_moves", self.W, self.H, self.N, n, _ptr(recs), _ptr(items), _ptr(out), _stream())
         return out
 
+    def planes(self, recs, items_wh):
+        """dense float32 (n, N+1, H, W) input planes of compact states (items_wh per state)"""
+        recs = self._recs(recs)
+        items = _dev(items_wh, torch.int32, self.device)
+        n = recs.shape[0]
+        out = torch.empty((n, self.N + 1, self.H, self.W), dtype=torch.float32, device=self.device)
+        call("bpp_env_planes", self.W, self.H, self.N, n, _ptr(recs), _ptr(items), _ptr(out), _stream())
+        return out
+
     def next_state(self, recs, items_wh, actions):
         recs = self._recs(recs)
         items = _dev(items_wh, torch.int32, self.device)
