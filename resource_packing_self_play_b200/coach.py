@@ -173,6 +173,97 @@ class CoachBPP:
             self.seeds_iter = seeds_iter
             self.save_rewards_list()
 
+    # ------------------------------------------------------------------------------------------------------------------
+    def learn_batched(self, games_per_iter, num_iters=None, checkpoint=True):
+        """Lockstep / multi-GPU counterpart of learn() (BASELINE.json configs[3]).  Per iteration: rank 0 draws the
+        generator height and `games_per_iter` seeds (CoachBPP.py:117-127) and broadcasts them; every rank plays its
+        contiguous shard of the games in lockstep (no collective); scores and compact examples are all-gathered so that
+        every rank holds the same rewards_list and replay history; the learner runs data-parallel with one flat
+        gradient all-reduce per step.  Differences from learn(), by construction: all games of an iteration see the
+        rewards_list of the iteration's start, and the scores are appended in global game order afterwards.
+        Returns a list of per-iteration dicts (timings in seconds, mean score, losses)."""
+        import time
+        from . import distributed as D
+        from .engine import EnvOps
+        rank, ws = D.world()
+        dev = self.nnet.device
+        g = self.game
+        if ws > 1:
+            D.broadcast_parameters(self.nnet.nnet)
+            self.nnet.sync_weights()
+        ops = EnvOps(g.bin_width, g.bin_height, g.num_items, dev.index or 0)
+        history = getattr(self, "_compact_history", [])
+        out = []
+        for i in range(1, (num_iters or self.args.numIters) + 1):
+            t0 = time.perf_counter()
+            hdr = torch.zeros(games_per_iter + 1, dtype=torch.int64, device=dev)
+            if rank == 0:
+                np.random.seed()
+                h = np.random.randint(self.args.binH_min, self.args.binH + 1)
+                hdr[0] = int(h)
+                hdr[1:] = torch.from_numpy(np.random.randint(int(1e5), size=games_per_iter)).to(dev)
+            if ws > 1:
+                torch.distributed.broadcast(hdr, 0)
+            h = int(hdr[0])
+            seeds = hdr[1:].cpu().numpy()
+            self.gen.bin_height = h
+            self.items_total_area = h * self.gen.bin_width
+            lo, hi = D.shard_range(games_per_iter, rank, ws)
+            items = self.gen.items_batch(seeds[lo:hi])
+            areas = np.full(hi - lo, self.items_total_area, dtype=np.int32)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            compact, score, r = self.executeEpisodesBatched(items, areas, greedy=i > self.args.iterStepThreshold,
+                                                            expand=False)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            compact = D.gather_examples(compact, dev)
+            scores = D.all_gather_variable(torch.from_numpy(np.asarray(score)).to(dev)).cpu().numpy()
+            # rewards buffer (CoachBPP.py:134-139): append every score, then drop minima until numScoresForRank remain
+            # (repeated `pop(argmin)` == remove the smallest, earliest-first; survivors keep their order)
+            rl = np.asarray(list(self.rewards_list) + [float(x) for x in scores], dtype=np.float64)
+            extra = len(rl) - int(self.args.numScoresForRank)
+            if extra > 0:
+                drop = np.lexsort((np.arange(len(rl)), rl))[:extra]
+                rl = np.delete(rl, drop)
+            self.rewards_list = [float(x) for x in rl]
+            self.log_fn({"iter mean reward": float(np.mean(scores)),
+                         "optimality percentage": float(np.mean(scores == 1.0)),
+                         "min reward": float(np.min(scores)), "max reward": float(np.max(scores))}, step=i)
+            # flatten the iteration's examples: one row per played move
+            moves = compact["moves"]
+            N, G = compact["roots"].shape[0], compact["roots"].shape[1]
+            played = np.arange(N)[:, None] < moves[None, :]
+            mi, gi = np.nonzero(played)
+            counts = compact["counts"][mi, gi].astype(np.float32)
+            if i > self.args.iterStepThreshold:
+                pis = np.zeros_like(counts)
+                pis[np.arange(len(mi)), compact["actions"][mi, gi]] = 1.0
+            else:
+                pis = counts / counts.sum(axis=1, keepdims=True)
+            history.append({"recs": compact["roots"][mi, gi], "items": compact["items"][gi], "pis": pis,
+                            "vs": compact["r"][gi].astype(np.float32)})
+            if len(history) > self.args.numItersForTrainExamplesHistory:
+                history.pop(0)
+            self._compact_history = history
+            recs_t = torch.from_numpy(np.concatenate([e["recs"] for e in history]).view(np.int32)).to(dev)
+            items_t = torch.from_numpy(np.concatenate([e["items"] for e in history]).astype(np.int32)).to(dev)
+            pis_t = torch.from_numpy(np.concatenate([e["pis"] for e in history])).to(dev)
+            vs_t = torch.from_numpy(np.concatenate([e["vs"] for e in history])).to(dev)
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            if checkpoint and rank == 0:
+                self.nnet.save_checkpoint(folder=self.args.checkpoint, filename='temp.pth.tar')
+            l_pi, l_v = self.nnet.train_compact(recs_t, items_t, pis_t, vs_t, ops)
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+            if checkpoint and rank == 0:
+                self.save_rewards_list()
+            out.append({"iter": i, "games": int(G), "examples": int(len(mi)), "history_examples": int(recs_t.shape[0]),
+                        "mean_score": float(np.mean(scores)), "t_setup": t1 - t0, "t_selfplay": t2 - t1,
+                        "t_gather": t3 - t2, "t_train": t4 - t3, "loss_pi": l_pi, "loss_v": l_v})
+        return out
+
     def save_rewards_list(self):  # CoachBPP.py:198-202
         file_n = 'rewards_list_' + str(self.args.numItems) + '_items.pkl'
         if not os.path.exists(self.args.checkpoint):

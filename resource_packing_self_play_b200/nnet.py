@@ -190,6 +190,42 @@ class NNetWrapper:
         self.nnet.eval()
         self.sync_weights()
 
+    def train_compact(self, recs, items_wh, pis, vs, ops, steps_per_epoch=None, seed=None):
+        """Learner on compact examples that already live on the device (the batched / multi-GPU path).
+        recs int32 (M, 32), items_wh int32 (M, N, 2), pis float32 (M, A), vs float32 (M,); `ops` = EnvOps (builds the
+        dense input planes of each minibatch on the device).  Same optimiser, losses and sampling-with-replacement as
+        `train` (NNet.py:27-67); with torch.distributed initialised every rank draws its own minibatches and the
+        gradients are averaged with one flat all-reduce per step.  Returns (mean pi loss, mean v loss) of the last
+        epoch."""
+        from .distributed import world
+        rank, ws = world()
+        M = recs.shape[0]
+        optimizer = torch.optim.Adam(self.nnet.parameters())
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed((seed if seed is not None else int(np.random.randint(1 << 30))) * 977 + rank)
+        bs = int(self.args.batch_size)
+        if steps_per_epoch is None:
+            steps_per_epoch = max(1, int(M / (bs * ws)))
+        pi_m, v_m = AverageMeter(), AverageMeter()
+        for epoch in range(self.args.epochs):
+            self.nnet.train()
+            pi_m, v_m = AverageMeter(), AverageMeter()
+            for _ in range(steps_per_epoch):
+                ids = torch.randint(0, M, (bs,), device=self.device, generator=gen)
+                boards = ops.planes(recs[ids].contiguous(), items_wh[ids].contiguous())
+                out_pi, out_v = self.nnet(boards)
+                l_pi = self.loss_pi(pis[ids], out_pi)
+                l_v = self.loss_v(vs[ids], out_v)
+                optimizer.zero_grad(set_to_none=True)
+                (l_pi + l_v).backward()
+                allreduce_gradients(self.nnet)
+                optimizer.step()
+                pi_m.update(float(l_pi.detach()), bs)
+                v_m.update(float(l_v.detach()), bs)
+        self.nnet.eval()
+        self.sync_weights()
+        return pi_m.avg, v_m.avg
+
     def loss_pi(self, targets, outputs):  # NNet.py:87-88
         return -torch.sum(targets * outputs) / targets.size()[0]
 

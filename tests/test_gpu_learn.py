@@ -72,3 +72,33 @@ def test_examples_save_and_load_round_trip(tmp_path):
     coach.trainExamplesHistory = []
     coach.loadTrainExamples()
     assert coach.skipFirstSelfPlay and len(coach.trainExamplesHistory[0]) == n
+
+
+def test_learn_batched_single_rank(tmp_path):
+    coach, net, args = _setup(tmp_path, numMCTSSims=10, epochs=1, batch_size=32, numScoresForRank=20,
+                              iterStepThreshold=1)
+    before = {k: v.clone() for k, v in net.nnet.state_dict().items()}
+    log = coach.learn_batched(games_per_iter=48, num_iters=2)
+    assert len(log) == 2 and log[0]["games"] == 48 and log[0]["examples"] >= 48 * 4
+    assert log[1]["history_examples"] == log[0]["examples"] + log[1]["examples"]
+    assert len(coach.rewards_list) == 20 and min(coach.rewards_list) >= 0.0
+    # the buffer keeps the LARGEST scores (minima are dropped, CoachBPP.py:136-139)
+    assert np.isfinite(log[1]["loss_pi"]) and np.isfinite(log[1]["loss_v"])
+    assert any(not torch.equal(before[k], v) for k, v in net.nnet.state_dict().items())
+    assert os.path.exists(os.path.join(str(tmp_path), "temp.pth.tar"))
+
+
+def test_env_planes_match_host_unpack():
+    from resource_packing_self_play_b200.engine import EnvOps, pack_states, unpack_states
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    rng = np.random.RandomState(5)
+    W, H, N, n = 20, 20, 10, 40
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(n), rng.randint(2, 21, size=n))
+    recs = np.zeros((n, 32), dtype=np.uint32)
+    recs[:, :H] = rng.randint(0, 1 << W, size=(n, H))
+    recs[:, 28] = rng.randint(0, 1 << N, size=n)
+    planes = EnvOps(W, H, N).planes(recs, items).cpu().numpy()
+    want = unpack_states(recs, items, W, H, N)
+    assert planes.shape == (n, N + 1, H, W) and np.array_equal(planes, want.astype(np.float32))
+    r2, i2 = pack_states(want, W, H, N)
+    assert np.array_equal(r2[:, :H], recs[:, :H]) and np.array_equal(r2[:, 28], recs[:, 28])
