@@ -28,6 +28,11 @@ def _dev(x, dtype, device):
     return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
 
 
+def _devidx(device):
+    """None -> the calling process' current CUDA device (one process per GPU: torch.cuda.set_device(LOCAL_RANK))"""
+    return torch.cuda.current_device() if device is None else int(device)
+
+
 def _ptr(t):
     if t is None:
         return C.c_void_p(0)
@@ -87,10 +92,10 @@ def unpack_states(recs, items_wh, W, H, N, dtype=np.int64):
 class EnvOps:
     """Batched stateless environment ops on device tensors (bpp_env_* entry points)."""
 
-    def __init__(self, W, H, N, device=0):
+    def __init__(self, W, H, N, device=None):
         _lib.load()
         self.W, self.H, self.N, self.A = W, H, N, W * N
-        self.device = torch.device("cuda", device)
+        self.device = torch.device("cuda", _devidx(device))
 
     def valid_moves(self, recs, items_wh):
         recs = self._recs(recs)
@@ -147,10 +152,11 @@ class EnvOps:
 class SearchEngine:
     """G lockstep games with device-resident search graphs (one handle per device)."""
 
-    def __init__(self, W, H, N, G, num_sims, cpuct=1.0, device=0, node_cap=0, edge_cap=0):
+    def __init__(self, W, H, N, G, num_sims, cpuct=1.0, device=None, node_cap=0, edge_cap=0):
         _lib.load()
         self.W, self.H, self.N, self.G, self.A = W, H, N, G, W * N
         self.num_sims, self.cpuct = int(num_sims), float(cpuct)
+        device = _devidx(device)
         self.device = torch.device("cuda", device)
         cfg = Config(W, H, N, G, int(num_sims), float(cpuct), int(node_cap), int(edge_cap), int(device))
         h = C.c_void_p()

@@ -16,7 +16,7 @@ class BinPackingGame:
     """Rules facade, same surface as BinPackingGame.py:8-218 (dead Othello leftovers and the disabled, buggy
     getSymmetries are not provided; see DESIGN.md "out of scope")."""
 
-    def __init__(self, bin_width, bin_height, num_items, n, device=0):  # BinPackingGame.py:15-22
+    def __init__(self, bin_width, bin_height, num_items, n, device=None):  # BinPackingGame.py:15-22
         self.bin_width = bin_width
         self.bin_height = bin_height
         self.num_items = num_items

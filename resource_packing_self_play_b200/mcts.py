@@ -16,11 +16,11 @@ from .engine import REC_REM, SearchEngine, pack_states, ranked_threshold
 
 
 class MCTS:
-    def __init__(self, game, nnet, args, device=0):  # MCTS_bpp.py:16-26
+    def __init__(self, game, nnet, args, device=None):  # MCTS_bpp.py:16-26
         self.game = game
         self.nnet = nnet
         self.args = args
-        self.device = device
+        self.device = device if device is not None else getattr(getattr(nnet, "device", None), "index", None)
         self._eng = None
         self._items = None    # (N, 2) dims known for this episode (0,0 = never seen)
         self._consts = None   # (total_area, bl, max_h)
@@ -115,8 +115,10 @@ class MCTS:
 class BatchedMCTS:
     """G lockstep games: the batched counterpart of MCTS.getActionProb + CoachBPP.executeEpisode's move loop."""
 
-    def __init__(self, game, nnet, args, G, device=0):
+    def __init__(self, game, nnet, args, G, device=None):
         self.game, self.nnet, self.args, self.G = game, nnet, args, G
+        if device is None:
+            device = getattr(getattr(nnet, "device", None), "index", None)
         self.eng = SearchEngine(game.bin_width, game.bin_height, game.num_items, G, int(args.numMCTSSims),
                                 float(args.cpuct), device=device)
         self.steps = 0

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 from . import _lib
 from ._lib import call
 from .distributed import allreduce_gradients
-from .engine import _ptr, _stream, pack_states
+from .engine import _devidx, _ptr, _stream, pack_states
 from .utils import AverageMeter
 
 
@@ -80,8 +80,9 @@ class BinPackingNNet(nn.Module):  # BinpackingNNet.py:50-81
 class DeviceNet:
     """Handle of the CUDA forward (bpp_net_*)."""
 
-    def __init__(self, W, H, N, max_batch, device=0):
+    def __init__(self, W, H, N, max_batch, device=None):
         _lib.load()
+        device = _devidx(device)
         self.W, self.H, self.N, self.A = W, H, N, W * N
         self.max_batch = max_batch
         self.device = torch.device("cuda", device)
@@ -135,7 +136,8 @@ class DeviceNet:
 class NNetWrapper:
     """Same surface as NNet.py:17-111: predict / train / save_checkpoint / load_checkpoint."""
 
-    def __init__(self, game, args, max_batch=8192, device=0, precision="bf16"):
+    def __init__(self, game, args, max_batch=8192, device=None, precision="bf16"):
+        device = _devidx(device)
         self.args = args
         self.game = game
         self.nnet = BinPackingNNet(game, args)
