@@ -93,8 +93,9 @@ class CoachBPP:
         g = self.game
         N, A = g.num_items, g.getActionSize()
         bm = getattr(self, "_bm", None)
-        if bm is None or bm.G != G or bm.nnet is not self.nnet:
+        if bm is None or bm.G != G:
             bm = self._bm = BatchedMCTS(g, self.nnet, self.args, G)
+        bm.nnet = self.nnet  # the search engine is independent of the evaluator: swapping nets keeps the pools
         bm.reset(items_batch, np.asarray(total_areas, dtype=np.int32), self.rewards_list)
         eng = bm.eng
         if seed is None:
