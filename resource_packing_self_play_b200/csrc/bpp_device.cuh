@@ -255,7 +255,10 @@ __host__ __device__ __forceinline__ int edge_units(int nv) {
 
 // PUCT arg-max with the reference's exact operation order and first-max tie-break (ascending action == ascending
 // edge index).  u = Q + ((cpuct*P)*sqrt(Ns)) / (1+Nsa) for visited edges, (cpuct*P)*sqrt(Ns+1e-8) otherwise.
-__device__ __forceinline__ int puct_select(const EdgeBlock& eb, int nv, int Ns, double cpuct, int lane) {
+// sqrt_tab: optional host-computed tables sqrt(n) [0..tab_n) and sqrt(n + 1e-8) [tab_n..2*tab_n) — the same correctly
+// rounded IEEE values __dsqrt_rn returns, as one broadcast load instead of a ~50-instruction software sequence.
+__device__ __forceinline__ int puct_select(const EdgeBlock& eb, int nv, int Ns, double cpuct, int lane,
+                                           const double* __restrict__ sqrt_tab, int tab_n) {
     double bu = __longlong_as_double((long long)0xfff0000000000000ull);  // -inf
     int be = 0x7fffffff;
     // first round from registers: issue all loads, then decide which square root is needed (the root has every edge
@@ -271,8 +274,14 @@ __device__ __forceinline__ int puct_select(const EdgeBlock& eb, int nv, int Ns, 
         need_sq |= n > 0;
         need_sqe |= n <= 0;
     }
-    const double sq = __any_sync(FULL, need_sq) ? __dsqrt_rn((double)Ns) : 0.0;
-    const double sqe = __any_sync(FULL, need_sqe) ? __dsqrt_rn(__dadd_rn((double)Ns, 1e-8)) : 0.0;
+    double sq, sqe;
+    if (Ns < tab_n) {
+        sq = __ldg(sqrt_tab + Ns);
+        sqe = __ldg(sqrt_tab + tab_n + Ns);
+    } else {
+        sq = __any_sync(FULL, need_sq) ? __dsqrt_rn((double)Ns) : 0.0;
+        sqe = __any_sync(FULL, need_sqe) ? __dsqrt_rn(__dadd_rn((double)Ns, 1e-8)) : 0.0;
+    }
     if (in0) {
         const double cp = __dmul_rn(cpuct, p0);
         double u = n0 > 0 ? __dadd_rn(q0, __ddiv_rn(__dmul_rn(cp, sq), (double)(1 + n0))) : __dmul_rn(cp, sqe);

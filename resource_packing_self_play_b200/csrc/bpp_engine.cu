@@ -89,6 +89,8 @@ struct Params {
     uint32_t* table;
     unsigned long long* edges;
     unsigned long long* stats;  // [8]
+    const double* sqrt_tab;     // [2][sqrt_n]: sqrt(n), sqrt(n + 1e-8)
+    int sqrt_n;
 };
 
 struct __align__(16) WarpSmem {
@@ -300,7 +302,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
         const int nv = (int)(meta & 0xffffu);
         const int nvp = (nv + 3) & ~3;
         EdgeBlock eb(gm.edges + off, nvp);
-        const int e = puct_select(eb, nv, Ns, P.cpuct, lane);
+        const int e = puct_select(eb, nv, Ns, P.cpuct, lane, P.sqrt_tab, P.sqrt_n);
         const int act = eb.ACT[e];
         int child = eb.NC[e].y;
         if (lane == depth) {
@@ -900,6 +902,24 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     P.edge_cap = cap;
     ALLOC(P.edges, G * (size_t)cap);
 #undef ALLOC
+#define ALLOC2(ptr, count)                         \
+    if ((rc = dev_alloc(e, &(ptr), (count))) != 0) { \
+        bpp_engine_destroy(e);                     \
+        return rc;                                 \
+    }
+    {   // Ns[s] never exceeds the simulations of an episode (num_sims per move, at most N moves)
+        const int tn = cfg->num_sims * cfg->N + 2;
+        std::vector<double> tab(2 * (size_t)tn);
+        for (int i = 0; i < tn; ++i) {
+            tab[i] = sqrt((double)i);
+            tab[tn + i] = sqrt((double)i + 1e-8);
+        }
+        double* d_tab = nullptr;
+        ALLOC2(d_tab, 2 * (size_t)tn);
+        CUDA_TRY(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        P.sqrt_tab = d_tab;
+        P.sqrt_n = tn;
+    }
     CUDA_TRY(cudaMemset(P.stats, 0, 8 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(P.status, 0xff, G * sizeof(int)));  // not reset yet
     CUDA_TRY(cudaMemset(P.pend_depth, 0xff, G * sizeof(int)));
