@@ -134,6 +134,13 @@ int bpp_engine_set_roots(bpp_engine *e, const uint32_t *roots_dev, void *stream)
 int bpp_engine_set_max_h(bpp_engine *e, const int32_t *max_h_dev, void *stream);
 /* Change the per-move simulation budget (args.numMCTSSims); MCTS.search() is one simulation: budget 1. */
 int bpp_engine_set_num_sims(bpp_engine *e, int num_sims);
+/* Lockstep mode: cap the simulations one game runs inside one bpp_engine_select launch (0 = no cap, the default).  A game
+ * whose simulations keep ending on terminal states parks no leaf; with a cap it continues in the next step instead of
+ * delaying the leaf batch of every other game.  The order of a game's simulations, hence every result, is unchanged. */
+int bpp_engine_set_select_cap(bpp_engine *e, int max_sims_per_launch);
+/* games that stopped at the cap in the last select (valid after bpp_engine_leaf_count); the move is finished when both
+ * the leaf count and this count are 0 */
+int bpp_engine_unfinished(bpp_engine *e, int32_t *count_host);
 /* v returned by the most recent simulation of each game (the return value of MCTS.search, MCTS_bpp.py:83,104,139).
  * values_out_dev: float64 [G]. */
 int bpp_engine_last_values(bpp_engine *e, double *values_out_dev, void *stream);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "bpp_engine_set_max_h": [_vp, _vp, _vp],
     "bpp_engine_set_num_sims": [_vp, _i32],
     "bpp_engine_last_values": [_vp, _vp, _vp],
+    "bpp_engine_set_select_cap": [_vp, _i32],
+    "bpp_engine_unfinished": [_vp, C.POINTER(_i32)],
     "bpp_engine_select": [_vp, _vp],
     "bpp_engine_leaf_count": [_vp, C.POINTER(_i32), _vp],
     "bpp_engine_leaf_buffers": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],

@@ -91,6 +91,7 @@ struct Params {
     unsigned long long* stats;  // [8]
     const double* sqrt_tab;     // [2][sqrt_n]: sqrt(n), sqrt(n + 1e-8)
     int sqrt_n;
+    int select_cap;             // lockstep: simulations per game and select launch (0 = until a leaf is parked)
 };
 
 struct __align__(16) WarpSmem {
@@ -346,13 +347,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_search(Params P) {
     load_ctx(P, g, lane, gm, sm);
     Stats st = {0, 0, 0, 0, 0, 0};
     int done = P.sims_done[g];
-    while (done < P.num_sims) {
+    // lockstep mode: a game whose simulations keep ending on terminal states needs no evaluator; capping its work per
+    // launch keeps it from holding back the leaf batch of all other games (it simply continues in the next step)
+    const int stop = (STUB == 0 && P.select_cap > 0) ? min(P.num_sims, done + P.select_cap) : P.num_sims;
+    while (done < stop) {
         const int rc = simulate<STUB, HC>(P, gm, sm, lane, st);
         if (rc != 0) break;  // parked leaf (counted when it is expanded) or overflow
         done++;
         st.sims++;
     }
     if (lane == 0) P.sims_done[g] = done;
+    if (STUB == 0 && lane == 0 && done < P.num_sims && P.pend_depth[g] < 0) atomicAdd(P.leaf_count + 1, 1);
     store_ctx(P, gm, lane);
     flush_stats(P, st, lane);
 }
@@ -788,6 +793,7 @@ struct bpp_engine {
     int64_t bytes = 0;
     unsigned long long launches = 0;
     bool leaf_parked = false;
+    int unfinished = 0;  // games that hit the select cap in the last select (still owe simulations)
     int32_t* d_actions = nullptr;  // scratch for play_stub
     int32_t* d_items = nullptr;    // staging for the *_host entry points
     int32_t* d_area = nullptr;
@@ -875,7 +881,7 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     ALLOC(P.pend_leaf, G);
     ALLOC(P.pend_path, G * 32);
     ALLOC(P.pend_valid, G * MAX_AW);
-    ALLOC(P.leaf_count, 1);
+    ALLOC(P.leaf_count, 2);  // [0] parked leaves, [1] games that stopped at the per-launch cap
     ALLOC(P.leaf_game, G);
     ALLOC(P.leaf_rec, G * REC_WORDS);
     ALLOC(P.stats, 8);
@@ -923,7 +929,7 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     CUDA_TRY(cudaMemset(P.stats, 0, 8 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(P.status, 0xff, G * sizeof(int)));  // not reset yet
     CUDA_TRY(cudaMemset(P.pend_depth, 0xff, G * sizeof(int)));
-    CUDA_TRY(cudaMemset(P.leaf_count, 0, sizeof(int)));
+    CUDA_TRY(cudaMemset(P.leaf_count, 0, 2 * sizeof(int)));
     CUDA_TRY(cudaMallocHost(&e->h_status, G * sizeof(int)));
     *out = e;
     return BPP_OK;
@@ -997,6 +1003,18 @@ extern "C" int bpp_engine_set_num_sims(bpp_engine* e, int num_sims) {
     return BPP_OK;
 }
 
+extern "C" int bpp_engine_set_select_cap(bpp_engine* e, int max_sims_per_launch) {
+    if (!e || max_sims_per_launch < 0) return set_err(BPP_E_INVALID, "bad argument");
+    e->P.select_cap = max_sims_per_launch;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_unfinished(bpp_engine* e, int32_t* count_host) {
+    if (!e || !count_host) return set_err(BPP_E_INVALID, "null argument");
+    *count_host = e->unfinished;
+    return BPP_OK;
+}
+
 extern "C" int bpp_engine_last_values(bpp_engine* e, double* values_out_dev, void* stream) {
     if (!e || !values_out_dev) return set_err(BPP_E_INVALID, "null argument");
     CUDA_TRY(cudaMemcpyAsync(values_out_dev, e->P.last_v, (size_t)e->P.G * sizeof(double), cudaMemcpyDeviceToDevice,
@@ -1024,7 +1042,7 @@ static void launch_search(bpp_engine* e, void* stream) {
 extern "C" int bpp_engine_select(bpp_engine* e, void* stream) {
     if (!e) return set_err(BPP_E_INVALID, "null argument");
     if (e->leaf_parked) return set_err(BPP_E_STATE, "bpp_engine_select called with leaves still parked");
-    CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, sizeof(int), S(stream)));
+    CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, 2 * sizeof(int), S(stream)));
     launch_search<0>(e, stream);
     LAUNCH_CHECK(e);
     e->leaf_parked = true;
@@ -1033,9 +1051,12 @@ extern "C" int bpp_engine_select(bpp_engine* e, void* stream) {
 
 extern "C" int bpp_engine_leaf_count(bpp_engine* e, int32_t* count_host, void* stream) {
     if (!e || !count_host) return set_err(BPP_E_INVALID, "null argument");
-    CUDA_TRY(cudaMemcpyAsync(count_host, e->P.leaf_count, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    int both[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(both, e->P.leaf_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
-    if (*count_host == 0) e->leaf_parked = false;  // nothing to expand: the select/expand pairing is complete
+    *count_host = both[0];
+    e->unfinished = both[1];
+    if (both[0] == 0) e->leaf_parked = false;  // nothing to expand: the select/expand pairing is complete
     return BPP_OK;
 }
 

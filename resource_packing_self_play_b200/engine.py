@@ -218,6 +218,14 @@ class SearchEngine:
         call("bpp_engine_set_num_sims", self._h, int(n))
         self.num_sims = int(n)
 
+    def set_select_cap(self, k):
+        call("bpp_engine_set_select_cap", self._h, int(k))
+
+    def unfinished(self):
+        n = C.c_int32(0)
+        call("bpp_engine_unfinished", self._h, C.byref(n))
+        return int(n.value)
+
     def last_values(self):
         out = torch.empty(self.G, dtype=torch.float64, device=self.device)
         call("bpp_engine_last_values", self._h, _ptr(out), _stream())

@@ -129,7 +129,7 @@ class BatchedMCTS:
             tie = np.where(np.random.random(self.G) < 0.5, 1, -1).astype(np.int8)
         self.eng.reset(items_wh, total_area, bl, tie)
 
-    def search(self, chunk=8):
+    def search(self, chunk=8, select_cap=8):
         """numMCTSSims simulations for every running game.  One lockstep step = select (descents + terminal backups
         until every game parks one unexpanded leaf) -> ONE batched forward over the parked leaves, read straight
         from the engine's leaf buffers -> expand + backup.  The leaf count stays on the device (the evaluator and the
@@ -140,6 +140,9 @@ class BatchedMCTS:
             self._pol = torch.empty((self.G, eng.A), dtype=torch.float32, device=eng.device)
             self._val = torch.empty(self.G, dtype=torch.float32, device=eng.device)
         eng.begin_move()
+        # a game whose simulations keep ending on terminal states parks no leaf: cap its work per launch so that it
+        # does not delay the leaf batch of the others; once few leaves are left the cap is lifted
+        eng.set_select_cap(select_cap)
         while True:
             for _ in range(chunk):
                 eng.select()
@@ -147,6 +150,10 @@ class BatchedMCTS:
                             value_out=self._val, batch=self.G)
                 eng.expand_backup(self._pol, self._val)
                 self.steps += 1
-            if eng.leaf_count() == 0:  # the last select parked nothing: every game has done its simulations
+            n = eng.leaf_count()
+            if n == 0 and eng.unfinished() == 0:  # nothing parked, nobody capped: the move is complete
                 break
+            if n < self.G // 16:
+                eng.set_select_cap(0)
+        eng.set_select_cap(0)
         return eng.root_counts()
