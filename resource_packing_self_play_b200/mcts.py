@@ -8,6 +8,8 @@ while an NNetWrapper of this package is evaluated on the device without leaving 
 
 `BatchedMCTS` runs G games in lockstep (the fast path).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -129,7 +131,7 @@ class BatchedMCTS:
             tie = np.where(np.random.random(self.G) < 0.5, 1, -1).astype(np.int8)
         self.eng.reset(items_wh, total_area, bl, tie)
 
-    def search(self, chunk=8, select_cap=8):
+    def search(self, chunk=8, select_cap=None):
         """numMCTSSims simulations for every running game.  One lockstep step = select (descents + terminal backups
         until every game parks one unexpanded leaf) -> ONE batched forward over the parked leaves, read straight
         from the engine's leaf buffers -> expand + backup.  The leaf count stays on the device (the evaluator and the
@@ -142,6 +144,9 @@ class BatchedMCTS:
         eng.begin_move()
         # a game whose simulations keep ending on terminal states parks no leaf: cap its work per launch so that it
         # does not delay the leaf batch of the others; once few leaves are left the cap is lifted
+        if select_cap is None:
+            select_cap = int(os.environ.get("BPP_SELECT_CAP", "4"))
+        lift = int(os.environ.get("BPP_SELECT_LIFT", "16"))
         eng.set_select_cap(select_cap)
         while True:
             for _ in range(chunk):
@@ -153,7 +158,7 @@ class BatchedMCTS:
             n = eng.leaf_count()
             if n == 0 and eng.unfinished() == 0:  # nothing parked, nobody capped: the move is complete
                 break
-            if n < self.G // 16:
+            if n < self.G // lift:
                 eng.set_select_cap(0)
         eng.set_select_cap(0)
         return eng.root_counts()
