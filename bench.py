@@ -221,7 +221,8 @@ def run_gpu_arm(args):
     for k in range(2 * n_steps_total):  # first half: device-resident arm, second half: e2e arm
         first = ((k * world) + rank) * G
         seeds, heights, areas = workload(first, G)
-        inst.append((gen.items_batch(seeds, heights), areas))
+        # the package's device-side generator (bit-identical to numpy's legacy RNG path, tests/test_gpu_env.py)
+        inst.append((gen.items_batch_device(seeds, heights, device=local).cpu().numpy(), areas))
     edge_cap = 0
     if args.edge_frac < 1.0:  # profiling runs: a smaller edge pool keeps ncu's save/restore cheap
         worst_units_per_node = 3 * ((W * N + 3) // 4 * 4) + ((W * N + 3) // 4 * 4) // 4

@@ -73,6 +73,14 @@ int bpp_version(void);
 int bpp_env_valid_moves(int W, int H, int N, int n, const uint32_t *recs_dev, const int32_t *items_wh_dev,
                         uint8_t *valid_out_dev, void *stream);
 
+/* ItemsGenerator.items_generator (BinPackingGame.py:257-285) for n seeds at once, on the device: replays numpy's legacy
+ * global RNG (np.random.seed(seed); np.random.randint draws) so the instances equal the reference's for the same
+ * seeds.  seeds_dev int64 [n] (0 <= seed < 2^32), heights_dev int32 [n] generator bin height (the generator's width is
+ * W; a rectangle W x height must be splittable into N items, i.e. W*height >= N); items_wh_out_dev int32 [n][N][2] =
+ * (w, h); rects_out_dev (may be NULL) int32 [n][N][4] = the reference's [w, h, a, b]. */
+int bpp_items_generate(int W, int N, int n, const int64_t *seeds_dev, const int32_t *heights_dev,
+                       int32_t *items_wh_out_dev, int32_t *rects_out_dev, void *stream);
+
 /* BinPackingGame.getBinItem (BinPackingGame.py:118-120) for compact states: the dense evaluator / learner input
  * planes_out_dev float32 [n][N+1][H][W] (plane 0 = bin occupancy, plane i+1 = item i's [0:h, 0:w] block while it is
  * still to be placed). */

@@ -36,6 +36,7 @@ SIGNATURES = {
     "bpp_last_error": [],
     "bpp_version": [],
     "bpp_env_valid_moves": [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "bpp_items_generate": [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "bpp_env_planes": [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "bpp_env_next_state": [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "bpp_env_game_ended": [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

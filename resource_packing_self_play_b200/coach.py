@@ -88,6 +88,10 @@ class CoachBPP:
         (the reference appends to it after every episode, so inside one call the ranked-reward threshold is the one at
         the start of the batch).  Returns (examples, scores, outcomes): examples is the reference's list of
         (state (N+1,H,W) int64, pi list, r) when expand=True, else a dict of compact arrays."""
+        items_dev = None
+        if isinstance(items_batch, torch.Tensor):  # e.g. from ItemsGenerator.items_batch_device
+            items_dev = items_batch.to(torch.int32)
+            items_batch = items_dev.cpu().numpy()
         items_batch = np.asarray(items_batch, dtype=np.int32)
         G = items_batch.shape[0]
         g = self.game
@@ -96,7 +100,8 @@ class CoachBPP:
         if bm is None or bm.G != G:
             bm = self._bm = BatchedMCTS(g, self.nnet, self.args, G)
         bm.nnet = self.nnet  # the search engine is independent of the evaluator: swapping nets keeps the pools
-        bm.reset(items_batch, np.asarray(total_areas, dtype=np.int32), self.rewards_list)
+        bm.reset(items_dev if items_dev is not None else items_batch, np.asarray(total_areas, dtype=np.int32),
+                 self.rewards_list)
         eng = bm.eng
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")
@@ -210,7 +215,7 @@ class CoachBPP:
             self.gen.bin_height = h
             self.items_total_area = h * self.gen.bin_width
             lo, hi = D.shard_range(games_per_iter, rank, ws)
-            items = self.gen.items_batch(seeds[lo:hi])
+            items = self.gen.items_batch_device(seeds[lo:hi], device=dev.index)
             areas = np.full(hi - lo, self.items_total_area, dtype=np.int32)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
@@ -322,7 +327,7 @@ class CoachBPP:
         """Batched arena (BASELINE.json configs[4]): every seed is played greedily with both nets in lockstep.
         Returns (p_scores, n_scores, accept) with accept as in arena_playing."""
         seeds = np.asarray(seeds)
-        items = self.gen.items_batch(seeds, bin_heights)
+        items = self.gen.items_batch_device(seeds, bin_heights, device=self.nnet.device.index)
         hts = np.full(len(seeds), self.gen.bin_height) if bin_heights is None else np.asarray(bin_heights)
         areas = (hts * self.gen.bin_width).astype(np.int32)
         out = []

@@ -733,6 +733,88 @@ k_env_ended(EnvArgs E, const int32_t* total_area, const int32_t* max_h, const do
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-side ItemsGenerator.items_generator (BinPackingGame.py:257-285): one thread per seed replays numpy's legacy
+// global RNG — MT19937 seeded by init_genrand(seed) (np.random.seed(int)), randint = masked rejection over 32-bit
+// draws with NO draw when the range holds a single value — and the guillotine-split loop, so the instances are
+// identical to the reference's for the same seeds.  The 2.5 KB generator state lives in local memory.
+struct DevMT {
+    uint32_t mt[624];
+    int pos;
+    __device__ void seed(uint32_t s) {
+        for (int i = 0; i < 624; ++i) {
+            mt[i] = s;
+            s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+        }
+        pos = 624;
+    }
+    __device__ void twist() {
+        for (int i = 0; i < 624; ++i) {
+            const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+            mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        pos = 0;
+    }
+    __device__ uint32_t u32() {
+        if (pos >= 624) twist();
+        uint32_t y = mt[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    __device__ int randint(int low, int high) {  // np.random.randint(low, high), high exclusive
+        const uint32_t rng = (uint32_t)(high - 1 - low);
+        if (rng == 0u) return low;
+        uint32_t mask = rng;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t v;
+        do { v = u32() & mask; } while (v > rng);
+        return low + (int)v;
+    }
+};
+
+__global__ void k_items_generate(int W, int N, int n, const int64_t* __restrict__ seeds,
+                                 const int32_t* __restrict__ heights, int32_t* __restrict__ items_wh,
+                                 int32_t* __restrict__ rects_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DevMT r;
+    r.seed((uint32_t)seeds[i]);
+    short rc[2 * BPP_MAX_ITEMS + 2][4];  // [w, h, a, b]
+    int len = 1;
+    rc[0][0] = (short)W; rc[0][1] = (short)heights[i]; rc[0][2] = 0; rc[0][3] = 0;
+    while (len < N) {
+        const int axis = r.randint(0, 2);
+        const int k = r.randint(0, len);
+        const int w = rc[k][0], h = rc[k][1], a = rc[k][2], b = rc[k][3];
+        if (axis == 0) {
+            if (w == 1) continue;
+            const int cut = r.randint(a + 1, a + w);
+            rc[len][0] = (short)(cut - a); rc[len][1] = (short)h; rc[len][2] = (short)a; rc[len][3] = (short)b;
+            rc[len + 1][0] = (short)(w - (cut - a)); rc[len + 1][1] = (short)h; rc[len + 1][2] = (short)cut; rc[len + 1][3] = (short)b;
+        } else {
+            if (h == 1) continue;
+            const int cut = r.randint(b + 1, b + h);
+            rc[len][0] = (short)w; rc[len][1] = (short)(cut - b); rc[len][2] = (short)a; rc[len][3] = (short)b;
+            rc[len + 1][0] = (short)w; rc[len + 1][1] = (short)(h - (cut - b)); rc[len + 1][2] = (short)a; rc[len + 1][3] = (short)cut;
+        }
+        len += 2;
+        for (int j = k; j < len - 1; ++j) {  // item_list.pop(idx_item)
+            rc[j][0] = rc[j + 1][0]; rc[j][1] = rc[j + 1][1]; rc[j][2] = rc[j + 1][2]; rc[j][3] = rc[j + 1][3];
+        }
+        len -= 1;
+    }
+    for (int j = 0; j < N; ++j) {
+        items_wh[((size_t)i * N + j) * 2 + 0] = rc[j][0];
+        items_wh[((size_t)i * N + j) * 2 + 1] = rc[j][1];
+        if (rects_out) {
+            for (int c = 0; c < 4; ++c) rects_out[((size_t)i * N + j) * 4 + c] = rc[j][c];
+        }
+    }
+}
+
 // dense planes of arbitrary compact states (learner input batches): out float32 [n][N+1][H][W]
 __global__ void k_env_planes(EnvArgs E, float* out) {
     const Geom& ge = E.geom;
@@ -1287,6 +1369,17 @@ extern "C" int bpp_env_valid_moves(int W, int H, int N, int n, const uint32_t* r
     if (n == 0) return BPP_OK;
     if (!valid_out_dev) return set_err(BPP_E_INVALID, "null output");
     k_env_valid<<<grid_warps(n), WARPS_PER_CTA * 32, 0, S(stream)>>>(E, valid_out_dev);
+    ENV_LAUNCH_CHECK();
+    return BPP_OK;
+}
+
+extern "C" int bpp_items_generate(int W, int N, int n, const int64_t* seeds_dev, const int32_t* heights_dev,
+                                  int32_t* items_wh_out_dev, int32_t* rects_out_dev, void* stream) {
+    if (W < 1 || W > 32 || N < 1 || N > BPP_MAX_ITEMS || n < 0)
+        return set_err(BPP_E_INVALID, "bad generator arguments W=%d N=%d n=%d", W, N, n);
+    if (n == 0) return BPP_OK;
+    if (!seeds_dev || !heights_dev || !items_wh_out_dev) return set_err(BPP_E_INVALID, "null argument");
+    k_items_generate<<<(n + 63) / 64, 64, 0, S(stream)>>>(W, N, n, seeds_dev, heights_dev, items_wh_out_dev, rects_out_dev);
     ENV_LAUNCH_CHECK();
     return BPP_OK;
 }

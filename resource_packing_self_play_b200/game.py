@@ -154,6 +154,23 @@ class ItemsGenerator:
         np.random.seed(seed)
         return self._generate(np.random)
 
+    def items_batch_device(self, seeds, bin_heights=None, device=None, rects=False):
+        """items_batch on the GPU (bpp_items_generate): int32 (len(seeds), n, 2) device tensor, identical to the host
+        generator for the same seeds.  With rects=True also returns the reference's [w, h, a, b] rows."""
+        import ctypes as C
+        from ._lib import call
+        from .engine import _dev, _devidx, _ptr, _stream
+        dev = torch.device("cuda", _devidx(device))
+        n = len(seeds)
+        seeds_t = _dev(np.asarray(seeds, dtype=np.int64), torch.int64, dev)
+        hts = np.full(n, self.bin_height, dtype=np.int32) if bin_heights is None else np.asarray(bin_heights)
+        hts_t = _dev(hts.astype(np.int32), torch.int32, dev)
+        out = torch.empty((n, self.n, 2), dtype=torch.int32, device=dev)
+        rc = torch.empty((n, self.n, 4), dtype=torch.int32, device=dev) if rects else None
+        call("bpp_items_generate", self.bin_width, self.n, n, _ptr(seeds_t), _ptr(hts_t), _ptr(out),
+             _ptr(rc) if rects else C.c_void_p(0), _stream())
+        return (out, rc) if rects else out
+
     def items_batch(self, seeds, bin_heights=None):
         """(len(seeds), n, 2) int32 (w, h) array for the batched engine; leaves the global RNG untouched.
         bin_heights: optional per-seed generator height (the per-iteration draw of CoachBPP.py:117-119)."""

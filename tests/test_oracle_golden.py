@@ -102,3 +102,16 @@ def test_ranked_threshold_helper():
     assert bl_of([0.3]) == 0.3          # index -1 wraps
     assert bl_of([0.2, 0.95]) == 0.2
     assert bl_of([1.0] * 100) == 1.0
+
+
+def test_legacy_mt19937_restatement_matches_numpy_and_reference_fixtures():
+    from oracle.mt_items import LegacyMT19937, items_generator
+    for seed in (0, 1, 100, 4242, 99999, 2 ** 31 + 5, 2 ** 32 - 1):
+        np.random.seed(seed)
+        r = LegacyMT19937(seed)
+        for hi in (2, 3, 7, 10, 15, 150, 1000, 2 ** 20 + 3):
+            assert int(np.random.randint(hi)) == r.randint(hi)
+        assert int(np.random.randint(5, 6)) == r.randint(5, 6)   # single value: no draw on either side
+        assert int(np.random.randint(9)) == r.randint(9)
+    for rec in load_items_golden():
+        assert items_generator(rec["W"], rec["Hgen"], rec["N"], rec["seed"]) == rec["items"]
