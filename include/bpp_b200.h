@@ -243,6 +243,8 @@ int bpp_net_commit(bpp_net *n, void *stream);
 #define BPP_NET_BF16 0      /* tcgen05 tensor-core kernel (implicit GEMM, TMEM accumulators) */
 #define BPP_NET_FP32 1      /* CUDA-core kernel, fp32 weights and activations */
 #define BPP_NET_BF16_SIMT 2 /* CUDA-core kernel with the bf16 roundings of mode 0 (cross-check of the tensor-core path) */
+#define BPP_NET_BF16X3 3    /* tcgen05 kernel in split-bf16: activations and weights as hi + lo bf16 halves, three MMAs per
+                               product, fp32 heads (~16 mantissa bits): the tensor-core mode for TRAINED checkpoints */
 int bpp_net_set_precision(bpp_net *n, int mode);
 /* Phase timers (SM clock cycles, CTA 0 of the last tensor-core forward; synchronises the device):
  * [0] input planes, [1] weight staging, [2] MMA issue, [3] MMA wait, [4] epilogue, [5] pooling, [6] heads, [7] total. */

@@ -225,8 +225,10 @@ k_net_forward(NetParams P, int Bmax, const int32_t* __restrict__ count_dev, cons
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 forward: one CTA = S leaves through the whole network (see bpp_net_tc.cuh)
-template <int NS>  // leaves per CTA the head accumulators are unrolled for (4 or 8)
-__global__ void __launch_bounds__(bpptc::TC_THREADS, (NS <= 4 ? 2 : 1))
+// NS = leaves per CTA the head accumulators are unrolled for (4 or 8); X3 = split-bf16 mode (hi + lo halves, 3 MMAs per
+// product, fp32 heads) for networks whose dynamic range exceeds plain bf16
+template <int NS, bool X3>
+__global__ void __launch_bounds__(bpptc::TC_THREADS, ((NS <= 4 && !X3) ? 2 : 1))
 k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__ count_dev,
                  const uint32_t* __restrict__ recs, const int32_t* __restrict__ game,
                  const int32_t* __restrict__ items_wh, float* __restrict__ policy, float* __restrict__ value,
@@ -264,13 +266,14 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     WPre pre;
     auto lay_w = [&](int l) { return T.wts_umma + T.w_off[l]; };
     auto lay_b = [&](int l) { return P.bias + P.conv[l].b_off; };
-    if ((int)blockIdx.x < ngroups) wpre_load(pre, lay_w(0), T.lay_n16[0], lay_b(0), P.conv[0].co);
+    auto lay_wl = [&](int l) { return T.wts_umma_lo + T.w_off[l]; };
+    if (!X3 && (int)blockIdx.x < ngroups) wpre_load(pre, lay_w(0), T.lay_n16[0], lay_b(0), P.conv[0].co);
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const int nvalid = min(S, B - grp * S);
         long long tq = clock64();
         // ---- level-0 operand planes from the compact records (getBinItem, BinPackingGame.py:118-120)
         const Level& L0 = T.lv[0];
-        zero_bytes(regA, 2 * cin16_0 * L0.RT * 16);
+        zero_bytes(regA, (X3 ? 2 : 1) * 2 * cin16_0 * L0.RT * 16);  // split mode: the lo planes of the 0/1 input stay zero
         for (int i = tid; i < nvalid * 32; i += TC_THREADS) s_rec[i >> 5][i & 31] = recs[(size_t)(grp * S + (i >> 5)) * 32 + (i & 31)];
         for (int i = tid; i < nvalid * P.N * 2; i += TC_THREADS) {
             const int j = i / (P.N * 2), r = i - j * P.N * 2;
@@ -311,28 +314,34 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             const Level& La = T.lv[s];
             const Level& Lb = T.lv[s + 1];
             const int cout = P.conv[li].co;
-            conv_layer(T, cx, La, nvalid, cin16, cout, lay_w(li), lay_b(li), in, EPI_CONV, regB, nullptr, pre,
-                       lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co);
+            const uint32_t in_lo = (uint32_t)(2 * cin16) * (uint32_t)La.RT * 16u;   // bytes of the input's hi planes
+            const uint32_t t_lo = (uint32_t)(cout / 8) * (uint32_t)La.RT * 16u;     // bytes of T's hi planes
+            conv_layer<X3>(T, cx, La, nvalid, cin16, cout, lay_w(li), lay_b(li), in, EPI_CONV, regB, nullptr, pre,
+                           lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co, lay_wl(li), in_lo, t_lo, 0u);
             ++li;
             tq = clock64();
             const int planes = cout / 8;
-            const size_t pb = (size_t)planes * Lb.RT * 16;
+            const size_t pb = (size_t)planes * Lb.RT * 16;   // one logical buffer (hi planes)
+            const size_t bs = X3 ? 2 * pb : pb;               // stride between logical buffers (hi [+ lo])
             raw = regA;
-            unsigned char* actA = regA + pb;
-            unsigned char* actB = regA + 2 * pb;
-            zero_bytes(regA, (int)(3 * pb));
+            unsigned char* actA = regA + bs;
+            unsigned char* actB = regA + 2 * bs;
+            zero_bytes(regA, (int)(3 * bs));
             __syncthreads();
-            pool_level(La, Lb, nvalid, planes, regB, raw, actA);
+            if (X3) pool_level_x3(La, Lb, nvalid, planes, regB, t_lo, raw, (uint32_t)pb, actA, (uint32_t)pb);
+            else pool_level(La, Lb, nvalid, planes, regB, raw, actA);
             __syncthreads();
             TC_PROF(5, tq);
             for (int blk = 0; blk < 2; ++blk) {
-                conv_layer(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actA, EPI_RES0, actB, nullptr, pre,
-                           lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co);
+                conv_layer<X3>(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actA, EPI_RES0, actB, nullptr, pre,
+                               lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co, lay_wl(li),
+                               (uint32_t)pb, (uint32_t)pb, (uint32_t)pb);
                 ++li;
                 {
                     const int nx = (li + 1) % NCONV;  // after the last layer: layer 0 of this CTA's next group
-                    conv_layer(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actB, EPI_RES1, actA, raw, pre,
-                               lay_w(nx), T.lay_n16[nx], lay_b(nx), P.conv[nx].co);
+                    conv_layer<X3>(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actB, EPI_RES1, actA, raw, pre,
+                                   lay_w(nx), T.lay_n16[nx], lay_b(nx), P.conv[nx].co, lay_wl(li), (uint32_t)pb,
+                                   (uint32_t)pb, (uint32_t)pb);
                 }
                 ++li;
             }
@@ -347,6 +356,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         float* lg = hid + NS * HIDDEN;                            // [NS][A]
         float* part = lg + NS * P.A;                              // [2][NS][256] / [2][NS][A] partial sums
         const int hw3 = L3.h * L3.w;
+        const size_t raw_lo3 = (size_t)(P.conv[NCONV - 1].co / 8) * L3.RT * 16;
         for (int idx = tid; idx < NS * P.flat; idx += TC_THREADS) {
             const int j = idx / P.flat, f = idx - j * P.flat;
             float v = 0.f;
@@ -354,9 +364,11 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
                 const int c = f / hw3, q = f - c * hw3;
                 const int y = q / L3.w, x = q - y * L3.w;
                 const size_t row = (size_t)L3.guard + (size_t)j * L3.P + (size_t)(y + 1) * L3.wp + (x + 1);
-                const __nv_bfloat16* e =
-                    reinterpret_cast<const __nv_bfloat16*>(raw + ((size_t)(c >> 3) * L3.RT + row) * 16) + (c & 7);
-                v = fmaxf(__bfloat162float(*e), 0.f);
+                const size_t eoff = ((size_t)(c >> 3) * L3.RT + row) * 16;
+                const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(raw + eoff) + (c & 7);
+                v = __bfloat162float(*e);
+                if (X3) v += __bfloat162float(*(reinterpret_cast<const __nv_bfloat16*>(raw + raw_lo3 + eoff) + (c & 7)));
+                v = fmaxf(v, 0.f);
             }
             feat[idx] = v;
         }
@@ -374,8 +386,14 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             const int i0 = hh * (P.flat / 2), i1 = hh ? P.flat : P.flat / 2;
 #pragma unroll 16
             for (int i = i0; i < i1; ++i) {
-                const uint32_t wv = __ldg(wp32 + (size_t)i * (HIDDEN / 2));
-                const float w0 = bf16_lo(wv), w1 = bf16_hi(wv);
+                float w0, w1;
+                if (X3) {
+                    const float2 wf = __ldg(reinterpret_cast<const float2*>(P.wts32 + P.fc_hidden_off + (size_t)i * HIDDEN) + ot);
+                    w0 = wf.x; w1 = wf.y;
+                } else {
+                    const uint32_t wv = __ldg(wp32 + (size_t)i * (HIDDEN / 2));
+                    w0 = bf16_lo(wv); w1 = bf16_hi(wv);
+                }
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
                     const float f = feat[j * P.flat + i];
@@ -391,7 +409,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         }
         __syncthreads();
         for (int idx = tid; idx < NS * HIDDEN; idx += TC_THREADS)
-            hid[idx] = act_round<false>(fmaxf(part[idx] + part[NS * HIDDEN + idx], 0.f));
+            hid[idx] = act_round<X3>(fmaxf(part[idx] + part[NS * HIDDEN + idx], 0.f));
         __syncthreads();
         if (2 * ot < T.A_pad) {  // logits: padded [256][A_pad] copy of the weights, outputs 2*ot, 2*ot+1
             const int o = 2 * ot;
@@ -404,8 +422,15 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             const int i0 = hh * (HIDDEN / 2), i1 = i0 + HIDDEN / 2;
 #pragma unroll 16
             for (int i = i0; i < i1; ++i) {
-                const uint32_t wv = __ldg(wp32 + (size_t)i * (T.A_pad / 2));
-                const float w0 = bf16_lo(wv), w1 = bf16_hi(wv);
+                float w0, w1;
+                if (X3) {
+                    const float* wr = P.wts32 + P.fc_logits_off + (size_t)i * P.A + o;
+                    w0 = __ldg(wr);
+                    w1 = o + 1 < P.A ? __ldg(wr + 1) : 0.f;
+                } else {
+                    const uint32_t wv = __ldg(wp32 + (size_t)i * (T.A_pad / 2));
+                    w0 = bf16_lo(wv); w1 = bf16_hi(wv);
+                }
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
                     const float f = hid[j * HIDDEN + i];
@@ -429,7 +454,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             const int b = grp * S + j;
             float acc = 0.f;
             for (int i = lane; i < HIDDEN; i += 32)
-                acc = fmaf(hid[j * HIDDEN + i], __bfloat162float(P.wts[P.fc_value_off + i]), acc);
+                acc = fmaf(hid[j * HIDDEN + i], wt<X3>(P, P.fc_value_off + i), acc);
             float mx = -INFINITY;
             for (int o = lane; o < P.A; o += 32) mx = fmaxf(mx, lg[j * P.A + o]);
             for (int o = 16; o; o >>= 1) {
@@ -485,7 +510,10 @@ struct bpp_net {
     float* d_wts32 = nullptr;
     float* d_bias = nullptr;
     int precision = 0;  // BPP_NET_BF16
-    bpptc::TcParams T;
+    bpptc::TcParams T;    // plain bf16 mode
+    bpptc::TcParams T3;   // split-bf16 (x3) mode: doubled activation and weight buffers
+    bool tc3_ok = false;
+    __nv_bfloat16* d_wts_umma_lo = nullptr;
     __nv_bfloat16* d_wts_umma = nullptr;
     __nv_bfloat16* d_wts_logits_pad = nullptr;
     long long umma_elems = 0;
@@ -561,7 +589,8 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
     {   // UMMA-layout conv weights (size known before the Tc setup below: recompute here)
         long long u = 0;
         for (int l = 0; l < NCONV; ++l) u += 9LL * ((P.conv[l].ci + 15) / 16) * 2 * P.conv[l].co * 8;
-        if (cudaMalloc(&n->d_wts_umma, (size_t)u * sizeof(__nv_bfloat16)) != cudaSuccess) {
+        if (cudaMalloc(&n->d_wts_umma, (size_t)u * sizeof(__nv_bfloat16)) != cudaSuccess ||
+            cudaMalloc(&n->d_wts_umma_lo, (size_t)u * sizeof(__nv_bfloat16)) != cudaSuccess) {
             cudaGetLastError();
             delete n;
             return nerr(BPP_E_NOMEM, "cudaMalloc of the network parameters failed");
@@ -593,51 +622,66 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         }
         n->umma_elems = uoff;
         const int cin16_0 = (P.Cin + 15) / 16;
-        for (int S = 8; S >= 1 && !n->tc_ok; --S) {
-            for (int l = 0; l < 4; ++l) {
-                bpptc::Level& L = T.lv[l];
-                L.h = P.hs[l]; L.w = P.ws[l]; L.hp = L.h + 2; L.wp = L.w + 2; L.P = L.hp * L.wp;
-                L.guard = (L.wp + 1 + 7) & ~7;
-                L.RT = L.guard + S * L.P + L.guard;
-                L.ntiles = (S * L.P + 127) / 128;
+        auto plan = [&](bpptc::TcParams& T, bool x3, int cap_bytes, int& ctas_out) -> bool {
+            const int f = x3 ? 2 : 1;
+            for (int S = 8; S >= 1; --S) {
+                for (int l = 0; l < 4; ++l) {
+                    bpptc::Level& L = T.lv[l];
+                    L.h = P.hs[l]; L.w = P.ws[l]; L.hp = L.h + 2; L.wp = L.w + 2; L.P = L.hp * L.wp;
+                    L.guard = (L.wp + 1 + 7) & ~7;
+                    L.RT = L.guard + S * L.P + L.guard;
+                    L.ntiles = (S * L.P + 127) / 128;
+                }
+                long long a = (long long)f * 2 * cin16_0 * T.lv[0].RT * 16, b = 0;
+                for (int s2 = 0; s2 < 3; ++s2) {
+                    const int planes = chans[s2] / 8;
+                    a = std::max(a, (long long)f * 3 * planes * T.lv[s2 + 1].RT * 16);
+                    b = std::max(b, (long long)f * planes * T.lv[s2].RT * 16);
+                }
+                const int NSs = S <= 4 ? 4 : 8;
+                b = std::max(b, (long long)NSs * (P.flat + 4 * HIDDEN + 3 * (P.A + 1)) * 4);
+                T.S = S;
+                T.regA_bytes = (int)((a + 1023) & ~1023LL);
+                T.regB_bytes = (int)((b + 4096 + 1023) & ~1023LL);  // + slack: the last tile's shifted windows over-read
+                T.wbuf_bytes = (f * wmax + 256 + 1023) & ~1023;     // + the layer's bias behind the weights
+                T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
+                if (T.smem_bytes <= cap_bytes && T.lv[0].RT < 16384) {
+                    // CTAs that fit on one SM (227 KB shared memory, 1 KB reserved per CTA) share the 512 TMEM columns
+                    int ctas = (227 * 1024) / (T.smem_bytes + 2048);
+                    if (ctas > 2) ctas = 2;
+                    if (S > 4 || x3) ctas = 1;
+                    if (ctas < 1) ctas = 1;
+                    T.tmem_cols = ctas == 2 ? 256 : 512;
+                    ctas_out = ctas;
+                    return true;
+                }
             }
-            long long a = 2LL * cin16_0 * T.lv[0].RT * 16, b = 0;
-            for (int s2 = 0; s2 < 3; ++s2) {
-                const int planes = chans[s2] / 8;
-                a = std::max(a, 3LL * planes * T.lv[s2 + 1].RT * 16);
-                b = std::max(b, (long long)planes * T.lv[s2].RT * 16);
-            }
-            const int NSs = S <= 4 ? 4 : 8;
-            b = std::max(b, (long long)NSs * (P.flat + 4 * HIDDEN + 3 * (P.A + 1)) * 4);
-            T.S = S;
-            T.regA_bytes = (int)((a + 1023) & ~1023LL);
-            T.regB_bytes = (int)((b + 4096 + 1023) & ~1023LL);  // + slack: the last tile's shifted windows over-read
-            T.wbuf_bytes = (wmax + 256 + 1023) & ~1023;  // + the layer's bias behind the weights
-            T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
-            if (T.smem_bytes <= tc_smem_cap() && T.lv[0].RT < 16384) n->tc_ok = true;
-            // CTAs that fit on one SM (227 KB shared memory, 1 KB reserved per CTA) share the 512 TMEM columns
-            int ctas = (227 * 1024) / (T.smem_bytes + 2048);
-            if (ctas > 2) ctas = 2;
-            if (S > 4) ctas = 1;
-            if (ctas < 1) ctas = 1;
-            T.tmem_cols = ctas >= 3 ? 128 : (ctas == 2 ? 256 : 512);
-            n->ctas_per_sm = ctas;
-        }
+            return false;
+        };
+        n->tc_ok = plan(T, false, tc_smem_cap(), n->ctas_per_sm);
+        n->T3 = T;
+        int c3 = 1;
+        n->tc3_ok = plan(n->T3, true, 220 * 1024, c3);
     }
     n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
     if (cudaFuncSetAttribute(k_net_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
             cudaSuccess ||
         cudaFuncSetAttribute(k_net_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
             cudaSuccess ||
-        (n->tc_ok && (cudaFuncSetAttribute(k_net_forward_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (n->tc_ok && (cudaFuncSetAttribute(k_net_forward_tc<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            n->T.smem_bytes) != cudaSuccess ||
-                      cudaFuncSetAttribute(k_net_forward_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           n->T.smem_bytes) != cudaSuccess))) {
+                      cudaFuncSetAttribute(k_net_forward_tc<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           n->T.smem_bytes) != cudaSuccess)) ||
+        (n->tc3_ok && (cudaFuncSetAttribute(k_net_forward_tc<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            n->T3.smem_bytes) != cudaSuccess ||
+                       cudaFuncSetAttribute(k_net_forward_tc<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            n->T3.smem_bytes) != cudaSuccess))) {
         cudaGetLastError();
         delete n;
         return nerr(BPP_E_CUDA, "cannot reserve shared memory for the forward kernel");
     }
     n->T.wts_umma = n->d_wts_umma;
+    n->T.wts_umma_lo = n->d_wts_umma_lo;
     n->T.A_pad = (P.A + 1) & ~1;
     if (cudaMalloc(&n->d_wts_logits_pad, (size_t)HIDDEN * n->T.A_pad * 2) != cudaSuccess) {
         cudaGetLastError();
@@ -645,6 +689,13 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         return nerr(BPP_E_NOMEM, "cudaMalloc of the network parameters failed");
     }
     n->T.wts_logits_pad = n->d_wts_logits_pad;
+    {   // the split-mode plan shares the weight pointers and layer tables
+        bpptc::TcParams keep = n->T3;
+        n->T3 = n->T;
+        n->T3.S = keep.S; n->T3.regA_bytes = keep.regA_bytes; n->T3.regB_bytes = keep.regB_bytes;
+        n->T3.wbuf_bytes = keep.wbuf_bytes; n->T3.smem_bytes = keep.smem_bytes; n->T3.tmem_cols = keep.tmem_cols;
+        for (int l = 0; l < 4; ++l) n->T3.lv[l] = keep.lv[l];
+    }
     if (cudaMalloc(&n->d_prof, 8 * sizeof(long long)) == cudaSuccess) cudaMemset(n->d_prof, 0, 8 * sizeof(long long));
     *out = n;
     return BPP_OK;
@@ -655,6 +706,7 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     cudaFree(n->d_wts);
     cudaFree(n->d_wts32);
     cudaFree(n->d_wts_umma);
+    cudaFree(n->d_wts_umma_lo);
     cudaFree(n->d_wts_logits_pad);
     cudaFree(n->d_prof);
     cudaFree(n->d_bias);
@@ -714,7 +766,7 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
         b[P.b_value_off] = n->host["value_fc.bias"][0];
     }
     // conv weights in the UMMA K-major B layout: [tap][kc][k-half][cout][8 cin]
-    std::vector<uint16_t> wu((size_t)n->umma_elems, 0);
+    std::vector<uint16_t> wu((size_t)n->umma_elems, 0), wul((size_t)n->umma_elems, 0);
     li = 0;
     for (int s = 0; s < 3; ++s)
         for (int k = 0; k < 5; ++k) {
@@ -729,8 +781,12 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
                             for (int j = 0; j < 8; ++j) {
                                 const int ci = kc * 16 + kh * 8 + j;
                                 const float v = ci < d.ci ? src[((size_t)co * d.ci + ci) * 9 + t] : 0.f;
-                                wu[(size_t)n->T.w_off[li] + ((((size_t)t * c16 + kc) * 2 + kh) * d.co + co) * 8 + j] =
-                                    f32_to_bf16_rne(v);
+                                const size_t ui = (size_t)n->T.w_off[li] + ((((size_t)t * c16 + kc) * 2 + kh) * d.co + co) * 8 + j;
+                                wu[ui] = f32_to_bf16_rne(v);
+                                uint32_t hb = (uint32_t)wu[ui] << 16;
+                                float hf;
+                                memcpy(&hf, &hb, 4);
+                                wul[ui] = f32_to_bf16_rne(v - hf);  // low half for the split-bf16 mode
                             }
             ++li;
         }
@@ -743,6 +799,7 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (cudaMemcpyAsync(n->d_wts_logits_pad, wlp.data(), wlp.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts_umma, wu.data(), wu.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(n->d_wts_umma_lo, wul.data(), wul.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts, w.data(), w.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -760,7 +817,7 @@ extern "C" int bpp_net_profile(bpp_net* n, int64_t cycles_host[8]) {
 }
 
 extern "C" int bpp_net_set_precision(bpp_net* n, int mode) {
-    if (!n || (mode != BPP_NET_BF16 && mode != BPP_NET_FP32 && mode != BPP_NET_BF16_SIMT))
+    if (!n || (mode != BPP_NET_BF16 && mode != BPP_NET_FP32 && mode != BPP_NET_BF16_SIMT && mode != BPP_NET_BF16X3))
         return nerr(BPP_E_INVALID, "unknown precision mode");
     n->precision = mode;
     return BPP_OK;
@@ -781,11 +838,20 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int cap = 148 * n->ctas_per_sm;
         const int g2 = groups < cap ? groups : cap;
         if (n->T.S <= 4)
-            k_net_forward_tc<4><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
+            k_net_forward_tc<4, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
                 n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
         else
-            k_net_forward_tc<8><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
+            k_net_forward_tc<8, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
                 n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
+    } else if (n->precision == BPP_NET_BF16X3 && n->tc3_ok) {
+        const int groups = (B + n->T3.S - 1) / n->T3.S;
+        const int g2 = groups < 148 ? groups : 148;
+        if (n->T3.S <= 4)
+            k_net_forward_tc<4, true><<<g2, bpptc::TC_THREADS, n->T3.smem_bytes, st>>>(
+                n->P, n->T3, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
+        else
+            k_net_forward_tc<8, true><<<g2, bpptc::TC_THREADS, n->T3.smem_bytes, st>>>(
+                n->P, n->T3, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
     } else if (n->precision == BPP_NET_FP32)
         k_net_forward<true><<<grid, NET_THREADS, n->smem_bytes, st>>>(n->P, B, count_dev, recs_dev, game_dev, items_wh_dev,
                                                                       policy_out_dev, value_out_dev);

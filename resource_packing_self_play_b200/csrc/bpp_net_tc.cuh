@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace bpptc {
@@ -41,6 +42,7 @@ struct TcParams {
     long long w_off[15];   // element offsets of each conv layer in wts_umma
     int lay_n16[15];       // 16-byte chunks of each layer's staged weights (9 * cin16 * 2 * cout)
     const __nv_bfloat16* wts_umma;
+    const __nv_bfloat16* wts_umma_lo;      // bf16(w - bf16(w)): low halves for the split-bf16 (x3) mode
     int A_pad;                             // action size rounded up to even
     const __nv_bfloat16* wts_logits_pad;   // logits weights [256][A_pad] (bf16x2 loads)
 };
@@ -150,6 +152,18 @@ __device__ __forceinline__ float bf16_hi(uint32_t x) { return __uint_as_float(x 
 
 enum { EPI_CONV = 0, EPI_RES0 = 1, EPI_RES1 = 2 };
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), for 8 values packed as two uint4 of bf16 pairs
+__device__ __forceinline__ void split8(const float* u, uint4& h4, uint4& l4) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = pack_bf16(u[2 * i], u[2 * i + 1]);
+        l[i] = pack_bf16(u[2 * i] - bf16_lo(h[i]), u[2 * i + 1] - bf16_hi(h[i]));
+    }
+    h4 = make_uint4(h[0], h[1], h[2], h[3]);
+    l4 = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // Register prefetch of the NEXT layer's weights and bias: the global loads are issued at the start of a layer and are
 // consumed (stored to shared memory) at the start of the next one, so their L2 latency hides behind the layer's MMAs
 // and epilogues without a second shared-memory weight buffer.
@@ -182,26 +196,43 @@ struct Ctx {
 //   EPI_CONV: out0 <- bf16(acc + bias)                       (raw conv output, to be pooled)
 //   EPI_RES0: out0 <- relu(bf16(acc + bias))
 //   EPI_RES1: v = acc + bias + raw; raw <- bf16(v); out0 <- relu(bf16(v))          (raw is read and updated in place)
+// X3 = split-bf16 mode: every activation and weight is carried as hi + lo bf16 halves (lo planes / lo weights sit
+// `*_lo_off` bytes behind the hi ones) and each product is the three MMAs hi*hi + hi*lo + lo*hi into the same fp32
+// accumulator (the lo*lo term is below fp32 resolution): ~16 mantissa bits, enough for the reference's trained
+// checkpoints whose logits reach 3e3.
+template <bool X3>
 __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Level& L, int nvalid, int cin16, int cout,
                                            const __nv_bfloat16* __restrict__ wsrc, const float* __restrict__ bias,
                                            const unsigned char* in_planes, int kind, unsigned char* out0,
                                            unsigned char* raw, WPre& pre, const __nv_bfloat16* next_wsrc, int next_n16,
-                                           const float* next_bias, int next_cout) {
+                                           const float* next_bias, int next_cout, const __nv_bfloat16* wsrc_lo = nullptr,
+                                           uint32_t in_lo_off = 0, uint32_t out_lo_off = 0, uint32_t raw_lo_off = 0) {
     const int tid = threadIdx.x;
     long long tp = clock64();
-    // this layer's weights (already in the UMMA B layout) were prefetched into registers: park them in shared memory
     const int wbytes = 9 * cin16 * 2 * cout * 16;
-    {
+    float* s_bias = reinterpret_cast<float*>(cx.wbuf + (X3 ? 2 : 1) * wbytes);  // Cout floats behind the staged weights
+    if (X3) {
+        // split mode: stage hi and lo weights straight from global memory (this mode runs one CTA per SM)
+        const uint4* sh = reinterpret_cast<const uint4*>(wsrc);
+        const uint4* sl = reinterpret_cast<const uint4*>(wsrc_lo);
+        uint4* dst = reinterpret_cast<uint4*>(cx.wbuf);
+        const int n16 = wbytes / 16;
+        for (int i = tid; i < n16; i += TC_THREADS) {
+            dst[i] = __ldg(sh + i);
+            dst[n16 + i] = __ldg(sl + i);
+        }
+        if (tid < cout) s_bias[tid] = __ldg(bias + tid);
+    } else {
+        // this layer's weights (already in the UMMA B layout) were prefetched into registers: park them in shared memory
         uint4* dst = reinterpret_cast<uint4*>(cx.wbuf);
 #pragma unroll
         for (int k = 0; k < WPRE; ++k) {
             const int i = tid + k * TC_THREADS;
             if (i < wbytes / 16) dst[i] = pre.w[k];
         }
+        if (tid < cout) s_bias[tid] = pre.b;
+        wpre_load(pre, next_wsrc, next_n16, next_bias, next_cout);  // in flight during this layer
     }
-    float* s_bias = reinterpret_cast<float*>(cx.wbuf + wbytes);  // Cout floats right behind the staged weights
-    if (tid < cout) s_bias[tid] = pre.b;
-    wpre_load(pre, next_wsrc, next_n16, next_bias, next_cout);  // in flight during this layer
     fence_proxy_async();  // generic-proxy writes (weights, previous epilogue) -> visible to the tensor core's async proxy
     __syncthreads();
     TC_PROF(1, tp);
@@ -223,6 +254,7 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         const uint64_t a00 = umma_desc(a_base + (uint32_t)L.guard * 16u, (uint32_t)L.RT, 8u);
         const uint32_t ahi = (uint32_t)(a00 >> 32), bhi = (uint32_t)(b0 >> 32), blo0 = (uint32_t)b0;
         const uint32_t a_kc = 2u * plane_b >> 4, b_blk = (uint32_t)(2 * cout), b_tap = b_blk * (uint32_t)cin16;
+        const uint32_t a_lo16 = in_lo_off >> 4, w_lo16 = (uint32_t)wbytes >> 4;
         for (int b = 0; b < nb; ++b) {
             const uint32_t alo0 = (uint32_t)a00 + (uint32_t)(t0 + b) * 128u;  // +128 rows (16-byte units) per tile
             const uint32_t d = cx.tmem + (uint32_t)(b * cout);
@@ -231,7 +263,17 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
                 const uint32_t at = alo0 + (uint32_t)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
                 const uint32_t bt = blo0 + (uint32_t)tap * b_tap;
                 umma_bf16_lh(d, at, ahi, bt, bhi, idesc, tap > 0 ? 1u : 0u);
-                if (cin16 == 2) umma_bf16_lh(d, at + a_kc, ahi, bt + b_blk, bhi, idesc, 1u);
+                if (X3) {
+                    umma_bf16_lh(d, at, ahi, bt + w_lo16, bhi, idesc, 1u);          // a_hi * w_lo
+                    umma_bf16_lh(d, at + a_lo16, ahi, bt, bhi, idesc, 1u);          // a_lo * w_hi
+                }
+                if (cin16 == 2) {
+                    umma_bf16_lh(d, at + a_kc, ahi, bt + b_blk, bhi, idesc, 1u);
+                    if (X3) {
+                        umma_bf16_lh(d, at + a_kc, ahi, bt + b_blk + w_lo16, bhi, idesc, 1u);
+                        umma_bf16_lh(d, at + a_kc + a_lo16, ahi, bt + b_blk, bhi, idesc, 1u);
+                    }
+                }
             }
             umma_commit(cx.bar + 8u * (uint32_t)b);
         }
@@ -261,22 +303,46 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
                 for (int hp8 = 0; hp8 < 2; ++hp8) {
                     const int plane = (c0 >> 3) + hp8;
                     float* u = v + hp8 * 8;
-                    uint4 o;
-                    if (kind == EPI_RES1) {
-                        uint4* rp = reinterpret_cast<uint4*>(raw + (size_t)plane * plane_b + rowb);
-                        const uint4 rv = *rp;
-                        u[0] += bf16_lo(rv.x); u[1] += bf16_hi(rv.x); u[2] += bf16_lo(rv.y); u[3] += bf16_hi(rv.y);
-                        u[4] += bf16_lo(rv.z); u[5] += bf16_hi(rv.z); u[6] += bf16_lo(rv.w); u[7] += bf16_hi(rv.w);
-                        o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]),
-                                       pack_bf16(u[6], u[7]));
-                        *rp = o;
+                    const size_t poff = (size_t)plane * plane_b + rowb;
+                    if (!X3) {
+                        uint4 o;
+                        if (kind == EPI_RES1) {
+                            uint4* rp = reinterpret_cast<uint4*>(raw + poff);
+                            const uint4 rv = *rp;
+                            u[0] += bf16_lo(rv.x); u[1] += bf16_hi(rv.x); u[2] += bf16_lo(rv.y); u[3] += bf16_hi(rv.y);
+                            u[4] += bf16_lo(rv.z); u[5] += bf16_hi(rv.z); u[6] += bf16_lo(rv.w); u[7] += bf16_hi(rv.w);
+                            o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]),
+                                           pack_bf16(u[6], u[7]));
+                            *rp = o;
+                        } else {
+                            o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]),
+                                           pack_bf16(u[6], u[7]));
+                        }
+                        if (kind != EPI_CONV)
+                            o = make_uint4(relu_bf16x2(o.x), relu_bf16x2(o.y), relu_bf16x2(o.z), relu_bf16x2(o.w));
+                        *reinterpret_cast<uint4*>(out0 + poff) = o;
                     } else {
-                        o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]),
-                                       pack_bf16(u[6], u[7]));
+                        if (kind == EPI_RES1) {
+                            const uint4 rh = *reinterpret_cast<const uint4*>(raw + poff);
+                            const uint4 rl2 = *reinterpret_cast<const uint4*>(raw + raw_lo_off + poff);
+                            u[0] += bf16_lo(rh.x) + bf16_lo(rl2.x); u[1] += bf16_hi(rh.x) + bf16_hi(rl2.x);
+                            u[2] += bf16_lo(rh.y) + bf16_lo(rl2.y); u[3] += bf16_hi(rh.y) + bf16_hi(rl2.y);
+                            u[4] += bf16_lo(rh.z) + bf16_lo(rl2.z); u[5] += bf16_hi(rh.z) + bf16_hi(rl2.z);
+                            u[6] += bf16_lo(rh.w) + bf16_lo(rl2.w); u[7] += bf16_hi(rh.w) + bf16_hi(rl2.w);
+                            uint4 h4, l4;
+                            split8(u, h4, l4);
+                            *reinterpret_cast<uint4*>(raw + poff) = h4;
+                            *reinterpret_cast<uint4*>(raw + raw_lo_off + poff) = l4;
+                        }
+                        if (kind != EPI_CONV) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) u[i] = fmaxf(u[i], 0.f);
+                        }
+                        uint4 h4, l4;
+                        split8(u, h4, l4);
+                        *reinterpret_cast<uint4*>(out0 + poff) = h4;
+                        *reinterpret_cast<uint4*>(out0 + out_lo_off + poff) = l4;
                     }
-                    if (kind != EPI_CONV)
-                        o = make_uint4(relu_bf16x2(o.x), relu_bf16x2(o.y), relu_bf16x2(o.z), relu_bf16x2(o.w));
-                    *reinterpret_cast<uint4*>(out0 + (size_t)plane * plane_b + rowb) = o;
                 }
             }
         }
@@ -289,6 +355,55 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
 }
 
 // max_pool2d(kernel 3, stride 2, padding 1) from the conv output T (level La) into raw/actA of level Lb
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+// split-bf16 variant: values are hi + lo (lo buffers `*_lo` bytes behind)
+__device__ __forceinline__ void pool_level_x3(const Level& La, const Level& Lb, int nvalid, int planes,
+                                              const unsigned char* Tbuf, uint32_t t_lo, unsigned char* raw, uint32_t raw_lo,
+                                              unsigned char* actA, uint32_t act_lo) {
+    const int per = Lb.h * Lb.w;
+    const int total = nvalid * per * planes;
+    for (int idx = threadIdx.x; idx < total; idx += TC_THREADS) {
+        const int p = idx / (nvalid * per);
+        int r = idx - p * nvalid * per;
+        const int j = r / per;
+        r -= j * per;
+        const int oy = r / Lb.w, ox = r - oy * Lb.w;
+        float m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = 2 * oy + dy;
+            if (yy < 0 || yy >= La.h) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = 2 * ox + dx;
+                if (xx < 0 || xx >= La.w) continue;
+                const size_t row = (size_t)La.guard + (size_t)j * La.P + (size_t)(yy + 1) * La.wp + (xx + 1);
+                const size_t off = ((size_t)p * La.RT + row) * 16;
+                float a[8], b[8];
+                unpack8(*reinterpret_cast<const uint4*>(Tbuf + off), a);
+                unpack8(*reinterpret_cast<const uint4*>(Tbuf + t_lo + off), b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], a[i] + b[i]);
+            }
+        }
+        const size_t orow = (size_t)Lb.guard + (size_t)j * Lb.P + (size_t)(oy + 1) * Lb.wp + (ox + 1);
+        const size_t ooff = ((size_t)p * Lb.RT + orow) * 16;
+        uint4 h4, l4;
+        split8(m, h4, l4);
+        *reinterpret_cast<uint4*>(raw + ooff) = h4;
+        *reinterpret_cast<uint4*>(raw + raw_lo + ooff) = l4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+        split8(m, h4, l4);
+        *reinterpret_cast<uint4*>(actA + ooff) = h4;
+        *reinterpret_cast<uint4*>(actA + act_lo + ooff) = l4;
+    }
+}
+
 __device__ __forceinline__ void pool_level(const Level& La, const Level& Lb, int nvalid, int planes,
                                            const unsigned char* Tbuf, unsigned char* raw, unsigned char* actA) {
     const uint32_t NEG = 0xff80ff80u;  // bf16 -inf pair

@@ -103,7 +103,7 @@ class DeviceNet:
 
     def set_precision(self, mode):
         """'bf16' (tcgen05 kernel: bf16 weights/activations, fp32 accumulate), 'fp32', or 'bf16_simt'"""
-        call("bpp_net_set_precision", self._h, {"bf16": 0, "fp32": 1, "bf16_simt": 2}[mode])
+        call("bpp_net_set_precision", self._h, {"bf16": 0, "fp32": 1, "bf16_simt": 2, "bf16x3": 3}[mode])
         self.precision = mode
 
     def profile(self):
