@@ -219,6 +219,15 @@ int bpp_engine_play_stub_host(bpp_engine *e, int stub_kind, int choose_mode, uin
 int bpp_engine_stats(bpp_engine *e, uint64_t stats_host[8], int reset, void *stream);
 /* Synchronises and returns BPP_E_CAPACITY if any game overflowed its pools (the search of that game stopped). */
 int bpp_engine_check(bpp_engine *e, void *stream);
+/* Dump the search graph of one game to the host (the content of the reference's dicts Qsa/Nsa/Ns/Ps/Es/Vs,
+ * MCTS_bpp.py:16-26).  Call with NULL buffers to obtain the sizes.  nodes_out_host: uint32 [n_nodes][32] records (words
+ * 0..H-1 rows, 28 remaining mask, 29 Ns, 30 edge-block offset in 8-byte units, 31 = nvalid | kind<<16 with kind 0 = key
+ * only, 1 = expanded, 2 = terminal +1, 3 = terminal -1).  edges_out_host: uint64 [n_units]; the block of an expanded
+ * node with nv valid actions (nvp = nv rounded up to 4) is Q float64[nvp] | P float64[nvp] | {int32 Nsa, int32 child}[nvp]
+ * | uint16 action[nvp].  Synchronises. */
+int bpp_engine_export_game(bpp_engine *e, int game, uint32_t *nodes_out_host, int32_t nodes_cap,
+                           uint64_t *edges_out_host, int64_t units_cap, int32_t *n_nodes_host, int64_t *n_units_host,
+                           void *stream);
 /* per-game graph sizes: nodes int32 [G], edge units int32 [G] (either may be NULL) */
 int bpp_engine_graph_sizes(bpp_engine *e, int32_t *nodes_out_dev, int32_t *units_out_dev, void *stream);
 

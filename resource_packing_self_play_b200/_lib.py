@@ -68,6 +68,7 @@ SIGNATURES = {
     "bpp_engine_play_stub_host": [_vp, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "bpp_engine_stats": [_vp, C.POINTER(_u64), _i32, _vp],
     "bpp_engine_check": [_vp, _vp],
+    "bpp_engine_export_game": [_vp, _i32, _vp, _i32, _vp, _i64, C.POINTER(_i32), C.POINTER(_i64), _vp],
     "bpp_engine_graph_sizes": [_vp, _vp, _vp, _vp],
     "bpp_net_create": [_i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)],
     "bpp_net_destroy": [_vp],

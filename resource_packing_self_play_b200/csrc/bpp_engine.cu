@@ -1334,6 +1334,31 @@ extern "C" int bpp_engine_check(bpp_engine* e, void* stream) {
     return BPP_OK;
 }
 
+extern "C" int bpp_engine_export_game(bpp_engine* e, int game, uint32_t* nodes_out_host, int32_t nodes_cap,
+                                      uint64_t* edges_out_host, int64_t units_cap, int32_t* n_nodes_host,
+                                      int64_t* n_units_host, void* stream) {
+    if (!e || !n_nodes_host || !n_units_host) return set_err(BPP_E_INVALID, "null argument");
+    if (game < 0 || game >= e->P.G) return set_err(BPP_E_INVALID, "game index %d out of range", game);
+    int nn = 0, nu = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nn, e->P.n_nodes + game, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaMemcpyAsync(&nu, e->P.n_units + game, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    *n_nodes_host = nn;
+    *n_units_host = nu;
+    if (nodes_out_host) {
+        if (nodes_cap < nn) return set_err(BPP_E_INVALID, "nodes buffer too small (%d < %d)", nodes_cap, nn);
+        CUDA_TRY(cudaMemcpyAsync(nodes_out_host, e->P.nodes + (size_t)game * e->P.node_cap * REC_WORDS,
+                                 (size_t)nn * REC_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, S(stream)));
+    }
+    if (edges_out_host) {
+        if (units_cap < nu) return set_err(BPP_E_INVALID, "edges buffer too small");
+        CUDA_TRY(cudaMemcpyAsync(edges_out_host, e->P.edges + (size_t)game * (size_t)e->P.edge_cap,
+                                 (size_t)nu * sizeof(uint64_t), cudaMemcpyDeviceToHost, S(stream)));
+    }
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    return BPP_OK;
+}
+
 extern "C" int bpp_engine_graph_sizes(bpp_engine* e, int32_t* nodes_out_dev, int32_t* units_out_dev, void* stream) {
     if (!e) return set_err(BPP_E_INVALID, "null argument");
     const size_t G = (size_t)e->P.G;

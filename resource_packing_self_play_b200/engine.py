@@ -351,6 +351,51 @@ class SearchEngine:
         call("bpp_engine_graph_sizes", self._h, _ptr(nodes), _ptr(units), _stream())
         return nodes, units
 
+    def export_game(self, g=0):
+        """search graph of game g as host arrays: (nodes uint32 (n, 32), edges uint64 (units,))"""
+        nn, nu = C.c_int32(0), C.c_int64(0)
+        call("bpp_engine_export_game", self._h, int(g), C.c_void_p(0), 0, C.c_void_p(0), 0, C.byref(nn), C.byref(nu),
+             _stream())
+        nodes = np.zeros((max(1, nn.value), REC_WORDS), dtype=np.uint32)
+        edges = np.zeros(max(1, nu.value), dtype=np.uint64)
+        call("bpp_engine_export_game", self._h, int(g), nodes.ctypes.data_as(C.c_void_p), nodes.shape[0],
+             edges.ctypes.data_as(C.c_void_p), edges.shape[0], C.byref(nn), C.byref(nu), _stream())
+        return nodes[:nn.value], edges[:nu.value]
+
+    def export_dicts(self, g, items_wh, dtype=np.int64):
+        """The reference's six dicts (MCTS_bpp.py:16-26) for game g, keyed by the reference's state bytes
+        (stringRepresentation of the (N+1, H, W) tensor): Qsa, Nsa, Ns, Ps, Es, Vs."""
+        nodes, edges = self.export_game(g)
+        states = unpack_states(nodes, np.repeat(np.asarray(items_wh)[None], len(nodes), axis=0), self.W, self.H, self.N,
+                               dtype=dtype) if len(nodes) else []
+        Qsa, Nsa, Ns, Ps, Es, Vs = {}, {}, {}, {}, {}, {}
+        for rec, st in zip(nodes, states):
+            key = st.tobytes()
+            kind = (int(rec[31]) >> 16) & 0xFF
+            if kind == 0:
+                continue  # key known only (created by a real move, not yet visited by search)
+            Es[key] = {1: 0, 2: 1, 3: -1}[kind]
+            if kind != 1:
+                continue
+            nv = int(rec[31]) & 0xFFFF
+            nvp = (nv + 3) & ~3
+            off = int(rec[30])
+            blk = edges[off:off + 3 * nvp + nvp // 4]
+            Q = blk[:nvp].view(np.float64)
+            Pv = blk[nvp:2 * nvp].view(np.float64)
+            NC = blk[2 * nvp:3 * nvp].view(np.int32).reshape(nvp, 2)
+            act = blk[3 * nvp:].view(np.uint16)[:nv]
+            p = np.zeros(self.A, dtype=np.float64)
+            v = np.zeros(self.A, dtype=np.int64)
+            p[act] = Pv[:nv]
+            v[act] = 1
+            Ps[key], Vs[key], Ns[key] = p, v, int(rec[29])
+            for e in range(nv):
+                if NC[e, 0] > 0:
+                    Qsa[(key, int(act[e]))] = float(Q[e])
+                    Nsa[(key, int(act[e]))] = int(NC[e, 0])
+        return Qsa, Nsa, Ns, Ps, Es, Vs
+
     def stats(self, reset=False):
         arr = (C.c_uint64 * 8)()
         call("bpp_engine_stats", self._h, arr, int(reset), _stream())

@@ -113,6 +113,20 @@ class MCTS:
     def root_counts(self):
         return [int(c) for c in self._engine().root_counts_host()[0]]
 
+    # the reference's public dict attributes (MCTS_bpp.py:20-26), materialised on demand from the device graph.
+    # Keys are the reference's state bytes; dims of items placed before the first search call are unknown (0).
+    def _dicts(self):
+        if self._eng is None or self._items is None:
+            return ({},) * 6
+        return self._eng.export_dicts(0, self._items)
+
+    Qsa = property(lambda self: self._dicts()[0])
+    Nsa = property(lambda self: self._dicts()[1])
+    Ns = property(lambda self: self._dicts()[2])
+    Ps = property(lambda self: self._dicts()[3])
+    Es = property(lambda self: self._dicts()[4])
+    Vs = property(lambda self: self._dicts()[5])
+
 
 class BatchedMCTS:
     """G lockstep games: the batched counterpart of MCTS.getActionProb + CoachBPP.executeEpisode's move loop."""

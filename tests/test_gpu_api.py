@@ -199,3 +199,32 @@ def test_execute_episodes_batched_produces_reference_shaped_examples():
     # batched arena: the same net against itself must be accepted (mean scores are equal up to tie-breaks in choose)
     p, n_, acc = coach.arena_sweep(net, net, np.arange(8) + 7, seed=3)
     assert len(p) == len(n_) == 8 and np.array_equal(p, n_) and acc == 1
+
+
+@pytest.mark.parametrize("ci", [4, 7, 8, 15])
+def test_whole_search_graph_equals_the_reference_dicts(ci):
+    """Not only the root visit counts: after an episode the device graph, dumped as the reference's six dicts, equals
+    the oracle's dicts entry by entry — Qsa and Ps bit for bit (float64), Nsa, Ns, Es, Vs exactly."""
+    from resource_packing_self_play_b200.game import BinPackingGame
+    from resource_packing_self_play_b200.mcts import MCTS
+    c = CASES[ci]
+    W, H, N = c["W"], c["H"], c["N"]
+    g, og = BinPackingGame(W, H, N, 1), O.OracleGame(W, H, N, 1)
+    args = _args(numMCTSSims=c["sims"], cpuct=c["cpuct"], alpha=c["alpha"])
+    m, om = MCTS(g, O.StubNet(c["stub"], W * N), args), O.OracleMCTS(og, O.StubNet(c["stub"], W * N), args)
+    board, planes = g.getInitBoard(), g.getInitItems(c["items"])
+    og.getInitItems(c["items"])
+    area = c["genW"] * c["genH"]
+    for a in c["actions"][:4]:
+        state = g.getBinItem(board, planes)
+        m.getActionProb(state, area, c["rewards"])
+        om.getActionProb(state, area, c["rewards"])
+        board, planes = g.getNextState(board, a, planes)
+    Qsa, Nsa, Ns, Ps, Es, Vs = m.Qsa, m.Nsa, m.Ns, m.Ps, m.Es, m.Vs
+    assert Nsa == om.Nsa and Ns == om.Ns
+    assert set(Es) == set(om.Es) and all(Es[k] == om.Es[k] for k in Es)
+    assert set(Qsa) == set(om.Qsa) and all(float(Qsa[k]) == float(om.Qsa[k]) for k in Qsa)   # bit-exact float64
+    assert set(Ps) == set(om.Ps)
+    for k in Ps:
+        assert np.array_equal(Ps[k], om.Ps[k]) and np.array_equal(Vs[k], om.Vs[k])
+    assert len(Qsa) > 20
