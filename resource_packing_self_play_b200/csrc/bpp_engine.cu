@@ -89,7 +89,7 @@ struct Params {
     uint32_t* table;
     unsigned long long* edges;
     unsigned long long* stats;  // [8]
-    const double* sqrt_tab;     // [2][sqrt_n]: sqrt(n), sqrt(n + 1e-8)
+    const double* sqrt_tab;     // [3][sqrt_n]: sqrt(n), sqrt(n + 1e-8), 1/n (correctly rounded, host-computed)
     int sqrt_n;
     int select_cap;             // lockstep: simulations per game and select launch (0 = until a leaf is parked)
 };
@@ -323,7 +323,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
         }
         cur = child;
     }
-    backup_path(gm.nodes, gm.edges, pe, depth, v, lane);
+    backup_path(gm.nodes, gm.edges, pe, depth, v, lane, P.sqrt_tab, P.sqrt_n);
     if (lane == 0) P.last_v[gm.g] = v;
     return 0;
 }
@@ -392,7 +392,7 @@ k_expand_backup(Params P, const void* policy, int policy_f64, const void* value,
     if (ok) {
         const double v = value_f64 ? reinterpret_cast<const double*>(value)[b]
                                    : (double)reinterpret_cast<const float*>(value)[b];
-        backup_path(gm.nodes, gm.edges, pe, depth, v, lane);
+        backup_path(gm.nodes, gm.edges, pe, depth, v, lane, P.sqrt_tab, P.sqrt_n);
         if (lane == 0) P.last_v[g] = v;
         st.expansions++;
         st.sims++;
@@ -997,13 +997,14 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     }
     {   // Ns[s] never exceeds the simulations of an episode (num_sims per move, at most N moves)
         const int tn = cfg->num_sims * cfg->N + 2;
-        std::vector<double> tab(2 * (size_t)tn);
+        std::vector<double> tab(3 * (size_t)tn);
         for (int i = 0; i < tn; ++i) {
             tab[i] = sqrt((double)i);
             tab[tn + i] = sqrt((double)i + 1e-8);
+            tab[2 * tn + i] = i ? 1.0 / (double)i : 0.0;
         }
         double* d_tab = nullptr;
-        ALLOC2(d_tab, 2 * (size_t)tn);
+        ALLOC2(d_tab, 3 * (size_t)tn);
         CUDA_TRY(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
         P.sqrt_tab = d_tab;
         P.sqrt_n = tn;
