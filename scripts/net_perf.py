@@ -53,7 +53,7 @@ def run(W, H, N, B, modes=("bf16", "bf16_simt", "fp32"), iters=20):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         out[m] = {"ms": ms, "evals_per_s": B / ms * 1e3, "tflops": B * FLOPS[(W, H, N)] / ms / 1e9}
-        if m == "bf16":
+        if m in ("bf16", "bf16x3"):
             out[m]["cta0_cycles"] = net.dnet.profile()
     return out
 
