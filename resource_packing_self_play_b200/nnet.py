@@ -192,41 +192,88 @@ class NNetWrapper:
         self.nnet.eval()
         self.sync_weights()
 
-    def train_compact(self, recs, items_wh, pis, vs, ops, steps_per_epoch=None, seed=None):
+    def train_compact(self, recs, items_wh, pis, vs, ops, steps_per_epoch=None, seed=None, use_graph=True):
         """Learner on compact examples that already live on the device (the batched / multi-GPU path).
         recs int32 (M, 32), items_wh int32 (M, N, 2), pis float32 (M, A), vs float32 (M,); `ops` = EnvOps (builds the
         dense input planes of each minibatch on the device).  Same optimiser, losses and sampling-with-replacement as
         `train` (NNet.py:27-67); with torch.distributed initialised every rank draws its own minibatches and the
-        gradients are averaged with one flat all-reduce per step.  Returns (mean pi loss, mean v loss) of the last
+        gradients are averaged with one flat all-reduce per step.  The step (planes kernel -> forward -> losses ->
+        backward -> gradient all-reduce -> Adam) is captured once in a CUDA graph and replayed: the learner of this
+        170 K-parameter net is launch-bound (~150 kernels per step).  Returns (mean pi loss, mean v loss) of the last
         epoch."""
         from .distributed import world
         rank, ws = world()
         M = recs.shape[0]
-        optimizer = torch.optim.Adam(self.nnet.parameters())
-        gen = torch.Generator(device=self.device)
-        gen.manual_seed((seed if seed is not None else int(np.random.randint(1 << 30))) * 977 + rank)
+        dev = self.device
         bs = int(self.args.batch_size)
         if steps_per_epoch is None:
             steps_per_epoch = max(1, int(M / (bs * ws)))
-        pi_m, v_m = AverageMeter(), AverageMeter()
-        for epoch in range(self.args.epochs):
-            self.nnet.train()
-            pi_m, v_m = AverageMeter(), AverageMeter()
-            for _ in range(steps_per_epoch):
-                ids = torch.randint(0, M, (bs,), device=self.device, generator=gen)
-                boards = ops.planes(recs[ids].contiguous(), items_wh[ids].contiguous())
-                out_pi, out_v = self.nnet(boards)
-                l_pi = self.loss_pi(pis[ids], out_pi)
-                l_v = self.loss_v(vs[ids], out_v)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed((seed if seed is not None else int(np.random.randint(1 << 30))) * 977 + rank)
+        optimizer = torch.optim.Adam(self.nnet.parameters(), capturable=use_graph)
+        self.nnet.train()
+        # static minibatch buffers (graph inputs) and loss outputs
+        b_recs = torch.zeros((bs, 32), dtype=torch.int32, device=dev)
+        b_items = torch.zeros((bs,) + tuple(items_wh.shape[1:]), dtype=torch.int32, device=dev)
+        b_pis = torch.zeros((bs, pis.shape[1]), dtype=torch.float32, device=dev)
+        b_vs = torch.zeros(bs, dtype=torch.float32, device=dev)
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+
+        def load_batch():
+            ids = torch.randint(0, M, (bs,), device=dev, generator=gen)
+            b_recs.copy_(recs[ids])
+            b_items.copy_(items_wh[ids])
+            b_pis.copy_(pis[ids])
+            b_vs.copy_(vs[ids])
+
+        def step():
+            boards = ops.planes(b_recs, b_items)
+            out_pi, out_v = self.nnet(boards)
+            l_pi = self.loss_pi(b_pis, out_pi)
+            l_v = self.loss_v(b_vs, out_v)
+            (l_pi + l_v).backward()
+            allreduce_gradients(self.nnet)
+            optimizer.step()
+            losses[0] = l_pi.detach()
+            losses[1] = l_v.detach()
+
+        total_steps = steps_per_epoch * int(self.args.epochs)
+        graph = None
+        done = 0
+        if use_graph and total_steps > 8:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):  # warm-up steps on a side stream (they are real training steps)
+                    load_batch()
+                    optimizer.zero_grad(set_to_none=True)
+                    step()
+                    done += 1
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            load_batch()
+            optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                step()
+            done += 1
+        acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        n_acc = 0
+        last_epoch_start = total_steps - steps_per_epoch
+        while done < total_steps:
+            load_batch()
+            if graph is not None:
+                graph.replay()
+            else:
                 optimizer.zero_grad(set_to_none=True)
-                (l_pi + l_v).backward()
-                allreduce_gradients(self.nnet)
-                optimizer.step()
-                pi_m.update(float(l_pi.detach()), bs)
-                v_m.update(float(l_v.detach()), bs)
+                step()
+            if done >= last_epoch_start:
+                acc += losses.double()
+                n_acc += 1
+            done += 1
         self.nnet.eval()
         self.sync_weights()
-        return pi_m.avg, v_m.avg
+        mean = (acc / max(1, n_acc)).cpu().numpy()
+        return float(mean[0]), float(mean[1])
 
     def loss_pi(self, targets, outputs):  # NNet.py:87-88
         return -torch.sum(targets * outputs) / targets.size()[0]
