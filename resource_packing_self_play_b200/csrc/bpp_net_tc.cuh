@@ -248,19 +248,25 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
       const int nb = min(tpp, nt - t0);
       // ---- issue: ONE thread queues the MMAs of all nb tiles (each tile into its own TMEM columns, each followed by a
       // commit to its own mbarrier); the tensor core drains the queue while the 128 threads run the epilogues below
-      if ((tid >> 5) == 0 && elect_one()) {  // warp-uniform branch + elect.sync: no per-thread serialisation loop
+      // the tiles of a pass are issued by DIFFERENT warps (tile b by warp b mod 8, one elected lane each): a single
+      // thread needs ~65 cycles of dependent uniform-datapath work per tcgen05.mma, which - not the tensor pipe - paced
+      // the MMA phase when one thread issued everything
+      if (elect_one()) {  // warp-uniform: every warp elects one lane; elect.sync avoids a per-thread serialisation loop
         tc_fence_after();
         const uint64_t b0 = umma_desc(w_base, (uint32_t)cout, 8u);
         const uint64_t a00 = umma_desc(a_base + (uint32_t)L.guard * 16u, (uint32_t)L.RT, 8u);
         const uint32_t ahi = (uint32_t)(a00 >> 32), bhi = (uint32_t)(b0 >> 32), blo0 = (uint32_t)b0;
         const uint32_t a_kc = 2u * plane_b >> 4, b_blk = (uint32_t)(2 * cout), b_tap = b_blk * (uint32_t)cin16;
         const uint32_t a_lo16 = in_lo_off >> 4, w_lo16 = (uint32_t)wbytes >> 4;
-        for (int b = 0; b < nb; ++b) {
+        for (int b = tid >> 5; b < nb; b += TC_THREADS / 32) {
             const uint32_t alo0 = (uint32_t)a00 + (uint32_t)(t0 + b) * 128u;  // +128 rows (16-byte units) per tile
             const uint32_t d = cx.tmem + (uint32_t)(b * cout);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t at = alo0 + (uint32_t)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
+                uint32_t at = alo0 + (uint32_t)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
+#ifdef BPP_TC_EXPERIMENT_ALIGNED
+                at &= ~7u;  // TIMING EXPERIMENT ONLY (wrong results): force 128-byte aligned operand windows
+#endif
                 const uint32_t bt = blo0 + (uint32_t)tap * b_tap;
                 umma_bf16_lh(d, at, ahi, bt, bhi, idesc, tap > 0 ? 1u : 0u);
                 if (X3) {
