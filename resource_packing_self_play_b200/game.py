@@ -12,6 +12,9 @@ import torch
 from .engine import EnvOps, pack_states, ranked_threshold, unpack_states
 
 
+_TIE_RNG = np.random.default_rng()  # never touches numpy's global legacy generator
+
+
 class BinPackingGame:
     """Rules facade, same surface as BinPackingGame.py:8-218 (dead Othello leftovers and the disabled, buggy
     getSymmetries are not provided; see DESIGN.md "out of scope")."""
@@ -86,7 +89,7 @@ class BinPackingGame:
         assert len(total_board) == self.num_items + self.n
         recs, items = self._pack(total_board)
         if tie is None:
-            tie = 1 if np.random.random() < 0.5 else -1  # the reference draws +-1 on r == bl (:212)
+            tie = 1 if _TIE_RNG.random() < 0.5 else -1  # the reference draws +-1 on r == bl (:212); private generator
         ended, score = self._ops.game_ended(recs, items, [int(items_total_area)], [int(self.max_h)],
                                             [ranked_threshold(rewards_list, alpha)], [tie])
         e = int(ended.item())
@@ -100,7 +103,7 @@ class BinPackingGame:
         recs = recs.copy()
         recs[:, 28] = 0  # no remaining items -> no legal move -> the kernel evaluates the reward branch
         if tie is None:
-            tie = 1 if np.random.random() < 0.5 else -1
+            tie = 1 if _TIE_RNG.random() < 0.5 else -1
         ended, score = self._ops.game_ended(recs, items, [int(items_total_area)], [int(self.max_h)],
                                             [ranked_threshold(rewards_list, alpha)], [tie])
         return int(ended.item()), np.float64(score.item())

@@ -17,6 +17,9 @@ from . import _lib
 from .engine import REC_REM, SearchEngine, pack_states, ranked_threshold
 
 
+_TIE_RNG = np.random.default_rng()
+
+
 class MCTS:
     def __init__(self, game, nnet, args, device=None):  # MCTS_bpp.py:16-26
         self.game = game
@@ -48,10 +51,9 @@ class MCTS:
         items = items[0]
         bl = ranked_threshold(rewardsList, self.args.alpha)
         max_h = int(getattr(g, "max_h", 0)) or int(items[:, 1].max())
-        consts = (int(totalArea), bl, max_h)
-        same = self._items is not None and (consts == self._consts or
-                                            (consts[:1] == self._consts[:1] and consts[2] == self._consts[2] and
-                                             np.isnan(bl) and np.isnan(self._consts[1])))
+        consts = (int(totalArea), None if np.isnan(bl) else bl, max_h)  # NaN (empty rewards list) compares as None
+        # same episode <=> same constants and every REMAINING item has the dims this episode started with
+        same = self._items is not None and consts == self._consts
         if same:
             for i in range(g.num_items):
                 if rem >> i & 1 and tuple(items[i]) != tuple(self._items[i]):
@@ -63,7 +65,9 @@ class MCTS:
             # the old dict entries; dropping the graph is equivalent (see DESIGN.md for the one exception)
             self._items = items.copy()
             self._consts = consts
-            tie = np.array([1 if np.random.random() < 0.5 else -1], dtype=np.int8)  # BinPackingGame.py:212
+            # value of a ranked-reward tie r == bl: the reference draws +-1 from numpy's GLOBAL generator when a tie
+            # happens (BinPackingGame.py:212); drawn here from a private generator so that the global stream is untouched
+            tie = np.array([1 if _TIE_RNG.random() < 0.5 else -1], dtype=np.int8)
             eng.reset(self._items[None], np.array([consts[0]], dtype=np.int32), np.array([bl]), tie)
             eng.set_max_h(np.array([max_h], dtype=np.int32))
         eng.set_roots(recs)
@@ -142,7 +146,7 @@ class BatchedMCTS:
     def reset(self, items_wh, total_area, rewards_list, tie=None):
         bl = np.full(self.G, ranked_threshold(rewards_list, self.args.alpha))
         if tie is None:
-            tie = np.where(np.random.random(self.G) < 0.5, 1, -1).astype(np.int8)
+            tie = np.where(_TIE_RNG.random(self.G) < 0.5, 1, -1).astype(np.int8)
         self.eng.reset(items_wh, total_area, bl, tie)
 
     def search(self, chunk=8, select_cap=None):
