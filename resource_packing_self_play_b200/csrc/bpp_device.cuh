@@ -274,6 +274,7 @@ __device__ __forceinline__ double div_small(double a, int d, const double* __res
 // rounded IEEE values __dsqrt_rn returns, as one broadcast load instead of a ~50-instruction software sequence.
 __device__ __forceinline__ int puct_select(const EdgeBlock& eb, int nv, int Ns, double cpuct, int lane,
                                            const double* __restrict__ sqrt_tab, int tab_n) {
+    if (nv == 1) return 0;  // a single legal action: the arg-max needs no arithmetic
     double bu = __longlong_as_double((long long)0xfff0000000000000ull);  // -inf
     int be = 0x7fffffff;
     // first round from registers: issue all loads, then decide which square root is needed (the root has every edge
