@@ -261,23 +261,26 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     const long long t_start = clock64();
     const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
     const int S = T.S;
-    const int ngroups = (B + S - 1) / S;
     const int cin16_0 = (P.Cin + 15) / 16;
     WPre pre;
     auto lay_w = [&](int l) { return T.wts_umma + T.w_off[l]; };
     auto lay_b = [&](int l) { return P.bias + P.conv[l].b_off; };
     auto lay_wl = [&](int l) { return T.wts_umma_lo + T.w_off[l]; };
-    if (!X3 && (int)blockIdx.x < ngroups) wpre_load(pre, lay_w(0), T.lay_n16[0], lay_b(0), P.conv[0].co);
-    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const int nvalid = min(S, B - grp * S);
+    if (!X3) wpre_load(pre, lay_w(0), T.lay_n16[0], lay_b(0), P.conv[0].co);
+    // every CTA takes one contiguous, equally sized slice of the batch and walks it in groups of <= S leaves: all CTAs
+    // finish together (with "group g -> CTA g mod grid" a batch of 2,800 leaves left 36 % of the CTAs idle in the last wave)
+    const int slice_lo = (int)(((long long)blockIdx.x * B) / gridDim.x);
+    const int slice_hi = (int)(((long long)(blockIdx.x + 1) * B) / gridDim.x);
+    for (int b0 = slice_lo; b0 < slice_hi; b0 += S) {
+        const int nvalid = min(S, slice_hi - b0);
         long long tq = clock64();
         // ---- level-0 operand planes from the compact records (getBinItem, BinPackingGame.py:118-120)
         const Level& L0 = T.lv[0];
         zero_bytes(regA, (X3 ? 2 : 1) * 2 * cin16_0 * L0.RT * 16);  // split mode: the lo planes of the 0/1 input stay zero
-        for (int i = tid; i < nvalid * 32; i += TC_THREADS) s_rec[i >> 5][i & 31] = recs[(size_t)(grp * S + (i >> 5)) * 32 + (i & 31)];
+        for (int i = tid; i < nvalid * 32; i += TC_THREADS) s_rec[i >> 5][i & 31] = recs[(size_t)(b0 + (i >> 5)) * 32 + (i & 31)];
         for (int i = tid; i < nvalid * P.N * 2; i += TC_THREADS) {
             const int j = i / (P.N * 2), r = i - j * P.N * 2;
-            const int b = grp * S + j;
+            const int b = b0 + j;
             const int g = game ? game[b] : b;
             s_it[j][r >> 1][r & 1] = items_wh[(size_t)g * P.N * 2 + r];
         }
@@ -451,7 +454,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         }
         __syncthreads();
         for (int j = warp; j < nvalid; j += TC_THREADS / 32) {  // one warp per leaf: value head + softmax
-            const int b = grp * S + j;
+            const int b = b0 + j;
             float acc = 0.f;
             for (int i = lane; i < HIDDEN; i += 32)
                 acc = fmaf(hid[j * HIDDEN + i], wt<X3>(P, P.fc_value_off + i), acc);
