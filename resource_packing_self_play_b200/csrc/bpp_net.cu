@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(bpptc::TC_THREADS, ((NS <= 4 && !X3) ? 2 : 1))
 k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__ count_dev,
                  const uint32_t* __restrict__ recs, const int32_t* __restrict__ game,
                  const int32_t* __restrict__ items_wh, float* __restrict__ policy, float* __restrict__ value,
-                 long long* prof) {
+                 long long* prof, __nv_bfloat16* __restrict__ feat_out) {
     using namespace bpptc;
     extern __shared__ __align__(1024) unsigned char arena[];
     __shared__ __align__(8) uint64_t s_bar[MAX_BARS];
@@ -360,6 +360,21 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         float* part = lg + NS * P.A;                              // [2][NS][256] / [2][NS][A] partial sums
         const int hw3 = L3.h * L3.w;
         const size_t raw_lo3 = (size_t)(P.conv[NCONV - 1].co / 8) * L3.RT * 16;
+        if (!X3 && feat_out) {
+            // trunk only: relu(flatten(x)) goes to HBM as bf16 [B][flat]; the two FC heads run as real GEMMs over the
+            // whole batch in k_net_heads_tc (128-leaf M tiles) instead of per group of S leaves here
+            for (int idx = tid; idx < nvalid * P.flat; idx += TC_THREADS) {
+                const int j = idx / P.flat, f = idx - j * P.flat;
+                const int c = f / hw3, q = f - c * hw3;
+                const int y = q / L3.w, x = q - y * L3.w;
+                const size_t row = (size_t)L3.guard + (size_t)j * L3.P + (size_t)(y + 1) * L3.wp + (x + 1);
+                const uint16_t e = *(reinterpret_cast<const uint16_t*>(raw + ((size_t)(c >> 3) * L3.RT + row) * 16) + (c & 7));
+                reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (e & 0x8000u) ? (uint16_t)0 : e;
+            }
+            __syncthreads();
+            TC_PROF(6, tq);
+            continue;
+        }
         for (int idx = tid; idx < NS * P.flat; idx += TC_THREADS) {
             const int j = idx / P.flat, f = idx - j * P.flat;
             float v = 0.f;
@@ -484,6 +499,158 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"((uint32_t)T.tmem_cols));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FC heads as batched GEMMs on the tensor core: one CTA = 128 leaves (one M tile).
+//   hidden = relu(feat[128 x flat] * W1^T + b1)   -> TMEM columns [0, 256)
+//   logits = hidden[128 x 256] * W2^T + b2        -> TMEM columns [256, 256 + N2)
+//   value  = tanh(hidden . wv + bv);  policy = softmax(logits)   (thread t = leaf t = TMEM lane t)
+// The A operand (features, then the bf16 hidden activations) sits in shared memory in the 8-channel-plane layout; the
+// weights stream through two 32 KB stages in the UMMA B layout prepared on the host.
+struct HeadParams {
+    int flat, A, N2;                      // N2 = A rounded up to 16 (UMMA N granularity for M = 128)
+    const __nv_bfloat16* w1u;             // [flat/16][2][256][8]
+    const __nv_bfloat16* w2u;             // [16][2][N2][8]
+    const float* b1;                      // [256]
+    const float* b2;                      // [A]
+    const float* wv;                      // [256] (bf16-rounded values, as fp32)
+    float bv;
+};
+constexpr int HEAD_THREADS = 128;
+constexpr int HEAD_STAGE_BYTES = 32 * 1024;
+
+__global__ void __launch_bounds__(HEAD_THREADS, 1)
+k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, const __nv_bfloat16* __restrict__ feat,
+               float* __restrict__ policy, float* __restrict__ value) {
+    using namespace bpptc;
+    extern __shared__ __align__(1024) unsigned char hsm[];
+    __shared__ __align__(8) uint64_t s_bar[3];  // [0], [1]: weight stages free again; [2]: GEMM complete
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_b1[HIDDEN], s_wv[HIDDEN];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
+    const int row0 = blockIdx.x * 128;
+    if (row0 >= B) return;
+    const int kplanes = (Hp.flat > HIDDEN ? Hp.flat : HIDDEN) / 8;
+    unsigned char* areg = hsm;                                   // planes x 128 rows x 16 B
+    unsigned char* stage0 = hsm + (size_t)kplanes * 2048;
+    if (tid < 3) mbar_init(smem_u32(&s_bar[tid]), 1);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    for (int i = tid; i < HIDDEN; i += HEAD_THREADS) {
+        s_b1[i] = Hp.b1[i];
+        s_wv[i] = Hp.wv[i];
+    }
+    // A operand: features of rows row0..row0+127 (zero beyond the batch), thread = row, loop over planes
+    {
+        const int r = row0 + tid;
+        const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)r * Hp.flat);
+        for (int p = 0; p < Hp.flat / 8; ++p) {
+            const uint4 v = r < B ? __ldg(src + p) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(areg + (size_t)p * 2048 + tid * 16) = v;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t bar0 = smem_u32(&s_bar[0]);
+    uint32_t ph[3] = {0, 0, 0};
+    int used[2] = {0, 0};
+
+    // one GEMM: D[tmem + dcol] (128 x N) = A planes (K = 16*nkc) * Wu^T, weights streamed in chunks of `kpc` k-blocks
+    auto gemm = [&](const __nv_bfloat16* wu, int nkc, int N, uint32_t dcol) {
+        const int blk_bytes = 2 * N * 16;
+        const int kpc = HEAD_STAGE_BYTES / blk_bytes;
+        const uint32_t idesc = umma_idesc(N);
+        int chunk = 0;
+        for (int kc0 = 0; kc0 < nkc; kc0 += kpc, ++chunk) {
+            const int st = chunk & 1;
+            const int nk = min(kpc, nkc - kc0);
+            if (used[st]) {  // the MMAs that read this stage must have completed
+                mbar_wait(bar0 + 8u * st, ph[st]);
+                ph[st] ^= 1u;
+            }
+            unsigned char* sb = stage0 + (size_t)st * HEAD_STAGE_BYTES;
+            const uint4* src = reinterpret_cast<const uint4*>(wu + (size_t)kc0 * blk_bytes / 2);
+            for (int i = tid; i < nk * blk_bytes / 16; i += HEAD_THREADS)
+                reinterpret_cast<uint4*>(sb)[i] = __ldg(src + i);
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0 && elect_one()) {
+                tc_fence_after();
+                const uint64_t a0 = umma_desc(smem_u32(areg), 128u, 8u);
+                const uint64_t b0 = umma_desc(smem_u32(sb), (uint32_t)N, 8u);
+                for (int k = 0; k < nk; ++k)
+                    umma_bf16(tmem + dcol, a0 + (uint64_t)((kc0 + k) * 2 * 2048 >> 4), b0 + (uint64_t)(k * blk_bytes >> 4),
+                              idesc, (kc0 + k) > 0 ? 1u : 0u);
+                umma_commit(bar0 + 8u * st);
+                if (kc0 + nk >= nkc) umma_commit(bar0 + 16u);
+            }
+            __syncwarp();
+            used[st] = 1;
+        }
+        mbar_wait(bar0 + 16u, ph[2]);
+        ph[2] ^= 1u;
+        tc_fence_after();
+    };
+
+    gemm(Hp.w1u, Hp.flat / 16, HIDDEN, 0u);
+    // epilogue 1: hidden = relu(acc + b1) -> bf16 planes (A operand of the logits GEMM) + value head dot product
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    float vacc = 0.f;
+    for (int c0 = 0; c0 < HIDDEN; c0 += 16) {
+        float v[16];
+        tmem_ld16(lane_base + (uint32_t)c0, v);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float h0 = fmaxf(v[2 * i] + s_b1[c0 + 2 * i], 0.f), h1 = fmaxf(v[2 * i + 1] + s_b1[c0 + 2 * i + 1], 0.f);
+            pk[i] = pack_bf16(h0, h1);
+            vacc = fmaf(bf16_lo(pk[i]), s_wv[c0 + 2 * i], vacc);
+            vacc = fmaf(bf16_hi(pk[i]), s_wv[c0 + 2 * i + 1], vacc);
+        }
+        *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8) * 2048 + tid * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8 + 1) * 2048 + tid * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    tc_fence_before();
+    __syncthreads();  // all hidden planes written (gemm() fences them towards the async proxy with the first weight chunk)
+    gemm(Hp.w2u, HIDDEN / 16, Hp.N2, 256u);
+    // epilogue 2: online softmax over this thread's row, then normalised write-out
+    const int r = row0 + tid;
+    float mx = -INFINITY, sum = 0.f;
+    for (int c0 = 0; c0 < Hp.A; c0 += 16) {
+        float v[16];
+        tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (c0 + i < Hp.A) {
+                const float l = v[i] + __ldg(Hp.b2 + c0 + i);
+                const float nm = fmaxf(mx, l);
+                sum = sum * __expf(mx - nm) + __expf(l - nm);
+                mx = nm;
+            }
+        }
+    }
+    const float lse = mx + logf(sum);
+    for (int c0 = 0; c0 < Hp.A; c0 += 16) {
+        float v[16];
+        tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
+        if (r < B) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < Hp.A) policy[(size_t)r * Hp.A + c0 + i] = expf(v[i] + __ldg(Hp.b2 + c0 + i) - lse);
+        }
+    }
+    if (r < B) value[r] = tanhf(vacc + Hp.bv);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
 // shared-memory budget of the tensor-core kernel: ~110 KB lets two CTAs share an SM so that one CTA's epilogue overlaps
 // the other's MMAs (BPP_TC_SMEM_KB overrides, for experiments)
 int tc_smem_cap() {
@@ -521,6 +688,13 @@ struct bpp_net {
     __nv_bfloat16* d_wts_logits_pad = nullptr;
     long long umma_elems = 0;
     long long* d_prof = nullptr;  // phase timers of CTA 0 (bpp_net_profile)
+    __nv_bfloat16* d_feat = nullptr;     // [max_batch][flat] trunk output (bf16 mode)
+    __nv_bfloat16* d_w1u = nullptr;      // FC weights in the UMMA B layout
+    __nv_bfloat16* d_w2u = nullptr;
+    float* d_wv32 = nullptr;
+    HeadParams Hp;
+    int heads_smem = 0;
+    bool heads_ok = false;
     bool tc_ok = false;
     int ctas_per_sm = 1;
     bool committed = false;
@@ -692,6 +866,26 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         return nerr(BPP_E_NOMEM, "cudaMalloc of the network parameters failed");
     }
     n->T.wts_logits_pad = n->d_wts_logits_pad;
+    {   // tensor-core heads
+        HeadParams& Hp = n->Hp;
+        Hp.flat = P.flat; Hp.A = P.A; Hp.N2 = (P.A + 15) & ~15;
+        const int kplanes = (P.flat > HIDDEN ? P.flat : HIDDEN) / 8;
+        n->heads_smem = kplanes * 2048 + 2 * HEAD_STAGE_BYTES;
+        n->heads_ok = (P.flat % 16 == 0) && Hp.N2 <= 256 && n->heads_smem <= 220 * 1024 && getenv("BPP_NO_TC_HEADS") == nullptr;
+        if (n->heads_ok) {
+            if (cudaMalloc(&n->d_feat, (size_t)max_batch * P.flat * 2) != cudaSuccess ||
+                cudaMalloc(&n->d_w1u, (size_t)P.flat * HIDDEN * 2) != cudaSuccess ||
+                cudaMalloc(&n->d_w2u, (size_t)HIDDEN * Hp.N2 * 2) != cudaSuccess ||
+                cudaMalloc(&n->d_wv32, HIDDEN * sizeof(float)) != cudaSuccess ||
+                cudaFuncSetAttribute(k_net_heads_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, n->heads_smem) != cudaSuccess) {
+                cudaGetLastError();
+                delete n;
+                return nerr(BPP_E_NOMEM, "cudaMalloc of the head buffers failed");
+            }
+            Hp.w1u = n->d_w1u; Hp.w2u = n->d_w2u; Hp.wv = n->d_wv32;
+            Hp.b1 = n->d_bias + P.b_hidden_off; Hp.b2 = n->d_bias + P.b_logits_off;
+        }
+    }
     {   // the split-mode plan shares the weight pointers and layer tables
         bpptc::TcParams keep = n->T3;
         n->T3 = n->T;
@@ -712,6 +906,10 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     cudaFree(n->d_wts_umma_lo);
     cudaFree(n->d_wts_logits_pad);
     cudaFree(n->d_prof);
+    cudaFree(n->d_feat);
+    cudaFree(n->d_w1u);
+    cudaFree(n->d_w2u);
+    cudaFree(n->d_wv32);
     cudaFree(n->d_bias);
     delete n;
     return BPP_OK;
@@ -793,6 +991,35 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
                             }
             ++li;
         }
+    if (n->heads_ok) {  // FC weights in the UMMA K-major B layout [k-block][k-half][n][8]
+        const HeadParams& Hp = n->Hp;
+        std::vector<uint16_t> w1u((size_t)P.flat * HIDDEN, 0), w2u((size_t)HIDDEN * Hp.N2, 0);
+        std::vector<float> wv32(HIDDEN);
+        const std::vector<float>& h1 = n->host["hidden_fc.weight"];  // [256][flat]
+        for (int kc = 0; kc < P.flat / 16; ++kc)
+            for (int kh = 0; kh < 2; ++kh)
+                for (int o = 0; o < HIDDEN; ++o)
+                    for (int j = 0; j < 8; ++j)
+                        w1u[((((size_t)kc * 2 + kh) * HIDDEN + o) * 8) + j] =
+                            f32_to_bf16_rne(h1[(size_t)o * P.flat + kc * 16 + kh * 8 + j]);
+        const std::vector<float>& l2 = n->host["logits_fc.weight"];  // [A][256]
+        for (int kc = 0; kc < HIDDEN / 16; ++kc)
+            for (int kh = 0; kh < 2; ++kh)
+                for (int o = 0; o < P.A; ++o)
+                    for (int j = 0; j < 8; ++j)
+                        w2u[((((size_t)kc * 2 + kh) * Hp.N2 + o) * 8) + j] =
+                            f32_to_bf16_rne(l2[(size_t)o * HIDDEN + kc * 16 + kh * 8 + j]);
+        const std::vector<float>& v3 = n->host["value_fc.weight"];
+        for (int i = 0; i < HIDDEN; ++i) {
+            uint32_t hb = (uint32_t)f32_to_bf16_rne(v3[i]) << 16;
+            memcpy(&wv32[i], &hb, 4);
+        }
+        n->Hp.bv = n->host["value_fc.bias"][0];
+        if (cudaMemcpy(n->d_w1u, w1u.data(), w1u.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(n->d_w2u, w2u.data(), w2u.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(n->d_wv32, wv32.data(), wv32.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            return nerr(BPP_E_CUDA, "head parameter upload failed");
+    }
     std::vector<uint16_t> wlp((size_t)HIDDEN * n->T.A_pad, 0);
     {
         const std::vector<float>& src2 = n->host["logits_fc.weight"];  // [A][256]
@@ -840,21 +1067,27 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int groups = (B + n->T.S - 1) / n->T.S;
         const int cap = 148 * n->ctas_per_sm;
         const int g2 = groups < cap ? groups : cap;
+        __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
         if (n->T.S <= 4)
             k_net_forward_tc<4, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
-                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
+                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
         else
             k_net_forward_tc<8, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
-                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
+                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
+        if (fo)
+            k_net_heads_tc<<<(B + 127) / 128, HEAD_THREADS, n->heads_smem, st>>>(n->Hp, B, count_dev, n->d_feat,
+                                                                               policy_out_dev, value_out_dev);
     } else if (n->precision == BPP_NET_BF16X3 && n->tc3_ok) {
         const int groups = (B + n->T3.S - 1) / n->T3.S;
         const int g2 = groups < 148 ? groups : 148;
         if (n->T3.S <= 4)
             k_net_forward_tc<4, true><<<g2, bpptc::TC_THREADS, n->T3.smem_bytes, st>>>(
-                n->P, n->T3, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
+                n->P, n->T3, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof,
+                nullptr);
         else
             k_net_forward_tc<8, true><<<g2, bpptc::TC_THREADS, n->T3.smem_bytes, st>>>(
-                n->P, n->T3, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof);
+                n->P, n->T3, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof,
+                nullptr);
     } else if (n->precision == BPP_NET_FP32)
         k_net_forward<true><<<grid, NET_THREADS, n->smem_bytes, st>>>(n->P, B, count_dev, recs_dev, game_dev, items_wh_dev,
                                                                       policy_out_dev, value_out_dev);
