@@ -264,6 +264,32 @@ int bpp_net_profile(bpp_net *n, int64_t cycles_host[8]);
 int bpp_net_forward(bpp_net *n, int B, const int32_t *count_dev, const uint32_t *recs_dev, const int32_t *game_dev,
                     const int32_t *items_wh_dev, float *policy_out_dev, float *value_out_dev, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Learner step (NNetWrapper.train, NNet.py:27-67; losses NNet.py:87-91) in fp32 on the device: forward with stashed
+ * activations, loss_pi + loss_v, backward through the whole network, gradients reduced in a fixed order.  Parameters,
+ * gradients and Adam moments are flat caller-owned fp32 device buffers in the reference's state_dict order
+ * (conv_seqs.{0,1,2}.{conv,res_block0.conv0,res_block0.conv1,res_block1.conv0,res_block1.conv1}.{weight,bias},
+ * hidden_fc, logits_fc, value_fc; PyTorch layouts), see bpp_learner_param_offset.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct bpp_learner bpp_learner;
+int bpp_learner_create(int W, int H, int N, int max_batch, int device, bpp_learner **out);
+int bpp_learner_destroy(bpp_learner *l);
+int bpp_learner_num_params(bpp_learner *l, int64_t *out);
+int bpp_learner_param_offset(bpp_learner *l, const char *name, int64_t *offset, int64_t *numel);
+/* One minibatch of B examples: example b is row ids_dev[b] (int64; NULL = identity) of recs_dev uint32 [*][32],
+ * items_wh_dev int32 [*][N][2], pis_dev float32 [*][A], vs_dev float32 [*].  losses_out_dev float32 [2] =
+ * {loss_pi, loss_v} (NNet.py:87-91, means over the batch).  grads_out_dev float32 [num_params] = d(loss_pi + loss_v)/dp;
+ * NULL = forward and losses only.  Optional outputs: logp_out_dev float32 [B][A] (log_softmax), v_out_dev float32 [B]. */
+int bpp_learner_grad(bpp_learner *l, int B, const float *params_dev, const uint32_t *recs_dev,
+                     const int32_t *items_wh_dev, const int64_t *ids_dev, const float *pis_dev, const float *vs_dev,
+                     float *grads_out_dev, float *losses_out_dev, float *logp_out_dev, float *v_out_dev, void *stream);
+/* torch.optim.Adam update (optimizer of NNet.py:31; no weight decay) on flat buffers: g = grads * grad_scale (1/world
+ * after a sum all-reduce).  The step count t >= 1 comes from step_dev (int32 in device memory, for CUDA-graph replay)
+ * when it is not NULL, else from `step`. */
+int bpp_learner_adam(int64_t n, float *params_dev, const float *grads_dev, float *exp_avg_dev, float *exp_avg_sq_dev,
+                     int step, const int32_t *step_dev, float grad_scale, float lr, float beta1, float beta2, float eps,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,12 @@ SIGNATURES = {
     "bpp_net_set_precision": [_vp, _i32],
     "bpp_net_profile": [_vp, C.POINTER(_i64)],
     "bpp_net_forward": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "bpp_learner_create": [_i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)],
+    "bpp_learner_destroy": [_vp],
+    "bpp_learner_num_params": [_vp, C.POINTER(_i64)],
+    "bpp_learner_param_offset": [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)],
+    "bpp_learner_grad": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "bpp_learner_adam": [_i64, _vp, _vp, _vp, _vp, _i32, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp],
 }
 _RESTYPES = {"bpp_last_error": C.c_char_p, "bpp_engine_device_bytes": C.c_int64}
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libbpp_b200.so")
-SOURCES = ["bpp_engine.cu", "bpp_net.cu"]
+SOURCES = ["bpp_engine.cu", "bpp_net.cu", "bpp_learner.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 

@@ -1,0 +1,872 @@
+// Learner step of the policy/value network in fp32 on the CUDA cores: forward with stashed activations, losses, full
+// backward, deterministic gradient reduction, Adam.  Follows NNetWrapper.train (NNet.py:27-67: Adam with default
+// hyper-parameters, loss = loss_pi + loss_v, NNet.py:87-91) over BinPackingNNet.forward (BinpackingNNet.py:72-81),
+// ConvSequence (:29-48: conv -> max_pool2d(3, 2, 1) -> two residual blocks) and ResidualBlock (:15-27, pre-activation).
+//
+// Why fp32 SIMT and not tcgen05: the gradients must reproduce the reference's fp32 training (the trained reference
+// checkpoints reach logits of -3e3, which bf16 operands cannot represent, DESIGN.md "leaf evaluation"), and the net is
+// 4.4 MFLOP per sample, so a minibatch step is ~7 GFLOP: launch- and latency-bound, not FLOP-bound.
+//
+// Layout: activations fp32 [B][C][h*w] per tensor in one device buffer.  Parameters, gradients and Adam moments are
+// flat caller-owned fp32 device buffers in state_dict order (bpp_learner_param_offset).  Per-chunk partial gradients
+// [chunk][param] are summed in a fixed order (no atomics): the step is run-to-run deterministic.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bpp_b200.h"
+
+int bpp_set_error_message(int code, const char* msg);  // defined in bpp_engine.cu
+
+namespace {
+
+constexpr int REC_WORDS = 32, REC_REM = 28;
+constexpr int HIDDEN = 256;
+constexpr int NSTAGE = 3, NCONV = 15;
+constexpr int SMAX = 16;      // samples per gradient chunk (register arrays in the heads kernel)
+constexpr int NCHUNK0 = 32;   // chunks for batches up to NCHUNK0 * SMAX
+constexpr int THREADS = 256;
+
+int lerr(int code, const std::string& m) { return bpp_set_error_message(code, m.c_str()); }
+
+struct ConvL {
+    int cin, cout, h, w;
+    long long w_off, b_off;     // offsets into the flat parameter vector
+    long long in_off, out_off;  // per-sample-scaled offsets are resolved on the host into pointers at launch
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// input planes (BinPackingGame.getBinItem layout: plane 0 = bin, plane 1+i = item i while it is still to be placed)
+__global__ void k_lr_planes(int B, int W, int H, int N, const uint32_t* __restrict__ recs, const int32_t* __restrict__ items_wh,
+                            const int64_t* __restrict__ ids, float* __restrict__ out) {
+    const int hw = H * W, per = (N + 1) * hw;
+    const long long total = (long long)B * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        int r = (int)(i - (long long)b * per);
+        const int c = r / hw;
+        r -= c * hw;
+        const int y = r / W, x = r - y * W;
+        const long long e = ids ? ids[b] : b;
+        const uint32_t* rec = recs + (size_t)e * REC_WORDS;
+        float v;
+        if (c == 0) {
+            v = (float)((rec[y] >> x) & 1u);
+        } else {
+            const int32_t* wh = items_wh + ((size_t)e * N + (c - 1)) * 2;
+            v = (((rec[REC_REM] >> (c - 1)) & 1u) && y < wh[1] && x < wh[0]) ? 1.f : 0.f;
+        }
+        out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 / pad 1 convolution over [B][cin][h*w] -> [B][cout][h*w] (cout a multiple of 16), used for the forward and, with
+// `transpose`, for the data gradient (weights read as W[k][o] rotated by 180 degrees).
+//   out = (mask ? (mask > 0) : 1) * (bias + conv(relu_in ? relu(in) : in)) + (add ? add : 0)
+// One CTA = G samples; one work item = one output position x 16 output channels.
+struct ConvArgs {
+    const float* in;
+    const float* wt;    // [cout][cin][9] (forward) or [cin][cout][9] read transposed + flipped (dgrad)
+    const float* bias;  // nullable
+    const float* mask;  // nullable, [B][cout][hw]
+    const float* add;   // nullable, [B][cout][hw]
+    float* out;
+    int B, cin, cout, h, w, G, relu_in, transpose;
+};
+
+__global__ void __launch_bounds__(THREADS) k_lr_conv(ConvArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int hw = a.h * a.w, wp = a.w + 2, PP = (a.h + 2) * wp;
+    float* s_w = sm;                               // [cin*9][cout]
+    float* s_in = sm + a.cin * 9 * a.cout;         // [cin][G][PP]
+    const int tid = threadIdx.x, b0 = blockIdx.x * a.G;
+    const int nk = a.cin * 9;
+    for (int idx = tid; idx < nk * a.cout; idx += THREADS) {
+        const int k = idx / a.cout, co = idx - k * a.cout;
+        const int ci = k / 9, tap = k - ci * 9;
+        s_w[idx] = a.transpose ? a.wt[((size_t)ci * a.cout + co) * 9 + (8 - tap)] : a.wt[((size_t)co * a.cin + ci) * 9 + tap];
+    }
+    for (int idx = tid; idx < a.cin * a.G * PP; idx += THREADS) s_in[idx] = 0.f;
+    __syncthreads();
+    const int per = a.cin * hw;
+    for (int idx = tid; idx < a.G * per; idx += THREADS) {
+        const int g = idx / per;
+        int r = idx - g * per;
+        const int ci = r / hw;
+        r -= ci * hw;
+        const int y = r / a.w, x = r - y * a.w;
+        if (b0 + g < a.B) {
+            float v = a.in[(size_t)(b0 + g) * per + ci * hw + r];
+            if (a.relu_in) v = fmaxf(v, 0.f);
+            s_in[(ci * a.G + g) * PP + (y + 1) * wp + x + 1] = v;
+        }
+    }
+    __syncthreads();
+    const int npos = a.G * hw, items = npos * (a.cout >> 4);
+    const int cstride = a.G * PP;
+    for (int item = tid; item < items; item += THREADS) {
+        const int cb = item / npos, p = item - cb * npos;
+        const int g = p / hw, pos = p - g * hw;
+        const int b = b0 + g;
+        if (b >= a.B) continue;
+        const int y = pos / a.w, x = pos - y * a.w;
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = a.bias ? a.bias[cb * 16 + j] : 0.f;
+        const float* sp = s_in + g * PP + y * wp + x;  // top-left of the 3x3 window in the padded plane
+        const float* wp0 = s_w + cb * 16;
+        for (int ci = 0; ci < a.cin; ++ci) {
+#pragma unroll
+            for (int ty = 0; ty < 3; ++ty) {
+#pragma unroll
+                for (int tx = 0; tx < 3; ++tx) {
+                    const float v = sp[ci * cstride + ty * wp + tx];
+                    const float4* wv = reinterpret_cast<const float4*>(wp0 + (size_t)(ci * 9 + ty * 3 + tx) * a.cout);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w4 = wv[q];
+                        acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
+                        acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+                    }
+                }
+            }
+        }
+        const size_t o0 = ((size_t)b * a.cout + cb * 16) * hw + pos;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const size_t o = o0 + (size_t)j * hw;
+            float r = acc[j];
+            if (a.mask) r = a.mask[o] > 0.f ? r : 0.f;
+            if (a.add) r += a.add[o];
+            a.out[o] = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// max_pool2d(kernel 3, stride 2, padding 1) with the arg-max rule of torch (first maximum in row-major window order)
+__global__ void k_lr_pool_fwd(int BC, int h, int w, int oh, int ow, const float* __restrict__ in, float* __restrict__ out,
+                              uint8_t* __restrict__ amax) {
+    const long long total = (long long)BC * oh * ow;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int bc = (int)(i / (oh * ow));
+        const int r = (int)(i - (long long)bc * oh * ow);
+        const int oy = r / ow, ox = r - oy * ow;
+        const float* p = in + (size_t)bc * h * w;
+        float best = -INFINITY;
+        int code = 0;
+        bool first = true;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            if (iy < 0 || iy >= h) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < 0 || ix >= w) continue;
+                const float v = p[iy * w + ix];
+                if (first || v > best || v != v) {
+                    best = v;
+                    code = ky * 3 + kx;
+                    first = false;
+                }
+            }
+        }
+        out[i] = best;
+        amax[i] = (uint8_t)code;
+    }
+}
+
+__global__ void k_lr_pool_bwd(int BC, int h, int w, int oh, int ow, const float* __restrict__ dout,
+                              const uint8_t* __restrict__ amax, float* __restrict__ din) {
+    const long long total = (long long)BC * h * w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int bc = (int)(i / (h * w));
+        const int r = (int)(i - (long long)bc * h * w);
+        const int iy = r / w, ix = r - iy * w;
+        const float* dp = dout + (size_t)bc * oh * ow;
+        const uint8_t* am = amax + (size_t)bc * oh * ow;
+        float g = 0.f;
+        for (int oy = iy >> 1; oy <= ((iy + 1) >> 1) && oy < oh; ++oy) {
+            const int ky = iy - (2 * oy - 1);
+            if (ky < 0 || ky > 2) continue;
+            for (int ox = ix >> 1; ox <= ((ix + 1) >> 1) && ox < ow; ++ox) {
+                const int kx = ix - (2 * ox - 1);
+                if (kx < 0 || kx > 2) continue;
+                if (am[oy * ow + ox] == ky * 3 + kx) g += dp[oy * ow + ox];
+            }
+        }
+        din[i] = g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// heads: relu(flatten) -> hidden_fc -> relu -> {logits_fc -> log_softmax, value_fc -> tanh}, the two losses
+// (NNet.py:87-91), their backward, and this chunk's partial gradients of the three linear layers.
+// One CTA = one chunk of S <= SMAX samples.
+struct HeadArgs {
+    int B, S, flat, A;
+    const float* o2;       // [B][flat] last stage output (pre-relu)
+    const float* params;   // flat parameter vector
+    long long w1, b1, w2, b2, wv, bv;
+    const float* pis;      // [*][A] target policies
+    const float* vs;       // [*]    target values
+    const int64_t* ids;    // nullable gather index into pis / vs
+    float* dfeat;          // [B][flat] gradient w.r.t. o2
+    float* partial;        // [chunk][nparams]
+    long long nparams;
+    float* loss_partial;   // [chunk][2]
+    float* logp_out;       // nullable [B][A]: log-softmax output (evaluation)
+    float* v_out;          // nullable [B]
+};
+
+__global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_f = sm;                        // [S][flat]   relu(features)
+    float* s_h = s_f + SMAX * a.flat;       // [S][256]    hidden activations, later their gradients
+    float* s_l = s_h + SMAX * HIDDEN;       // [S][A + 1]  logits -> dlogits; column A = dv (pre-tanh gradient)
+    __shared__ float s_loss[2][THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = blockIdx.x * a.S;
+    const int S = min(a.S, a.B - b0);
+    const int A1 = a.A + 1;
+    const float invB = 1.f / (float)a.B;
+    const float* W1 = a.params + a.w1;
+    const float* W2 = a.params + a.w2;
+    const float* WV = a.params + a.wv;
+    float* part = a.partial + (size_t)blockIdx.x * a.nparams;
+
+    for (int idx = tid; idx < SMAX * a.flat; idx += THREADS) {
+        const int s = idx / a.flat, i = idx - s * a.flat;
+        s_f[idx] = s < S ? fmaxf(a.o2[(size_t)(b0 + s) * a.flat + i], 0.f) : 0.f;
+    }
+    __syncthreads();
+    // hidden = relu(W1 f + b1): thread = hidden unit
+    float hreg[SMAX];
+    {
+        const int o = tid;
+        float acc[SMAX];
+        const float bias = a.params[a.b1 + o];
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) acc[s] = bias;
+        const float4* wrow = reinterpret_cast<const float4*>(W1 + (size_t)o * a.flat);
+        for (int i4 = 0; i4 < a.flat / 4; ++i4) {
+            const float4 w4 = __ldg(wrow + i4);
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) {
+                const float4 f4 = *reinterpret_cast<const float4*>(s_f + s * a.flat + 4 * i4);
+                acc[s] = fmaf(w4.x, f4.x, acc[s]);
+                acc[s] = fmaf(w4.y, f4.y, acc[s]);
+                acc[s] = fmaf(w4.z, f4.z, acc[s]);
+                acc[s] = fmaf(w4.w, f4.w, acc[s]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) {
+            hreg[s] = fmaxf(acc[s], 0.f);
+            s_h[s * HIDDEN + o] = hreg[s];
+        }
+    }
+    __syncthreads();
+    // logits (threads j < A) and the value pre-activation (j == A)
+    for (int j = tid; j <= a.A; j += THREADS) {
+        float acc[SMAX];
+        const float bias = a.params[(j < a.A ? a.b2 : a.bv) + (j < a.A ? j : 0)];
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) acc[s] = bias;
+        const float* wrow = j < a.A ? W2 + (size_t)j * HIDDEN : WV;  // WV may not be 16-byte aligned (A odd multiples)
+        for (int o4 = 0; o4 < HIDDEN / 4; ++o4) {
+            const float4 w4 = j < a.A ? __ldg(reinterpret_cast<const float4*>(wrow) + o4)
+                                      : make_float4(__ldg(wrow + 4 * o4), __ldg(wrow + 4 * o4 + 1), __ldg(wrow + 4 * o4 + 2),
+                                                    __ldg(wrow + 4 * o4 + 3));
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) {
+                const float4 h4 = *reinterpret_cast<const float4*>(s_h + s * HIDDEN + 4 * o4);
+                acc[s] = fmaf(w4.x, h4.x, acc[s]);
+                acc[s] = fmaf(w4.y, h4.y, acc[s]);
+                acc[s] = fmaf(w4.z, h4.z, acc[s]);
+                acc[s] = fmaf(w4.w, h4.w, acc[s]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) s_l[s * A1 + j] = acc[s];
+    }
+    __syncthreads();
+    // per sample: log-softmax, losses, gradient of the logits and of the value pre-activation (one warp per sample)
+    float lpi = 0.f, lv = 0.f;
+    for (int s = warp; s < S; s += THREADS / 32) {
+        const long long e = a.ids ? a.ids[b0 + s] : (b0 + s);
+        const float* pi = a.pis + (size_t)e * a.A;
+        float* row = s_l + s * A1;
+        float mx = -INFINITY;
+        for (int j = lane; j < a.A; j += 32) mx = fmaxf(mx, row[j]);
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f, psum = 0.f;
+        for (int j = lane; j < a.A; j += 32) {
+            sum += expf(row[j] - mx);
+            psum += pi[j];
+        }
+        for (int o = 16; o; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        }
+        const float lse = mx + logf(sum);
+        float dot = 0.f;
+        for (int j = lane; j < a.A; j += 32) {
+            const float lp = row[j] - lse, t = pi[j];
+            dot += t * lp;
+            if (a.logp_out) a.logp_out[(size_t)(b0 + s) * a.A + j] = lp;
+            row[j] = (expf(lp) * psum - t) * invB;  // d(-sum(t * logp) / B) / dlogit
+        }
+        for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (lane == 0) {
+            const float v = tanhf(row[a.A]), z = a.vs[e];
+            if (a.v_out) a.v_out[b0 + s] = v;
+            lpi -= dot;
+            lv += (z - v) * (z - v);
+            row[a.A] = 2.f * (v - z) * invB * (1.f - v * v);
+        }
+    }
+    if (lane == 0) {
+        s_loss[0][warp] = lpi;
+        s_loss[1][warp] = lv;
+    }
+    for (int idx = tid; idx < (SMAX - S) * A1; idx += THREADS) s_l[S * A1 + idx] = 0.f;  // rows of absent samples
+    __syncthreads();
+    if (tid < 2) {
+        float t = 0.f;
+        for (int i = 0; i < THREADS / 32; ++i) t += s_loss[tid][i];
+        a.loss_partial[blockIdx.x * 2 + tid] = t * invB;
+    }
+    if (!a.partial) return;  // evaluation only
+    // partial gradients of logits_fc / value_fc: thread = hidden unit o (coalesced over o)
+    {
+        const int o = tid;
+        for (int j = 0; j <= a.A; ++j) {
+            float g = 0.f;
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) g = fmaf(s_l[s * A1 + j], hreg[s], g);
+            part[(j < a.A ? a.w2 + (long long)j * HIDDEN : a.wv) + o] = g;
+        }
+    }
+    for (int j = tid; j <= a.A; j += THREADS) {
+        float g = 0.f;
+        for (int s = 0; s < SMAX; ++s) g += s_l[s * A1 + j];
+        part[j < a.A ? a.b2 + j : a.bv] = g;
+    }
+    // gradient of the hidden activations: dh[s][o] = (sum_j dl[s][j] W2[j][o] + dv[s] wv[o]) * (h > 0)
+    float dh[SMAX];
+    {
+        const int o = tid;
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) dh[s] = 0.f;
+        for (int j = 0; j <= a.A; ++j) {
+            const float w = j < a.A ? __ldg(W2 + (size_t)j * HIDDEN + o) : __ldg(WV + o);
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) dh[s] = fmaf(s_l[s * A1 + j], w, dh[s]);
+        }
+        float gb = 0.f;
+        __syncthreads();  // every thread is done reading s_h through hreg's producers; s_h is reused for dh
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) {
+            dh[s] = hreg[s] > 0.f ? dh[s] : 0.f;
+            s_h[s * HIDDEN + o] = dh[s];
+            gb += dh[s];
+        }
+        part[a.b1 + o] = gb;
+    }
+    __syncthreads();
+    // partial gradient of hidden_fc.weight [256][flat] (coalesced over the flattened index)
+    for (int idx = tid; idx < HIDDEN * a.flat; idx += THREADS) {
+        const int o = idx / a.flat, i = idx - o * a.flat;
+        float g = 0.f;
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) g = fmaf(s_h[s * HIDDEN + o], s_f[s * a.flat + i], g);
+        part[a.w1 + idx] = g;
+    }
+    // gradient w.r.t. the last stage output: (W1^T dh) * (o2 > 0)
+    for (int i = tid; i < a.flat; i += THREADS) {
+        float acc[SMAX];
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) acc[s] = 0.f;
+        for (int o = 0; o < HIDDEN; ++o) {
+            const float w = __ldg(W1 + (size_t)o * a.flat + i);
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) acc[s] = fmaf(s_h[s * HIDDEN + o], w, acc[s]);
+        }
+        for (int s = 0; s < S; ++s) a.dfeat[(size_t)(b0 + s) * a.flat + i] = s_f[s * a.flat + i] > 0.f ? acc[s] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight / bias gradients of all 15 convolutions in one launch: grid = (chunks, layers).
+//   dW[co][ci][t] = sum_{b, y, x} dY[b][co][y][x] * X[b][ci][y + ty - 1][x + tx - 1]     (X = relu(in) where the layer has it)
+// thread = (ci, 4 output channels, sample subgroup): 36 accumulators; subgroups split the chunk's samples.
+struct WgradLayer {
+    const float* in;
+    const float* dy;
+    int cin, cout, h, w, relu_in, pg;  // pg = sample subgroups staged at once
+    long long w_off, b_off;
+};
+struct WgradArgs {
+    WgradLayer L[NCONV];
+    int B, S;
+    float* partial;
+    long long nparams;
+};
+
+__global__ void __launch_bounds__(THREADS) k_lr_wgrad(WgradArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const WgradLayer& L = a.L[blockIdx.y];
+    const int cin = L.cin, cout = L.cout, h = L.h, w = L.w, hw = h * w, wp = w + 2;
+    const int PPs = ((h + 2) * wp) | 1;  // odd plane stride: lanes (consecutive ci) hit distinct banks
+    const int pairs = cin * (cout >> 2), PG = L.pg;
+    float* s_x = sm;                       // [PG][cin][PPs]
+    float* s_dy = sm + ((PG * cin * PPs + 3) & ~3);  // [PG][hw][cout]
+    const int tid = threadIdx.x;
+    const int pair = tid % pairs, sg = tid / pairs;
+    const int ci = pair % cin, cq = pair / cin;
+    const bool active = sg < PG;
+    const int b0 = blockIdx.x * a.S;
+    const int S = min(a.S, a.B - b0);
+    float acc[4][9];
+    float accb[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        accb[c] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
+    }
+    for (int idx = tid; idx < PG * cin * PPs; idx += THREADS) s_x[idx] = 0.f;  // halos stay zero
+    for (int j0 = 0; j0 < S; j0 += PG) {
+        __syncthreads();
+        const int ns = min(PG, S - j0);
+        const int perx = cin * hw;
+        for (int idx = tid; idx < ns * perx; idx += THREADS) {
+            const int g = idx / perx;
+            int r = idx - g * perx;
+            const int c = r / hw;
+            r -= c * hw;
+            const int y = r / w, x = r - y * w;
+            float v = L.in[(size_t)(b0 + j0 + g) * perx + c * hw + r];
+            if (L.relu_in) v = fmaxf(v, 0.f);
+            s_x[(g * cin + c) * PPs + (y + 1) * wp + x + 1] = v;
+        }
+        const int pery = cout * hw;
+        for (int idx = tid; idx < ns * pery; idx += THREADS) {
+            const int g = idx / pery;
+            int r = idx - g * pery;
+            const int c = r / hw;
+            r -= c * hw;
+            s_dy[(g * hw + r) * cout + c] = L.dy[(size_t)(b0 + j0 + g) * pery + c * hw + r];
+        }
+        __syncthreads();
+        if (active && sg < ns) {
+            const float* xp = s_x + (sg * cin + ci) * PPs;
+            const float* dp = s_dy + (size_t)sg * hw * cout + cq * 4;
+            for (int y = 0; y < h; ++y) {
+                for (int x = 0; x < w; ++x) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(dp + (y * w + x) * cout);
+                    const float* q = xp + y * wp + x;
+#pragma unroll
+                    for (int ty = 0; ty < 3; ++ty) {
+#pragma unroll
+                        for (int tx = 0; tx < 3; ++tx) {
+                            const float v = q[ty * wp + tx];
+                            acc[0][ty * 3 + tx] = fmaf(d4.x, v, acc[0][ty * 3 + tx]);
+                            acc[1][ty * 3 + tx] = fmaf(d4.y, v, acc[1][ty * 3 + tx]);
+                            acc[2][ty * 3 + tx] = fmaf(d4.z, v, acc[2][ty * 3 + tx]);
+                            acc[3][ty * 3 + tx] = fmaf(d4.w, v, acc[3][ty * 3 + tx]);
+                        }
+                    }
+                    accb[0] += d4.x;
+                    accb[1] += d4.y;
+                    accb[2] += d4.z;
+                    accb[3] += d4.w;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // reduce the subgroups through shared memory, write this chunk's partial gradient (fixed order: deterministic)
+    float* s_red = sm;  // [PG][pairs][40]
+    if (active) {
+        float* r = s_red + ((size_t)sg * pairs + pair) * 40;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) r[c * 9 + t] = acc[c][t];
+            r[36 + c] = accb[c];
+        }
+    }
+    __syncthreads();
+    float* part = a.partial + (size_t)blockIdx.x * a.nparams;
+    const int nw = cout * cin * 9;
+    for (int idx = tid; idx < nw; idx += THREADS) {
+        const int co = idx / (cin * 9);
+        const int r = idx - co * cin * 9;
+        const int c = r / 9, t = r - c * 9;
+        const int pr = c + cin * (co >> 2);
+        float g = 0.f;
+        for (int s = 0; s < PG; ++s) g += s_red[((size_t)s * pairs + pr) * 40 + (co & 3) * 9 + t];
+        part[L.w_off + idx] = g;
+    }
+    for (int co = tid; co < cout; co += THREADS) {
+        const int pr = 0 + cin * (co >> 2);  // the ci == 0 thread of this channel quad
+        float g = 0.f;
+        for (int s = 0; s < PG; ++s) g += s_red[((size_t)s * pairs + pr) * 40 + 36 + (co & 3)];
+        part[L.b_off + co] = g;
+    }
+}
+
+// grads[p] = sum over chunks (fixed order); losses[0..1] likewise
+__global__ void k_lr_reduce(long long nparams, int nchunk, const float* __restrict__ partial, float* __restrict__ grads,
+                            const float* __restrict__ loss_partial, float* __restrict__ losses) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < nparams) {
+        float g = 0.f;
+        for (int k = 0; k < nchunk; ++k) g += partial[(size_t)k * nparams + i];
+        grads[i] = g;
+    }
+    if (i < 2 && losses) {
+        float t = 0.f;
+        for (int k = 0; k < nchunk; ++k) t += loss_partial[k * 2 + i];
+        losses[i] = t;
+    }
+}
+
+// torch.optim.Adam (no weight decay, no amsgrad): the update of torch/optim/adam.py::_single_tensor_adam
+__global__ void k_lr_adam(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                          float* __restrict__ v, float grad_scale, float lr, float beta1, float beta2, float eps,
+                          float bc1, float bc2_sqrt, const int32_t* __restrict__ step_dev) {
+    __shared__ float s_bc[2];
+    if (step_dev) {  // step count in device memory (CUDA-graph replays): bias corrections computed here
+        if (threadIdx.x == 0) {
+            const double t = (double)*step_dev;
+            s_bc[0] = (float)(1.0 - pow((double)beta1, t));
+            s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, t));
+        }
+        __syncthreads();
+        bc1 = s_bc[0];
+        bc2_sqrt = s_bc[1];
+    }
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * grad_scale;
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;        // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct bpp_learner {
+    int W, H, N, A, Cin, max_batch, device;
+    int hs[4], ws[4], chans[3];
+    int flat;
+    ConvL conv[NCONV];
+    long long w1, b1, w2, b2, wv, bv, nparams;
+    std::vector<std::pair<std::string, std::pair<long long, long long>>> names;  // state_dict order
+    // activation tensors (device); per stage: c (input resolution), p, a0, q, a1, o (pooled resolution)
+    float* planes = nullptr;
+    float *c[3] = {}, *p[3] = {}, *a0[3] = {}, *q[3] = {}, *a1[3] = {}, *o[3] = {};
+    float *dc[3] = {}, *dp[3] = {}, *da0[3] = {}, *dq[3] = {}, *da1[3] = {}, *dout[3] = {};
+    uint8_t* amax[3] = {};
+    float* partial = nullptr;
+    float* loss_partial = nullptr;
+    int max_chunks = 0;
+    int smem_cap = 0;
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+bool dalloc(bpp_learner* l, void** p, size_t bytes) {
+    if (cudaMalloc(p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    l->allocs.push_back(*p);
+    return true;
+}
+
+void chunking(int B, int& S, int& nchunk) {
+    S = (B + NCHUNK0 - 1) / NCHUNK0;
+    if (S > SMAX) S = SMAX;
+    nchunk = (B + S - 1) / S;
+}
+
+int launch_conv(bpp_learner* l, cudaStream_t st, int B, const float* in, const float* wt, const float* bias,
+                const float* mask, const float* add, float* out, int cin, int cout, int h, int w, int relu_in,
+                int transpose) {
+    ConvArgs a;
+    a.in = in; a.wt = wt; a.bias = bias; a.mask = mask; a.add = add; a.out = out;
+    a.B = B; a.cin = cin; a.cout = cout; a.h = h; a.w = w; a.relu_in = relu_in; a.transpose = transpose;
+    const int hw = h * w, PP = (h + 2) * (w + 2);
+    int G = std::max(1, (256 * 16) / (cout * hw));
+    G = std::max(1, std::min(G, (B + 147) / 148));
+    const size_t wbytes = (size_t)cin * 9 * cout * 4;
+    while (G > 1 && wbytes + (size_t)cin * G * PP * 4 > (size_t)l->smem_cap) --G;
+    a.G = G;
+    const size_t smem = wbytes + (size_t)cin * G * PP * 4;
+    if (smem > (size_t)l->smem_cap) return lerr(BPP_E_INVALID, "convolution does not fit in shared memory");
+    k_lr_conv<<<(B + G - 1) / G, THREADS, smem, st>>>(a);
+    return BPP_OK;
+}
+
+}  // namespace
+
+extern "C" int bpp_learner_create(int W, int H, int N, int max_batch, int device, bpp_learner** out) {
+    if (!out) return lerr(BPP_E_INVALID, "null argument");
+    if (W < 1 || W > 32 || H < 1 || H > 28 || N < 1 || N > 16 || max_batch < 1)
+        return lerr(BPP_E_INVALID, "unsupported network geometry");
+    if (cudaSetDevice(device) != cudaSuccess) return lerr(BPP_E_CUDA, "cudaSetDevice failed");
+    bpp_learner* l = new bpp_learner();
+    l->W = W; l->H = H; l->N = N; l->A = W * N; l->Cin = N + 1; l->max_batch = max_batch; l->device = device;
+    l->chans[0] = 16; l->chans[1] = 32; l->chans[2] = 32;
+    l->hs[0] = H; l->ws[0] = W;
+    for (int s = 0; s < 3; ++s) {
+        l->hs[s + 1] = (l->hs[s] + 1) / 2;
+        l->ws[s + 1] = (l->ws[s] + 1) / 2;
+    }
+    l->flat = 32 * l->hs[3] * l->ws[3];
+    if (l->flat % 4) { delete l; return lerr(BPP_E_INVALID, "unsupported network geometry"); }
+    long long off = 0;
+    auto reg = [&](const std::string& name, long long numel) {
+        l->names.push_back({name, {off, numel}});
+        const long long o = off;
+        off += numel;
+        return o;
+    };
+    int cin = l->Cin;
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int ch = l->chans[s];
+        const std::string pre = "conv_seqs." + std::to_string(s) + ".";
+        const char* sub[5] = {"conv", "res_block0.conv0", "res_block0.conv1", "res_block1.conv0", "res_block1.conv1"};
+        for (int k = 0; k < 5; ++k) {
+            ConvL& L = l->conv[s * 5 + k];
+            L.cin = k == 0 ? cin : ch;
+            L.cout = ch;
+            L.h = k == 0 ? l->hs[s] : l->hs[s + 1];
+            L.w = k == 0 ? l->ws[s] : l->ws[s + 1];
+            L.w_off = reg(pre + sub[k] + ".weight", (long long)L.cout * L.cin * 9);
+            L.b_off = reg(pre + sub[k] + ".bias", L.cout);
+        }
+        cin = ch;
+    }
+    l->w1 = reg("hidden_fc.weight", (long long)HIDDEN * l->flat);
+    l->b1 = reg("hidden_fc.bias", HIDDEN);
+    l->w2 = reg("logits_fc.weight", (long long)l->A * HIDDEN);
+    l->b2 = reg("logits_fc.bias", l->A);
+    l->wv = reg("value_fc.weight", HIDDEN);
+    l->bv = reg("value_fc.bias", 1);
+    l->nparams = off;
+    // every tensor offset must keep float4 alignment for the vector loads of the FC rows
+    if ((l->w1 % 4) || (l->w2 % 4)) { delete l; return lerr(BPP_E_INVALID, "unaligned parameter layout"); }
+
+    int smem_optin = 0;
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    l->smem_cap = std::min(smem_optin, 200 * 1024);
+    if (cudaFuncSetAttribute(k_lr_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_cap) != cudaSuccess) {
+        cudaGetLastError();
+        delete l;
+        return lerr(BPP_E_CUDA, "cannot reserve shared memory for the learner kernels");
+    }
+    const size_t B = (size_t)max_batch;
+    bool ok = dalloc(l, (void**)&l->planes, B * l->Cin * H * W * 4);
+    for (int s = 0; s < 3 && ok; ++s) {
+        const size_t ch = l->chans[s], hw0 = (size_t)l->hs[s] * l->ws[s], hw1 = (size_t)l->hs[s + 1] * l->ws[s + 1];
+        ok = ok && dalloc(l, (void**)&l->c[s], B * ch * hw0 * 4) && dalloc(l, (void**)&l->dc[s], B * ch * hw0 * 4) &&
+             dalloc(l, (void**)&l->amax[s], B * ch * hw1);
+        float** t[10] = {&l->p[s], &l->a0[s], &l->q[s], &l->a1[s], &l->o[s], &l->dp[s], &l->da0[s], &l->dq[s], &l->da1[s],
+                         &l->dout[s]};
+        for (int k = 0; k < 10 && ok; ++k) ok = dalloc(l, (void**)t[k], B * ch * hw1 * 4);
+    }
+    int S, nchunk;
+    chunking(max_batch, S, nchunk);
+    l->max_chunks = std::max(nchunk, NCHUNK0);
+    ok = ok && dalloc(l, (void**)&l->partial, (size_t)l->max_chunks * l->nparams * 4) &&
+         dalloc(l, (void**)&l->loss_partial, (size_t)l->max_chunks * 2 * 4);
+    if (!ok) {
+        for (void* p : l->allocs) cudaFree(p);
+        delete l;
+        return lerr(BPP_E_NOMEM, "cudaMalloc of the learner buffers failed");
+    }
+    *out = l;
+    return BPP_OK;
+}
+
+extern "C" int bpp_learner_destroy(bpp_learner* l) {
+    if (!l) return BPP_OK;
+    cudaSetDevice(l->device);
+    for (void* p : l->allocs) cudaFree(p);
+    delete l;
+    return BPP_OK;
+}
+
+extern "C" int bpp_learner_num_params(bpp_learner* l, int64_t* out) {
+    if (!l || !out) return lerr(BPP_E_INVALID, "null argument");
+    *out = l->nparams;
+    return BPP_OK;
+}
+
+extern "C" int bpp_learner_param_offset(bpp_learner* l, const char* name, int64_t* offset, int64_t* numel) {
+    if (!l || !name || !offset || !numel) return lerr(BPP_E_INVALID, "null argument");
+    for (auto& e : l->names)
+        if (e.first == name) {
+            *offset = e.second.first;
+            *numel = e.second.second;
+            return BPP_OK;
+        }
+    return lerr(BPP_E_INVALID, std::string("unknown parameter ") + name);
+}
+
+// forward + losses (+ backward and flat gradient when grads_out_dev != NULL)
+extern "C" int bpp_learner_grad(bpp_learner* l, int B, const float* params_dev, const uint32_t* recs_dev,
+                                const int32_t* items_wh_dev, const int64_t* ids_dev, const float* pis_dev,
+                                const float* vs_dev, float* grads_out_dev, float* losses_out_dev, float* logp_out_dev,
+                                float* v_out_dev, void* stream) {
+    if (!l || !params_dev || !recs_dev || !items_wh_dev || !pis_dev || !vs_dev)
+        return lerr(BPP_E_INVALID, "null argument");
+    if (B < 1 || B > l->max_batch) return lerr(BPP_E_INVALID, "batch size out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool train = grads_out_dev != nullptr;
+    int rc;
+    {
+        const long long total = (long long)B * l->Cin * l->H * l->W;
+        k_lr_planes<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(B, l->W, l->H, l->N, recs_dev,
+                                                                                       items_wh_dev, ids_dev, l->planes);
+    }
+    // ---- forward ----
+    const float* u = l->planes;
+    for (int s = 0; s < NSTAGE; ++s) {
+        const ConvL* L = &l->conv[s * 5];
+        const int ch = l->chans[s], h1 = l->hs[s + 1], w1 = l->ws[s + 1];
+        if ((rc = launch_conv(l, st, B, u, params_dev + L[0].w_off, params_dev + L[0].b_off, nullptr, nullptr, l->c[s],
+                              L[0].cin, ch, L[0].h, L[0].w, 0, 0)))
+            return rc;
+        {
+            const long long total = (long long)B * ch * h1 * w1;
+            k_lr_pool_fwd<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(
+                B * ch, L[0].h, L[0].w, h1, w1, l->c[s], l->p[s], l->amax[s]);
+        }
+        if ((rc = launch_conv(l, st, B, l->p[s], params_dev + L[1].w_off, params_dev + L[1].b_off, nullptr, nullptr,
+                              l->a0[s], ch, ch, h1, w1, 1, 0)) ||
+            (rc = launch_conv(l, st, B, l->a0[s], params_dev + L[2].w_off, params_dev + L[2].b_off, nullptr, l->p[s],
+                              l->q[s], ch, ch, h1, w1, 1, 0)) ||
+            (rc = launch_conv(l, st, B, l->q[s], params_dev + L[3].w_off, params_dev + L[3].b_off, nullptr, nullptr,
+                              l->a1[s], ch, ch, h1, w1, 1, 0)) ||
+            (rc = launch_conv(l, st, B, l->a1[s], params_dev + L[4].w_off, params_dev + L[4].b_off, nullptr, l->q[s],
+                              l->o[s], ch, ch, h1, w1, 1, 0)))
+            return rc;
+        u = l->o[s];
+    }
+    // ---- heads: forward, losses, backward of the linear layers ----
+    int S, nchunk;
+    chunking(B, S, nchunk);
+    {
+        HeadArgs a;
+        a.B = B; a.S = S; a.flat = l->flat; a.A = l->A;
+        a.o2 = l->o[2]; a.params = params_dev;
+        a.w1 = l->w1; a.b1 = l->b1; a.w2 = l->w2; a.b2 = l->b2; a.wv = l->wv; a.bv = l->bv;
+        a.pis = pis_dev; a.vs = vs_dev; a.ids = ids_dev;
+        a.dfeat = l->dout[2];
+        a.partial = train ? l->partial : nullptr;
+        a.nparams = l->nparams;
+        a.loss_partial = l->loss_partial;
+        a.logp_out = logp_out_dev; a.v_out = v_out_dev;
+        const size_t smem = ((size_t)SMAX * l->flat + (size_t)SMAX * HIDDEN + (size_t)SMAX * (l->A + 1)) * 4;
+        if (smem > (size_t)l->smem_cap) return lerr(BPP_E_INVALID, "heads do not fit in shared memory");
+        k_lr_heads<<<nchunk, THREADS, smem, st>>>(a);
+    }
+    if (!train) {
+        k_lr_reduce<<<1, 32, 0, st>>>(0, nchunk, l->partial, nullptr, l->loss_partial, losses_out_dev);
+        return cudaGetLastError() == cudaSuccess ? BPP_OK : lerr(BPP_E_CUDA, "learner forward launch failed");
+    }
+    // ---- backward: data gradients, last stage first ----
+    for (int s = NSTAGE - 1; s >= 0; --s) {
+        const ConvL* L = &l->conv[s * 5];
+        const int ch = l->chans[s], h1 = l->hs[s + 1], w1 = l->ws[s + 1];
+        // da1 = dgrad(res1.conv1, do) * (a1 > 0)
+        if ((rc = launch_conv(l, st, B, l->dout[s], params_dev + L[4].w_off, nullptr, l->a1[s], nullptr, l->da1[s], ch, ch,
+                              h1, w1, 0, 1)) ||
+            // dq = do + dgrad(res1.conv0, da1) * (q > 0)
+            (rc = launch_conv(l, st, B, l->da1[s], params_dev + L[3].w_off, nullptr, l->q[s], l->dout[s], l->dq[s], ch, ch,
+                              h1, w1, 0, 1)) ||
+            // da0 = dgrad(res0.conv1, dq) * (a0 > 0)
+            (rc = launch_conv(l, st, B, l->dq[s], params_dev + L[2].w_off, nullptr, l->a0[s], nullptr, l->da0[s], ch, ch,
+                              h1, w1, 0, 1)) ||
+            // dp = dq + dgrad(res0.conv0, da0) * (p > 0)
+            (rc = launch_conv(l, st, B, l->da0[s], params_dev + L[1].w_off, nullptr, l->p[s], l->dq[s], l->dp[s], ch, ch,
+                              h1, w1, 0, 1)))
+            return rc;
+        {
+            const long long total = (long long)B * ch * L[0].h * L[0].w;
+            k_lr_pool_bwd<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(
+                B * ch, L[0].h, L[0].w, h1, w1, l->dp[s], l->amax[s], l->dc[s]);
+        }
+        if (s > 0) {  // gradient w.r.t. the previous stage's output (no activation in between)
+            if ((rc = launch_conv(l, st, B, l->dc[s], params_dev + L[0].w_off, nullptr, nullptr, nullptr, l->dout[s - 1],
+                                  ch, L[0].cin, L[0].h, L[0].w, 0, 1)))
+                return rc;
+        }
+    }
+    // ---- weight gradients of all convolutions, then the ordered reduction over chunks ----
+    {
+        WgradArgs a;
+        a.B = B; a.S = S; a.partial = l->partial; a.nparams = l->nparams;
+        size_t smem_max = 0;
+        for (int s = 0; s < NSTAGE; ++s) {
+            const float* ins[5] = {s == 0 ? l->planes : l->o[s - 1], l->p[s], l->a0[s], l->q[s], l->a1[s]};
+            const float* dys[5] = {l->dc[s], l->da0[s], l->dq[s], l->da1[s], l->dout[s]};
+            for (int k = 0; k < 5; ++k) {
+                const ConvL& C = l->conv[s * 5 + k];
+                WgradLayer& Lw = a.L[s * 5 + k];
+                Lw.in = ins[k]; Lw.dy = dys[k];
+                Lw.cin = C.cin; Lw.cout = C.cout; Lw.h = C.h; Lw.w = C.w; Lw.relu_in = k != 0;
+                Lw.w_off = C.w_off; Lw.b_off = C.b_off;
+                const int pairs = C.cin * (C.cout / 4);
+                if (pairs > THREADS) return lerr(BPP_E_INVALID, "unsupported channel counts");
+                const int PPs = ((C.h + 2) * (C.w + 2)) | 1;
+                const size_t per = ((size_t)C.cin * PPs + (size_t)C.h * C.w * C.cout) * 4 + 16;
+                int pg = std::max(1, std::min(THREADS / pairs, S));
+                while (pg > 1 && per * pg > (size_t)l->smem_cap) --pg;
+                Lw.pg = pg;
+                const size_t need = std::max(per * pg, (size_t)pg * pairs * 40 * 4);
+                if (need > (size_t)l->smem_cap) return lerr(BPP_E_INVALID, "weight gradient does not fit in shared memory");
+                smem_max = std::max(smem_max, need);
+            }
+        }
+        k_lr_wgrad<<<dim3(nchunk, NCONV), THREADS, smem_max, st>>>(a);
+    }
+    k_lr_reduce<<<(int)((l->nparams + 255) / 256), 256, 0, st>>>(l->nparams, nchunk, l->partial, grads_out_dev,
+                                                               l->loss_partial, losses_out_dev);
+    return cudaGetLastError() == cudaSuccess ? BPP_OK : lerr(BPP_E_CUDA, "learner step launch failed");
+}
+
+extern "C" int bpp_learner_adam(int64_t n, float* params_dev, const float* grads_dev, float* exp_avg_dev,
+                                float* exp_avg_sq_dev, int step, const int32_t* step_dev, float grad_scale, float lr,
+                                float beta1, float beta2, float eps, void* stream) {
+    if (!params_dev || !grads_dev || !exp_avg_dev || !exp_avg_sq_dev || n < 0 || (step < 1 && !step_dev))
+        return lerr(BPP_E_INVALID, "invalid argument");
+    if (n == 0) return BPP_OK;
+    const float bc1 = (float)(1.0 - std::pow((double)beta1, std::max(step, 1)));
+    const float bc2s = (float)std::sqrt(1.0 - std::pow((double)beta2, std::max(step, 1)));
+    k_lr_adam<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, params_dev, grads_dev, exp_avg_dev,
+                                                                       exp_avg_sq_dev, grad_scale, lr, beta1, beta2, eps,
+                                                                       bc1, bc2s, step_dev);
+    return cudaGetLastError() == cudaSuccess ? BPP_OK : lerr(BPP_E_CUDA, "adam launch failed");
+}

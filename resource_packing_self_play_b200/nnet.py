@@ -133,6 +133,92 @@ class DeviceNet:
         return policy_out, value_out
 
 
+PARAM_ORDER = tuple(
+    ["conv_seqs.%d.%s.%s" % (s, sub, wb) for s in range(3)
+     for sub in ("conv", "res_block0.conv0", "res_block0.conv1", "res_block1.conv0", "res_block1.conv1")
+     for wb in ("weight", "bias")] +
+    ["hidden_fc.weight", "hidden_fc.bias", "logits_fc.weight", "logits_fc.bias", "value_fc.weight", "value_fc.bias"])
+
+
+class DeviceLearner:
+    """fp32 learner step in hand-written CUDA (csrc/bpp_learner.cu, bpp_learner_* in include/bpp_b200.h): forward with
+    stashed activations, the two losses of NNet.py:87-91, the full backward and Adam (NNet.py:31) on flat device
+    buffers in state_dict order.  Deterministic (fixed-order gradient reduction, no atomics)."""
+
+    def __init__(self, W, H, N, max_batch, device=None):
+        _lib.load()
+        device = _devidx(device)
+        self.device = torch.device("cuda", device)
+        self.W, self.H, self.N, self.A, self.max_batch = W, H, N, W * N, int(max_batch)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            call("bpp_learner_create", W, H, N, int(max_batch), int(device), C.byref(h))
+        self._h = h
+        n = C.c_int64()
+        call("bpp_learner_num_params", self._h, C.byref(n))
+        self.num_params = int(n.value)
+        self.slices = {}
+        for name in PARAM_ORDER:
+            off, numel = C.c_int64(), C.c_int64()
+            call("bpp_learner_param_offset", self._h, name.encode(), C.byref(off), C.byref(numel))
+            self.slices[name] = (int(off.value), int(numel.value))
+        self.params = torch.zeros(self.num_params, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.losses = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.reset_optimizer()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            call("bpp_learner_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset_optimizer(self):
+        """a fresh torch.optim.Adam (the reference re-creates the optimiser in every train() call, NNet.py:31)"""
+        self.exp_avg = torch.zeros(self.num_params, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros_like(self.exp_avg)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def load_state_dict(self, state_dict):
+        for name in PARAM_ORDER:
+            off, numel = self.slices[name]
+            t = state_dict[name].detach().to(self.device, torch.float32).reshape(-1)
+            if t.numel() != numel:
+                raise ValueError("parameter %s has %d elements, expected %d" % (name, t.numel(), numel))
+            self.params[off:off + numel].copy_(t)
+
+    def state_dict_into(self, module):
+        """write the flat parameters back into a torch module with the reference's parameter names"""
+        sd = module.state_dict()
+        with torch.no_grad():
+            for name in PARAM_ORDER:
+                off, numel = self.slices[name]
+                sd[name].copy_(self.params[off:off + numel].view_as(sd[name]))
+
+    def grad_dict(self):
+        return {name: self.grads[off:off + numel] for name, (off, numel) in self.slices.items()}
+
+    def grad(self, recs, items_wh, pis, vs, ids=None, batch=None, train=True, logp_out=None, v_out=None):
+        """losses (and gradients into self.grads when train) of one minibatch; example b = row ids[b] of the tables"""
+        B = int(batch if batch is not None else (ids.shape[0] if ids is not None else recs.shape[0]))
+        call("bpp_learner_grad", self._h, B, _ptr(self.params), _ptr(recs), _ptr(items_wh), _ptr(ids), _ptr(pis),
+             _ptr(vs), _ptr(self.grads) if train else C.c_void_p(0), _ptr(self.losses), _ptr(logp_out), _ptr(v_out),
+             _stream())
+        return self.losses
+
+    def adam(self, grad_scale=1.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        """one Adam update from self.grads; the step counter lives on the device (graph-capturable)"""
+        self.step_dev += 1
+        call("bpp_learner_adam", self.num_params, _ptr(self.params), _ptr(self.grads), _ptr(self.exp_avg),
+             _ptr(self.exp_avg_sq), 0, _ptr(self.step_dev), float(grad_scale), float(lr), float(betas[0]),
+             float(betas[1]), float(eps), _stream())
+
+
 class NNetWrapper:
     """Same surface as NNet.py:17-111: predict / train / save_checkpoint / load_checkpoint."""
 
