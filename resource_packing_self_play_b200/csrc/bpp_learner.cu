@@ -30,15 +30,23 @@ constexpr int REC_WORDS = 32, REC_REM = 28;
 constexpr int HIDDEN = 256;
 constexpr int NSTAGE = 3, NCONV = 15;
 constexpr int SMAX = 16;      // samples per gradient chunk (register arrays in the heads kernel)
-constexpr int NCHUNK0 = 32;   // chunks for batches up to NCHUNK0 * SMAX
 constexpr int THREADS = 256;
 
 int lerr(int code, const std::string& m) { return bpp_set_error_message(code, m.c_str()); }
 
+// asynchronous global -> shared copies (LDGSTS): the staging loops issue them back to back instead of paying one
+// L2 round trip per loop iteration
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src));
+}
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct ConvL {
     int cin, cout, h, w;
     long long w_off, b_off;     // offsets into the flat parameter vector
-    long long in_off, out_off;  // per-sample-scaled offsets are resolved on the host into pointers at launch
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -67,88 +75,187 @@ __global__ void k_lr_planes(int B, int W, int H, int N, const uint32_t* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// 3x3 / pad 1 convolution over [B][cin][h*w] -> [B][cout][h*w] (cout a multiple of 16), used for the forward and, with
-// `transpose`, for the data gradient (weights read as W[k][o] rotated by 180 degrees).
-//   out = (mask ? (mask > 0) : 1) * (bias + conv(relu_in ? relu(in) : in)) + (add ? add : 0)
-// One CTA = G samples; one work item = one output position x 16 output channels.
-struct ConvArgs {
-    const float* in;
-    const float* wt;    // [cout][cin][9] (forward) or [cin][cout][9] read transposed + flipped (dgrad)
-    const float* bias;  // nullable
-    const float* mask;  // nullable, [B][cout][hw]
-    const float* add;   // nullable, [B][cout][hw]
-    float* out;
-    int B, cin, cout, h, w, G, relu_in, transpose;
+// conv weights re-laid out once per step for coalesced staging: fwd[k = ci*9 + tap][co] = W[co][ci][tap] and, for the
+// data gradient, bwd[k = co*9 + tap][ci] = W[co][ci][8 - tap] (transposed, rotated by 180 degrees); both at w_off.
+struct RelayoutArgs {
+    long long w_off[NCONV];
+    int cin[NCONV], cout[NCONV];
 };
-
-__global__ void __launch_bounds__(THREADS) k_lr_conv(ConvArgs a) {
-    extern __shared__ __align__(16) float sm[];
-    const int hw = a.h * a.w, wp = a.w + 2, PP = (a.h + 2) * wp;
-    float* s_w = sm;                               // [cin*9][cout]
-    float* s_in = sm + a.cin * 9 * a.cout;         // [cin][G][PP]
-    const int tid = threadIdx.x, b0 = blockIdx.x * a.G;
-    const int nk = a.cin * 9;
-    for (int idx = tid; idx < nk * a.cout; idx += THREADS) {
-        const int k = idx / a.cout, co = idx - k * a.cout;
-        const int ci = k / 9, tap = k - ci * 9;
-        s_w[idx] = a.transpose ? a.wt[((size_t)ci * a.cout + co) * 9 + (8 - tap)] : a.wt[((size_t)co * a.cin + ci) * 9 + tap];
-    }
-    for (int idx = tid; idx < a.cin * a.G * PP; idx += THREADS) s_in[idx] = 0.f;
-    __syncthreads();
-    const int per = a.cin * hw;
-    for (int idx = tid; idx < a.G * per; idx += THREADS) {
-        const int g = idx / per;
-        int r = idx - g * per;
-        const int ci = r / hw;
-        r -= ci * hw;
-        const int y = r / a.w, x = r - y * a.w;
-        if (b0 + g < a.B) {
-            float v = a.in[(size_t)(b0 + g) * per + ci * hw + r];
-            if (a.relu_in) v = fmaxf(v, 0.f);
-            s_in[(ci * a.G + g) * PP + (y + 1) * wp + x + 1] = v;
+__global__ void k_lr_relayout(RelayoutArgs a, const float* __restrict__ params, float* __restrict__ fwd,
+                              float* __restrict__ bwd) {
+    const int l = blockIdx.y, cin = a.cin[l], cout = a.cout[l], n = cin * cout * 9;
+    const float* w = params + a.w_off[l];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        {   // forward layout: idx = (ci*9 + tap)*cout + co
+            const int k = idx / cout, co = idx - k * cout, ci = k / 9, tap = k - ci * 9;
+            fwd[a.w_off[l] + idx] = w[((size_t)co * cin + ci) * 9 + tap];
+        }
+        {   // dgrad layout: idx = (co*9 + tap)*cin + ci
+            const int k = idx / cin, ci = idx - k * cin, co = k / 9, tap = k - co * 9;
+            bwd[a.w_off[l] + idx] = w[((size_t)co * cin + ci) * 9 + (8 - tap)];
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 / pad 1 convolution over [B][cin][h*w] -> [B][cout][h*w] (cout a multiple of 8), used for the forward and, with
+// the transposed + rotated weights, for the data gradient.
+//   out = (mask ? (mask > 0) : 1) * (bias + conv(relu_in ? relu(in) : in)) + (add ? add : 0)
+// One CTA = G samples staged with zero halos in shared memory; one work item = a row segment of TP output positions x 8
+// output channels: per (input channel, kernel row) TP + 2 inputs and 3 x 8 weights feed 24 * TP FMAs, which keeps the
+// shared-memory pipe (128 B/clk) below the FMA pipe.
+struct ConvArgs {
+    const float* __restrict__ in;
+    const float* __restrict__ wt;    // [cin*9][cout] (k_lr_relayout)
+    const float* __restrict__ bias;  // nullable
+    const float* __restrict__ mask;  // nullable, [B][cout][hw]
+    const float* __restrict__ add;   // nullable, [B][cout][hw]
+    float* __restrict__ out;
+    int B, cin, cout, h, w, G, relu_in;
+    int wp;             // padded row stride in shared memory (odd: rows of one column fall into distinct banks)
+    int KS;             // input-channel split: KS threads share one work item (small layers: latency, not FMAs, bounds them)
+};
+
+// acc[j][k] += sum over ci in [ci0, ci1), 3x3 taps: in(position k + tap) * w[ci][tap][channel j]
+template <int TP>
+__device__ __forceinline__ void conv_tile(float (&acc)[8][TP], const float* sp, const float* wp0, int ci0, int ci1,
+                                          int cstride, int wp, int cout, float lo) {
+    for (int ci = ci0; ci < ci1; ++ci) {
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty) {
+            float in[TP + 2];
+#pragma unroll
+            for (int k = 0; k < TP + 2; ++k) in[k] = fmaxf(sp[ci * cstride + ty * wp + k], lo);  // lo = 0: relu(in)
+#pragma unroll
+            for (int tx = 0; tx < 3; ++tx) {
+                const float4* wv = reinterpret_cast<const float4*>(wp0 + (size_t)(ci * 9 + ty * 3 + tx) * cout);
+                const float4 w0 = wv[0], w1 = wv[1];
+                const float wj[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int k = 0; k < TP; ++k) acc[j][k] = fmaf(in[k + tx], wj[j], acc[j][k]);
+            }
+        }
+    }
+}
+
+template <int TP>
+__global__ void __launch_bounds__(THREADS, 2) k_lr_conv(ConvArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int hw = a.h * a.w, wp = a.wp, PP = (a.h + 2) * wp;
+    float* s_w = sm;                                            // [cin*9][cout]
+    float* s_in = sm + a.cin * 9 * a.cout;                      // [cin][G][PP] + 8 floats of slack (segment over-read)
+    float* s_part = s_in + ((a.cin * a.G * PP + 8 + 3) & ~3);   // [8*TP][KS*items] (KS > 1 only)
+    const int tid = threadIdx.x, b0 = blockIdx.x * a.G;
+    {
+        const int n4 = a.cin * 9 * a.cout / 4;
+        for (int idx = tid; idx < n4; idx += THREADS) cp_async16(s_w + 4 * idx, a.wt + 4 * idx);
+    }
+    for (int idx = tid; idx < a.cin * a.G * PP + 8; idx += THREADS) s_in[idx] = 0.f;
     __syncthreads();
-    const int npos = a.G * hw, items = npos * (a.cout >> 4);
+    const int per = a.cin * hw;
+    {   // one (sample, channel) plane per warp and pass; y = pos / w by multiply-shift (exact for pos < 1024, w <= 32)
+        const int lane = tid & 31, warp = tid >> 5;
+        const unsigned magic = (65536u + a.w - 1) / a.w;
+        const int gmax = min(a.G, a.B - b0);
+        for (int pl = warp; pl < gmax * a.cin; pl += THREADS / 32) {
+            const int g = pl / a.cin, ci = pl - g * a.cin;
+            const float* src = a.in + (size_t)(b0 + g) * per + ci * hw;
+            float* dst = s_in + (ci * a.G + g) * PP + wp + 1;
+            for (int pos = lane; pos < hw; pos += 32) {
+                const int y = (int)(((unsigned)pos * magic) >> 16);
+                cp_async4(dst + pos + y * (wp - a.w), src + pos);
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const float lo = a.relu_in ? 0.f : -INFINITY;
+    const int nseg = (a.w + TP - 1) / TP;
+    const int rows = a.G * a.h * nseg, items = rows * (a.cout >> 3);
     const int cstride = a.G * PP;
-    for (int item = tid; item < items; item += THREADS) {
-        const int cb = item / npos, p = item - cb * npos;
-        const int g = p / hw, pos = p - g * hw;
-        const int b = b0 + g;
-        if (b >= a.B) continue;
-        const int y = pos / a.w, x = pos - y * a.w;
-        float acc[16];
+    if (a.KS == 1) {
+        for (int item = tid; item < items; item += THREADS) {
+            const int cb = item / rows;
+            int r = item - cb * rows;
+            const int g = r / (a.h * nseg);
+            r -= g * a.h * nseg;
+            const int y = r / nseg, x0 = (r - y * nseg) * TP;
+            const int b = b0 + g;
+            if (b >= a.B) continue;
+            float acc[8][TP];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = a.bias ? a.bias[cb * 16 + j] : 0.f;
-        const float* sp = s_in + g * PP + y * wp + x;  // top-left of the 3x3 window in the padded plane
-        const float* wp0 = s_w + cb * 16;
-        for (int ci = 0; ci < a.cin; ++ci) {
+            for (int j = 0; j < 8; ++j) {
+                const float bj = a.bias ? __ldg(a.bias + cb * 8 + j) : 0.f;
 #pragma unroll
-            for (int ty = 0; ty < 3; ++ty) {
+                for (int k = 0; k < TP; ++k) acc[j][k] = bj;
+            }
+            conv_tile<TP>(acc, s_in + g * PP + y * wp + x0, s_w + cb * 8, 0, a.cin, cstride, wp, a.cout, lo);
 #pragma unroll
-                for (int tx = 0; tx < 3; ++tx) {
-                    const float v = sp[ci * cstride + ty * wp + tx];
-                    const float4* wv = reinterpret_cast<const float4*>(wp0 + (size_t)(ci * 9 + ty * 3 + tx) * a.cout);
+            for (int j0 = 0; j0 < 8; j0 += 2) {  // per channel pair: all loads of the epilogue first, then the stores
+                float mk[2][TP], ad[2][TP];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 w4 = wv[q];
-                        acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
-                        acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+                for (int j = 0; j < 2; ++j) {
+                    const size_t o0 = ((size_t)b * a.cout + cb * 8 + j0 + j) * hw + y * a.w + x0;
+#pragma unroll
+                    for (int k = 0; k < TP; ++k) {
+                        const bool in_row = x0 + k < a.w;
+                        mk[j][k] = (a.mask && in_row) ? a.mask[o0 + k] : 1.f;
+                        ad[j][k] = (a.add && in_row) ? a.add[o0 + k] : 0.f;
                     }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const size_t o0 = ((size_t)b * a.cout + cb * 8 + j0 + j) * hw + y * a.w + x0;
+#pragma unroll
+                    for (int k = 0; k < TP; ++k)
+                        if (x0 + k < a.w) a.out[o0 + k] = (mk[j][k] > 0.f ? acc[j0 + j][k] : 0.f) + ad[j][k];
                 }
             }
         }
-        const size_t o0 = ((size_t)b * a.cout + cb * 16) * hw + pos;
+        return;
+    }
+    // split over the input channels: thread = (work item, channel slice); partial sums meet in shared memory
+    const int slots = items * a.KS;
+    if (tid < slots) {
+        const int item = tid % items, ks = tid / items;
+        const int cb = item / rows;
+        int r = item - cb * rows;
+        const int g = r / (a.h * nseg);
+        r -= g * a.h * nseg;
+        const int y = r / nseg, x0 = (r - y * nseg) * TP;
+        const int cpk = (a.cin + a.KS - 1) / a.KS;
+        float acc[8][TP];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const size_t o = o0 + (size_t)j * hw;
-            float r = acc[j];
-            if (a.mask) r = a.mask[o] > 0.f ? r : 0.f;
-            if (a.add) r += a.add[o];
-            a.out[o] = r;
-        }
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < TP; ++k) acc[j][k] = 0.f;
+        conv_tile<TP>(acc, s_in + g * PP + y * wp + x0, s_w + cb * 8, ks * cpk, min(a.cin, (ks + 1) * cpk), cstride, wp,
+                      a.cout, lo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < TP; ++k) s_part[(j * TP + k) * slots + tid] = acc[j][k];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int oidx = tid; oidx < items * 8 * TP; oidx += THREADS) {
+        const int jk = oidx / items, item = oidx - jk * items;
+        const int j = jk / TP, k = jk - j * TP;
+        const int cb = item / rows;
+        int r = item - cb * rows;
+        const int g = r / (a.h * nseg);
+        r -= g * a.h * nseg;
+        const int y = r / nseg, x = (r - y * nseg) * TP + k;
+        const int b = b0 + g;
+        if (b >= a.B || x >= a.w) continue;
+        float v = a.bias ? __ldg(a.bias + cb * 8 + j) : 0.f;
+        for (int ks = 0; ks < a.KS; ++ks) v += s_part[jk * slots + ks * items + item];
+        const size_t o = ((size_t)b * a.cout + cb * 8 + j) * hw + y * a.w + x;
+        if (a.mask) v = a.mask[o] > 0.f ? v : 0.f;
+        if (a.add) v += a.add[o];
+        a.out[o] = v;
     }
 }
 
@@ -220,18 +327,19 @@ struct HeadArgs {
     const float* vs;       // [*]    target values
     const int64_t* ids;    // nullable gather index into pis / vs
     float* dfeat;          // [B][flat] gradient w.r.t. o2
-    float* partial;        // [chunk][nparams]
-    long long nparams;
+    float* partial;        // [chunk][nparams rounded up to 4]
+    long long nparams;     // row stride of `partial`
     float* loss_partial;   // [chunk][2]
     float* logp_out;       // nullable [B][A]: log-softmax output (evaluation)
     float* v_out;          // nullable [B]
 };
 
+template <int SM>  // SM = samples per chunk rounded up to a power of two (register arrays)
 __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
     extern __shared__ __align__(16) float sm[];
     float* s_f = sm;                        // [S][flat]   relu(features)
-    float* s_h = s_f + SMAX * a.flat;       // [S][256]    hidden activations, later their gradients
-    float* s_l = s_h + SMAX * HIDDEN;       // [S][A + 1]  logits -> dlogits; column A = dv (pre-tanh gradient)
+    float* s_h = s_f + SM * a.flat;       // [S][256]    hidden activations, later their gradients
+    float* s_l = s_h + SM * HIDDEN;       // [S][A + 1]  logits -> dlogits; column A = dv (pre-tanh gradient)
     __shared__ float s_loss[2][THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * a.S;
@@ -243,24 +351,24 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
     const float* WV = a.params + a.wv;
     float* part = a.partial + (size_t)blockIdx.x * a.nparams;
 
-    for (int idx = tid; idx < SMAX * a.flat; idx += THREADS) {
+    for (int idx = tid; idx < SM * a.flat; idx += THREADS) {
         const int s = idx / a.flat, i = idx - s * a.flat;
         s_f[idx] = s < S ? fmaxf(a.o2[(size_t)(b0 + s) * a.flat + i], 0.f) : 0.f;
     }
     __syncthreads();
     // hidden = relu(W1 f + b1): thread = hidden unit
-    float hreg[SMAX];
+    float hreg[SM];
     {
         const int o = tid;
-        float acc[SMAX];
+        float acc[SM];
         const float bias = a.params[a.b1 + o];
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) acc[s] = bias;
+        for (int s = 0; s < SM; ++s) acc[s] = bias;
         const float4* wrow = reinterpret_cast<const float4*>(W1 + (size_t)o * a.flat);
         for (int i4 = 0; i4 < a.flat / 4; ++i4) {
             const float4 w4 = __ldg(wrow + i4);
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s) {
+            for (int s = 0; s < SM; ++s) {
                 const float4 f4 = *reinterpret_cast<const float4*>(s_f + s * a.flat + 4 * i4);
                 acc[s] = fmaf(w4.x, f4.x, acc[s]);
                 acc[s] = fmaf(w4.y, f4.y, acc[s]);
@@ -269,7 +377,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
             }
         }
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) {
+        for (int s = 0; s < SM; ++s) {
             hreg[s] = fmaxf(acc[s], 0.f);
             s_h[s * HIDDEN + o] = hreg[s];
         }
@@ -277,17 +385,17 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
     __syncthreads();
     // logits (threads j < A) and the value pre-activation (j == A)
     for (int j = tid; j <= a.A; j += THREADS) {
-        float acc[SMAX];
+        float acc[SM];
         const float bias = a.params[(j < a.A ? a.b2 : a.bv) + (j < a.A ? j : 0)];
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) acc[s] = bias;
+        for (int s = 0; s < SM; ++s) acc[s] = bias;
         const float* wrow = j < a.A ? W2 + (size_t)j * HIDDEN : WV;  // WV may not be 16-byte aligned (A odd multiples)
         for (int o4 = 0; o4 < HIDDEN / 4; ++o4) {
             const float4 w4 = j < a.A ? __ldg(reinterpret_cast<const float4*>(wrow) + o4)
                                       : make_float4(__ldg(wrow + 4 * o4), __ldg(wrow + 4 * o4 + 1), __ldg(wrow + 4 * o4 + 2),
                                                     __ldg(wrow + 4 * o4 + 3));
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s) {
+            for (int s = 0; s < SM; ++s) {
                 const float4 h4 = *reinterpret_cast<const float4*>(s_h + s * HIDDEN + 4 * o4);
                 acc[s] = fmaf(w4.x, h4.x, acc[s]);
                 acc[s] = fmaf(w4.y, h4.y, acc[s]);
@@ -296,7 +404,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
             }
         }
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) s_l[s * A1 + j] = acc[s];
+        for (int s = 0; s < SM; ++s) s_l[s * A1 + j] = acc[s];
     }
     __syncthreads();
     // per sample: log-softmax, losses, gradient of the logits and of the value pre-activation (one warp per sample)
@@ -338,7 +446,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
         s_loss[0][warp] = lpi;
         s_loss[1][warp] = lv;
     }
-    for (int idx = tid; idx < (SMAX - S) * A1; idx += THREADS) s_l[S * A1 + idx] = 0.f;  // rows of absent samples
+    for (int idx = tid; idx < (SM - S) * A1; idx += THREADS) s_l[S * A1 + idx] = 0.f;  // rows of absent samples
     __syncthreads();
     if (tid < 2) {
         float t = 0.f;
@@ -352,30 +460,30 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
         for (int j = 0; j <= a.A; ++j) {
             float g = 0.f;
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s) g = fmaf(s_l[s * A1 + j], hreg[s], g);
+            for (int s = 0; s < SM; ++s) g = fmaf(s_l[s * A1 + j], hreg[s], g);
             part[(j < a.A ? a.w2 + (long long)j * HIDDEN : a.wv) + o] = g;
         }
     }
     for (int j = tid; j <= a.A; j += THREADS) {
         float g = 0.f;
-        for (int s = 0; s < SMAX; ++s) g += s_l[s * A1 + j];
+        for (int s = 0; s < SM; ++s) g += s_l[s * A1 + j];
         part[j < a.A ? a.b2 + j : a.bv] = g;
     }
     // gradient of the hidden activations: dh[s][o] = (sum_j dl[s][j] W2[j][o] + dv[s] wv[o]) * (h > 0)
-    float dh[SMAX];
+    float dh[SM];
     {
         const int o = tid;
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) dh[s] = 0.f;
+        for (int s = 0; s < SM; ++s) dh[s] = 0.f;
         for (int j = 0; j <= a.A; ++j) {
             const float w = j < a.A ? __ldg(W2 + (size_t)j * HIDDEN + o) : __ldg(WV + o);
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s) dh[s] = fmaf(s_l[s * A1 + j], w, dh[s]);
+            for (int s = 0; s < SM; ++s) dh[s] = fmaf(s_l[s * A1 + j], w, dh[s]);
         }
         float gb = 0.f;
         __syncthreads();  // every thread is done reading s_h through hreg's producers; s_h is reused for dh
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) {
+        for (int s = 0; s < SM; ++s) {
             dh[s] = hreg[s] > 0.f ? dh[s] : 0.f;
             s_h[s * HIDDEN + o] = dh[s];
             gb += dh[s];
@@ -388,18 +496,18 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
         const int o = idx / a.flat, i = idx - o * a.flat;
         float g = 0.f;
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) g = fmaf(s_h[s * HIDDEN + o], s_f[s * a.flat + i], g);
+        for (int s = 0; s < SM; ++s) g = fmaf(s_h[s * HIDDEN + o], s_f[s * a.flat + i], g);
         part[a.w1 + idx] = g;
     }
     // gradient w.r.t. the last stage output: (W1^T dh) * (o2 > 0)
     for (int i = tid; i < a.flat; i += THREADS) {
-        float acc[SMAX];
+        float acc[SM];
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) acc[s] = 0.f;
+        for (int s = 0; s < SM; ++s) acc[s] = 0.f;
         for (int o = 0; o < HIDDEN; ++o) {
             const float w = __ldg(W1 + (size_t)o * a.flat + i);
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s) acc[s] = fmaf(s_h[s * HIDDEN + o], w, acc[s]);
+            for (int s = 0; s < SM; ++s) acc[s] = fmaf(s_h[s * HIDDEN + o], w, acc[s]);
         }
         for (int s = 0; s < S; ++s) a.dfeat[(size_t)(b0 + s) * a.flat + i] = s_f[s * a.flat + i] > 0.f ? acc[s] : 0.f;
     }
@@ -412,7 +520,9 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
 struct WgradLayer {
     const float* in;
     const float* dy;
-    int cin, cout, h, w, relu_in, pg;  // pg = sample subgroups staged at once
+    int cin, cout, h, w, relu_in;
+    int pg;      // sample subgroups working in parallel (threads = pairs * pg)
+    int round;   // samples staged in shared memory at once
     long long w_off, b_off;
 };
 struct WgradArgs {
@@ -422,20 +532,38 @@ struct WgradArgs {
     long long nparams;
 };
 
+#define WG_FMA(L0, L1, L2, M0, M1, M2, R0, R1, R2, D)                        \
+    {                                                                        \
+        const float win[9] = {L0, M0, R0, L1, M1, R1, L2, M2, R2};           \
+        const float4 d4 = (D);                                               \
+        _Pragma("unroll") for (int t = 0; t < 9; ++t) {                      \
+            acc[0][t] = fmaf(d4.x, win[t], acc[0][t]);                       \
+            acc[1][t] = fmaf(d4.y, win[t], acc[1][t]);                       \
+            acc[2][t] = fmaf(d4.z, win[t], acc[2][t]);                       \
+            acc[3][t] = fmaf(d4.w, win[t], acc[3][t]);                       \
+        }                                                                    \
+        accb[0] += d4.x;                                                     \
+        accb[1] += d4.y;                                                     \
+        accb[2] += d4.z;                                                     \
+        accb[3] += d4.w;                                                     \
+    }
+
 __global__ void __launch_bounds__(THREADS) k_lr_wgrad(WgradArgs a) {
     extern __shared__ __align__(16) float sm[];
     const WgradLayer& L = a.L[blockIdx.y];
     const int cin = L.cin, cout = L.cout, h = L.h, w = L.w, hw = h * w, wp = w + 2;
     const int PPs = ((h + 2) * wp) | 1;  // odd plane stride: lanes (consecutive ci) hit distinct banks
-    const int pairs = cin * (cout >> 2), PG = L.pg;
-    float* s_x = sm;                       // [PG][cin][PPs]
-    float* s_dy = sm + ((PG * cin * PPs + 3) & ~3);  // [PG][hw][cout]
+    const int cq4 = cout >> 2;
+    const int pairs = cin * cq4, PG = L.pg, R = L.round;
+    float* s_x = sm;                                 // [R][cin][PPs]   inputs with zero halo
+    float* s_dy = sm + ((R * cin * PPs + 3) & ~3);   // [R][cout/4][hw][4]  output gradients, channel quads innermost
     const int tid = threadIdx.x;
     const int pair = tid % pairs, sg = tid / pairs;
     const int ci = pair % cin, cq = pair / cin;
     const bool active = sg < PG;
     const int b0 = blockIdx.x * a.S;
     const int S = min(a.S, a.B - b0);
+    const float lo = L.relu_in ? 0.f : -INFINITY;
     float acc[4][9];
     float accb[4];
 #pragma unroll
@@ -444,61 +572,64 @@ __global__ void __launch_bounds__(THREADS) k_lr_wgrad(WgradArgs a) {
 #pragma unroll
         for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
     }
-    for (int idx = tid; idx < PG * cin * PPs; idx += THREADS) s_x[idx] = 0.f;  // halos stay zero
-    for (int j0 = 0; j0 < S; j0 += PG) {
+    for (int idx = tid; idx < R * cin * PPs; idx += THREADS) s_x[idx] = 0.f;  // halos stay zero
+    for (int j0 = 0; j0 < S; j0 += R) {
         __syncthreads();
-        const int ns = min(PG, S - j0);
-        const int perx = cin * hw;
-        for (int idx = tid; idx < ns * perx; idx += THREADS) {
-            const int g = idx / perx;
-            int r = idx - g * perx;
-            const int c = r / hw;
-            r -= c * hw;
-            const int y = r / w, x = r - y * w;
-            float v = L.in[(size_t)(b0 + j0 + g) * perx + c * hw + r];
-            if (L.relu_in) v = fmaxf(v, 0.f);
-            s_x[(g * cin + c) * PPs + (y + 1) * wp + x + 1] = v;
+        const int ns = min(R, S - j0);
+        const int perx = cin * hw, pery = cout * hw;
+        const int lane = tid & 31, warp = tid >> 5;
+        const unsigned magic = (65536u + w - 1) / w;
+        for (int pl = warp; pl < ns * cin; pl += THREADS / 32) {  // one input plane per warp and pass
+            const int g = pl / cin, c = pl - g * cin;
+            const float* src = L.in + (size_t)(b0 + j0 + g) * perx + c * hw;
+            float* dst = s_x + (g * cin + c) * PPs + wp + 1;
+            for (int pos = lane; pos < hw; pos += 32) {
+                const int y = (int)(((unsigned)pos * magic) >> 16);
+                cp_async4(dst + pos + 2 * y, src + pos);
+            }
         }
-        const int pery = cout * hw;
-        for (int idx = tid; idx < ns * pery; idx += THREADS) {
-            const int g = idx / pery;
-            int r = idx - g * pery;
-            const int c = r / hw;
-            r -= c * hw;
-            s_dy[(g * hw + r) * cout + c] = L.dy[(size_t)(b0 + j0 + g) * pery + c * hw + r];
+        for (int gq = warp; gq < ns * cq4; gq += THREADS / 32) {  // one (sample, channel quad) per warp and pass
+            const int g = gq / cq4, q = gq - g * cq4;
+            const float* src = L.dy + (size_t)(b0 + j0 + g) * pery + (size_t)q * 4 * hw;
+            float* dst = s_dy + (size_t)gq * hw * 4;
+            for (int r = lane; r < ((hw + 7) >> 3) * 32; r += 32) {  // r = (8-position group, channel in quad, position)
+                const int grp = r >> 5, pos = (grp << 3) + (r & 7), ce = (r >> 3) & 3;  // 4 runs of 8 floats per warp load
+                if (pos < hw) cp_async4(dst + pos * 4 + ce, src + ce * hw + pos);
+            }
         }
+        cp_async_wait_all();
         __syncthreads();
-        if (active && sg < ns) {
-            const float* xp = s_x + (sg * cin + ci) * PPs;
-            const float* dp = s_dy + (size_t)sg * hw * cout + cq * 4;
-            for (int y = 0; y < h; ++y) {
-                for (int x = 0; x < w; ++x) {
-                    const float4 d4 = *reinterpret_cast<const float4*>(dp + (y * w + x) * cout);
-                    const float* q = xp + y * wp + x;
-#pragma unroll
-                    for (int ty = 0; ty < 3; ++ty) {
-#pragma unroll
-                        for (int tx = 0; tx < 3; ++tx) {
-                            const float v = q[ty * wp + tx];
-                            acc[0][ty * 3 + tx] = fmaf(d4.x, v, acc[0][ty * 3 + tx]);
-                            acc[1][ty * 3 + tx] = fmaf(d4.y, v, acc[1][ty * 3 + tx]);
-                            acc[2][ty * 3 + tx] = fmaf(d4.z, v, acc[2][ty * 3 + tx]);
-                            acc[3][ty * 3 + tx] = fmaf(d4.w, v, acc[3][ty * 3 + tx]);
-                        }
+        if (active) {
+            for (int u = sg; u < ns * h; u += PG) {  // unit = one row of one sample; the 3x3 window slides along it
+                const int g = u / h, y = u - g * h;
+                const float* r0 = s_x + (g * cin + ci) * PPs + y * wp;
+                const float *r1 = r0 + wp, *r2 = r1 + wp;
+                const float4* dr = reinterpret_cast<const float4*>(s_dy) + (size_t)(g * cq4 + cq) * hw + y * w;
+#define WG_LD(p, i) fmaxf((p)[i], lo)  /* lo = 0: the layer's input is relu(in) */
+                float a0 = WG_LD(r0, 0), a1 = WG_LD(r1, 0), a2 = WG_LD(r2, 0);
+                float b0v = WG_LD(r0, 1), b1v = WG_LD(r1, 1), b2v = WG_LD(r2, 1), c0, c1, c2;
+                for (int x = 0; x < w; x += 3) {
+                    c0 = WG_LD(r0, x + 2); c1 = WG_LD(r1, x + 2); c2 = WG_LD(r2, x + 2);
+                    WG_FMA(a0, a1, a2, b0v, b1v, b2v, c0, c1, c2, dr[x]);
+                    if (x + 1 < w) {
+                        a0 = WG_LD(r0, x + 3); a1 = WG_LD(r1, x + 3); a2 = WG_LD(r2, x + 3);
+                        WG_FMA(b0v, b1v, b2v, c0, c1, c2, a0, a1, a2, dr[x + 1]);
                     }
-                    accb[0] += d4.x;
-                    accb[1] += d4.y;
-                    accb[2] += d4.z;
-                    accb[3] += d4.w;
+                    if (x + 2 < w) {
+                        b0v = WG_LD(r0, x + 4); b1v = WG_LD(r1, x + 4); b2v = WG_LD(r2, x + 4);
+                        WG_FMA(c0, c1, c2, a0, a1, a2, b0v, b1v, b2v, dr[x + 2]);
+                    }
                 }
             }
         }
     }
     __syncthreads();
-    // reduce the subgroups through shared memory, write this chunk's partial gradient (fixed order: deterministic)
-    float* s_red = sm;  // [PG][pairs][40]
+    // reduce the subgroups through shared memory (fixed order: deterministic), lay the sums out in parameter order and
+    // write this chunk's partial gradient with coalesced vector stores
+    float* s_red = sm;                                     // [PG][pairs][41] (odd stride)
+    float* s_out = sm + ((PG * pairs * 41 + 3) & ~3);      // [cout*cin*9] weights | [cout] bias
     if (active) {
-        float* r = s_red + ((size_t)sg * pairs + pair) * 40;
+        float* r = s_red + ((size_t)sg * pairs + pair) * 41;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -507,32 +638,39 @@ __global__ void __launch_bounds__(THREADS) k_lr_wgrad(WgradArgs a) {
         }
     }
     __syncthreads();
-    float* part = a.partial + (size_t)blockIdx.x * a.nparams;
     const int nw = cout * cin * 9;
-    for (int idx = tid; idx < nw; idx += THREADS) {
-        const int co = idx / (cin * 9);
-        const int r = idx - co * cin * 9;
-        const int c = r / 9, t = r - c * 9;
-        const int pr = c + cin * (co >> 2);
-        float g = 0.f;
-        for (int s = 0; s < PG; ++s) g += s_red[((size_t)s * pairs + pr) * 40 + (co & 3) * 9 + t];
-        part[L.w_off + idx] = g;
+    if (tid < pairs) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float* o = s_out + ((size_t)(cq * 4 + c) * cin + ci) * 9;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                float g = 0.f;
+                for (int s2 = 0; s2 < PG; ++s2) g += s_red[((size_t)s2 * pairs + pair) * 41 + c * 9 + t];
+                o[t] = g;
+            }
+            if (ci == 0) {
+                float g = 0.f;
+                for (int s2 = 0; s2 < PG; ++s2) g += s_red[((size_t)s2 * pairs + pair) * 41 + 36 + c];
+                s_out[nw + cq * 4 + c] = g;
+            }
+        }
     }
-    for (int co = tid; co < cout; co += THREADS) {
-        const int pr = 0 + cin * (co >> 2);  // the ci == 0 thread of this channel quad
-        float g = 0.f;
-        for (int s = 0; s < PG; ++s) g += s_red[((size_t)s * pairs + pr) * 40 + 36 + (co & 3)];
-        part[L.b_off + co] = g;
-    }
+    __syncthreads();
+    float* part = a.partial + (size_t)blockIdx.x * a.nparams;
+    for (int i4 = tid; i4 < nw / 4; i4 += THREADS)
+        reinterpret_cast<float4*>(part + L.w_off)[i4] = reinterpret_cast<const float4*>(s_out)[i4];
+    for (int co = tid; co < cout; co += THREADS) part[L.b_off + co] = s_out[nw + co];
 }
 
 // grads[p] = sum over chunks (fixed order); losses[0..1] likewise
-__global__ void k_lr_reduce(long long nparams, int nchunk, const float* __restrict__ partial, float* __restrict__ grads,
+__global__ void k_lr_reduce(long long nparams, long long pstride, int nchunk, const float* __restrict__ partial,
+                            float* __restrict__ grads,
                             const float* __restrict__ loss_partial, float* __restrict__ losses) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < nparams) {
         float g = 0.f;
-        for (int k = 0; k < nchunk; ++k) g += partial[(size_t)k * nparams + i];
+        for (int k = 0; k < nchunk; ++k) g += partial[(size_t)k * pstride + i];
         grads[i] = g;
     }
     if (i < 2 && losses) {
@@ -583,9 +721,12 @@ struct bpp_learner {
     float *c[3] = {}, *p[3] = {}, *a0[3] = {}, *q[3] = {}, *a1[3] = {}, *o[3] = {};
     float *dc[3] = {}, *dp[3] = {}, *da0[3] = {}, *dq[3] = {}, *da1[3] = {}, *dout[3] = {};
     uint8_t* amax[3] = {};
+    float* wfwd = nullptr;   // conv weights as [cin*9][cout] (forward) and transposed + rotated (data gradient)
+    float* wbwd = nullptr;
     float* partial = nullptr;
     float* loss_partial = nullptr;
     int max_chunks = 0;
+    int sms = 148;
     int smem_cap = 0;
     std::vector<void*> allocs;
 };
@@ -601,27 +742,38 @@ bool dalloc(bpp_learner* l, void** p, size_t bytes) {
     return true;
 }
 
-void chunking(int B, int& S, int& nchunk) {
-    S = (B + NCHUNK0 - 1) / NCHUNK0;
-    if (S > SMAX) S = SMAX;
+// samples per gradient chunk: about one chunk per SM, at most SMAX samples each
+void chunking(int B, int sms, int& S, int& nchunk) {
+    S = std::min(SMAX, (B + sms - 1) / sms);
     nchunk = (B + S - 1) / S;
 }
 
 int launch_conv(bpp_learner* l, cudaStream_t st, int B, const float* in, const float* wt, const float* bias,
-                const float* mask, const float* add, float* out, int cin, int cout, int h, int w, int relu_in,
-                int transpose) {
+                const float* mask, const float* add, float* out, int cin, int cout, int h, int w, int relu_in) {
     ConvArgs a;
     a.in = in; a.wt = wt; a.bias = bias; a.mask = mask; a.add = add; a.out = out;
-    a.B = B; a.cin = cin; a.cout = cout; a.h = h; a.w = w; a.relu_in = relu_in; a.transpose = transpose;
-    const int hw = h * w, PP = (h + 2) * (w + 2);
-    int G = std::max(1, (256 * 16) / (cout * hw));
-    G = std::max(1, std::min(G, (B + 147) / 148));
+    a.B = B; a.cin = cin; a.cout = cout; a.h = h; a.w = w; a.relu_in = relu_in;
+    const int TP = w >= 7 ? 8 : (w >= 3 ? 4 : 2);  // output positions per work item (row segment)
+    a.wp = (w + 2) | 1;
+    const int PP = (h + 2) * a.wp;
     const size_t wbytes = (size_t)cin * 9 * cout * 4;
-    while (G > 1 && wbytes + (size_t)cin * G * PP * 4 > (size_t)l->smem_cap) --G;
+    const size_t part_bytes = (size_t)THREADS * 8 * TP * 4;
+    auto bytes = [&](int G) { return wbytes + ((size_t)cin * G * PP + 12) * 4 + part_bytes; };
+    int G = std::max(1, (B + 2 * l->sms - 1) / (2 * l->sms));  // two CTAs per SM when the batch allows
+    while (G > 1 && bytes(G) > (size_t)l->smem_cap) --G;
+    if (bytes(G) > (size_t)l->smem_cap) return lerr(BPP_E_INVALID, "convolution does not fit in shared memory");
     a.G = G;
-    const size_t smem = wbytes + (size_t)cin * G * PP * 4;
-    if (smem > (size_t)l->smem_cap) return lerr(BPP_E_INVALID, "convolution does not fit in shared memory");
-    k_lr_conv<<<(B + G - 1) / G, THREADS, smem, st>>>(a);
+    const int items = G * h * ((w + TP - 1) / TP) * (cout / 8);
+    a.KS = items >= THREADS ? 1 : std::max(1, std::min(cin, THREADS / items));
+    const int grid = (B + G - 1) / G;
+    const size_t smem = bytes(G);
+    if (TP == 8) k_lr_conv<8><<<grid, THREADS, smem, st>>>(a);
+    else if (TP == 4) k_lr_conv<4><<<grid, THREADS, smem, st>>>(a);
+    else k_lr_conv<2><<<grid, THREADS, smem, st>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return lerr(BPP_E_CUDA, std::string("convolution launch failed: ") + cudaGetErrorString(e) + " (smem " +
+                                    std::to_string(smem) + ", G " + std::to_string(G) + ", TP " + std::to_string(TP) + ")");
     return BPP_OK;
 }
 
@@ -678,9 +830,18 @@ extern "C" int bpp_learner_create(int W, int H, int N, int max_batch, int device
     int smem_optin = 0;
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     l->smem_cap = std::min(smem_optin, 200 * 1024);
-    if (cudaFuncSetAttribute(k_lr_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_cap) != cudaSuccess ||
-        cudaFuncSetAttribute(k_lr_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_cap) != cudaSuccess ||
-        cudaFuncSetAttribute(k_lr_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_cap) != cudaSuccess) {
+    cudaDeviceGetAttribute(&l->sms, cudaDevAttrMultiProcessorCount, device);
+    if (l->sms < 1) l->sms = 148;
+    const cudaFuncAttribute dyn = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (cudaFuncSetAttribute(k_lr_conv<8>, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_conv<4>, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_conv<2>, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_wgrad, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_heads<1>, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_heads<2>, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_heads<4>, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_heads<8>, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_heads<16>, dyn, l->smem_cap) != cudaSuccess) {
         cudaGetLastError();
         delete l;
         return lerr(BPP_E_CUDA, "cannot reserve shared memory for the learner kernels");
@@ -695,10 +856,9 @@ extern "C" int bpp_learner_create(int W, int H, int N, int max_batch, int device
                          &l->dout[s]};
         for (int k = 0; k < 10 && ok; ++k) ok = dalloc(l, (void**)t[k], B * ch * hw1 * 4);
     }
-    int S, nchunk;
-    chunking(max_batch, S, nchunk);
-    l->max_chunks = std::max(nchunk, NCHUNK0);
-    ok = ok && dalloc(l, (void**)&l->partial, (size_t)l->max_chunks * l->nparams * 4) &&
+    l->max_chunks = std::max(l->sms, (max_batch + SMAX - 1) / SMAX);
+    ok = ok && dalloc(l, (void**)&l->wfwd, (size_t)l->w1 * 4) && dalloc(l, (void**)&l->wbwd, (size_t)l->w1 * 4);
+    ok = ok && dalloc(l, (void**)&l->partial, (size_t)l->max_chunks * ((l->nparams + 3) & ~3LL) * 4) &&
          dalloc(l, (void**)&l->loss_partial, (size_t)l->max_chunks * 2 * 4);
     if (!ok) {
         for (void* p : l->allocs) cudaFree(p);
@@ -744,8 +904,16 @@ extern "C" int bpp_learner_grad(bpp_learner* l, int B, const float* params_dev, 
     if (B < 1 || B > l->max_batch) return lerr(BPP_E_INVALID, "batch size out of range");
     cudaStream_t st = (cudaStream_t)stream;
     const bool train = grads_out_dev != nullptr;
+    const float* P = params_dev;
     int rc;
     {
+        RelayoutArgs ra;
+        for (int i = 0; i < NCONV; ++i) {
+            ra.w_off[i] = l->conv[i].w_off;
+            ra.cin[i] = l->conv[i].cin;
+            ra.cout[i] = l->conv[i].cout;
+        }
+        k_lr_relayout<<<dim3(8, NCONV), 256, 0, st>>>(ra, P, l->wfwd, l->wbwd);
         const long long total = (long long)B * l->Cin * l->H * l->W;
         k_lr_planes<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(B, l->W, l->H, l->N, recs_dev,
                                                                                        items_wh_dev, ids_dev, l->planes);
@@ -755,63 +923,73 @@ extern "C" int bpp_learner_grad(bpp_learner* l, int B, const float* params_dev, 
     for (int s = 0; s < NSTAGE; ++s) {
         const ConvL* L = &l->conv[s * 5];
         const int ch = l->chans[s], h1 = l->hs[s + 1], w1 = l->ws[s + 1];
-        if ((rc = launch_conv(l, st, B, u, params_dev + L[0].w_off, params_dev + L[0].b_off, nullptr, nullptr, l->c[s],
-                              L[0].cin, ch, L[0].h, L[0].w, 0, 0)))
+        if ((rc = launch_conv(l, st, B, u, l->wfwd + L[0].w_off, P + L[0].b_off, nullptr, nullptr, l->c[s], L[0].cin, ch,
+                              L[0].h, L[0].w, 0)))
             return rc;
         {
             const long long total = (long long)B * ch * h1 * w1;
             k_lr_pool_fwd<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(
                 B * ch, L[0].h, L[0].w, h1, w1, l->c[s], l->p[s], l->amax[s]);
         }
-        if ((rc = launch_conv(l, st, B, l->p[s], params_dev + L[1].w_off, params_dev + L[1].b_off, nullptr, nullptr,
-                              l->a0[s], ch, ch, h1, w1, 1, 0)) ||
-            (rc = launch_conv(l, st, B, l->a0[s], params_dev + L[2].w_off, params_dev + L[2].b_off, nullptr, l->p[s],
-                              l->q[s], ch, ch, h1, w1, 1, 0)) ||
-            (rc = launch_conv(l, st, B, l->q[s], params_dev + L[3].w_off, params_dev + L[3].b_off, nullptr, nullptr,
-                              l->a1[s], ch, ch, h1, w1, 1, 0)) ||
-            (rc = launch_conv(l, st, B, l->a1[s], params_dev + L[4].w_off, params_dev + L[4].b_off, nullptr, l->q[s],
-                              l->o[s], ch, ch, h1, w1, 1, 0)))
+        if ((rc = launch_conv(l, st, B, l->p[s], l->wfwd + L[1].w_off, P + L[1].b_off, nullptr, nullptr, l->a0[s], ch, ch,
+                              h1, w1, 1)) ||
+            (rc = launch_conv(l, st, B, l->a0[s], l->wfwd + L[2].w_off, P + L[2].b_off, nullptr, l->p[s], l->q[s], ch, ch,
+                              h1, w1, 1)) ||
+            (rc = launch_conv(l, st, B, l->q[s], l->wfwd + L[3].w_off, P + L[3].b_off, nullptr, nullptr, l->a1[s], ch, ch,
+                              h1, w1, 1)) ||
+            (rc = launch_conv(l, st, B, l->a1[s], l->wfwd + L[4].w_off, P + L[4].b_off, nullptr, l->q[s], l->o[s], ch, ch,
+                              h1, w1, 1)))
             return rc;
         u = l->o[s];
     }
     // ---- heads: forward, losses, backward of the linear layers ----
     int S, nchunk;
-    chunking(B, S, nchunk);
+    chunking(B, l->sms, S, nchunk);
     {
         HeadArgs a;
         a.B = B; a.S = S; a.flat = l->flat; a.A = l->A;
-        a.o2 = l->o[2]; a.params = params_dev;
+        a.o2 = l->o[2]; a.params = P;
         a.w1 = l->w1; a.b1 = l->b1; a.w2 = l->w2; a.b2 = l->b2; a.wv = l->wv; a.bv = l->bv;
         a.pis = pis_dev; a.vs = vs_dev; a.ids = ids_dev;
         a.dfeat = l->dout[2];
         a.partial = train ? l->partial : nullptr;
-        a.nparams = l->nparams;
+        a.nparams = (l->nparams + 3) & ~3LL;
         a.loss_partial = l->loss_partial;
         a.logp_out = logp_out_dev; a.v_out = v_out_dev;
-        const size_t smem = ((size_t)SMAX * l->flat + (size_t)SMAX * HIDDEN + (size_t)SMAX * (l->A + 1)) * 4;
+        int SM = 1;
+        while (SM < S) SM <<= 1;
+        const size_t smem = ((size_t)SM * l->flat + (size_t)SM * HIDDEN + (size_t)SM * (l->A + 1)) * 4;
         if (smem > (size_t)l->smem_cap) return lerr(BPP_E_INVALID, "heads do not fit in shared memory");
-        k_lr_heads<<<nchunk, THREADS, smem, st>>>(a);
+        switch (SM) {
+            case 1: k_lr_heads<1><<<nchunk, THREADS, smem, st>>>(a); break;
+            case 2: k_lr_heads<2><<<nchunk, THREADS, smem, st>>>(a); break;
+            case 4: k_lr_heads<4><<<nchunk, THREADS, smem, st>>>(a); break;
+            case 8: k_lr_heads<8><<<nchunk, THREADS, smem, st>>>(a); break;
+            default: k_lr_heads<16><<<nchunk, THREADS, smem, st>>>(a); break;
+        }
     }
     if (!train) {
-        k_lr_reduce<<<1, 32, 0, st>>>(0, nchunk, l->partial, nullptr, l->loss_partial, losses_out_dev);
-        return cudaGetLastError() == cudaSuccess ? BPP_OK : lerr(BPP_E_CUDA, "learner forward launch failed");
+        k_lr_reduce<<<1, 32, 0, st>>>(0, 0, nchunk, l->partial, nullptr, l->loss_partial, losses_out_dev);
+        const cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? BPP_OK
+                                : lerr(BPP_E_CUDA, std::string("learner forward launch failed: ") + cudaGetErrorString(e));
     }
     // ---- backward: data gradients, last stage first ----
     for (int s = NSTAGE - 1; s >= 0; --s) {
         const ConvL* L = &l->conv[s * 5];
         const int ch = l->chans[s], h1 = l->hs[s + 1], w1 = l->ws[s + 1];
         // da1 = dgrad(res1.conv1, do) * (a1 > 0)
-        if ((rc = launch_conv(l, st, B, l->dout[s], params_dev + L[4].w_off, nullptr, l->a1[s], nullptr, l->da1[s], ch, ch,
-                              h1, w1, 0, 1)) ||
+        if ((rc = launch_conv(l, st, B, l->dout[s], l->wbwd + L[4].w_off, nullptr, l->a1[s], nullptr, l->da1[s], ch, ch, h1,
+                              w1, 0)) ||
             // dq = do + dgrad(res1.conv0, da1) * (q > 0)
-            (rc = launch_conv(l, st, B, l->da1[s], params_dev + L[3].w_off, nullptr, l->q[s], l->dout[s], l->dq[s], ch, ch,
-                              h1, w1, 0, 1)) ||
+            (rc = launch_conv(l, st, B, l->da1[s], l->wbwd + L[3].w_off, nullptr, l->q[s], l->dout[s], l->dq[s], ch, ch, h1,
+                              w1, 0)) ||
             // da0 = dgrad(res0.conv1, dq) * (a0 > 0)
-            (rc = launch_conv(l, st, B, l->dq[s], params_dev + L[2].w_off, nullptr, l->a0[s], nullptr, l->da0[s], ch, ch,
-                              h1, w1, 0, 1)) ||
+            (rc = launch_conv(l, st, B, l->dq[s], l->wbwd + L[2].w_off, nullptr, l->a0[s], nullptr, l->da0[s], ch, ch, h1,
+                              w1, 0)) ||
             // dp = dq + dgrad(res0.conv0, da0) * (p > 0)
-            (rc = launch_conv(l, st, B, l->da0[s], params_dev + L[1].w_off, nullptr, l->p[s], l->dq[s], l->dp[s], ch, ch,
-                              h1, w1, 0, 1)))
+            (rc = launch_conv(l, st, B, l->da0[s], l->wbwd + L[1].w_off, nullptr, l->p[s], l->dq[s], l->dp[s], ch, ch, h1,
+                              w1, 0)))
             return rc;
         {
             const long long total = (long long)B * ch * L[0].h * L[0].w;
@@ -819,15 +997,15 @@ extern "C" int bpp_learner_grad(bpp_learner* l, int B, const float* params_dev, 
                 B * ch, L[0].h, L[0].w, h1, w1, l->dp[s], l->amax[s], l->dc[s]);
         }
         if (s > 0) {  // gradient w.r.t. the previous stage's output (no activation in between)
-            if ((rc = launch_conv(l, st, B, l->dc[s], params_dev + L[0].w_off, nullptr, nullptr, nullptr, l->dout[s - 1],
-                                  ch, L[0].cin, L[0].h, L[0].w, 0, 1)))
+            if ((rc = launch_conv(l, st, B, l->dc[s], l->wbwd + L[0].w_off, nullptr, nullptr, nullptr, l->dout[s - 1], ch,
+                                  L[0].cin, L[0].h, L[0].w, 0)))
                 return rc;
         }
     }
     // ---- weight gradients of all convolutions, then the ordered reduction over chunks ----
     {
         WgradArgs a;
-        a.B = B; a.S = S; a.partial = l->partial; a.nparams = l->nparams;
+        a.B = B; a.S = S; a.partial = l->partial; a.nparams = (l->nparams + 3) & ~3LL;
         size_t smem_max = 0;
         for (int s = 0; s < NSTAGE; ++s) {
             const float* ins[5] = {s == 0 ? l->planes : l->o[s - 1], l->p[s], l->a0[s], l->q[s], l->a1[s]};
@@ -841,20 +1019,24 @@ extern "C" int bpp_learner_grad(bpp_learner* l, int B, const float* params_dev, 
                 const int pairs = C.cin * (C.cout / 4);
                 if (pairs > THREADS) return lerr(BPP_E_INVALID, "unsupported channel counts");
                 const int PPs = ((C.h + 2) * (C.w + 2)) | 1;
-                const size_t per = ((size_t)C.cin * PPs + (size_t)C.h * C.w * C.cout) * 4 + 16;
-                int pg = std::max(1, std::min(THREADS / pairs, S));
-                while (pg > 1 && per * pg > (size_t)l->smem_cap) --pg;
+                const size_t per = ((size_t)C.cin * PPs + (size_t)C.h * C.w * C.cout) * 4;
+                int round = S;  // samples staged at once: keep a CTA near 56 KB so that four of them share an SM
+                while (round > 1 && per * round + 16 > (size_t)std::min(l->smem_cap, 56 * 1024)) --round;
+                const int pg = std::max(1, std::min(THREADS / pairs, round * C.h));
                 Lw.pg = pg;
-                const size_t need = std::max(per * pg, (size_t)pg * pairs * 40 * 4);
+                Lw.round = round;
+                const size_t need = std::max(per * round + 16, ((size_t)pg * pairs * 41 + 4 + (size_t)C.cout * C.cin * 9 + C.cout) * 4);
                 if (need > (size_t)l->smem_cap) return lerr(BPP_E_INVALID, "weight gradient does not fit in shared memory");
                 smem_max = std::max(smem_max, need);
             }
         }
         k_lr_wgrad<<<dim3(nchunk, NCONV), THREADS, smem_max, st>>>(a);
     }
-    k_lr_reduce<<<(int)((l->nparams + 255) / 256), 256, 0, st>>>(l->nparams, nchunk, l->partial, grads_out_dev,
+    k_lr_reduce<<<(int)((l->nparams + 255) / 256), 256, 0, st>>>(l->nparams, (l->nparams + 3) & ~3LL, nchunk, l->partial,
+                                                               grads_out_dev,
                                                                l->loss_partial, losses_out_dev);
-    return cudaGetLastError() == cudaSuccess ? BPP_OK : lerr(BPP_E_CUDA, "learner step launch failed");
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? BPP_OK : lerr(BPP_E_CUDA, std::string("learner step launch failed: ") + cudaGetErrorString(e));
 }
 
 extern "C" int bpp_learner_adam(int64_t n, float* params_dev, const float* grads_dev, float* exp_avg_dev,

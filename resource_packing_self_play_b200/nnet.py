@@ -253,7 +253,46 @@ class NNetWrapper:
         return self.dnet.forward(recs, items_wh, game, count_dev)
 
     # ---- learner (same semantics as NNet.py:27-67,87-91) --------------------------------------
-    def train(self, examples):
+    def _device_learner(self, batch):
+        L = getattr(self, "_learner", None)
+        if L is None or L.max_batch < batch:
+            if L is not None:
+                L.close()
+            L = self._learner = DeviceLearner(self.board_w, self.board_h, self.num_items, batch, self.device.index)
+        L.load_state_dict(self.nnet.state_dict())
+        L.reset_optimizer()  # the reference builds a new Adam in every train() call (NNet.py:31)
+        return L
+
+    def train(self, examples, learner=None):
+        """examples: list of (board (N+1, H, W), pi (A,), v) as CoachBPP builds them (NNet.py:27-67).  Minibatches are
+        drawn with np.random.randint exactly like the reference; the step itself (forward, losses, backward, Adam) is the
+        hand-written CUDA learner (learner="cuda", csrc/bpp_learner.cu) or torch autograd (learner="torch", the
+        cross-check)."""
+        if (learner or os.environ.get("BPP_LEARNER", "cuda")) == "torch":
+            return self._train_torch(examples)
+        from .distributed import world
+        rank, ws = world()
+        bs = int(self.args.batch_size)
+        boards, pis, vs = list(zip(*examples))
+        recs, items = pack_states(np.asarray(boards), self.board_w, self.board_h, self.num_items)
+        recs_t = torch.from_numpy(recs.view(np.int32)).to(self.device)
+        items_t = torch.from_numpy(items).to(self.device)
+        pis_t = torch.as_tensor(np.asarray(pis, dtype=np.float32), device=self.device)
+        vs_t = torch.as_tensor(np.asarray(vs).astype(np.float64).astype(np.float32).reshape(-1), device=self.device)
+        L = self._device_learner(bs)
+        for epoch in range(self.args.epochs):
+            batch_count = int(len(examples) / bs)
+            for _ in range(batch_count):
+                ids = torch.from_numpy(np.random.randint(len(examples), size=bs).astype(np.int64)).to(self.device)
+                L.grad(recs_t, items_t, pis_t, vs_t, ids=ids)
+                if ws > 1:
+                    torch.distributed.all_reduce(L.grads)
+                L.adam(grad_scale=1.0 / ws)
+        L.state_dict_into(self.nnet)
+        self.nnet.eval()
+        self.sync_weights()
+
+    def _train_torch(self, examples):
         optimizer = torch.optim.Adam(self.nnet.parameters())  # re-created per call, default lr (args.lr ignored)
         for epoch in range(self.args.epochs):
             self.nnet.train()
@@ -278,15 +317,82 @@ class NNetWrapper:
         self.nnet.eval()
         self.sync_weights()
 
-    def train_compact(self, recs, items_wh, pis, vs, ops, steps_per_epoch=None, seed=None, use_graph=True):
+    def train_compact(self, recs, items_wh, pis, vs, ops=None, steps_per_epoch=None, seed=None, use_graph=True,
+                      learner=None):
         """Learner on compact examples that already live on the device (the batched / multi-GPU path).
-        recs int32 (M, 32), items_wh int32 (M, N, 2), pis float32 (M, A), vs float32 (M,); `ops` = EnvOps (builds the
-        dense input planes of each minibatch on the device).  Same optimiser, losses and sampling-with-replacement as
-        `train` (NNet.py:27-67); with torch.distributed initialised every rank draws its own minibatches and the
-        gradients are averaged with one flat all-reduce per step.  The step (planes kernel -> forward -> losses ->
-        backward -> gradient all-reduce -> Adam) is captured once in a CUDA graph and replayed: the learner of this
-        170 K-parameter net is launch-bound (~150 kernels per step).  Returns (mean pi loss, mean v loss) of the last
-        epoch."""
+        recs int32 (M, 32), items_wh int32 (M, N, 2), pis float32 (M, A), vs float32 (M,).  Same optimiser, losses and
+        sampling-with-replacement as `train` (NNet.py:27-67); with torch.distributed initialised every rank draws its
+        own minibatches and the gradients are averaged with one flat all-reduce per step.  learner="cuda": the
+        hand-written step (bpp_learner_grad gathers the minibatch rows itself -> flat gradient -> NCCL all-reduce ->
+        bpp_learner_adam), captured once in a CUDA graph and replayed.  learner="torch": the same loop on torch
+        autograd (`ops` = EnvOps builds the dense input planes), kept as the cross-check.  Returns (mean pi loss, mean v
+        loss) of the last epoch."""
+        if (learner or os.environ.get("BPP_LEARNER", "cuda")) == "torch":
+            return self._train_compact_torch(recs, items_wh, pis, vs, ops, steps_per_epoch, seed, use_graph)
+        from .distributed import world
+        rank, ws = world()
+        M = recs.shape[0]
+        dev = self.device
+        bs = int(self.args.batch_size)
+        if steps_per_epoch is None:
+            steps_per_epoch = max(1, int(M / (bs * ws)))
+        gen = torch.Generator(device=dev)
+        gen.manual_seed((seed if seed is not None else int(np.random.randint(1 << 30))) * 977 + rank)
+        recs = recs.contiguous()
+        items_wh = items_wh.contiguous()
+        pis = pis.contiguous().float()
+        vs = vs.contiguous().float()
+        L = self._device_learner(bs)
+        ids = torch.zeros(bs, dtype=torch.int64, device=dev)
+        acc = torch.zeros(2, dtype=torch.float64, device=dev)
+
+        def step():
+            L.grad(recs, items_wh, pis, vs, ids=ids)
+            if ws > 1:
+                torch.distributed.all_reduce(L.grads)
+            L.adam(grad_scale=1.0 / ws)
+            acc.add_(L.losses)
+
+        total_steps = steps_per_epoch * int(self.args.epochs)
+        last_epoch_start = total_steps - steps_per_epoch
+        state = {"done": 0, "n_acc": 0}
+
+        def next_batch():
+            if state["done"] == last_epoch_start:  # the returned losses are the last epoch's means
+                acc.zero_()
+                state["n_acc"] = 0
+            ids.copy_(torch.randint(0, M, (bs,), device=dev, generator=gen))
+            state["done"] += 1
+            state["n_acc"] += 1
+
+        graph = None
+        if use_graph and total_steps > 8:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up on a side stream (real training steps)
+                    next_batch()
+                    step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            next_batch()
+            with torch.cuda.graph(graph):
+                step()
+            graph.replay()  # capture records the step without running it
+        while state["done"] < total_steps:
+            next_batch()
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+        n_acc = state["n_acc"]
+        L.state_dict_into(self.nnet)
+        self.nnet.eval()
+        self.sync_weights()
+        mean = (acc / max(1, n_acc)).cpu().numpy()
+        return float(mean[0]), float(mean[1])
+
+    def _train_compact_torch(self, recs, items_wh, pis, vs, ops, steps_per_epoch=None, seed=None, use_graph=True):
         from .distributed import world
         rank, ws = world()
         M = recs.shape[0]
@@ -341,6 +447,7 @@ class NNetWrapper:
             optimizer.zero_grad(set_to_none=True)
             with torch.cuda.graph(graph):
                 step()
+            graph.replay()  # capture records the step without running it
             done += 1
         acc = torch.zeros(2, dtype=torch.float64, device=dev)
         n_acc = 0

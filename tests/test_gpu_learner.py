@@ -158,3 +158,41 @@ def test_training_trajectory_follows_torch():
     L.grad(recs, items, pis, vs, train=False, logp_out=logp, v_out=v)
     assert float((logp - logp_t).abs().max()) < 1e-4 and float((v - v_t.view(-1)).abs().max()) < 1e-5
     L.close()
+
+
+def test_wrapper_train_paths_agree():
+    """NNetWrapper.train / train_compact with the CUDA learner against the torch-autograd cross-check: same minibatch
+    stream (np.random / seeded generator), so the trained weights agree to fp32 noise amplified by Adam."""
+    from resource_packing_self_play_b200.game import BinPackingGame
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+    W, H, N, M = 15, 15, 10, 256
+    ops, recs, items, pis, vs = _examples(M, W, H, N, seed=21)
+    args = dotdict(num_items=N, num_bins=1, epochs=2, batch_size=32, cuda=True)
+    g = BinPackingGame(W, H, N, 1)
+    out = {}
+    for learner in ("cuda", "torch"):
+        torch.manual_seed(0)
+        net = NNetWrapper(g, args, max_batch=64)
+        out[learner] = net.train_compact(recs, items, pis, vs, ops, seed=5, use_graph=(learner == "cuda"), learner=learner)
+        out[learner + "_w"] = torch.cat([p.detach().reshape(-1) for p in net.nnet.parameters()])
+    assert abs(out["cuda"][0] - out["torch"][0]) < 2e-2 * abs(out["torch"][0])
+    assert abs(out["cuda"][1] - out["torch"][1]) < 5e-2 * abs(out["torch"][1]) + 1e-3
+    # Adam moves a weight whose gradient is ~0 by up to lr per step in a direction set by rounding noise: bound the
+    # largest difference by lr * steps and ask the typical one to be far smaller
+    d = (out["cuda_w"] - out["torch_w"]).abs()
+    assert float(d.max()) <= 2 * 1e-3 * 16 and float(d.mean()) < 1e-3, (float(d.max()), float(d.mean()))
+    # reference-surface train(): dense boards in, same np.random minibatch stream on both paths
+    planes = ops.planes(recs, items).cpu().numpy().astype(np.int64)
+    examples = [(planes[i], pis[i].cpu().numpy(), float(vs[i])) for i in range(M)]
+    ws = {}
+    for learner in ("cuda", "torch"):
+        torch.manual_seed(0)
+        net = NNetWrapper(g, args, max_batch=64)
+        np.random.seed(9)
+        net.train(examples, learner=learner)
+        ws[learner] = torch.cat([p.detach().reshape(-1) for p in net.nnet.parameters()])
+        pi, v = net.predict(planes[0])
+        assert abs(pi.sum() - 1) < 1e-3
+    d = (ws["cuda"] - ws["torch"]).abs()
+    assert float(d.max()) <= 2 * 1e-3 * 16 and float(d.mean()) < 1e-3, (float(d.max()), float(d.mean()))
