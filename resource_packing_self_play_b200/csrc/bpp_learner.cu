@@ -216,15 +216,18 @@ __global__ void __launch_bounds__(THREADS, 2) k_lr_conv(ConvArgs a) {
         }
         return;
     }
-    // split over the input channels: thread = (work item, channel slice); partial sums meet in shared memory
+    // split over the input channels: thread = (work item, channel slice); partial sums meet in shared memory and every
+    // thread then reduces and writes a slice of its own item's 8 x TP outputs
     const int slots = items * a.KS;
-    if (tid < slots) {
-        const int item = tid % items, ks = tid / items;
-        const int cb = item / rows;
-        int r = item - cb * rows;
-        const int g = r / (a.h * nseg);
-        r -= g * a.h * nseg;
-        const int y = r / nseg, x0 = (r - y * nseg) * TP;
+    const bool live = tid < slots;
+    const int item = live ? tid % items : 0, ks = live ? tid / items : 0;
+    const int cb = item / rows;
+    int r = item - cb * rows;
+    const int g = r / (a.h * nseg);
+    r -= g * a.h * nseg;
+    const int y = r / nseg, x0 = (r - y * nseg) * TP;
+    const int b = b0 + g;
+    if (live) {
         const int cpk = (a.cin + a.KS - 1) / a.KS;
         float acc[8][TP];
 #pragma unroll
@@ -239,23 +242,18 @@ __global__ void __launch_bounds__(THREADS, 2) k_lr_conv(ConvArgs a) {
             for (int k = 0; k < TP; ++k) s_part[(j * TP + k) * slots + tid] = acc[j][k];
     }
     __syncthreads();
-#pragma unroll 4
-    for (int oidx = tid; oidx < items * 8 * TP; oidx += THREADS) {
-        const int jk = oidx / items, item = oidx - jk * items;
-        const int j = jk / TP, k = jk - j * TP;
-        const int cb = item / rows;
-        int r = item - cb * rows;
-        const int g = r / (a.h * nseg);
-        r -= g * a.h * nseg;
-        const int y = r / nseg, x = (r - y * nseg) * TP + k;
-        const int b = b0 + g;
-        if (b >= a.B || x >= a.w) continue;
+    if (!live || b >= a.B) return;
+    const size_t obase = ((size_t)b * a.cout + cb * 8) * hw + y * a.w + x0;
+    for (int jk = ks; jk < 8 * TP; jk += a.KS) {
+        const int j = jk / TP, k = jk % TP;  // TP is a compile-time power of two
+        if (x0 + k >= a.w) continue;
+        const size_t o = obase + (size_t)j * hw + k;
+        const float mk = a.mask ? a.mask[o] : 1.f;
+        const float ad = a.add ? a.add[o] : 0.f;
         float v = a.bias ? __ldg(a.bias + cb * 8 + j) : 0.f;
-        for (int ks = 0; ks < a.KS; ++ks) v += s_part[jk * slots + ks * items + item];
-        const size_t o = ((size_t)b * a.cout + cb * 8 + j) * hw + y * a.w + x;
-        if (a.mask) v = a.mask[o] > 0.f ? v : 0.f;
-        if (a.add) v += a.add[o];
-        a.out[o] = v;
+        const float* sp = s_part + jk * slots + item;
+        for (int q = 0; q < a.KS; ++q) v += sp[q * items];
+        a.out[o] = (mk > 0.f ? v : 0.f) + ad;
     }
 }
 
@@ -300,16 +298,18 @@ __global__ void k_lr_pool_bwd(int BC, int h, int w, int oh, int ow, const float*
         const int iy = r / w, ix = r - iy * w;
         const float* dp = dout + (size_t)bc * oh * ow;
         const uint8_t* am = amax + (size_t)bc * oh * ow;
-        float g = 0.f;
-        for (int oy = iy >> 1; oy <= ((iy + 1) >> 1) && oy < oh; ++oy) {
-            const int ky = iy - (2 * oy - 1);
-            if (ky < 0 || ky > 2) continue;
-            for (int ox = ix >> 1; ox <= ((ix + 1) >> 1) && ox < ow; ++ox) {
-                const int kx = ix - (2 * ox - 1);
-                if (kx < 0 || kx > 2) continue;
-                if (am[oy * ow + ox] == ky * 3 + kx) g += dp[oy * ow + ox];
-            }
-        }
+        // at most two candidate windows per axis; all loads first (clamped indices), then the selects
+        const int oy0 = iy >> 1, oy1 = (iy + 1) >> 1, ox0 = ix >> 1, ox1 = (ix + 1) >> 1;
+        const bool vy1 = oy1 != oy0 && oy1 < oh, vx1 = ox1 != ox0 && ox1 < ow;
+        const int cy1 = vy1 ? oy1 : oy0, cx1 = vx1 ? ox1 : ox0;
+        const int i00 = oy0 * ow + ox0, i01 = oy0 * ow + cx1, i10 = cy1 * ow + ox0, i11 = cy1 * ow + cx1;
+        const int a00 = am[i00], a01 = am[i01], a10 = am[i10], a11 = am[i11];
+        const float d00 = dp[i00], d01 = dp[i01], d10 = dp[i10], d11 = dp[i11];
+        const int ky0 = iy - (2 * oy0 - 1), ky1 = iy - (2 * cy1 - 1), kx0 = ix - (2 * ox0 - 1), kx1 = ix - (2 * cx1 - 1);
+        float g = (a00 == ky0 * 3 + kx0) ? d00 : 0.f;
+        if (vx1 && a01 == ky0 * 3 + kx1) g += d01;
+        if (vy1 && a10 == ky1 * 3 + kx0) g += d10;
+        if (vy1 && vx1 && a11 == ky1 * 3 + kx1) g += d11;
         din[i] = g;
     }
 }
@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
 #pragma unroll
         for (int s = 0; s < SM; ++s) acc[s] = bias;
         const float4* wrow = reinterpret_cast<const float4*>(W1 + (size_t)o * a.flat);
+#pragma unroll 8
         for (int i4 = 0; i4 < a.flat / 4; ++i4) {
             const float4 w4 = __ldg(wrow + i4);
 #pragma unroll
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
 #pragma unroll
         for (int s = 0; s < SM; ++s) acc[s] = bias;
         const float* wrow = j < a.A ? W2 + (size_t)j * HIDDEN : WV;  // WV may not be 16-byte aligned (A odd multiples)
+#pragma unroll 8
         for (int o4 = 0; o4 < HIDDEN / 4; ++o4) {
             const float4 w4 = j < a.A ? __ldg(reinterpret_cast<const float4*>(wrow) + o4)
                                       : make_float4(__ldg(wrow + 4 * o4), __ldg(wrow + 4 * o4 + 1), __ldg(wrow + 4 * o4 + 2),
@@ -457,6 +459,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
     // partial gradients of logits_fc / value_fc: thread = hidden unit o (coalesced over o)
     {
         const int o = tid;
+#pragma unroll 8
         for (int j = 0; j <= a.A; ++j) {
             float g = 0.f;
 #pragma unroll
@@ -475,6 +478,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
         const int o = tid;
 #pragma unroll
         for (int s = 0; s < SM; ++s) dh[s] = 0.f;
+#pragma unroll 8
         for (int j = 0; j <= a.A; ++j) {
             const float w = j < a.A ? __ldg(W2 + (size_t)j * HIDDEN + o) : __ldg(WV + o);
 #pragma unroll
@@ -504,6 +508,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_heads(HeadArgs a) {
         float acc[SM];
 #pragma unroll
         for (int s = 0; s < SM; ++s) acc[s] = 0.f;
+#pragma unroll 8
         for (int o = 0; o < HIDDEN; ++o) {
             const float w = __ldg(W1 + (size_t)o * a.flat + i);
 #pragma unroll
@@ -579,8 +584,9 @@ __global__ void __launch_bounds__(THREADS) k_lr_wgrad(WgradArgs a) {
         const int perx = cin * hw, pery = cout * hw;
         const int lane = tid & 31, warp = tid >> 5;
         const unsigned magic = (65536u + w - 1) / w;
+        const unsigned mcin = (65536u + cin - 1) / cin, mcq = (65536u + cq4 - 1) / cq4;  // exact for operands < 2048
         for (int pl = warp; pl < ns * cin; pl += THREADS / 32) {  // one input plane per warp and pass
-            const int g = pl / cin, c = pl - g * cin;
+            const int g = (int)(((unsigned)pl * mcin) >> 16), c = pl - g * cin;
             const float* src = L.in + (size_t)(b0 + j0 + g) * perx + c * hw;
             float* dst = s_x + (g * cin + c) * PPs + wp + 1;
             for (int pos = lane; pos < hw; pos += 32) {
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(THREADS) k_lr_wgrad(WgradArgs a) {
             }
         }
         for (int gq = warp; gq < ns * cq4; gq += THREADS / 32) {  // one (sample, channel quad) per warp and pass
-            const int g = gq / cq4, q = gq - g * cq4;
+            const int g = (int)(((unsigned)gq * mcq) >> 16), q = gq - g * cq4;
             const float* src = L.dy + (size_t)(b0 + j0 + g) * pery + (size_t)q * 4 * hw;
             float* dst = s_dy + (size_t)gq * hw * 4;
             for (int r = lane; r < ((hw + 7) >> 3) * 32; r += 32) {  // r = (8-position group, channel in quad, position)
@@ -600,8 +606,9 @@ __global__ void __launch_bounds__(THREADS) k_lr_wgrad(WgradArgs a) {
         cp_async_wait_all();
         __syncthreads();
         if (active) {
+            const unsigned mh = (65536u + h - 1) / h;
             for (int u = sg; u < ns * h; u += PG) {  // unit = one row of one sample; the 3x3 window slides along it
-                const int g = u / h, y = u - g * h;
+                const int g = (int)(((unsigned)u * mh) >> 16), y = u - g * h;
                 const float* r0 = s_x + (g * cin + ci) * PPs + y * wp;
                 const float *r1 = r0 + wp, *r2 = r1 + wp;
                 const float4* dr = reinterpret_cast<const float4*>(s_dy) + (size_t)(g * cq4 + cq) * hw + y * w;
@@ -643,15 +650,17 @@ __global__ void __launch_bounds__(THREADS) k_lr_wgrad(WgradArgs a) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             float* o = s_out + ((size_t)(cq * 4 + c) * cin + ci) * 9;
+            const float* rp = s_red + (size_t)pair * 41 + c * 9;
+            const int sstride = pairs * 41;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 float g = 0.f;
-                for (int s2 = 0; s2 < PG; ++s2) g += s_red[((size_t)s2 * pairs + pair) * 41 + c * 9 + t];
+                for (int s2 = 0; s2 < PG; ++s2) g += rp[s2 * sstride + t];
                 o[t] = g;
             }
             if (ci == 0) {
                 float g = 0.f;
-                for (int s2 = 0; s2 < PG; ++s2) g += s_red[((size_t)s2 * pairs + pair) * 41 + 36 + c];
+                for (int s2 = 0; s2 < PG; ++s2) g += s_red[(size_t)s2 * sstride + pair * 41 + 36 + c];
                 s_out[nw + cq * 4 + c] = g;
             }
         }
