@@ -517,14 +517,19 @@ struct HeadParams {
     float bv;
 };
 constexpr int HEAD_THREADS = 128;
-constexpr int HEAD_STAGE_BYTES = 32 * 1024;
+constexpr int HEAD_STAGES = 4;               // ring of weight stages filled by cp.async, drained by the MMAs
+constexpr int HEAD_STAGE_BYTES = 16 * 1024;
+
+__device__ __forceinline__ void head_cp16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bpptc::smem_u32(dst_smem)), "l"(src));
+}
 
 __global__ void __launch_bounds__(HEAD_THREADS, 1)
 k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, const __nv_bfloat16* __restrict__ feat,
                float* __restrict__ policy, float* __restrict__ value) {
     using namespace bpptc;
     extern __shared__ __align__(1024) unsigned char hsm[];
-    __shared__ __align__(8) uint64_t s_bar[3];  // [0], [1]: weight stages free again; [2]: GEMM complete
+    __shared__ __align__(8) uint64_t s_bar[HEAD_STAGES + 1];  // [s]: MMAs that read stage s are done; [last]: GEMM done
     __shared__ uint32_t s_tmem;
     __shared__ float s_b1[HIDDEN], s_wv[HIDDEN];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -534,7 +539,27 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     const int kplanes = (Hp.flat > HIDDEN ? Hp.flat : HIDDEN) / 8;
     unsigned char* areg = hsm;                                   // planes x 128 rows x 16 B
     unsigned char* stage0 = hsm + (size_t)kplanes * 2048;
-    if (tid < 3) mbar_init(smem_u32(&s_bar[tid]), 1);
+    // the weight chunks of both GEMMs as one list: chunk c covers k-blocks [kb, kb + nk) of GEMM g
+    const int blk1 = 2 * HIDDEN * 16, blk2 = 2 * Hp.N2 * 16;     // bytes per 16-deep k-block of W1 / W2 (UMMA B layout)
+    const int kpc1 = HEAD_STAGE_BYTES / blk1, kpc2 = HEAD_STAGE_BYTES / blk2;
+    const int nkb1 = Hp.flat / 16, nkb2 = HIDDEN / 16;
+    const int nch1 = (nkb1 + kpc1 - 1) / kpc1, nch2 = (nkb2 + kpc2 - 1) / kpc2;
+    const int nch = nch1 + nch2;
+    auto issue_chunk = [&](int c) {  // cp.async this thread's share of chunk c into stage c % HEAD_STAGES
+        if (c < nch) {
+            const bool g2 = c >= nch1;
+            const int cc = g2 ? c - nch1 : c;
+            const int kpc = g2 ? kpc2 : kpc1, blk = g2 ? blk2 : blk1, nkb = g2 ? nkb2 : nkb1;
+            const int kb = cc * kpc, nk = min(kpc, nkb - kb);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(g2 ? Hp.w2u : Hp.w1u) + (size_t)kb * blk;
+            unsigned char* dst = stage0 + (size_t)(c % HEAD_STAGES) * HEAD_STAGE_BYTES;
+            for (int i = tid * 16; i < nk * blk; i += HEAD_THREADS * 16) head_cp16(dst + i, src + i);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per chunk slot, possibly empty
+    };
+#pragma unroll
+    for (int c = 0; c < HEAD_STAGES; ++c) issue_chunk(c);  // weights are in flight while the rest of the prologue runs
+    if (tid <= HEAD_STAGES) mbar_init(smem_u32(&s_bar[tid]), 1);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "r"(512u));
@@ -548,6 +573,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     {
         const int r = row0 + tid;
         const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)r * Hp.flat);
+#pragma unroll 4
         for (int p = 0; p < Hp.flat / 8; ++p) {
             const uint4 v = r < B ? __ldg(src + p) : make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(areg + (size_t)p * 2048 + tid * 16) = v;
@@ -558,47 +584,43 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     tc_fence_after();
     const uint32_t tmem = s_tmem;
     const uint32_t bar0 = smem_u32(&s_bar[0]);
-    uint32_t ph[3] = {0, 0, 0};
-    int used[2] = {0, 0};
+    const uint32_t bar_done = bar0 + 8u * HEAD_STAGES;
+    uint32_t ph_stage = 0;  // bit s = parity to wait for on stage s
+    uint32_t ph_done = 0;
 
-    // one GEMM: D[tmem + dcol] (128 x N) = A planes (K = 16*nkc) * Wu^T, weights streamed in chunks of `kpc` k-blocks
-    auto gemm = [&](const __nv_bfloat16* wu, int nkc, int N, uint32_t dcol) {
-        const int blk_bytes = 2 * N * 16;
-        const int kpc = HEAD_STAGE_BYTES / blk_bytes;
-        const uint32_t idesc = umma_idesc(N);
-        int chunk = 0;
-        for (int kc0 = 0; kc0 < nkc; kc0 += kpc, ++chunk) {
-            const int st = chunk & 1;
-            const int nk = min(kpc, nkc - kc0);
-            if (used[st]) {  // the MMAs that read this stage must have completed
-                mbar_wait(bar0 + 8u * st, ph[st]);
-                ph[st] ^= 1u;
-            }
-            unsigned char* sb = stage0 + (size_t)st * HEAD_STAGE_BYTES;
-            const uint4* src = reinterpret_cast<const uint4*>(wu + (size_t)kc0 * blk_bytes / 2);
-            for (int i = tid; i < nk * blk_bytes / 16; i += HEAD_THREADS)
-                reinterpret_cast<uint4*>(sb)[i] = __ldg(src + i);
+    // consume chunks [c0, c1): wait for the chunk, issue its MMAs, refill the stage with chunk c + HEAD_STAGES
+    auto run_chunks = [&](int c0, int c1, bool g2) {
+        const int N = g2 ? Hp.N2 : HIDDEN, blk = g2 ? blk2 : blk1, kpc = g2 ? kpc2 : kpc1, nkb = g2 ? nkb2 : nkb1;
+        const uint32_t idesc = umma_idesc(N), dcol = g2 ? 256u : 0u;
+        for (int c = c0; c < c1; ++c) {
+            const int st = c % HEAD_STAGES;
+            asm volatile("cp.async.wait_group %0;" ::"n"(HEAD_STAGES - 1) : "memory");  // this thread's part of chunk c
             fence_proxy_async();
             __syncthreads();
+            const int kb = (c - c0) * kpc, nk = min(kpc, nkb - kb);
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 const uint64_t a0 = umma_desc(smem_u32(areg), 128u, 8u);
-                const uint64_t b0 = umma_desc(smem_u32(sb), (uint32_t)N, 8u);
+                const uint64_t b0 = umma_desc(smem_u32(stage0 + (size_t)st * HEAD_STAGE_BYTES), (uint32_t)N, 8u);
                 for (int k = 0; k < nk; ++k)
-                    umma_bf16(tmem + dcol, a0 + (uint64_t)((kc0 + k) * 2 * 2048 >> 4), b0 + (uint64_t)(k * blk_bytes >> 4),
-                              idesc, (kc0 + k) > 0 ? 1u : 0u);
+                    umma_bf16(tmem + dcol, a0 + (uint64_t)((kb + k) * 2 * 2048 >> 4), b0 + (uint64_t)(k * blk >> 4), idesc,
+                              (kb + k) > 0 ? 1u : 0u);
                 umma_commit(bar0 + 8u * st);
-                if (kc0 + nk >= nkc) umma_commit(bar0 + 16u);
+                if (c == c1 - 1) umma_commit(bar_done);
             }
             __syncwarp();
-            used[st] = 1;
+            if (c + HEAD_STAGES < nch) {  // the stage is free once its MMAs have completed
+                mbar_wait(bar0 + 8u * st, (ph_stage >> st) & 1u);
+                ph_stage ^= 1u << st;
+            }
+            issue_chunk(c + HEAD_STAGES);
         }
-        mbar_wait(bar0 + 16u, ph[2]);
-        ph[2] ^= 1u;
+        mbar_wait(bar_done, ph_done);
+        ph_done ^= 1u;
         tc_fence_after();
     };
 
-    gemm(Hp.w1u, Hp.flat / 16, HIDDEN, 0u);
+    run_chunks(0, nch1, false);
     // epilogue 1: hidden = relu(acc + b1) -> bf16 planes (A operand of the logits GEMM) + value head dot product
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     float vacc = 0.f;
@@ -617,9 +639,10 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8 + 1) * 2048 + tid * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
     tc_fence_before();
-    __syncthreads();  // all hidden planes written (gemm() fences them towards the async proxy with the first weight chunk)
-    gemm(Hp.w2u, HIDDEN / 16, Hp.N2, 256u);
-    // epilogue 2: online softmax over this thread's row, then normalised write-out
+    __syncthreads();  // all hidden planes written (run_chunks fences them towards the async proxy before its first MMA)
+    run_chunks(nch1, nch, true);
+    // epilogue 2: online softmax over this thread's row; the normalised row goes to shared memory (the operand planes
+    // and the weight stages are free now) so that the CTA writes its [128][A] block of the policy with coalesced stores
     const int r = row0 + tid;
     float mx = -INFINITY, sum = 0.f;
     for (int c0 = 0; c0 < Hp.A; c0 += 16) {
@@ -636,18 +659,26 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         }
     }
     const float lse = mx + logf(sum);
+    float* s_pol = reinterpret_cast<float*>(hsm);  // [128][A + 1] (odd-ish stride keeps the row writes off one bank)
+    const int ldp = Hp.A | 1;
     for (int c0 = 0; c0 < Hp.A; c0 += 16) {
         float v[16];
         tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
-        if (r < B) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < Hp.A) policy[(size_t)r * Hp.A + c0 + i] = expf(v[i] + __ldg(Hp.b2 + c0 + i) - lse);
-        }
+        for (int i = 0; i < 16; ++i)
+            if (c0 + i < Hp.A) s_pol[tid * ldp + c0 + i] = expf(v[i] + __ldg(Hp.b2 + c0 + i) - lse);
     }
     if (r < B) value[r] = tanhf(vacc + Hp.bv);
     tc_fence_before();
     __syncthreads();
+    {
+        const int nrows = min(128, B - row0);
+        float* dst = policy + (size_t)row0 * Hp.A;
+        for (int i = tid; i < nrows * Hp.A; i += HEAD_THREADS) {
+            const int rr = i / Hp.A, cc = i - rr * Hp.A;
+            dst[i] = s_pol[rr * ldp + cc];
+        }
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
@@ -870,7 +901,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         HeadParams& Hp = n->Hp;
         Hp.flat = P.flat; Hp.A = P.A; Hp.N2 = (P.A + 15) & ~15;
         const int kplanes = (P.flat > HIDDEN ? P.flat : HIDDEN) / 8;
-        n->heads_smem = kplanes * 2048 + 2 * HEAD_STAGE_BYTES;
+        n->heads_smem = std::max(kplanes * 2048 + HEAD_STAGES * HEAD_STAGE_BYTES, 128 * ((P.A | 1) + 1) * 4);
         n->heads_ok = (P.flat % 16 == 0) && Hp.N2 <= 256 && n->heads_smem <= 220 * 1024 && getenv("BPP_NO_TC_HEADS") == nullptr;
         if (n->heads_ok) {
             if (cudaMalloc(&n->d_feat, (size_t)max_batch * P.flat * 2) != cudaSuccess ||
