@@ -485,8 +485,8 @@ def run_real_arm(args):
                                    f"policy/value net (random init, seed 0) in bf16 on tcgen05, {G} lockstep games",
                        "games_per_gpu": G},
             "episodes_per_sec": args.steps * G / (ms * 1e-3), "leaf_evals_per_sec": st["expansions"] / (ms * 1e-3),
-            "lockstep_steps": bm.steps, "gpu_launches": st["launches"] + len(fwd_events),
-            "roofline": {"bound": "tensor", "kernel": "k_net_forward_tc", "achieved": achieved, "peak": peak,
+            "lockstep_steps": bm.steps, "gpu_launches": st["launches"] + 2 * len(fwd_events),  # trunk + heads kernels
+            "roofline": {"bound": "tensor", "kernel": "k_net_forward_tc + k_net_heads_tc", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "flop_per_eval": flops, "evals_per_launch": st["expansions"] / max(1, len(fwd_events)),
                          "kernel_share_of_step": fwd_ms / ms,

@@ -516,6 +516,11 @@ struct HeadParams {
     const float* wv;                      // [256] (bf16-rounded values, as fp32)
     float bv;
 };
+#ifdef BPP_HEADS_PROF  // phase timers of the heads kernel (debug builds: nvcc -DBPP_HEADS_PROF), printed by CTA 0
+#define HP_T(i) t_[i] = clock64()
+#else
+#define HP_T(i)
+#endif
 constexpr int HEAD_THREADS = 128;
 constexpr int HEAD_STAGES = 4;               // ring of weight stages filled by cp.async, drained by the MMAs
 constexpr int HEAD_STAGE_BYTES = 16 * 1024;
@@ -531,8 +536,12 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     extern __shared__ __align__(1024) unsigned char hsm[];
     __shared__ __align__(8) uint64_t s_bar[HEAD_STAGES + 1];  // [s]: MMAs that read stage s are done; [last]: GEMM done
     __shared__ uint32_t s_tmem;
-    __shared__ float s_b1[HIDDEN], s_wv[HIDDEN];
+    __shared__ float s_b1[HIDDEN], s_wv[HIDDEN], s_b2[256], s_inv[128];
     const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef BPP_HEADS_PROF
+    long long t_[8];
+#endif
+    HP_T(0);
     const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
     const int row0 = blockIdx.x * 128;
     if (row0 >= B) return;
@@ -568,6 +577,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     for (int i = tid; i < HIDDEN; i += HEAD_THREADS) {
         s_b1[i] = Hp.b1[i];
         s_wv[i] = Hp.wv[i];
+        s_b2[i] = i < Hp.A ? Hp.b2[i] : 0.f;
     }
     // A operand: features of rows row0..row0+127 (zero beyond the batch), thread = row, loop over planes
     {
@@ -582,6 +592,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    HP_T(1);
     const uint32_t tmem = s_tmem;
     const uint32_t bar0 = smem_u32(&s_bar[0]);
     const uint32_t bar_done = bar0 + 8u * HEAD_STAGES;
@@ -621,6 +632,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     };
 
     run_chunks(0, nch1, false);
+    HP_T(2);
     // epilogue 1: hidden = relu(acc + b1) -> bf16 planes (A operand of the logits GEMM) + value head dot product
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     float vacc = 0.f;
@@ -640,45 +652,63 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     }
     tc_fence_before();
     __syncthreads();  // all hidden planes written (run_chunks fences them towards the async proxy before its first MMA)
+    HP_T(3);
     run_chunks(nch1, nch, true);
-    // epilogue 2: online softmax over this thread's row; the normalised row goes to shared memory (the operand planes
-    // and the weight stages are free now) so that the CTA writes its [128][A] block of the policy with coalesced stores
+    HP_T(4);
+    // epilogue 2 (the operand planes and the weight stages are free now and become the [128][A] policy tile):
+    //   A. thread = row: logits = acc + b2 from TMEM into the tile, running maximum
+    //   B. thread = row: e = exp(logit - max) back into the tile, row sum
+    //   C. whole CTA: policy = e / sum, coalesced stores
     const int r = row0 + tid;
-    float mx = -INFINITY, sum = 0.f;
+    float* s_pol = reinterpret_cast<float*>(hsm);
+    const int ldp = Hp.A | 1;  // odd row stride: the 32 rows of a warp fall into distinct banks
+    float* prow = s_pol + tid * ldp;
+    float mx = -INFINITY;
     for (int c0 = 0; c0 < Hp.A; c0 += 16) {
         float v[16];
         tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             if (c0 + i < Hp.A) {
-                const float l = v[i] + __ldg(Hp.b2 + c0 + i);
-                const float nm = fmaxf(mx, l);
-                sum = sum * __expf(mx - nm) + __expf(l - nm);
-                mx = nm;
+                const float l = v[i] + s_b2[c0 + i];
+                mx = fmaxf(mx, l);
+                prow[c0 + i] = l;
             }
         }
     }
-    const float lse = mx + logf(sum);
-    float* s_pol = reinterpret_cast<float*>(hsm);  // [128][A + 1] (odd-ish stride keeps the row writes off one bank)
-    const int ldp = Hp.A | 1;
-    for (int c0 = 0; c0 < Hp.A; c0 += 16) {
-        float v[16];
-        tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (c0 + i < Hp.A) s_pol[tid * ldp + c0 + i] = expf(v[i] + __ldg(Hp.b2 + c0 + i) - lse);
+    HP_T(5);
+    float sum = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < Hp.A; ++c) {
+        const float e = __expf(prow[c] - mx);
+        sum += e;
+        prow[c] = e;
     }
+    s_inv[tid] = 1.f / sum;
     if (r < B) value[r] = tanhf(vacc + Hp.bv);
     tc_fence_before();
     __syncthreads();
+    HP_T(6);
     {
-        const int nrows = min(128, B - row0);
-        float* dst = policy + (size_t)row0 * Hp.A;
-        for (int i = tid; i < nrows * Hp.A; i += HEAD_THREADS) {
-            const int rr = i / Hp.A, cc = i - rr * Hp.A;
-            dst[i] = s_pol[rr * ldp + cc];
+        const int nrows = min(128, B - row0), lane = tid & 31;
+        for (int rr = warp; rr < nrows; rr += HEAD_THREADS / 32) {  // one row per warp and pass, 8 independent loads
+            const float inv = s_inv[rr];
+            const float* src = s_pol + rr * ldp;
+            float* dst = policy + (size_t)(row0 + rr) * Hp.A;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (lane + 32 * k < Hp.A) ? src[lane + 32 * k] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (lane + 32 * k < Hp.A) dst[lane + 32 * k] = v[k] * inv;
         }
     }
+#ifdef BPP_HEADS_PROF
+    HP_T(7);
+    if (blockIdx.x == 0 && tid == 0)
+        printf("heads cyc: prologue %lld gemm1 %lld epi1 %lld gemm2 %lld logits %lld exp %lld store %lld\n", t_[1] - t_[0],
+               t_[2] - t_[1], t_[3] - t_[2], t_[4] - t_[3], t_[5] - t_[4], t_[6] - t_[5], t_[7] - t_[6]);
+#endif
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
