@@ -67,7 +67,8 @@ def _torch_step(m, ops, recs, items, pis, vs):
     return float(l_pi.detach()), float(l_v.detach()), logp.detach(), v.detach().view(-1)
 
 
-@pytest.mark.parametrize("W,H,N,B", [(15, 15, 10, 64), (15, 15, 10, 37), (20, 20, 10, 48), (9, 12, 5, 130), (15, 15, 10, 512)])
+@pytest.mark.parametrize("W,H,N,B", [(15, 15, 10, 64), (15, 15, 10, 37), (20, 20, 10, 48), (9, 12, 5, 130), (15, 15, 10, 512),
+                                     (15, 15, 10, 1), (15, 15, 10, 2400), (32, 28, 16, 20), (3, 2, 2, 9)])
 def test_gradients_match_autograd(W, H, N, B):
     from resource_packing_self_play_b200.nnet import DeviceLearner
     ops, recs, items, pis, vs = _examples(B, W, H, N, seed=7)
