@@ -521,7 +521,7 @@ struct HeadParams {
 #else
 #define HP_T(i)
 #endif
-constexpr int HEAD_THREADS = 128;
+constexpr int HEAD_THREADS = 256;           // warps w and w + 4 share a TMEM lane quarter (rows) and split the columns
 constexpr int HEAD_STAGES = 4;               // ring of weight stages filled by cp.async, drained by the MMAs
 constexpr int HEAD_STAGE_BYTES = 16 * 1024;
 
@@ -536,8 +536,9 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     extern __shared__ __align__(1024) unsigned char hsm[];
     __shared__ __align__(8) uint64_t s_bar[HEAD_STAGES + 1];  // [s]: MMAs that read stage s are done; [last]: GEMM done
     __shared__ uint32_t s_tmem;
-    __shared__ float s_b1[HIDDEN], s_wv[HIDDEN], s_b2[256], s_inv[128];
+    __shared__ float s_b1[HIDDEN], s_wv[HIDDEN], s_b2[256], s_x0[2][128], s_x1[2][128];
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row_l = tid & 127, hv = tid >> 7;  // row of the tile, column half
 #ifdef BPP_HEADS_PROF
     long long t_[8];
 #endif
@@ -566,6 +567,18 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         }
         asm volatile("cp.async.commit_group;" ::: "memory");  // one group per chunk slot, possibly empty
     };
+    // A operand: features of rows row0..row0+127 (zero beyond the batch): thread = (row, plane parity), 16 bytes per
+    // plane by cp.async, all copies in flight at once
+    {
+        const int r = row0 + row_l;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(feat + (size_t)r * Hp.flat);
+        for (int p = hv; p < Hp.flat / 8; p += 2) {
+            unsigned char* dst = areg + (size_t)p * 2048 + row_l * 16;
+            if (r < B) head_cp16(dst, src + p * 16);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // group 0; the weight chunks follow
+    }
 #pragma unroll
     for (int c = 0; c < HEAD_STAGES; ++c) issue_chunk(c);  // weights are in flight while the rest of the prologue runs
     if (tid <= HEAD_STAGES) mbar_init(smem_u32(&s_bar[tid]), 1);
@@ -579,16 +592,8 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         s_wv[i] = Hp.wv[i];
         s_b2[i] = i < Hp.A ? Hp.b2[i] : 0.f;
     }
-    // A operand: features of rows row0..row0+127 (zero beyond the batch), thread = row, loop over planes
-    {
-        const int r = row0 + tid;
-        const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)r * Hp.flat);
-#pragma unroll 4
-        for (int p = 0; p < Hp.flat / 8; ++p) {
-            const uint4 v = r < B ? __ldg(src + p) : make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(areg + (size_t)p * 2048 + tid * 16) = v;
-        }
-    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(HEAD_STAGES) : "memory");  // the A operand (oldest group) has landed
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -605,7 +610,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         const uint32_t idesc = umma_idesc(N), dcol = g2 ? 256u : 0u;
         for (int c = c0; c < c1; ++c) {
             const int st = c % HEAD_STAGES;
-            asm volatile("cp.async.wait_group %0;" ::"n"(HEAD_STAGES - 1) : "memory");  // this thread's part of chunk c
+            asm volatile("cp.async.wait_group %0;" ::"n"(HEAD_STAGES - 2) : "memory");  // this thread's part of chunk c
             fence_proxy_async();
             __syncthreads();
             const int kb = (c - c0) * kpc, nk = min(kpc, nkb - kb);
@@ -620,11 +625,17 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
                 if (c == c1 - 1) umma_commit(bar_done);
             }
             __syncwarp();
-            if (c + HEAD_STAGES < nch) {  // the stage is free once its MMAs have completed
-                mbar_wait(bar0 + 8u * st, (ph_stage >> st) & 1u);
-                ph_stage ^= 1u << st;
+            // refill the stage of the PREVIOUS chunk (its MMAs were issued one iteration ago and are normally complete
+            // by now, so this wait does not stall) with chunk c - 1 + HEAD_STAGES
+            const int pc = c - 1;
+            if (pc >= 0 && pc + HEAD_STAGES < nch) {
+                const int ps = pc % HEAD_STAGES;
+                mbar_wait(bar0 + 8u * ps, (ph_stage >> ps) & 1u);
+                ph_stage ^= 1u << ps;
+                issue_chunk(pc + HEAD_STAGES);
+            } else {
+                asm volatile("cp.async.commit_group;" ::: "memory");  // keep one group per iteration
             }
-            issue_chunk(c + HEAD_STAGES);
         }
         mbar_wait(bar_done, ph_done);
         ph_done ^= 1u;
@@ -634,9 +645,9 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     run_chunks(0, nch1, false);
     HP_T(2);
     // epilogue 1: hidden = relu(acc + b1) -> bf16 planes (A operand of the logits GEMM) + value head dot product
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float vacc = 0.f;
-    for (int c0 = 0; c0 < HIDDEN; c0 += 16) {
+    for (int c0 = hv * (HIDDEN / 2); c0 < (hv + 1) * (HIDDEN / 2); c0 += 16) {
         float v[16];
         tmem_ld16(lane_base + (uint32_t)c0, v);
         uint32_t pk[8];
@@ -647,52 +658,58 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
             vacc = fmaf(bf16_lo(pk[i]), s_wv[c0 + 2 * i], vacc);
             vacc = fmaf(bf16_hi(pk[i]), s_wv[c0 + 2 * i + 1], vacc);
         }
-        *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8) * 2048 + tid * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8 + 1) * 2048 + tid * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8) * 2048 + row_l * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8 + 1) * 2048 + row_l * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
+    s_x0[hv][row_l] = vacc;  // the value head's dot product: one half per thread
     tc_fence_before();
     __syncthreads();  // all hidden planes written (run_chunks fences them towards the async proxy before its first MMA)
     HP_T(3);
     run_chunks(nch1, nch, true);
     HP_T(4);
     // epilogue 2 (the operand planes and the weight stages are free now and become the [128][A] policy tile):
-    //   A. thread = row: logits = acc + b2 from TMEM into the tile, running maximum
-    //   B. thread = row: e = exp(logit - max) back into the tile, row sum
-    //   C. whole CTA: policy = e / sum, coalesced stores
-    const int r = row0 + tid;
+    //   A. thread = (row, column half): logits = acc + b2 from TMEM into the tile, maximum of the half
+    //   B. thread = (row, column half): e = exp(logit - row max) back into the tile, sum of the half
+    //   C. whole CTA: policy = e / row sum, one row per warp and pass, coalesced stores
+    const int r = row0 + row_l;
+    if (hv == 0 && r < B) value[r] = tanhf(s_x0[0][row_l] + s_x0[1][row_l] + Hp.bv);
     float* s_pol = reinterpret_cast<float*>(hsm);
     const int ldp = Hp.A | 1;  // odd row stride: the 32 rows of a warp fall into distinct banks
-    float* prow = s_pol + tid * ldp;
+    float* prow = s_pol + row_l * ldp;
+    const int csplit = min(Hp.A, ((Hp.A / 2 + 15) >> 4) << 4);
+    const int cbeg = hv ? csplit : 0, cend = hv ? Hp.A : csplit;
     float mx = -INFINITY;
-    for (int c0 = 0; c0 < Hp.A; c0 += 16) {
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
         float v[16];
         tmem_ld16(lane_base + 256u + (uint32_t)c0, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            if (c0 + i < Hp.A) {
+            if (c0 + i < cend) {
                 const float l = v[i] + s_b2[c0 + i];
                 mx = fmaxf(mx, l);
                 prow[c0 + i] = l;
             }
         }
     }
+    s_x1[hv][row_l] = mx;
+    tc_fence_before();
+    __syncthreads();
     HP_T(5);
+    mx = fmaxf(s_x1[0][row_l], s_x1[1][row_l]);
     float sum = 0.f;
 #pragma unroll 4
-    for (int c = 0; c < Hp.A; ++c) {
+    for (int c = cbeg; c < cend; ++c) {
         const float e = __expf(prow[c] - mx);
         sum += e;
         prow[c] = e;
     }
-    s_inv[tid] = 1.f / sum;
-    if (r < B) value[r] = tanhf(vacc + Hp.bv);
-    tc_fence_before();
+    s_x0[hv][row_l] = sum;  // (the value head has consumed s_x0 before the barrier above)
     __syncthreads();
     HP_T(6);
     {
         const int nrows = min(128, B - row0), lane = tid & 31;
         for (int rr = warp; rr < nrows; rr += HEAD_THREADS / 32) {  // one row per warp and pass, 8 independent loads
-            const float inv = s_inv[rr];
+            const float inv = __fdividef(1.f, s_x0[0][rr] + s_x0[1][rr]);
             const float* src = s_pol + rr * ldp;
             float* dst = policy + (size_t)(row0 + rr) * Hp.A;
             float v[8];
