@@ -879,10 +879,14 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         const int cin16_0 = (P.Cin + 15) / 16;
         auto plan = [&](bpptc::TcParams& T, bool x3, int cap_bytes, int& ctas_out) -> bool {
             const int f = x3 ? 2 : 1;
-            for (int S = 8; S >= 1; --S) {
+            // the two-CTAs-per-SM instantiation holds at most 4 leaves per CTA
+            for (int S = (!x3 && cap_bytes <= 113 * 1024) ? 4 : 8; S >= 1; --S) {
                 for (int l = 0; l < 4; ++l) {
                     bpptc::Level& L = T.lv[l];
-                    L.h = P.hs[l]; L.w = P.ws[l]; L.hp = L.h + 2; L.wp = L.w + 2; L.P = L.hp * L.wp;
+                    // shared halos: one zero column between consecutive grid rows (the right halo of row y IS the left
+                    // halo of row y+1) and one zero row between consecutive samples, so a sample is (h+1) x (w+1) rows
+                    // instead of (h+2) x (w+2); the guards in front of the first and behind the last sample stay zero
+                    L.h = P.hs[l]; L.w = P.ws[l]; L.hp = L.h + 1; L.wp = L.w + 1; L.P = L.hp * L.wp;
                     L.guard = (L.wp + 1 + 7) & ~7;
                     L.RT = L.guard + S * L.P + L.guard;
                     L.ntiles = (S * L.P + 127) / 128;

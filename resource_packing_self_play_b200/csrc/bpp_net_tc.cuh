@@ -3,8 +3,11 @@
 // One CTA evaluates a group of S leaves through the WHOLE network without touching HBM in between: activations live
 // in shared memory in the UMMA canonical K-major (no-swizzle) layout, accumulators in tensor memory.
 //
-// Convolution as implicit GEMM without im2col.  At spatial level l every sample is a zero-haloed (h+2) x (w+2) grid and
-// the S grids are concatenated into one long ROW axis (row = one padded pixel).  Activations are stored channels-last
+// Convolution as implicit GEMM without im2col.  At spatial level l every sample is a zero-haloed grid and the S grids are
+// concatenated into one long ROW axis (row = one padded pixel).  Halos are SHARED: a grid row is w+1 rows long (its zero
+// column is the right halo of the grid row above and the left halo of its own), and a sample is h+1 grid rows (its zero
+// row is the bottom halo of the previous sample), so a sample costs (h+1)(w+1) rows instead of (h+2)(w+2) - 29 % fewer
+// MMAs and epilogue rows at 15x15 (256 rows per sample at level 0: a 128-row tile is exactly half a sample).  Activations are stored channels-last
 // in 8-channel planes: plane p holds, for every row, the 16 bytes of channels 8p..8p+7 — exactly the 8-row x 16-byte
 // "core matrix" tiling the tensor core reads for a K-major operand (SBO = 128 B between 8-row groups, LBO = plane
 // stride between the two 8-channel halves of a K=16 slice).  For the 3x3 tap (dy, dx) the A operand of output rows
