@@ -227,8 +227,10 @@ k_net_forward(NetParams P, int Bmax, const int32_t* __restrict__ count_dev, cons
 // tcgen05 forward: one CTA = S leaves through the whole network (see bpp_net_tc.cuh)
 // NS = leaves per CTA the head accumulators are unrolled for (4 or 8); X3 = split-bf16 mode (hi + lo halves, 3 MMAs per
 // product, fp32 heads) for networks whose dynamic range exceeds plain bf16
-template <int NS, bool X3>
-__global__ void __launch_bounds__(bpptc::TC_THREADS, ((NS <= 4 && !X3) ? 2 : 1))
+// TRUNK = the kernel ends at relu(flatten) (feat_out) and the in-kernel CUDA-core heads are compiled out; MINB = CTAs per
+// SM the register allocation is bounded for
+template <int NS, bool X3, bool TRUNK = false, int MINB = ((NS <= 4 && !X3) ? 2 : 1)>
+__global__ void __launch_bounds__(bpptc::TC_THREADS, MINB)
 k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__ count_dev,
                  const uint32_t* __restrict__ recs, const int32_t* __restrict__ game,
                  const int32_t* __restrict__ items_wh, float* __restrict__ policy, float* __restrict__ value,
@@ -286,25 +288,41 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         }
         __syncthreads();
         {
-            const int hw = P.H * P.W, nplanes = 2 * cin16_0;
-            for (int idx = tid; idx < nvalid * hw * nplanes; idx += TC_THREADS) {
-                const int p = idx / (nvalid * hw);
-                int r = idx - p * nvalid * hw;
-                const int j = r / hw;
-                r -= j * hw;
-                const int y = r / P.W, x = r - y * P.W;
+            // one thread builds half a grid row of one 8-channel plane: the 8 channels' column masks of that row once, then
+            // one 16-byte pixel per step.  The lanes of a warp walk their rows from different starting columns, so that
+            // their simultaneous 16-byte stores fall into different bank groups (rows are wp * 16 bytes apart).
+            const int nplanes = 2 * cin16_0, rows = nvalid * P.H;
+            const int xh = (P.W + 1) >> 1;
+            const uint32_t mrows = fdiv_magic((uint32_t)rows);
+            for (int idx = tid; idx < 2 * nplanes * rows; idx += TC_THREADS) {
+                const int hp = fdiv(idx, mrows);
+                int r = idx - hp * rows;
+                const int j = fdiv(r, T.mH), y = r - j * P.H;
+                const int half = hp >= nplanes ? 1 : 0, p = hp - half * nplanes;
                 const uint32_t rem = s_rec[j][BPP_REC_REM];
-                uint32_t w[4] = {0, 0, 0, 0};
+                uint32_t m[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int c = p * 8 + k;
-                    bool on = false;
-                    if (c == 0) on = (s_rec[j][y] >> x) & 1u;
-                    else if (c <= P.N) on = ((rem >> (c - 1)) & 1u) && y < s_it[j][c - 1][1] && x < s_it[j][c - 1][0];
-                    if (on) w[k >> 1] |= (k & 1) ? 0x3f800000u : 0x00003f80u;  // bf16 1.0
+                    m[k] = 0;
+                    if (c == 0) m[k] = s_rec[j][y];
+                    else if (c <= P.N && ((rem >> (c - 1)) & 1u) && y < s_it[j][c - 1][1]) {
+                        const int iw = s_it[j][c - 1][0];
+                        m[k] = iw >= 32 ? 0xffffffffu : (1u << iw) - 1u;
+                    }
                 }
-                const size_t row = (size_t)L0.guard + (size_t)j * L0.P + (size_t)(y + 1) * L0.wp + (x + 1);
-                *reinterpret_cast<uint4*>(regA + ((size_t)p * L0.RT + row) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                const int x0 = half ? xh : 0, n = half ? P.W - xh : xh;
+                uint4* dst = reinterpret_cast<uint4*>(regA) + (size_t)p * L0.RT + L0.guard + j * L0.P + (y + 1) * L0.wp + 1 + x0;
+                int i = n > 0 ? lane % n : 0;
+                for (int step = 0; step < n; ++step) {
+                    const int x = x0 + i;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        w[q] = (((m[2 * q] >> x) & 1u) | (((m[2 * q + 1] >> x) & 1u) << 16)) * 0x3f80u;  // bf16 1.0 pairs
+                    dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                    if (++i == n) i = 0;
+                }
             }
         }
         __syncthreads();
@@ -360,13 +378,14 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         float* part = lg + NS * P.A;                              // [2][NS][256] / [2][NS][A] partial sums
         const int hw3 = L3.h * L3.w;
         const size_t raw_lo3 = (size_t)(P.conv[NCONV - 1].co / 8) * L3.RT * 16;
-        if (!X3 && feat_out) {
+        if (TRUNK || (!X3 && feat_out)) {
             // trunk only: relu(flatten(x)) goes to HBM as bf16 [B][flat]; the two FC heads run as real GEMMs over the
             // whole batch in k_net_heads_tc (128-leaf M tiles) instead of per group of S leaves here
+            const uint32_t mflat = fdiv_magic((uint32_t)P.flat);
             for (int idx = tid; idx < nvalid * P.flat; idx += TC_THREADS) {
-                const int j = idx / P.flat, f = idx - j * P.flat;
-                const int c = f / hw3, q = f - c * hw3;
-                const int y = q / L3.w, x = q - y * L3.w;
+                const int j = fdiv(idx, mflat), f = idx - j * P.flat;
+                const int c = fdiv(f, L3.mhw), q = f - c * hw3;
+                const int y = fdiv(q, L3.mw), x = q - y * L3.w;
                 const size_t row = (size_t)L3.guard + (size_t)j * L3.P + (size_t)(y + 1) * L3.wp + (x + 1);
                 const uint16_t e = *(reinterpret_cast<const uint16_t*>(raw + ((size_t)(c >> 3) * L3.RT + row) * 16) + (c & 7));
                 reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (e & 0x8000u) ? (uint16_t)0 : e;
@@ -375,6 +394,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             TC_PROF(6, tq);
             continue;
         }
+        if (TRUNK) continue;
         for (int idx = tid; idx < NS * P.flat; idx += TC_THREADS) {
             const int j = idx / P.flat, f = idx - j * P.flat;
             float v = 0.f;
@@ -729,14 +749,6 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
-// shared-memory budget of the tensor-core kernel: ~110 KB lets two CTAs share an SM so that one CTA's epilogue overlaps
-// the other's MMAs (BPP_TC_SMEM_KB overrides, for experiments)
-int tc_smem_cap() {
-    const char* e = getenv("BPP_TC_SMEM_KB");
-    const int kb = e ? atoi(e) : 110;
-    return kb * 1024;
-}
-
 uint16_t f32_to_bf16_rne(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -877,16 +889,19 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         }
         n->umma_elems = uoff;
         const int cin16_0 = (P.Cin + 15) / 16;
-        auto plan = [&](bpptc::TcParams& T, bool x3, int cap_bytes, int& ctas_out) -> bool {
+        // ctas_want = CTAs per SM the plan is made for (bf16 mode: 2 or 3; they share the SM's 227 KB of shared memory,
+        // its registers and its 512 TMEM columns); the largest group size S whose buffers fit is taken
+        auto plan = [&](bpptc::TcParams& T, bool x3, int cap_bytes, int ctas_want, int& ctas_out) -> bool {
             const int f = x3 ? 2 : 1;
-            // the two-CTAs-per-SM instantiation holds at most 4 leaves per CTA
-            for (int S = (!x3 && cap_bytes <= 113 * 1024) ? 4 : 8; S >= 1; --S) {
+            for (int S = ctas_want >= 2 ? 4 : 8; S >= 1; --S) {  // the multi-CTA instantiations hold at most 4 leaves
                 for (int l = 0; l < 4; ++l) {
                     bpptc::Level& L = T.lv[l];
                     // shared halos: one zero column between consecutive grid rows (the right halo of row y IS the left
                     // halo of row y+1) and one zero row between consecutive samples, so a sample is (h+1) x (w+1) rows
                     // instead of (h+2) x (w+2); the guards in front of the first and behind the last sample stay zero
                     L.h = P.hs[l]; L.w = P.ws[l]; L.hp = L.h + 1; L.wp = L.w + 1; L.P = L.hp * L.wp;
+                    L.mP = bpptc::fdiv_magic((uint32_t)L.P); L.mwp = bpptc::fdiv_magic((uint32_t)L.wp);
+                    L.mhw = bpptc::fdiv_magic((uint32_t)(L.h * L.w)); L.mw = bpptc::fdiv_magic((uint32_t)L.w);
                     L.guard = (L.wp + 1 + 7) & ~7;
                     L.RT = L.guard + S * L.P + L.guard;
                     L.ntiles = (S * L.P + 127) / 128;
@@ -898,29 +913,38 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                     b = std::max(b, (long long)f * planes * T.lv[s2].RT * 16);
                 }
                 const int NSs = S <= 4 ? 4 : 8;
-                b = std::max(b, (long long)NSs * (P.flat + 4 * HIDDEN + 3 * (P.A + 1)) * 4);
+                if (x3 || ctas_want < 2)  // in-kernel CUDA-core heads need their scratch
+                    b = std::max(b, (long long)NSs * (P.flat + 4 * HIDDEN + 3 * (P.A + 1)) * 4);
+                // the last tile's shifted windows over-read up to 128 + wp + 1 rows behind region A: region B must cover that
+                b = std::max(b, (long long)(128 + T.lv[0].wp + 8) * 16);
                 T.S = S;
-                T.regA_bytes = (int)((a + 1023) & ~1023LL);
-                T.regB_bytes = (int)((b + 4096 + 1023) & ~1023LL);  // + slack: the last tile's shifted windows over-read
-                T.wbuf_bytes = (f * wmax + 256 + 1023) & ~1023;     // + the layer's bias behind the weights
+                T.regA_bytes = (int)((a + 127) & ~127LL);
+                T.regB_bytes = (int)((b + 127) & ~127LL);
+                T.wbuf_bytes = (f * wmax + 256 + 127) & ~127;     // + the layer's bias behind the weights
                 T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
                 if (T.smem_bytes <= cap_bytes && T.lv[0].RT < 16384) {
-                    // CTAs that fit on one SM (227 KB shared memory, 1 KB reserved per CTA) share the 512 TMEM columns
-                    int ctas = (227 * 1024) / (T.smem_bytes + 2048);
-                    if (ctas > 2) ctas = 2;
-                    if (S > 4 || x3) ctas = 1;
-                    if (ctas < 1) ctas = 1;
-                    T.tmem_cols = ctas == 2 ? 256 : 512;
-                    ctas_out = ctas;
+                    T.tmem_cols = ctas_want >= 3 ? 128 : ctas_want == 2 ? 256 : 512;
+                    ctas_out = ctas_want;
                     return true;
                 }
             }
             return false;
         };
-        n->tc_ok = plan(T, false, tc_smem_cap(), n->ctas_per_sm);
+        {
+            // 227 KB per SM, 1 KB reserved per CTA, ~3.2 KB static shared memory per CTA
+            const char* e = getenv("BPP_TC_CTAS");
+            int want = e ? atoi(e) : 2;
+            if (want < 1 || want > 3) want = 2;
+            const int hk = (P.flat > HIDDEN ? P.flat : HIDDEN) / 8;
+            const int hsm = std::max(hk * 2048 + HEAD_STAGES * HEAD_STAGE_BYTES, 128 * ((P.A | 1) + 1) * 4);
+            const bool heads_possible = (P.flat % 16 == 0) && ((P.A + 15) & ~15) <= 256 && hsm <= 220 * 1024 &&
+                                        getenv("BPP_NO_TC_HEADS") == nullptr;
+            if (!heads_possible) want = 1;  // the multi-CTA instantiations are trunk-only
+            n->tc_ok = plan(T, false, (227 * 1024) / want - 1024 - 3328, want, n->ctas_per_sm);
+        }
         n->T3 = T;
         int c3 = 1;
-        n->tc3_ok = plan(n->T3, true, 220 * 1024, c3);
+        n->tc3_ok = plan(n->T3, true, 220 * 1024, 1, c3);
     }
     n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
     if (cudaFuncSetAttribute(k_net_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
@@ -930,7 +954,11 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         (n->tc_ok && (cudaFuncSetAttribute(k_net_forward_tc<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            n->T.smem_bytes) != cudaSuccess ||
                       cudaFuncSetAttribute(k_net_forward_tc<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           n->T.smem_bytes) != cudaSuccess)) ||
+                                           n->T.smem_bytes) != cudaSuccess ||
+                      cudaFuncSetAttribute(k_net_forward_tc<4, false, true, 2>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, n->T.smem_bytes) != cudaSuccess ||
+                      cudaFuncSetAttribute(k_net_forward_tc<4, false, true, 3>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, n->T.smem_bytes) != cudaSuccess)) ||
         (n->tc3_ok && (cudaFuncSetAttribute(k_net_forward_tc<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             n->T3.smem_bytes) != cudaSuccess ||
                        cudaFuncSetAttribute(k_net_forward_tc<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -942,6 +970,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
     n->T.wts_umma = n->d_wts_umma;
     n->T.wts_umma_lo = n->d_wts_umma_lo;
     n->T.A_pad = (P.A + 1) & ~1;
+    n->T.mH = bpptc::fdiv_magic((uint32_t)P.H);
     if (cudaMalloc(&n->d_wts_logits_pad, (size_t)HIDDEN * n->T.A_pad * 2) != cudaSuccess) {
         cudaGetLastError();
         delete n;
@@ -1150,7 +1179,13 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int cap = 148 * n->ctas_per_sm;
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
-        if (n->T.S <= 4)
+        if (fo && n->T.S <= 4 && n->ctas_per_sm == 3)
+            k_net_forward_tc<4, false, true, 3><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
+                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
+        else if (fo && n->T.S <= 4)
+            k_net_forward_tc<4, false, true, 2><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
+                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
+        else if (n->T.S <= 4)
             k_net_forward_tc<4, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
                 n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
         else

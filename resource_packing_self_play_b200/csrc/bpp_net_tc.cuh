@@ -32,7 +32,13 @@ constexpr int MAX_BARS = 16;
 
 struct Level {
     int h, w, hp, wp, P, guard, RT, ntiles;  // RT = rows of one plane = guard + S*P + guard
+    uint32_t mP, mwp, mhw, mw;               // division magics (fdiv) of P, wp, h*w, w
 };
+
+// n / d for n, d < 65536 with the host-computed magic m = ceil(2^32 / d) (0 encodes d = 1): one IMAD.HI instead of the
+// ~35-instruction software division; index math was a quarter of the kernel's instructions before
+__host__ __device__ __forceinline__ uint32_t fdiv_magic(uint32_t d) { return d <= 1 ? 0u : 0xffffffffu / d + 1u; }
+__device__ __forceinline__ int fdiv(int n, uint32_t m) { return m ? (int)__umulhi((uint32_t)n, m) : n; }
 
 struct TcParams {
     int S;                 // leaves per CTA
@@ -46,6 +52,7 @@ struct TcParams {
     int lay_n16[15];       // 16-byte chunks of each layer's staged weights (9 * cin16 * 2 * cout)
     const __nv_bfloat16* wts_umma;
     const __nv_bfloat16* wts_umma_lo;      // bf16(w - bf16(w)): low halves for the split-bf16 (x3) mode
+    uint32_t mH;                           // fdiv magic of the bin height
     int A_pad;                             // action size rounded up to even
     const __nv_bfloat16* wts_logits_pad;   // logits weights [256][A_pad] (bf16x2 loads)
 };
@@ -297,8 +304,8 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         TC_PROF(3, tp);
         // ---- epilogue: thread tid owns output row t*128 + tid
         const int rl = t * 128 + lt;
-        const int j = rl / L.P, q = rl - j * L.P;
-        const int yp = q / L.wp, xp = q - yp * L.wp;
+        const int j = fdiv(rl, L.mP), q = rl - j * L.P;
+        const int yp = fdiv(q, L.mwp), xp = q - yp * L.wp;
         const bool interior = rl < rows_valid && yp >= 1 && yp <= L.h && xp >= 1 && xp <= L.w;
         const size_t rowb = (size_t)(L.guard + rl) * 16;
         const uint32_t taddr = cx.tmem + ((uint32_t)(((lt >> 5) & 3) * 32) << 16) + (uint32_t)(b * cout);
@@ -375,12 +382,13 @@ __device__ __forceinline__ void pool_level_x3(const Level& La, const Level& Lb, 
                                               unsigned char* actA, uint32_t act_lo) {
     const int per = Lb.h * Lb.w;
     const int total = nvalid * per * planes;
+    const uint32_t mnp = fdiv_magic((uint32_t)(nvalid * per));
     for (int idx = threadIdx.x; idx < total; idx += TC_THREADS) {
-        const int p = idx / (nvalid * per);
+        const int p = fdiv(idx, mnp);
         int r = idx - p * nvalid * per;
-        const int j = r / per;
+        const int j = fdiv(r, Lb.mhw);
         r -= j * per;
-        const int oy = r / Lb.w, ox = r - oy * Lb.w;
+        const int oy = fdiv(r, Lb.mw), ox = r - oy * Lb.w;
         float m[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
@@ -418,12 +426,13 @@ __device__ __forceinline__ void pool_level(const Level& La, const Level& Lb, int
     const uint32_t NEG = 0xff80ff80u;  // bf16 -inf pair
     const int per = Lb.h * Lb.w;
     const int total = nvalid * per * planes;
+    const uint32_t mnp = fdiv_magic((uint32_t)(nvalid * per));
     for (int idx = threadIdx.x; idx < total; idx += TC_THREADS) {
-        const int p = idx / (nvalid * per);
+        const int p = fdiv(idx, mnp);
         int r = idx - p * nvalid * per;
-        const int j = r / per;
+        const int j = fdiv(r, Lb.mhw);
         r -= j * per;
-        const int oy = r / Lb.w, ox = r - oy * Lb.w;
+        const int oy = fdiv(r, Lb.mw), ox = r - oy * Lb.w;
         uint4 m = make_uint4(NEG, NEG, NEG, NEG);
         for (int dy = -1; dy <= 1; ++dy) {
             const int yy = 2 * oy + dy;
