@@ -348,6 +348,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
             unsigned char* actA = regA + bs;
             unsigned char* actB = regA + 2 * bs;
             zero_bytes(regA, (int)(3 * bs));
+            if (!X3) pool_pad_tail(La, nvalid, planes, regB);
             __syncthreads();
             if (X3) pool_level_x3(La, Lb, nvalid, planes, regB, t_lo, raw, (uint32_t)pb, actA, (uint32_t)pb);
             else pool_level(La, Lb, nvalid, planes, regB, raw, actA);

@@ -309,12 +309,24 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         const bool interior = rl < rows_valid && yp >= 1 && yp <= L.h && xp >= 1 && xp <= L.w;
         const size_t rowb = (size_t)(L.guard + rl) * 16;
         const uint32_t taddr = cx.tmem + ((uint32_t)(((lt >> 5) & 3) * 32) << 16) + (uint32_t)(b * cout);
+        // EPI_CONV (bf16 mode): the halo rows of T are set to -inf, the max-pool's padding value, so that the pooling
+        // pass reads its 3x3 windows without bounds checks (rows up to one grid row behind the last sample)
+        const bool pad_row = !X3 && kind == EPI_CONV && !interior && rl < rows_valid + L.wp + 1;
         for (int c0 = 0; c0 < cout; c0 += 16) {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);  // warp-collective: executed by every lane
+            if (pad_row) {
+                const uint4 ninf = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+                *reinterpret_cast<uint4*>(out0 + (size_t)(c0 >> 3) * plane_b + rowb) = ninf;
+                *reinterpret_cast<uint4*>(out0 + (size_t)((c0 >> 3) + 1) * plane_b + rowb) = ninf;
+            }
             if (interior) {
+                const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += s_bias[c0 + i];
+                for (int i = 0; i < 4; ++i) {
+                    const float4 bb = b4[i];
+                    v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                }
 #pragma unroll
                 for (int hp8 = 0; hp8 < 2; ++hp8) {
                     const int plane = (c0 >> 3) + hp8;
@@ -421,9 +433,10 @@ __device__ __forceinline__ void pool_level_x3(const Level& La, const Level& Lb, 
     }
 }
 
+// bf16 mode: the halo rows of T hold -inf (written by the EPI_CONV epilogue and pool_pad_tail), so every 3x3 window is
+// read without bounds checks: window row yy = 2*oy + dy maps to grid row yy + 1, i.e. 2*oy .. 2*oy + 2
 __device__ __forceinline__ void pool_level(const Level& La, const Level& Lb, int nvalid, int planes,
                                            const unsigned char* Tbuf, unsigned char* raw, unsigned char* actA) {
-    const uint32_t NEG = 0xff80ff80u;  // bf16 -inf pair
     const int per = Lb.h * Lb.w;
     const int total = nvalid * per * planes;
     const uint32_t mnp = fdiv_magic((uint32_t)(nvalid * per));
@@ -433,22 +446,32 @@ __device__ __forceinline__ void pool_level(const Level& La, const Level& Lb, int
         const int j = fdiv(r, Lb.mhw);
         r -= j * per;
         const int oy = fdiv(r, Lb.mw), ox = r - oy * Lb.w;
-        uint4 m = make_uint4(NEG, NEG, NEG, NEG);
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = 2 * oy + dy;
-            if (yy < 0 || yy >= La.h) continue;
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int xx = 2 * ox + dx;
-                if (xx < 0 || xx >= La.w) continue;
-                const size_t row = (size_t)La.guard + (size_t)j * La.P + (size_t)(yy + 1) * La.wp + (xx + 1);
-                const uint4 v = *reinterpret_cast<const uint4*>(Tbuf + ((size_t)p * La.RT + row) * 16);
-                m = make_uint4(max_bf16x2(m.x, v.x), max_bf16x2(m.y, v.y), max_bf16x2(m.z, v.z), max_bf16x2(m.w, v.w));
-            }
-        }
+        const uint4* src = reinterpret_cast<const uint4*>(Tbuf) + (size_t)p * La.RT + La.guard + j * La.P +
+                           (2 * oy) * La.wp + 2 * ox;
+        uint4 v[9];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) v[dy * 3 + dx] = src[dy * La.wp + dx];
+        uint4 m = v[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k)
+            m = make_uint4(max_bf16x2(m.x, v[k].x), max_bf16x2(m.y, v[k].y), max_bf16x2(m.z, v[k].z), max_bf16x2(m.w, v[k].w));
         const size_t orow = (size_t)Lb.guard + (size_t)j * Lb.P + (size_t)(oy + 1) * Lb.wp + (ox + 1);
         *reinterpret_cast<uint4*>(raw + ((size_t)p * Lb.RT + orow) * 16) = m;
         *reinterpret_cast<uint4*>(actA + ((size_t)p * Lb.RT + orow) * 16) =
             make_uint4(relu_bf16x2(m.x), relu_bf16x2(m.y), relu_bf16x2(m.z), relu_bf16x2(m.w));
+    }
+}
+
+// the grid row behind the last present sample (its bottom halo) belongs to no processed tile when the samples end on a
+// tile boundary: set it to -inf here (runs between the convolution's final barrier and the barrier before pool_level)
+__device__ __forceinline__ void pool_pad_tail(const Level& La, int nvalid, int planes, unsigned char* Tbuf) {
+    const uint4 ninf = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+    const int n = La.wp + 1;
+    for (int idx = threadIdx.x; idx < planes * n; idx += TC_THREADS) {
+        const int p = idx / n, k = idx - p * n;
+        reinterpret_cast<uint4*>(Tbuf)[(size_t)p * La.RT + La.guard + nvalid * La.P + k] = ninf;
     }
 }
 
