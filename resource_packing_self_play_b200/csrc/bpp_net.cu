@@ -413,7 +413,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         }
         __syncthreads();
         const int hh = tid >> 7, ot = tid & 127;  // input half, output pair
-        {   // hidden layer: thread -> outputs 2*ot, 2*ot+1 over one half of the inputs (coalesced bf16x2 loads)
+        if (tid < TC_WORKERS) {   // hidden layer: thread -> outputs 2*ot, 2*ot+1 over one half of the inputs (coalesced bf16x2 loads)
             const int o = 2 * ot;
             float a0[NS], a1[NS];
 #pragma unroll
@@ -450,7 +450,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         for (int idx = tid; idx < NS * HIDDEN; idx += TC_THREADS)
             hid[idx] = act_round<X3>(fmaxf(part[idx] + part[NS * HIDDEN + idx], 0.f));
         __syncthreads();
-        if (2 * ot < T.A_pad) {  // logits: padded [256][A_pad] copy of the weights, outputs 2*ot, 2*ot+1
+        if (tid < TC_WORKERS && 2 * ot < T.A_pad) {  // logits: padded [256][A_pad] copy of the weights, outputs 2*ot, 2*ot+1
             const int o = 2 * ot;
             float a0[NS], a1[NS];
             const float b0 = hh ? 0.f : P.bias[P.b_logits_off + o];

@@ -27,7 +27,8 @@
 
 namespace bpptc {
 
-constexpr int TC_THREADS = 256;   // 8 warps: warps w and w+4 own the same TMEM lane quarter and alternate output tiles
+constexpr int TC_WORKERS = 256;   // 8 epilogue warps: warps w and w+4 own the same TMEM lane quarter and share the tiles
+constexpr int TC_THREADS = 288;   // + warp 8, which issues the MMAs of a layer tile by tile, in order
 constexpr int MAX_BARS = 16;
 
 struct Level {
@@ -177,7 +178,7 @@ __device__ __forceinline__ void split8(const float* u, uint4& h4, uint4& l4) {
 // Register prefetch of the NEXT layer's weights and bias: the global loads are issued at the start of a layer and are
 // consumed (stored to shared memory) at the start of the next one, so their L2 latency hides behind the layer's MMAs
 // and epilogues without a second shared-memory weight buffer.
-constexpr int WPRE = 5;  // ceil(18,432 B / 16 B / 256 threads)
+constexpr int WPRE = 4;  // 18,432 B / 16 B / 288 threads
 struct WPre {
     uint4 w[WPRE];
     float b;
@@ -256,27 +257,24 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
     if (tpp > MAX_BARS) tpp = MAX_BARS;
     for (int t0 = 0; t0 < nt; t0 += tpp) {
       const int nb = min(tpp, nt - t0);
-      // ---- issue: ONE thread queues the MMAs of all nb tiles (each tile into its own TMEM columns, each followed by a
-      // commit to its own mbarrier); the tensor core drains the queue while the 128 threads run the epilogues below
-      // the tiles of a pass are issued by DIFFERENT warps (tile b by warp b mod 8, one elected lane each): a single
-      // thread needs ~65 cycles of dependent uniform-datapath work per tcgen05.mma, which - not the tensor pipe - paced
-      // the MMA phase when one thread issued everything
-      if (elect_one()) {  // warp-uniform: every warp elects one lane; elect.sync avoids a per-thread serialisation loop
+      // ---- issue: one elected lane of the issuer warp queues the MMAs of all nb tiles IN TILE ORDER (each tile into its
+      // own TMEM columns, followed by a commit to its own mbarrier): tile 0 completes after its own 9 * cin16 MMAs and
+      // its epilogue runs while the tensor core works on the later tiles.  (Issuing tile b from warp b, as an earlier
+      // version did, interleaves the tiles in the queue: they all complete together at the end and nothing overlaps.)
+      if (tid >= TC_WORKERS) {
+       if (elect_one()) {
         tc_fence_after();
         const uint64_t b0 = umma_desc(w_base, (uint32_t)cout, 8u);
         const uint64_t a00 = umma_desc(a_base + (uint32_t)L.guard * 16u, (uint32_t)L.RT, 8u);
         const uint32_t ahi = (uint32_t)(a00 >> 32), bhi = (uint32_t)(b0 >> 32), blo0 = (uint32_t)b0;
         const uint32_t a_kc = 2u * plane_b >> 4, b_blk = (uint32_t)(2 * cout), b_tap = b_blk * (uint32_t)cin16;
         const uint32_t a_lo16 = in_lo_off >> 4, w_lo16 = (uint32_t)wbytes >> 4;
-        for (int b = tid >> 5; b < nb; b += TC_THREADS / 32) {
+        for (int b = 0; b < nb; ++b) {
             const uint32_t alo0 = (uint32_t)a00 + (uint32_t)(t0 + b) * 128u;  // +128 rows (16-byte units) per tile
             const uint32_t d = cx.tmem + (uint32_t)(b * cout);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 uint32_t at = alo0 + (uint32_t)((tap / 3 - 1) * L.wp + (tap % 3 - 1));
-#ifdef BPP_TC_EXPERIMENT_ALIGNED
-                at &= ~7u;  // TIMING EXPERIMENT ONLY (wrong results): force 128-byte aligned operand windows
-#endif
                 const uint32_t bt = blo0 + (uint32_t)tap * b_tap;
                 umma_bf16_lh(d, at, ahi, bt, bhi, idesc, tap > 0 ? 1u : 0u);
                 if (X3) {
@@ -293,11 +291,17 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
             }
             umma_commit(cx.bar + 8u * (uint32_t)b);
         }
+       }
+       __syncwarp();
       }
-      __syncwarp();
       TC_PROF(2, tp);
       const int half = tid >> 7, lt = tid & 127;  // lt = TMEM lane = row inside the tile
-      for (int b = half; b < nb; b += 2) {
+      const int nch = cout >> 4;                    // 16-column chunks per tile
+      // work unit = (tile, chunk): the two halves (warps w and w + 4 read the same TMEM lane quarter) alternate units, so
+      // that a single-tile layer with 32 output channels still occupies all eight warps
+      for (int un = half; un < nb * nch && half < 2; un += 2) {
+        const int b = nch == 2 ? un >> 1 : un;
+        const int c0 = nch == 2 ? (un & 1) << 4 : 0;
         const int t = t0 + b;
         mbar_wait(cx.bar + 8u * (uint32_t)b, (cx.phase >> b) & 1u);
         tc_fence_after();
@@ -312,7 +316,7 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
         // EPI_CONV (bf16 mode): the halo rows of T are set to -inf, the max-pool's padding value, so that the pooling
         // pass reads its 3x3 windows without bounds checks (rows up to one grid row behind the last sample)
         const bool pad_row = !X3 && kind == EPI_CONV && !interior && rl < rows_valid + L.wp + 1;
-        for (int c0 = 0; c0 < cout; c0 += 16) {
+        {
             float v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);  // warp-collective: executed by every lane
             if (pad_row) {

@@ -17,6 +17,7 @@ struct Case {
     int nd;         // accumulators written round-robin (1 = one dependent chain)
     int chain;      // MMAs per accumulator before moving to the next
     int m64;        // 1: M = 64
+    int bg;         // background traffic of the other warps: 0 none, 1 st.shared.v4, 2 ld.shared.v4, 3 tcgen05.ld x16
 };
 
 __device__ __forceinline__ uint64_t mk_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16, uint32_t layout) {
@@ -30,12 +31,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-__global__ void __launch_bounds__(128, 1) k_probe(const Case* cases, int ncases, int nmma, long long* out) {
+__global__ void __launch_bounds__(256, 1) k_probe(const Case* cases, int ncases, int nmma, long long* out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 7);
+    __shared__ volatile int s_stop;
+    for (int i = tid; i < 160 * 1024 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (i & 7);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -53,6 +55,39 @@ __global__ void __launch_bounds__(128, 1) k_probe(const Case* cases, int ncases,
     for (int c = 0; c < ncases; ++c) {
         const Case cs = cases[c];
         long long dt = 0;
+        if (tid == 0) s_stop = 0;
+        __syncthreads();
+        if (tid >= 32 && cs.bg) {
+            // background traffic until the issuing thread has seen its MMAs complete
+            uint4* buf = reinterpret_cast<uint4*>(smem + 64 * 1024) + (tid - 32);
+            uint4 acc4 = make_uint4(tid, 0, 0, 0);
+            uint32_t sink = 0;
+            while (!s_stop) {
+                if (cs.bg == 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) buf[k * 224] = acc4;
+                } else if (cs.bg == 2) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        uint4 v;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                     : "r"(smem_u32(buf + k * 224)));
+                        sink += v.x;
+                    }
+                } else {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + 256u;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    sink += r[0] + r[15];
+                }
+            }
+            if (sink == 0x12345678u) out[63] = sink;
+        }
         if (tid < 32 && elect_one()) {
             const uint32_t m = cs.m64 ? 64u : 128u;
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cs.n >> 3) << 17) | ((m >> 4) << 24);
@@ -95,6 +130,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(const Case* cases, int ncases,
             }
             dt = done ? clock64() - t0 : -1;
             if (blockIdx.x == 0) out[c] = dt;
+            s_stop = 1;
         }
         parity ^= 1u;
         __syncthreads();
@@ -130,6 +166,9 @@ int main(int argc, char** argv) {
         add("SW128     aligned  (SBO 1024 B)", Case{N, 2, 1, 64, 0, 0, 1, 9, 0});
         add("SW128     step 1 row (128 B)", Case{N, 2, 1, 64, 8, 0, 1, 9, 0});
         add("M=64 planar aligned", Case{N, 0, PL, 8, 0, 0, 1, 9, 1});
+        add("planar taps + 7 warps st.shared.v4", Case{N, 0, PL, 8, 17, 0, 1, 9, 0, 1});
+        add("planar taps + 7 warps ld.shared.v4", Case{N, 0, PL, 8, 17, 0, 1, 9, 0, 2});
+        add("planar taps + 7 warps tcgen05.ld", Case{N, 0, PL, 8, 17, 0, 1, 9, 0, 3});
     }
     Case* d_cs;
     long long* d_out;
@@ -139,7 +178,7 @@ int main(int argc, char** argv) {
     cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int blocks = argc > 1 ? atoi(argv[1]) : 1;
     for (int rep = 0; rep < 2; ++rep) {
-        k_probe<<<blocks, 128, 200 * 1024>>>(d_cs, n, nmma, d_out);
+        k_probe<<<blocks, 256, 200 * 1024>>>(d_cs, n, nmma, d_out);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
     }
