@@ -273,8 +273,13 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     // finish together (with "group g -> CTA g mod grid" a batch of 2,800 leaves left 36 % of the CTAs idle in the last wave)
     const int slice_lo = (int)(((long long)blockIdx.x * B) / gridDim.x);
     const int slice_hi = (int)(((long long)(blockIdx.x + 1) * B) / gridDim.x);
-    for (int b0 = slice_lo; b0 < slice_hi; b0 += S) {
-        const int nvalid = min(S, slice_hi - b0);
+    // ... in equally sized groups (a 9-leaf slice at S = 5 is 5 + 4, a 6-leaf slice 3 + 3): a group's time is dominated
+    // by the latency chain of its 15 layers, not by its size
+    const int n_slice = slice_hi - slice_lo;
+    const int n_groups = (n_slice + S - 1) / S;
+    const int gsz = n_groups > 0 ? (n_slice + n_groups - 1) / n_groups : S;
+    for (int b0 = slice_lo; b0 < slice_hi; b0 += gsz) {
+        const int nvalid = min(gsz, slice_hi - b0);
         long long tq = clock64();
         // ---- level-0 operand planes from the compact records (getBinItem, BinPackingGame.py:118-120)
         const Level& L0 = T.lv[0];
@@ -890,11 +895,11 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         }
         n->umma_elems = uoff;
         const int cin16_0 = (P.Cin + 15) / 16;
-        // ctas_want = CTAs per SM the plan is made for (bf16 mode: 2 or 3; they share the SM's 227 KB of shared memory,
+        // ctas_want = CTAs per SM the plan is made for (bf16 mode: 1 or 2; they share the SM's 227 KB of shared memory,
         // its registers and its 512 TMEM columns); the largest group size S whose buffers fit is taken
         auto plan = [&](bpptc::TcParams& T, bool x3, int cap_bytes, int ctas_want, int& ctas_out) -> bool {
             const int f = x3 ? 2 : 1;
-            for (int S = ctas_want >= 2 ? 4 : 8; S >= 1; --S) {  // the multi-CTA instantiations hold at most 4 leaves
+            for (int S = 8; S >= 1; --S) {
                 for (int l = 0; l < 4; ++l) {
                     bpptc::Level& L = T.lv[l];
                     // shared halos: one zero column between consecutive grid rows (the right halo of row y IS the left
@@ -924,7 +929,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                 T.wbuf_bytes = (f * wmax + 256 + 127) & ~127;     // + the layer's bias behind the weights
                 T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
                 if (T.smem_bytes <= cap_bytes && T.lv[0].RT < 16384) {
-                    T.tmem_cols = ctas_want >= 3 ? 128 : ctas_want == 2 ? 256 : 512;
+                    T.tmem_cols = ctas_want == 2 ? 256 : 512;
                     ctas_out = ctas_want;
                     return true;
                 }
@@ -932,16 +937,17 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             return false;
         };
         {
-            // 227 KB per SM, 1 KB reserved per CTA, ~3.2 KB static shared memory per CTA
+            // 227 KB per SM, 1 KB reserved per CTA, 4.3 KB static shared memory per CTA.  Two CTAs per SM: while one waits
+            // for its MMAs the other runs its CUDA-core phases (BPP_TC_CTAS=1: one CTA with larger groups, experiments)
             const char* e = getenv("BPP_TC_CTAS");
             int want = e ? atoi(e) : 2;
-            if (want < 1 || want > 3) want = 2;
+            if (want < 1 || want > 2) want = 2;
             const int hk = (P.flat > HIDDEN ? P.flat : HIDDEN) / 8;
             const int hsm = std::max(hk * 2048 + HEAD_STAGES * HEAD_STAGE_BYTES, 128 * ((P.A | 1) + 1) * 4);
             const bool heads_possible = (P.flat % 16 == 0) && ((P.A + 15) & ~15) <= 256 && hsm <= 220 * 1024 &&
                                         getenv("BPP_NO_TC_HEADS") == nullptr;
             if (!heads_possible) want = 1;  // the multi-CTA instantiations are trunk-only
-            n->tc_ok = plan(T, false, (227 * 1024) / want - 1024 - 3328, want, n->ctas_per_sm);
+            n->tc_ok = plan(T, false, (227 * 1024) / want - 1024 - 4352, want, n->ctas_per_sm);
         }
         n->T3 = T;
         int c3 = 1;
@@ -956,9 +962,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                                            n->T.smem_bytes) != cudaSuccess ||
                       cudaFuncSetAttribute(k_net_forward_tc<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            n->T.smem_bytes) != cudaSuccess ||
-                      cudaFuncSetAttribute(k_net_forward_tc<4, false, true, 2>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, n->T.smem_bytes) != cudaSuccess ||
-                      cudaFuncSetAttribute(k_net_forward_tc<4, false, true, 3>,
+                      cudaFuncSetAttribute(k_net_forward_tc<8, false, true, 2>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, n->T.smem_bytes) != cudaSuccess)) ||
         (n->tc3_ok && (cudaFuncSetAttribute(k_net_forward_tc<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             n->T3.smem_bytes) != cudaSuccess ||
@@ -1180,11 +1184,8 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int cap = 148 * n->ctas_per_sm;
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
-        if (fo && n->T.S <= 4 && n->ctas_per_sm == 3)
-            k_net_forward_tc<4, false, true, 3><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
-                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
-        else if (fo && n->T.S <= 4)
-            k_net_forward_tc<4, false, true, 2><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
+        if (fo && n->ctas_per_sm == 2)
+            k_net_forward_tc<8, false, true, 2><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
                 n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
         else if (n->T.S <= 4)
             k_net_forward_tc<4, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(

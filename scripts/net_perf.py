@@ -61,5 +61,5 @@ def run(W, H, N, B, modes=("bf16", "bf16_simt", "fp32"), iters=20):
 if __name__ == "__main__":
     modes = tuple(sys.argv[1].split(",")) if len(sys.argv) > 1 else ("bf16", "bf16x3", "bf16_simt", "fp32")
     for (W, H, N) in [(15, 15, 10), (20, 20, 10)]:
-        for B in (2048, 8192):
+        for B in (2048, 2800, 8192):
             print(json.dumps({"cfg": [W, H, N], "B": B, **run(W, H, N, B, modes)}))
