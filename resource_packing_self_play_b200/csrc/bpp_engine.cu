@@ -465,6 +465,23 @@ __device__ __forceinline__ void root_counts_warp(const Params& P, int g, int roo
     for (int e = lane; e < nv; e += 32) row[eb.ACT[e]] = eb.NC[e].x;
 }
 
+// Mirror of one visit-count row into mapped host memory as full 128-byte stores (k_episode writes the results of
+// bpp_engine_play_stub_host straight into the caller's pinned buffer while the episodes run).  noinline + scalar
+// arguments: called once per move, kept out of the search loop's register allocation.
+__device__ __noinline__ void mirror_row(const int32_t* dev_row, int32_t* host_row, int A, int lane) {
+    __syncwarp();
+    for (int a = lane; a < A; a += 32) host_row[a] = dev_row[a];
+}
+// rows of moves a game did not play: counts 0, action -1
+__device__ __noinline__ void fill_unplayed(int32_t* counts_host, int32_t* actions_out, int g, int G, int A, int m0, int m1,
+                                           int lane) {
+    for (int m = m0; m < m1; ++m) {
+        if (counts_host)
+            for (int a = lane; a < A; a += 32) counts_host[((size_t)m * G + g) * A + a] = 0;
+        if (actions_out && lane == 0) actions_out[(size_t)m * G + g] = -1;
+    }
+}
+
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_root_counts(Params P, int32_t* out) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = blockIdx.x * WARPS_PER_CTA + wid;
@@ -591,12 +608,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_advance(Params P, const 
 // for one move no longer holds back the others (the only tail left is the end of the batch).
 template <int STUB, int HC>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7)
-k_episode(Params P, int mode, unsigned long long seed, int max_moves, int32_t* counts_out, int32_t* actions_out) {
+k_episode(Params P, int mode, unsigned long long seed, int max_moves, int32_t* counts_out, int32_t* actions_out,
+          int32_t* counts_host) {
+    // counts_host != nullptr: results go to mapped host memory (counts_out is then the device scratch the rows are built
+    // in, actions_out the host alias) and this kernel also writes the rows of unplayed moves
     __shared__ WarpSmem smem[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = blockIdx.x * WARPS_PER_CTA + wid;
     if (g >= P.G) return;
-    if (P.status[g] != 0) return;
+    if (P.status[g] != 0) {
+        if (counts_host) fill_unplayed(counts_host, actions_out, g, P.G, P.geom.A, 0, max_moves, lane);
+        return;
+    }
     WarpSmem& sm = smem[wid];
     GameCtx gm;
     load_ctx(P, g, lane, gm, sm);
@@ -605,24 +628,30 @@ k_episode(Params P, int mode, unsigned long long seed, int max_moves, int32_t* c
     int move_no = P.moves_done[g];
     int done = P.sims_done[g];
     const size_t GA = (size_t)P.G * P.geom.A;
-    for (int m = 0; m < max_moves; ++m) {
+    int m = 0;
+    for (; m < max_moves; ++m) {
         while (done < P.num_sims) {
             if (simulate<STUB, HC>(P, gm, sm, lane, st) != 0) break;
             done++;
             st.sims++;
         }
         if (gm.err) break;
-        if (counts_out) root_counts_warp(P, g, gm.root_node, lane, counts_out + m * GA + (size_t)g * P.geom.A);
+        if (counts_out) {
+            int32_t* row = counts_out + m * GA + (size_t)g * P.geom.A;
+            root_counts_warp(P, g, gm.root_node, lane, row);
+            if (counts_host) mirror_row(row, counts_host + m * GA + (size_t)g * P.geom.A, P.geom.A, lane);
+        }
         int a = lane == 0 ? choose_action(P, g, gm.root_node, move_no, mode, seed) : 0;
         a = __shfl_sync(FULL, a, 0);
         if (actions_out && lane == 0) actions_out[(size_t)m * P.G + g] = a;
         const int status = advance_game(P, gm, sm, lane, a, rec, st);
         move_no++;
         done = 0;
-        if (status != 0) break;
+        if (status != 0) { ++m; break; }
     }
     store_ctx(P, gm, lane);
     flush_stats(P, st, lane);
+    if (counts_host) fill_unplayed(counts_host, actions_out, g, P.G, P.geom.A, m, max_moves, lane);
 }
 
 // dense evaluator input: planes [B][N+1][H][W] float32 (getBinItem, BinPackingGame.py:118-120)
@@ -1241,19 +1270,21 @@ extern "C" int bpp_engine_roots(bpp_engine* e, uint32_t* roots_out_dev, void* st
 
 template <int STUB>
 static void launch_episode(bpp_engine* e, int mode, uint64_t seed, int moves, int32_t* counts, int32_t* actions,
-                           void* stream) {
+                           int32_t* counts_host, void* stream) {
     const int grid = grid_warps(e->P.G), block = WARPS_PER_CTA * 32;
     const unsigned long long sd = (unsigned long long)seed;
     switch (e->P.geom.H) {
-        case 15: k_episode<STUB, 15><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions); break;
-        case 20: k_episode<STUB, 20><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions); break;
-        default: k_episode<STUB, 0><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions); break;
+        case 15: k_episode<STUB, 15><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions, counts_host); break;
+        case 20: k_episode<STUB, 20><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions, counts_host); break;
+        default: k_episode<STUB, 0><<<grid, block, 0, S(stream)>>>(e->P, mode, sd, moves, counts, actions, counts_host); break;
     }
 }
 
-extern "C" int bpp_engine_play_stub(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed, int max_moves,
-                                    int32_t* counts_out_dev, int32_t* actions_out_dev, int32_t* moves_run_host,
-                                    void* stream) {
+// counts_host_map != nullptr: results go to mapped host memory (counts_out_dev is the device scratch, actions_out_dev
+// the host alias) and the kernel itself writes the rows of unplayed moves
+static int play_stub_impl(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed, int max_moves,
+                          int32_t* counts_out_dev, int32_t* actions_out_dev, int32_t* moves_run_host,
+                          int32_t* counts_host_map, void* stream) {
     if (!e) return set_err(BPP_E_INVALID, "null argument");
     if (e->leaf_parked) return set_err(BPP_E_STATE, "leaves are parked; call bpp_engine_expand_backup first");
     if (choose_mode < 0 || choose_mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", choose_mode);
@@ -1261,18 +1292,41 @@ extern "C" int bpp_engine_play_stub(bpp_engine* e, int stub_kind, int choose_mod
     const int moves = max_moves > 0 && max_moves < e->P.geom.N ? max_moves : e->P.geom.N;
     const size_t G = (size_t)e->P.G, GA = G * e->P.geom.A;
     // rows of moves a game does not play: counts 0, action -1
-    if (counts_out_dev) CUDA_TRY(cudaMemsetAsync(counts_out_dev, 0, (size_t)moves * GA * sizeof(int32_t), S(stream)));
-    if (actions_out_dev) CUDA_TRY(cudaMemsetAsync(actions_out_dev, 0xff, (size_t)moves * G * sizeof(int32_t), S(stream)));
+    if (!counts_host_map) {
+        if (counts_out_dev) CUDA_TRY(cudaMemsetAsync(counts_out_dev, 0, (size_t)moves * GA * sizeof(int32_t), S(stream)));
+        if (actions_out_dev)
+            CUDA_TRY(cudaMemsetAsync(actions_out_dev, 0xff, (size_t)moves * G * sizeof(int32_t), S(stream)));
+    }
+    int32_t* f = counts_host_map;
     switch (stub_kind) {
-        case BPP_STUB_U: launch_episode<1>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, stream); break;
-        case BPP_STUB_V: launch_episode<2>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, stream); break;
-        case BPP_STUB_H: launch_episode<3>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, stream); break;
-        case BPP_STUB_D: launch_episode<4>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, stream); break;
+        case BPP_STUB_U: launch_episode<1>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, f, stream); break;
+        case BPP_STUB_V: launch_episode<2>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, f, stream); break;
+        case BPP_STUB_H: launch_episode<3>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, f, stream); break;
+        case BPP_STUB_D: launch_episode<4>(e, choose_mode, seed, moves, counts_out_dev, actions_out_dev, f, stream); break;
         default: return set_err(BPP_E_INVALID, "unknown stub kind %d", stub_kind);
     }
     LAUNCH_CHECK(e);
     if (moves_run_host) *moves_run_host = moves;
     return BPP_OK;
+}
+
+extern "C" int bpp_engine_play_stub(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed, int max_moves,
+                                    int32_t* counts_out_dev, int32_t* actions_out_dev, int32_t* moves_run_host,
+                                    void* stream) {
+    return play_stub_impl(e, stub_kind, choose_mode, seed, max_moves, counts_out_dev, actions_out_dev, moves_run_host,
+                          nullptr, stream);
+}
+
+// device alias of a host buffer the kernels can write directly (pinned + mapped: cudaHostAlloc / cudaHostRegister under
+// unified addressing), or nullptr for pageable memory
+static void* mapped_alias(void* host_ptr) {
+    if (!host_ptr) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
 extern "C" int bpp_engine_play_stub_host(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed,
@@ -1283,20 +1337,32 @@ extern "C" int bpp_engine_play_stub_host(bpp_engine* e, int stub_kind, int choos
     if (!e) return set_err(BPP_E_INVALID, "null argument");
     const size_t G = (size_t)e->P.G, A = (size_t)e->P.geom.A, N = (size_t)e->P.geom.N;
     int rc;
+    // Pinned (mapped) result buffers are written by the episode kernel itself, row by row while the games run: the
+    // 25 MB of visit counts then cross PCIe under the kernel instead of in a copy after it.  Pageable buffers take the
+    // staged path (device buffer + copy).
+    int32_t* counts_map = static_cast<int32_t*>(mapped_alias(counts_out_host));
+    int32_t* actions_map = static_cast<int32_t*>(mapped_alias(actions_out_host));
+    const bool direct = counts_map && (!actions_out_host || actions_map) && getenv("BPP_NO_ZERO_COPY") == nullptr;
     if (counts_out_host && !e->d_counts_all) {
         if ((rc = dev_alloc(e, &e->d_counts_all, N * G * A))) return rc;
     }
-    if (!e->d_actions_all && (rc = dev_alloc(e, &e->d_actions_all, N * G))) return rc;
+    if (!direct && !e->d_actions_all && (rc = dev_alloc(e, &e->d_actions_all, N * G))) return rc;
     if ((rc = bpp_engine_reset_host(e, items_wh_host, total_area_host, bl_host, tie_host, stream))) return rc;
-    if ((rc = bpp_engine_play_stub(e, stub_kind, choose_mode, seed, 0, counts_out_host ? e->d_counts_all : nullptr,
-                                   e->d_actions_all, nullptr, stream)))
-        return rc;
-    if (counts_out_host)
-        CUDA_TRY(cudaMemcpyAsync(counts_out_host, e->d_counts_all, N * G * A * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 S(stream)));
-    if (actions_out_host)
-        CUDA_TRY(cudaMemcpyAsync(actions_out_host, e->d_actions_all, N * G * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 S(stream)));
+    if (direct) {
+        if ((rc = play_stub_impl(e, stub_kind, choose_mode, seed, 0, e->d_counts_all, actions_map, nullptr, counts_map,
+                                 stream)))
+            return rc;
+    } else {
+        if ((rc = bpp_engine_play_stub(e, stub_kind, choose_mode, seed, 0, counts_out_host ? e->d_counts_all : nullptr,
+                                       e->d_actions_all, nullptr, stream)))
+            return rc;
+        if (counts_out_host)
+            CUDA_TRY(cudaMemcpyAsync(counts_out_host, e->d_counts_all, N * G * A * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     S(stream)));
+        if (actions_out_host)
+            CUDA_TRY(cudaMemcpyAsync(actions_out_host, e->d_actions_all, N * G * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     S(stream)));
+    }
     if (r_out_host)
         CUDA_TRY(cudaMemcpyAsync(r_out_host, e->P.ep_r, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
     if (score_out_host)

@@ -148,3 +148,51 @@ def test_whole_episode_kernel_equals_the_per_move_kernels():
         for k in sa:
             assert torch.equal(sa[k], sb[k]), k
         assert a.stats()["sims"] == b.stats()["sims"]
+
+
+@pytest.mark.parametrize("kind", ["U", "V"])
+def test_host_buffer_episode_call_direct_and_staged_paths_agree(kind):
+    """bpp_engine_play_stub_host writes the visit counts straight into PINNED result buffers from the episode kernel
+    (mapped host memory) and through a device buffer + copy into pageable ones: both must equal the device-buffer call
+    bpp_engine_play_stub, including the zero rows / -1 actions of moves a game does not play, and the C oracle."""
+    import torch
+    from oracle import c_oracle as CO
+    from resource_packing_self_play_b200 import _lib
+    from resource_packing_self_play_b200.engine import SearchEngine
+    from resource_packing_self_play_b200.game import ItemsGenerator
+
+    W, H, N, G, SIMS = 15, 15, 10, 37, 48
+    rng = np.random.RandomState(11)
+    heights = rng.randint(2, 16, size=G).astype(np.int32)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(G) + 7000, heights)
+    area = (W * heights).astype(np.int32)
+    bl = np.full(G, np.nan)
+    eng = SearchEngine(W, H, N, G, SIMS, 1.0, device=0)
+    eng.reset(items, area, bl)
+    counts_d, actions_d = eng.play_stub(kind, _lib.CHOOSE_ARGMAX_FIRST)
+    eng.check()
+    counts_d, actions_d = counts_d.cpu().numpy(), actions_d.cpu().numpy()
+    moves_d = eng.status()["moves"].cpu().numpy() if "moves" in eng.status() else None
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+
+    out_pin = {"counts": pinned((N, G, W * N), torch.int32), "actions": pinned((N, G), torch.int32),
+               "r": pinned(G, torch.int32), "score": pinned(G, torch.float64), "moves": pinned(G, torch.int32)}
+    out_pin["counts"][:] = 12345   # stale contents must be overwritten everywhere
+    out_pin["actions"][:] = 777
+    eng.play_stub_host(kind, items, area, bl, choose_mode=_lib.CHOOSE_ARGMAX_FIRST, out=out_pin)
+    out_pag = eng.play_stub_host(kind, items, area, bl, choose_mode=_lib.CHOOSE_ARGMAX_FIRST)
+    for out in (out_pin, out_pag):
+        assert np.array_equal(out["counts"], counts_d)
+        assert np.array_equal(out["actions"], actions_d)
+        if moves_d is not None:
+            assert np.array_equal(out["moves"], moves_d)
+    assert (out_pin["actions"] == -1).any(), "the sample should contain episodes shorter than N moves"
+    for g in range(0, G, 6):
+        ref = CO.play_episode(W, H, N, items[g], int(area[g]), float("nan"), kind, SIMS, 1.0, policy=0)
+        m = ref["moves"]
+        assert int(out_pin["moves"][g]) == m
+        assert np.array_equal(out_pin["counts"][:m, g], ref["counts"])
+        assert not out_pin["counts"][m:, g].any() and (out_pin["actions"][m:, g] == -1).all()
+        assert (int(out_pin["r"][g]), float(out_pin["score"][g])) == (ref["r"], ref["score"])
