@@ -142,12 +142,43 @@ class BatchedMCTS:
         self.eng = SearchEngine(game.bin_width, game.bin_height, game.num_items, G, int(args.numMCTSSims),
                                 float(args.cpuct), device=device)
         self.steps = 0
+        self.use_graphs = os.environ.get("BPP_NO_GRAPHS") is None
+        self._graphs, self._eager_chunks, self.graph_launches = {}, 0, 0
 
     def reset(self, items_wh, total_area, rewards_list, tie=None):
         bl = np.full(self.G, ranked_threshold(rewards_list, self.args.alpha))
         if tie is None:
             tie = np.where(_TIE_RNG.random(self.G) < 0.5, 1, -1).astype(np.int8)
         self.eng.reset(items_wh, total_area, bl, tie)
+
+    def _run_chunk(self, chunk, cap, count_ptr, game_ptr, recs_ptr):
+        """`chunk` lockstep steps (select -> forward -> expand + backup).  Every kernel of a step has a fixed grid and
+        reads the leaf count from device memory, so the chunk is captured ONCE per (chunk, select cap) into a CUDA graph
+        and replayed: one graph launch instead of 4 * chunk kernel launches through Python/ctypes, which left the GPU
+        idle for a quarter of a step.  The first chunks run eagerly (lazy allocations must not happen in a capture)."""
+        eng, net = self.eng, self.nnet.dnet
+
+        def body():
+            for _ in range(chunk):
+                eng.select()
+                net.forward(recs_ptr, self._items_dev, game=game_ptr, count_dev=count_ptr, policy_out=self._pol,
+                            value_out=self._val, batch=self.G)
+                eng.expand_backup(self._pol, self._val)
+        key = (chunk, cap, torch.cuda.current_stream().cuda_stream, net._h.value, getattr(net, "precision", None))
+        graph = self._graphs.get(key) if self.use_graphs else None
+        if graph is None and self.use_graphs and self._eager_chunks >= 2:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            self._graphs[key] = graph
+        if graph is not None:
+            graph.replay()
+            self.graph_launches += 4 * chunk   # k_search, trunk, heads, k_expand_backup per step
+        else:
+            body()
+            self._eager_chunks += 1
+        self.steps += chunk
 
     def search(self, chunk=8, select_cap=None):
         """numMCTSSims simulations for every running game.  One lockstep step = select (descents + terminal backups
@@ -156,6 +187,12 @@ class BatchedMCTS:
         expansion kernel read it there); the host only polls it every `chunk` steps to learn that the move is done."""
         eng, net = self.eng, self.nnet.dnet
         count_ptr, game_ptr, recs_ptr = eng.leaf_buffers()
+        # the evaluator reads the item dimensions from a buffer that keeps its address (captured graphs point at it)
+        if getattr(self, "_items_dev", None) is None:
+            self._items_dev, self._items_src = torch.empty_like(eng.items_wh), None
+        if self._items_src is not eng.items_wh:
+            self._items_dev.copy_(eng.items_wh)
+            self._items_src = eng.items_wh
         if getattr(self, "_pol", None) is None:
             self._pol = torch.empty((self.G, eng.A), dtype=torch.float32, device=eng.device)
             self._val = torch.empty(self.G, dtype=torch.float32, device=eng.device)
@@ -166,17 +203,14 @@ class BatchedMCTS:
             select_cap = int(os.environ.get("BPP_SELECT_CAP", "4"))
         lift = int(os.environ.get("BPP_SELECT_LIFT", "16"))
         eng.set_select_cap(select_cap)
+        cap = select_cap
         while True:
-            for _ in range(chunk):
-                eng.select()
-                net.forward(recs_ptr, eng.items_wh, game=game_ptr, count_dev=count_ptr, policy_out=self._pol,
-                            value_out=self._val, batch=self.G)
-                eng.expand_backup(self._pol, self._val)
-                self.steps += 1
+            self._run_chunk(chunk, cap, count_ptr, game_ptr, recs_ptr)
             n = eng.leaf_count()
             if n == 0 and eng.unfinished() == 0:  # nothing parked, nobody capped: the move is complete
                 break
-            if n < self.G // lift:
+            if n < self.G // lift and cap != 0:
                 eng.set_select_cap(0)
+                cap = 0
         eng.set_select_cap(0)
         return eng.root_counts()
