@@ -177,6 +177,13 @@ int bpp_engine_leaf_planes(bpp_engine *e, float *planes_out_dev, void *stream);
 int bpp_engine_expand_backup(bpp_engine *e, const void *policy_dev, int policy_dtype, const void *value_dev,
                              int value_dtype, void *stream);
 
+/* bpp_engine_expand_backup followed by bpp_engine_select in ONE launch (one warp per game: the expansion and backup of
+ * the game's parked leaf, MCTS_bpp.py:85-104,130-139, then the next descents :107-125 until it parks its next leaf).
+ * Results are identical to the two separate calls; games without a parked leaf only select.  The new leaf batch
+ * replaces the old one (same buffers, bpp_engine_leaf_buffers). */
+int bpp_engine_expand_select(bpp_engine *e, const void *policy_dev, int policy_dtype, const void *value_dev,
+                             int value_dtype, void *stream);
+
 /* Whole getActionProb simulation loop (MCTS_bpp.py:37-38) in ONE launch with an in-kernel stub evaluator:
  * every game runs simulations until its per-move counter reaches num_sims. */
 int bpp_engine_search_stub(bpp_engine *e, int stub_kind, void *stream);

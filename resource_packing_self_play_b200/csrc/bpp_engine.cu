@@ -79,6 +79,7 @@ struct Params {
     // parked leaves (lockstep)
     int* pend_depth;         // [G] -1 = none
     int* pend_leaf;          // [G]
+    int* pend_slot;          // [G] slot of the parked leaf in the leaf batch (row of the evaluator's outputs)
     int4* pend_path;         // [G][32]
     uint32_t* pend_valid;    // [G][16]
     int* leaf_count;         // [1]
@@ -281,6 +282,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
                     P.leaf_game[b] = gm.g;
                     P.pend_depth[gm.g] = depth;
                     P.pend_leaf[gm.g] = cur;
+                    P.pend_slot[gm.g] = b;
                 }
                 P.leaf_rec[(size_t)b * REC_WORDS + lane] = state_lane(lane, ge.H) ? rec : 0u;
                 P.pend_path[(size_t)gm.g * 32 + lane] = make_int4(pe.node, pe.off, pe.nvp, pe.e);
@@ -399,6 +401,67 @@ k_expand_backup(Params P, const void* policy, int policy_f64, const void* value,
         if (lane == 0) P.sims_done[g] += 1;
     }
     if (lane == 0) P.pend_depth[g] = -1;
+    store_ctx(P, gm, lane);
+    flush_stats(P, st, lane);
+}
+
+// Lockstep step in ONE launch per game warp: expansion + backup of the game's parked leaf (evaluator outputs of the
+// previous step, row pend_slot[g]) followed by the next descents until the game parks its next leaf (k_expand_backup +
+// k_search<0>): the game context is loaded once, and the second launch with its tail disappears from every step.  New
+// leaves go to slots counted from zero (leaf_count is cleared before the launch); nothing in this kernel reads the
+// old leaf records, and the evaluator outputs are only read.
+template <int HC>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7)
+k_expand_search(Params P, const void* policy, int policy_f64, const void* value, int value_f64) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    if (g >= P.G) return;
+    if (P.status[g] != 0) return;
+    WarpSmem& sm = smem[wid];
+    GameCtx gm;
+    load_ctx(P, g, lane, gm, sm);
+    Stats st = {0, 0, 0, 0, 0, 0};
+    int done = P.sims_done[g];
+    const int depth = P.pend_depth[g];
+    bool ok = true;
+    if (depth >= 0) {
+        const int b = P.pend_slot[g];
+        const int cur = P.pend_leaf[g];
+        if (lane < MAX_AW) sm.vw[lane] = P.pend_valid[(size_t)g * MAX_AW + lane];
+        __syncwarp();
+        const int4 pp = P.pend_path[(size_t)g * 32 + lane];
+        PathEntry pe = {pp.x, pp.y, pp.z, pp.w};
+        const size_t row = (size_t)b * P.geom.A;
+        const double* pol64 = reinterpret_cast<const double*>(policy) + row;
+        const float* pol32 = reinterpret_cast<const float*>(policy) + row;
+        ok = expand_node(P, gm, sm, cur, lane,
+                         [=](int a) -> double { return policy_f64 ? pol64[a] : (double)pol32[a]; });
+        if (ok) {
+            const double v = value_f64 ? reinterpret_cast<const double*>(value)[b]
+                                       : (double)reinterpret_cast<const float*>(value)[b];
+            backup_path(gm.nodes, gm.edges, pe, depth, v, lane, P.sqrt_tab, P.sqrt_n);
+            if (lane == 0) P.last_v[g] = v;
+            st.expansions++;
+            st.sims++;
+            done++;
+        }
+        if (lane == 0) P.pend_depth[g] = -1;
+        __syncwarp();
+    }
+    if (ok) {
+        const int stop = P.select_cap > 0 ? min(P.num_sims, done + P.select_cap) : P.num_sims;
+        while (done < stop) {
+            const int rc = simulate<0, HC>(P, gm, sm, lane, st);
+            if (rc != 0) break;  // parked leaf (counted when it is expanded) or overflow
+            done++;
+            st.sims++;
+        }
+    }
+    if (lane == 0) {
+        P.sims_done[g] = done;
+        if (done < P.num_sims && P.pend_depth[g] < 0) atomicAdd(P.leaf_count + 1, 1);
+    }
     store_ctx(P, gm, lane);
     flush_stats(P, st, lane);
 }
@@ -990,6 +1053,7 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     ALLOC(P.last_v, G);
     ALLOC(P.pend_depth, G);
     ALLOC(P.pend_leaf, G);
+    ALLOC(P.pend_slot, G);
     ALLOC(P.pend_path, G * 32);
     ALLOC(P.pend_valid, G * MAX_AW);
     ALLOC(P.leaf_count, 2);  // [0] parked leaves, [1] games that stopped at the per-launch cap
@@ -1196,6 +1260,22 @@ extern "C" int bpp_engine_expand_backup(bpp_engine* e, const void* policy_dev, i
         e->P, policy_dev, policy_dtype == BPP_DTYPE_F64, value_dev, value_dtype == BPP_DTYPE_F64);
     LAUNCH_CHECK(e);
     e->leaf_parked = false;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_expand_select(bpp_engine* e, const void* policy_dev, int policy_dtype, const void* value_dev,
+                                        int value_dtype, void* stream) {
+    if (!e || !policy_dev || !value_dev) return set_err(BPP_E_INVALID, "null argument");
+    CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, 2 * sizeof(int), S(stream)));
+    const int grid = grid_warps(e->P.G), block = WARPS_PER_CTA * 32;
+    const int pf = policy_dtype == BPP_DTYPE_F64, vf = value_dtype == BPP_DTYPE_F64;
+    switch (e->P.geom.H) {
+        case 15: k_expand_search<15><<<grid, block, 0, S(stream)>>>(e->P, policy_dev, pf, value_dev, vf); break;
+        case 20: k_expand_search<20><<<grid, block, 0, S(stream)>>>(e->P, policy_dev, pf, value_dev, vf); break;
+        default: k_expand_search<0><<<grid, block, 0, S(stream)>>>(e->P, policy_dev, pf, value_dev, vf); break;
+    }
+    LAUNCH_CHECK(e);
+    e->leaf_parked = true;
     return BPP_OK;
 }
 

@@ -261,6 +261,14 @@ class SearchEngine:
         call("bpp_engine_expand_backup", self._h, _ptr(policy), _TORCH_DT[policy.dtype], _ptr(value),
              _TORCH_DT[value.dtype], _stream())
 
+    def expand_select(self, policy, value):
+        """expand_backup + select in one launch (bpp_engine_expand_select)"""
+        policy = policy.contiguous()
+        value = value.contiguous()
+        self._keep_eval = (policy, value)
+        call("bpp_engine_expand_select", self._h, _ptr(policy), _TORCH_DT[policy.dtype], _ptr(value),
+             _TORCH_DT[value.dtype], _stream())
+
     def search_with(self, evaluator):
         """Run the numMCTSSims simulations of this move for every game with a batched evaluator:
         evaluator(planes float32 (B, N+1, H, W) on device) -> (policy (B, A) f32|f64, value (B,) f32|f64)."""

@@ -143,6 +143,7 @@ class BatchedMCTS:
                                 float(args.cpuct), device=device)
         self.steps = 0
         self.use_graphs = os.environ.get("BPP_NO_GRAPHS") is None
+        self.fused = os.environ.get("BPP_NO_FUSED_STEP") is None
         self._graphs, self._eager_chunks, self.graph_launches = {}, 0, 0
 
     def reset(self, items_wh, total_area, rewards_list, tie=None):
@@ -160,11 +161,15 @@ class BatchedMCTS:
 
         def body():
             for _ in range(chunk):
-                eng.select()
+                if not self.fused:
+                    eng.select()
                 net.forward(recs_ptr, self._items_dev, game=game_ptr, count_dev=count_ptr, policy_out=self._pol,
                             value_out=self._val, batch=self.G)
-                eng.expand_backup(self._pol, self._val)
-        key = (chunk, cap, torch.cuda.current_stream().cuda_stream, net._h.value, getattr(net, "precision", None))
+                if self.fused:   # expansion + backup of this step and the descents of the next one in ONE launch
+                    eng.expand_select(self._pol, self._val)
+                else:
+                    eng.expand_backup(self._pol, self._val)
+        key = (chunk, cap, self.fused, torch.cuda.current_stream().cuda_stream, net._h.value, getattr(net, "precision", None))
         graph = self._graphs.get(key) if self.use_graphs else None
         if graph is None and self.use_graphs and self._eager_chunks >= 2:
             torch.cuda.synchronize()
@@ -174,7 +179,7 @@ class BatchedMCTS:
             self._graphs[key] = graph
         if graph is not None:
             graph.replay()
-            self.graph_launches += 4 * chunk   # k_search, trunk, heads, k_expand_backup per step
+            self.graph_launches += (3 if self.fused else 4) * chunk   # [k_search,] trunk, heads, k_expand_[backup|search]
         else:
             body()
             self._eager_chunks += 1
@@ -204,6 +209,8 @@ class BatchedMCTS:
         lift = int(os.environ.get("BPP_SELECT_LIFT", "16"))
         eng.set_select_cap(select_cap)
         cap = select_cap
+        if self.fused:
+            eng.select()   # the first leaves of the move; every later select rides on the expansion launch
         while True:
             self._run_chunk(chunk, cap, count_ptr, game_ptr, recs_ptr)
             n = eng.leaf_count()

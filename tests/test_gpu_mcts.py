@@ -196,3 +196,52 @@ def test_host_buffer_episode_call_direct_and_staged_paths_agree(kind):
         assert np.array_equal(out_pin["counts"][:m, g], ref["counts"])
         assert not out_pin["counts"][m:, g].any() and (out_pin["actions"][m:, g] == -1).all()
         assert (int(out_pin["r"][g]), float(out_pin["score"][g])) == (ref["r"], ref["score"])
+
+
+def test_batched_mcts_fused_graph_replay_equals_plain_lockstep():
+    """BatchedMCTS.search with the fused expand+select launch replayed from CUDA graphs must give exactly the visit counts
+    of the plain select -> forward -> expand_backup loop launched eagerly (games are independent and the evaluator is
+    deterministic per leaf, so neither the launch structure nor the leaf order may change a count)."""
+    import torch
+    from resource_packing_self_play_b200 import _lib
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    from resource_packing_self_play_b200.mcts import BatchedMCTS
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+
+    W, H, N, G, SIMS = 15, 15, 10, 96, 40
+
+    class Gm:
+        bin_width, bin_height, num_items = W, H, N
+
+        def getBoardSize(self):
+            return (H, W)
+
+        def getActionSize(self):
+            return W * N
+    args = dotdict(numMCTSSims=SIMS, cpuct=1.0, alpha=0.75, num_items=N, num_bins=1, cuda=True)
+    torch.manual_seed(3)
+    net = NNetWrapper(Gm(), args, max_batch=G, precision="bf16")
+    rng = np.random.RandomState(5)
+    heights = rng.randint(4, 16, size=G).astype(np.int32)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(G) + 31000, heights)
+    area = (W * heights).astype(np.int32)
+    tie = np.ones(G, dtype=np.int8)
+    runs = []
+    for fused, graphs in ((True, True), (False, False), (True, False)):
+        bm = BatchedMCTS(Gm(), net, args, G)
+        bm.fused, bm.use_graphs = fused, graphs
+        bm.reset(items, area, [0.5, 0.7, 0.9001], tie=tie)
+        per_move = []
+        for m in range(6):
+            counts = bm.search(chunk=4)
+            act = bm.eng.choose(_lib.CHOOSE_ARGMAX_FIRST)
+            bm.eng.advance(act)
+            per_move.append((counts.cpu().numpy().copy(), act.cpu().numpy().copy()))
+        bm.eng.check()
+        runs.append((per_move, bm.graph_launches))
+    assert runs[0][1] > 0 and runs[1][1] == 0, "the first run must have replayed graphs, the second none"
+    for other in (runs[1][0], runs[2][0]):
+        for (c0, a0), (c1, a1) in zip(runs[0][0], other):
+            assert np.array_equal(c0, c1) and np.array_equal(a0, a1)
+    assert runs[0][0][0][0].sum() > 0
