@@ -81,13 +81,14 @@ class CoachBPP:
                 return [(x[0], x[1], r) for x in trainExamples]
 
     # ------------------------------------------------------------------------------------------------------------------
-    def executeEpisodesBatched(self, items_batch, total_areas, greedy=False, seed=None, expand=True):
+    def executeEpisodesBatched(self, items_batch, total_areas, greedy=False, seed=None, expand=True, on_device=False):
         """G episodes in lockstep on the device with the batched leaf evaluator.
 
         items_batch: (G, N, 2) int (w, h); total_areas: (G,) int.  All games share this call's `self.rewards_list`
         (the reference appends to it after every episode, so inside one call the ranked-reward threshold is the one at
         the start of the batch).  Returns (examples, scores, outcomes): examples is the reference's list of
-        (state (N+1,H,W) int64, pi list, r) when expand=True, else a dict of compact arrays."""
+        (state (N+1,H,W) int64, pi list, r) when expand=True, else a dict of compact arrays (numpy, or device tensors
+        that never visit the host when on_device=True; scores and outcomes are then device tensors too)."""
         items_dev = None
         if isinstance(items_batch, torch.Tensor):  # e.g. from ItemsGenerator.items_batch_device
             items_dev = items_batch.to(torch.int32)
@@ -113,6 +114,12 @@ class CoachBPP:
             acts.append(act)
             eng.advance(act)
         eng.check()
+        if on_device and not expand:
+            st = eng.status()
+            return {"roots": torch.stack(roots), "counts": torch.stack(counts), "actions": torch.stack(acts),
+                    "moves": st["moves"], "r": st["r"],
+                    "items": items_dev if items_dev is not None else torch.from_numpy(items_batch).to(eng.device)}, \
+                st["score"], st["r"]
         st = {k: v.cpu().numpy() for k, v in eng.status().items()}
         roots = torch.stack(roots).cpu().numpy().view(np.uint32)      # (N, G, 32)
         counts = torch.stack(counts).cpu().numpy()                      # (N, G, A)
@@ -219,12 +226,14 @@ class CoachBPP:
             areas = np.full(hi - lo, self.items_total_area, dtype=np.int32)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
+            # the examples stay on the device from the search kernels to the learner: compact arrays -> all-gather over
+            # the game axis (NCCL) -> one row per played move -> replay history, all as device tensors
             compact, score, r = self.executeEpisodesBatched(items, areas, greedy=i > self.args.iterStepThreshold,
-                                                            expand=False)
+                                                            expand=False, on_device=True)
             torch.cuda.synchronize()
             t2 = time.perf_counter()
             compact = D.gather_examples(compact, dev)
-            scores = D.all_gather_variable(torch.from_numpy(np.asarray(score)).to(dev)).cpu().numpy()
+            scores = D.all_gather_variable(score).cpu().numpy()
             # rewards buffer (CoachBPP.py:134-139): append every score, then drop minima until numScoresForRank remain
             # (repeated `pop(argmin)` == remove the smallest, earliest-first; survivors keep their order)
             rl = np.asarray(list(self.rewards_list) + [float(x) for x in scores], dtype=np.float64)
@@ -236,26 +245,28 @@ class CoachBPP:
             self.log_fn({"iter mean reward": float(np.mean(scores)),
                          "optimality percentage": float(np.mean(scores == 1.0)),
                          "min reward": float(np.min(scores)), "max reward": float(np.max(scores))}, step=i)
-            # flatten the iteration's examples: one row per played move
+            # flatten the iteration's examples: one row per played move (move-major, then game: np.nonzero order)
             moves = compact["moves"]
             N, G = compact["roots"].shape[0], compact["roots"].shape[1]
-            played = np.arange(N)[:, None] < moves[None, :]
-            mi, gi = np.nonzero(played)
-            counts = compact["counts"][mi, gi].astype(np.float32)
+            played = torch.arange(N, device=dev)[:, None] < moves[None, :]
+            mi, gi = played.nonzero(as_tuple=True)
+            counts = compact["counts"][mi, gi].to(torch.float32)
             if i > self.args.iterStepThreshold:
-                pis = np.zeros_like(counts)
-                pis[np.arange(len(mi)), compact["actions"][mi, gi]] = 1.0
+                pis = torch.zeros_like(counts)
+                pis[torch.arange(len(mi), device=dev), compact["actions"][mi, gi].long()] = 1.0
             else:
-                pis = counts / counts.sum(axis=1, keepdims=True)
-            history.append({"recs": compact["roots"][mi, gi], "items": compact["items"][gi], "pis": pis,
-                            "vs": compact["r"][gi].astype(np.float32)})
+                pis = counts / counts.sum(dim=1, keepdim=True)
+            history.append({"recs": compact["roots"][mi, gi], "items": compact["items"][gi].to(torch.int32), "pis": pis,
+                            "vs": compact["r"][gi].to(torch.float32)})
             if len(history) > self.args.numItersForTrainExamplesHistory:
                 history.pop(0)
             self._compact_history = history
-            recs_t = torch.from_numpy(np.concatenate([e["recs"] for e in history]).view(np.int32)).to(dev)
-            items_t = torch.from_numpy(np.concatenate([e["items"] for e in history]).astype(np.int32)).to(dev)
-            pis_t = torch.from_numpy(np.concatenate([e["pis"] for e in history])).to(dev)
-            vs_t = torch.from_numpy(np.concatenate([e["vs"] for e in history])).to(dev)
+
+            def cat(key, dt):
+                return torch.cat([torch.as_tensor(e[key]).to(dev).view(dt) if not isinstance(e[key], torch.Tensor)
+                                  else e[key] for e in history])
+            recs_t, items_t = cat("recs", torch.int32), cat("items", torch.int32)
+            pis_t, vs_t = cat("pis", torch.float32), cat("vs", torch.float32)
             torch.cuda.synchronize()
             t3 = time.perf_counter()
             if checkpoint and rank == 0:

@@ -42,13 +42,17 @@ def all_gather_variable(t):
 
 
 def gather_examples(compact, device):
-    """compact: dict of numpy arrays as returned by CoachBPP.executeEpisodesBatched(expand=False) with the game
-    dimension second for roots/counts/actions.  Returns the same dict with the games of all ranks concatenated."""
+    """compact: dict of numpy arrays (or device tensors, on_device=True) as returned by
+    CoachBPP.executeEpisodesBatched(expand=False) with the game dimension second for roots/counts/actions.  Returns the same dict with the games of all ranks concatenated."""
     rank, ws = world()
     if ws == 1:
         return compact
     out = {}
     for k, v in compact.items():
+        if isinstance(v, torch.Tensor):  # device-resident examples: no host hop on either side of the collective
+            game_axis = 1 if k in ("roots", "counts", "actions") else 0
+            out[k] = all_gather_variable(v.movedim(game_axis, 0).contiguous()).movedim(0, game_axis)
+            continue
         a = np.asarray(v)
         game_axis = 1 if k in ("roots", "counts", "actions") else 0
         t = torch.from_numpy(np.ascontiguousarray(np.moveaxis(a, game_axis, 0)).view(
