@@ -346,8 +346,9 @@ class CoachBPP:
         try:
             for net in (pnet, nnet):
                 self.nnet = net
-                _, score, _ = self.executeEpisodesBatched(items, areas, greedy=True, seed=seed, expand=False)
-                out.append(score)
+                _, score, _ = self.executeEpisodesBatched(items, areas, greedy=True, seed=seed, expand=False,
+                                                          on_device=True)  # only the G scores leave the device
+                out.append(score.cpu().numpy())
         finally:
             self.nnet = keep
         return out[0], out[1], 1 if np.mean(out[1]) >= np.mean(out[0]) else 0
