@@ -253,7 +253,8 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
     const uint32_t plane_b = (uint32_t)L.RT * 16u;
     const int rows_valid = nvalid * L.P;
     const int nt = min(L.ntiles, (rows_valid + 127) >> 7);  // tiles that hold at least one present sample
-    int tpp = T.tmem_cols / cout;                              // tiles in flight per pass
+    // tiles in flight per pass (cout is 16 or 32 in this network: no integer division on the issuer's critical path)
+    int tpp = cout == 16 ? T.tmem_cols >> 4 : cout == 32 ? T.tmem_cols >> 5 : T.tmem_cols / cout;
     if (tpp > MAX_BARS) tpp = MAX_BARS;
     for (int t0 = 0; t0 < nt; t0 += tpp) {
       const int nb = min(tpp, nt - t0);
