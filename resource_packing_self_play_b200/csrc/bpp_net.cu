@@ -539,8 +539,7 @@ struct HeadParams {
     const __nv_bfloat16* w2u;             // [16][2][N2][8]
     const float* b1;                      // [256]
     const float* b2;                      // [A]
-    const float* wv;                      // [256] (bf16-rounded values, as fp32)
-    float bv;
+    const float* wv;                      // [256] (bf16-rounded values, as fp32) + [256] = the value head's bias
 };
 #ifdef BPP_HEADS_PROF  // phase timers of the heads kernel (debug builds: nvcc -DBPP_HEADS_PROF), printed by CTA 0
 #define HP_T(i) t_[i] = clock64()
@@ -698,7 +697,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     //   B. thread = (row, column half): e = exp(logit - row max) back into the tile, sum of the half
     //   C. whole CTA: policy = e / row sum, one row per warp and pass, coalesced stores
     const int r = row0 + row_l;
-    if (hv == 0 && r < B) value[r] = tanhf(s_x0[0][row_l] + s_x0[1][row_l] + Hp.bv);
+    if (hv == 0 && r < B) value[r] = tanhf(s_x0[0][row_l] + s_x0[1][row_l] + __ldg(Hp.wv + HIDDEN));
     float* s_pol = reinterpret_cast<float*>(hsm);
     const int ldp = Hp.A | 1;  // odd row stride: the 32 rows of a warp fall into distinct banks
     float* prow = s_pol + row_l * ldp;
@@ -992,7 +991,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             if (cudaMalloc(&n->d_feat, (size_t)max_batch * P.flat * 2) != cudaSuccess ||
                 cudaMalloc(&n->d_w1u, (size_t)P.flat * HIDDEN * 2) != cudaSuccess ||
                 cudaMalloc(&n->d_w2u, (size_t)HIDDEN * Hp.N2 * 2) != cudaSuccess ||
-                cudaMalloc(&n->d_wv32, HIDDEN * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&n->d_wv32, (HIDDEN + 1) * sizeof(float)) != cudaSuccess ||
                 cudaFuncSetAttribute(k_net_heads_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, n->heads_smem) != cudaSuccess) {
                 cudaGetLastError();
                 delete n;
@@ -1110,7 +1109,7 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
     if (n->heads_ok) {  // FC weights in the UMMA K-major B layout [k-block][k-half][n][8]
         const HeadParams& Hp = n->Hp;
         std::vector<uint16_t> w1u((size_t)P.flat * HIDDEN, 0), w2u((size_t)HIDDEN * Hp.N2, 0);
-        std::vector<float> wv32(HIDDEN);
+        std::vector<float> wv32(HIDDEN + 1);  // + the value head's bias
         const std::vector<float>& h1 = n->host["hidden_fc.weight"];  // [256][flat]
         for (int kc = 0; kc < P.flat / 16; ++kc)
             for (int kh = 0; kh < 2; ++kh)
@@ -1130,7 +1129,9 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
             uint32_t hb = (uint32_t)f32_to_bf16_rne(v3[i]) << 16;
             memcpy(&wv32[i], &hb, 4);
         }
-        n->Hp.bv = n->host["value_fc.bias"][0];
+        // in device memory, not in the by-value kernel parameter: captured CUDA graphs replay the parameters of their
+        // capture, and the weights change between iterations
+        wv32[HIDDEN] = n->host["value_fc.bias"][0];
         if (cudaMemcpy(n->d_w1u, w1u.data(), w1u.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
             cudaMemcpy(n->d_w2u, w2u.data(), w2u.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
             cudaMemcpy(n->d_wv32, wv32.data(), wv32.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)

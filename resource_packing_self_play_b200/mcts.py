@@ -169,7 +169,7 @@ class BatchedMCTS:
                     eng.expand_select(self._pol, self._val)
                 else:
                     eng.expand_backup(self._pol, self._val)
-        key = (chunk, cap, self.fused, torch.cuda.current_stream().cuda_stream, net._h.value, getattr(net, "precision", None))
+        key = (chunk, cap, eng.num_sims, self.fused, torch.cuda.current_stream().cuda_stream, net._h.value, getattr(net, "precision", None))
         graph = self._graphs.get(key) if self.use_graphs else None
         if graph is None and self.use_graphs and self._eager_chunks >= 2:
             torch.cuda.synchronize()

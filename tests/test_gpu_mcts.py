@@ -227,21 +227,37 @@ def test_batched_mcts_fused_graph_replay_equals_plain_lockstep():
     items = ItemsGenerator(W, H, N).items_batch(np.arange(G) + 31000, heights)
     area = (W * heights).astype(np.int32)
     tie = np.ones(G, dtype=np.int8)
-    runs = []
-    for fused, graphs in ((True, True), (False, False), (True, False)):
-        bm = BatchedMCTS(Gm(), net, args, G)
-        bm.fused, bm.use_graphs = fused, graphs
+    def play(bm, moves):
         bm.reset(items, area, [0.5, 0.7, 0.9001], tie=tie)
         per_move = []
-        for m in range(6):
+        for m in range(moves):
             counts = bm.search(chunk=4)
             act = bm.eng.choose(_lib.CHOOSE_ARGMAX_FIRST)
             bm.eng.advance(act)
             per_move.append((counts.cpu().numpy().copy(), act.cpu().numpy().copy()))
         bm.eng.check()
-        runs.append((per_move, bm.graph_launches))
-    assert runs[0][1] > 0 and runs[1][1] == 0, "the first run must have replayed graphs, the second none"
-    for other in (runs[1][0], runs[2][0]):
-        for (c0, a0), (c1, a1) in zip(runs[0][0], other):
+        return per_move
+    runs, bms = [], []
+    for fused, graphs in ((True, True), (False, False), (True, False)):
+        bm = BatchedMCTS(Gm(), net, args, G)
+        bm.fused, bm.use_graphs = fused, graphs
+        runs.append(play(bm, 6))
+        bms.append(bm)
+    assert bms[0].graph_launches > 0 and bms[1].graph_launches == 0, "the first run must have replayed graphs"
+    for other in runs[1:]:
+        for (c0, a0), (c1, a1) in zip(runs[0], other):
             assert np.array_equal(c0, c1) and np.array_equal(a0, a1)
-    assert runs[0][0][0][0].sum() > 0
+    assert runs[0][0][0].sum() > 0
+    # new weights (as after a learner step) must reach the ALREADY CAPTURED graphs: every parameter lives in device
+    # buffers that are updated in place, nothing that changes is a by-value kernel argument
+    with torch.no_grad():
+        for prm in net.nnet.parameters():
+            prm.add_(0.05 * torch.randn_like(prm))
+        net.nnet.value_fc.bias.add_(0.4)
+    net.sync_weights()
+    before = bms[0].graph_launches
+    after_graph, after_eager = play(bms[0], 3), play(bms[1], 3)
+    assert bms[0].graph_launches > before
+    for (c0, a0), (c1, a1) in zip(after_graph, after_eager):
+        assert np.array_equal(c0, c1) and np.array_equal(a0, a1)
+    assert any(not np.array_equal(x[0], y[0]) for x, y in zip(after_graph, runs[0])), "the new weights changed nothing?"
