@@ -205,7 +205,7 @@ class BatchedMCTS:
         # a game whose simulations keep ending on terminal states parks no leaf: cap its work per launch so that it
         # does not delay the leaf batch of the others; once few leaves are left the cap is lifted
         if select_cap is None:
-            select_cap = int(os.environ.get("BPP_SELECT_CAP", "4"))
+            select_cap = int(os.environ.get("BPP_SELECT_CAP", "2"))
         lift = int(os.environ.get("BPP_SELECT_LIFT", "16"))
         eng.set_select_cap(select_cap)
         cap = select_cap
