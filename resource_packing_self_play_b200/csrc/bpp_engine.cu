@@ -416,6 +416,9 @@ k_expand_search(Params P, const void* policy, int policy_f64, const void* value,
     __shared__ WarpSmem smem[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    // the evaluator's trunk kernel, launched programmatically behind this one, may set itself up (barriers, tensor memory,
+    // first weights) on the SMs this kernel's short warps have left while its longest descents still run
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (g >= P.G) return;
     if (P.status[g] != 0) return;
     WarpSmem& sm = smem[wid];

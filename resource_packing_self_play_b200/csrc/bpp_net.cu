@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/bpp_b200.h"
@@ -261,7 +262,6 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     cx.wbuf = wbuf;
     for (int i = 0; i < 8; ++i) cx.prof[i] = 0;
     const long long t_start = clock64();
-    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
     const int S = T.S;
     const int cin16_0 = (P.Cin + 15) / 16;
     WPre pre;
@@ -269,6 +269,11 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     auto lay_b = [&](int l) { return P.bias + P.conv[l].b_off; };
     auto lay_wl = [&](int l) { return T.wts_umma_lo + T.w_off[l]; };
     if (!X3) wpre_load(pre, lay_w(0), T.lay_n16[0], lay_b(0), P.conv[0].co);
+    // everything above (barriers, TMEM, first weights) is independent of the kernel that produced the leaf batch: with a
+    // programmatic launch it overlaps that kernel's tail; the heads kernel behind us may start launching right away
+    pdl_launch_dependents();
+    pdl_wait();
+    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
     // every CTA takes one contiguous, equally sized slice of the batch and walks it in groups of <= S leaves: all CTAs
     // finish together (with "group g -> CTA g mod grid" a batch of 2,800 leaves left 36 % of the CTAs idle in the last wave)
     const int slice_lo = (int)(((long long)blockIdx.x * B) / gridDim.x);
@@ -568,9 +573,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     long long t_[8];
 #endif
     HP_T(0);
-    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
     const int row0 = blockIdx.x * 128;
-    if (row0 >= B) return;
     const int kplanes = (Hp.flat > HIDDEN ? Hp.flat : HIDDEN) / 8;
     unsigned char* areg = hsm;                                   // planes x 128 rows x 16 B
     unsigned char* stage0 = hsm + (size_t)kplanes * 2048;
@@ -592,20 +595,10 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         }
         asm volatile("cp.async.commit_group;" ::: "memory");  // one group per chunk slot, possibly empty
     };
-    // A operand: features of rows row0..row0+127 (zero beyond the batch): thread = (row, plane parity), 16 bytes per
-    // plane by cp.async, all copies in flight at once
-    {
-        const int r = row0 + row_l;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(feat + (size_t)r * Hp.flat);
-        for (int p = hv; p < Hp.flat / 8; p += 2) {
-            unsigned char* dst = areg + (size_t)p * 2048 + row_l * 16;
-            if (r < B) head_cp16(dst, src + p * 16);
-            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");  // group 0; the weight chunks follow
-    }
+    // Prologue that does not depend on the trunk kernel (with a programmatic launch it runs under the trunk's tail): the
+    // first weight chunks in flight, barriers, TMEM, biases.
 #pragma unroll
-    for (int c = 0; c < HEAD_STAGES; ++c) issue_chunk(c);  // weights are in flight while the rest of the prologue runs
+    for (int c = 0; c < HEAD_STAGES; ++c) issue_chunk(c);
     if (tid <= HEAD_STAGES) mbar_init(smem_u32(&s_bar[tid]), 1);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
@@ -617,7 +610,28 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         s_wv[i] = Hp.wv[i];
         s_b2[i] = i < Hp.A ? Hp.b2[i] : 0.f;
     }
-    asm volatile("cp.async.wait_group %0;" ::"n"(HEAD_STAGES) : "memory");  // the A operand (oldest group) has landed
+    pdl_wait();  // the trunk's features and the leaf count are complete and visible from here on
+    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
+    if (row0 >= B) {  // no leaves for this tile: drain the copies, give the tensor memory back
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(512u));
+        return;
+    }
+    // A operand: features of rows row0..row0+127 (zero beyond the batch): thread = (row, plane parity), 16 bytes per
+    // plane by cp.async, all copies in flight at once
+    {
+        const int r = row0 + row_l;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(feat + (size_t)r * Hp.flat);
+        for (int p = hv; p < Hp.flat / 8; p += 2) {
+            unsigned char* dst = areg + (size_t)p * 2048 + row_l * 16;
+            if (r < B) head_cp16(dst, src + p * 16);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // the A operand (newest group) and the first weight chunks have landed
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -1170,6 +1184,24 @@ extern "C" int bpp_net_set_precision(bpp_net* n, int mode) {
     return BPP_OK;
 }
 
+// launch with the programmatic-stream-serialization attribute (see pdl_wait in bpp_net_tc.cuh); BPP_NO_PDL=1 falls back
+// to plain stream order
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool use_pdl = getenv("BPP_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, const uint32_t* recs_dev,
                                const int32_t* game_dev, const int32_t* items_wh_dev, float* policy_out_dev,
                                float* value_out_dev, void* stream) {
@@ -1186,8 +1218,8 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
         if (fo && n->ctas_per_sm == 2)
-            k_net_forward_tc<8, false, true, 2><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
-                n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
+            launch_pdl(k_net_forward_tc<8, false, true, 2>, g2, bpptc::TC_THREADS, (size_t)n->T.smem_bytes, st, n->P, n->T, B,
+                       count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
         else if (n->T.S <= 4)
             k_net_forward_tc<4, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
                 n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
@@ -1195,8 +1227,8 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
             k_net_forward_tc<8, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
                 n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
         if (fo)
-            k_net_heads_tc<<<(B + 127) / 128, HEAD_THREADS, n->heads_smem, st>>>(n->Hp, B, count_dev, n->d_feat,
-                                                                               policy_out_dev, value_out_dev);
+            launch_pdl(k_net_heads_tc, (B + 127) / 128, HEAD_THREADS, (size_t)n->heads_smem, st, n->Hp, B, count_dev,
+                       (const __nv_bfloat16*)n->d_feat, policy_out_dev, value_out_dev);
     } else if (n->precision == BPP_NET_BF16X3 && n->tc3_ok) {
         const int groups = (B + n->T3.S - 1) / n->T3.S;
         const int g2 = groups < 148 ? groups : 148;

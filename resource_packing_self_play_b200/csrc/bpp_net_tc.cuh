@@ -64,6 +64,12 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may become
+// resident while its predecessor in the stream still runs; pdl_wait() blocks until the predecessor grid has completed and
+// its writes are visible (a no-op for a normal launch), pdl_launch_dependents() lets the successor start launching.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
