@@ -164,6 +164,10 @@ int bpp_engine_select(bpp_engine *e, void *stream);
 /* number of parked leaves (synchronises `stream`); a count of 0 completes the select/expand pairing, i.e. no
  * bpp_engine_expand_backup call is needed (every game has finished its simulations for this move) */
 int bpp_engine_leaf_count(bpp_engine *e, int32_t *count_host, void *stream);
+/* the same without synchronising: copies {parked leaves, games stopped by the select cap} into counts_host2 (int32[2],
+ * pinned host memory) in stream order; the caller waits on its own event.  Lets a driver queue the next chunk of
+ * lockstep steps before it learns whether the previous one finished the move (steps after the end are no-ops). */
+int bpp_engine_leaf_count_async(bpp_engine *e, int32_t *counts_host2, void *stream);
 /* device-side leaf batch for a device evaluator: count int32[1], game index int32 [<=G], records uint32 [<=G][32]
  * (row b = leaf b).  Pointers stay valid for the life of the handle. */
 int bpp_engine_leaf_buffers(bpp_engine *e, const int32_t **count_dev, const int32_t **game_dev,

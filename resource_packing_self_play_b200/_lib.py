@@ -58,6 +58,7 @@ SIGNATURES = {
     "bpp_engine_leaf_planes": [_vp, _vp, _vp],
     "bpp_engine_expand_backup": [_vp, _vp, _i32, _vp, _i32, _vp],
     "bpp_engine_expand_select": [_vp, _vp, _i32, _vp, _i32, _vp],
+    "bpp_engine_leaf_count_async": [_vp, _vp, _vp],
     "bpp_engine_search_stub": [_vp, _i32, _vp],
     "bpp_engine_root_counts": [_vp, _vp, _vp],
     "bpp_engine_root_counts_host": [_vp, _vp, _vp],

@@ -1239,6 +1239,12 @@ extern "C" int bpp_engine_leaf_count(bpp_engine* e, int32_t* count_host, void* s
     return BPP_OK;
 }
 
+extern "C" int bpp_engine_leaf_count_async(bpp_engine* e, int32_t* counts_host2, void* stream) {
+    if (!e || !counts_host2) return set_err(BPP_E_INVALID, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(counts_host2, e->P.leaf_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    return BPP_OK;
+}
+
 extern "C" int bpp_engine_leaf_buffers(bpp_engine* e, const int32_t** count_dev, const int32_t** game_dev,
                                        const uint32_t** recs_dev) {
     if (!e) return set_err(BPP_E_INVALID, "null argument");

@@ -243,6 +243,10 @@ class SearchEngine:
         call("bpp_engine_leaf_count", self._h, C.byref(n), _stream())
         return int(n.value)
 
+    def leaf_count_async(self, pinned2):
+        """queue a copy of [parked leaves, capped games] into a pinned int32[2] tensor (no synchronisation)"""
+        call("bpp_engine_leaf_count_async", self._h, C.c_void_p(pinned2.data_ptr()), _stream())
+
     def leaf_planes(self, count):
         out = torch.empty((count, self.N + 1, self.H, self.W), dtype=torch.float32, device=self.device)
         if count:

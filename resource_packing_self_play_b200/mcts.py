@@ -144,6 +144,7 @@ class BatchedMCTS:
         self.steps = 0
         self.use_graphs = os.environ.get("BPP_NO_GRAPHS") is None
         self.fused = os.environ.get("BPP_NO_FUSED_STEP") is None
+        self.pipeline = os.environ.get("BPP_NO_PIPELINE") is None
         self._graphs, self._eager_chunks, self.graph_launches = {}, 0, 0
 
     def reset(self, items_wh, total_area, rewards_list, tie=None):
@@ -211,13 +212,38 @@ class BatchedMCTS:
         cap = select_cap
         if self.fused:
             eng.select()   # the first leaves of the move; every later select rides on the expansion launch
-        while True:
-            self._run_chunk(chunk, cap, count_ptr, game_ptr, recs_ptr)
-            n = eng.leaf_count()
-            if n == 0 and eng.unfinished() == 0:  # nothing parked, nobody capped: the move is complete
-                break
-            if n < self.G // lift and cap != 0:
-                eng.set_select_cap(0)
-                cap = 0
+        if self.fused and self.use_graphs and self.pipeline:
+            # chunk k+1 is queued BEFORE the host learns how chunk k ended (async read-back of the counters into pinned
+            # memory + an event): no idle GPU at the chunk boundaries.  Steps queued after the move is complete are
+            # no-ops (nothing parked, nobody owes simulations), so the one speculative chunk at the end changes nothing.
+            if getattr(self, "_poll", None) is None:
+                self._poll = [(torch.zeros(2, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+            prev, k = None, 0
+            while True:
+                self._run_chunk(chunk, cap, count_ptr, game_ptr, recs_ptr)
+                buf, ev = self._poll[k & 1]
+                eng.leaf_count_async(buf)
+                ev.record()
+                if prev is not None:
+                    pbuf, pev = prev
+                    pev.synchronize()
+                    n, unfinished = int(pbuf[0]), int(pbuf[1])
+                    if n == 0 and unfinished == 0:
+                        break
+                    if n < self.G // lift and cap != 0:
+                        eng.set_select_cap(0)
+                        cap = 0
+                prev, k = (buf, ev), k + 1
+            n = eng.leaf_count()  # synchronises and settles the engine's host-side pairing state
+            assert n == 0 and eng.unfinished() == 0
+        else:
+            while True:
+                self._run_chunk(chunk, cap, count_ptr, game_ptr, recs_ptr)
+                n = eng.leaf_count()
+                if n == 0 and eng.unfinished() == 0:  # nothing parked, nobody capped: the move is complete
+                    break
+                if n < self.G // lift and cap != 0:
+                    eng.set_select_cap(0)
+                    cap = 0
         eng.set_select_cap(0)
         return eng.root_counts()
