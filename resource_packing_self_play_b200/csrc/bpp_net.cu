@@ -338,32 +338,46 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         __syncthreads();
         TC_PROF(0, tq);
         // ---- three ConvSequences
+        // Arena use.  Classic: region A = level-0 input, then the {raw, actA, actB} triples; region B = conv outputs T
+        // awaiting pooling; weights behind both.  Compact (bf16 trunk, two CTAs per SM): the triples live in region B;
+        // T_0 ALIASES the input planes, shifted down by `guard` rows - tile t's epilogue writes physical rows
+        // [128t, 128t+128) while the MMAs still queued (tiles > t, issued and completed in order) read input rows
+        // >= 128(t+1) - wp - 1, i.e. physical rows >= 128(t+1) because guard >= wp + 1; T_1, T_2 and every layer's
+        // weights sit in whatever region is idle at that layer.  This halves the level-0 footprint: larger groups.
+        const bool compact = !X3 && T.compact;
+        unsigned char* const tri = compact ? regB : regA;
         const unsigned char* in = regA;
         int cin16 = cin16_0, li = 0;
-        unsigned char* raw = regA;
+        unsigned char* raw = tri;
         for (int s = 0; s < 3; ++s) {
             const Level& La = T.lv[s];
             const Level& Lb = T.lv[s + 1];
             const int cout = P.conv[li].co;
             const uint32_t in_lo = (uint32_t)(2 * cin16) * (uint32_t)La.RT * 16u;   // bytes of the input's hi planes
             const uint32_t t_lo = (uint32_t)(cout / 8) * (uint32_t)La.RT * 16u;     // bytes of T's hi planes
-            conv_layer<X3>(T, cx, La, nvalid, cin16, cout, lay_w(li), lay_b(li), in, EPI_CONV, regB, nullptr, pre,
+            unsigned char* Tbuf = regB;
+            if (compact) {
+                Tbuf = s == 0 ? regA - (size_t)La.guard * 16 : regA;
+                cx.wbuf = s == 0 ? regB : regA + ((t_lo + 127u) & ~127u);
+            }
+            conv_layer<X3>(T, cx, La, nvalid, cin16, cout, lay_w(li), lay_b(li), in, EPI_CONV, Tbuf, nullptr, pre,
                            lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co, lay_wl(li), in_lo, t_lo, 0u);
             ++li;
             tq = clock64();
             const int planes = cout / 8;
             const size_t pb = (size_t)planes * Lb.RT * 16;   // one logical buffer (hi planes)
             const size_t bs = X3 ? 2 * pb : pb;               // stride between logical buffers (hi [+ lo])
-            raw = regA;
-            unsigned char* actA = regA + bs;
-            unsigned char* actB = regA + 2 * bs;
-            zero_bytes(regA, (int)(3 * bs));
-            if (!X3) pool_pad_tail(La, nvalid, planes, regB);
+            raw = tri;
+            unsigned char* actA = tri + bs;
+            unsigned char* actB = tri + 2 * bs;
+            zero_bytes(tri, (int)(3 * bs));
+            if (!X3) pool_pad_tail(La, nvalid, planes, Tbuf);
             __syncthreads();
-            if (X3) pool_level_x3(La, Lb, nvalid, planes, regB, t_lo, raw, (uint32_t)pb, actA, (uint32_t)pb);
-            else pool_level(La, Lb, nvalid, planes, regB, raw, actA);
+            if (X3) pool_level_x3(La, Lb, nvalid, planes, Tbuf, t_lo, raw, (uint32_t)pb, actA, (uint32_t)pb);
+            else pool_level(La, Lb, nvalid, planes, Tbuf, raw, actA);
             __syncthreads();
             TC_PROF(5, tq);
+            if (compact) cx.wbuf = regA;  // T is dead: the residual layers' weights go to region A
             for (int blk = 0; blk < 2; ++blk) {
                 conv_layer<X3>(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actA, EPI_RES0, actB, nullptr, pre,
                                lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co, lay_wl(li),
@@ -910,9 +924,11 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         const int cin16_0 = (P.Cin + 15) / 16;
         // ctas_want = CTAs per SM the plan is made for (bf16 mode: 1 or 2; they share the SM's 227 KB of shared memory,
         // its registers and its 512 TMEM columns); the largest group size S whose buffers fit is taken
-        auto plan = [&](bpptc::TcParams& T, bool x3, int cap_bytes, int ctas_want, int& ctas_out) -> bool {
+        auto plan = [&](bpptc::TcParams& T, bool x3, int cap_bytes, int ctas_want, int& ctas_out, bool allow_compact) -> bool {
             const int f = x3 ? 2 : 1;
-            for (int S = 8; S >= 1; --S) {
+            const char* smax_env = getenv("BPP_TC_SMAX");  // experiments: cap the group size
+            const int smax = smax_env ? std::max(1, std::min(8, atoi(smax_env))) : 8;
+            for (int S = smax; S >= 1; --S) {
                 for (int l = 0; l < 4; ++l) {
                     bpptc::Level& L = T.lv[l];
                     // shared halos: one zero column between consecutive grid rows (the right halo of row y IS the left
@@ -935,11 +951,27 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                 if (x3 || ctas_want < 2)  // in-kernel CUDA-core heads need their scratch
                     b = std::max(b, (long long)NSs * (P.flat + 4 * HIDDEN + 3 * (P.A + 1)) * 4);
                 // the last tile's shifted windows over-read up to 128 + wp + 1 rows behind region A: region B must cover that
-                b = std::max(b, (long long)(128 + T.lv[0].wp + 8) * 16);
+                const long long over = (long long)(128 + T.lv[0].wp + 8) * 16;
+                b = std::max(b, over);
                 T.S = S;
+                T.compact = (allow_compact && !x3 && ctas_want >= 2) ? 1 : 0;
+                if (T.compact) {
+                    // compact arena (see k_net_forward_tc): A = max(input [= aliased T_0], T_s + conv weights of
+                    // sequences 1 and 2, residual weights); B = max(level triples, level-0 conv weights) + over-read slack
+                    auto wbytes = [&](int l) { return (long long)T.lay_n16[l] * 16 + 256; };
+                    long long ca = (long long)2 * cin16_0 * T.lv[0].RT * 16, cb = wbytes(0);
+                    for (int s2 = 0; s2 < 3; ++s2) {
+                        const long long planes = chans[s2] / 8;
+                        if (s2 > 0) ca = std::max(ca, ((planes * T.lv[s2].RT * 16 + 127) & ~127LL) + wbytes(5 * s2));
+                        cb = std::max(cb, 3 * planes * T.lv[s2 + 1].RT * 16);
+                        for (int l = 5 * s2 + 1; l < 5 * s2 + 5; ++l) ca = std::max(ca, wbytes(l));
+                    }
+                    if (chans[0] / 8 > 2 * cin16_0) T.compact = 0;  // T_0 must fit into the input's planes
+                    else { a = ca; b = cb + over; }
+                }
                 T.regA_bytes = (int)((a + 127) & ~127LL);
                 T.regB_bytes = (int)((b + 127) & ~127LL);
-                T.wbuf_bytes = (f * wmax + 256 + 127) & ~127;     // + the layer's bias behind the weights
+                T.wbuf_bytes = T.compact ? 0 : ((f * wmax + 256 + 127) & ~127);     // + the layer's bias behind the weights
                 T.smem_bytes = T.regA_bytes + T.regB_bytes + T.wbuf_bytes;
                 if (T.smem_bytes <= cap_bytes && T.lv[0].RT < 16384) {
                     T.tmem_cols = ctas_want == 2 ? 256 : 512;
@@ -960,11 +992,29 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             const bool heads_possible = (P.flat % 16 == 0) && ((P.A + 15) & ~15) <= 256 && hsm <= 220 * 1024 &&
                                         getenv("BPP_NO_TC_HEADS") == nullptr;
             if (!heads_possible) want = 1;  // the multi-CTA instantiations are trunk-only
-            n->tc_ok = plan(T, false, (227 * 1024) / want - 1024 - 4352, want, n->ctas_per_sm);
+            // The compact arena holds larger groups but costs ~3 % at equal group size (measured: 15x15, S = 5, both
+            // layouts), so it is taken only where it buys at least a third more leaves per group (20x20: 4 instead of 3,
+            // +8..15 %); BPP_TC_COMPACT=0/1 forces the choice.
+            const int cap = (227 * 1024) / want - 1024 - 4352;
+            bpptc::TcParams Tc = T;
+            int ctas_c = 1;
+            n->tc_ok = plan(T, false, cap, want, n->ctas_per_sm, false);
+            const bool okc = plan(Tc, false, cap, want, ctas_c, true) && Tc.compact;
+            const char* fc = getenv("BPP_TC_COMPACT");
+            const bool take = okc && (fc ? atoi(fc) != 0 : (!n->tc_ok || 3 * Tc.S >= 4 * T.S));
+            if (take) {
+                T = Tc;
+                n->ctas_per_sm = ctas_c;
+                n->tc_ok = true;
+            }
         }
+        if (getenv("BPP_TC_VERBOSE"))
+            fprintf(stderr, "bpp_net: tcgen05 plan %dx%d: S = %d, %d CTA(s)/SM, %s arena, %d B shared memory (A %d, B %d)\n",
+                    P.W, P.H, T.S, n->ctas_per_sm, T.compact ? "compact" : "classic", T.smem_bytes, T.regA_bytes,
+                    T.regB_bytes);
         n->T3 = T;
         int c3 = 1;
-        n->tc3_ok = plan(n->T3, true, 220 * 1024, 1, c3);
+        n->tc3_ok = plan(n->T3, true, 220 * 1024, 1, c3, false);
     }
     n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
     if (cudaFuncSetAttribute(k_net_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=

@@ -47,6 +47,8 @@ struct TcParams {
     int regA_bytes;        // region A: input planes of level 0, then the {raw, actA, actB} triple of levels 1..3
     int regB_bytes;        // region B: conv outputs awaiting pooling (T_0..T_2), then the head scratch
     int wbuf_bytes;        // one layer of weights
+    int compact;           // 1: compact arena (see the plan in bpp_net_create): T_0 aliases the input planes, the level
+                           // triples live in region B, the weights wherever the current layer leaves room
     int smem_bytes;
     int tmem_cols;         // TMEM columns allocated per CTA: 512 / (CTAs per SM), a power of two
     long long w_off[15];   // element offsets of each conv layer in wts_umma
