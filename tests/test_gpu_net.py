@@ -155,3 +155,31 @@ def test_tensor_core_kernel_matches_the_simt_kernel_with_the_same_roundings(tag,
         assert float((pi_tc.sum(dim=1) - 1).abs().max()) < 1e-4
         assert float((pi_tc - pi_s).abs().max()) <= tol, (B, float((pi_tc - pi_s).abs().max()))
         assert float((v_tc - v_s).abs().max()) <= tol
+
+
+@pytest.mark.parametrize("W,H,N,B", [(15, 15, 10, 777), (20, 20, 10, 301), (9, 12, 5, 64)])
+def test_both_shared_memory_plans_of_the_tensor_core_kernel_agree_bit_for_bit(W, H, N, B, monkeypatch):
+    """The classic and the compact shared-memory arena (the latter aliases the level-0 conv output with its own input
+    planes and relocates triples and weights) run the same arithmetic in the same order: identical outputs, for ragged
+    batch sizes (partial groups, partial tiles)."""
+    from resource_packing_self_play_b200.engine import pack_states  # noqa: F401
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+    rng = np.random.RandomState(1)
+    recs = np.zeros((B, 32), dtype=np.uint32)
+    recs[:, :H] = rng.randint(0, 1 << W, size=(B, H)) & rng.randint(0, 1 << W, size=(B, H))
+    recs[:, 28] = rng.randint(1, 1 << N, size=B)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(B) % 53 + 9, None)
+    outs = []
+    for compact in ("0", "1"):
+        monkeypatch.setenv("BPP_TC_COMPACT", compact)
+        torch.manual_seed(4)
+        net = NNetWrapper(_Game(W, H, N), dotdict(num_items=N, num_bins=1, cuda=True, epochs=1, batch_size=8),
+                          max_batch=B, precision="bf16")
+        dev = net.device
+        pol, val = net.dnet.forward(torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev))
+        torch.cuda.synchronize()
+        outs.append((pol.cpu().numpy(), val.cpu().numpy()))
+    assert np.isfinite(outs[0][0]).all() and abs(outs[0][0].sum(axis=1) - 1).max() < 1e-4
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
