@@ -565,7 +565,8 @@ struct HeadParams {
 #else
 #define HP_T(i)
 #endif
-constexpr int HEAD_THREADS = 256;           // warps w and w + 4 share a TMEM lane quarter (rows) and split the columns
+constexpr int HEAD_THREADS = 512;           // warps w, w + 4, w + 8, w + 12 share a TMEM lane quarter (rows) and split the columns
+constexpr int HEAD_NQ = HEAD_THREADS / 128;  // column parts per row
 constexpr int HEAD_STAGES = 4;               // ring of weight stages filled by cp.async, drained by the MMAs
 constexpr int HEAD_STAGE_BYTES = 16 * 1024;
 
@@ -580,9 +581,9 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     extern __shared__ __align__(1024) unsigned char hsm[];
     __shared__ __align__(8) uint64_t s_bar[HEAD_STAGES + 1];  // [s]: MMAs that read stage s are done; [last]: GEMM done
     __shared__ uint32_t s_tmem;
-    __shared__ float s_b1[HIDDEN], s_wv[HIDDEN], s_b2[256], s_x0[2][128], s_x1[2][128];
+    __shared__ float s_b1[HIDDEN], s_wv[HIDDEN], s_b2[256], s_x0[HEAD_NQ][128], s_x1[HEAD_NQ][128];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int row_l = tid & 127, hv = tid >> 7;  // row of the tile, column half
+    const int row_l = tid & 127, hv = tid >> 7;  // row of the tile, column part (0 .. HEAD_NQ-1)
 #ifdef BPP_HEADS_PROF
     long long t_[8];
 #endif
@@ -638,7 +639,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     {
         const int r = row0 + row_l;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(feat + (size_t)r * Hp.flat);
-        for (int p = hv; p < Hp.flat / 8; p += 2) {
+        for (int p = hv; p < Hp.flat / 8; p += HEAD_NQ) {
             unsigned char* dst = areg + (size_t)p * 2048 + row_l * 16;
             if (r < B) head_cp16(dst, src + p * 16);
             else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
@@ -700,7 +701,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     // epilogue 1: hidden = relu(acc + b1) -> bf16 planes (A operand of the logits GEMM) + value head dot product
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float vacc = 0.f;
-    for (int c0 = hv * (HIDDEN / 2); c0 < (hv + 1) * (HIDDEN / 2); c0 += 16) {
+    for (int c0 = hv * (HIDDEN / HEAD_NQ); c0 < (hv + 1) * (HIDDEN / HEAD_NQ); c0 += 16) {
         float v[16];
         tmem_ld16(lane_base + (uint32_t)c0, v);
         uint32_t pk[8];
@@ -714,7 +715,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8) * 2048 + row_l * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8 + 1) * 2048 + row_l * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
-    s_x0[hv][row_l] = vacc;  // the value head's dot product: one half per thread
+    s_x0[hv][row_l] = vacc;  // the value head's dot product: one part per thread
     tc_fence_before();
     __syncthreads();  // all hidden planes written (run_chunks fences them towards the async proxy before its first MMA)
     HP_T(3);
@@ -725,12 +726,17 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     //   B. thread = (row, column half): e = exp(logit - row max) back into the tile, sum of the half
     //   C. whole CTA: policy = e / row sum, one row per warp and pass, coalesced stores
     const int r = row0 + row_l;
-    if (hv == 0 && r < B) value[r] = tanhf(s_x0[0][row_l] + s_x0[1][row_l] + __ldg(Hp.wv + HIDDEN));
+    if (hv == 0 && r < B) {
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < HEAD_NQ; ++q) dot += s_x0[q][row_l];
+        value[r] = tanhf(dot + __ldg(Hp.wv + HIDDEN));
+    }
     float* s_pol = reinterpret_cast<float*>(hsm);
     const int ldp = Hp.A | 1;  // odd row stride: the 32 rows of a warp fall into distinct banks
     float* prow = s_pol + row_l * ldp;
-    const int csplit = min(Hp.A, ((Hp.A / 2 + 15) >> 4) << 4);
-    const int cbeg = hv ? csplit : 0, cend = hv ? Hp.A : csplit;
+    const int cw = (((Hp.A + HEAD_NQ - 1) / HEAD_NQ + 15) >> 4) << 4;  // columns per part, a multiple of the 16-column TMEM load
+    const int cbeg = min(Hp.A, hv * cw), cend = min(Hp.A, (hv + 1) * cw);
     float mx = -INFINITY;
     for (int c0 = cbeg; c0 < cend; c0 += 16) {
         float v[16];
@@ -748,7 +754,9 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     tc_fence_before();
     __syncthreads();
     HP_T(5);
-    mx = fmaxf(s_x1[0][row_l], s_x1[1][row_l]);
+    mx = s_x1[0][row_l];
+#pragma unroll
+    for (int q = 1; q < HEAD_NQ; ++q) mx = fmaxf(mx, s_x1[q][row_l]);
     float sum = 0.f;
 #pragma unroll 4
     for (int c = cbeg; c < cend; ++c) {
@@ -762,7 +770,10 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     {
         const int nrows = min(128, B - row0), lane = tid & 31;
         for (int rr = warp; rr < nrows; rr += HEAD_THREADS / 32) {  // one row per warp and pass, 8 independent loads
-            const float inv = __fdividef(1.f, s_x0[0][rr] + s_x0[1][rr]);
+            float den = 0.f;
+#pragma unroll
+            for (int q = 0; q < HEAD_NQ; ++q) den += s_x0[q][rr];
+            const float inv = __fdividef(1.f, den);
             const float* src = s_pol + rr * ldp;
             float* dst = policy + (size_t)(row0 + rr) * Hp.A;
             float v[8];
