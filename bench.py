@@ -398,6 +398,9 @@ def _cpu_real_episode(ep_index, sims, Wb, Hb, net):
             return moves * sims
 
 
+NET_TRAFFIC_NCU = {(15, 15, 10): 706.3e3 + 776.4e3}
+
+
 def run_real_arm(args):
     import torch
     from resource_packing_self_play_b200 import _lib
@@ -509,7 +512,11 @@ def run_real_arm(args):
             "gpu_launches": graph_launches + st["launches"] + (0 if bm.use_graphs else 2 * (bm.steps - steps_before)),
             "cuda_graphs": bool(bm.use_graphs), "ms_per_step_eager_launches": eager_ms / args.steps,
             "roofline": {"bound": "tensor", "kernel": "k_net_forward_tc + k_net_heads_tc", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak,
+                         # dram__bytes_read + write per launch of trunk + heads, ncu on this very workload
+                         # (profiles/r01_real15_lockstep_kernels_ncu.csv): weights and leaf records only, everything
+                         # else stays in shared / tensor memory; not captured for the other geometries
+                         "traffic": NET_TRAFFIC_NCU.get((Wb, Hb, N)),
                          "flop_per_eval": flops, "evals_per_launch": eager_st["expansions"] / max(1, n_fwd),
                          "kernel_share_of_step": fwd_ms / eager_ms,
                          "measured_in": "eager-launch pass of the same steps (CUDA events around every forward)",
