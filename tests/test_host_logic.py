@@ -128,3 +128,21 @@ def test_torch_module_is_the_reference_architecture():
         assert np.abs(v.view(-1).numpy() - d[tag + "_v"]).max() < 1e-4
         if tag == "ck":
             assert sum(p.numel() for p in net.parameters()) == 170583
+
+
+def test_multiply_shift_division_used_by_the_forward_kernel_is_exact():
+    """bpptc::fdiv (csrc/bpp_net_tc.cuh): n // d == (n * ceil(2^32 / d)) >> 32 for every divisor and dividend the kernel
+    can form (row indices below 2^15 + tile padding, divisors = rows per leaf, row pitch, h*w, w, batch slices);
+    d = 1 is encoded as magic 0 and bypasses the multiply."""
+    n = np.arange(0, 40000, dtype=np.uint64)
+    for d in list(range(2, 1200)) + [4095, 4096, 4097, 16383, 16384, 32767, 65535]:
+        m = np.uint64(0xFFFFFFFF // d + 1)
+        assert m < (1 << 32)
+        q = (n * m) >> np.uint64(32)
+        assert np.array_equal(q, n // np.uint64(d)), d
+    # the bound the kernel relies on: exact whenever n * d < 2^32
+    rng = np.random.RandomState(0)
+    d = rng.randint(2, 65536, size=200000).astype(np.uint64)
+    nn = (rng.randint(0, 1 << 31, size=200000).astype(np.uint64) * np.uint64(2)) % ((np.uint64(1) << np.uint64(32)) // d)
+    m = np.uint64(0xFFFFFFFF) // d + np.uint64(1)
+    assert np.array_equal((nn * m) >> np.uint64(32), nn // d)
