@@ -36,6 +36,11 @@ def _worker(rank, ws, port, out):
     res["gather_ok"] = (g["roots"].shape == (10, 7, 32) and g["roots"].dtype == np.uint32 and
                         g["moves"].tolist() == [5, 5, 5, 6, 6, 6, 6] and g["counts"][:, 3:].min() == 1 and
                         g["counts"][:, :3].max() == 0 and g["r"].tolist() == [1, 1, 1, -1, -1, -1, -1])
+    # (2b) the same with torch tensors (the device-resident path of learn_batched: no numpy hop around the collective)
+    tcompact = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v) for k, v in compact.items()}
+    tg = D.gather_examples(tcompact, torch.device("cpu"))
+    res["gather_tensor_ok"] = all(isinstance(v, torch.Tensor) for v in tg.values()) and all(
+        np.array_equal(tg[k].numpy(), g[k].view(np.int32) if g[k].dtype == np.uint32 else g[k]) for k in g)
     # (3) gradient all-reduce == mean of the per-rank gradients; parameters stay in sync
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
