@@ -114,7 +114,8 @@ typedef struct bpp_config {
     int32_t num_sims;     /* args.numMCTSSims */
     double cpuct;         /* args.cpuct */
     int32_t node_cap;     /* nodes per game; 0 = num_sims*N + 2 (the per-episode worst case) */
-    int64_t edge_cap;     /* 8-byte edge units per game; 0 = auto (worst case if it fits in free memory) */
+    int64_t edge_cap;     /* 8-byte edge units per game; 0 = auto: a quarter of the worst case (3x the measured maximum),
+                             clipped to half of the free device memory; overflow = sticky BPP_E_CAPACITY, re-create larger */
     int32_t device;       /* CUDA device ordinal */
 } bpp_config;
 
@@ -122,6 +123,8 @@ int bpp_engine_create(const bpp_config *cfg, bpp_engine **out);
 int bpp_engine_destroy(bpp_engine *e);
 /* bytes of device memory held by the handle */
 int64_t bpp_engine_device_bytes(const bpp_engine *e);
+/* edge-pool capacity per game actually allocated (8-byte units), see bpp_config.edge_cap */
+int bpp_engine_edge_cap(const bpp_engine *e, int64_t *units_out);
 
 /* New episode for every game (a fresh MCTS object, CoachBPP.py:124, plus getInitBoard/getInitItems,
  * BinPackingGame.py:24-51).  items_wh: int32 [G][N][2]; total_area: int32 [G]; bl: float64 [G] (NaN = empty
@@ -224,9 +227,50 @@ int bpp_engine_play_stub_host(bpp_engine *e, int stub_kind, int choose_mode, uin
                               const int8_t *tie_host, int32_t *counts_out_host, int32_t *actions_out_host,
                               int32_t *r_out_host, double *score_out_host, int32_t *moves_out_host, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Asynchronous self-play episodes with the batched device evaluator (CoachBPP.executeEpisode, CoachBPP.py:50-99, for
+ * all G games at once; the real-net counterpart of bpp_engine_play_stub).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct bpp_net bpp_net;
+
+/* Arm (choose_mode = BPP_CHOOSE_*) or disarm (choose_mode = -1) per-game move completion inside
+ * bpp_engine_expand_select: a game that has run its num_sims simulations writes its visit-count row
+ * counts_out_dev[m][g][:] (MCTS_bpp.py:40-41), the root record it searched from roots_out_dev[m][g][:] (getBinItem of the
+ * example, CoachBPP.py:74-80), chooses with the stream (seed, game, move number) exactly like bpp_engine_choose, stores
+ * actions_out_dev[m][g], plays the move like bpp_engine_advance (CoachBPP.py:88-98) and continues with the next move in
+ * the same launch.  No game waits for the slowest game of a move; results per game are identical to the per-move
+ * sequence select/expand ... root_counts, choose, advance.  counts int32 [N][G][A], actions int32 [N][G], roots uint32
+ * [N][G][32]; any may be NULL; caller-zeroed. */
+int bpp_engine_set_auto_play(bpp_engine *e, int choose_mode, uint64_t seed, int32_t *counts_out_dev,
+                             int32_t *actions_out_dev, uint32_t *roots_out_dev);
+/* progress counters of the last select / expand_select launch, copied in stream order into counts_host4 (int32[4],
+ * pinned): [0] parked leaves, [1] games stopped by the select cap, [2] games still playing their episode, [3] 0 */
+int bpp_engine_progress_async(bpp_engine *e, int32_t *counts_host4, void *stream);
+/* Whole episodes for all G games after bpp_engine_reset: loops {bpp_net_forward on the parked leaves ->
+ * bpp_engine_expand_select} with auto-play armed until every game has ended; the lockstep steps are queued in chunks and
+ * the host only reads the progress counters of the previous chunk.  Output rows of moves a game did not play: counts 0,
+ * action -1, root 0.  Synchronises the stream.  steps_run_host (may be NULL) = lockstep steps queued. */
+int bpp_engine_play_net(bpp_engine *e, bpp_net *net, int choose_mode, uint64_t seed, int32_t *counts_out_dev,
+                        int32_t *actions_out_dev, uint32_t *roots_out_dev, int32_t *steps_run_host, void *stream);
+/* Accounting pass for bench.py: with on != 0 bpp_engine_play_net records CUDA events around every evaluator call and every
+ * expand_select call (slower: use it for kernel shares, not for throughput) and accumulates their durations;
+ * bpp_engine_profile returns {evaluator ms, expand+select ms, lockstep steps timed, 0} since the last set_profile. */
+int bpp_engine_set_profile(bpp_engine *e, int on);
+int bpp_engine_profile(bpp_engine *e, double ms_out4[4]);
+/* The same with HOST buffers, the reference-facing batched executeEpisode with the real net: uploads the instances,
+ * resets, plays, downloads the compact examples (root records + visit counts + actions per move) and the outcomes.
+ * roots_out_host uint32 [N][G][32], counts_out_host int32 [N][G][A], actions_out_host int32 [N][G], r_out_host int32
+ * [G], score_out_host float64 [G], moves_out_host int32 [G]; any output may be NULL.  BPP_E_CAPACITY if a game
+ * overflowed its pools. */
+int bpp_engine_play_net_host(bpp_engine *e, bpp_net *net, int choose_mode, uint64_t seed, const int32_t *items_wh_host,
+                             const int32_t *total_area_host, const double *bl_host, const int8_t *tie_host,
+                             uint32_t *roots_out_host, int32_t *counts_out_host, int32_t *actions_out_host,
+                             int32_t *r_out_host, double *score_out_host, int32_t *moves_out_host,
+                             int32_t *steps_run_host, void *stream);
+
 /* Counters since creation (or the last bpp_engine_stats with reset != 0), copied to the host (synchronises):
  * [0] simulations, [1] edges traversed, [2] expansions, [3] terminal hits, [4] nodes created, [5] hash probes,
- * [6] kernels launched by this handle, [7] reserved. */
+ * [6] kernels launched by this handle, [7] 8-byte edge-block units read by the PUCT selections (layout traffic). */
 int bpp_engine_stats(bpp_engine *e, uint64_t stats_host[8], int reset, void *stream);
 /* Synchronises and returns BPP_E_CAPACITY if any game overflowed its pools (the search of that game stopped). */
 int bpp_engine_check(bpp_engine *e, void *stream);
@@ -246,8 +290,6 @@ int bpp_engine_graph_sizes(bpp_engine *e, int32_t *nodes_out_dev, int32_t *units
  * Batched policy/value network forward (NNetWrapper.predict, NNet.py:69-85, over BinPackingNNet.forward,
  * BinpackingNNet.py:72-81) in bf16 with fp32 accumulation.  Declared in bpp_net section of the library.
  * ---------------------------------------------------------------------------------------------------------------- */
-typedef struct bpp_net bpp_net;
-
 /* Create for board H x W, N items (in_channels = N + 1), action size A = W*N. */
 int bpp_net_create(int W, int H, int N, int max_batch, int device, bpp_net **out);
 int bpp_net_destroy(bpp_net *n);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "bpp_engine_create": [C.POINTER(Config), C.POINTER(_vp)],
     "bpp_engine_destroy": [_vp],
     "bpp_engine_device_bytes": [_vp],
+    "bpp_engine_edge_cap": [_vp, C.POINTER(_i64)],
     "bpp_engine_reset": [_vp, _vp, _vp, _vp, _vp, _vp],
     "bpp_engine_reset_host": [_vp, _vp, _vp, _vp, _vp, _vp],
     "bpp_engine_set_roots": [_vp, _vp, _vp],
@@ -68,6 +69,13 @@ SIGNATURES = {
     "bpp_engine_roots": [_vp, _vp, _vp],
     "bpp_engine_play_stub": [_vp, _i32, _i32, _u64, _i32, _vp, _vp, C.POINTER(_i32), _vp],
     "bpp_engine_play_stub_host": [_vp, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "bpp_engine_set_auto_play": [_vp, _i32, _u64, _vp, _vp, _vp],
+    "bpp_engine_progress_async": [_vp, _vp, _vp],
+    "bpp_engine_play_net": [_vp, _vp, _i32, _u64, _vp, _vp, _vp, C.POINTER(_i32), _vp],
+    "bpp_engine_play_net_host": [_vp, _vp, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 C.POINTER(_i32), _vp],
+    "bpp_engine_set_profile": [_vp, _i32],
+    "bpp_engine_profile": [_vp, C.POINTER(C.c_double)],
     "bpp_engine_stats": [_vp, C.POINTER(_u64), _i32, _vp],
     "bpp_engine_check": [_vp, _vp],
     "bpp_engine_export_game": [_vp, _i32, _vp, _i32, _vp, _i64, C.POINTER(_i32), C.POINTER(_i64), _vp],

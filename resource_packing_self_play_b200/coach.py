@@ -35,6 +35,18 @@ def _default_log_fn():
     return lambda metrics, step=None: wandb.log(metrics, step=step) if wandb.run is not None else None
 
 
+def trim_rewards(rewards_list, new_scores, cap):
+    """CoachBPP.py:134-139 for a whole batch of episodes: append every score, then `while len > cap: pop(argmin)`.
+    np.argmin returns the FIRST minimum, so the loop removes the (len - cap) smallest entries, earliest first among
+    equals, and the survivors keep their order: one stable sort instead of a quadratic loop."""
+    rl = np.asarray(list(rewards_list) + [float(x) for x in new_scores], dtype=np.float64)
+    extra = len(rl) - int(cap)
+    if extra > 0:
+        drop = np.lexsort((np.arange(len(rl)), rl))[:extra]
+        rl = np.delete(rl, drop)
+    return [float(x) for x in rl]
+
+
 class CoachBPP:
     def __init__(self, game, nnet, items_list, total_area, gen, args, saved_rewards_list=[]):  # CoachBPP.py:28-48
         self.game = game
@@ -81,14 +93,18 @@ class CoachBPP:
                 return [(x[0], x[1], r) for x in trainExamples]
 
     # ------------------------------------------------------------------------------------------------------------------
-    def executeEpisodesBatched(self, items_batch, total_areas, greedy=False, seed=None, expand=True, on_device=False):
-        """G episodes in lockstep on the device with the batched leaf evaluator.
+    def executeEpisodesBatched(self, items_batch, total_areas, greedy=False, seed=None, expand=True, on_device=False,
+                               per_move=False, record=True):
+        """G episodes at once on the device with the batched leaf evaluator.
 
         items_batch: (G, N, 2) int (w, h); total_areas: (G,) int.  All games share this call's `self.rewards_list`
         (the reference appends to it after every episode, so inside one call the ranked-reward threshold is the one at
-        the start of the batch).  Returns (examples, scores, outcomes): examples is the reference's list of
-        (state (N+1,H,W) int64, pi list, r) when expand=True, else a dict of compact arrays (numpy, or device tensors
-        that never visit the host when on_device=True; scores and outcomes are then device tensors too)."""
+        the start of the batch).  Every game runs at its own pace (BatchedMCTS.play_episodes: visit counts -> choose ->
+        play inside the search kernels); per_move=True runs the older move-synchronous loop (search / choose / advance
+        per move for all games) that gives identical results for the same seed.  Returns (examples, scores, outcomes):
+        examples is the reference's list of (state (N+1,H,W) int64, pi list, r) when expand=True, else a dict of compact
+        arrays (numpy, or device tensors that never visit the host when on_device=True; scores and outcomes are then
+        device tensors too)."""
         items_dev = None
         if isinstance(items_batch, torch.Tensor):  # e.g. from ItemsGenerator.items_batch_device
             items_dev = items_batch.to(torch.int32)
@@ -97,51 +113,73 @@ class CoachBPP:
         G = items_batch.shape[0]
         g = self.game
         N, A = g.num_items, g.getActionSize()
-        bm = getattr(self, "_bm", None)
-        if bm is None or bm.G != G:
-            bm = self._bm = BatchedMCTS(g, self.nnet, self.args, G)
-        bm.nnet = self.nnet  # the search engine is independent of the evaluator: swapping nets keeps the pools
-        bm.reset(items_dev if items_dev is not None else items_batch, np.asarray(total_areas, dtype=np.int32),
-                 self.rewards_list)
-        eng = bm.eng
         if seed is None:
-            seed = int.from_bytes(os.urandom(8), "little")
-        roots, counts, acts = [], [], []
-        for move in range(N):
-            roots.append(eng.roots())
-            counts.append(bm.search())
-            act = eng.choose(_lib.CHOOSE_GREEDY if greedy else _lib.CHOOSE_SAMPLE, seed + move)
-            acts.append(act)
-            eng.advance(act)
-        eng.check()
+            seed = int.from_bytes(os.urandom(8), "little") >> 1
+        areas = np.asarray(total_areas, dtype=np.int32)
+        # greedy: False = sample ~ counts (CoachBPP.py:86-87); True = random arg-max (MCTS_bpp.py:43-49); "first" = first
+        # arg-max (deterministic)
+        mode = _lib.CHOOSE_ARGMAX_FIRST if greedy == "first" else (_lib.CHOOSE_GREEDY if greedy else _lib.CHOOSE_SAMPLE)
+        edge_cap = 0
+        while True:
+            bm = getattr(self, "_bm", None)
+            if bm is None or bm.G != G or edge_cap:
+                if bm is not None:  # free the old pools (and the graphs captured on them) BEFORE sizing the new ones
+                    bm.close()
+                    self._bm = bm = None
+                bm = self._bm = BatchedMCTS(g, self.nnet, self.args, G, edge_cap=edge_cap)
+            bm.nnet = self.nnet  # the search engine is independent of the evaluator: swapping nets keeps the pools
+            eng = bm.eng
+            try:
+                if per_move:
+                    bm.reset(items_dev if items_dev is not None else items_batch, areas, self.rewards_list)
+                    roots, counts, acts = [], [], []
+                    for move in range(N):
+                        roots.append(eng.roots())
+                        counts.append(bm.search())
+                        act = eng.choose(mode, seed)
+                        acts.append(act)
+                        eng.advance(act)
+                    roots, counts, acts = torch.stack(roots), torch.stack(counts), torch.stack(acts)
+                    live = torch.arange(N, device=eng.device)[:, None] < eng.status()["moves"][None, :]
+                    roots = roots * live[:, :, None]      # rows of moves a game did not play: like play_episodes
+                else:
+                    ep = bm.play_episodes(items_dev if items_dev is not None else items_batch, areas, self.rewards_list,
+                                          mode=mode, seed=seed, record=record)
+                    roots, counts, acts = ep["roots"], ep["counts"], ep["actions"]
+                eng.check()
+                break
+            except _lib.BppError as err:
+                # a game outgrew its edge pool (sized from measured episodes, not from the worst case): re-create the
+                # engine with a larger pool and replay the batch; results do not depend on the pool size
+                if err.code != -4 or eng.edge_cap >= eng.edge_cap_worst:
+                    raise
+                edge_cap = min(eng.edge_cap_worst, 2 * eng.edge_cap)
+        st = eng.status()
         if on_device and not expand:
-            st = eng.status()
-            return {"roots": torch.stack(roots), "counts": torch.stack(counts), "actions": torch.stack(acts),
-                    "moves": st["moves"], "r": st["r"],
+            return {"roots": roots, "counts": counts, "actions": acts, "moves": st["moves"], "r": st["r"],
                     "items": items_dev if items_dev is not None else torch.from_numpy(items_batch).to(eng.device)}, \
                 st["score"], st["r"]
-        st = {k: v.cpu().numpy() for k, v in eng.status().items()}
-        roots = torch.stack(roots).cpu().numpy().view(np.uint32)      # (N, G, 32)
-        counts = torch.stack(counts).cpu().numpy()                      # (N, G, A)
-        acts = torch.stack(acts).cpu().numpy()                          # (N, G)
+        st = {k: v.cpu().numpy() for k, v in st.items()}
+        roots = roots.cpu().numpy().view(np.uint32)      # (N, G, 32)
+        counts = counts.cpu().numpy()                      # (N, G, A)
+        acts = acts.cpu().numpy()                          # (N, G)
         moves, r, score = st["moves"], st["r"], st["score"]
         assert (st["done"] == 1).all()
         if not expand:
             return {"roots": roots, "counts": counts, "actions": acts, "moves": moves, "r": r,
                     "items": items_batch}, score, r
-        examples = []
-        for gi in range(G):
-            m = int(moves[gi])
-            states = unpack_states(roots[:m, gi], np.repeat(items_batch[gi][None], m, axis=0), g.bin_width,
-                                   g.bin_height, N)
-            for k in range(m):
-                c = counts[k, gi].astype(np.float64)
-                if greedy:
-                    pi = [0] * A
-                    pi[int(acts[k, gi])] = 1  # one-hot of the arg-max the device drew (MCTS_bpp.py:43-49)
-                else:
-                    pi = list(c / c.sum())
-                examples.append((states[k], pi, int(r[gi])))
+        # the reference's example list, game by game and move by move (CoachBPP.py:80,99); all array work is vectorised
+        gi, mi = np.nonzero(np.arange(N)[None, :] < moves[:, None])         # game-major, then move
+        states = unpack_states(roots[mi, gi], items_batch[gi], g.bin_width, g.bin_height, N)
+        if greedy:   # one-hot of the arg-max the device drew (MCTS_bpp.py:43-49)
+            pis = np.zeros((len(gi), A), dtype=np.int64)
+            pis[np.arange(len(gi)), acts[mi, gi]] = 1
+        else:
+            c = counts[mi, gi].astype(np.float64)
+            pis = c / c.sum(axis=1, keepdims=True)
+        pis = pis.tolist()
+        rr = r[gi].tolist()
+        examples = [(states[k], pis[k], rr[k]) for k in range(len(gi))]
         return examples, score, r
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -236,12 +274,7 @@ class CoachBPP:
             scores = D.all_gather_variable(score).cpu().numpy()
             # rewards buffer (CoachBPP.py:134-139): append every score, then drop minima until numScoresForRank remain
             # (repeated `pop(argmin)` == remove the smallest, earliest-first; survivors keep their order)
-            rl = np.asarray(list(self.rewards_list) + [float(x) for x in scores], dtype=np.float64)
-            extra = len(rl) - int(self.args.numScoresForRank)
-            if extra > 0:
-                drop = np.lexsort((np.arange(len(rl)), rl))[:extra]
-                rl = np.delete(rl, drop)
-            self.rewards_list = [float(x) for x in rl]
+            self.rewards_list = trim_rewards(self.rewards_list, scores, self.args.numScoresForRank)
             self.log_fn({"iter mean reward": float(np.mean(scores)),
                          "optimality percentage": float(np.mean(scores == 1.0)),
                          "min reward": float(np.min(scores)), "max reward": float(np.max(scores))}, step=i)
@@ -334,9 +367,10 @@ class CoachBPP:
             n_scores.append(self._play_greedy(nmcts, np.copy(items_list)))
         return 1 if np.mean(n_scores) >= np.mean(p_scores) else 0
 
-    def arena_sweep(self, pnet, nnet, seeds, bin_heights=None, seed=0):
-        """Batched arena (BASELINE.json configs[4]): every seed is played greedily with both nets in lockstep.
-        Returns (p_scores, n_scores, accept) with accept as in arena_playing."""
+    def arena_sweep(self, pnet, nnet, seeds, bin_heights=None, seed=0, choose="greedy"):
+        """Batched arena (BASELINE.json configs[4]): every seed is played greedily with both nets at once.
+        Returns (p_scores, n_scores, accept) with accept as in arena_playing.  choose="greedy" draws a uniformly random
+        arg-max like MCTS_bpp.py:43-49; choose="first" takes the first arg-max (deterministic; parity tests)."""
         seeds = np.asarray(seeds)
         items = self.gen.items_batch_device(seeds, bin_heights, device=self.nnet.device.index)
         hts = np.full(len(seeds), self.gen.bin_height) if bin_heights is None else np.asarray(bin_heights)
@@ -346,8 +380,9 @@ class CoachBPP:
         try:
             for net in (pnet, nnet):
                 self.nnet = net
-                _, score, _ = self.executeEpisodesBatched(items, areas, greedy=True, seed=seed, expand=False,
-                                                          on_device=True)  # only the G scores leave the device
+                _, score, _ = self.executeEpisodesBatched(items, areas, greedy=True if choose == "greedy" else "first",
+                                                          seed=seed, expand=False, on_device=True,
+                                                          record=False)  # only the G scores leave the device
                 out.append(score.cpu().numpy())
         finally:
             self.nnet = keep

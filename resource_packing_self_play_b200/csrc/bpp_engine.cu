@@ -93,6 +93,13 @@ struct Params {
     const double* sqrt_tab;     // [3][sqrt_n]: sqrt(n), sqrt(n + 1e-8), 1/n (correctly rounded, host-computed)
     int sqrt_n;
     int select_cap;             // lockstep: simulations per game and select launch (0 = until a leaf is parked)
+    // asynchronous episodes (bpp_engine_set_auto_play): a game that completes its num_sims simulations inside
+    // k_expand_search writes its visit-count row, chooses, plays the move and goes on with the next move in the same launch
+    int auto_mode;              // -1 = off, else BPP_CHOOSE_*
+    unsigned long long auto_seed;
+    int32_t* ep_counts;         // [N][G][A] or nullptr
+    int32_t* ep_actions;        // [N][G] or nullptr
+    uint32_t* ep_roots;         // [N][G][32] root record each move was searched from, or nullptr
 };
 
 struct __align__(16) WarpSmem {
@@ -104,7 +111,7 @@ struct __align__(16) WarpSmem {
 };
 
 struct Stats {
-    unsigned sims, edges, expansions, terminals, created, probes;
+    unsigned sims, edges, expansions, terminals, created, probes, units;
 };
 
 struct GameCtx {
@@ -149,6 +156,7 @@ __device__ __forceinline__ void flush_stats(const Params& P, const Stats& st, in
         if (st.terminals) atomicAdd(&P.stats[3], (unsigned long long)st.terminals);
         if (st.created) atomicAdd(&P.stats[4], (unsigned long long)st.created);
         if (st.probes) atomicAdd(&P.stats[5], (unsigned long long)st.probes);
+        if (st.units) atomicAdd(&P.stats[7], (unsigned long long)st.units);
     }
 }
 
@@ -313,6 +321,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
         }
         depth++;
         st.edges++;
+        st.units += (unsigned)(3 * nvp + (nvp >> 2));  // 8-byte units of the edge block this selection read
         if (child < 0) {  // first traversal of this edge: getNextState + key lookup (:125-128)
             const int item = div_w(ge, act);
             const int x = act - item * ge.W;
@@ -347,7 +356,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7) k_search(Params P) {
     WarpSmem& sm = smem[wid];
     GameCtx gm;
     load_ctx(P, g, lane, gm, sm);
-    Stats st = {0, 0, 0, 0, 0, 0};
+    Stats st = {0, 0, 0, 0, 0, 0, 0};
     int done = P.sims_done[g];
     // lockstep mode: a game whose simulations keep ending on terminal states needs no evaluator; capping its work per
     // launch keeps it from holding back the leaf batch of all other games (it simply continues in the next step)
@@ -375,7 +384,7 @@ k_expand_backup(Params P, const void* policy, int policy_f64, const void* value,
     WarpSmem& sm = smem[wid];
     GameCtx gm;
     load_ctx(P, g, lane, gm, sm);
-    Stats st = {0, 0, 0, 0, 0, 0};
+    Stats st = {0, 0, 0, 0, 0, 0, 0};
     const int cur = P.pend_leaf[g];
     const int depth = P.pend_depth[g];
     if (lane < MAX_AW) sm.vw[lane] = P.pend_valid[(size_t)g * MAX_AW + lane];
@@ -401,70 +410,6 @@ k_expand_backup(Params P, const void* policy, int policy_f64, const void* value,
         if (lane == 0) P.sims_done[g] += 1;
     }
     if (lane == 0) P.pend_depth[g] = -1;
-    store_ctx(P, gm, lane);
-    flush_stats(P, st, lane);
-}
-
-// Lockstep step in ONE launch per game warp: expansion + backup of the game's parked leaf (evaluator outputs of the
-// previous step, row pend_slot[g]) followed by the next descents until the game parks its next leaf (k_expand_backup +
-// k_search<0>): the game context is loaded once, and the second launch with its tail disappears from every step.  New
-// leaves go to slots counted from zero (leaf_count is cleared before the launch); nothing in this kernel reads the
-// old leaf records, and the evaluator outputs are only read.
-template <int HC>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7)
-k_expand_search(Params P, const void* policy, int policy_f64, const void* value, int value_f64) {
-    __shared__ WarpSmem smem[WARPS_PER_CTA];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = blockIdx.x * WARPS_PER_CTA + wid;
-    // the evaluator's trunk kernel, launched programmatically behind this one, may set itself up (barriers, tensor memory,
-    // first weights) on the SMs this kernel's short warps have left while its longest descents still run
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (g >= P.G) return;
-    if (P.status[g] != 0) return;
-    WarpSmem& sm = smem[wid];
-    GameCtx gm;
-    load_ctx(P, g, lane, gm, sm);
-    Stats st = {0, 0, 0, 0, 0, 0};
-    int done = P.sims_done[g];
-    const int depth = P.pend_depth[g];
-    bool ok = true;
-    if (depth >= 0) {
-        const int b = P.pend_slot[g];
-        const int cur = P.pend_leaf[g];
-        if (lane < MAX_AW) sm.vw[lane] = P.pend_valid[(size_t)g * MAX_AW + lane];
-        __syncwarp();
-        const int4 pp = P.pend_path[(size_t)g * 32 + lane];
-        PathEntry pe = {pp.x, pp.y, pp.z, pp.w};
-        const size_t row = (size_t)b * P.geom.A;
-        const double* pol64 = reinterpret_cast<const double*>(policy) + row;
-        const float* pol32 = reinterpret_cast<const float*>(policy) + row;
-        ok = expand_node(P, gm, sm, cur, lane,
-                         [=](int a) -> double { return policy_f64 ? pol64[a] : (double)pol32[a]; });
-        if (ok) {
-            const double v = value_f64 ? reinterpret_cast<const double*>(value)[b]
-                                       : (double)reinterpret_cast<const float*>(value)[b];
-            backup_path(gm.nodes, gm.edges, pe, depth, v, lane, P.sqrt_tab, P.sqrt_n);
-            if (lane == 0) P.last_v[g] = v;
-            st.expansions++;
-            st.sims++;
-            done++;
-        }
-        if (lane == 0) P.pend_depth[g] = -1;
-        __syncwarp();
-    }
-    if (ok) {
-        const int stop = P.select_cap > 0 ? min(P.num_sims, done + P.select_cap) : P.num_sims;
-        while (done < stop) {
-            const int rc = simulate<0, HC>(P, gm, sm, lane, st);
-            if (rc != 0) break;  // parked leaf (counted when it is expanded) or overflow
-            done++;
-            st.sims++;
-        }
-    }
-    if (lane == 0) {
-        P.sims_done[g] = done;
-        if (done < P.num_sims && P.pend_depth[g] < 0) atomicAdd(P.leaf_count + 1, 1);
-    }
     store_ctx(P, gm, lane);
     flush_stats(P, st, lane);
 }
@@ -662,9 +607,101 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_advance(Params P, const 
     WarpSmem& sm = smem[wid];
     GameCtx gm;
     load_ctx(P, g, lane, gm, sm);
-    Stats st = {0, 0, 0, 0, 0, 0};
+    Stats st = {0, 0, 0, 0, 0, 0, 0};
     uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
     if (advance_game(P, gm, sm, lane, actions[g], rec, st) == -1) return;
+    store_ctx(P, gm, lane);
+    flush_stats(P, st, lane);
+}
+
+// Lockstep step in ONE launch per game warp: expansion + backup of the game's parked leaf (evaluator outputs of the
+// previous step, row pend_slot[g]) followed by the next descents until the game parks its next leaf (k_expand_backup +
+// k_search<0>): the game context is loaded once, and the second launch with its tail disappears from every step.  New
+// leaves go to slots counted from zero (leaf_count is cleared before the launch); nothing in this kernel reads the
+// old leaf records, and the evaluator outputs are only read.
+template <int HC>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 7)
+k_expand_search(Params P, const void* policy, int policy_f64, const void* value, int value_f64) {
+    __shared__ WarpSmem smem[WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    // the evaluator's trunk kernel, launched programmatically behind this one, may set itself up (barriers, tensor memory,
+    // first weights) on the SMs this kernel's short warps have left while its longest descents still run
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (g >= P.G) return;
+    if (P.status[g] != 0) return;
+    WarpSmem& sm = smem[wid];
+    GameCtx gm;
+    load_ctx(P, g, lane, gm, sm);
+    Stats st = {0, 0, 0, 0, 0, 0, 0};
+    int done = P.sims_done[g];
+    const int depth = P.pend_depth[g];
+    bool ok = true;
+    if (depth >= 0) {
+        const int b = P.pend_slot[g];
+        const int cur = P.pend_leaf[g];
+        if (lane < MAX_AW) sm.vw[lane] = P.pend_valid[(size_t)g * MAX_AW + lane];
+        __syncwarp();
+        const int4 pp = P.pend_path[(size_t)g * 32 + lane];
+        PathEntry pe = {pp.x, pp.y, pp.z, pp.w};
+        const size_t row = (size_t)b * P.geom.A;
+        const double* pol64 = reinterpret_cast<const double*>(policy) + row;
+        const float* pol32 = reinterpret_cast<const float*>(policy) + row;
+        ok = expand_node(P, gm, sm, cur, lane,
+                         [=](int a) -> double { return policy_f64 ? pol64[a] : (double)pol32[a]; });
+        if (ok) {
+            const double v = value_f64 ? reinterpret_cast<const double*>(value)[b]
+                                       : (double)reinterpret_cast<const float*>(value)[b];
+            backup_path(gm.nodes, gm.edges, pe, depth, v, lane, P.sqrt_tab, P.sqrt_n);
+            if (lane == 0) P.last_v[g] = v;
+            st.expansions++;
+            st.sims++;
+            done++;
+        }
+        if (lane == 0) P.pend_depth[g] = -1;
+        __syncwarp();
+    }
+    bool running = ok;
+    if (ok) {
+        int budget = P.select_cap > 0 ? P.select_cap : 0x7fffffff;
+        for (;;) {
+            bool parked = false;
+            while (done < P.num_sims && budget > 0) {
+                const int rc = simulate<0, HC>(P, gm, sm, lane, st);
+                if (rc != 0) {  // parked leaf (counted when it is expanded) or overflow
+                    parked = true;
+                    running = rc > 0;
+                    break;
+                }
+                done++;
+                st.sims++;
+                budget--;
+            }
+            if (parked || done < P.num_sims || P.auto_mode < 0) break;
+            // asynchronous episodes: this game's move is searched (MCTS_bpp.py:37-41) -> counts out, choose
+            // (CoachBPP.py:86-87 / MCTS_bpp.py:43-49), play (CoachBPP.py:88-98) and straight on to the next move; no
+            // game waits for the slowest game of a move and the host never synchronises per move
+            const int m = P.moves_done[g];
+            uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
+            const size_t mg = (size_t)m * P.G + g;
+            if (P.ep_roots) P.ep_roots[mg * REC_WORDS + lane] = rec;
+            if (P.ep_counts) root_counts_warp(P, g, gm.root_node, lane, P.ep_counts + mg * P.geom.A);
+            int a = lane == 0 ? choose_action(P, g, gm.root_node, m, P.auto_mode, P.auto_seed) : 0;
+            a = __shfl_sync(FULL, a, 0);
+            if (P.ep_actions && lane == 0) P.ep_actions[mg] = a;
+            const int status = advance_game(P, gm, sm, lane, a, rec, st);
+            done = 0;
+            if (status != 0) {
+                running = false;
+                break;
+            }
+        }
+    }
+    if (lane == 0) {
+        P.sims_done[g] = done;
+        if (running && done < P.num_sims && P.pend_depth[g] < 0) atomicAdd(P.leaf_count + 1, 1);
+        if (running) atomicAdd(P.leaf_count + 2, 1);  // games still playing their episode
+    }
     store_ctx(P, gm, lane);
     flush_stats(P, st, lane);
 }
@@ -689,7 +726,7 @@ k_episode(Params P, int mode, unsigned long long seed, int max_moves, int32_t* c
     WarpSmem& sm = smem[wid];
     GameCtx gm;
     load_ctx(P, g, lane, gm, sm);
-    Stats st = {0, 0, 0, 0, 0, 0};
+    Stats st = {0, 0, 0, 0, 0, 0, 0};
     uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
     int move_no = P.moves_done[g];
     int done = P.sims_done[g];
@@ -980,6 +1017,17 @@ struct bpp_engine {
     int32_t* d_counts_all = nullptr;   // [N][G][A], lazily allocated by play_stub_host
     int32_t* d_actions_all = nullptr;  // [N][G]
     int* h_status = nullptr;
+    // bpp_engine_play_net: evaluator outputs of one lockstep step, progress counters read back asynchronously
+    float* d_pol = nullptr;            // [G][A]
+    float* d_val = nullptr;            // [G]
+    uint32_t* d_roots_all = nullptr;   // [N][G][32], lazily allocated by play_net_host
+    int32_t* h_prog = nullptr;         // pinned [2][4]
+    cudaEvent_t ev_prog[2] = {nullptr, nullptr};
+    const int32_t* items_ref = nullptr;  // int32 [G][N][2] item list of the current episodes (evaluator input)
+    int num_sms = 148;
+    bool prof_on = false;              // bpp_engine_set_profile: CUDA events around every call of play_net's steps
+    std::vector<cudaEvent_t> prof_ev;
+    double prof_ms[4] = {0, 0, 0, 0};  // evaluator ms, expand+select ms, steps timed, -
 };
 
 template <typename T>
@@ -1001,9 +1049,24 @@ extern "C" int bpp_engine_destroy(bpp_engine* e) {
     if (!e) return BPP_OK;
     for (void* p : e->allocs) cudaFree(p);
     if (e->h_status) cudaFreeHost(e->h_status);
+    if (e->h_prog) cudaFreeHost(e->h_prog);
+    for (int i = 0; i < 2; ++i)
+        if (e->ev_prog[i]) cudaEventDestroy(e->ev_prog[i]);
+    for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
     delete e;
     return BPP_OK;
 }
+
+// inside bpp_engine_create, after the handle exists: a failing CUDA call frees everything the handle owns
+#define CREATE_TRY(expr)                                                                                 \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            bpp_engine_destroy(e);                                                                       \
+            return set_err(BPP_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                                    \
+        }                                                                                                \
+    } while (0)
 
 extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     if (!cfg || !out) return set_err(BPP_E_INVALID, "null argument");
@@ -1015,6 +1078,8 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     CUDA_TRY(cudaSetDevice(cfg->device));
     bpp_engine* e = new bpp_engine();
     e->cfg = *cfg;
+    if (cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || e->num_sms < 1)
+        e->num_sms = 148;
     Params& P = e->P;
     memset(&P, 0, sizeof(P));
     P.geom = ge;
@@ -1024,7 +1089,7 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     // every simulation creates at most one node, every real move at most one more (+ the first root)
     P.node_cap = cfg->node_cap > 0 ? cfg->node_cap : cfg->num_sims * cfg->N + cfg->N + 2;
     if (P.node_cap >= (1 << 20) - 1) {
-        delete e;
+        bpp_engine_destroy(e);
         return set_err(BPP_E_INVALID, "node_cap %d too large (max 2^20-2)", P.node_cap);
     }
     unsigned tc = 64;
@@ -1059,7 +1124,7 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     ALLOC(P.pend_slot, G);
     ALLOC(P.pend_path, G * 32);
     ALLOC(P.pend_valid, G * MAX_AW);
-    ALLOC(P.leaf_count, 2);  // [0] parked leaves, [1] games that stopped at the per-launch cap
+    ALLOC(P.leaf_count, 4);  // [0] parked leaves, [1] games that stopped at the per-launch cap, [2] games still playing
     ALLOC(P.leaf_game, G);
     ALLOC(P.leaf_rec, G * REC_WORDS);
     ALLOC(P.stats, 8);
@@ -1071,13 +1136,18 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     ALLOC(e->d_counts, G * (size_t)ge.A);
     ALLOC(P.nodes, G * (size_t)P.node_cap * REC_WORDS);
     ALLOC(P.table, G * (size_t)tc);
-    // edge pool: worst case = every node expanded with all A actions valid; shrink to fit free memory
+    // Edge pool.  Worst case = every node expanded with all A actions valid (7.9 MB per game at the default config);
+    // measured need over whole 10-move episodes: mean 47 K units, maximum 87 K units per game = 9 % of that worst case
+    // (15x15, 200 simulations).  Default = a quarter of the worst case (3x the measured maximum), clipped to half of the
+    // free memory so that a second engine, the evaluator and the learner still fit in the same process.  A game that
+    // outgrows its pool sets the sticky BPP_E_CAPACITY error (bpp_engine_check): the caller re-creates the engine
+    // with a larger cfg.edge_cap (cfg.edge_cap = worst case never overflows) and replays the batch.
     const long long worst = (long long)P.node_cap * edge_units(ge.A);
-    long long cap = cfg->edge_cap > 0 ? cfg->edge_cap : worst;
+    long long cap = cfg->edge_cap > 0 ? cfg->edge_cap : worst / 4;
     if (cfg->edge_cap <= 0) {
         size_t free_b = 0, total_b = 0;
-        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const long long fit = (long long)((double)free_b * 0.70 / (double)G / 8.0);
+        CREATE_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const long long fit = (long long)((double)free_b * 0.50 / (double)G / 8.0);
         if (cap > fit) cap = fit;
         const long long floor_units = (long long)edge_units(ge.A) * 4;
         if (cap < floor_units) cap = floor_units;
@@ -1101,20 +1171,28 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
         }
         double* d_tab = nullptr;
         ALLOC2(d_tab, 3 * (size_t)tn);
-        CUDA_TRY(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
         P.sqrt_tab = d_tab;
         P.sqrt_n = tn;
     }
-    CUDA_TRY(cudaMemset(P.stats, 0, 8 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(P.status, 0xff, G * sizeof(int)));  // not reset yet
-    CUDA_TRY(cudaMemset(P.pend_depth, 0xff, G * sizeof(int)));
-    CUDA_TRY(cudaMemset(P.leaf_count, 0, 2 * sizeof(int)));
-    CUDA_TRY(cudaMallocHost(&e->h_status, G * sizeof(int)));
+    CREATE_TRY(cudaMemset(P.stats, 0, 8 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(P.status, 0xff, G * sizeof(int)));  // not reset yet
+    CREATE_TRY(cudaMemset(P.pend_depth, 0xff, G * sizeof(int)));
+    CREATE_TRY(cudaMemset(P.leaf_count, 0, 4 * sizeof(int)));
+    CREATE_TRY(cudaMallocHost(&e->h_status, G * sizeof(int)));
+    CREATE_TRY(cudaMallocHost(&e->h_prog, 8 * sizeof(int32_t)));
+    for (int i = 0; i < 2; ++i) CREATE_TRY(cudaEventCreateWithFlags(&e->ev_prog[i], cudaEventDisableTiming));
+    P.auto_mode = -1;
     *out = e;
     return BPP_OK;
 }
 
 extern "C" int64_t bpp_engine_device_bytes(const bpp_engine* e) { return e ? e->bytes : 0; }
+extern "C" int bpp_engine_edge_cap(const bpp_engine* e, int64_t* units_out) {
+    if (!e || !units_out) return set_err(BPP_E_INVALID, "null argument");
+    *units_out = e->P.edge_cap;
+    return BPP_OK;
+}
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int grid_warps(int n) { return (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
@@ -1135,6 +1213,11 @@ extern "C" int bpp_engine_reset(bpp_engine* e, const int32_t* items_wh_dev, cons
     k_reset<<<(P.G + 127) / 128, 128, 0, S(stream)>>>(P, items_wh_dev, total_area_dev, bl_dev, tie_dev);
     LAUNCH_CHECK(e);
     e->leaf_parked = false;
+    // the evaluator reads the item dimensions as int32 [G][N][2]: keep an engine-owned copy (bpp_engine_play_net)
+    if (items_wh_dev != e->d_items)
+        CUDA_TRY(cudaMemcpyAsync(e->d_items, items_wh_dev, (size_t)P.G * P.geom.N * 2 * sizeof(int32_t),
+                                 cudaMemcpyDeviceToDevice, S(stream)));
+    e->items_ref = e->d_items;
     return BPP_OK;
 }
 
@@ -1221,7 +1304,7 @@ static void launch_search(bpp_engine* e, void* stream) {
 extern "C" int bpp_engine_select(bpp_engine* e, void* stream) {
     if (!e) return set_err(BPP_E_INVALID, "null argument");
     if (e->leaf_parked) return set_err(BPP_E_STATE, "bpp_engine_select called with leaves still parked");
-    CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, 2 * sizeof(int), S(stream)));
+    CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, 4 * sizeof(int), S(stream)));
     launch_search<0>(e, stream);
     LAUNCH_CHECK(e);
     e->leaf_parked = true;
@@ -1256,7 +1339,7 @@ extern "C" int bpp_engine_leaf_buffers(bpp_engine* e, const int32_t** count_dev,
 
 extern "C" int bpp_engine_leaf_planes(bpp_engine* e, float* planes_out_dev, void* stream) {
     if (!e || !planes_out_dev) return set_err(BPP_E_INVALID, "null argument");
-    k_leaf_planes<<<296, 256, 0, S(stream)>>>(e->P, planes_out_dev);
+    k_leaf_planes<<<2 * e->num_sms, 256, 0, S(stream)>>>(e->P, planes_out_dev);
     LAUNCH_CHECK(e);
     return BPP_OK;
 }
@@ -1275,7 +1358,7 @@ extern "C" int bpp_engine_expand_backup(bpp_engine* e, const void* policy_dev, i
 extern "C" int bpp_engine_expand_select(bpp_engine* e, const void* policy_dev, int policy_dtype, const void* value_dev,
                                         int value_dtype, void* stream) {
     if (!e || !policy_dev || !value_dev) return set_err(BPP_E_INVALID, "null argument");
-    CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, 2 * sizeof(int), S(stream)));
+    CUDA_TRY(cudaMemsetAsync(e->P.leaf_count, 0, 4 * sizeof(int), S(stream)));
     const int grid = grid_warps(e->P.G), block = WARPS_PER_CTA * 32;
     const int pf = policy_dtype == BPP_DTYPE_F64, vf = value_dtype == BPP_DTYPE_F64;
     switch (e->P.geom.H) {
@@ -1452,6 +1535,169 @@ extern "C" int bpp_engine_play_stub_host(bpp_engine* e, int stub_kind, int choos
             CUDA_TRY(cudaMemcpyAsync(actions_out_host, e->d_actions_all, N * G * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                      S(stream)));
     }
+    if (r_out_host)
+        CUDA_TRY(cudaMemcpyAsync(r_out_host, e->P.ep_r, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    if (score_out_host)
+        CUDA_TRY(cudaMemcpyAsync(score_out_host, e->P.ep_score, G * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
+    if (moves_out_host)
+        CUDA_TRY(cudaMemcpyAsync(moves_out_host, e->P.moves_done, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    return bpp_engine_check(e, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Asynchronous episodes with an external (batched, device) evaluator
+extern "C" int bpp_engine_set_auto_play(bpp_engine* e, int choose_mode, uint64_t seed, int32_t* counts_out_dev,
+                                        int32_t* actions_out_dev, uint32_t* roots_out_dev) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    if (choose_mode < -1 || choose_mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", choose_mode);
+    e->P.auto_mode = choose_mode;
+    e->P.auto_seed = (unsigned long long)seed;
+    e->P.ep_counts = choose_mode < 0 ? nullptr : counts_out_dev;
+    e->P.ep_actions = choose_mode < 0 ? nullptr : actions_out_dev;
+    e->P.ep_roots = choose_mode < 0 ? nullptr : roots_out_dev;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_progress_async(bpp_engine* e, int32_t* counts_host4, void* stream) {
+    if (!e || !counts_host4) return set_err(BPP_E_INVALID, "null argument");
+    CUDA_TRY(cudaMemcpyAsync(counts_host4, e->P.leaf_count, 4 * sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    return BPP_OK;
+}
+
+extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, const uint32_t* recs_dev,
+                               const int32_t* game_dev, const int32_t* items_wh_dev, float* policy_out_dev,
+                               float* value_out_dev, void* stream);
+
+extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t seed, int32_t* counts_out_dev,
+                                   int32_t* actions_out_dev, uint32_t* roots_out_dev, int32_t* steps_run_host,
+                                   void* stream) {
+    if (!e || !net) return set_err(BPP_E_INVALID, "null argument");
+    if (e->leaf_parked) return set_err(BPP_E_STATE, "leaves are parked; call bpp_engine_expand_backup first");
+    if (choose_mode < 0 || choose_mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", choose_mode);
+    if (!e->items_ref) return set_err(BPP_E_STATE, "bpp_engine_play_net before bpp_engine_reset");
+    Params& P = e->P;
+    const size_t G = (size_t)P.G, A = (size_t)P.geom.A, N = (size_t)P.geom.N;
+    int rc;
+    if (!e->d_pol && ((rc = dev_alloc(e, &e->d_pol, G * A)) || (rc = dev_alloc(e, &e->d_val, G)))) return rc;
+    // rows of moves a game does not play: counts 0, action -1, root record 0
+    if (counts_out_dev) CUDA_TRY(cudaMemsetAsync(counts_out_dev, 0, N * G * A * sizeof(int32_t), S(stream)));
+    if (actions_out_dev) CUDA_TRY(cudaMemsetAsync(actions_out_dev, 0xff, N * G * sizeof(int32_t), S(stream)));
+    if (roots_out_dev) CUDA_TRY(cudaMemsetAsync(roots_out_dev, 0, N * G * REC_WORDS * sizeof(uint32_t), S(stream)));
+    const int keep_cap = P.select_cap;
+    const char* cap_env = getenv("BPP_SELECT_CAP");
+    P.select_cap = cap_env ? atoi(cap_env) : 2;
+    if (P.select_cap < 0) P.select_cap = 0;
+    if ((rc = bpp_engine_set_auto_play(e, choose_mode, seed, counts_out_dev, actions_out_dev, roots_out_dev))) return rc;
+    auto restore = [&]() {
+        P.select_cap = keep_cap;
+        bpp_engine_set_auto_play(e, -1, 0, nullptr, nullptr, nullptr);
+    };
+    if ((rc = bpp_engine_begin_move(e, stream)) || (rc = bpp_engine_select(e, stream))) {
+        restore();
+        return rc;
+    }
+    // Lockstep steps are queued in chunks; the progress counters of chunk k are read back asynchronously and looked at
+    // after chunk k+1 has been queued, so the GPU never waits for the host.  Steps queued after the last game has ended
+    // are no-ops (no parked leaf, every game's status != 0).
+    const int chunk = 8;
+    int steps = 0;
+    size_t nev = 0;
+    auto mark = [&]() {  // profiling pass only: one event per call boundary
+        if (!e->prof_on) return;
+        if (nev == e->prof_ev.size()) {
+            cudaEvent_t ev;
+            if (cudaEventCreate(&ev) != cudaSuccess) return;
+            e->prof_ev.push_back(ev);
+        }
+        cudaEventRecord(e->prof_ev[nev++], S(stream));
+    };
+    for (int k = 0;; ++k) {
+        for (int i = 0; i < chunk; ++i) {
+            mark();
+            rc = bpp_net_forward(net, P.G, P.leaf_count, P.leaf_rec, P.leaf_game, e->items_ref, e->d_pol, e->d_val, stream);
+            mark();
+            if (!rc) rc = bpp_engine_expand_select(e, e->d_pol, BPP_DTYPE_F32, e->d_val, BPP_DTYPE_F32, stream);
+            mark();
+            if (rc) {
+                restore();
+                return rc;
+            }
+        }
+        steps += chunk;
+        int32_t* hp = e->h_prog + 4 * (k & 1);
+        cudaError_t ce = cudaMemcpyAsync(hp, P.leaf_count, 4 * sizeof(int), cudaMemcpyDeviceToHost, S(stream));
+        if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_prog[k & 1], S(stream));
+        if (ce == cudaSuccess && k > 0) {
+            ce = cudaEventSynchronize(e->ev_prog[(k - 1) & 1]);
+            const int32_t* pp = e->h_prog + 4 * ((k - 1) & 1);
+            if (ce == cudaSuccess && pp[0] == 0 && pp[2] == 0) break;  // nothing parked, nobody playing
+        }
+        if (ce != cudaSuccess) {
+            restore();
+            return set_err(BPP_E_CUDA, "bpp_engine_play_net: %s", cudaGetErrorString(ce));
+        }
+        if (steps > 400 * P.num_sims * (int)N + 4096) {  // cannot happen: every step with a running game makes progress
+            restore();
+            return set_err(BPP_E_STATE, "bpp_engine_play_net made no progress");
+        }
+    }
+    restore();
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    e->leaf_parked = false;
+    if (steps_run_host) *steps_run_host = steps;
+    if (e->prof_on) {
+        for (size_t i = 0; i + 2 < nev; i += 3) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, e->prof_ev[i], e->prof_ev[i + 1]);
+            cudaEventElapsedTime(&b, e->prof_ev[i + 1], e->prof_ev[i + 2]);
+            e->prof_ms[0] += a;
+            e->prof_ms[1] += b;
+            e->prof_ms[2] += 1.0;
+        }
+    }
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_set_profile(bpp_engine* e, int on) {
+    if (!e) return set_err(BPP_E_INVALID, "null argument");
+    e->prof_on = on != 0;
+    for (double& v : e->prof_ms) v = 0.0;
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_profile(bpp_engine* e, double ms_out4[4]) {
+    if (!e || !ms_out4) return set_err(BPP_E_INVALID, "null argument");
+    for (int i = 0; i < 4; ++i) ms_out4[i] = e->prof_ms[i];
+    return BPP_OK;
+}
+
+extern "C" int bpp_engine_play_net_host(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t seed,
+                                        const int32_t* items_wh_host, const int32_t* total_area_host,
+                                        const double* bl_host, const int8_t* tie_host, uint32_t* roots_out_host,
+                                        int32_t* counts_out_host, int32_t* actions_out_host, int32_t* r_out_host,
+                                        double* score_out_host, int32_t* moves_out_host, int32_t* steps_run_host,
+                                        void* stream) {
+    if (!e || !net) return set_err(BPP_E_INVALID, "null argument");
+    const size_t G = (size_t)e->P.G, A = (size_t)e->P.geom.A, N = (size_t)e->P.geom.N;
+    int rc;
+    if (counts_out_host && !e->d_counts_all && (rc = dev_alloc(e, &e->d_counts_all, N * G * A))) return rc;
+    if (actions_out_host && !e->d_actions_all && (rc = dev_alloc(e, &e->d_actions_all, N * G))) return rc;
+    if (roots_out_host && !e->d_roots_all && (rc = dev_alloc(e, &e->d_roots_all, N * G * REC_WORDS))) return rc;
+    if ((rc = bpp_engine_reset_host(e, items_wh_host, total_area_host, bl_host, tie_host, stream))) return rc;
+    if ((rc = bpp_engine_play_net(e, net, choose_mode, seed, counts_out_host ? e->d_counts_all : nullptr,
+                                  actions_out_host ? e->d_actions_all : nullptr,
+                                  roots_out_host ? e->d_roots_all : nullptr, steps_run_host, stream)))
+        return rc;
+    if (roots_out_host)
+        CUDA_TRY(cudaMemcpyAsync(roots_out_host, e->d_roots_all, N * G * REC_WORDS * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, S(stream)));
+    if (counts_out_host)
+        CUDA_TRY(cudaMemcpyAsync(counts_out_host, e->d_counts_all, N * G * A * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 S(stream)));
+    if (actions_out_host)
+        CUDA_TRY(cudaMemcpyAsync(actions_out_host, e->d_actions_all, N * G * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 S(stream)));
     if (r_out_host)
         CUDA_TRY(cudaMemcpyAsync(r_out_host, e->P.ep_r, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
     if (score_out_host)

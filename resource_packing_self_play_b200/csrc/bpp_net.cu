@@ -833,6 +833,7 @@ struct bpp_net {
     int ctas_per_sm = 1;
     bool committed = false;
     int smem_bytes = 0;
+    int num_sms = 148;
 };
 
 static const char* kSeqConvNames[5] = {"conv", "res_block0.conv0", "res_block0.conv1", "res_block1.conv0",
@@ -897,6 +898,8 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
     n->expect["value_fc.weight"] = HIDDEN;
     n->expect["value_fc.bias"] = 1;
     if (cudaSetDevice(device) != cudaSuccess) { delete n; return nerr(BPP_E_CUDA, "cudaSetDevice failed"); }
+    if (cudaDeviceGetAttribute(&n->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n->num_sms < 1)
+        n->num_sms = 148;
     {   // UMMA-layout conv weights (size known before the Tc setup below: recompute here)
         long long u = 0;
         for (int l = 0; l < NCONV; ++l) u += 9LL * ((P.conv[l].ci + 15) / 16) * 2 * P.conv[l].co * 8;
@@ -1181,10 +1184,16 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
                             }
             ++li;
         }
+    // every upload below is queued on the caller's stream (a forward or a captured graph still in flight on that stream is
+    // ordered before it) and the staging vectors live until the cudaStreamSynchronize at the end
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    std::vector<uint16_t> w1u, w2u;
+    std::vector<float> wv32;
     if (n->heads_ok) {  // FC weights in the UMMA K-major B layout [k-block][k-half][n][8]
         const HeadParams& Hp = n->Hp;
-        std::vector<uint16_t> w1u((size_t)P.flat * HIDDEN, 0), w2u((size_t)HIDDEN * Hp.N2, 0);
-        std::vector<float> wv32(HIDDEN + 1);  // + the value head's bias
+        w1u.assign((size_t)P.flat * HIDDEN, 0);
+        w2u.assign((size_t)HIDDEN * Hp.N2, 0);
+        wv32.assign(HIDDEN + 1, 0.f);  // + the value head's bias
         const std::vector<float>& h1 = n->host["hidden_fc.weight"];  // [256][flat]
         for (int kc = 0; kc < P.flat / 16; ++kc)
             for (int kh = 0; kh < 2; ++kh)
@@ -1207,9 +1216,9 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
         // in device memory, not in the by-value kernel parameter: captured CUDA graphs replay the parameters of their
         // capture, and the weights change between iterations
         wv32[HIDDEN] = n->host["value_fc.bias"][0];
-        if (cudaMemcpy(n->d_w1u, w1u.data(), w1u.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(n->d_w2u, w2u.data(), w2u.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(n->d_wv32, wv32.data(), wv32.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        if (cudaMemcpyAsync(n->d_w1u, w1u.data(), w1u.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(n->d_w2u, w2u.data(), w2u.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(n->d_wv32, wv32.data(), wv32.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
             return nerr(BPP_E_CUDA, "head parameter upload failed");
     }
     std::vector<uint16_t> wlp((size_t)HIDDEN * n->T.A_pad, 0);
@@ -1218,7 +1227,6 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
         for (int o = 0; o < P.A; ++o)
             for (int i = 0; i < HIDDEN; ++i) wlp[(size_t)i * n->T.A_pad + o] = f32_to_bf16_rne(src2[(size_t)o * HIDDEN + i]);
     }
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (cudaMemcpyAsync(n->d_wts_logits_pad, wlp.data(), wlp.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts_umma, wu.data(), wu.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts_umma_lo, wul.data(), wul.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -1271,11 +1279,11 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
     if (!n->committed) return nerr(BPP_E_STATE, "bpp_net_forward before bpp_net_commit");
     if (B < 0 || B > n->max_batch) return nerr(BPP_E_INVALID, "batch larger than max_batch");
     if (B == 0) return BPP_OK;
-    int grid = B < 148 * 8 ? B : 148 * 8;
+    int grid = B < n->num_sms * 8 ? B : n->num_sms * 8;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (n->precision == BPP_NET_BF16 && n->tc_ok) {
         const int groups = (B + n->T.S - 1) / n->T.S;
-        const int cap = 148 * n->ctas_per_sm;
+        const int cap = n->num_sms * n->ctas_per_sm;
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
         if (fo && n->ctas_per_sm == 2)
@@ -1292,7 +1300,7 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
                        (const __nv_bfloat16*)n->d_feat, policy_out_dev, value_out_dev);
     } else if (n->precision == BPP_NET_BF16X3 && n->tc3_ok) {
         const int groups = (B + n->T3.S - 1) / n->T3.S;
-        const int g2 = groups < 148 ? groups : 148;
+        const int g2 = groups < n->num_sms ? groups : n->num_sms;
         if (n->T3.S <= 4)
             k_net_forward_tc<4, true><<<g2, bpptc::TC_THREADS, n->T3.smem_bytes, st>>>(
                 n->P, n->T3, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof,

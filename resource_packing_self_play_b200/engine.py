@@ -164,6 +164,12 @@ class SearchEngine:
             call("bpp_engine_create", C.byref(cfg), C.byref(h))
         self._h = h
         self._keep = []
+        nvp = (self.A + 3) // 4 * 4
+        node_cap = int(node_cap) if node_cap else self.num_sims * N + N + 2
+        self.edge_cap_worst = node_cap * (3 * nvp + nvp // 4)   # every node expanded with all A actions valid
+        cap = C.c_int64(0)
+        call("bpp_engine_edge_cap", self._h, C.byref(cap))
+        self.edge_cap = int(cap.value)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -322,6 +328,62 @@ class SearchEngine:
              vp(out["r"]), vp(out["score"]), vp(out["moves"]), _stream())
         return out
 
+    # -- asynchronous whole episodes with the batched device evaluator ---------------------------------------------------
+    def set_auto_play(self, mode, seed=0, counts=None, actions=None, roots=None):
+        """arm (mode = CHOOSE_*) / disarm (mode = -1) per-game move completion inside expand_select"""
+        self._keep_auto = (counts, actions, roots)
+        call("bpp_engine_set_auto_play", self._h, int(mode), C.c_uint64(seed), _ptr(counts), _ptr(actions), _ptr(roots))
+
+    def progress_async(self, pinned4):
+        """queue a copy of [parked leaves, capped games, games still playing, 0] into a pinned int32[4] tensor"""
+        call("bpp_engine_progress_async", self._h, C.c_void_p(pinned4.data_ptr()), _stream())
+
+    def set_profile(self, on):
+        call("bpp_engine_set_profile", self._h, int(bool(on)))
+
+    def profile(self):
+        arr = (C.c_double * 4)()
+        call("bpp_engine_profile", self._h, arr)
+        return {"evaluator_ms": arr[0], "expand_select_ms": arr[1], "steps": int(arr[2])}
+
+    def play_net(self, dnet, choose_mode=_lib.CHOOSE_SAMPLE, seed=0, record=True):
+        """Whole episodes for all games after reset(), leaves evaluated by `dnet` (a DeviceNet): one C call, no per-move
+        host round trip.  Returns a dict of device tensors: roots (N, G, 32) int32, counts (N, G, A) int32, actions
+        (N, G) int32 (rows of moves a game did not play: 0 / 0 / -1) and `steps` (lockstep steps queued)."""
+        roots = counts = actions = None
+        if record:
+            roots = torch.empty((self.N, self.G, REC_WORDS), dtype=torch.int32, device=self.device)
+            counts = torch.empty((self.N, self.G, self.A), dtype=torch.int32, device=self.device)
+            actions = torch.empty((self.N, self.G), dtype=torch.int32, device=self.device)
+        steps = C.c_int32(0)
+        call("bpp_engine_play_net", self._h, dnet._h, int(choose_mode), C.c_uint64(seed), _ptr(counts), _ptr(actions),
+             _ptr(roots), C.byref(steps), _stream())
+        return {"roots": roots, "counts": counts, "actions": actions, "steps": int(steps.value)}
+
+    def play_net_host(self, dnet, items_wh, total_area, bl, tie=None, choose_mode=_lib.CHOOSE_SAMPLE, seed=0, out=None):
+        """HOST-buffer episode batch with the real net through the C ABI (uploads, plays, downloads, synchronises).
+        `out` may hold preallocated (ideally pinned) numpy arrays: roots (N,G,32) u32, counts (N,G,A) i32, actions
+        (N,G) i32, r (G,) i32, score (G,) f64, moves (G,) i32."""
+        items = np.ascontiguousarray(items_wh, dtype=np.int32)
+        area = np.ascontiguousarray(total_area, dtype=np.int32)
+        blh = np.ascontiguousarray(bl, dtype=np.float64)
+        tieh = np.ascontiguousarray(tie, dtype=np.int8) if tie is not None else None
+        if out is None:
+            out = {}
+        out.setdefault("roots", np.empty((self.N, self.G, REC_WORDS), dtype=np.uint32))
+        out.setdefault("counts", np.empty((self.N, self.G, self.A), dtype=np.int32))
+        out.setdefault("actions", np.empty((self.N, self.G), dtype=np.int32))
+        out.setdefault("r", np.empty(self.G, dtype=np.int32))
+        out.setdefault("score", np.empty(self.G, dtype=np.float64))
+        out.setdefault("moves", np.empty(self.G, dtype=np.int32))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        steps = C.c_int32(0)
+        call("bpp_engine_play_net_host", self._h, dnet._h, int(choose_mode), C.c_uint64(seed), vp(items), vp(area),
+             vp(blh), vp(tieh) if tieh is not None else C.c_void_p(0), vp(out["roots"]), vp(out["counts"]),
+             vp(out["actions"]), vp(out["r"]), vp(out["score"]), vp(out["moves"]), C.byref(steps), _stream())
+        out["steps"] = int(steps.value)
+        return out
+
     # -- results ------------------------------------------------------------------------------------------------------
     def root_counts(self):
         out = torch.empty((self.G, self.A), dtype=torch.int32, device=self.device)
@@ -411,7 +473,7 @@ class SearchEngine:
     def stats(self, reset=False):
         arr = (C.c_uint64 * 8)()
         call("bpp_engine_stats", self._h, arr, int(reset), _stream())
-        keys = ["sims", "edges", "expansions", "terminals", "nodes_created", "probes", "launches", "_"]
+        keys = ["sims", "edges", "expansions", "terminals", "nodes_created", "probes", "launches", "edge_units_read"]
         return {k: int(v) for k, v in zip(keys, arr)}
 
     def check(self):

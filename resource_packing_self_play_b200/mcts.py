@@ -21,6 +21,8 @@ _TIE_RNG = np.random.default_rng()
 
 
 class MCTS:
+    EPISODES_WARM = 8  # episodes one object can search on a warm graph before it is dropped (see _prepare)
+
     def __init__(self, game, nnet, args, device=None):  # MCTS_bpp.py:16-26
         self.game = game
         self.nnet = nnet
@@ -35,8 +37,14 @@ class MCTS:
     def _engine(self):
         if self._eng is None:
             g = self.game
-            self._eng = SearchEngine(g.bin_width, g.bin_height, g.num_items, 1, int(self.args.numMCTSSims),
-                                     float(self.args.cpuct), device=self.device)
+            # One game: memory is no concern, so the pools hold EPISODES_WARM episodes' worth of nodes (the reference's
+            # dicts keep growing when one MCTS object plays several games, CoachBPP.arena_playing :233-283, or when
+            # search() is called many times); edge_cap = worst case, which can never overflow before the nodes do.
+            sims, N, A = int(self.args.numMCTSSims), g.num_items, g.bin_width * g.num_items
+            self._node_cap = self.EPISODES_WARM * (sims * N + N + 2)
+            nvp = (A + 3) // 4 * 4
+            self._eng = SearchEngine(g.bin_width, g.bin_height, N, 1, sims, float(self.args.cpuct), device=self.device,
+                                     node_cap=self._node_cap, edge_cap=self._node_cap * (3 * nvp + nvp // 4))
         return self._eng
 
     def reset(self):
@@ -60,6 +68,14 @@ class MCTS:
                     same = False  # a remaining item has other dims than this episode's: a different instance
                     break
         eng = self._engine()
+        if same:
+            # The reference's dicts grow without bound; the device pools do not.  If this call could outgrow them (more
+            # than EPISODES_WARM episodes' worth of nodes on one object, e.g. the same instance replayed many times), the
+            # graph is dropped: the search then starts cold, which changes visit counts only relative to a reference MCTS
+            # object that was itself kept warm that long.
+            nodes, _ = eng.graph_sizes()
+            if int(nodes[0]) + int(self.args.numMCTSSims) + 2 > self._node_cap:
+                same = False
         if not same:
             # new episode: a state key of the reference is the full tensor, so states of another instance never match
             # the old dict entries; dropping the graph is equivalent (see DESIGN.md for the one exception)
@@ -135,17 +151,36 @@ class MCTS:
 class BatchedMCTS:
     """G lockstep games: the batched counterpart of MCTS.getActionProb + CoachBPP.executeEpisode's move loop."""
 
-    def __init__(self, game, nnet, args, G, device=None):
+    def __init__(self, game, nnet, args, G, device=None, edge_cap=0):
         self.game, self.nnet, self.args, self.G = game, nnet, args, G
         if device is None:
             device = getattr(getattr(nnet, "device", None), "index", None)
         self.eng = SearchEngine(game.bin_width, game.bin_height, game.num_items, G, int(args.numMCTSSims),
-                                float(args.cpuct), device=device)
+                                float(args.cpuct), device=device, edge_cap=edge_cap)
         self.steps = 0
         self.use_graphs = os.environ.get("BPP_NO_GRAPHS") is None
         self.fused = os.environ.get("BPP_NO_FUSED_STEP") is None
         self.pipeline = os.environ.get("BPP_NO_PIPELINE") is None
         self._graphs, self._eager_chunks, self.graph_launches = {}, 0, 0
+
+    def close(self):
+        """free the engine's device pools and drop the captured step graphs (they point into those pools)"""
+        self._graphs = {}
+        self.eng.close()
+
+    def play_episodes(self, items_wh, total_area, rewards_list, greedy=False, seed=0, tie=None, record=True, mode=None):
+        """Whole self-play episodes for all G games (CoachBPP.executeEpisode, CoachBPP.py:50-99, batched): every game
+        runs numMCTSSims simulations per move, chooses (sample ~ counts, or a random arg-max when greedy) and plays on
+        at its own pace inside the search kernels (bpp_engine_play_net); the host only polls for the end of the batch.
+        Returns the compact examples as device tensors: roots (N,G,32), counts (N,G,A), actions (N,G), moves, r, score."""
+        self.reset(items_wh, total_area, rewards_list, tie)
+        if mode is None:
+            mode = _lib.CHOOSE_GREEDY if greedy else _lib.CHOOSE_SAMPLE
+        out = self.eng.play_net(self.nnet.dnet, mode, seed, record)
+        self.steps += out.pop("steps")
+        st = self.eng.status()
+        out.update(moves=st["moves"], r=st["r"], score=st["score"], done=st["done"])
+        return out
 
     def reset(self, items_wh, total_area, rewards_list, tie=None):
         bl = np.full(self.G, ranked_threshold(rewards_list, self.args.alpha))
@@ -170,7 +205,10 @@ class BatchedMCTS:
                     eng.expand_select(self._pol, self._val)
                 else:
                     eng.expand_backup(self._pol, self._val)
-        key = (chunk, cap, eng.num_sims, self.fused, torch.cuda.current_stream().cuda_stream, net._h.value, getattr(net, "precision", None))
+        # the evaluator is identified by a per-DeviceNet serial number, not by its handle's address (a freed handle's
+        # address can be reused by the next DeviceNet, whose buffers a replayed graph would then miss)
+        key = (chunk, cap, eng.num_sims, self.fused, torch.cuda.current_stream().cuda_stream, net.uid,
+               getattr(net, "precision", None))
         graph = self._graphs.get(key) if self.use_graphs else None
         if graph is None and self.use_graphs and self._eager_chunks >= 2:
             torch.cuda.synchronize()

@@ -79,16 +79,21 @@ class BinPackingNNet(nn.Module):  # BinpackingNNet.py:50-81
 
 class DeviceNet:
     """Handle of the CUDA forward (bpp_net_*)."""
+    _serial = 0
 
     def __init__(self, W, H, N, max_batch, device=None):
         _lib.load()
+        DeviceNet._serial += 1
+        self.uid = DeviceNet._serial
         device = _devidx(device)
         self.W, self.H, self.N, self.A = W, H, N, W * N
         self.max_batch = max_batch
         self.device = torch.device("cuda", device)
         h = C.c_void_p()
-        call("bpp_net_create", W, H, N, max_batch, device, C.byref(h))
+        with torch.cuda.device(self.device):
+            call("bpp_net_create", W, H, N, max_batch, device, C.byref(h))
         self._h = h
+        self.precision = "bf16"
 
     def close(self):
         if getattr(self, "_h", None):
@@ -222,7 +227,15 @@ class DeviceLearner:
 class NNetWrapper:
     """Same surface as NNet.py:17-111: predict / train / save_checkpoint / load_checkpoint."""
 
-    def __init__(self, game, args, max_batch=8192, device=None, precision="bf16"):
+    # calibration bound of precision="auto": half of the stated tolerance |d pi| <= 2e-2, |d v| <= 2e-2 (SURVEY.md §8(d))
+    AUTO_TOL = 1e-2
+
+    def __init__(self, game, args, max_batch=8192, device=None, precision="auto"):
+        """precision: "auto" (default) picks, at every sync_weights(), the fastest tensor-core mode that reproduces the
+        fp32 forward of the CURRENT weights on a set of calibration states: plain "bf16" for well-conditioned networks
+        (fresh initialisations), split-bf16 "bf16x3" otherwise (the reference's trained checkpoints have logits down to
+        -4.8e3: one rounding to bf16 or fp16 anywhere in the network moves pi by up to 0.6, profiles/
+        r02_precision_study.txt), "fp32" (CUDA cores) if even that fails.  An explicit mode is taken as given."""
         device = _devidx(device)
         self.args = args
         self.game = game
@@ -233,12 +246,61 @@ class NNetWrapper:
         self.device = torch.device("cuda", device)
         self.nnet.to(self.device)  # the reference moves the module only if args.cuda; this path is CUDA-only
         self.dnet = DeviceNet(self.board_w, self.board_h, self.num_items, max_batch, device)
-        self.dnet.set_precision(precision)
+        self.precision_request = precision
+        self.calibration = None
+        if precision != "auto":
+            self.dnet.set_precision(precision)
         self.sync_weights()
 
     def sync_weights(self):
         """push the torch parameters into the CUDA forward (after init / load_checkpoint / train)"""
         self.dnet.load_state_dict(self.nnet.state_dict())
+        if self.precision_request == "auto":
+            self._calibrate()
+
+    def _calibration_states(self, n=64):
+        """n reachable states (random legal play from generated instances), as compact records + item lists on the device"""
+        cal = getattr(self, "_cal_states", None)
+        if cal is None:
+            from .engine import EnvOps
+            from .game import ItemsGenerator
+            W, H, N = self.board_w, self.board_h, self.num_items
+            rs = np.random.RandomState(20201113)
+            hts = rs.randint(max(1, (N + W - 1) // W), H + 1, size=n).astype(np.int32)
+            items = torch.from_numpy(ItemsGenerator(W, H, N).items_batch(np.arange(n) + 31337, hts)).to(self.device)
+            ops = EnvOps(W, H, N, self.device.index)
+            recs = torch.zeros((n, 32), dtype=torch.int32, device=self.device)
+            recs[:, 28] = (1 << N) - 1
+            depth = torch.from_numpy(rs.randint(0, N, size=n)).to(self.device)
+            u = torch.from_numpy(rs.random_sample((N, n))).to(self.device)
+            for k in range(N - 1):
+                valid = ops.valid_moves(recs, items).bool()
+                cnt = valid.sum(dim=1)
+                pick = (u[k] * cnt.clamp(min=1)).long().clamp(max=(cnt - 1).clamp(min=0))
+                act = (valid.cumsum(dim=1) == (pick + 1)[:, None]).int().argmax(dim=1).to(torch.int32)
+                nxt = ops.next_state(recs, items, act)
+                go = (depth > k) & (cnt > 0)
+                still = ops.valid_moves(nxt, items).any(dim=1)   # never calibrate on a terminal state
+                recs = torch.where((go & still)[:, None], nxt, recs)
+            cal = self._cal_states = (recs.contiguous(), items.contiguous())
+        return cal
+
+    def _calibrate(self):
+        recs, items = self._calibration_states()
+        self.dnet.set_precision("fp32")
+        p_ref, v_ref = self.dnet.forward(recs, items)
+        chosen, report = "fp32", {}
+        for mode in ("bf16", "bf16x3"):
+            self.dnet.set_precision(mode)
+            p, v = self.dnet.forward(recs, items)
+            dp, dv = float((p - p_ref).abs().max()), float((v - v_ref).abs().max())
+            report[mode] = (dp, dv)
+            if dp <= self.AUTO_TOL and dv <= self.AUTO_TOL and np.isfinite(dp) and np.isfinite(dv):
+                chosen = mode
+                break
+        self.dnet.set_precision(chosen)
+        self.calibration = {"mode": chosen, "errors": report}
+        return chosen
 
     # ---- inference ---------------------------------------------------------------------------------------------------
     def predict(self, board):
@@ -279,16 +341,23 @@ class NNetWrapper:
         items_t = torch.from_numpy(items).to(self.device)
         pis_t = torch.as_tensor(np.asarray(pis, dtype=np.float32), device=self.device)
         vs_t = torch.as_tensor(np.asarray(vs).astype(np.float64).astype(np.float32).reshape(-1), device=self.device)
-        L = self._device_learner(bs)
-        for epoch in range(self.args.epochs):
-            batch_count = int(len(examples) / bs)
-            for _ in range(batch_count):
-                ids = torch.from_numpy(np.random.randint(len(examples), size=bs).astype(np.int64)).to(self.device)
-                L.grad(recs_t, items_t, pis_t, vs_t, ids=ids)
-                if ws > 1:
-                    torch.distributed.all_reduce(L.grads)
-                L.adam(grad_scale=1.0 / ws)
-        L.state_dict_into(self.nnet)
+        batch_count = int(len(examples) / bs)
+        if ws > 1:
+            # every rank must issue the same number of gradient all-reduces: agree on the smallest per-rank step count
+            # (ranks holding different numbers of examples would otherwise hang in NCCL)
+            bc = torch.tensor([batch_count], dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(bc, op=torch.distributed.ReduceOp.MIN)
+            batch_count = int(bc.item())
+        with torch.cuda.device(self.device):  # the learner's entry points launch on the current device's stream
+            L = self._device_learner(bs)
+            for epoch in range(self.args.epochs):
+                for _ in range(batch_count):
+                    ids = torch.from_numpy(np.random.randint(len(examples), size=bs).astype(np.int64)).to(self.device)
+                    L.grad(recs_t, items_t, pis_t, vs_t, ids=ids)
+                    if ws > 1:
+                        torch.distributed.all_reduce(L.grads)
+                    L.adam(grad_scale=1.0 / ws)
+            L.state_dict_into(self.nnet)
         self.nnet.eval()
         self.sync_weights()
 

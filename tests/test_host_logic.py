@@ -146,3 +146,19 @@ def test_multiply_shift_division_used_by_the_forward_kernel_is_exact():
     nn = (rng.randint(0, 1 << 31, size=200000).astype(np.uint64) * np.uint64(2)) % ((np.uint64(1) << np.uint64(32)) // d)
     m = np.uint64(0xFFFFFFFF) // d + np.uint64(1)
     assert np.array_equal((nn * m) >> np.uint64(32), nn // d)
+
+
+def test_trim_rewards_equals_the_reference_loop():
+    """learn_batched appends a whole batch of scores and trims once; CoachBPP.py:134-139 appends one score per episode and
+    trims after the iteration with `while len > cap: pop(argmin)`.  Same multiset, same order of the survivors — also at
+    G = numEps = 20 with ties (the shipped buffer is 100 x 1.0)."""
+    from resource_packing_self_play_b200.coach import trim_rewards
+    rng = np.random.RandomState(0)
+    for trial in range(200):
+        cap = int(rng.choice([5, 20, 100]))
+        old = list(rng.choice([1.0, 0.5, 0.75, 0.9], size=rng.randint(0, cap + 1))) if trial % 2 else [1.0] * cap
+        new = list(np.round(rng.random_sample(rng.choice([1, 20, 37])), 2))
+        ref = list(old) + list(new)
+        while len(ref) > cap:  # the reference's loop, CoachBPP.py:136-139
+            ref.pop(int(np.argmin(ref)))
+        assert trim_rewards(old, new, cap) == [float(x) for x in ref]
