@@ -311,6 +311,8 @@ int bpp_net_set_precision(bpp_net *n, int mode);
 /* Phase timers (SM clock cycles, CTA 0 of the last tensor-core forward; synchronises the device):
  * [0] input planes, [1] weight staging, [2] MMA issue, [3] MMA wait, [4] epilogue, [5] pooling, [6] heads, [7] total. */
 int bpp_net_profile(bpp_net *n, int64_t cycles_host[8]);
+/* the same timers per role kernel of the split trunk (k_net_role<0..2>): cycles_host[8 * role + slot] */
+int bpp_net_profile_roles(bpp_net *n, int64_t cycles_host[24]);
 /* Forward for B compact states.  recs_dev uint32 [B][32], game_dev int32 [B] (index into items_wh_dev rows; may be
  * NULL for identity), items_wh_dev int32 [*][N][2]; if count_dev != NULL the batch size is read from device memory
  * (*count_dev <= B).  policy_out_dev float32 [B][A] = exp(log_softmax(logits)); value_out_dev float32 [B]. */

@@ -93,6 +93,8 @@ struct Params {
     const double* sqrt_tab;     // [3][sqrt_n]: sqrt(n), sqrt(n + 1e-8), 1/n (correctly rounded, host-computed)
     int sqrt_n;
     int select_cap;             // lockstep: simulations per game and select launch (0 = until a leaf is parked)
+    int edge_budget;            // lockstep: a game starts no new simulation in a launch once it has walked this many edges
+                                // in it (0 = no limit); bounds the launch time in work units instead of simulations
     // asynchronous episodes (bpp_engine_set_auto_play): a game that completes its num_sims simulations inside
     // k_expand_search writes its visit-count row, chooses, plays the move and goes on with the next move in the same launch
     int auto_mode;              // -1 = off, else BPP_CHOOSE_*
@@ -666,7 +668,7 @@ k_expand_search(Params P, const void* policy, int policy_f64, const void* value,
         int budget = P.select_cap > 0 ? P.select_cap : 0x7fffffff;
         for (;;) {
             bool parked = false;
-            while (done < P.num_sims && budget > 0) {
+            while (done < P.num_sims && budget > 0 && (P.edge_budget == 0 || st.edges < (unsigned)P.edge_budget)) {
                 const int rc = simulate<0, HC>(P, gm, sm, lane, st);
                 if (rc != 0) {  // parked leaf (counted when it is expanded) or overflow
                     parked = true;
@@ -1584,13 +1586,22 @@ extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode,
     if (counts_out_dev) CUDA_TRY(cudaMemsetAsync(counts_out_dev, 0, N * G * A * sizeof(int32_t), S(stream)));
     if (actions_out_dev) CUDA_TRY(cudaMemsetAsync(actions_out_dev, 0xff, N * G * sizeof(int32_t), S(stream)));
     if (roots_out_dev) CUDA_TRY(cudaMemsetAsync(roots_out_dev, 0, N * G * REC_WORDS * sizeof(uint32_t), S(stream)));
+    // Work per game and launch.  A launch lasts as long as its slowest warp, and a game whose simulations end on terminal
+    // states parks no leaf, so its work per launch is bounded - in EDGES WALKED (a late-game simulation is 1-2 edges deep,
+    // an early one 5-10), not in simulations.  The bound adapts to the leaf supply: with a sharp trained policy only ~2 %
+    // of the simulations need the evaluator, and the bound grows until about half of the running games park a leaf per
+    // step; with a flat prior it stays small so that parked games do not wait for long descents of the others.
     const int keep_cap = P.select_cap;
-    const char* cap_env = getenv("BPP_SELECT_CAP");
-    P.select_cap = cap_env ? atoi(cap_env) : 2;
-    if (P.select_cap < 0) P.select_cap = 0;
+    const char* bud_env = getenv("BPP_EDGE_BUDGET");
+    const bool adapt = bud_env == nullptr;
+    int budget = bud_env ? atoi(bud_env) : 16;
+    if (budget < 0) budget = 0;
+    P.select_cap = 0;
+    P.edge_budget = budget;
     if ((rc = bpp_engine_set_auto_play(e, choose_mode, seed, counts_out_dev, actions_out_dev, roots_out_dev))) return rc;
     auto restore = [&]() {
         P.select_cap = keep_cap;
+        P.edge_budget = 0;
         bpp_engine_set_auto_play(e, -1, 0, nullptr, nullptr, nullptr);
     };
     if ((rc = bpp_engine_begin_move(e, stream)) || (rc = bpp_engine_select(e, stream))) {
@@ -1632,6 +1643,11 @@ extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode,
             ce = cudaEventSynchronize(e->ev_prog[(k - 1) & 1]);
             const int32_t* pp = e->h_prog + 4 * ((k - 1) & 1);
             if (ce == cudaSuccess && pp[0] == 0 && pp[2] == 0) break;  // nothing parked, nobody playing
+            if (adapt && pp[2] > 0) {
+                if (pp[0] * 3 < pp[2] && budget < 8192) budget *= 2;          // < 1/3 of the running games parked a leaf
+                else if (pp[0] * 4 > pp[2] * 3 && budget > 8) budget /= 2;    // > 3/4 did
+                P.edge_budget = budget;
+            }
         }
         if (ce != cudaSuccess) {
             restore();

@@ -242,11 +242,13 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     __shared__ uint32_t s_rec[NS][32];
     __shared__ int s_it[NS][BPP_MAX_ITEMS][2];
     __shared__ uint32_t s_tmem;
+    __shared__ long long s_prof[8];
     unsigned char* regA = arena;
     unsigned char* regB = arena + T.regA_bytes;
     unsigned char* wbuf = regB + T.regB_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < MAX_BARS) mbar_init(smem_u32(&s_bar[tid]), 1);
+    if (tid < 8) s_prof[tid] = 0;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "r"((uint32_t)T.tmem_cols));
@@ -260,7 +262,7 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
     cx.bar = smem_u32(&s_bar[0]);
     cx.phase = 0;
     cx.wbuf = wbuf;
-    for (int i = 0; i < 8; ++i) cx.prof[i] = 0;
+    cx.prof = s_prof;
     const long long t_start = clock64();
     const int S = T.S;
     const int cin16_0 = (P.Cin + 15) / 16;
@@ -544,6 +546,220 @@ k_net_forward_tc(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __rest
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"((uint32_t)T.tmem_cols));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Role kernels: the trunk split at the ConvSequence boundaries.  k_net_role<SEQ> runs sequence SEQ (conv3x3 -> max-pool ->
+// two residual blocks, BinpackingNNet.py:29-48) for the WHOLE batch and hands its residual stream to the next role
+// through HBM (8x8x16 / 4x4x32 bf16 per leaf at 15x15: 2 KB / 1 KB), so that every role picks its own group size: the
+// deep levels are tiny (25 and 9 rows per leaf), and with the one-kernel trunk's 5 leaves per group nine of its fifteen
+// layers ran a single, mostly empty 128-row tile behind a full per-layer latency chain (weights -> barrier -> MMAs ->
+// epilogue -> barrier).  Here role 1 takes ~8 and role 2 ~25 leaves per group: full tiles, the chain amortised 2-5x.
+// Hand-over layout: [leaf][hi|lo (X3 only)][8-channel plane][pixel] 16-byte units, interior pixels only.
+template <int SEQ, bool X3, int MINB>
+__global__ void __launch_bounds__(bpptc::TC_THREADS, MINB)
+k_net_role(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__ count_dev,
+           const uint32_t* __restrict__ recs, const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh,
+           const uint4* __restrict__ xin, uint4* __restrict__ xout, __nv_bfloat16* __restrict__ feat_out, long long* prof) {
+    using namespace bpptc;
+    constexpr int NSR = SEQ == 0 ? 8 : 1;
+    extern __shared__ __align__(1024) unsigned char arena[];
+    __shared__ __align__(8) uint64_t s_bar[MAX_BARS];
+    __shared__ uint32_t s_rec[NSR][32];
+    __shared__ int s_it[NSR][BPP_MAX_ITEMS][2];
+    __shared__ uint32_t s_tmem;
+    __shared__ long long s_prof[8];
+    unsigned char* regA = arena;
+    unsigned char* regB = arena + T.regA_bytes;
+    unsigned char* wbuf = regB + T.regB_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < MAX_BARS) mbar_init(smem_u32(&s_bar[tid]), 1);
+    if (tid < 8) s_prof[tid] = 0;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)T.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    Ctx cx;
+    cx.tmem = s_tmem;
+    cx.bar = smem_u32(&s_bar[0]);
+    cx.phase = 0;
+    cx.wbuf = wbuf;
+    cx.prof = s_prof;
+    const long long t_start = clock64();
+    const int S = T.S;
+    constexpr int l0 = 5 * SEQ;  // this role's first conv layer
+    const int cin16 = (P.conv[l0].ci + 15) / 16;
+    const int cout = P.conv[l0].co;
+    const int fx = X3 ? 2 : 1;
+    WPre pre;
+    auto lay_w = [&](int l) { return T.wts_umma + T.w_off[l]; };
+    auto lay_b = [&](int l) { return P.bias + P.conv[l].b_off; };
+    auto lay_wl = [&](int l) { return T.wts_umma_lo + T.w_off[l]; };
+    if (!X3) wpre_load(pre, lay_w(l0), T.lay_n16[l0], lay_b(l0), cout);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
+    const int slice_lo = (int)(((long long)blockIdx.x * B) / gridDim.x);
+    const int slice_hi = (int)(((long long)(blockIdx.x + 1) * B) / gridDim.x);
+    const int n_slice = slice_hi - slice_lo;
+    const int n_groups = (n_slice + S - 1) / S;
+    const int gsz = n_groups > 0 ? (n_slice + n_groups - 1) / n_groups : S;
+    const Level& La = T.lv[SEQ];
+    const Level& Lb = T.lv[SEQ + 1];
+    const int in_planes_n = 2 * cin16;
+    const int hwa = La.h * La.w, hwb = Lb.h * Lb.w;
+    const int planes = cout / 8;
+    for (int b0 = slice_lo; b0 < slice_hi; b0 += gsz) {
+        const int nvalid = min(gsz, slice_hi - b0);
+        long long tq = clock64();
+        // ---- this role's input in the level-SEQ operand planes (region A)
+        zero_bytes(regA, fx * in_planes_n * La.RT * 16);
+        if (SEQ == 0) {
+            for (int i = tid; i < nvalid * 32; i += TC_THREADS) s_rec[i >> 5][i & 31] = recs[(size_t)(b0 + (i >> 5)) * 32 + (i & 31)];
+            for (int i = tid; i < nvalid * P.N * 2; i += TC_THREADS) {
+                const int j = i / (P.N * 2), r = i - j * P.N * 2;
+                const int b = b0 + j;
+                const int g = game ? game[b] : b;
+                s_it[j][r >> 1][r & 1] = items_wh[(size_t)g * P.N * 2 + r];
+            }
+        }
+        __syncthreads();
+        if (SEQ == 0) {
+            // input planes from the compact records (getBinItem, BinPackingGame.py:118-120): one thread builds half a grid
+            // row of one 8-channel plane (see k_net_forward_tc)
+            const int rows = nvalid * P.H;
+            const int xh = (P.W + 1) >> 1;
+            const uint32_t mrows = fdiv_magic((uint32_t)rows);
+            for (int idx = tid; idx < 2 * in_planes_n * rows; idx += TC_THREADS) {
+                const int hp = fdiv(idx, mrows);
+                int r = idx - hp * rows;
+                const int j = fdiv(r, T.mH), y = r - j * P.H;
+                const int half = hp >= in_planes_n ? 1 : 0, p = hp - half * in_planes_n;
+                const uint32_t rem = s_rec[j][BPP_REC_REM];
+                uint32_t m[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int c = p * 8 + k;
+                    m[k] = 0;
+                    if (c == 0) m[k] = s_rec[j][y];
+                    else if (c <= P.N && ((rem >> (c - 1)) & 1u) && y < s_it[j][c - 1][1]) {
+                        const int iw = s_it[j][c - 1][0];
+                        m[k] = iw >= 32 ? 0xffffffffu : (1u << iw) - 1u;
+                    }
+                }
+                const int x0 = half ? xh : 0, n = half ? P.W - xh : xh;
+                uint4* dst = reinterpret_cast<uint4*>(regA) + (size_t)p * La.RT + La.guard + j * La.P + (y + 1) * La.wp + 1 + x0;
+                int i = n > 0 ? lane % n : 0;
+                for (int step = 0; step < n; ++step) {
+                    const int x = x0 + i;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        w[q] = (((m[2 * q] >> x) & 1u) | (((m[2 * q + 1] >> x) & 1u) << 16)) * 0x3f80u;  // bf16 1.0 pairs
+                    dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                    if (++i == n) i = 0;
+                }
+            }
+        } else {
+            // the previous role's residual stream: [leaf][hi|lo][plane][pixel] -> zero-haloed grids
+            const int per = fx * in_planes_n * hwa;
+            const uint32_t mper = fdiv_magic((uint32_t)per);
+            const uint32_t mhwa = fdiv_magic((uint32_t)hwa);
+            const uint4* src = xin + (size_t)b0 * per;
+            for (int idx = tid; idx < nvalid * per; idx += TC_THREADS) {
+                const int j = fdiv(idx, mper);
+                int r = idx - j * per;
+                const int hp = fdiv(r, mhwa), q = r - hp * hwa;   // hp = half * planes + plane
+                const int y = fdiv(q, La.mw), x = q - y * La.w;
+                const size_t row = (size_t)La.guard + (size_t)j * La.P + (size_t)(y + 1) * La.wp + (x + 1);
+                reinterpret_cast<uint4*>(regA)[(size_t)hp * La.RT + row] = __ldg(src + idx);
+            }
+        }
+        __syncthreads();
+        TC_PROF(0, tq);
+        int li = l0;
+        const uint32_t in_lo = (uint32_t)in_planes_n * (uint32_t)La.RT * 16u;   // bytes of the input's hi planes
+        const uint32_t t_lo = (uint32_t)planes * (uint32_t)La.RT * 16u;         // bytes of T's hi planes
+        unsigned char* Tbuf = regB;
+        conv_layer<X3>(T, cx, La, nvalid, cin16, cout, lay_w(li), lay_b(li), regA, EPI_CONV, Tbuf, nullptr, pre,
+                       lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co, lay_wl(li), in_lo, t_lo, 0u);
+        ++li;
+        tq = clock64();
+        const size_t pb = (size_t)planes * Lb.RT * 16;   // one logical buffer (hi planes)
+        const size_t bs = X3 ? 2 * pb : pb;               // stride between logical buffers (hi [+ lo])
+        unsigned char* raw = regA;
+        unsigned char* actA = regA + bs;
+        unsigned char* actB = regA + 2 * bs;
+        zero_bytes(regA, (int)(3 * bs));
+        if (!X3) pool_pad_tail(La, nvalid, planes, Tbuf);
+        __syncthreads();
+        if (X3) pool_level_x3(La, Lb, nvalid, planes, Tbuf, t_lo, raw, (uint32_t)pb, actA, (uint32_t)pb);
+        else pool_level(La, Lb, nvalid, planes, Tbuf, raw, actA);
+        __syncthreads();
+        TC_PROF(5, tq);
+        for (int blk = 0; blk < 2; ++blk) {
+            conv_layer<X3>(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actA, EPI_RES0, actB, nullptr, pre,
+                           lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co, lay_wl(li), (uint32_t)pb,
+                           (uint32_t)pb, (uint32_t)pb);
+            ++li;
+            const int nx = li + 1 == l0 + 5 ? l0 : li + 1;   // after the role's last layer: its first layer (next group)
+            conv_layer<X3>(T, cx, Lb, nvalid, cout / 16, cout, lay_w(li), lay_b(li), actB, EPI_RES1, actA, raw, pre,
+                           lay_w(nx), T.lay_n16[nx], lay_b(nx), P.conv[nx].co, lay_wl(li), (uint32_t)pb, (uint32_t)pb,
+                           (uint32_t)pb);
+            ++li;
+        }
+        tq = clock64();
+        if (SEQ < 2) {
+            // hand the residual stream (interior pixels) to the next role
+            const int per = fx * planes * hwb;
+            const uint32_t mper = fdiv_magic((uint32_t)per);
+            const uint32_t mhwb = fdiv_magic((uint32_t)hwb);
+            uint4* dst = xout + (size_t)b0 * per;
+            for (int idx = tid; idx < nvalid * per; idx += TC_THREADS) {
+                const int j = fdiv(idx, mper);
+                int r = idx - j * per;
+                const int hp = fdiv(r, mhwb), q = r - hp * hwb;
+                const int y = fdiv(q, Lb.mw), x = q - y * Lb.w;
+                const size_t row = (size_t)Lb.guard + (size_t)j * Lb.P + (size_t)(y + 1) * Lb.wp + (x + 1);
+                dst[idx] = reinterpret_cast<const uint4*>(raw)[(size_t)hp * Lb.RT + row];
+            }
+        } else {
+            // relu(flatten(x)) as bf16 [B][flat] (hi, and lo `flat_lo_off` elements behind it in X3 mode) for the FC heads
+            const uint32_t mflat = fdiv_magic((uint32_t)P.flat);
+            for (int idx = tid; idx < nvalid * P.flat; idx += TC_THREADS) {
+                const int j = fdiv(idx, mflat), f = idx - j * P.flat;
+                const int c = fdiv(f, Lb.mhw), q = f - c * hwb;
+                const int y = fdiv(q, Lb.mw), x = q - y * Lb.w;
+                const size_t row = (size_t)Lb.guard + (size_t)j * Lb.P + (size_t)(y + 1) * Lb.wp + (x + 1);
+                const size_t eoff = ((size_t)(c >> 3) * Lb.RT + row) * 16;
+                const uint16_t e = *(reinterpret_cast<const uint16_t*>(raw + eoff) + (c & 7));
+                if (!X3) {
+                    reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (e & 0x8000u) ? (uint16_t)0 : e;
+                } else {
+                    const uint16_t el = *(reinterpret_cast<const uint16_t*>(raw + pb + eoff) + (c & 7));
+                    const float v = fmaxf(__uint_as_float((uint32_t)e << 16) + __uint_as_float((uint32_t)el << 16), 0.f);
+                    const uint32_t hb = pack_bf16(v, 0.f) & 0xffffu;
+                    const uint32_t lb = pack_bf16(v - __uint_as_float(hb << 16), 0.f) & 0xffffu;
+                    reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (uint16_t)hb;
+                    reinterpret_cast<uint16_t*>(feat_out)[(size_t)(Bmax + b0 + j) * P.flat + f] = (uint16_t)lb;
+                }
+            }
+        }
+        __syncthreads();
+        TC_PROF(6, tq);
+    }
+    if (prof && blockIdx.x == 0 && tid == 0) {
+        cx.prof[7] = clock64() - t_start;
+        for (int i = 0; i < 8; ++i) prof[8 * SEQ + i] = cx.prof[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"((uint32_t)T.tmem_cols));
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // FC heads as batched GEMMs on the tensor core: one CTA = 128 leaves (one M tile).
@@ -834,6 +1050,12 @@ struct bpp_net {
     bool committed = false;
     int smem_bytes = 0;
     int num_sms = 148;
+    // role kernels (k_net_role): one plan per ConvSequence, bf16 [0] and split-bf16 [1]
+    bpptc::TcParams Tr[2][3];
+    int role_ctas[2][3] = {{2, 2, 2}, {1, 1, 1}};
+    bool roles_ok[2] = {false, false};
+    uint4* d_x1 = nullptr;   // hand-over buffers between the roles (sized for the split mode: hi + lo)
+    uint4* d_x2 = nullptr;
 };
 
 static const char* kSeqConvNames[5] = {"conv", "res_block0.conv0", "res_block0.conv1", "res_block1.conv0",
@@ -1029,6 +1251,62 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         n->T3 = T;
         int c3 = 1;
         n->tc3_ok = plan(n->T3, true, 220 * 1024, 1, c3, false);
+        // ---- role kernels: one plan per ConvSequence.  Region A = the role's input planes (level s), later the
+        // {raw, actA, actB} triple of level s+1; region B = the conv output T_s awaiting pooling; one layer of weights.
+        {
+            auto plan_role = [&](bpptc::TcParams& R, int seq, bool x3, int ctas) -> bool {
+                const int f = x3 ? 2 : 1;
+                const int cap_bytes = (227 * 1024) / ctas - 1024 - 4352;
+                const int cin16 = seq == 0 ? cin16_0 : chans[seq - 1] / 16;
+                const int planes_out = chans[seq] / 8;
+                int wrole = 0;
+                for (int l = 5 * seq; l < 5 * seq + 5; ++l) wrole = std::max(wrole, T.lay_n16[l] * 16);
+                const char* smax_env = getenv(seq == 0 ? "BPP_ROLE_S0" : seq == 1 ? "BPP_ROLE_S1" : "BPP_ROLE_S2");
+                const int smax = smax_env ? std::max(1, atoi(smax_env)) : (seq == 0 ? 8 : 48);
+                for (int S = std::min(smax, seq == 0 ? 8 : 48); S >= 1; --S) {
+                    R = T;  // weight tables, pointers
+                    for (int l = 0; l < 4; ++l) {
+                        bpptc::Level& L = R.lv[l];
+                        L.h = P.hs[l]; L.w = P.ws[l]; L.hp = L.h + 1; L.wp = L.w + 1; L.P = L.hp * L.wp;
+                        L.mP = bpptc::fdiv_magic((uint32_t)L.P); L.mwp = bpptc::fdiv_magic((uint32_t)L.wp);
+                        L.mhw = bpptc::fdiv_magic((uint32_t)(L.h * L.w)); L.mw = bpptc::fdiv_magic((uint32_t)L.w);
+                        L.guard = (L.wp + 1 + 7) & ~7;
+                        L.RT = L.guard + S * L.P + L.guard;
+                        L.ntiles = (S * L.P + 127) / 128;
+                    }
+                    const bpptc::Level& La = R.lv[seq];
+                    const bpptc::Level& Lb = R.lv[seq + 1];
+                    const long long a = std::max((long long)f * 2 * cin16 * La.RT * 16, (long long)f * 3 * planes_out * Lb.RT * 16);
+                    const long long over = (long long)(128 + La.wp + 8) * 16;
+                    const long long b = std::max((long long)f * planes_out * La.RT * 16, over);
+                    R.S = S;
+                    R.compact = 0;
+                    R.regA_bytes = (int)((a + 127) & ~127LL);
+                    R.regB_bytes = (int)((b + 127) & ~127LL);
+                    R.wbuf_bytes = (f * wrole + 256 + 127) & ~127;
+                    R.smem_bytes = R.regA_bytes + R.regB_bytes + R.wbuf_bytes;
+                    R.tmem_cols = ctas == 1 ? 512 : ctas == 2 ? 256 : 128;
+                    if (R.smem_bytes <= cap_bytes && La.RT < 16384 && Lb.RT < 16384) return true;
+                }
+                return false;
+            };
+            for (int x = 0; x < 2; ++x) {
+                const char* ce = getenv(x ? "BPP_ROLE_CTAS_X3" : "BPP_ROLE_CTAS");   // e.g. "2,2,2"
+                if (ce) sscanf(ce, "%d,%d,%d", &n->role_ctas[x][0], &n->role_ctas[x][1], &n->role_ctas[x][2]);
+                bool ok = getenv("BPP_NO_ROLES") == nullptr && (P.flat % 16 == 0);
+                for (int sq = 0; sq < 3 && ok; ++sq) {
+                    int& c = n->role_ctas[x][sq];
+                    if (c < 1 || c > 2) c = x ? 1 : 2;
+                    ok = plan_role(n->Tr[x][sq], sq, x != 0, c);
+                }
+                n->roles_ok[x] = ok;
+                if (ok && getenv("BPP_TC_VERBOSE"))
+                    for (int sq = 0; sq < 3; ++sq)
+                        fprintf(stderr, "bpp_net: role %d (%s): S = %d, %d CTA(s)/SM, %d B shared memory (A %d, B %d, W %d)\n", sq,
+                                x ? "bf16x3" : "bf16", n->Tr[x][sq].S, n->role_ctas[x][sq], n->Tr[x][sq].smem_bytes,
+                                n->Tr[x][sq].regA_bytes, n->Tr[x][sq].regB_bytes, n->Tr[x][sq].wbuf_bytes);
+            }
+        }
     }
     n->smem_bytes = 3 * P.buf_elems * (int)sizeof(float);
     if (cudaFuncSetAttribute(k_net_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->smem_bytes) !=
@@ -1086,7 +1364,32 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         n->T3.wbuf_bytes = keep.wbuf_bytes; n->T3.smem_bytes = keep.smem_bytes; n->T3.tmem_cols = keep.tmem_cols;
         for (int l = 0; l < 4; ++l) n->T3.lv[l] = keep.lv[l];
     }
-    if (cudaMalloc(&n->d_prof, 8 * sizeof(long long)) == cudaSuccess) cudaMemset(n->d_prof, 0, 8 * sizeof(long long));
+    for (int x = 0; x < 2; ++x)
+        for (int sq = 0; sq < 3; ++sq) {  // the role plans share the weight pointers and tables too
+            bpptc::TcParams& R = n->Tr[x][sq];
+            R.wts_umma = n->T.wts_umma; R.wts_umma_lo = n->T.wts_umma_lo; R.A_pad = n->T.A_pad; R.mH = n->T.mH;
+            R.wts_logits_pad = n->T.wts_logits_pad;
+            for (int l = 0; l < NCONV; ++l) { R.w_off[l] = n->T.w_off[l]; R.lay_n16[l] = n->T.lay_n16[l]; }
+        }
+    if (n->roles_ok[0] || n->roles_ok[1]) {
+        const size_t x1 = (size_t)max_batch * 2 * 2 * P.hs[1] * P.ws[1] * 16, x2 = (size_t)max_batch * 2 * 4 * P.hs[2] * P.ws[2] * 16;
+        bool ok = cudaMalloc(&n->d_x1, x1) == cudaSuccess && cudaMalloc(&n->d_x2, x2) == cudaSuccess;
+        auto attr = [&](const void* fn, int bytes) {
+            return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+        };
+        if (ok && n->roles_ok[0])
+            ok = attr((const void*)k_net_role<0, false, 2>, n->Tr[0][0].smem_bytes) &&
+                 attr((const void*)k_net_role<1, false, 2>, n->Tr[0][1].smem_bytes) &&
+                 attr((const void*)k_net_role<2, false, 2>, n->Tr[0][2].smem_bytes) &&
+                 attr((const void*)k_net_role<0, false, 1>, n->Tr[0][0].smem_bytes) &&
+                 attr((const void*)k_net_role<1, false, 1>, n->Tr[0][1].smem_bytes) &&
+                 attr((const void*)k_net_role<2, false, 1>, n->Tr[0][2].smem_bytes);
+        if (!ok) {
+            cudaGetLastError();
+            n->roles_ok[0] = n->roles_ok[1] = false;
+        }
+    }
+    if (cudaMalloc(&n->d_prof, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(n->d_prof, 0, 32 * sizeof(long long));
     *out = n;
     return BPP_OK;
 }
@@ -1104,6 +1407,8 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     cudaFree(n->d_w2u);
     cudaFree(n->d_wv32);
     cudaFree(n->d_bias);
+    cudaFree(n->d_x1);
+    cudaFree(n->d_x2);
     delete n;
     return BPP_OK;
 }
@@ -1241,7 +1546,17 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
 
 extern "C" int bpp_net_profile(bpp_net* n, int64_t cycles_host[8]) {
     if (!n || !cycles_host || !n->d_prof) return nerr(BPP_E_INVALID, "null argument");
-    if (cudaMemcpy(cycles_host, n->d_prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    long long all[32];
+    if (cudaMemcpy(all, n->d_prof, sizeof(all), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return nerr(BPP_E_CUDA, "profile copy failed");
+    // role kernels write one block of 8 timers each (rows 0..2): report their sum; the one-kernel trunk writes row 0
+    const bool roles = n->precision == BPP_NET_BF16 && n->roles_ok[0] && n->heads_ok;
+    for (int i = 0; i < 8; ++i) cycles_host[i] = roles ? all[i] + all[8 + i] + all[16 + i] : all[i];
+    return BPP_OK;
+}
+extern "C" int bpp_net_profile_roles(bpp_net* n, int64_t cycles_host[24]) {
+    if (!n || !cycles_host || !n->d_prof) return nerr(BPP_E_INVALID, "null argument");
+    if (cudaMemcpy(cycles_host, n->d_prof, 24 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
         return nerr(BPP_E_CUDA, "profile copy failed");
     return BPP_OK;
 }
@@ -1286,7 +1601,24 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int cap = n->num_sms * n->ctas_per_sm;
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
-        if (fo && n->ctas_per_sm == 2)
+        if (fo && n->roles_ok[0]) {
+            // three role kernels (one per ConvSequence, each with its own group size) chained by programmatic launches,
+            // then the FC heads
+            const uint4* xin[3] = {nullptr, n->d_x1, n->d_x2};
+            uint4* xout[3] = {n->d_x1, n->d_x2, nullptr};
+            for (int sq = 0; sq < 3; ++sq) {
+                const bpptc::TcParams& R = n->Tr[0][sq];
+                const int c = n->role_ctas[0][sq];
+                const int gr = std::max(1, std::min((B + R.S - 1) / R.S, n->num_sms * c));
+#define ROLE_LAUNCH(SQ, MB)                                                                                            \
+    launch_pdl(k_net_role<SQ, false, MB>, gr, bpptc::TC_THREADS, (size_t)R.smem_bytes, st, n->P, R, B, count_dev, recs_dev, \
+               game_dev, items_wh_dev, xin[SQ], xout[SQ], fo, n->d_prof)
+                if (sq == 0) { if (c == 2) ROLE_LAUNCH(0, 2); else ROLE_LAUNCH(0, 1); }
+                else if (sq == 1) { if (c == 2) ROLE_LAUNCH(1, 2); else ROLE_LAUNCH(1, 1); }
+                else { if (c == 2) ROLE_LAUNCH(2, 2); else ROLE_LAUNCH(2, 1); }
+#undef ROLE_LAUNCH
+            }
+        } else if (fo && n->ctas_per_sm == 2)
             launch_pdl(k_net_forward_tc<8, false, true, 2>, g2, bpptc::TC_THREADS, (size_t)n->T.smem_bytes, st, n->P, n->T, B,
                        count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
         else if (n->T.S <= 4)

@@ -206,8 +206,8 @@ struct Ctx {
     uint32_t bar;       // shared address of mbarrier[0] (MAX_BARS barriers, 8 bytes apart)
     uint32_t phase;     // one parity bit per barrier
     unsigned char* wbuf;
-    long long prof[8];  // optional phase timers (thread 0): 0 input, 1 weights, 2 mma issue, 3 mma wait, 4 epilogue,
-                        // 5 pool+zero, 6 heads, 7 total
+    long long* prof;    // phase timers of thread 0, in shared memory (registers are scarce here): 0 input, 1 weights,
+                        // 2 mma issue, 3 mma wait, 4 epilogue, 5 pool+zero, 6 heads / hand-over, 7 total
 };
 #define TC_PROF(slot, t0) do { if (threadIdx.x == 0) { const long long _t = clock64(); cx.prof[slot] += _t - (t0); (t0) = _t; } } while (0)
 

@@ -117,6 +117,12 @@ class DeviceNet:
         keys = ["input", "weights", "mma_issue", "mma_wait", "epilogue", "pool", "heads", "total"]
         return {k: int(v) for k, v in zip(keys, arr)}
 
+    def profile_roles(self):
+        arr = (C.c_int64 * 24)()
+        call("bpp_net_profile_roles", self._h, arr)
+        keys = ["input", "weights", "mma_issue", "mma_wait", "epilogue", "pool", "output", "total"]
+        return [{k: int(arr[8 * r + i]) for i, k in enumerate(keys)} for r in range(3)]
+
     def load_state_dict(self, state_dict):
         for name, t in state_dict.items():
             a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())

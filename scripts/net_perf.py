@@ -28,7 +28,7 @@ class G:
 
 def run(W, H, N, B, modes=("bf16", "bf16_simt", "fp32"), iters=20):
     torch.manual_seed(0)
-    net = NNetWrapper(G(W, H, N), dotdict(num_items=N, num_bins=1), max_batch=B)
+    net = NNetWrapper(G(W, H, N), dotdict(num_items=N, num_bins=1), max_batch=B, precision="bf16")
     rng = np.random.RandomState(0)
     recs = np.zeros((B, 32), dtype=np.uint32)
     recs[:, :H] = rng.randint(0, 1 << W, size=(B, H)) & rng.randint(0, 1 << W, size=(B, H))
@@ -55,6 +55,8 @@ def run(W, H, N, B, modes=("bf16", "bf16_simt", "fp32"), iters=20):
         out[m] = {"ms": ms, "evals_per_s": B / ms * 1e3, "tflops": B * FLOPS[(W, H, N)] / ms / 1e9}
         if m in ("bf16", "bf16x3"):
             out[m]["cta0_cycles"] = net.dnet.profile()
+            if m == "bf16" and os.environ.get("BPP_NO_ROLES") is None:
+                out[m]["cta0_cycles_per_role"] = net.dnet.profile_roles()
     return out
 
 

@@ -183,3 +183,44 @@ def test_both_shared_memory_plans_of_the_tensor_core_kernel_agree_bit_for_bit(W,
         outs.append((pol.cpu().numpy(), val.cpu().numpy()))
     assert np.isfinite(outs[0][0]).all() and abs(outs[0][0].sum(axis=1) - 1).max() < 1e-4
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("W,H,N,B", [(15, 15, 10, 777), (20, 20, 10, 301), (9, 12, 5, 64), (15, 15, 10, 3)])
+def test_role_kernels_equal_the_one_kernel_trunk_bit_for_bit(W, H, N, B, monkeypatch):
+    """The trunk split at the ConvSequence boundaries (k_net_role<0..2>, each role with its own group size, residual
+    stream handed over through HBM as bf16) runs the same arithmetic in the same order as the one-kernel trunk
+    (BPP_NO_ROLES=1): identical outputs for ragged batch sizes."""
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+    rng = np.random.RandomState(2)
+    recs = np.zeros((B, 32), dtype=np.uint32)
+    recs[:, :H] = rng.randint(0, 1 << W, size=(B, H)) & rng.randint(0, 1 << W, size=(B, H))
+    recs[:, 28] = rng.randint(1, 1 << N, size=B)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(B) % 53 + 9, None)
+    outs = []
+    for no_roles in ("", "1"):
+        if no_roles:
+            monkeypatch.setenv("BPP_NO_ROLES", "1")
+        else:
+            monkeypatch.delenv("BPP_NO_ROLES", raising=False)
+        torch.manual_seed(4)
+        net = NNetWrapper(_Game(W, H, N), dotdict(num_items=N, num_bins=1, cuda=True, epochs=1, batch_size=8),
+                          max_batch=B, precision="bf16")
+        with torch.no_grad():
+            net.nnet.logits_fc.weight.mul_(25.0)
+        net.sync_weights()
+        dev = net.device
+        pol, val = net.dnet.forward(torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev))
+        count = torch.tensor([max(1, B // 3)], dtype=torch.int32, device=dev)   # device-side batch size
+        pol2 = torch.zeros_like(pol)
+        val2 = torch.zeros_like(val)
+        net.dnet.forward(torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev), count_dev=count,
+                         policy_out=pol2, value_out=val2)
+        torch.cuda.synchronize()
+        outs.append((pol.cpu().numpy(), val.cpu().numpy(), pol2.cpu().numpy(), val2.cpu().numpy()))
+    assert np.isfinite(outs[0][0]).all() and abs(outs[0][0].sum(axis=1) - 1).max() < 1e-4
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    k = max(1, B // 3)
+    assert np.array_equal(outs[0][2][:k], outs[0][0][:k]) and not outs[0][2][k:].any()
