@@ -1614,6 +1614,7 @@ extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode,
     const int chunk = 8;
     int steps = 0;
     size_t nev = 0;
+    const bool trace = getenv("BPP_PLAY_TRACE") != nullptr;
     auto mark = [&]() {  // profiling pass only: one event per call boundary
         if (!e->prof_on) return;
         if (nev == e->prof_ev.size()) {
@@ -1642,6 +1643,7 @@ extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode,
         if (ce == cudaSuccess && k > 0) {
             ce = cudaEventSynchronize(e->ev_prog[(k - 1) & 1]);
             const int32_t* pp = e->h_prog + 4 * ((k - 1) & 1);
+            if (trace) fprintf(stderr, "play_net chunk %d: leaves %d capped %d running %d budget %d\n", k - 1, pp[0], pp[1], pp[2], budget);
             if (ce == cudaSuccess && pp[0] == 0 && pp[2] == 0) break;  // nothing parked, nobody playing
             if (adapt && pp[2] > 0) {
                 if (pp[0] * 3 < pp[2] && budget < 8192) budget *= 2;          // < 1/3 of the running games parked a leaf

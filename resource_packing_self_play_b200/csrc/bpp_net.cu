@@ -559,7 +559,8 @@ template <int SEQ, bool X3, int MINB>
 __global__ void __launch_bounds__(bpptc::TC_THREADS, MINB)
 k_net_role(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__ count_dev,
            const uint32_t* __restrict__ recs, const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh,
-           const uint4* __restrict__ xin, uint4* __restrict__ xout, __nv_bfloat16* __restrict__ feat_out, long long* prof) {
+           const uint4* __restrict__ xin, uint4* __restrict__ xout, __nv_bfloat16* __restrict__ feat_out,
+           long long feat_lo_off, long long* prof) {
     using namespace bpptc;
     constexpr int NSR = SEQ == 0 ? 8 : 1;
     extern __shared__ __align__(1024) unsigned char arena[];
@@ -616,7 +617,7 @@ k_net_role(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__
         const int nvalid = min(gsz, slice_hi - b0);
         long long tq = clock64();
         // ---- this role's input in the level-SEQ operand planes (region A)
-        zero_bytes(regA, fx * in_planes_n * La.RT * 16);
+        zero_bytes(regA, (SEQ == 0 ? 1 : fx) * in_planes_n * La.RT * 16);
         if (SEQ == 0) {
             for (int i = tid; i < nvalid * 32; i += TC_THREADS) s_rec[i >> 5][i & 31] = recs[(size_t)(b0 + (i >> 5)) * 32 + (i & 31)];
             for (int i = tid; i < nvalid * P.N * 2; i += TC_THREADS) {
@@ -685,7 +686,8 @@ k_net_role(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__
         const uint32_t t_lo = (uint32_t)planes * (uint32_t)La.RT * 16u;         // bytes of T's hi planes
         unsigned char* Tbuf = regB;
         conv_layer<X3>(T, cx, La, nvalid, cin16, cout, lay_w(li), lay_b(li), regA, EPI_CONV, Tbuf, nullptr, pre,
-                       lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co, lay_wl(li), in_lo, t_lo, 0u);
+                       lay_w(li + 1), T.lay_n16[li + 1], lay_b(li + 1), P.conv[li + 1].co, lay_wl(li), in_lo, t_lo, 0u,
+                       SEQ == 0);   // the 0/1 input planes are exact in bf16: no a_lo term in the network's first layer
         ++li;
         tq = clock64();
         const size_t pb = (size_t)planes * Lb.RT * 16;   // one logical buffer (hi planes)
@@ -744,7 +746,7 @@ k_net_role(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__
                     const uint32_t hb = pack_bf16(v, 0.f) & 0xffffu;
                     const uint32_t lb = pack_bf16(v - __uint_as_float(hb << 16), 0.f) & 0xffffu;
                     reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (uint16_t)hb;
-                    reinterpret_cast<uint16_t*>(feat_out)[(size_t)(Bmax + b0 + j) * P.flat + f] = (uint16_t)lb;
+                    reinterpret_cast<uint16_t*>(feat_out)[(size_t)feat_lo_off + (size_t)(b0 + j) * P.flat + f] = (uint16_t)lb;
                 }
             }
         }
@@ -775,6 +777,12 @@ struct HeadParams {
     const float* b1;                      // [256]
     const float* b2;                      // [A]
     const float* wv;                      // [256] (bf16-rounded values, as fp32) + [256] = the value head's bias
+    // split-bf16 (X3) mode: low halves of the FC weights in the same layouts, the exact fp32 value weights (+ bias), and
+    // the offset (elements) of the low halves of the features behind the high ones
+    const __nv_bfloat16* w1u_lo;
+    const __nv_bfloat16* w2u_lo;
+    const float* wv_f32;
+    long long feat_lo_off;
 };
 #ifdef BPP_HEADS_PROF  // phase timers of the heads kernel (debug builds: nvcc -DBPP_HEADS_PROF), printed by CTA 0
 #define HP_T(i) t_[i] = clock64()
@@ -790,6 +798,9 @@ __device__ __forceinline__ void head_cp16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bpptc::smem_u32(dst_smem)), "l"(src));
 }
 
+// X3 = split-bf16: features, hidden activations and both weight matrices are hi + lo bf16 pairs and every product is the
+// three MMAs hi*hi + lo*hi + hi*lo (the weight chunks stream twice: high halves, then low halves)
+template <bool X3>
 __global__ void __launch_bounds__(HEAD_THREADS, 1)
 k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, const __nv_bfloat16* __restrict__ feat,
                float* __restrict__ policy, float* __restrict__ value) {
@@ -806,21 +817,32 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     HP_T(0);
     const int row0 = blockIdx.x * 128;
     const int kplanes = (Hp.flat > HIDDEN ? Hp.flat : HIDDEN) / 8;
-    unsigned char* areg = hsm;                                   // planes x 128 rows x 16 B
-    unsigned char* stage0 = hsm + (size_t)kplanes * 2048;
+    unsigned char* areg = hsm;                                   // planes x 128 rows x 16 B (X3: the lo planes behind)
+    const uint32_t alo_off = (uint32_t)kplanes * 2048u;
+    unsigned char* stage0 = hsm + (size_t)(X3 ? 2 : 1) * kplanes * 2048;
     // the weight chunks of both GEMMs as one list: chunk c covers k-blocks [kb, kb + nk) of GEMM g
     const int blk1 = 2 * HIDDEN * 16, blk2 = 2 * Hp.N2 * 16;     // bytes per 16-deep k-block of W1 / W2 (UMMA B layout)
     const int kpc1 = HEAD_STAGE_BYTES / blk1, kpc2 = HEAD_STAGE_BYTES / blk2;
     const int nkb1 = Hp.flat / 16, nkb2 = HIDDEN / 16;
     const int nch1 = (nkb1 + kpc1 - 1) / kpc1, nch2 = (nkb2 + kpc2 - 1) / kpc2;
-    const int nch = nch1 + nch2;
+    const int n1 = (X3 ? 2 : 1) * nch1, n2 = (X3 ? 2 : 1) * nch2;
+    const int nch = n1 + n2;
+    // chunk c -> (GEMM 2?, low-half pass?, index inside the pass)
+    auto chunk_info = [&](int c, bool& g2, bool& lo, int& cc) {
+        g2 = c >= n1;
+        const int c2 = g2 ? c - n1 : c, np = g2 ? nch2 : nch1;
+        lo = c2 >= np;
+        cc = lo ? c2 - np : c2;
+    };
     auto issue_chunk = [&](int c) {  // cp.async this thread's share of chunk c into stage c % HEAD_STAGES
         if (c < nch) {
-            const bool g2 = c >= nch1;
-            const int cc = g2 ? c - nch1 : c;
+            bool g2, lo;
+            int cc;
+            chunk_info(c, g2, lo, cc);
             const int kpc = g2 ? kpc2 : kpc1, blk = g2 ? blk2 : blk1, nkb = g2 ? nkb2 : nkb1;
             const int kb = cc * kpc, nk = min(kpc, nkb - kb);
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(g2 ? Hp.w2u : Hp.w1u) + (size_t)kb * blk;
+            const __nv_bfloat16* wsrc = g2 ? (lo ? Hp.w2u_lo : Hp.w2u) : (lo ? Hp.w1u_lo : Hp.w1u);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(wsrc) + (size_t)kb * blk;
             unsigned char* dst = stage0 + (size_t)(c % HEAD_STAGES) * HEAD_STAGE_BYTES;
             for (int i = tid * 16; i < nk * blk; i += HEAD_THREADS * 16) head_cp16(dst + i, src + i);
         }
@@ -838,7 +860,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     }
     for (int i = tid; i < HIDDEN; i += HEAD_THREADS) {
         s_b1[i] = Hp.b1[i];
-        s_wv[i] = Hp.wv[i];
+        s_wv[i] = X3 ? Hp.wv_f32[i] : Hp.wv[i];
         s_b2[i] = i < Hp.A ? Hp.b2[i] : 0.f;
     }
     pdl_wait();  // the trunk's features and the leaf count are complete and visible from here on
@@ -855,10 +877,16 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     {
         const int r = row0 + row_l;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(feat + (size_t)r * Hp.flat);
+        const unsigned char* src_lo = reinterpret_cast<const unsigned char*>(feat + Hp.feat_lo_off + (size_t)r * Hp.flat);
         for (int p = hv; p < Hp.flat / 8; p += HEAD_NQ) {
             unsigned char* dst = areg + (size_t)p * 2048 + row_l * 16;
-            if (r < B) head_cp16(dst, src + p * 16);
-            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+            if (r < B) {
+                head_cp16(dst, src + p * 16);
+                if (X3) head_cp16(dst + alo_off, src_lo + p * 16);
+            } else {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                if (X3) *reinterpret_cast<uint4*>(dst + alo_off) = make_uint4(0, 0, 0, 0);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -883,14 +911,20 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
             asm volatile("cp.async.wait_group %0;" ::"n"(HEAD_STAGES - 2) : "memory");  // this thread's part of chunk c
             fence_proxy_async();
             __syncthreads();
-            const int kb = (c - c0) * kpc, nk = min(kpc, nkb - kb);
+            bool g2c, lo;
+            int cc;
+            chunk_info(c, g2c, lo, cc);
+            const int kb = cc * kpc, nk = min(kpc, nkb - kb);
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 const uint64_t a0 = umma_desc(smem_u32(areg), 128u, 8u);
+                const uint64_t a0l = umma_desc(smem_u32(areg + alo_off), 128u, 8u);
                 const uint64_t b0 = umma_desc(smem_u32(stage0 + (size_t)st * HEAD_STAGE_BYTES), (uint32_t)N, 8u);
-                for (int k = 0; k < nk; ++k)
-                    umma_bf16(tmem + dcol, a0 + (uint64_t)((kb + k) * 2 * 2048 >> 4), b0 + (uint64_t)(k * blk >> 4), idesc,
-                              (kb + k) > 0 ? 1u : 0u);
+                for (int k = 0; k < nk; ++k) {
+                    const uint64_t ak = (uint64_t)((kb + k) * 2 * 2048 >> 4), bk = (uint64_t)(k * blk >> 4);
+                    umma_bf16(tmem + dcol, a0 + ak, b0 + bk, idesc, (lo || (kb + k) > 0) ? 1u : 0u);  // a_hi * w_(hi|lo)
+                    if (X3 && !lo) umma_bf16(tmem + dcol, a0l + ak, b0 + bk, idesc, 1u);                // a_lo * w_hi
+                }
                 umma_commit(bar0 + 8u * st);
                 if (c == c1 - 1) umma_commit(bar_done);
             }
@@ -912,7 +946,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         tc_fence_after();
     };
 
-    run_chunks(0, nch1, false);
+    run_chunks(0, n1, false);
     HP_T(2);
     // epilogue 1: hidden = relu(acc + b1) -> bf16 planes (A operand of the logits GEMM) + value head dot product
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -920,22 +954,32 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
     for (int c0 = hv * (HIDDEN / HEAD_NQ); c0 < (hv + 1) * (HIDDEN / HEAD_NQ); c0 += 16) {
         float v[16];
         tmem_ld16(lane_base + (uint32_t)c0, v);
-        uint32_t pk[8];
+        uint32_t pk[8], pl[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float h0 = fmaxf(v[2 * i] + s_b1[c0 + 2 * i], 0.f), h1 = fmaxf(v[2 * i + 1] + s_b1[c0 + 2 * i + 1], 0.f);
             pk[i] = pack_bf16(h0, h1);
-            vacc = fmaf(bf16_lo(pk[i]), s_wv[c0 + 2 * i], vacc);
-            vacc = fmaf(bf16_hi(pk[i]), s_wv[c0 + 2 * i + 1], vacc);
+            if (X3) {  // hi + lo halves of the hidden activations; the value head in full fp32
+                pl[i] = pack_bf16(h0 - bf16_lo(pk[i]), h1 - bf16_hi(pk[i]));
+                vacc = fmaf(h0, s_wv[c0 + 2 * i], vacc);
+                vacc = fmaf(h1, s_wv[c0 + 2 * i + 1], vacc);
+            } else {
+                vacc = fmaf(bf16_lo(pk[i]), s_wv[c0 + 2 * i], vacc);
+                vacc = fmaf(bf16_hi(pk[i]), s_wv[c0 + 2 * i + 1], vacc);
+            }
         }
         *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8) * 2048 + row_l * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(areg + (size_t)(c0 / 8 + 1) * 2048 + row_l * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (X3) {
+            *reinterpret_cast<uint4*>(areg + alo_off + (size_t)(c0 / 8) * 2048 + row_l * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            *reinterpret_cast<uint4*>(areg + alo_off + (size_t)(c0 / 8 + 1) * 2048 + row_l * 16) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+        }
     }
     s_x0[hv][row_l] = vacc;  // the value head's dot product: one part per thread
     tc_fence_before();
     __syncthreads();  // all hidden planes written (run_chunks fences them towards the async proxy before its first MMA)
     HP_T(3);
-    run_chunks(nch1, nch, true);
+    run_chunks(n1, nch, true);
     HP_T(4);
     // epilogue 2 (the operand planes and the weight stages are free now and become the [128][A] policy tile):
     //   A. thread = (row, column half): logits = acc + b2 from TMEM into the tile, maximum of the half
@@ -946,7 +990,7 @@ k_net_heads_tc(HeadParams Hp, int Bmax, const int32_t* __restrict__ count_dev, c
         float dot = 0.f;
 #pragma unroll
         for (int q = 0; q < HEAD_NQ; ++q) dot += s_x0[q][row_l];
-        value[r] = tanhf(dot + __ldg(Hp.wv + HIDDEN));
+        value[r] = tanhf(dot + __ldg((X3 ? Hp.wv_f32 : Hp.wv) + HIDDEN));
     }
     float* s_pol = reinterpret_cast<float*>(hsm);
     const int ldp = Hp.A | 1;  // odd row stride: the 32 rows of a warp fall into distinct banks
@@ -1042,9 +1086,12 @@ struct bpp_net {
     __nv_bfloat16* d_w1u = nullptr;      // FC weights in the UMMA B layout
     __nv_bfloat16* d_w2u = nullptr;
     float* d_wv32 = nullptr;
+    __nv_bfloat16* d_w1u_lo = nullptr;   // split mode: low halves of the FC weights, exact fp32 value weights (+ bias)
+    __nv_bfloat16* d_w2u_lo = nullptr;
+    float* d_wvf = nullptr;
     HeadParams Hp;
-    int heads_smem = 0;
-    bool heads_ok = false;
+    int heads_smem = 0, heads_smem3 = 0;
+    bool heads_ok = false, heads3_ok = false;
     bool tc_ok = false;
     int ctas_per_sm = 1;
     bool committed = false;
@@ -1343,17 +1390,26 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         const int kplanes = (P.flat > HIDDEN ? P.flat : HIDDEN) / 8;
         n->heads_smem = std::max(kplanes * 2048 + HEAD_STAGES * HEAD_STAGE_BYTES, 128 * ((P.A | 1) + 1) * 4);
         n->heads_ok = (P.flat % 16 == 0) && Hp.N2 <= 256 && n->heads_smem <= 220 * 1024 && getenv("BPP_NO_TC_HEADS") == nullptr;
+        n->heads_smem3 = std::max(2 * kplanes * 2048 + HEAD_STAGES * HEAD_STAGE_BYTES, 128 * ((P.A | 1) + 1) * 4);
+        n->heads3_ok = n->heads_ok && n->heads_smem3 <= 220 * 1024;
         if (n->heads_ok) {
-            if (cudaMalloc(&n->d_feat, (size_t)max_batch * P.flat * 2) != cudaSuccess ||
+            if (cudaMalloc(&n->d_feat, (size_t)max_batch * P.flat * 2 * 2) != cudaSuccess ||   // hi [+ lo]
                 cudaMalloc(&n->d_w1u, (size_t)P.flat * HIDDEN * 2) != cudaSuccess ||
                 cudaMalloc(&n->d_w2u, (size_t)HIDDEN * Hp.N2 * 2) != cudaSuccess ||
+                cudaMalloc(&n->d_w1u_lo, (size_t)P.flat * HIDDEN * 2) != cudaSuccess ||
+                cudaMalloc(&n->d_w2u_lo, (size_t)HIDDEN * Hp.N2 * 2) != cudaSuccess ||
                 cudaMalloc(&n->d_wv32, (HIDDEN + 1) * sizeof(float)) != cudaSuccess ||
-                cudaFuncSetAttribute(k_net_heads_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, n->heads_smem) != cudaSuccess) {
+                cudaMalloc(&n->d_wvf, (HIDDEN + 1) * sizeof(float)) != cudaSuccess ||
+                cudaFuncSetAttribute(k_net_heads_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->heads_smem) != cudaSuccess ||
+                (n->heads3_ok && cudaFuncSetAttribute(k_net_heads_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      n->heads_smem3) != cudaSuccess)) {
                 cudaGetLastError();
                 delete n;
                 return nerr(BPP_E_NOMEM, "cudaMalloc of the head buffers failed");
             }
             Hp.w1u = n->d_w1u; Hp.w2u = n->d_w2u; Hp.wv = n->d_wv32;
+            Hp.w1u_lo = n->d_w1u_lo; Hp.w2u_lo = n->d_w2u_lo; Hp.wv_f32 = n->d_wvf;
+            Hp.feat_lo_off = (long long)max_batch * P.flat;
             Hp.b1 = n->d_bias + P.b_hidden_off; Hp.b2 = n->d_bias + P.b_logits_off;
         }
     }
@@ -1384,6 +1440,13 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                  attr((const void*)k_net_role<0, false, 1>, n->Tr[0][0].smem_bytes) &&
                  attr((const void*)k_net_role<1, false, 1>, n->Tr[0][1].smem_bytes) &&
                  attr((const void*)k_net_role<2, false, 1>, n->Tr[0][2].smem_bytes);
+        if (ok && n->roles_ok[1])
+            ok = attr((const void*)k_net_role<0, true, 2>, n->Tr[1][0].smem_bytes) &&
+                 attr((const void*)k_net_role<1, true, 2>, n->Tr[1][1].smem_bytes) &&
+                 attr((const void*)k_net_role<2, true, 2>, n->Tr[1][2].smem_bytes) &&
+                 attr((const void*)k_net_role<0, true, 1>, n->Tr[1][0].smem_bytes) &&
+                 attr((const void*)k_net_role<1, true, 1>, n->Tr[1][1].smem_bytes) &&
+                 attr((const void*)k_net_role<2, true, 1>, n->Tr[1][2].smem_bytes);
         if (!ok) {
             cudaGetLastError();
             n->roles_ok[0] = n->roles_ok[1] = false;
@@ -1406,6 +1469,9 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     cudaFree(n->d_w1u);
     cudaFree(n->d_w2u);
     cudaFree(n->d_wv32);
+    cudaFree(n->d_w1u_lo);
+    cudaFree(n->d_w2u_lo);
+    cudaFree(n->d_wvf);
     cudaFree(n->d_bias);
     cudaFree(n->d_x1);
     cudaFree(n->d_x2);
@@ -1492,37 +1558,54 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
     // every upload below is queued on the caller's stream (a forward or a captured graph still in flight on that stream is
     // ordered before it) and the staging vectors live until the cudaStreamSynchronize at the end
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    std::vector<uint16_t> w1u, w2u;
-    std::vector<float> wv32;
+    std::vector<uint16_t> w1u, w2u, w1l, w2l;
+    std::vector<float> wv32, wvf;
+    auto split_bf16 = [](float v, uint16_t& hi, uint16_t& lo) {
+        hi = f32_to_bf16_rne(v);
+        uint32_t hb = (uint32_t)hi << 16;
+        float hf;
+        memcpy(&hf, &hb, 4);
+        lo = f32_to_bf16_rne(v - hf);
+    };
     if (n->heads_ok) {  // FC weights in the UMMA K-major B layout [k-block][k-half][n][8]
         const HeadParams& Hp = n->Hp;
         w1u.assign((size_t)P.flat * HIDDEN, 0);
         w2u.assign((size_t)HIDDEN * Hp.N2, 0);
+        w1l.assign((size_t)P.flat * HIDDEN, 0);
+        w2l.assign((size_t)HIDDEN * Hp.N2, 0);
         wv32.assign(HIDDEN + 1, 0.f);  // + the value head's bias
+        wvf.assign(HIDDEN + 1, 0.f);
         const std::vector<float>& h1 = n->host["hidden_fc.weight"];  // [256][flat]
         for (int kc = 0; kc < P.flat / 16; ++kc)
             for (int kh = 0; kh < 2; ++kh)
                 for (int o = 0; o < HIDDEN; ++o)
-                    for (int j = 0; j < 8; ++j)
-                        w1u[((((size_t)kc * 2 + kh) * HIDDEN + o) * 8) + j] =
-                            f32_to_bf16_rne(h1[(size_t)o * P.flat + kc * 16 + kh * 8 + j]);
+                    for (int j = 0; j < 8; ++j) {
+                        const size_t ui = ((((size_t)kc * 2 + kh) * HIDDEN + o) * 8) + j;
+                        split_bf16(h1[(size_t)o * P.flat + kc * 16 + kh * 8 + j], w1u[ui], w1l[ui]);
+                    }
         const std::vector<float>& l2 = n->host["logits_fc.weight"];  // [A][256]
         for (int kc = 0; kc < HIDDEN / 16; ++kc)
             for (int kh = 0; kh < 2; ++kh)
                 for (int o = 0; o < P.A; ++o)
-                    for (int j = 0; j < 8; ++j)
-                        w2u[((((size_t)kc * 2 + kh) * Hp.N2 + o) * 8) + j] =
-                            f32_to_bf16_rne(l2[(size_t)o * HIDDEN + kc * 16 + kh * 8 + j]);
+                    for (int j = 0; j < 8; ++j) {
+                        const size_t ui = ((((size_t)kc * 2 + kh) * Hp.N2 + o) * 8) + j;
+                        split_bf16(l2[(size_t)o * HIDDEN + kc * 16 + kh * 8 + j], w2u[ui], w2l[ui]);
+                    }
         const std::vector<float>& v3 = n->host["value_fc.weight"];
         for (int i = 0; i < HIDDEN; ++i) {
             uint32_t hb = (uint32_t)f32_to_bf16_rne(v3[i]) << 16;
             memcpy(&wv32[i], &hb, 4);
+            wvf[i] = v3[i];
         }
+        wvf[HIDDEN] = n->host["value_fc.bias"][0];
         // in device memory, not in the by-value kernel parameter: captured CUDA graphs replay the parameters of their
         // capture, and the weights change between iterations
         wv32[HIDDEN] = n->host["value_fc.bias"][0];
         if (cudaMemcpyAsync(n->d_w1u, w1u.data(), w1u.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
             cudaMemcpyAsync(n->d_w2u, w2u.data(), w2u.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(n->d_w1u_lo, w1l.data(), w1l.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(n->d_w2u_lo, w2l.data(), w2l.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(n->d_wvf, wvf.data(), wvf.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
             cudaMemcpyAsync(n->d_wv32, wv32.data(), wv32.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
             return nerr(BPP_E_CUDA, "head parameter upload failed");
     }
@@ -1550,7 +1633,8 @@ extern "C" int bpp_net_profile(bpp_net* n, int64_t cycles_host[8]) {
     if (cudaMemcpy(all, n->d_prof, sizeof(all), cudaMemcpyDeviceToHost) != cudaSuccess)
         return nerr(BPP_E_CUDA, "profile copy failed");
     // role kernels write one block of 8 timers each (rows 0..2): report their sum; the one-kernel trunk writes row 0
-    const bool roles = n->precision == BPP_NET_BF16 && n->roles_ok[0] && n->heads_ok;
+    const bool roles = (n->precision == BPP_NET_BF16 && n->roles_ok[0] && n->heads_ok) ||
+                       (n->precision == BPP_NET_BF16X3 && n->roles_ok[1] && n->heads3_ok);
     for (int i = 0; i < 8; ++i) cycles_host[i] = roles ? all[i] + all[8 + i] + all[16 + i] : all[i];
     return BPP_OK;
 }
@@ -1586,6 +1670,35 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// three role kernels (one per ConvSequence, each with its own group size) chained by programmatic launches
+static int launch_roles(bpp_net* n, int x3, int B, const int32_t* count_dev, const uint32_t* recs_dev, const int32_t* game_dev,
+                        const int32_t* items_wh_dev, cudaStream_t st) {
+    const uint4* xin[3] = {nullptr, n->d_x1, n->d_x2};
+    uint4* xout[3] = {n->d_x1, n->d_x2, nullptr};
+    const long long flo = (long long)n->max_batch * n->P.flat;
+    cudaError_t ce = cudaSuccess;
+    for (int sq = 0; sq < 3 && ce == cudaSuccess; ++sq) {
+        const bpptc::TcParams& R = n->Tr[x3][sq];
+        const int c = n->role_ctas[x3][sq];
+        const int gr = std::max(1, std::min((B + R.S - 1) / R.S, n->num_sms * c));
+#define ROLE_LAUNCH(SQ, X, MB)                                                                                              \
+    ce = launch_pdl(k_net_role<SQ, X, MB>, gr, bpptc::TC_THREADS, (size_t)R.smem_bytes, st, n->P, R, B, count_dev, recs_dev, \
+                    game_dev, items_wh_dev, xin[SQ], xout[SQ], n->d_feat, flo, n->d_prof)
+#define ROLE_PICK(SQ)                                                     \
+    do {                                                                  \
+        if (x3) { if (c == 2) ROLE_LAUNCH(SQ, true, 2); else ROLE_LAUNCH(SQ, true, 1); }    \
+        else { if (c == 2) ROLE_LAUNCH(SQ, false, 2); else ROLE_LAUNCH(SQ, false, 1); }     \
+    } while (0)
+        if (sq == 0) ROLE_PICK(0);
+        else if (sq == 1) ROLE_PICK(1);
+        else ROLE_PICK(2);
+#undef ROLE_PICK
+#undef ROLE_LAUNCH
+    }
+    if (ce != cudaSuccess) return nerr(BPP_E_CUDA, std::string("role kernel launch failed: ") + cudaGetErrorString(ce));
+    return BPP_OK;
+}
+
 extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, const uint32_t* recs_dev,
                                const int32_t* game_dev, const int32_t* items_wh_dev, float* policy_out_dev,
                                float* value_out_dev, void* stream) {
@@ -1602,22 +1715,8 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
         if (fo && n->roles_ok[0]) {
-            // three role kernels (one per ConvSequence, each with its own group size) chained by programmatic launches,
-            // then the FC heads
-            const uint4* xin[3] = {nullptr, n->d_x1, n->d_x2};
-            uint4* xout[3] = {n->d_x1, n->d_x2, nullptr};
-            for (int sq = 0; sq < 3; ++sq) {
-                const bpptc::TcParams& R = n->Tr[0][sq];
-                const int c = n->role_ctas[0][sq];
-                const int gr = std::max(1, std::min((B + R.S - 1) / R.S, n->num_sms * c));
-#define ROLE_LAUNCH(SQ, MB)                                                                                            \
-    launch_pdl(k_net_role<SQ, false, MB>, gr, bpptc::TC_THREADS, (size_t)R.smem_bytes, st, n->P, R, B, count_dev, recs_dev, \
-               game_dev, items_wh_dev, xin[SQ], xout[SQ], fo, n->d_prof)
-                if (sq == 0) { if (c == 2) ROLE_LAUNCH(0, 2); else ROLE_LAUNCH(0, 1); }
-                else if (sq == 1) { if (c == 2) ROLE_LAUNCH(1, 2); else ROLE_LAUNCH(1, 1); }
-                else { if (c == 2) ROLE_LAUNCH(2, 2); else ROLE_LAUNCH(2, 1); }
-#undef ROLE_LAUNCH
-            }
+            int rc = launch_roles(n, 0, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
+            if (rc) return rc;
         } else if (fo && n->ctas_per_sm == 2)
             launch_pdl(k_net_forward_tc<8, false, true, 2>, g2, bpptc::TC_THREADS, (size_t)n->T.smem_bytes, st, n->P, n->T, B,
                        count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
@@ -1628,8 +1727,13 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
             k_net_forward_tc<8, false><<<g2, bpptc::TC_THREADS, n->T.smem_bytes, st>>>(
                 n->P, n->T, B, count_dev, recs_dev, game_dev, items_wh_dev, policy_out_dev, value_out_dev, n->d_prof, fo);
         if (fo)
-            launch_pdl(k_net_heads_tc, (B + 127) / 128, HEAD_THREADS, (size_t)n->heads_smem, st, n->Hp, B, count_dev,
+            launch_pdl(k_net_heads_tc<false>, (B + 127) / 128, HEAD_THREADS, (size_t)n->heads_smem, st, n->Hp, B, count_dev,
                        (const __nv_bfloat16*)n->d_feat, policy_out_dev, value_out_dev);
+    } else if (n->precision == BPP_NET_BF16X3 && n->roles_ok[1] && n->heads3_ok) {
+        int rc = launch_roles(n, 1, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
+        if (rc) return rc;
+        launch_pdl(k_net_heads_tc<true>, (B + 127) / 128, HEAD_THREADS, (size_t)n->heads_smem3, st, n->Hp, B, count_dev,
+                   (const __nv_bfloat16*)n->d_feat, policy_out_dev, value_out_dev);
     } else if (n->precision == BPP_NET_BF16X3 && n->tc3_ok) {
         const int groups = (B + n->T3.S - 1) / n->T3.S;
         const int g2 = groups < n->num_sms ? groups : n->num_sms;

@@ -225,7 +225,8 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
                                            const unsigned char* in_planes, int kind, unsigned char* out0,
                                            unsigned char* raw, WPre& pre, const __nv_bfloat16* next_wsrc, int next_n16,
                                            const float* next_bias, int next_cout, const __nv_bfloat16* wsrc_lo = nullptr,
-                                           uint32_t in_lo_off = 0, uint32_t out_lo_off = 0, uint32_t raw_lo_off = 0) {
+                                           uint32_t in_lo_off = 0, uint32_t out_lo_off = 0, uint32_t raw_lo_off = 0,
+                                           bool a_lo_zero = false) {
     const int tid = threadIdx.x;
     long long tp = clock64();
     const int wbytes = 9 * cin16 * 2 * cout * 16;
@@ -287,14 +288,14 @@ __device__ __forceinline__ void conv_layer(const TcParams& T, Ctx& cx, const Lev
                 const uint32_t bt = blo0 + (uint32_t)tap * b_tap;
                 umma_bf16_lh(d, at, ahi, bt, bhi, idesc, tap > 0 ? 1u : 0u);
                 if (X3) {
-                    umma_bf16_lh(d, at, ahi, bt + w_lo16, bhi, idesc, 1u);          // a_hi * w_lo
-                    umma_bf16_lh(d, at + a_lo16, ahi, bt, bhi, idesc, 1u);          // a_lo * w_hi
+                    umma_bf16_lh(d, at, ahi, bt + w_lo16, bhi, idesc, 1u);                          // a_hi * w_lo
+                    if (!a_lo_zero) umma_bf16_lh(d, at + a_lo16, ahi, bt, bhi, idesc, 1u);          // a_lo * w_hi
                 }
                 if (cin16 == 2) {
                     umma_bf16_lh(d, at + a_kc, ahi, bt + b_blk, bhi, idesc, 1u);
                     if (X3) {
                         umma_bf16_lh(d, at + a_kc, ahi, bt + b_blk + w_lo16, bhi, idesc, 1u);
-                        umma_bf16_lh(d, at + a_kc + a_lo16, ahi, bt + b_blk, bhi, idesc, 1u);
+                        if (!a_lo_zero) umma_bf16_lh(d, at + a_kc + a_lo16, ahi, bt + b_blk, bhi, idesc, 1u);
                     }
                 }
             }

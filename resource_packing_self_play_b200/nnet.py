@@ -287,7 +287,7 @@ class NNetWrapper:
                 nxt = ops.next_state(recs, items, act)
                 go = (depth > k) & (cnt > 0)
                 still = ops.valid_moves(nxt, items).any(dim=1)   # never calibrate on a terminal state
-                recs = torch.where((go & still)[:, None], nxt, recs)
+                recs = torch.where((go & still.bool())[:, None], nxt, recs)
             cal = self._cal_states = (recs.contiguous(), items.contiguous())
         return cal
 
