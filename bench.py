@@ -63,7 +63,9 @@ def workload(first_episode, count, Wb=W, Hb=H):
     seeds = 1000 + idx
     # height per batch of 20 episodes (CoachBPP.py:117-119 draws it once per iteration of numEps = 20 episodes)
     batch = idx // 20
-    heights = np.array([np.random.RandomState(77000 + int(b)).randint(2, Hb + 1) for b in batch], dtype=np.int32)
+    ub = np.unique(batch)
+    hb = {int(b): np.random.RandomState(77000 + int(b)).randint(2, Hb + 1) for b in ub}
+    heights = np.array([hb[int(b)] for b in batch], dtype=np.int32)
     return seeds, heights, (Wb * heights).astype(np.int32)
 
 
@@ -535,23 +537,29 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
     gen = ItemsGenerator(Wb, Hb, N)
     n_tot = warmup + steps
 
+    E = args.stream_mult * G   # episodes per step, streamed through the G resident games
+
     def instances(k):
-        seeds, hts, areas = workload(((k * cx.world) + cx.rank) * G, G, Wb, Hb)
+        seeds, hts, areas = workload(((k * cx.world) + cx.rank) * E, E, Wb, Hb)
         return gen.items_batch_device(seeds, hts, device=cx.local).cpu().numpy(), areas
     inst = [instances(k) for k in range(2 * n_tot)]
     dev_inst = [(torch.from_numpy(i).to(cx.dev), torch.from_numpy(a).to(cx.dev)) for i, a in inst[:n_tot]]
-    roots = torch.empty((N, G, 32), dtype=torch.int32, device=cx.dev)
-    counts = torch.empty((N, G, Wb * N), dtype=torch.int32, device=cx.dev)
-    actions = torch.empty((N, G), dtype=torch.int32, device=cx.dev)
-    nan_bl = torch.full((G,), float("nan"), dtype=torch.float64, device=cx.dev)
+    roots = torch.empty((N, E, 32), dtype=torch.int32, device=cx.dev)
+    counts = torch.empty((N, E, Wb * N), dtype=torch.int32, device=cx.dev)
+    actions = torch.empty((N, E), dtype=torch.int32, device=cx.dev)
+    r_out = torch.empty(E, dtype=torch.int32, device=cx.dev)
+    score_out = torch.empty(E, dtype=torch.float64, device=cx.dev)
+    moves_out = torch.zeros(E, dtype=torch.int32, device=cx.dev)
+    nan_bl = torch.full((E,), float("nan"), dtype=torch.float64, device=cx.dev)
     nsteps = C.c_int32(0)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
     def step(k):
         items, area = dev_inst[k]
-        eng.reset(items, area, nan_bl)
-        _lib.call("bpp_engine_play_net", eng._h, net.dnet._h, _lib.CHOOSE_SAMPLE, C.c_uint64(7 + k),
-                  C.c_void_p(counts.data_ptr()), C.c_void_p(actions.data_ptr()), C.c_void_p(roots.data_ptr()),
-                  C.byref(nsteps), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        moves_out.zero_()
+        _lib.call("bpp_engine_play_net_stream", eng._h, net.dnet._h, _lib.CHOOSE_SAMPLE, C.c_uint64(7 + k), E, vp(items),
+                  vp(area), vp(nan_bl), C.c_void_p(0), vp(counts), vp(actions), vp(roots), vp(r_out), vp(score_out),
+                  vp(moves_out), C.byref(nsteps), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return int(nsteps.value)
 
     for k in range(warmup):
@@ -568,19 +576,19 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
     ms, _, clocks, lock_steps = cx.timed(lambda k: step(warmup + k), steps)
     eng.check()
     st = eng.stats(reset=True)
-    assert bool((eng.status()["done"] == 1).all()), "some games did not finish their episode"
+    assert bool((moves_out > 0).all()), "some episodes did not finish"
     e2e = None
     if with_e2e:
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
         h_inst = [(pin(i), pin(a)) for i, a in inst[n_tot:]]
-        out = {"roots": pin(np.empty((N, G, 32), dtype=np.uint32)), "counts": pin(np.empty((N, G, Wb * N), dtype=np.int32)),
-               "actions": pin(np.empty((N, G), dtype=np.int32)), "r": pin(np.empty(G, dtype=np.int32)),
-               "score": pin(np.empty(G, dtype=np.float64)), "moves": pin(np.empty(G, dtype=np.int32))}
-        h_bl = pin(np.full(G, np.nan))
+        out = {"roots": pin(np.empty((N, E, 32), dtype=np.uint32)), "counts": pin(np.empty((N, E, Wb * N), dtype=np.int32)),
+               "actions": pin(np.empty((N, E), dtype=np.int32)), "r": pin(np.empty(E, dtype=np.int32)),
+               "score": pin(np.empty(E, dtype=np.float64)), "moves": pin(np.empty(E, dtype=np.int32))}
+        h_bl = pin(np.full(E, np.nan))
 
         def step_e2e(k):
-            eng.play_net_host(net.dnet, h_inst[k][0], h_inst[k][1], h_bl, choose_mode=_lib.CHOOSE_SAMPLE, seed=99 + k,
-                              out=out)
+            eng.play_net_stream_host(net.dnet, h_inst[k][0], h_inst[k][1], h_bl, choose_mode=_lib.CHOOSE_SAMPLE,
+                                     seed=99 + k, out=out)
             return int(out["moves"].sum())
         for k in range(min(warmup, 2)):
             step_e2e(k)
@@ -588,11 +596,11 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
         d_ms, w_ms, _, _ = cx.timed(lambda k: step_e2e(warmup + k), steps)
         st2 = eng.stats(reset=True)
         e2e = {"ms": max(d_ms, w_ms), "sims": st2["sims"],
-               "h2d": int(inst[0][0].nbytes + inst[0][1].nbytes + 8 * G),
+               "h2d": int(inst[0][0].nbytes + inst[0][1].nbytes + 8 * E),
                "d2h": int(sum(v.nbytes for k2, v in out.items() if k2 != "steps"))}
     (ms, e2e_ms), (sims, sims2, exps, launches, episodes) = cx.reduce(
         [ms, e2e["ms"] if e2e else 0.0],
-        [st["sims"], e2e["sims"] if e2e else 0, st["expansions"], st["launches"] + 2 * sum(lock_steps), steps * G])
+        [st["sims"], e2e["sims"] if e2e else 0, st["expansions"], st["launches"] + 2 * sum(lock_steps), steps * E])
     rec = None
     if cx.rank == 0:
         peak = float(cx.peaks.get("bf16_tflops_sustained", 1400.0))
@@ -604,8 +612,9 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
                "dtype": f"{mode} (net) / f64 (tree)", "precision_mode": mode,
                "precision_requested": precision, "calibration": net.calibration,
                "config": {"workload": f"{Wb}x{Hb} bin, 10 items, numMCTSSims={args.sims}, real policy/value net as leaf "
-                                      f"evaluator, {G} games per GPU, whole self-play episodes, asynchronous per game",
-                          "weights": weights, "games_per_gpu": G},
+                                      f"evaluator, {G} resident games per GPU, {E} whole self-play episodes per step "
+                                      "streamed through them (a game whose episode ends takes the next instance)",
+                          "weights": weights, "games_per_gpu": G, "episodes_per_step": E},
                "lockstep_steps_per_batch": float(np.mean(lock_steps)),
                "leaf_batch_fill": exps / max(1.0, cx.world * sum(lock_steps) * G),
                "gpu_launches": int(launches),
@@ -763,6 +772,8 @@ def main():
     ap.add_argument("--workload", default="all",
                     help="comma list of: stub (headline), real15, real20, iteration, arena, checksum; all = every one")
     ap.add_argument("--precision", default="auto", help="precision mode of a single real15/real20 run")
+    ap.add_argument("--stream-mult", type=int, default=4,
+                    help="real-net workloads: episodes per step = stream-mult x games, streamed through the resident games")
     ap.add_argument("--iteration-games", type=int, default=8192)
     ap.add_argument("--arena-seeds", type=int, default=8192)
     args = ap.parse_args()

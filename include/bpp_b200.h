@@ -252,6 +252,24 @@ int bpp_engine_progress_async(bpp_engine *e, int32_t *counts_host4, void *stream
  * action -1, root 0.  Synchronises the stream.  steps_run_host (may be NULL) = lockstep steps queued. */
 int bpp_engine_play_net(bpp_engine *e, bpp_net *net, int choose_mode, uint64_t seed, int32_t *counts_out_dev,
                         int32_t *actions_out_dev, uint32_t *roots_out_dev, int32_t *steps_run_host, void *stream);
+/* Episode STREAM: num_episodes >= 1 instances played through the G resident games.  Games 0..G-1 start with episodes
+ * 0..G-1; a game whose episode ends latches the outcome and takes the next instance of the queue inside the same search
+ * launch, so the device always holds G running games until the queue is empty (no batch waits for its slowest episode).
+ * Inputs are indexed by episode: items_wh int32 [E][N][2], total_area int32 [E], bl float64 [E], tie int8 [E] or NULL.
+ * Outputs are indexed by episode too: counts int32 [N][E][A], actions int32 [N][E], roots uint32 [N][E][32], r int32 [E],
+ * score float64 [E], moves int32 [E]; any may be NULL.  The action stream is keyed by (seed, episode, move), so results do
+ * not depend on which game slot an episode lands in; with num_episodes == G they equal bpp_engine_reset +
+ * bpp_engine_play_net.  No bpp_engine_reset is needed before the call. */
+int bpp_engine_play_net_stream(bpp_engine *e, bpp_net *net, int choose_mode, uint64_t seed, int num_episodes,
+                               const int32_t *items_wh_dev, const int32_t *total_area_dev, const double *bl_dev,
+                               const int8_t *tie_dev, int32_t *counts_out_dev, int32_t *actions_out_dev,
+                               uint32_t *roots_out_dev, int32_t *r_out_dev, double *score_out_dev, int32_t *moves_out_dev,
+                               int32_t *steps_run_host, void *stream);
+int bpp_engine_play_net_stream_host(bpp_engine *e, bpp_net *net, int choose_mode, uint64_t seed, int num_episodes,
+                                    const int32_t *items_wh_host, const int32_t *total_area_host, const double *bl_host,
+                                    const int8_t *tie_host, uint32_t *roots_out_host, int32_t *counts_out_host,
+                                    int32_t *actions_out_host, int32_t *r_out_host, double *score_out_host,
+                                    int32_t *moves_out_host, int32_t *steps_run_host, void *stream);
 /* Accounting pass for bench.py: with on != 0 bpp_engine_play_net records CUDA events around every evaluator call and every
  * expand_select call (slower: use it for kernel shares, not for throughput) and accumulates their durations;
  * bpp_engine_profile returns {evaluator ms, expand+select ms, lockstep steps timed, 0} since the last set_profile. */

@@ -74,6 +74,10 @@ SIGNATURES = {
     "bpp_engine_play_net": [_vp, _vp, _i32, _u64, _vp, _vp, _vp, C.POINTER(_i32), _vp],
     "bpp_engine_play_net_host": [_vp, _vp, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  C.POINTER(_i32), _vp],
+    "bpp_engine_play_net_stream": [_vp, _vp, _i32, _u64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   C.POINTER(_i32), _vp],
+    "bpp_engine_play_net_stream_host": [_vp, _vp, _i32, _u64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        C.POINTER(_i32), _vp],
     "bpp_engine_set_profile": [_vp, _i32],
     "bpp_engine_profile": [_vp, C.POINTER(C.c_double)],
     "bpp_engine_stats": [_vp, C.POINTER(_u64), _i32, _vp],

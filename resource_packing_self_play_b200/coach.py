@@ -93,8 +93,10 @@ class CoachBPP:
                 return [(x[0], x[1], r) for x in trainExamples]
 
     # ------------------------------------------------------------------------------------------------------------------
+    RESIDENT_GAMES = 4096  # default number of games resident on the device; larger batches stream through them
+
     def executeEpisodesBatched(self, items_batch, total_areas, greedy=False, seed=None, expand=True, on_device=False,
-                               per_move=False, record=True):
+                               per_move=False, record=True, resident=None):
         """G episodes at once on the device with the batched leaf evaluator.
 
         items_batch: (G, N, 2) int (w, h); total_areas: (G,) int.  All games share this call's `self.rewards_list`
@@ -110,7 +112,10 @@ class CoachBPP:
             items_dev = items_batch.to(torch.int32)
             items_batch = items_dev.cpu().numpy()
         items_batch = np.asarray(items_batch, dtype=np.int32)
-        G = items_batch.shape[0]
+        E = items_batch.shape[0]
+        # games resident on the device; a larger batch is STREAMED through them (a game whose episode ends takes the next
+        # instance inside the search kernel): memory is bounded by `resident`, results do not depend on it
+        G = E if per_move else min(E, int(resident or getattr(self.args, "residentGames", 0) or self.RESIDENT_GAMES))
         g = self.game
         N, A = g.num_items, g.getActionSize()
         if seed is None:
@@ -147,6 +152,7 @@ class CoachBPP:
                                           mode=mode, seed=seed, record=record)
                     roots, counts, acts = ep["roots"], ep["counts"], ep["actions"]
                 eng.check()
+                st = eng.status() if per_move else ep
                 break
             except _lib.BppError as err:
                 # a game outgrew its edge pool (sized from measured episodes, not from the worst case): re-create the
@@ -154,17 +160,16 @@ class CoachBPP:
                 if err.code != -4 or eng.edge_cap >= eng.edge_cap_worst:
                     raise
                 edge_cap = min(eng.edge_cap_worst, 2 * eng.edge_cap)
-        st = eng.status()
         if on_device and not expand:
             return {"roots": roots, "counts": counts, "actions": acts, "moves": st["moves"], "r": st["r"],
                     "items": items_dev if items_dev is not None else torch.from_numpy(items_batch).to(eng.device)}, \
                 st["score"], st["r"]
-        st = {k: v.cpu().numpy() for k, v in st.items()}
+        st = {k: v.cpu().numpy() for k, v in st.items() if k in ("moves", "r", "score")}
         roots = roots.cpu().numpy().view(np.uint32)      # (N, G, 32)
         counts = counts.cpu().numpy()                      # (N, G, A)
         acts = acts.cpu().numpy()                          # (N, G)
         moves, r, score = st["moves"], st["r"], st["score"]
-        assert (st["done"] == 1).all()
+        assert (moves > 0).all()
         if not expand:
             return {"roots": roots, "counts": counts, "actions": acts, "moves": moves, "r": r,
                     "items": items_batch}, score, r

@@ -102,6 +102,20 @@ struct Params {
     int32_t* ep_counts;         // [N][G][A] or nullptr
     int32_t* ep_actions;        // [N][G] or nullptr
     uint32_t* ep_roots;         // [N][G][32] root record each move was searched from, or nullptr
+    // episode stream (bpp_engine_play_net_stream): q_total >= 1 episodes through the G resident games; a game whose
+    // episode ends takes the next instance of the queue in the same launch.  The per-move outputs above are then indexed
+    // [move][episode] (row length q_total) and the outcomes go to the epq_* arrays.
+    int q_total;                // 0 = no stream (game g plays episode g only)
+    int* q_next;                // [1] next episode to hand out
+    const int32_t* q_items;     // [E][N][2]
+    const int32_t* q_area;      // [E]
+    const double* q_bl;         // [E]
+    const int8_t* q_tie;        // [E] or nullptr
+    int* slot_ep;               // [G] episode the game is playing
+    int32_t* items_i32;         // [G][N][2] item list of the resident games, read by the evaluator
+    int32_t* epq_r;             // [E] outcomes per episode (any may be nullptr)
+    double* epq_score;
+    int32_t* epq_moves;
 };
 
 struct __align__(16) WarpSmem {
@@ -416,6 +430,61 @@ k_expand_backup(Params P, const void* policy, int policy_f64, const void* value,
     flush_stats(P, st, lane);
 }
 
+// Put episode `ep` of the queue into game slot g (warp-collective): a fresh MCTS object (CoachBPP.py:124) plus
+// getInitBoard / getInitItems (BinPackingGame.py:24-51) - the per-game part of k_reset - and an empty hash table.
+__device__ __forceinline__ void load_episode(const Params& P, int g, int ep, int lane) {
+    const int N = P.geom.N;
+    int w = 0, h = 0;
+    if (lane < N) {
+        w = P.q_items[((size_t)ep * N + lane) * 2 + 0];
+        h = P.q_items[((size_t)ep * N + lane) * 2 + 1];
+        P.items_i32[((size_t)g * N + lane) * 2 + 0] = w;
+        P.items_i32[((size_t)g * N + lane) * 2 + 1] = h;
+    }
+    if (lane < BPP_MAX_ITEMS) {
+        P.item_w[g * BPP_MAX_ITEMS + lane] = (uint8_t)w;
+        P.item_h[g * BPP_MAX_ITEMS + lane] = (uint8_t)h;
+    }
+    const int max_h = (int)__reduce_max_sync(FULL, (unsigned)h);
+    uint32_t* table = P.table + (size_t)g * (P.table_mask + 1u);
+    for (unsigned i = lane; i <= P.table_mask; i += 32) table[i] = 0u;
+    P.root_rec[(size_t)g * REC_WORDS + lane] =
+        lane == REC_REM ? ((N >= 32) ? 0xffffffffu : ((1u << N) - 1u)) : 0u;
+    if (lane == 0) {
+        const int area = P.q_area[ep];
+        const int cdiv = (area + P.geom.W - 1) / P.geom.W;
+        P.total_area[g] = area;
+        P.numer[g] = cdiv > max_h ? cdiv : max_h;
+        P.bl[g] = P.q_bl[ep];
+        P.tie[g] = P.q_tie ? P.q_tie[ep] : (int8_t)1;
+        P.root_node[g] = -1;
+        P.n_nodes[g] = 0;
+        P.n_units[g] = 0;
+        P.sims_done[g] = 0;
+        P.moves_done[g] = 0;
+        P.status[g] = 0;
+        P.ep_r[g] = 0;
+        P.ep_score[g] = 0.0;
+        P.pend_depth[g] = -1;
+        P.slot_ep[g] = ep;
+    }
+    __syncwarp();
+}
+
+// first G episodes of the stream into the G games; games beyond the queue length stay idle
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_stream_begin(Params P) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_CTA + wid;
+    if (g >= P.G) return;
+    if (g < P.q_total) {
+        load_episode(P, g, g, lane);
+    } else if (lane == 0) {
+        P.status[g] = 1;
+        P.pend_depth[g] = -1;
+        P.slot_ep[g] = -1;
+    }
+}
+
 __global__ void k_reset(Params P, const int32_t* items_wh, const int32_t* total_area, const double* bl,
                         const int8_t* tie) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -449,6 +518,7 @@ __global__ void k_reset(Params P, const int32_t* items_wh, const int32_t* total_
     P.ep_r[g] = 0;
     P.ep_score[g] = 0.0;
     P.pend_depth[g] = -1;
+    P.slot_ep[g] = g;
 }
 
 __global__ void k_set_roots(Params P, const uint32_t* roots) {
@@ -512,7 +582,8 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 // action choice from the root visit counts of one game (executed by ONE thread; <= A edges).  The random stream is a
 // pure function of (seed, game, move number), so the per-move kernels and the whole-episode kernel draw the same.
 __device__ __forceinline__ int choose_action(const Params& P, int g, int root, int move_no, int mode,
-                                             unsigned long long seed) {
+                                             unsigned long long seed, int key = -1) {
+    if (key < 0) key = g;  // stream key: the episode (== the game index unless episodes are streamed through the games)
     int act = -1;
     if (root < 0) return act;
     const uint32_t* nodes = P.nodes + (size_t)g * P.node_cap * REC_WORDS;
@@ -521,7 +592,7 @@ __device__ __forceinline__ int choose_action(const Params& P, int g, int root, i
     const int nv = (int)(meta & 0xffffu), nvp = (nv + 3) & ~3;
     EdgeBlock eb(P.edges + (size_t)g * (size_t)P.edge_cap + nodes[(size_t)root * REC_WORDS + REC_OFF], nvp);
     const unsigned long long rnd =
-        splitmix64(seed ^ splitmix64(((unsigned long long)g << 20) ^ (unsigned long long)move_no));
+        splitmix64(seed ^ splitmix64(((unsigned long long)key << 20) ^ (unsigned long long)move_no));
     if (mode == BPP_CHOOSE_SAMPLE) {  // a ~ counts / sum(counts), CoachBPP.py:86-87
         long long tot = 0;
         for (int e = 0; e < nv; ++e) tot += eb.NC[e].x;
@@ -685,18 +756,31 @@ k_expand_search(Params P, const void* policy, int policy_f64, const void* value,
             // game waits for the slowest game of a move and the host never synchronises per move
             const int m = P.moves_done[g];
             uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
-            const size_t mg = (size_t)m * P.G + g;
+            const int ep = P.q_total ? P.slot_ep[g] : g;
+            const size_t mg = (size_t)m * (P.q_total ? P.q_total : P.G) + ep;
             if (P.ep_roots) P.ep_roots[mg * REC_WORDS + lane] = rec;
             if (P.ep_counts) root_counts_warp(P, g, gm.root_node, lane, P.ep_counts + mg * P.geom.A);
-            int a = lane == 0 ? choose_action(P, g, gm.root_node, m, P.auto_mode, P.auto_seed) : 0;
+            int a = lane == 0 ? choose_action(P, g, gm.root_node, m, P.auto_mode, P.auto_seed, ep) : 0;
             a = __shfl_sync(FULL, a, 0);
             if (P.ep_actions && lane == 0) P.ep_actions[mg] = a;
             const int status = advance_game(P, gm, sm, lane, a, rec, st);
             done = 0;
-            if (status != 0) {
-                running = false;
-                break;
+            if (status == 0) continue;
+            running = false;
+            if (status != 1 || !P.q_total) break;
+            // the episode has ended: latch its outcome and take the next instance of the queue into this game
+            int nxt = 0;
+            if (lane == 0) {
+                if (P.epq_r) P.epq_r[ep] = P.ep_r[g];
+                if (P.epq_score) P.epq_score[ep] = P.ep_score[g];
+                if (P.epq_moves) P.epq_moves[ep] = P.moves_done[g];
+                nxt = atomicAdd(P.q_next, 1);
             }
+            nxt = __shfl_sync(FULL, nxt, 0);
+            if (nxt >= P.q_total) break;
+            load_episode(P, g, nxt, lane);
+            load_ctx(P, g, lane, gm, sm);
+            running = true;
         }
     }
     if (lane == 0) {
@@ -1027,6 +1111,17 @@ struct bpp_engine {
     cudaEvent_t ev_prog[2] = {nullptr, nullptr};
     const int32_t* items_ref = nullptr;  // int32 [G][N][2] item list of the current episodes (evaluator input)
     int num_sms = 148;
+    // staging of bpp_engine_play_net_stream_host (device; element counts)
+    int32_t* q_items = nullptr; size_t q_items_n = 0;
+    int32_t* q_area = nullptr; size_t q_area_n = 0;
+    double* q_bl = nullptr; size_t q_bl_n = 0;
+    int8_t* q_tie = nullptr; size_t q_tie_n = 0;
+    int32_t* q_r = nullptr; size_t q_r_n = 0;
+    double* q_score = nullptr; size_t q_score_n = 0;
+    int32_t* q_moves = nullptr; size_t q_moves_n = 0;
+    int32_t* q_counts = nullptr; size_t q_counts_n = 0;
+    int32_t* q_actions = nullptr; size_t q_actions_n = 0;
+    uint32_t* q_roots = nullptr; size_t q_roots_n = 0;
     bool prof_on = false;              // bpp_engine_set_profile: CUDA events around every call of play_net's steps
     std::vector<cudaEvent_t> prof_ev;
     double prof_ms[4] = {0, 0, 0, 0};  // evaluator ms, expand+select ms, steps timed, -
@@ -1130,8 +1225,11 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     ALLOC(P.leaf_game, G);
     ALLOC(P.leaf_rec, G * REC_WORDS);
     ALLOC(P.stats, 8);
+    ALLOC(P.slot_ep, G);
+    ALLOC(P.q_next, 1);
     ALLOC(e->d_actions, G);
     ALLOC(e->d_items, G * (size_t)ge.N * 2);
+    P.items_i32 = e->d_items;
     ALLOC(e->d_area, G);
     ALLOC(e->d_bl, G);
     ALLOC(e->d_tie, G);
@@ -1571,26 +1669,24 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
                                const int32_t* game_dev, const int32_t* items_wh_dev, float* policy_out_dev,
                                float* value_out_dev, void* stream);
 
-extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t seed, int32_t* counts_out_dev,
-                                   int32_t* actions_out_dev, uint32_t* roots_out_dev, int32_t* steps_run_host,
-                                   void* stream) {
-    if (!e || !net) return set_err(BPP_E_INVALID, "null argument");
-    if (e->leaf_parked) return set_err(BPP_E_STATE, "leaves are parked; call bpp_engine_expand_backup first");
-    if (choose_mode < 0 || choose_mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", choose_mode);
-    if (!e->items_ref) return set_err(BPP_E_STATE, "bpp_engine_play_net before bpp_engine_reset");
+// The lockstep loop of bpp_engine_play_net / bpp_engine_play_net_stream: games reset (or the stream begun), outputs with
+// `rows` entries per move (G games, or E episodes of a stream).
+static int run_lockstep(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t seed, int32_t* counts_out_dev,
+                        int32_t* actions_out_dev, uint32_t* roots_out_dev, size_t rows, int32_t* steps_run_host,
+                        void* stream) {
     Params& P = e->P;
     const size_t G = (size_t)P.G, A = (size_t)P.geom.A, N = (size_t)P.geom.N;
     int rc;
     if (!e->d_pol && ((rc = dev_alloc(e, &e->d_pol, G * A)) || (rc = dev_alloc(e, &e->d_val, G)))) return rc;
     // rows of moves a game does not play: counts 0, action -1, root record 0
-    if (counts_out_dev) CUDA_TRY(cudaMemsetAsync(counts_out_dev, 0, N * G * A * sizeof(int32_t), S(stream)));
-    if (actions_out_dev) CUDA_TRY(cudaMemsetAsync(actions_out_dev, 0xff, N * G * sizeof(int32_t), S(stream)));
-    if (roots_out_dev) CUDA_TRY(cudaMemsetAsync(roots_out_dev, 0, N * G * REC_WORDS * sizeof(uint32_t), S(stream)));
+    if (counts_out_dev) CUDA_TRY(cudaMemsetAsync(counts_out_dev, 0, N * rows * A * sizeof(int32_t), S(stream)));
+    if (actions_out_dev) CUDA_TRY(cudaMemsetAsync(actions_out_dev, 0xff, N * rows * sizeof(int32_t), S(stream)));
+    if (roots_out_dev) CUDA_TRY(cudaMemsetAsync(roots_out_dev, 0, N * rows * REC_WORDS * sizeof(uint32_t), S(stream)));
     // Work per game and launch.  A launch lasts as long as its slowest warp, and a game whose simulations end on terminal
     // states parks no leaf, so its work per launch is bounded - in EDGES WALKED (a late-game simulation is 1-2 edges deep,
     // an early one 5-10), not in simulations.  The bound adapts to the leaf supply: with a sharp trained policy only ~2 %
-    // of the simulations need the evaluator, and the bound grows until about half of the running games park a leaf per
-    // step; with a flat prior it stays small so that parked games do not wait for long descents of the others.
+    // of the simulations need the evaluator, and the bound grows until most of the running games park a leaf per step;
+    // with a flat prior it stays small so that parked games do not wait for long descents of the others.
     const int keep_cap = P.select_cap;
     const char* bud_env = getenv("BPP_EDGE_BUDGET");
     const bool adapt = bud_env == nullptr;
@@ -1646,8 +1742,8 @@ extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode,
             if (trace) fprintf(stderr, "play_net chunk %d: leaves %d capped %d running %d budget %d\n", k - 1, pp[0], pp[1], pp[2], budget);
             if (ce == cudaSuccess && pp[0] == 0 && pp[2] == 0) break;  // nothing parked, nobody playing
             if (adapt && pp[2] > 0) {
-                if (pp[0] * 3 < pp[2] && budget < 8192) budget *= 2;          // < 1/3 of the running games parked a leaf
-                else if (pp[0] * 4 > pp[2] * 3 && budget > 8) budget /= 2;    // > 3/4 did
+                if (pp[0] * 5 < pp[2] * 4 && budget < 8192) budget *= 2;         // < 80 % of the running games parked a leaf
+                else if (pp[0] * 20 > pp[2] * 19 && budget > 8) budget /= 2;     // > 95 % did
                 P.edge_budget = budget;
             }
         }
@@ -1655,7 +1751,7 @@ extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode,
             restore();
             return set_err(BPP_E_CUDA, "bpp_engine_play_net: %s", cudaGetErrorString(ce));
         }
-        if (steps > 400 * P.num_sims * (int)N + 4096) {  // cannot happen: every step with a running game makes progress
+        if ((double)steps > (400.0 * P.num_sims * (double)N + 4096.0) * (double)((rows + G - 1) / G)) {  // cannot happen
             restore();
             return set_err(BPP_E_STATE, "bpp_engine_play_net made no progress");
         }
@@ -1675,6 +1771,54 @@ extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode,
         }
     }
     return BPP_OK;
+}
+
+extern "C" int bpp_engine_play_net(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t seed, int32_t* counts_out_dev,
+                                   int32_t* actions_out_dev, uint32_t* roots_out_dev, int32_t* steps_run_host,
+                                   void* stream) {
+    if (!e || !net) return set_err(BPP_E_INVALID, "null argument");
+    if (e->leaf_parked) return set_err(BPP_E_STATE, "leaves are parked; call bpp_engine_expand_backup first");
+    if (choose_mode < 0 || choose_mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", choose_mode);
+    if (!e->items_ref) return set_err(BPP_E_STATE, "bpp_engine_play_net before bpp_engine_reset");
+    e->P.q_total = 0;
+    return run_lockstep(e, net, choose_mode, seed, counts_out_dev, actions_out_dev, roots_out_dev, (size_t)e->P.G,
+                        steps_run_host, stream);
+}
+
+extern "C" int bpp_engine_play_net_stream(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t seed, int num_episodes,
+                                          const int32_t* items_wh_dev, const int32_t* total_area_dev, const double* bl_dev,
+                                          const int8_t* tie_dev, int32_t* counts_out_dev, int32_t* actions_out_dev,
+                                          uint32_t* roots_out_dev, int32_t* r_out_dev, double* score_out_dev,
+                                          int32_t* moves_out_dev, int32_t* steps_run_host, void* stream) {
+    if (!e || !net || !items_wh_dev || !total_area_dev || !bl_dev) return set_err(BPP_E_INVALID, "null argument");
+    if (num_episodes < 1) return set_err(BPP_E_INVALID, "num_episodes = %d", num_episodes);
+    if (choose_mode < 0 || choose_mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", choose_mode);
+    Params& P = e->P;
+    P.q_total = num_episodes;
+    P.q_items = items_wh_dev;
+    P.q_area = total_area_dev;
+    P.q_bl = bl_dev;
+    P.q_tie = tie_dev;
+    P.epq_r = r_out_dev;
+    P.epq_score = score_out_dev;
+    P.epq_moves = moves_out_dev;
+    const int first = P.G;  // episodes 0..G-1 start in the games, the queue hands out the rest
+    cudaError_t ce = cudaMemcpyAsync(P.q_next, &first, sizeof(int), cudaMemcpyHostToDevice, S(stream));
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(P.leaf_count, 0, 4 * sizeof(int), S(stream));
+    if (ce != cudaSuccess) {
+        P.q_total = 0;
+        return set_err(BPP_E_CUDA, "bpp_engine_play_net_stream: %s", cudaGetErrorString(ce));
+    }
+    k_stream_begin<<<grid_warps(P.G), WARPS_PER_CTA * 32, 0, S(stream)>>>(P);
+    e->launches++;
+    e->leaf_parked = false;
+    e->items_ref = e->d_items;
+    int rc = run_lockstep(e, net, choose_mode, seed, counts_out_dev, actions_out_dev, roots_out_dev, (size_t)num_episodes,
+                          steps_run_host, stream);
+    P.q_total = 0;
+    P.q_items = nullptr; P.q_area = nullptr; P.q_bl = nullptr; P.q_tie = nullptr;
+    P.epq_r = nullptr; P.epq_score = nullptr; P.epq_moves = nullptr;
+    return rc;
 }
 
 extern "C" int bpp_engine_set_profile(bpp_engine* e, int on) {
@@ -1722,6 +1866,58 @@ extern "C" int bpp_engine_play_net_host(bpp_engine* e, bpp_net* net, int choose_
         CUDA_TRY(cudaMemcpyAsync(score_out_host, e->P.ep_score, G * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
     if (moves_out_host)
         CUDA_TRY(cudaMemcpyAsync(moves_out_host, e->P.moves_done, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    return bpp_engine_check(e, stream);
+}
+
+// queue / result staging of bpp_engine_play_net_stream_host, grown on demand
+template <typename T>
+static int ensure(bpp_engine* e, T** p, size_t* have, size_t need) {
+    if (*p && *have >= need) return BPP_OK;
+    *have = need;
+    return dev_alloc(e, p, need);  // the old block stays owned by the handle until destroy (rare: sizes repeat)
+}
+
+extern "C" int bpp_engine_play_net_stream_host(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t seed, int num_episodes,
+                                               const int32_t* items_wh_host, const int32_t* total_area_host,
+                                               const double* bl_host, const int8_t* tie_host, uint32_t* roots_out_host,
+                                               int32_t* counts_out_host, int32_t* actions_out_host, int32_t* r_out_host,
+                                               double* score_out_host, int32_t* moves_out_host, int32_t* steps_run_host,
+                                               void* stream) {
+    if (!e || !net || !items_wh_host || !total_area_host || !bl_host) return set_err(BPP_E_INVALID, "null argument");
+    if (num_episodes < 1) return set_err(BPP_E_INVALID, "num_episodes = %d", num_episodes);
+    const size_t E = (size_t)num_episodes, A = (size_t)e->P.geom.A, N = (size_t)e->P.geom.N;
+    int rc;
+    if ((rc = ensure(e, &e->q_items, &e->q_items_n, E * N * 2)) || (rc = ensure(e, &e->q_area, &e->q_area_n, E)) ||
+        (rc = ensure(e, &e->q_bl, &e->q_bl_n, E)) || (rc = ensure(e, &e->q_tie, &e->q_tie_n, E)) ||
+        (rc = ensure(e, &e->q_r, &e->q_r_n, E)) || (rc = ensure(e, &e->q_score, &e->q_score_n, E)) ||
+        (rc = ensure(e, &e->q_moves, &e->q_moves_n, E)))
+        return rc;
+    if (counts_out_host && (rc = ensure(e, &e->q_counts, &e->q_counts_n, N * E * A))) return rc;
+    if (actions_out_host && (rc = ensure(e, &e->q_actions, &e->q_actions_n, N * E))) return rc;
+    if (roots_out_host && (rc = ensure(e, &e->q_roots, &e->q_roots_n, N * E * REC_WORDS))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(e->q_items, items_wh_host, E * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, S(stream)));
+    CUDA_TRY(cudaMemcpyAsync(e->q_area, total_area_host, E * sizeof(int32_t), cudaMemcpyHostToDevice, S(stream)));
+    CUDA_TRY(cudaMemcpyAsync(e->q_bl, bl_host, E * sizeof(double), cudaMemcpyHostToDevice, S(stream)));
+    if (tie_host) CUDA_TRY(cudaMemcpyAsync(e->q_tie, tie_host, E * sizeof(int8_t), cudaMemcpyHostToDevice, S(stream)));
+    CUDA_TRY(cudaMemsetAsync(e->q_moves, 0, E * sizeof(int32_t), S(stream)));
+    if ((rc = bpp_engine_play_net_stream(e, net, choose_mode, seed, num_episodes, e->q_items, e->q_area, e->q_bl,
+                                         tie_host ? e->q_tie : nullptr, counts_out_host ? e->q_counts : nullptr,
+                                         actions_out_host ? e->q_actions : nullptr, roots_out_host ? e->q_roots : nullptr,
+                                         e->q_r, e->q_score, e->q_moves, steps_run_host, stream)))
+        return rc;
+    if (roots_out_host)
+        CUDA_TRY(cudaMemcpyAsync(roots_out_host, e->q_roots, N * E * REC_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                 S(stream)));
+    if (counts_out_host)
+        CUDA_TRY(cudaMemcpyAsync(counts_out_host, e->q_counts, N * E * A * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    if (actions_out_host)
+        CUDA_TRY(cudaMemcpyAsync(actions_out_host, e->q_actions, N * E * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    if (r_out_host) CUDA_TRY(cudaMemcpyAsync(r_out_host, e->q_r, E * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    if (score_out_host)
+        CUDA_TRY(cudaMemcpyAsync(score_out_host, e->q_score, E * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
+    if (moves_out_host)
+        CUDA_TRY(cudaMemcpyAsync(moves_out_host, e->q_moves, E * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
     return bpp_engine_check(e, stream);
 }

@@ -1099,7 +1099,8 @@ struct bpp_net {
     int num_sms = 148;
     // role kernels (k_net_role): one plan per ConvSequence, bf16 [0] and split-bf16 [1]
     bpptc::TcParams Tr[2][3];
-    int role_ctas[2][3] = {{2, 2, 2}, {1, 1, 1}};
+    int role_ctas[2][3] = {{2, 1, 2}, {1, 1, 1}};   // measured: profiles/r02_role_sweep.txt
+    int roles_min_batch = 6144;  // bf16: below this batch the one-kernel trunk is faster (three launches, emptier groups)
     bool roles_ok[2] = {false, false};
     uint4* d_x1 = nullptr;   // hand-over buffers between the roles (sized for the split mode: hi + lo)
     uint4* d_x2 = nullptr;
@@ -1340,6 +1341,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             for (int x = 0; x < 2; ++x) {
                 const char* ce = getenv(x ? "BPP_ROLE_CTAS_X3" : "BPP_ROLE_CTAS");   // e.g. "2,2,2"
                 if (ce) sscanf(ce, "%d,%d,%d", &n->role_ctas[x][0], &n->role_ctas[x][1], &n->role_ctas[x][2]);
+                if (const char* mb = getenv("BPP_ROLES_MIN_BATCH")) n->roles_min_batch = atoi(mb);
                 bool ok = getenv("BPP_NO_ROLES") == nullptr && (P.flat % 16 == 0);
                 for (int sq = 0; sq < 3 && ok; ++sq) {
                     int& c = n->role_ctas[x][sq];
@@ -1633,7 +1635,7 @@ extern "C" int bpp_net_profile(bpp_net* n, int64_t cycles_host[8]) {
     if (cudaMemcpy(all, n->d_prof, sizeof(all), cudaMemcpyDeviceToHost) != cudaSuccess)
         return nerr(BPP_E_CUDA, "profile copy failed");
     // role kernels write one block of 8 timers each (rows 0..2): report their sum; the one-kernel trunk writes row 0
-    const bool roles = (n->precision == BPP_NET_BF16 && n->roles_ok[0] && n->heads_ok) ||
+    const bool roles = (n->precision == BPP_NET_BF16 && n->roles_ok[0] && n->heads_ok && n->max_batch >= n->roles_min_batch) ||
                        (n->precision == BPP_NET_BF16X3 && n->roles_ok[1] && n->heads3_ok);
     for (int i = 0; i < 8; ++i) cycles_host[i] = roles ? all[i] + all[8 + i] + all[16 + i] : all[i];
     return BPP_OK;
@@ -1714,7 +1716,7 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int cap = n->num_sms * n->ctas_per_sm;
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
-        if (fo && n->roles_ok[0]) {
+        if (fo && n->roles_ok[0] && B >= n->roles_min_batch) {
             int rc = launch_roles(n, 0, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
             if (rc) return rc;
         } else if (fo && n->ctas_per_sm == 2)

@@ -360,6 +360,59 @@ class SearchEngine:
              _ptr(roots), C.byref(steps), _stream())
         return {"roots": roots, "counts": counts, "actions": actions, "steps": int(steps.value)}
 
+    def play_net_stream(self, dnet, items_wh, total_area, bl, tie=None, choose_mode=_lib.CHOOSE_SAMPLE, seed=0,
+                        record=True):
+        """E >= 1 episodes streamed through the G resident games (bpp_engine_play_net_stream): a game whose episode ends
+        takes the next instance of the queue inside the search kernel, so no batch waits for its slowest episode.
+        items_wh (E, N, 2), total_area (E,), bl (E,) float64 (NaN = empty rewards list), tie (E,) int8 or None.
+        Returns device tensors indexed by EPISODE: roots (N, E, 32), counts (N, E, A), actions (N, E) (None unless
+        record), r (E,), score (E,), moves (E,), and `steps`."""
+        items = _dev(items_wh, torch.int32, self.device)
+        E = items.shape[0]
+        items = items.reshape(E, self.N, 2)
+        area = _dev(total_area, torch.int32, self.device).reshape(E)
+        blt = _dev(bl, torch.float64, self.device).reshape(E)
+        tiet = _dev(tie, torch.int8, self.device).reshape(E) if tie is not None else None
+        roots = counts = actions = None
+        if record:
+            roots = torch.empty((self.N, E, REC_WORDS), dtype=torch.int32, device=self.device)
+            counts = torch.empty((self.N, E, self.A), dtype=torch.int32, device=self.device)
+            actions = torch.empty((self.N, E), dtype=torch.int32, device=self.device)
+        r = torch.zeros(E, dtype=torch.int32, device=self.device)
+        score = torch.zeros(E, dtype=torch.float64, device=self.device)
+        moves = torch.zeros(E, dtype=torch.int32, device=self.device)
+        steps = C.c_int32(0)
+        self.items_wh = items[:self.G] if E >= self.G else items
+        call("bpp_engine_play_net_stream", self._h, dnet._h, int(choose_mode), C.c_uint64(seed), int(E), _ptr(items),
+             _ptr(area), _ptr(blt), _ptr(tiet), _ptr(counts), _ptr(actions), _ptr(roots), _ptr(r), _ptr(score),
+             _ptr(moves), C.byref(steps), _stream())
+        return {"roots": roots, "counts": counts, "actions": actions, "r": r, "score": score, "moves": moves,
+                "steps": int(steps.value)}
+
+    def play_net_stream_host(self, dnet, items_wh, total_area, bl, tie=None, choose_mode=_lib.CHOOSE_SAMPLE, seed=0,
+                             out=None):
+        """the same from / to HOST buffers through the C ABI (uploads the queue, plays, downloads, synchronises)"""
+        items = np.ascontiguousarray(items_wh, dtype=np.int32)
+        E = items.shape[0]
+        area = np.ascontiguousarray(total_area, dtype=np.int32)
+        blh = np.ascontiguousarray(bl, dtype=np.float64)
+        tieh = np.ascontiguousarray(tie, dtype=np.int8) if tie is not None else None
+        if out is None:
+            out = {}
+        out.setdefault("roots", np.empty((self.N, E, REC_WORDS), dtype=np.uint32))
+        out.setdefault("counts", np.empty((self.N, E, self.A), dtype=np.int32))
+        out.setdefault("actions", np.empty((self.N, E), dtype=np.int32))
+        out.setdefault("r", np.empty(E, dtype=np.int32))
+        out.setdefault("score", np.empty(E, dtype=np.float64))
+        out.setdefault("moves", np.empty(E, dtype=np.int32))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        steps = C.c_int32(0)
+        call("bpp_engine_play_net_stream_host", self._h, dnet._h, int(choose_mode), C.c_uint64(seed), int(E), vp(items),
+             vp(area), vp(blh), vp(tieh) if tieh is not None else C.c_void_p(0), vp(out["roots"]), vp(out["counts"]),
+             vp(out["actions"]), vp(out["r"]), vp(out["score"]), vp(out["moves"]), C.byref(steps), _stream())
+        out["steps"] = int(steps.value)
+        return out
+
     def play_net_host(self, dnet, items_wh, total_area, bl, tie=None, choose_mode=_lib.CHOOSE_SAMPLE, seed=0, out=None):
         """HOST-buffer episode batch with the real net through the C ABI (uploads, plays, downloads, synchronises).
         `out` may hold preallocated (ideally pinned) numpy arrays: roots (N,G,32) u32, counts (N,G,A) i32, actions

@@ -169,17 +169,21 @@ class BatchedMCTS:
         self.eng.close()
 
     def play_episodes(self, items_wh, total_area, rewards_list, greedy=False, seed=0, tie=None, record=True, mode=None):
-        """Whole self-play episodes for all G games (CoachBPP.executeEpisode, CoachBPP.py:50-99, batched): every game
-        runs numMCTSSims simulations per move, chooses (sample ~ counts, or a random arg-max when greedy) and plays on
-        at its own pace inside the search kernels (bpp_engine_play_net); the host only polls for the end of the batch.
-        Returns the compact examples as device tensors: roots (N,G,32), counts (N,G,A), actions (N,G), moves, r, score."""
-        self.reset(items_wh, total_area, rewards_list, tie)
+        """Whole self-play episodes (CoachBPP.executeEpisode, CoachBPP.py:50-99, batched) for E >= 1 instances streamed
+        through the G resident games: every game runs numMCTSSims simulations per move, chooses (sample ~ counts, or a
+        random arg-max when greedy) and plays on at its own pace inside the search kernels, and takes the next instance
+        when its episode ends (bpp_engine_play_net_stream); the host only polls for the end of the stream.
+        Returns the compact examples as device tensors indexed by episode: roots (N,E,32), counts (N,E,A), actions
+        (N,E), moves, r, score, done."""
+        E = int(items_wh.shape[0])
+        bl = np.full(E, ranked_threshold(rewards_list, self.args.alpha))
+        if tie is None:
+            tie = np.where(_TIE_RNG.random(E) < 0.5, 1, -1).astype(np.int8)
         if mode is None:
             mode = _lib.CHOOSE_GREEDY if greedy else _lib.CHOOSE_SAMPLE
-        out = self.eng.play_net(self.nnet.dnet, mode, seed, record)
+        out = self.eng.play_net_stream(self.nnet.dnet, items_wh, total_area, bl, tie, mode, seed, record)
         self.steps += out.pop("steps")
-        st = self.eng.status()
-        out.update(moves=st["moves"], r=st["r"], score=st["score"], done=st["done"])
+        out["done"] = (out["moves"] > 0).to(torch.int32)
         return out
 
     def reset(self, items_wh, total_area, rewards_list, tie=None):

@@ -55,7 +55,7 @@ def run(W, H, N, B, modes=("bf16", "bf16_simt", "fp32"), iters=20):
         out[m] = {"ms": ms, "evals_per_s": B / ms * 1e3, "tflops": B * FLOPS[(W, H, N)] / ms / 1e9}
         if m in ("bf16", "bf16x3"):
             out[m]["cta0_cycles"] = net.dnet.profile()
-            if m == "bf16" and os.environ.get("BPP_NO_ROLES") is None:
+            if os.environ.get("BPP_NO_ROLES") is None:
                 out[m]["cta0_cycles_per_role"] = net.dnet.profile_roles()
     return out
 

@@ -264,3 +264,45 @@ def test_one_mcts_object_replays_the_same_instance_many_times():
                 first = pi
             board, planes = g.getNextState(board, int(np.argmax(pi)), planes)
     assert abs(sum(first) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("W,H,E,G,SIMS,mode", [(15, 15, 101, 32, 30, 1), (20, 20, 50, 7, 25, 2)])
+def test_streamed_episodes_do_not_depend_on_the_number_of_resident_games(W, H, E, G, SIMS, mode):
+    """E instances streamed through G < E resident games (a game whose episode ends takes the next instance inside the
+    search kernel, in whatever order the games finish) == the same E instances with one resident game each: identical
+    examples and outcomes per episode, because the action stream is keyed by (seed, episode, move)."""
+    from resource_packing_self_play_b200.game import BinPackingGame, ItemsGenerator
+    from resource_packing_self_play_b200.mcts import BatchedMCTS
+    N = 10
+    g = BinPackingGame(W, H, N, 1)
+    args = _args(numMCTSSims=SIMS)
+    net = _net(g, args, precision="bf16", max_batch=E)
+    with torch.no_grad():
+        net.nnet.logits_fc.weight.mul_(30.0)
+        net.nnet.value_fc.weight.mul_(20.0)
+    net.sync_weights()
+    rng = np.random.RandomState(3)
+    heights = rng.randint(2, H + 1, size=E).astype(np.int32)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(E) + 900, heights)
+    area = (W * heights).astype(np.int32)
+    tie = np.ones(E, dtype=np.int8)
+    rl = [0.4, 0.6, 0.8001]
+    outs = []
+    for resident in (E, G):
+        bm = BatchedMCTS(g, net, args, resident)
+        ep = bm.play_episodes(items, area, rl, seed=5, tie=tie, mode=mode)
+        bm.eng.check()
+        outs.append({k: v.cpu().numpy() for k, v in ep.items()})
+        bm.close()
+    a, b = outs
+    assert (a["moves"] > 0).all() and a["moves"].min() < N
+    for k in ("moves", "r", "score", "counts", "actions", "roots"):
+        assert np.array_equal(a[k], b[k]), k
+    # and the host-buffer entry point of the stream
+    bm = BatchedMCTS(g, net, args, G)
+    out = bm.eng.play_net_stream_host(net.dnet, items, area, np.full(E, bl_of(rl)), tie=tie, choose_mode=mode, seed=5)
+    bm.eng.check()
+    for k in ("moves", "r", "score", "counts", "actions"):
+        assert np.array_equal(out[k], a[k]), k
+    assert np.array_equal(out["roots"].view(np.int32), a["roots"])
+    bm.close()

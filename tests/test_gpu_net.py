@@ -200,6 +200,7 @@ def test_role_kernels_equal_the_one_kernel_trunk_bit_for_bit(W, H, N, B, monkeyp
     items = ItemsGenerator(W, H, N).items_batch(np.arange(B) % 53 + 9, None)
     outs = []
     for no_roles in ("", "1"):
+        monkeypatch.setenv("BPP_ROLES_MIN_BATCH", "1")   # role kernels at any batch size (default: large batches only)
         if no_roles:
             monkeypatch.setenv("BPP_NO_ROLES", "1")
         else:
