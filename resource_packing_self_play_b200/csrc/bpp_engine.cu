@@ -1107,8 +1107,8 @@ struct bpp_engine {
     float* d_pol = nullptr;            // [G][A]
     float* d_val = nullptr;            // [G]
     uint32_t* d_roots_all = nullptr;   // [N][G][32], lazily allocated by play_net_host
-    int32_t* h_prog = nullptr;         // pinned [2][4]
-    cudaEvent_t ev_prog[2] = {nullptr, nullptr};
+    int32_t* h_prog = nullptr;         // pinned [4][8]: leaf_count[4], simulations (u64), -
+    cudaEvent_t ev_prog[4] = {nullptr, nullptr, nullptr, nullptr};
     const int32_t* items_ref = nullptr;  // int32 [G][N][2] item list of the current episodes (evaluator input)
     int num_sms = 148;
     // staging of bpp_engine_play_net_stream_host (device; element counts)
@@ -1147,7 +1147,7 @@ extern "C" int bpp_engine_destroy(bpp_engine* e) {
     for (void* p : e->allocs) cudaFree(p);
     if (e->h_status) cudaFreeHost(e->h_status);
     if (e->h_prog) cudaFreeHost(e->h_prog);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
         if (e->ev_prog[i]) cudaEventDestroy(e->ev_prog[i]);
     for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
     delete e;
@@ -1280,8 +1280,8 @@ extern "C" int bpp_engine_create(const bpp_config* cfg, bpp_engine** out) {
     CREATE_TRY(cudaMemset(P.pend_depth, 0xff, G * sizeof(int)));
     CREATE_TRY(cudaMemset(P.leaf_count, 0, 4 * sizeof(int)));
     CREATE_TRY(cudaMallocHost(&e->h_status, G * sizeof(int)));
-    CREATE_TRY(cudaMallocHost(&e->h_prog, 8 * sizeof(int32_t)));
-    for (int i = 0; i < 2; ++i) CREATE_TRY(cudaEventCreateWithFlags(&e->ev_prog[i], cudaEventDisableTiming));
+    CREATE_TRY(cudaMallocHost(&e->h_prog, 32 * sizeof(int32_t)));
+    for (int i = 0; i < 4; ++i) CREATE_TRY(cudaEventCreate(&e->ev_prog[i]));
     P.auto_mode = -1;
     *out = e;
     return BPP_OK;
@@ -1685,8 +1685,8 @@ static int run_lockstep(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t s
     // Work per game and launch.  A launch lasts as long as its slowest warp, and a game whose simulations end on terminal
     // states parks no leaf, so its work per launch is bounded - in EDGES WALKED (a late-game simulation is 1-2 edges deep,
     // an early one 5-10), not in simulations.  The bound adapts to the leaf supply: with a sharp trained policy only ~2 %
-    // of the simulations need the evaluator, and the bound grows until most of the running games park a leaf per step;
-    // with a flat prior it stays small so that parked games do not wait for long descents of the others.
+    // of the simulations need the evaluator; with a flat prior most do.  The bound is therefore tuned while the stream
+    // runs, by hill climbing on the measured simulations per device-second of the last chunk.
     const int keep_cap = P.select_cap;
     const char* bud_env = getenv("BPP_EDGE_BUDGET");
     const bool adapt = bud_env == nullptr;
@@ -1710,6 +1710,9 @@ static int run_lockstep(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t s
     const int chunk = 8;
     int steps = 0;
     size_t nev = 0;
+    int used[4] = {budget, budget, budget, budget};   // edge budget the chunks of the progress ring were queued with
+    int dir = 1;
+    double last_rate = 0.0;
     const bool trace = getenv("BPP_PLAY_TRACE") != nullptr;
     auto mark = [&]() {  // profiling pass only: one event per call boundary
         if (!e->prof_on) return;
@@ -1733,18 +1736,38 @@ static int run_lockstep(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t s
             }
         }
         steps += chunk;
-        int32_t* hp = e->h_prog + 4 * (k & 1);
+        int32_t* hp = e->h_prog + 8 * (k & 3);
         cudaError_t ce = cudaMemcpyAsync(hp, P.leaf_count, 4 * sizeof(int), cudaMemcpyDeviceToHost, S(stream));
-        if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_prog[k & 1], S(stream));
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(hp + 4, P.stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, S(stream));
+        if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_prog[k & 3], S(stream));
+        used[k & 3] = budget;
         if (ce == cudaSuccess && k > 0) {
-            ce = cudaEventSynchronize(e->ev_prog[(k - 1) & 1]);
-            const int32_t* pp = e->h_prog + 4 * ((k - 1) & 1);
-            if (trace) fprintf(stderr, "play_net chunk %d: leaves %d capped %d running %d budget %d\n", k - 1, pp[0], pp[1], pp[2], budget);
+            ce = cudaEventSynchronize(e->ev_prog[(k - 1) & 3]);
+            const int32_t* pp = e->h_prog + 8 * ((k - 1) & 3);
+            if (trace) fprintf(stderr, "play_net chunk %d: leaves %d capped %d running %d budget %d rate %.1f M sims/s\n", k - 1,
+                               pp[0], pp[1], pp[2], used[(k - 1) & 3], last_rate * 1e-3);
             if (ce == cudaSuccess && pp[0] == 0 && pp[2] == 0) break;  // nothing parked, nobody playing
-            if (adapt && pp[2] > 0) {
-                if (pp[0] * 5 < pp[2] * 4 && budget < 8192) budget *= 2;         // < 80 % of the running games parked a leaf
-                else if (pp[0] * 20 > pp[2] * 19 && budget > 8) budget /= 2;     // > 95 % did
-                P.edge_budget = budget;
+            if (adapt && k > 1 && pp[2] > 0 && ce == cudaSuccess) {
+                // hill climbing on the measured throughput: simulations completed between the ends of the last two chunks
+                // (device counter) per device time (events), against the edge budget those steps ran with
+                float dt = 0.f;
+                unsigned long long s1, s0;
+                memcpy(&s1, pp + 4, 8);
+                memcpy(&s0, e->h_prog + 8 * ((k - 2) & 3) + 4, 8);
+                if (cudaEventElapsedTime(&dt, e->ev_prog[(k - 2) & 3], e->ev_prog[(k - 1) & 3]) == cudaSuccess && dt > 0.f) {
+                    const double rate = (double)(s1 - s0) / dt;  // simulations per ms
+                    if (used[(k - 1) & 3] == budget) {
+                        // that chunk ran with the current setting (a new setting takes effect one chunk after it is
+                        // chosen, because the next chunk is already queued): compare with the previous setting's rate
+                        if (last_rate > 0.0 && rate < 0.98 * last_rate) dir = -dir;
+                        last_rate = rate;
+                        int nb = dir > 0 ? budget * 2 : budget / 2;
+                        if (nb < 8) { nb = 8; dir = 1; }
+                        if (nb > 8192) { nb = 8192; dir = -1; }
+                        budget = nb;
+                        P.edge_budget = budget;
+                    }
+                }
             }
         }
         if (ce != cudaSuccess) {
