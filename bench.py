@@ -528,7 +528,7 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
     from resource_packing_self_play_b200.mcts import BatchedMCTS
     from resource_packing_self_play_b200.nnet import BinPackingNNet
     G = args.games
-    steps = steps or max(2, args.steps // 5)
+    steps = steps or max(3, args.steps // 5)
     warmup = warmup if warmup is not None else max(3, args.warmup)
     net, weights = _make_net(cx, Wb, Hb, G, precision)
     mode = net.dnet.precision
@@ -537,7 +537,12 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
     gen = ItemsGenerator(Wb, Hb, N)
     n_tot = warmup + steps
 
-    E = args.stream_mult * G   # episodes per step, streamed through the G resident games
+    # episodes per step, streamed through the G resident games.  A game that needs the evaluator on every simulation (flat
+    # prior) takes numMCTSSims x moves sequential lockstep steps whatever the batch does, so the stream must be long against
+    # that tail: 16 x G with the sharp trained policy (whose bulk of episodes is over in ~300 steps), 4 x G with the
+    # random-init net (all episodes alike)
+    mult = args.stream_mult or (16 if (Wb, Hb) == (15, 15) else 4)
+    E = mult * G
 
     def instances(k):
         seeds, hts, areas = workload(((k * cx.world) + cx.rank) * E, E, Wb, Hb)
@@ -772,7 +777,7 @@ def main():
     ap.add_argument("--workload", default="all",
                     help="comma list of: stub (headline), real15, real20, iteration, arena, checksum; all = every one")
     ap.add_argument("--precision", default="auto", help="precision mode of a single real15/real20 run")
-    ap.add_argument("--stream-mult", type=int, default=4,
+    ap.add_argument("--stream-mult", type=int, default=0,
                     help="real-net workloads: episodes per step = stream-mult x games, streamed through the resident games")
     ap.add_argument("--iteration-games", type=int, default=8192)
     ap.add_argument("--arena-seeds", type=int, default=8192)

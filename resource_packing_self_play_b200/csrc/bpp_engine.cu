@@ -1711,8 +1711,8 @@ static int run_lockstep(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t s
     int steps = 0;
     size_t nev = 0;
     int used[4] = {budget, budget, budget, budget};   // edge budget the chunks of the progress ring were queued with
-    int dir = 1;
-    double last_rate = 0.0;
+    int dir = 1, acc_n = 0;
+    double last_rate = 0.0, acc_sims = 0.0, acc_ms = 0.0;
     const bool trace = getenv("BPP_PLAY_TRACE") != nullptr;
     auto mark = [&]() {  // profiling pass only: one event per call boundary
         if (!e->prof_on) return;
@@ -1748,25 +1748,43 @@ static int run_lockstep(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t s
                                pp[0], pp[1], pp[2], used[(k - 1) & 3], last_rate * 1e-3);
             if (ce == cudaSuccess && pp[0] == 0 && pp[2] == 0) break;  // nothing parked, nobody playing
             if (adapt && k > 1 && pp[2] > 0 && ce == cudaSuccess) {
-                // hill climbing on the measured throughput: simulations completed between the ends of the last two chunks
-                // (device counter) per device time (events), against the edge budget those steps ran with
+                // Edge budget control.  (1) While fewer than 15 % of the running games stop at the budget there is nothing
+                // to gain from a larger one (nearly every game parks a leaf first): shrink towards the floor.  (2) Otherwise
+                // hill-climb on the measured throughput: simulations completed (device counter) per device time (events)
+                // over the last TWO chunks that ran entirely with the current setting; a new setting takes effect one chunk
+                // after it is chosen, because the next chunk is already queued.
                 float dt = 0.f;
                 unsigned long long s1, s0;
                 memcpy(&s1, pp + 4, 8);
                 memcpy(&s0, e->h_prog + 8 * ((k - 2) & 3) + 4, 8);
-                if (cudaEventElapsedTime(&dt, e->ev_prog[(k - 2) & 3], e->ev_prog[(k - 1) & 3]) == cudaSuccess && dt > 0.f) {
-                    const double rate = (double)(s1 - s0) / dt;  // simulations per ms
-                    if (used[(k - 1) & 3] == budget) {
-                        // that chunk ran with the current setting (a new setting takes effect one chunk after it is
-                        // chosen, because the next chunk is already queued): compare with the previous setting's rate
-                        if (last_rate > 0.0 && rate < 0.98 * last_rate) dir = -dir;
-                        last_rate = rate;
-                        int nb = dir > 0 ? budget * 2 : budget / 2;
-                        if (nb < 8) { nb = 8; dir = 1; }
-                        if (nb > 8192) { nb = 8192; dir = -1; }
-                        budget = nb;
-                        P.edge_budget = budget;
+                const bool same = used[(k - 1) & 3] == budget;
+                if (same && cudaEventElapsedTime(&dt, e->ev_prog[(k - 2) & 3], e->ev_prog[(k - 1) & 3]) == cudaSuccess && dt > 0.f) {
+                    acc_sims += (double)(s1 - s0);
+                    acc_ms += dt;
+                    acc_n++;
+                } else if (!same) {
+                    acc_sims = acc_ms = 0.0;
+                    acc_n = 0;
+                }
+                if (pp[1] * 100 < pp[2] * 15) {
+                    if (same && budget > 8) {
+                        budget /= 2;
+                        dir = -1;
+                        last_rate = 0.0;
                     }
+                } else if (acc_n >= 2) {
+                    const double rate = acc_sims / acc_ms;  // simulations per ms
+                    if (last_rate > 0.0 && rate < 0.98 * last_rate) dir = -dir;
+                    last_rate = rate;
+                    int nb = dir > 0 ? budget * 2 : budget / 2;
+                    if (nb < 8) { nb = 8; dir = 1; }
+                    if (nb > 8192) { nb = 8192; dir = -1; }
+                    budget = nb;
+                }
+                if (budget != P.edge_budget) {
+                    P.edge_budget = budget;
+                    acc_sims = acc_ms = 0.0;
+                    acc_n = 0;
                 }
             }
         }

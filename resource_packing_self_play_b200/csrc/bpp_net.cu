@@ -616,8 +616,11 @@ k_net_role(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__
     for (int b0 = slice_lo; b0 < slice_hi; b0 += gsz) {
         const int nvalid = min(gsz, slice_hi - b0);
         long long tq = clock64();
-        // ---- this role's input in the level-SEQ operand planes (region A)
-        zero_bytes(regA, (SEQ == 0 ? 1 : fx) * in_planes_n * La.RT * 16);
+        // ---- this role's input in the level-SEQ operand planes (region A).  One thread per grid entry (16 bytes = the 8
+        // channels of one padded pixel), consecutive threads on consecutive entries: halo entries are written as zeros in
+        // the same pass (no separate clearing of the region), up to one grid row behind the last present sample - the
+        // furthest entry a stored output row reads.  Entries beyond that keep stale data: they only feed accumulator rows
+        // that are never stored.
         if (SEQ == 0) {
             for (int i = tid; i < nvalid * 32; i += TC_THREADS) s_rec[i >> 5][i & 31] = recs[(size_t)(b0 + (i >> 5)) * 32 + (i & 31)];
             for (int i = tid; i < nvalid * P.N * 2; i += TC_THREADS) {
@@ -626,57 +629,49 @@ k_net_role(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__
                 const int g = game ? game[b] : b;
                 s_it[j][r >> 1][r & 1] = items_wh[(size_t)g * P.N * 2 + r];
             }
+            __syncthreads();
         }
-        __syncthreads();
-        if (SEQ == 0) {
-            // input planes from the compact records (getBinItem, BinPackingGame.py:118-120): one thread builds half a grid
-            // row of one 8-channel plane (see k_net_forward_tc)
-            const int rows = nvalid * P.H;
-            const int xh = (P.W + 1) >> 1;
-            const uint32_t mrows = fdiv_magic((uint32_t)rows);
-            for (int idx = tid; idx < 2 * in_planes_n * rows; idx += TC_THREADS) {
-                const int hp = fdiv(idx, mrows);
-                int r = idx - hp * rows;
-                const int j = fdiv(r, T.mH), y = r - j * P.H;
-                const int half = hp >= in_planes_n ? 1 : 0, p = hp - half * in_planes_n;
-                const uint32_t rem = s_rec[j][BPP_REC_REM];
-                uint32_t m[8];
+        {
+            const int nrows = nvalid * La.P + La.wp + 1;
+            const int nplanes = (SEQ == 0 ? 1 : fx) * in_planes_n;   // the 0/1 input has no low halves
+            const uint32_t mrows = fdiv_magic((uint32_t)nrows);
+            uint4* base = reinterpret_cast<uint4*>(regA);
+            for (int idx = tid; idx < nplanes * La.guard; idx += TC_THREADS) {   // front guard rows
+                const int p = idx / La.guard;
+                base[(size_t)p * La.RT + (idx - p * La.guard)] = make_uint4(0, 0, 0, 0);
+            }
+            const int per = nplanes * hwa;   // hand-over entries per leaf
+            for (int idx = tid; idx < nplanes * nrows; idx += TC_THREADS) {
+                const int p = fdiv(idx, mrows);
+                const int r = idx - p * nrows;
+                const int j = fdiv(r, La.mP), q = r - j * La.P;
+                const int yp = fdiv(q, La.mwp), xp = q - yp * La.wp;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (j < nvalid && yp >= 1 && xp >= 1) {
+                    const int y = yp - 1, x = xp - 1;
+                    if (SEQ == 0) {
+                        // input planes from the compact record (getBinItem, BinPackingGame.py:118-120): channel 0 = bin
+                        // occupancy, channel i+1 = item i's [0:h, 0:w] block while it is still to be placed
+                        const uint32_t rem = s_rec[j][BPP_REC_REM];
+                        uint32_t bits = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int c = p * 8 + k;
-                    m[k] = 0;
-                    if (c == 0) m[k] = s_rec[j][y];
-                    else if (c <= P.N && ((rem >> (c - 1)) & 1u) && y < s_it[j][c - 1][1]) {
-                        const int iw = s_it[j][c - 1][0];
-                        m[k] = iw >= 32 ? 0xffffffffu : (1u << iw) - 1u;
+                        for (int k = 0; k < 8; ++k) {
+                            const int c = p * 8 + k;
+                            uint32_t on;
+                            if (c == 0) on = (s_rec[j][y] >> x) & 1u;
+                            else on = (c <= P.N && ((rem >> (c - 1)) & 1u) && y < s_it[j][c - 1][1] && x < s_it[j][c - 1][0]) ? 1u : 0u;
+                            bits |= on << k;
+                        }
+                        v.x = ((bits & 1u) | ((bits & 2u) << 15)) * 0x3f80u;          // bf16 1.0 pairs
+                        v.y = (((bits >> 2) & 1u) | ((bits & 8u) << 13)) * 0x3f80u;
+                        v.z = (((bits >> 4) & 1u) | ((bits & 32u) << 11)) * 0x3f80u;
+                        v.w = (((bits >> 6) & 1u) | ((bits & 128u) << 9)) * 0x3f80u;
+                    } else {
+                        // the previous role's residual stream: [leaf][hi|lo][plane][pixel]
+                        v = __ldg(xin + (size_t)(b0 + j) * per + (size_t)p * hwa + y * La.w + x);
                     }
                 }
-                const int x0 = half ? xh : 0, n = half ? P.W - xh : xh;
-                uint4* dst = reinterpret_cast<uint4*>(regA) + (size_t)p * La.RT + La.guard + j * La.P + (y + 1) * La.wp + 1 + x0;
-                int i = n > 0 ? lane % n : 0;
-                for (int step = 0; step < n; ++step) {
-                    const int x = x0 + i;
-                    uint32_t w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        w[q] = (((m[2 * q] >> x) & 1u) | (((m[2 * q + 1] >> x) & 1u) << 16)) * 0x3f80u;  // bf16 1.0 pairs
-                    dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
-                    if (++i == n) i = 0;
-                }
-            }
-        } else {
-            // the previous role's residual stream: [leaf][hi|lo][plane][pixel] -> zero-haloed grids
-            const int per = fx * in_planes_n * hwa;
-            const uint32_t mper = fdiv_magic((uint32_t)per);
-            const uint32_t mhwa = fdiv_magic((uint32_t)hwa);
-            const uint4* src = xin + (size_t)b0 * per;
-            for (int idx = tid; idx < nvalid * per; idx += TC_THREADS) {
-                const int j = fdiv(idx, mper);
-                int r = idx - j * per;
-                const int hp = fdiv(r, mhwa), q = r - hp * hwa;   // hp = half * planes + plane
-                const int y = fdiv(q, La.mw), x = q - y * La.w;
-                const size_t row = (size_t)La.guard + (size_t)j * La.P + (size_t)(y + 1) * La.wp + (x + 1);
-                reinterpret_cast<uint4*>(regA)[(size_t)hp * La.RT + row] = __ldg(src + idx);
+                base[(size_t)p * La.RT + La.guard + r] = v;
             }
         }
         __syncthreads();
