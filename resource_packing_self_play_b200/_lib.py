@@ -91,6 +91,7 @@ SIGNATURES = {
     "bpp_net_set_precision": [_vp, _i32],
     "bpp_net_profile": [_vp, C.POINTER(_i64)],
     "bpp_net_profile_roles": [_vp, C.POINTER(_i64)],
+    "bpp_net_grid_row": [_vp],
     "bpp_net_forward": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "bpp_learner_create": [_i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)],
     "bpp_learner_destroy": [_vp],

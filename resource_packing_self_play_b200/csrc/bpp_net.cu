@@ -758,6 +758,8 @@ k_net_role(NetParams P, bpptc::TcParams T, int Bmax, const int32_t* __restrict__
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"((uint32_t)T.tmem_cols));
 }
 
+#include "bpp_net_gr.cuh"
+
 // ---------------------------------------------------------------------------------------------------------------------
 // FC heads as batched GEMMs on the tensor core: one CTA = 128 leaves (one M tile).
 //   hidden = relu(feat[128 x flat] * W1^T + b1)   -> TMEM columns [0, 256)
@@ -1099,6 +1101,12 @@ struct bpp_net {
     bool roles_ok[2] = {false, false};
     uint4* d_x1 = nullptr;   // hand-over buffers between the roles (sized for the split mode: hi + lo)
     uint4* d_x2 = nullptr;
+    // grid-row trunk (k_net_gr, bpp_net_gr.cuh): one plan per level
+    bppgr::GrStage Gr[4];
+    bool gr_ok = false;
+    __nv_bfloat16* d_wts_gr = nullptr;
+    long long gr_elems = 0;
+    uint4* d_g[3] = {nullptr, nullptr, nullptr};   // hand-over buffers x1, x2, x3
 };
 
 static const char* kSeqConvNames[5] = {"conv", "res_block0.conv0", "res_block0.conv1", "res_block1.conv0",
@@ -1449,6 +1457,91 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             n->roles_ok[0] = n->roles_ok[1] = false;
         }
     }
+
+    // ---- grid-row trunk (bpp_net_gr.cuh): one plan per level.  J = leaves per group (J * (w+1) <= 128 rows = one MMA
+    // tile per grid row), two groups in flight per CTA where shared memory and the TMEM columns allow it
+    {
+        const int cin16_0 = (P.Cin + 15) / 16;
+        const int chans_in[4] = {16 * cin16_0, 16, 32, 32};
+        long long goff = 0;
+        bool ok = getenv("BPP_NO_GR") == nullptr && P.flat % 16 == 0 && n->heads_ok;
+        const int cap = 232448 - 7 * 1024;   // 227 KB per block minus the kernel's static shared memory
+        for (int s = 0; s < 4 && ok; ++s) {
+            bppgr::GrStage& G = n->Gr[s];
+            memset(&G, 0, sizeof(G));
+            G.h = P.hs[s]; G.w = P.ws[s]; G.wp = G.w + 1; G.NT = G.h;
+            G.h2 = s < 3 ? P.hs[s + 1] : 0; G.w2 = s < 3 ? P.ws[s + 1] : 0;
+            G.cp = chans_in[s] / 8;
+            G.arena_planes = s == 0 ? std::max(G.cp, 2) : 2 * G.cp;
+            G.planes_out = s < 3 ? chans[s] / 8 : 0;
+            // layers: stage 0 = conv 0; stage s = the four residual convs at this level, then the next sequence's conv
+            int first = s == 0 ? 0 : 5 * (s - 1) + 1;
+            G.nlay = s == 0 ? 1 : s == 3 ? 4 : 5;
+            int off = 0, cmax = 0;
+            for (int l = 0; l < G.nlay; ++l) {
+                const ConvDesc& d = P.conv[first + l];
+                G.cin16[l] = (d.ci + 15) / 16;
+                G.cout[l] = d.co;
+                G.w_len[l] = 9 * G.cin16[l] * 2 * d.co * 16;
+                G.w_soff[l] = off;
+                G.w_goff[l] = goff;
+                G.b_goff[l] = d.b_off;
+                off += G.w_len[l];
+                goff += G.w_len[l] / 2;
+                cmax = std::max(cmax, d.co);
+            }
+            G.w_bytes = off;
+            G.arena_off = (off + G.nlay * 32 * 4 + 127) & ~127;
+            if (G.NT > bppgr::MAX_TILES || G.wp > 128) { ok = false; break; }
+            const char* je = getenv(s == 0 ? "BPP_GR_J0" : s == 1 ? "BPP_GR_J1" : s == 2 ? "BPP_GR_J2" : "BPP_GR_J3");
+            int jmax = std::min(128 / G.wp, s == 0 ? 8 : 255);
+            if (je) jmax = std::max(1, std::min(jmax, atoi(je)));
+            const char* se = getenv("BPP_GR_NSUB");
+            const int nsub_max = se ? std::max(1, std::min(2, atoi(se))) : 2;
+            bool fit = false;
+            for (int J = jmax; J >= 1 && !fit; --J)
+                for (int ns = nsub_max; ns >= 1 && !fit; --ns) {
+                    // prefer two groups in flight with slightly smaller groups over one full group
+                    if (ns == 1 && J > 1 && J * 4 > jmax * 3 && nsub_max == 2 && G.NT * cmax <= 256) continue;
+                    if (G.NT * cmax > 512 / ns) continue;
+                    G.J = J;
+                    G.TS = (J * G.wp + 7) & ~7;
+                    G.RT = bppgr::G0 + (G.NT - 1) * G.TS + 128 + 8;
+                    G.arena_bytes = G.arena_planes * G.RT * 16;
+                    G.nsub = ns;
+                    G.smem_bytes = G.arena_off + ns * G.arena_bytes;
+                    fit = G.smem_bytes <= cap && G.RT < 16384;
+                }
+            if (!fit) { ok = false; break; }
+            int cols = G.nsub * G.NT * cmax, tc = 32;
+            while (tc < cols) tc <<= 1;
+            G.col_sub = G.nsub == 2 ? tc / 2 : 0;
+            if (tc > 512) { ok = false; break; }
+            G.tmem_cols = tc;
+            G.m_w = bpptc::fdiv_magic((uint32_t)G.w);
+            G.m_w2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.w2));
+            G.m_hw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.h2 * G.w2));
+            G.m_php2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.h2 * G.w2));
+            G.m_flat = bpptc::fdiv_magic((uint32_t)P.flat);
+            G.dbg_serial = getenv("BPP_GR_SERIAL") ? atoi(getenv("BPP_GR_SERIAL")) : 0;
+            if (getenv("BPP_TC_VERBOSE"))
+                fprintf(stderr, "bpp_net: grid-row stage %d: %dx%d, J = %d, tile stride %d, %d group(s) per CTA, %d TMEM columns, "
+                        "%d B shared memory (weights %d)\n", s, G.h, G.w, G.J, G.TS, G.nsub, G.tmem_cols, G.smem_bytes, G.w_bytes);
+        }
+        n->gr_elems = goff;
+        if (ok) {
+            const size_t x1 = (size_t)max_batch * 2 * P.hs[1] * P.ws[1] * 16, x2 = (size_t)max_batch * 4 * P.hs[2] * P.ws[2] * 16,
+                         x3 = (size_t)max_batch * 4 * P.hs[3] * P.ws[3] * 16;
+            ok = cudaMalloc(&n->d_wts_gr, (size_t)goff * 2) == cudaSuccess && cudaMalloc(&n->d_g[0], x1) == cudaSuccess &&
+                 cudaMalloc(&n->d_g[1], x2) == cudaSuccess && cudaMalloc(&n->d_g[2], x3) == cudaSuccess &&
+                 cudaFuncSetAttribute(bppgr::k_net_gr<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->Gr[0].smem_bytes) == cudaSuccess &&
+                 cudaFuncSetAttribute(bppgr::k_net_gr<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->Gr[1].smem_bytes) == cudaSuccess &&
+                 cudaFuncSetAttribute(bppgr::k_net_gr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->Gr[2].smem_bytes) == cudaSuccess &&
+                 cudaFuncSetAttribute(bppgr::k_net_gr<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->Gr[3].smem_bytes) == cudaSuccess;
+            if (!ok) cudaGetLastError();
+        }
+        n->gr_ok = ok;
+    }
     if (cudaMalloc(&n->d_prof, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(n->d_prof, 0, 32 * sizeof(long long));
     *out = n;
     return BPP_OK;
@@ -1472,6 +1565,8 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     cudaFree(n->d_bias);
     cudaFree(n->d_x1);
     cudaFree(n->d_x2);
+    cudaFree(n->d_wts_gr);
+    for (int i = 0; i < 3; ++i) cudaFree(n->d_g[i]);
     delete n;
     return BPP_OK;
 }
@@ -1552,6 +1647,34 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
                             }
             ++li;
         }
+    // conv weights for the grid-row kernels: per layer [dx][kc][k-half][dy * cout + co][8 cin] - the three vertical taps of
+    // one horizontal tap are the N axis of one UMMA B operand (bpp_net_gr.cuh)
+    std::vector<uint16_t> wg;
+    if (n->gr_ok) {
+        wg.assign((size_t)n->gr_elems, 0);
+        for (int s = 0; s < 4; ++s) {
+            const bppgr::GrStage& G = n->Gr[s];
+            const int first = s == 0 ? 0 : 5 * (s - 1) + 1;
+            for (int l = 0; l < G.nlay; ++l) {
+                const ConvDesc& d = P.conv[first + l];
+                const int sq = (first + l) / 5, k = (first + l) % 5;
+                const std::vector<float>& src = n->host["conv_seqs." + std::to_string(sq) + "." + kSeqConvNames[k] + ".weight"];  // OIHW
+                const int c16 = G.cin16[l];
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int kc = 0; kc < c16; ++kc)
+                        for (int kh = 0; kh < 2; ++kh)
+                            for (int dy = 0; dy < 3; ++dy)
+                                for (int co = 0; co < d.co; ++co)
+                                    for (int j = 0; j < 8; ++j) {
+                                        const int ci = kc * 16 + kh * 8 + j;
+                                        const float v = ci < d.ci ? src[((size_t)co * d.ci + ci) * 9 + dy * 3 + dx] : 0.f;
+                                        const size_t ui = (size_t)G.w_goff[l] +
+                                                          ((((size_t)dx * c16 + kc) * 2 + kh) * (3 * d.co) + dy * d.co + co) * 8 + j;
+                                        wg[ui] = f32_to_bf16_rne(v);
+                                    }
+            }
+        }
+    }
     // every upload below is queued on the caller's stream (a forward or a captured graph still in flight on that stream is
     // ordered before it) and the staging vectors live until the cudaStreamSynchronize at the end
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1612,6 +1735,8 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
         for (int o = 0; o < P.A; ++o)
             for (int i = 0; i < HIDDEN; ++i) wlp[(size_t)i * n->T.A_pad + o] = f32_to_bf16_rne(src2[(size_t)o * HIDDEN + i]);
     }
+    if (n->gr_ok && cudaMemcpyAsync(n->d_wts_gr, wg.data(), wg.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return nerr(BPP_E_CUDA, "grid-row weight upload failed");
     if (cudaMemcpyAsync(n->d_wts_logits_pad, wlp.data(), wlp.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts_umma, wu.data(), wu.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts_umma_lo, wul.data(), wul.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -1635,9 +1760,10 @@ extern "C" int bpp_net_profile(bpp_net* n, int64_t cycles_host[8]) {
     for (int i = 0; i < 8; ++i) cycles_host[i] = roles ? all[i] + all[8 + i] + all[16 + i] : all[i];
     return BPP_OK;
 }
-extern "C" int bpp_net_profile_roles(bpp_net* n, int64_t cycles_host[24]) {
+extern "C" int bpp_net_grid_row(bpp_net* n) { return n && n->gr_ok ? 1 : 0; }
+extern "C" int bpp_net_profile_roles(bpp_net* n, int64_t cycles_host[32]) {
     if (!n || !cycles_host || !n->d_prof) return nerr(BPP_E_INVALID, "null argument");
-    if (cudaMemcpy(cycles_host, n->d_prof, 24 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (cudaMemcpy(cycles_host, n->d_prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
         return nerr(BPP_E_CUDA, "profile copy failed");
     return BPP_OK;
 }
@@ -1696,6 +1822,30 @@ static int launch_roles(bpp_net* n, int x3, int B, const int32_t* count_dev, con
     return BPP_OK;
 }
 
+
+// grid-row trunk: four level kernels chained by programmatic launches (bpp_net_gr.cuh)
+static int launch_gr(bpp_net* n, int B, const int32_t* count_dev, const uint32_t* recs_dev, const int32_t* game_dev,
+                     const int32_t* items_wh_dev, cudaStream_t st) {
+    cudaError_t ce = cudaSuccess;
+    for (int s = 0; s < 4 && ce == cudaSuccess; ++s) {
+        const bppgr::GrStage& G = n->Gr[s];
+        const int groups = (B + G.J - 1) / G.J;
+        const int gr = std::max(1, std::min((groups + G.nsub - 1) / G.nsub, n->num_sms));
+        const uint4* xin = s == 0 ? nullptr : n->d_g[s - 1];
+        uint4* xout = s < 3 ? n->d_g[s] : nullptr;
+#define GR_LAUNCH(SQ)                                                                                                      \
+    ce = launch_pdl(bppgr::k_net_gr<SQ>, gr, G.nsub * bppgr::SUB_THREADS, (size_t)G.smem_bytes, st, n->P, G, B, count_dev, \
+                    recs_dev, game_dev, items_wh_dev, xin, xout, n->d_feat, (const __nv_bfloat16*)n->d_wts_gr, n->d_prof)
+        if (s == 0) GR_LAUNCH(0);
+        else if (s == 1) GR_LAUNCH(1);
+        else if (s == 2) GR_LAUNCH(2);
+        else GR_LAUNCH(3);
+#undef GR_LAUNCH
+    }
+    if (ce != cudaSuccess) return nerr(BPP_E_CUDA, std::string("grid-row kernel launch failed: ") + cudaGetErrorString(ce));
+    return BPP_OK;
+}
+
 extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, const uint32_t* recs_dev,
                                const int32_t* game_dev, const int32_t* items_wh_dev, float* policy_out_dev,
                                float* value_out_dev, void* stream) {
@@ -1711,7 +1861,10 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int cap = n->num_sms * n->ctas_per_sm;
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
-        if (fo && n->roles_ok[0] && B >= n->roles_min_batch) {
+        if (fo && n->gr_ok) {
+            int rc = launch_gr(n, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
+            if (rc) return rc;
+        } else if (fo && n->roles_ok[0] && B >= n->roles_min_batch) {
             int rc = launch_roles(n, 0, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
             if (rc) return rc;
         } else if (fo && n->ctas_per_sm == 2)

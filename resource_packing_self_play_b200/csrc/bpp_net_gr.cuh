@@ -1,0 +1,554 @@
+// bpp_net_gr.cuh — "grid-row" tcgen05 trunk of the policy/value network (sm_100a).  Included by bpp_net.cu inside its
+// anonymous namespace, after NetParams.
+//
+// Why a second formulation.  With both operands in shared memory a tcgen05.mma of M = 128, K = 16 costs the fetch of its
+// 4 KB A operand (~40 cycles) however few output channels it feeds (profiles/r01_umma_probe.txt): with N = Cout = 16 / 32
+// the tensor pipe does math 20 % / 40 % of the time, and a 3x3 convolution as nine shifted N = Cout MMAs per 16 input
+// channels is bound by 89 x 40 cycles per leaf.  The only way to feed more columns per A fetch in this network is to
+// stack kernel taps along N - and a stacked tap has to be un-shifted again when the accumulators are read.  A shift along
+// the pixel ROW axis is a shift across TMEM lanes (impossible without going through shared memory); this layout makes the
+// vertical shift a shift across accumulator COLUMN blocks instead, which costs nothing:
+//
+//   * row axis of a level = [grid row y][leaf j][padded column xp], xp = 0 being the zero halo column shared by
+//     neighbouring leaves; one 128-row MMA tile = grid row y of the J leaves of a group (J*(w+1) <= 128: 8 leaves at 15x15,
+//     14 at 8x8, 25 at 4x4, 42 at 2x2 - hence one kernel per level, each with its own group size);
+//   * for INPUT tile t the three vertical taps are stacked along N: B = [W(dy=0,dx) | W(dy=1,dx) | W(dy=2,dx)], N = 3*Cout,
+//     accumulated over dx (A shifted by dx-1 rows, i.e. only the descriptor's start address moves) and the input-channel
+//     chunks; block dy belongs to OUTPUT tile t+1-dy.  Output tile Y owns TMEM columns base + (NT-1-Y)*Cout, so the three
+//     blocks of one MMA land in three consecutive column blocks = three consecutive output tiles, on the SAME lanes;
+//   * 3*cin16 (+1, see below) MMAs of N = 48 / 96 per tile instead of 9*cin16 of N = 16 / 32: ~2.3x fewer tensor cycles.
+//     The first MMA of a tile is split (its dy = 0 block opens a fresh output tile and must overwrite, the other two
+//     accumulate);
+//   * an input tile is read by ITS OWN MMAs only, so every layer runs IN PLACE: the epilogue of output tile Y (which waits
+//     for the MMAs of input tile Y+1) overwrites input tile Y.  A residual block needs two buffers (raw stream, relu'd
+//     activations) instead of three plus a pooling buffer; halo rows are never written and stay zero for the whole kernel;
+//   * the CTA is persistent, all weights of its level stay in shared memory (one bulk async copy per layer at kernel start),
+//     and the layers of a group are chained by per-tile mbarriers instead of CTA-wide barriers: the issuer starts layer l+1
+//     on tile t as soon as the epilogue warps have stored tiles <= t+1 of layer l, so the tensor pipe does not drain
+//     between layers;
+//   * a CTA runs up to two independent groups ("subs": 8 epilogue warps + 1 issuer warp each) that share the weights and
+//     split the 512 TMEM columns - one sub's epilogue / input / pooling phases overlap the other's MMAs.
+//
+// Stages: 0 = input planes from the compact records -> conv -> max-pool -> x1;  1 = x1 -> two residual blocks -> conv ->
+// max-pool -> x2;  2 = the same one level down -> x3;  3 = x3 -> two residual blocks -> relu(flatten) -> feat (the FC heads
+// run in k_net_heads_tc).  Hand-over layout: [leaf][plane of 8 channels][pixel] 16-byte units, interior pixels only
+// (BinpackingNNet.py:29-48,72-81).
+#pragma once
+
+namespace bppgr {
+using namespace bpptc;
+
+constexpr int SUB_THREADS = 288;   // 8 epilogue warps + 1 issuer warp
+constexpr int MAX_TILES = 28;      // grid rows of a level (H <= 28)
+constexpr int G0 = 8;              // zero guard rows in front of tile 0 (the dx = 0 window starts one row early)
+constexpr int MAX_LAY = 5;
+
+struct GrStage {
+    int h, w, wp, J, TS, NT, RT;   // level geometry, leaves per group, tile stride (rows), tiles (= h), rows per plane
+    int arena_planes;              // 8-channel planes per sub arena
+    int cp;                        // planes of the residual stream (= input channels / 8)
+    int h2, w2;                    // pooled geometry (stages 0..2)
+    int nsub, tmem_cols, col_sub;  // groups in flight per CTA, TMEM columns allocated, column offset of sub 1
+    int nlay;                      // conv layers of the stage; the LAST one of stages 0..2 is the sequence's first conv
+    int cin16[MAX_LAY], cout[MAX_LAY];
+    int w_soff[MAX_LAY];           // byte offset of each layer's weights in the shared weight block
+    int w_len[MAX_LAY];            // bytes
+    long long w_goff[MAX_LAY];     // element offset in the grid-row weight buffer
+    int b_goff[MAX_LAY];           // offset of the layer's bias in NetParams::bias
+    int w_bytes;                   // shared weight block
+    int arena_off, arena_bytes, smem_bytes;
+    uint32_t m_w, m_w2, m_hw2, m_php2, m_flat;   // fdiv magics: w, w2, h2*w2, planes_out*h2*w2, flat
+    int planes_out;                // planes of the pooled hand-over (stages 0..2)
+    int dbg_serial;                // experiments: 1 = drain the tensor pipe after every tile, 2 = after every MMA
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one bulk asynchronous copy global -> shared (TMA engine, no tensor map), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void sub_sync(int sub) {   // named barrier of one sub's 288 threads
+    asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(SUB_THREADS) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
+    if (NC == 8) tmem_ld8(taddr, v);
+    else tmem_ld16(taddr, v);
+}
+
+__host__ __device__ constexpr uint32_t gr_idesc(int n) {   // kind::f16: D = f32, A = B = bf16, K-major, M = 128, N = n
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// All MMAs of one layer, issued by one thread: straight-line code per tile (the issuing thread's own instruction stream is
+// what bounds the MMA rate of these small tiles: branches and address arithmetic per MMA cost more than the MMA).
+//   alo0 = descriptor low word of tile 0's dx = 0 window (it starts one row before the tile); wlo = descriptor low word of the
+//   layer's weights [dx][kc][k-half][3*COUT rows]; both advance in 16-byte units.  Input tile t feeds output tiles t+1, t,
+//   t-1 (column blocks c_next, +COUT, +2*COUT); its first MMA is split because the dy = 0 block OPENS output tile t+1.
+template <int CIN16, int COUT>
+__device__ __forceinline__ void issue_layer(uint32_t alo0, uint32_t ahi, uint32_t a_kc, uint32_t TS, uint32_t wlo, uint32_t bhi,
+                                            int NT, uint32_t cbase, uint32_t full, uint32_t ready, uint32_t rpar,
+                                            bool wait_ready) {
+    constexpr uint32_t id1 = gr_idesc(COUT), id2 = gr_idesc(2 * COUT), id3 = gr_idesc(3 * COUT);
+    constexpr uint32_t blk = 6u * COUT;   // 16-byte units of one (dx, kc) block: 2 K halves x 3*COUT rows
+    for (int t = 0; t < NT; ++t) {
+        if (wait_ready && t + 1 < NT) {
+            mbar_wait(ready + 8u * (uint32_t)(t + 1), rpar);   // data of tile t (and t-1, t), columns of t+1 drained
+            tc_fence_after();
+        }
+        const uint32_t alo = alo0 + (uint32_t)t * TS;
+        const uint32_t c_next = cbase + (uint32_t)(NT - 2 - t) * COUT;   // columns of output tile t+1; tile t follows
+        if (NT == 1) {
+#pragma unroll
+            for (int i = 0; i < 3 * CIN16; ++i)
+                umma_bf16_lh(cbase, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + COUT, bhi, id1, i ? 1u : 0u);
+        } else if (t == 0) {          // output tiles 1 and 0 open
+#pragma unroll
+            for (int i = 0; i < 3 * CIN16; ++i)
+                umma_bf16_lh(c_next, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id2, i ? 1u : 0u);
+        } else if (t == NT - 1) {     // no tile below: dy = 1, 2 only
+#pragma unroll
+            for (int i = 0; i < 3 * CIN16; ++i)
+                umma_bf16_lh(cbase, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + COUT, bhi, id2, 1u);
+        } else {
+            umma_bf16_lh(c_next, alo, ahi, wlo, bhi, id1, 0u);                        // dy = 0 opens output tile t+1
+            umma_bf16_lh(c_next + COUT, alo, ahi, wlo + COUT, bhi, id2, 1u);          // dy = 1, 2 accumulate onto t, t-1
+#pragma unroll
+            for (int i = 1; i < 3 * CIN16; ++i)
+                umma_bf16_lh(c_next, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id3, 1u);
+        }
+        umma_commit(full + 8u * (uint32_t)t);
+    }
+}
+
+enum { GR_CONV = 0, GR_RES0 = 1, GR_RES1 = 2 };
+
+// TMEM loads without the wait: the registers may be read only behind tmem_wait_dep on the same registers
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// tcgen05.wait::ld with the loaded registers as in/out operands, so that no use of them is scheduled in front of the wait
+__device__ __forceinline__ void tmem_wait_dep8(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ld_nw(uint32_t taddr, uint32_t* r) {
+    if (NC == 8) tmem_ld8_nw(taddr, r);
+    else tmem_ld16_nw(taddr, r);
+}
+template <int NC>
+__device__ __forceinline__ void tmem_wait_dep(uint32_t* r) {
+    tmem_wait_dep8(r);
+    if (NC == 16) tmem_wait_dep8(r + 8);
+}
+
+// Epilogue of one (tile, column part) unit of a thread: NC accumulator columns = NC/8 planes of its pixel row.
+//   GR_CONV: out <- bf16(acc + bias)
+//   GR_RES0: out <- relu(bf16(acc + bias))                                  (in place over the layer's input)
+//   GR_RES1: v = acc + bias + raw; raw <- bf16(v); out <- relu(bf16(v))
+template <int NC, int KIND>
+__device__ __forceinline__ void epi_unit(const uint32_t* acc, const float* bias_s, unsigned char* out, unsigned char* raw,
+                                         uint32_t PS) {
+    float v[NC];
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s);
+#pragma unroll
+    for (int i = 0; i < NC / 4; ++i) {
+        const float4 bb = b4[i];
+        v[4 * i] = __uint_as_float(acc[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bb.y;
+        v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bb.w;
+    }
+#pragma unroll
+    for (int p = 0; p < NC / 8; ++p) {
+        float* u = v + 8 * p;
+        uint4 o;
+        if (KIND == GR_RES1) {
+            uint4* rp = reinterpret_cast<uint4*>(raw + (size_t)p * PS);
+            const uint4 rv = *rp;
+            u[0] += bf16_lo(rv.x); u[1] += bf16_hi(rv.x); u[2] += bf16_lo(rv.y); u[3] += bf16_hi(rv.y);
+            u[4] += bf16_lo(rv.z); u[5] += bf16_hi(rv.z); u[6] += bf16_lo(rv.w); u[7] += bf16_hi(rv.w);
+            o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
+            *rp = o;
+        } else {
+            o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
+        }
+        if (KIND != GR_CONV) o = make_uint4(relu_bf16x2(o.x), relu_bf16x2(o.y), relu_bf16x2(o.z), relu_bf16x2(o.w));
+        *reinterpret_cast<uint4*>(out + (size_t)p * PS) = o;
+    }
+}
+
+// All epilogue units of one layer for this warp, in batches of TB tiles: one wait for the batch's last tile, the TMEM loads of
+// the whole batch in flight together, ONE cross-proxy fence per batch (it costs several hundred cycles), then one arrival
+// per tile on the tiles' "ready" barriers.  `publish` = a later layer reads the stores through the tensor core's proxy.
+#ifdef BPP_GR_PROF
+#define GR_T(slot) do { if (tprof) { const long long _t = clock64(); tprof[slot] += _t - tq; tq = _t; } } while (0)
+#else
+#define GR_T(slot) do { } while (0)
+#endif
+template <int NC, int KIND, int TB>
+__device__ __forceinline__ void epi_layer(const GrStage& S, uint32_t tmem_sub, uint32_t full, uint32_t ready, uint32_t par,
+                                          uint32_t cout, const float* bias_s, bool interior, int r, int quarter, int half,
+                                          unsigned char* out_base, unsigned char* raw_base, int lane, bool publish,
+                                          long long* tprof) {
+    const uint32_t PS = (uint32_t)S.RT * 16u;
+    const int NT = S.NT;
+    const uint32_t tbase = tmem_sub + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * NC);
+    const size_t rowb0 = (size_t)(G0 + r) * 16 + (size_t)(half * (NC / 8)) * PS;
+#ifdef BPP_GR_PROF
+    long long tq = tprof ? clock64() : 0;
+#endif
+    for (int T0 = 0; T0 < NT; T0 += TB) {
+        const int nb = min(TB, NT - T0);
+        const int fb = min(T0 + nb, NT - 1);   // the MMAs of input tile T+1 complete output tile T
+        mbar_wait(full + 8u * (uint32_t)fb, par);
+        tc_fence_after();
+        GR_T(0);
+        uint32_t acc[TB][NC];
+#pragma unroll
+        for (int b = 0; b < TB; ++b)
+            if (b < nb) tmem_ld_nw<NC>(tbase + (uint32_t)(NT - 1 - T0 - b) * cout, acc[b]);   // warp-collective
+#pragma unroll
+        for (int b = 0; b < TB; ++b)
+            if (b < nb) {
+                tmem_wait_dep<NC>(acc[b]);
+                if (b == 0) GR_T(1);
+                if (interior) {
+                    const size_t rowb = rowb0 + (size_t)((T0 + b) * S.TS) * 16;
+                    epi_unit<NC, KIND>(acc[b], bias_s + half * NC, out_base + rowb, raw_base + rowb, PS);
+                }
+            }
+        GR_T(2);
+        if (publish) fence_proxy_async();   // this thread's stores -> visible to the tensor core's reads of the next layer
+        GR_T(3);
+        tc_fence_before();                  // its TMEM reads are ordered before the MMAs that will overwrite the columns
+        __syncwarp();
+        if (lane == 0)
+            for (int b = 0; b < nb; ++b) mbar_arrive(ready + 8u * (uint32_t)(T0 + b));
+        GR_T(4);
+    }
+}
+
+template <int STAGE>
+__global__ void __launch_bounds__(2 * SUB_THREADS, 1)
+k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev, const uint32_t* __restrict__ recs,
+         const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh, const uint4* __restrict__ xin,
+         uint4* __restrict__ xout, __nv_bfloat16* __restrict__ feat_out, const __nv_bfloat16* __restrict__ wts_gr,
+         long long* prof) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_full[2][MAX_TILES];
+    __shared__ __align__(8) uint64_t s_ready[2][MAX_TILES];
+    __shared__ __align__(8) uint64_t s_wbar;
+    __shared__ __align__(8) uint64_t s_dbar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ long long s_tprof[8];
+    __shared__ uint16_t s_rowmap[128];   // row r of a tile -> leaf j | xp << 8 (0xffff: not a pixel row)
+    __shared__ uint32_t s_rec[STAGE == 0 ? 2 : 1][STAGE == 0 ? 8 : 1][32];
+    __shared__ uint32_t s_msk[STAGE == 0 ? 2 : 1][STAGE == 0 ? 8 : 1][2][32];   // [sub][leaf][rows | columns][index]
+    __shared__ uint4 s_lut[STAGE == 0 ? 256 : 1];                                 // 8 channel bits -> 8 x bf16 {0, 1}
+    const int tid = threadIdx.x;
+    const int sub = tid >= SUB_THREADS ? 1 : 0;
+    const int st = tid - sub * SUB_THREADS;          // thread inside the sub
+    const int warp_s = st >> 5, lane = tid & 31;
+    const int nthreads = S.nsub * SUB_THREADS;
+    float* s_bias = reinterpret_cast<float*>(smem + S.w_bytes);   // [nlay][32]
+    unsigned char* arena = smem + S.arena_off + (size_t)sub * S.arena_bytes;
+    const uint32_t PS = (uint32_t)S.RT * 16u;
+
+    if (tid < 2 * MAX_TILES) {
+        mbar_init(smem_u32(&s_full[0][0]) + 8u * (uint32_t)tid, 1);
+        mbar_init(smem_u32(&s_ready[0][0]) + 8u * (uint32_t)tid, 8);
+    }
+    if (tid == 0) { mbar_init(smem_u32(&s_wbar), 1); mbar_init(smem_u32(&s_dbar[0]), 1); mbar_init(smem_u32(&s_dbar[1]), 1); }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)S.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid < 128) {
+        const int j = tid / S.wp, xp = tid - j * S.wp;
+        s_rowmap[tid] = (tid < S.J * S.wp && xp != 0) ? (uint16_t)(j | (xp << 8)) : (uint16_t)0xffff;
+    }
+    if (STAGE == 0 && tid < 256) {
+        const uint32_t b8 = (uint32_t)tid;
+        uint4 v;
+        v.x = ((b8 & 1u) | ((b8 & 2u) << 15)) * 0x3f80u;          // bf16 1.0 pairs
+        v.y = (((b8 >> 2) & 1u) | ((b8 & 8u) << 13)) * 0x3f80u;
+        v.z = (((b8 >> 4) & 1u) | ((b8 & 32u) << 11)) * 0x3f80u;
+        v.w = (((b8 >> 6) & 1u) | ((b8 & 128u) << 9)) * 0x3f80u;
+        s_lut[tid] = v;
+    }
+    // halo rows, guards and padding rows are zero from here on: no epilogue, input or hand-over pass ever writes them
+    {
+        uint4* q = reinterpret_cast<uint4*>(smem + S.arena_off);
+        const int n16 = S.nsub * S.arena_bytes / 16;
+        for (int i = tid; i < n16; i += nthreads) q[i] = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < S.nlay * 32; i += nthreads) {
+        const int l = i >> 5, c = i & 31;
+        s_bias[i] = c < S.cout[l] ? P.bias[S.b_goff[l] + c] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {   // the stage's weights stay resident: one bulk async copy per layer
+        const uint32_t wb = smem_u32(&s_wbar);
+        mbar_expect_tx(wb, (uint32_t)S.w_bytes);
+        for (int l = 0; l < S.nlay; ++l)
+            bulk_g2s(smem_u32(smem + S.w_soff[l]), wts_gr + S.w_goff[l], (uint32_t)S.w_len[l], wb);
+    }
+    // everything above is independent of the kernel that produced this stage's input
+    pdl_launch_dependents();
+    pdl_wait();
+    mbar_wait(smem_u32(&s_wbar), 0);
+    const long long t_start = clock64();
+    long long t_in = 0, t_cv = 0, t_out = 0;
+
+    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
+    const int nwork = gridDim.x * S.nsub, wid = blockIdx.x * S.nsub + sub;
+    const int slice_lo = (int)(((long long)wid * B) / nwork);
+    const int slice_hi = (int)(((long long)(wid + 1) * B) / nwork);
+    const int n_slice = slice_hi - slice_lo;
+    const int n_groups = (n_slice + S.J - 1) / S.J;
+    const int gsz = n_groups > 0 ? (n_slice + n_groups - 1) / n_groups : S.J;
+
+    const uint32_t tmem_sub = s_tmem + (uint32_t)(sub * S.col_sub);
+    const uint32_t full = smem_u32(&s_full[sub][0]), ready = smem_u32(&s_ready[sub][0]);
+    const int NT = S.NT;
+    // epilogue warps: this thread's pixel row inside every tile
+    // a warp reads the TMEM lane quarter of its CTA-wide warp index (sub 1 starts at warp 9): the eight epilogue warps of a
+    // sub cover every (quarter, half) pair once either way
+    const int quarter = (tid >> 5) & 3, half = (warp_s >> 2) & 1;
+    const int r = quarter * 32 + lane;
+    const uint32_t rm = s_rowmap[r];
+    const int my_j = (int)(rm & 0xff);
+    uint32_t lc = 0;   // layers this sub has run (parity of its barriers)
+    uint32_t dpar = 0;
+    const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long* tprof = profiling ? s_tprof : nullptr;
+    if (profiling) for (int i = 0; i < 8; ++i) s_tprof[i] = 0;
+
+    if (sub < S.nsub)
+    for (int b0 = slice_lo; b0 < slice_hi; b0 += gsz) {
+        const int nvalid = min(gsz, slice_hi - b0);
+        long long tq = profiling ? clock64() : 0;
+        // ---------------------------------------------------------------------------------------------------- input
+        if (STAGE == 0) {
+            // input planes (getBinItem, BinPackingGame.py:118-120): channel 0 = bin occupancy, channel i+1 = item i's
+            // [0:h, 0:w] block while it is still to be placed.  Per leaf two small tables - items still to place that reach
+            // grid row y, items that reach column x - make a pixel's channel bits one AND; an 8-channel plane entry (bf16 0/1)
+            // comes from a 256-entry table.
+            for (int i = st; i < nvalid * 32; i += SUB_THREADS) s_rec[sub][i >> 5][i & 31] = recs[(size_t)(b0 + (i >> 5)) * 32 + (i & 31)];
+            for (int i = st; i < nvalid * 64; i += SUB_THREADS) {
+                const int j = i >> 6, k = i & 31, isx = (i >> 5) & 1;   // k = grid row y (isx = 0) or column x (isx = 1)
+                const int b = b0 + j;
+                const int g = game ? game[b] : b;
+                const uint32_t rem = recs[(size_t)b * 32 + BPP_REC_REM];
+                const int32_t* it = items_wh + (size_t)g * P.N * 2;
+                uint32_t m = 0;
+                for (int q = 0; q < P.N; ++q)
+                    if (((rem >> q) & 1u) && k < __ldg(it + 2 * q + (isx ? 0 : 1))) m |= 2u << q;
+                s_msk[sub][j][isx][k] = m;
+            }
+            sub_sync(sub);
+            const int nplanes = S.cp;
+            for (int idx = st; idx < NT * 128; idx += SUB_THREADS) {
+                const int t = idx >> 7;
+                const uint32_t m = s_rowmap[idx & 127];
+                const int j = (int)(m & 0xff);
+                if (m == 0xffffu || j >= nvalid) continue;
+                const int x = (int)(m >> 8) - 1;
+                const uint32_t bits = ((s_rec[sub][j][t] >> x) & 1u) | (s_msk[sub][j][0][t] & s_msk[sub][j][1][x]);
+                uint4* dst = reinterpret_cast<uint4*>(arena) + (G0 + t * S.TS + (idx & 127));
+                for (int p = 0; p < nplanes; ++p) dst[(size_t)p * S.RT] = s_lut[(bits >> (8 * p)) & 0xffu];
+            }
+        } else {
+            // the previous stage's residual stream [leaf][plane][pixel] -> raw planes, relu(raw) -> activation planes; the
+            // loads of LR rows are in flight together
+            const int hw = S.h * S.w;
+            constexpr int CPX = STAGE == 1 ? 2 : 4, LR = STAGE == 1 ? 2 : 1;
+            for (int i0 = st; i0 < NT * 128; i0 += LR * SUB_THREADS) {
+                uint4 v[LR][CPX];
+                uint4* dst[LR];
+#pragma unroll
+                for (int k = 0; k < LR; ++k) {
+                    const int idx = i0 + k * SUB_THREADS;
+                    dst[k] = nullptr;
+                    if (idx < NT * 128) {
+                        const int t = idx >> 7;
+                        const uint32_t m = s_rowmap[idx & 127];
+                        const int j = (int)(m & 0xff);
+                        if (m != 0xffffu && j < nvalid) {
+                            const uint4* src = xin + (size_t)(b0 + j) * CPX * hw + t * S.w + ((int)(m >> 8) - 1);
+                            dst[k] = reinterpret_cast<uint4*>(arena) + (G0 + t * S.TS + (idx & 127));
+#pragma unroll
+                            for (int p = 0; p < CPX; ++p) v[k][p] = __ldg(src + (size_t)p * hw);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < LR; ++k)
+                    if (dst[k]) {
+#pragma unroll
+                        for (int p = 0; p < CPX; ++p) {
+                            dst[k][(size_t)p * S.RT] = v[k][p];
+                            dst[k][(size_t)(CPX + p) * S.RT] = make_uint4(relu_bf16x2(v[k][p].x), relu_bf16x2(v[k][p].y),
+                                                                          relu_bf16x2(v[k][p].z), relu_bf16x2(v[k][p].w));
+                        }
+                    }
+            }
+        }
+        fence_proxy_async();
+        sub_sync(sub);
+        if (profiling) { const long long t_ = clock64(); t_in += t_ - tq; tq = t_; }
+        // --------------------------------------------------------------------------------------------------- layers
+        const int nres = STAGE == 0 ? 0 : 4;
+        const bool has_conv = STAGE != 3;
+        if (warp_s == 8) {
+            if (elect_one()) {
+                tc_fence_after();
+                const uint32_t ahi = (uint32_t)(umma_desc(0, (uint32_t)S.RT, 8u) >> 32);
+                const uint32_t a_lbo = ((uint32_t)S.RT & 0x3fffu) << 16;
+                const uint32_t arena_a = smem_u32(arena);
+                uint32_t lcl = lc;
+                for (int l = 0; l < nres + (has_conv ? 1 : 0); ++l, ++lcl) {
+                    const bool conv = l == nres;
+                    // residual layers read the activation planes, the sequence's first conv the raw stream (stage 0: input)
+                    const uint32_t abase = arena_a + ((conv || STAGE == 0) ? 0u : (uint32_t)S.cp * PS);
+                    const uint32_t alo0 = (((abase + (uint32_t)(G0 - 1) * 16u) >> 4) & 0x3fffu) | a_lbo;
+                    const uint64_t bd = umma_desc(smem_u32(smem + S.w_soff[l]), 3u * (uint32_t)S.cout[l], 8u);
+                    const uint32_t wlo = (uint32_t)bd, bhi = (uint32_t)(bd >> 32);
+                    const uint32_t a_kc = 2u * (uint32_t)S.RT;
+                    const uint32_t rpar = (lcl - 1u) & 1u;
+                    if (l > 0) {
+                        if (conv) {   // other column map: every tile of the last residual layer must have been drained
+                            for (int t = 0; t < NT; ++t) mbar_wait(ready + 8u * (uint32_t)t, rpar);
+                        } else mbar_wait(ready, rpar);
+                        tc_fence_after();
+                    }
+                    const bool wr = l > 0 && !conv;
+                    if (STAGE == 0) {
+                        if (S.cin16[0] == 1) issue_layer<1, 16>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                        else issue_layer<2, 16>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                    } else if (STAGE == 1) {
+                        if (!conv) issue_layer<1, 16>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                        else issue_layer<1, 32>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                    } else issue_layer<2, 32>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                }
+            }
+            __syncwarp();
+        } else {
+            const bool interior = rm != 0xffffu && my_j < nvalid;
+            unsigned char* raw_b = arena;
+            unsigned char* act_b = arena + (size_t)S.cp * PS;
+            uint32_t lcl = lc;
+            if (STAGE == 0) {
+                epi_layer<8, GR_CONV, 2>(S, tmem_sub, full, ready, lcl & 1u, 16u, s_bias, interior, r, quarter, half, raw_b, raw_b, lane, false, tprof);
+            } else if (STAGE == 1) {
+                for (int blk = 0; blk < 2; ++blk) {
+                    epi_layer<8, GR_RES0, 2>(S, tmem_sub, full, ready, lcl & 1u, 16u, s_bias + 32 * (2 * blk), interior, r, quarter, half, act_b, raw_b, lane, true, tprof);
+                    ++lcl;
+                    epi_layer<8, GR_RES1, 2>(S, tmem_sub, full, ready, lcl & 1u, 16u, s_bias + 32 * (2 * blk + 1), interior, r, quarter, half, act_b, raw_b, lane, true, tprof);
+                    ++lcl;
+                }
+                epi_layer<16, GR_CONV, 1>(S, tmem_sub, full, ready, lcl & 1u, 32u, s_bias + 32 * 4, interior, r, quarter, half, raw_b, raw_b, lane, false, tprof);
+            } else {
+                for (int blk = 0; blk < 2; ++blk) {
+                    epi_layer<16, GR_RES0, 1>(S, tmem_sub, full, ready, lcl & 1u, 32u, s_bias + 32 * (2 * blk), interior, r, quarter, half, act_b, raw_b, lane, true, tprof);
+                    ++lcl;
+                    epi_layer<16, GR_RES1, 1>(S, tmem_sub, full, ready, lcl & 1u, 32u, s_bias + 32 * (2 * blk + 1), interior, r, quarter, half, act_b, raw_b, lane, STAGE == 2 || blk == 0, tprof);
+                    ++lcl;
+                }
+                if (STAGE == 2)
+                    epi_layer<16, GR_CONV, 1>(S, tmem_sub, full, ready, lcl & 1u, 32u, s_bias + 32 * 4, interior, r, quarter, half, raw_b, raw_b, lane, false, tprof);
+            }
+        }
+        lc += (uint32_t)(nres + (has_conv ? 1 : 0));
+        tc_fence_before();
+        sub_sync(sub);
+        tc_fence_after();
+        if (profiling) { const long long t_ = clock64(); t_cv += t_ - tq; tq = t_; }
+        // --------------------------------------------------------------------------------------------------- output
+        if (STAGE < 3) {
+            // max_pool2d(3, 2, 1) of the conv output T (planes 0.. of the arena, interior rows) -> x[leaf][plane][pixel]
+            const int hw2 = S.h2 * S.w2, per = S.planes_out * hw2;
+            uint4* dst = xout + (size_t)b0 * per;
+            const uint4 ninf = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+            for (int idx = st; idx < nvalid * per; idx += SUB_THREADS) {
+                const int j = fdiv(idx, S.m_php2);
+                int q = idx - j * per;
+                const int p = fdiv(q, S.m_hw2);
+                q -= p * hw2;
+                const int oy = fdiv(q, S.m_w2), ox = q - oy * S.w2;
+                const uint4* src = reinterpret_cast<const uint4*>(arena) + (size_t)p * S.RT + G0 + j * S.wp + 2 * ox;   // xp = 2*ox + dx
+                uint4 m = ninf;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int y = 2 * oy + dy - 1;
+                    if (y < 0 || y >= S.h) continue;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int x = 2 * ox + dx - 1;
+                        if (x < 0 || x >= S.w) continue;
+                        const uint4 v = src[y * S.TS + dx];
+                        m = make_uint4(max_bf16x2(m.x, v.x), max_bf16x2(m.y, v.y), max_bf16x2(m.z, v.z), max_bf16x2(m.w, v.w));
+                    }
+                }
+                dst[idx] = m;
+            }
+        } else {
+            // relu(flatten(x)) as bf16 [B][flat] for the FC heads (flat index = channel * h*w + y*w + x)
+            const int hw = S.h * S.w;
+            const uint32_t m_hw = fdiv_magic((uint32_t)hw);
+            for (int idx = st; idx < nvalid * P.flat; idx += SUB_THREADS) {
+                const int j = fdiv(idx, S.m_flat), f = idx - j * P.flat;
+                const int c = fdiv(f, m_hw), q = f - c * hw;
+                const int y = fdiv(q, S.m_w), x = q - y * S.w;
+                const size_t row = (size_t)G0 + (size_t)y * S.TS + (size_t)j * S.wp + (x + 1);
+                const uint16_t e = *(reinterpret_cast<const uint16_t*>(arena + ((size_t)(c >> 3) * S.RT + row) * 16) + (c & 7));
+                reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (e & 0x8000u) ? (uint16_t)0 : e;
+            }
+        }
+        sub_sync(sub);
+        if (profiling) { const long long t_ = clock64(); t_out += t_ - tq; tq = t_; }
+    }
+    if (profiling) {
+        prof[8 * STAGE + 0] = t_in;
+        prof[8 * STAGE + 1] = t_cv;
+        prof[8 * STAGE + 2] = t_out;
+#ifdef BPP_GR_PROF
+        for (int i = 0; i < 4; ++i) prof[8 * STAGE + 3 + i] = s_tprof[i] + (i == 3 ? s_tprof[4] : 0);
+#endif
+        prof[8 * STAGE + 7] = clock64() - t_start;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"((uint32_t)S.tmem_cols));
+}
+
+}  // namespace bppgr

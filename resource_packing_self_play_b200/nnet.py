@@ -118,10 +118,17 @@ class DeviceNet:
         return {k: int(v) for k, v in zip(keys, arr)}
 
     def profile_roles(self):
-        arr = (C.c_int64 * 24)()
+        arr = (C.c_int64 * 32)()
         call("bpp_net_profile_roles", self._h, arr)
-        keys = ["input", "weights", "mma_issue", "mma_wait", "epilogue", "pool", "output", "total"]
-        return [{k: int(arr[8 * r + i]) for i, k in enumerate(keys)} for r in range(3)]
+        if self.grid_row():   # k_net_gr stages 0..3 (thread 0 of CTA 0): phases of a group, then epilogue-warp waits
+            keys = ["input", "layers", "output", "epi_wait_mma", "epi_tmem_ld", "epi_math_store", "epi_fence_arrive", "total"]
+        else:
+            keys = ["input", "weights", "mma_issue", "mma_wait", "epilogue", "pool", "output", "total"]
+        return [{k: int(arr[8 * r + i]) for i, k in enumerate(keys)} for r in range(4 if self.grid_row() else 3)]
+
+    def grid_row(self):
+        """True when the bf16 mode runs the grid-row stage kernels (bpp_net_gr.cuh)"""
+        return bool(_lib.load().bpp_net_grid_row(self._h))
 
     def load_state_dict(self, state_dict):
         for name, t in state_dict.items():
