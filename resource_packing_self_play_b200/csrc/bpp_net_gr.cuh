@@ -100,8 +100,10 @@ __host__ __device__ constexpr uint32_t gr_idesc(int n) {   // kind::f16: D = f32
 // what bounds the MMA rate of these small tiles: branches and address arithmetic per MMA cost more than the MMA).
 //   alo0 = descriptor low word of tile 0's dx = 0 window (it starts one row before the tile); wlo = descriptor low word of the
 //   layer's weights [dx][kc][k-half][3*COUT rows]; both advance in 16-byte units.  Input tile t feeds output tiles t+1, t,
-//   t-1 (column blocks c_next, +COUT, +2*COUT); its first MMA is split because the dy = 0 block OPENS output tile t+1.
-template <int CIN16, int COUT>
+//   t-1 (column blocks c_next, +COUT, +2*COUT).  PRE: the epilogue warps have pre-loaded every accumulator column with the
+//   layer's bias (tcgen05.st), so all MMAs accumulate; else the first MMA of a tile is split because its dy = 0 block OPENS
+//   output tile t+1 and must overwrite.
+template <int CIN16, int COUT, bool PRE>
 __device__ __forceinline__ void issue_layer(uint32_t alo0, uint32_t ahi, uint32_t a_kc, uint32_t TS, uint32_t wlo, uint32_t bhi,
                                             int NT, uint32_t cbase, uint32_t full, uint32_t ready, uint32_t rpar,
                                             bool wait_ready) {
@@ -117,18 +119,21 @@ __device__ __forceinline__ void issue_layer(uint32_t alo0, uint32_t ahi, uint32_
         if (NT == 1) {
 #pragma unroll
             for (int i = 0; i < 3 * CIN16; ++i)
-                umma_bf16_lh(cbase, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + COUT, bhi, id1, i ? 1u : 0u);
+                umma_bf16_lh(cbase, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + COUT, bhi, id1, (PRE || i) ? 1u : 0u);
         } else if (t == 0) {          // output tiles 1 and 0 open
 #pragma unroll
             for (int i = 0; i < 3 * CIN16; ++i)
-                umma_bf16_lh(c_next, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id2, i ? 1u : 0u);
+                umma_bf16_lh(c_next, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id2, (PRE || i) ? 1u : 0u);
         } else if (t == NT - 1) {     // no tile below: dy = 1, 2 only
 #pragma unroll
             for (int i = 0; i < 3 * CIN16; ++i)
                 umma_bf16_lh(cbase, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + COUT, bhi, id2, 1u);
         } else {
-            umma_bf16_lh(c_next, alo, ahi, wlo, bhi, id1, 0u);                        // dy = 0 opens output tile t+1
-            umma_bf16_lh(c_next + COUT, alo, ahi, wlo + COUT, bhi, id2, 1u);          // dy = 1, 2 accumulate onto t, t-1
+            if (PRE) umma_bf16_lh(c_next, alo, ahi, wlo, bhi, id3, 1u);
+            else {
+                umma_bf16_lh(c_next, alo, ahi, wlo, bhi, id1, 0u);                    // dy = 0 opens output tile t+1
+                umma_bf16_lh(c_next + COUT, alo, ahi, wlo + COUT, bhi, id2, 1u);      // dy = 1, 2 accumulate onto t, t-1
+            }
 #pragma unroll
             for (int i = 1; i < 3 * CIN16; ++i)
                 umma_bf16_lh(c_next, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id3, 1u);
@@ -168,60 +173,103 @@ __device__ __forceinline__ void tmem_wait_dep(uint32_t* r) {
     if (NC == 16) tmem_wait_dep8(r + 8);
 }
 
-// Epilogue of one (tile, column part) unit of a thread: NC accumulator columns = NC/8 planes of its pixel row.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+template <int NC>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* r) {
+    tmem_st8(taddr, r);
+    if (NC == 16) tmem_st8(taddr + 8u, r + 8);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Epilogue of one (tile, column part) unit of a thread: NC accumulator columns = NC/8 planes of its pixel row.  `out`, `raw`
+// = shared-space byte addresses of the row's entry in the first of those planes.  BIAS: the bias is added here (layers whose
+// accumulators were not pre-loaded with it).  Branch-free up to the stores, so that the units of a batch interleave.
 //   GR_CONV: out <- bf16(acc + bias)
 //   GR_RES0: out <- relu(bf16(acc + bias))                                  (in place over the layer's input)
 //   GR_RES1: v = acc + bias + raw; raw <- bf16(v); out <- relu(bf16(v))
-template <int NC, int KIND>
-__device__ __forceinline__ void epi_unit(const uint32_t* acc, const float* bias_s, unsigned char* out, unsigned char* raw,
+template <int NC, int KIND, bool BIAS>
+__device__ __forceinline__ void epi_unit(const uint32_t* acc, const float* bias_s, bool interior, uint32_t out, uint32_t raw,
                                          uint32_t PS) {
     float v[NC];
-    const float4* b4 = reinterpret_cast<const float4*>(bias_s);
+    if (BIAS) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s);
 #pragma unroll
-    for (int i = 0; i < NC / 4; ++i) {
-        const float4 bb = b4[i];
-        v[4 * i] = __uint_as_float(acc[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bb.y;
-        v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bb.w;
+        for (int i = 0; i < NC / 4; ++i) {
+            const float4 bb = b4[i];
+            v[4 * i] = __uint_as_float(acc[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bb.y;
+            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bb.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
     }
 #pragma unroll
     for (int p = 0; p < NC / 8; ++p) {
         float* u = v + 8 * p;
         uint4 o;
         if (KIND == GR_RES1) {
-            uint4* rp = reinterpret_cast<uint4*>(raw + (size_t)p * PS);
-            const uint4 rv = *rp;
+            const uint4 rv = lds128(raw + (uint32_t)p * PS);
             u[0] += bf16_lo(rv.x); u[1] += bf16_hi(rv.x); u[2] += bf16_lo(rv.y); u[3] += bf16_hi(rv.y);
             u[4] += bf16_lo(rv.z); u[5] += bf16_hi(rv.z); u[6] += bf16_lo(rv.w); u[7] += bf16_hi(rv.w);
             o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
-            *rp = o;
+            if (interior) sts128(raw + (uint32_t)p * PS, o);
         } else {
             o = make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
         }
         if (KIND != GR_CONV) o = make_uint4(relu_bf16x2(o.x), relu_bf16x2(o.y), relu_bf16x2(o.z), relu_bf16x2(o.w));
-        *reinterpret_cast<uint4*>(out + (size_t)p * PS) = o;
+        if (interior) sts128(out + (uint32_t)p * PS, o);
     }
 }
 
-// All epilogue units of one layer for this warp, in batches of TB tiles: one wait for the batch's last tile, the TMEM loads of
-// the whole batch in flight together, ONE cross-proxy fence per batch (it costs several hundred cycles), then one arrival
-// per tile on the tiles' "ready" barriers.  `publish` = a later layer reads the stores through the tensor core's proxy.
+// this warp's share of the accumulator columns of all tiles <- the bias of the group's first layer (start of a group)
+template <int NC>
+__device__ __forceinline__ void preload_bias(uint32_t tmem_sub, int NT, uint32_t cout, const float* bias_s, int quarter, int half) {
+    uint32_t bv[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) bv[i] = __float_as_uint(bias_s[half * NC + i]);
+    const uint32_t tbase = tmem_sub + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * NC);
+    for (int T = 0; T < NT; ++T) tmem_st<NC>(tbase + (uint32_t)T * cout, bv);
+    tmem_wait_st();
+    tc_fence_before();
+}
+
 #ifdef BPP_GR_PROF
 #define GR_T(slot) do { if (tprof) { const long long _t = clock64(); tprof[slot] += _t - tq; tq = _t; } } while (0)
 #else
 #define GR_T(slot) do { } while (0)
 #endif
-template <int NC, int KIND, int TB>
-__device__ __forceinline__ void epi_layer(const GrStage& S, uint32_t tmem_sub, uint32_t full, uint32_t ready, uint32_t par,
-                                          uint32_t cout, const float* bias_s, bool interior, int r, int quarter, int half,
-                                          unsigned char* out_base, unsigned char* raw_base, int lane, bool publish,
-                                          long long* tprof) {
-    const uint32_t PS = (uint32_t)S.RT * 16u;
-    const int NT = S.NT;
-    const uint32_t tbase = tmem_sub + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * NC);
-    const size_t rowb0 = (size_t)(G0 + r) * 16 + (size_t)(half * (NC / 8)) * PS;
+// All epilogue units of one layer for this warp, in batches of TB tiles: one wait for the batch's last tile, the TMEM loads of
+// the whole batch in flight together, one cross-proxy fence per batch, then one arrival per tile on the tiles' "ready"
+// barriers.  `publish` = a later layer reads the stores through the tensor core's proxy.  bias_next != nullptr: the drained
+// columns are re-loaded with the NEXT layer's bias (same column map), whose MMAs then only accumulate; BIAS: this layer's
+// accumulators were not pre-loaded, the bias is added here.
+template <int NC, int KIND, int TB, bool BIAS>
+__device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t PS, uint32_t tbase, uint32_t full, uint32_t ready,
+                                          uint32_t par, uint32_t cout, const float* bias_s, const float* bias_next, bool interior,
+                                          uint32_t out0, uint32_t raw0, int lane, bool publish, long long* tprof) {
+    // tbase = TMEM address of this warp's lane quarter and column part in the LAST tile's block (tile T sits (NT-1-T)*cout
+    // columns further); out0 / raw0 = shared addresses of this thread's row in tile 0, first plane of its column part
+    uint32_t bn[NC];
+    if (bias_next) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) bn[i] = __float_as_uint(bias_next[i]);
+    }
 #ifdef BPP_GR_PROF
     long long tq = tprof ? clock64() : 0;
 #endif
+    uint32_t tcol = tbase + (uint32_t)(NT - 1) * cout, orow = out0, rrow = raw0;
     for (int T0 = 0; T0 < NT; T0 += TB) {
         const int nb = min(TB, NT - T0);
         const int fb = min(T0 + nb, NT - 1);   // the MMAs of input tile T+1 complete output tile T
@@ -231,25 +279,30 @@ __device__ __forceinline__ void epi_layer(const GrStage& S, uint32_t tmem_sub, u
         uint32_t acc[TB][NC];
 #pragma unroll
         for (int b = 0; b < TB; ++b)
-            if (b < nb) tmem_ld_nw<NC>(tbase + (uint32_t)(NT - 1 - T0 - b) * cout, acc[b]);   // warp-collective
+            if (b < nb) tmem_ld_nw<NC>(tcol - (uint32_t)b * cout, acc[b]);   // warp-collective
 #pragma unroll
         for (int b = 0; b < TB; ++b)
             if (b < nb) {
                 tmem_wait_dep<NC>(acc[b]);
                 if (b == 0) GR_T(1);
-                if (interior) {
-                    const size_t rowb = rowb0 + (size_t)((T0 + b) * S.TS) * 16;
-                    epi_unit<NC, KIND>(acc[b], bias_s + half * NC, out_base + rowb, raw_base + rowb, PS);
-                }
+                if (bias_next) tmem_st<NC>(tcol - (uint32_t)b * cout, bn);
+                epi_unit<NC, KIND, BIAS>(acc[b], bias_s, interior, orow + (uint32_t)b * tile_bytes, rrow + (uint32_t)b * tile_bytes, PS);
             }
         GR_T(2);
         if (publish) fence_proxy_async();   // this thread's stores -> visible to the tensor core's reads of the next layer
+        if (bias_next) tmem_wait_st();
         GR_T(3);
-        tc_fence_before();                  // its TMEM reads are ordered before the MMAs that will overwrite the columns
+        tc_fence_before();                  // its TMEM accesses are ordered before the MMAs that will use the columns
         __syncwarp();
-        if (lane == 0)
-            for (int b = 0; b < nb; ++b) mbar_arrive(ready + 8u * (uint32_t)(T0 + b));
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < TB; ++b)
+                if (b < nb) mbar_arrive(ready + 8u * (uint32_t)(T0 + b));
+        }
         GR_T(4);
+        tcol -= (uint32_t)TB * cout;
+        orow += (uint32_t)TB * tile_bytes;
+        rrow += (uint32_t)TB * tile_bytes;
     }
 }
 
@@ -422,6 +475,10 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     }
             }
         }
+        if (warp_s < 8) {   // accumulator columns of the group's first layer <- its bias
+            if (STAGE <= 1) preload_bias<8>(tmem_sub, NT, 16u, s_bias, quarter, half);
+            else preload_bias<16>(tmem_sub, NT, 32u, s_bias, quarter, half);
+        }
         fence_proxy_async();
         sub_sync(sub);
         if (profiling) { const long long t_ = clock64(); t_in += t_ - tq; tq = t_; }
@@ -452,39 +509,43 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     }
                     const bool wr = l > 0 && !conv;
                     if (STAGE == 0) {
-                        if (S.cin16[0] == 1) issue_layer<1, 16>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
-                        else issue_layer<2, 16>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                        if (S.cin16[0] == 1) issue_layer<1, 16, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                        else issue_layer<2, 16, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
                     } else if (STAGE == 1) {
-                        if (!conv) issue_layer<1, 16>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
-                        else issue_layer<1, 32>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
-                    } else issue_layer<2, 32>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                        if (!conv) issue_layer<1, 16, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                        else issue_layer<1, 32, false>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                    } else if (!conv) issue_layer<2, 32, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                    else issue_layer<2, 32, false>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
                 }
             }
             __syncwarp();
         } else {
             const bool interior = rm != 0xffffu && my_j < nvalid;
-            unsigned char* raw_b = arena;
-            unsigned char* act_b = arena + (size_t)S.cp * PS;
             uint32_t lcl = lc;
+            // residual layers (and stage 0's conv): accumulators pre-loaded with the bias, drained columns re-loaded with the
+            // next layer's; the sequence's first conv at the end of stages 1, 2 has another column map: opening MMAs + bias here
+            constexpr int NCR = STAGE <= 1 ? 8 : 16;          // columns per warp in the residual layers (and stage 0's conv)
+            const uint32_t tile_bytes = (uint32_t)S.TS * 16u;
+            const uint32_t tq_ = tmem_sub + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t row_a = smem_u32(arena) + (uint32_t)(G0 + r) * 16u;
+            const uint32_t raw_r = row_a + (uint32_t)(half * (NCR / 8)) * PS;            // raw planes of this warp's column part
+            const uint32_t act_r = raw_r + (uint32_t)S.cp * PS;
+            const float* bs = s_bias + half * NCR;
             if (STAGE == 0) {
-                epi_layer<8, GR_CONV, 2>(S, tmem_sub, full, ready, lcl & 1u, 16u, s_bias, interior, r, quarter, half, raw_b, raw_b, lane, false, tprof);
-            } else if (STAGE == 1) {
-                for (int blk = 0; blk < 2; ++blk) {
-                    epi_layer<8, GR_RES0, 2>(S, tmem_sub, full, ready, lcl & 1u, 16u, s_bias + 32 * (2 * blk), interior, r, quarter, half, act_b, raw_b, lane, true, tprof);
-                    ++lcl;
-                    epi_layer<8, GR_RES1, 2>(S, tmem_sub, full, ready, lcl & 1u, 16u, s_bias + 32 * (2 * blk + 1), interior, r, quarter, half, act_b, raw_b, lane, true, tprof);
-                    ++lcl;
-                }
-                epi_layer<16, GR_CONV, 1>(S, tmem_sub, full, ready, lcl & 1u, 32u, s_bias + 32 * 4, interior, r, quarter, half, raw_b, raw_b, lane, false, tprof);
+                epi_layer<8, GR_CONV, 2, false>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof);
             } else {
+                constexpr uint32_t CO = STAGE == 1 ? 16u : 32u;
+                constexpr int TBR = STAGE == 1 ? 2 : 1;
                 for (int blk = 0; blk < 2; ++blk) {
-                    epi_layer<16, GR_RES0, 1>(S, tmem_sub, full, ready, lcl & 1u, 32u, s_bias + 32 * (2 * blk), interior, r, quarter, half, act_b, raw_b, lane, true, tprof);
+                    epi_layer<NCR, GR_RES0, TBR, false>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk), bs + 32 * (2 * blk + 1), interior, act_r, raw_r, lane, true, tprof);
                     ++lcl;
-                    epi_layer<16, GR_RES1, 1>(S, tmem_sub, full, ready, lcl & 1u, 32u, s_bias + 32 * (2 * blk + 1), interior, r, quarter, half, act_b, raw_b, lane, STAGE == 2 || blk == 0, tprof);
+                    epi_layer<NCR, GR_RES1, TBR, false>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk + 1), blk == 0 ? bs + 32 * 2 : nullptr, interior, act_r, raw_r, lane, STAGE != 3 || blk == 0, tprof);
                     ++lcl;
                 }
-                if (STAGE == 2)
-                    epi_layer<16, GR_CONV, 1>(S, tmem_sub, full, ready, lcl & 1u, 32u, s_bias + 32 * 4, interior, r, quarter, half, raw_b, raw_b, lane, false, tprof);
+                if (STAGE != 3) {   // 32 output channels: 16 columns = 2 planes per warp
+                    const uint32_t t_r = row_a + (uint32_t)(half * 2) * PS;
+                    epi_layer<16, GR_CONV, 1, true>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, s_bias + 32 * 4 + half * 16, nullptr, interior, t_r, t_r, lane, false, tprof);
+                }
             }
         }
         lc += (uint32_t)(nres + (has_conv ? 1 : 0));
