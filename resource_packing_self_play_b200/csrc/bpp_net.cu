@@ -1523,6 +1523,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             G.m_hw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.h2 * G.w2));
             G.m_php2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.h2 * G.w2));
             G.m_flat = bpptc::fdiv_magic((uint32_t)P.flat);
+            G.m_pw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.w2));
             G.dbg_serial = getenv("BPP_GR_SERIAL") ? atoi(getenv("BPP_GR_SERIAL")) : 0;
             if (getenv("BPP_TC_VERBOSE"))
                 fprintf(stderr, "bpp_net: grid-row stage %d: %dx%d, J = %d, tile stride %d, %d group(s) per CTA, %d TMEM columns, "

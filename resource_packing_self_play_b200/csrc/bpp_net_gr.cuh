@@ -57,7 +57,7 @@ struct GrStage {
     int b_goff[MAX_LAY];           // offset of the layer's bias in NetParams::bias
     int w_bytes;                   // shared weight block
     int arena_off, arena_bytes, smem_bytes;
-    uint32_t m_w, m_w2, m_hw2, m_php2, m_flat;   // fdiv magics: w, w2, h2*w2, planes_out*h2*w2, flat
+    uint32_t m_w, m_w2, m_hw2, m_php2, m_flat, m_pw2;   // fdiv magics: w, w2, h2*w2, planes_out*h2*w2, flat, planes_out*w2
     int planes_out;                // planes of the pooled hand-over (stages 0..2)
     int dbg_serial;                // experiments: 1 = drain the tensor pipe after every tile, 2 = after every MMA
 };
@@ -322,6 +322,7 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
     __shared__ uint16_t s_rowmap[128];   // row r of a tile -> leaf j | xp << 8 (0xffff: not a pixel row)
     __shared__ uint32_t s_rec[STAGE == 0 ? 2 : 1][STAGE == 0 ? 8 : 1][32];
     __shared__ uint32_t s_msk[STAGE == 0 ? 2 : 1][STAGE == 0 ? 8 : 1][2][32];   // [sub][leaf][rows | columns][index]
+    __shared__ int s_it[STAGE == 0 ? 2 : 1][STAGE == 0 ? 8 : 1][2 * BPP_MAX_ITEMS];     // [sub][leaf][item: w, h]
     __shared__ uint4 s_lut[STAGE == 0 ? 256 : 1];                                 // 8 channel bits -> 8 x bf16 {0, 1}
     const int tid = threadIdx.x;
     const int sub = tid >= SUB_THREADS ? 1 : 0;
@@ -405,6 +406,20 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
     long long* tprof = profiling ? s_tprof : nullptr;
     if (profiling) for (int i = 0; i < 8; ++i) s_tprof[i] = 0;
 
+    // stage 0: the compact record words and item-list entries this thread fetches ahead for its sub's next group
+    uint32_t pf_rec = 0;
+    int pf_it = 0, pf_j = 0, pf_q = 0;
+    const int n2 = 2 * P.N;
+    if (STAGE == 0 && sub < S.nsub) {
+        pf_j = st / n2;
+        pf_q = st - pf_j * n2;
+        const int nv = min(gsz, slice_hi - slice_lo);
+        if (st < nv * 32) pf_rec = recs[(size_t)(slice_lo + (st >> 5)) * 32 + (st & 31)];
+        if (st < nv * n2) {
+            const int g = game ? game[slice_lo + pf_j] : slice_lo + pf_j;
+            pf_it = items_wh[(size_t)g * n2 + pf_q];
+        }
+    }
     if (sub < S.nsub)
     for (int b0 = slice_lo; b0 < slice_hi; b0 += gsz) {
         const int nvalid = min(gsz, slice_hi - b0);
@@ -415,29 +430,41 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
             // [0:h, 0:w] block while it is still to be placed.  Per leaf two small tables - items still to place that reach
             // grid row y, items that reach column x - make a pixel's channel bits one AND; an 8-channel plane entry (bf16 0/1)
             // comes from a 256-entry table.
-            for (int i = st; i < nvalid * 32; i += SUB_THREADS) s_rec[sub][i >> 5][i & 31] = recs[(size_t)(b0 + (i >> 5)) * 32 + (i & 31)];
+            // (the records and item lists were fetched into registers while the previous group was being computed)
+            if (st < nvalid * 32) s_rec[sub][st >> 5][st & 31] = pf_rec;
+            if (st < nvalid * n2) s_it[sub][pf_j][pf_q] = pf_it;
+            sub_sync(sub);
             for (int i = st; i < nvalid * 64; i += SUB_THREADS) {
                 const int j = i >> 6, k = i & 31, isx = (i >> 5) & 1;   // k = grid row y (isx = 0) or column x (isx = 1)
-                const int b = b0 + j;
-                const int g = game ? game[b] : b;
-                const uint32_t rem = recs[(size_t)b * 32 + BPP_REC_REM];
-                const int32_t* it = items_wh + (size_t)g * P.N * 2;
+                const uint32_t rem = s_rec[sub][j][BPP_REC_REM];
                 uint32_t m = 0;
                 for (int q = 0; q < P.N; ++q)
-                    if (((rem >> q) & 1u) && k < __ldg(it + 2 * q + (isx ? 0 : 1))) m |= 2u << q;
+                    if (((rem >> q) & 1u) && k < s_it[sub][j][2 * q + (isx ? 0 : 1)]) m |= 2u << q;
                 s_msk[sub][j][isx][k] = m;
             }
+            {   // next group's inputs: in flight during this group's layers
+                const int nb0 = b0 + gsz, nv = min(gsz, slice_hi - nb0);
+                if (st < nv * 32) pf_rec = recs[(size_t)(nb0 + (st >> 5)) * 32 + (st & 31)];
+                if (st < nv * n2) {
+                    const int g = game ? game[nb0 + pf_j] : nb0 + pf_j;
+                    pf_it = items_wh[(size_t)g * n2 + pf_q];
+                }
+            }
             sub_sync(sub);
-            const int nplanes = S.cp;
-            for (int idx = st; idx < NT * 128; idx += SUB_THREADS) {
+            for (int idx = st; idx < NT * 128; idx += SUB_THREADS) {   // one pixel row entry of one tile per step
                 const int t = idx >> 7;
                 const uint32_t m = s_rowmap[idx & 127];
                 const int j = (int)(m & 0xff);
                 if (m == 0xffffu || j >= nvalid) continue;
                 const int x = (int)(m >> 8) - 1;
                 const uint32_t bits = ((s_rec[sub][j][t] >> x) & 1u) | (s_msk[sub][j][0][t] & s_msk[sub][j][1][x]);
-                uint4* dst = reinterpret_cast<uint4*>(arena) + (G0 + t * S.TS + (idx & 127));
-                for (int p = 0; p < nplanes; ++p) dst[(size_t)p * S.RT] = s_lut[(bits >> (8 * p)) & 0xffu];
+                const uint32_t dst = smem_u32(arena) + (uint32_t)(G0 + t * S.TS + (idx & 127)) * 16u;
+                sts128(dst, s_lut[bits & 0xffu]);
+                sts128(dst + PS, s_lut[(bits >> 8) & 0xffu]);
+                if (S.cp > 2) {
+                    sts128(dst + 2u * PS, s_lut[(bits >> 16) & 0xffu]);
+                    sts128(dst + 3u * PS, s_lut[0]);
+                }
             }
         } else {
             // the previous stage's residual stream [leaf][plane][pixel] -> raw planes, relu(raw) -> activation planes; the
@@ -555,31 +582,35 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
         if (profiling) { const long long t_ = clock64(); t_cv += t_ - tq; tq = t_; }
         // --------------------------------------------------------------------------------------------------- output
         if (STAGE < 3) {
-            // max_pool2d(3, 2, 1) of the conv output T (planes 0.. of the arena, interior rows) -> x[leaf][plane][pixel]
-            const int hw2 = S.h2 * S.w2, per = S.planes_out * hw2;
-            uint4* dst = xout + (size_t)b0 * per;
-            const uint4 ninf = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
-            for (int idx = st; idx < nvalid * per; idx += SUB_THREADS) {
-                const int j = fdiv(idx, S.m_php2);
-                int q = idx - j * per;
-                const int p = fdiv(q, S.m_hw2);
-                q -= p * hw2;
-                const int oy = fdiv(q, S.m_w2), ox = q - oy * S.w2;
-                const uint4* src = reinterpret_cast<const uint4*>(arena) + (size_t)p * S.RT + G0 + j * S.wp + 2 * ox;   // xp = 2*ox + dx
-                uint4 m = ninf;
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const int y = 2 * oy + dy - 1;
-                    if (y < 0 || y >= S.h) continue;
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int x = 2 * ox + dx - 1;
-                        if (x < 0 || x >= S.w) continue;
-                        const uint4 v = src[y * S.TS + dx];
-                        m = make_uint4(max_bf16x2(m.x, v.x), max_bf16x2(m.y, v.y), max_bf16x2(m.z, v.z), max_bf16x2(m.w, v.w));
-                    }
+            // max_pool2d(3, 2, 1) of the conv output T (planes 0.. of the arena, interior rows) -> x[leaf][plane][pixel].  One
+            // thread = one output column of one plane of one leaf: the horizontal 3-max of every input row is taken once and
+            // shared by the two output rows that use it.  A tap outside the image is replaced by its clamped neighbour, which
+            // lies inside the same window (the maximum is unchanged, no branches).
+            const int hw2 = S.h2 * S.w2, per = S.planes_out * hw2, pw2 = S.planes_out * S.w2;
+            const uint32_t abase = smem_u32(arena) + (uint32_t)(G0 + 1) * 16u;   // entry of leaf 0, column 0 in tile 0
+            const uint32_t trow = (uint32_t)S.TS * 16u;
+            for (int it = st; it < nvalid * pw2; it += SUB_THREADS) {
+                const int j = fdiv(it, S.m_pw2);
+                int q = it - j * pw2;
+                const int p = fdiv(q, S.m_w2), ox = q - p * S.w2;
+                const uint32_t a0 = abase + (uint32_t)p * PS + (uint32_t)(j * S.wp) * 16u;
+                const uint32_t c0 = a0 + (uint32_t)max(2 * ox - 1, 0) * 16u, c1 = a0 + (uint32_t)(2 * ox) * 16u,
+                               c2 = a0 + (uint32_t)min(2 * ox + 1, S.w - 1) * 16u;
+                auto hmax = [&](int y) {
+                    const uint32_t ro = (uint32_t)y * trow;
+                    const uint4 a = lds128(c0 + ro), b = lds128(c1 + ro), c = lds128(c2 + ro);
+                    return make_uint4(max_bf16x2(max_bf16x2(a.x, b.x), c.x), max_bf16x2(max_bf16x2(a.y, b.y), c.y),
+                                      max_bf16x2(max_bf16x2(a.z, b.z), c.z), max_bf16x2(max_bf16x2(a.w, b.w), c.w));
+                };
+                uint4* dst = xout + (size_t)(b0 + j) * per + p * hw2 + ox;
+                uint4 up = hmax(0);
+                for (int oy = 0; oy < S.h2; ++oy) {
+                    const uint4 mid = oy ? hmax(2 * oy) : up;
+                    const uint4 lo = hmax(min(2 * oy + 1, S.h - 1));
+                    dst[oy * S.w2] = make_uint4(max_bf16x2(max_bf16x2(up.x, mid.x), lo.x), max_bf16x2(max_bf16x2(up.y, mid.y), lo.y),
+                                                max_bf16x2(max_bf16x2(up.z, mid.z), lo.z), max_bf16x2(max_bf16x2(up.w, mid.w), lo.w));
+                    up = lo;
                 }
-                dst[idx] = m;
             }
         } else {
             // relu(flatten(x)) as bf16 [B][flat] for the FC heads (flat index = channel * h*w + y*w + x)

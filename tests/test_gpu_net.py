@@ -172,6 +172,7 @@ def test_both_shared_memory_plans_of_the_tensor_core_kernel_agree_bit_for_bit(W,
     recs[:, 28] = rng.randint(1, 1 << N, size=B)
     items = ItemsGenerator(W, H, N).items_batch(np.arange(B) % 53 + 9, None)
     outs = []
+    monkeypatch.setenv("BPP_NO_GR", "1")   # the one-kernel trunk (fallback of the grid-row stage kernels)
     for compact in ("0", "1"):
         monkeypatch.setenv("BPP_TC_COMPACT", compact)
         torch.manual_seed(4)
@@ -199,6 +200,7 @@ def test_role_kernels_equal_the_one_kernel_trunk_bit_for_bit(W, H, N, B, monkeyp
     recs[:, 28] = rng.randint(1, 1 << N, size=B)
     items = ItemsGenerator(W, H, N).items_batch(np.arange(B) % 53 + 9, None)
     outs = []
+    monkeypatch.setenv("BPP_NO_GR", "1")   # role kernels / one-kernel trunk (the split-bf16 mode's kernels, bf16 fallback)
     for no_roles in ("", "1"):
         monkeypatch.setenv("BPP_ROLES_MIN_BATCH", "1")   # role kernels at any batch size (default: large batches only)
         if no_roles:
@@ -225,3 +227,52 @@ def test_role_kernels_equal_the_one_kernel_trunk_bit_for_bit(W, H, N, B, monkeyp
         assert np.array_equal(a, b)
     k = max(1, B // 3)
     assert np.array_equal(outs[0][2][:k], outs[0][0][:k]) and not outs[0][2][k:].any()
+
+
+@pytest.mark.parametrize("W,H,N,B", [(15, 15, 10, 777), (20, 20, 10, 301), (9, 12, 5, 64), (15, 15, 10, 3), (12, 9, 16, 130),
+                                     (25, 28, 10, 50)])
+def test_grid_row_stage_kernels_match_the_previous_tensor_core_path_and_the_simt_kernel(W, H, N, B, monkeypatch):
+    """The grid-row stage kernels (k_net_gr<0..3>, bpp_net_gr.cuh: vertical taps stacked along N, in-place layers, bias
+    pre-loaded into the accumulators) apply the same bf16 roundings as the previous tensor-core path (BPP_NO_GR=1) and as the
+    CUDA-core kernel bf16_simt; only the fp32 accumulation order differs.  Ragged batches (partial groups), the device-side
+    batch size, 17 input channels (two K chunks in the first layer) and a 28-row board (28 tiles per layer)."""
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+    rng = np.random.RandomState(3)
+    recs = np.zeros((B, 32), dtype=np.uint32)
+    recs[:, :H] = rng.randint(0, 1 << min(W, 30), size=(B, H)) & rng.randint(0, 1 << min(W, 30), size=(B, H))
+    recs[:, 28] = rng.randint(1, 1 << N, size=B)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(B) % 53 + 9, None)
+    outs = {}
+    for tag in ("gr", "prev"):
+        if tag == "gr":
+            monkeypatch.delenv("BPP_NO_GR", raising=False)
+        else:
+            monkeypatch.setenv("BPP_NO_GR", "1")
+        torch.manual_seed(4)
+        net = NNetWrapper(_Game(W, H, N), dotdict(num_items=N, num_bins=1, cuda=True, epochs=1, batch_size=8),
+                          max_batch=B, precision="bf16")
+        with torch.no_grad():
+            net.nnet.logits_fc.weight.mul_(25.0)
+        net.sync_weights()
+        assert net.dnet.grid_row() == (tag == "gr")
+        dev = net.device
+        r_t, i_t = torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev)
+        pol, val = net.dnet.forward(r_t, i_t)
+        k = max(1, B // 3)
+        count = torch.tensor([k], dtype=torch.int32, device=dev)   # device-side batch size
+        pol2, val2 = torch.zeros_like(pol), torch.zeros_like(val)
+        net.dnet.forward(r_t, i_t, count_dev=count, policy_out=pol2, value_out=val2)
+        if tag == "prev":
+            net.dnet.set_precision("bf16_simt")
+            ps, vs = net.dnet.forward(r_t, i_t)
+            outs["simt"] = (ps.cpu().numpy(), vs.cpu().numpy())
+        torch.cuda.synchronize()
+        outs[tag] = (pol.cpu().numpy(), val.cpu().numpy(), pol2.cpu().numpy(), val2.cpu().numpy())
+    g, p, sm = outs["gr"], outs["prev"], outs["simt"]
+    assert np.isfinite(g[0]).all() and abs(g[0].sum(axis=1) - 1).max() < 1e-4
+    ref = max(np.abs(p[0] - sm[0]).max(), 1e-6)   # what another accumulation order of the same roundings moves
+    assert np.abs(g[0] - sm[0]).max() <= max(5e-4, 4 * ref) and np.abs(g[1] - sm[1]).max() <= 2e-3
+    assert np.abs(g[0] - p[0]).max() <= max(5e-4, 4 * ref)
+    assert np.array_equal(g[2][:k], g[0][:k]) and not g[2][k:].any()   # results do not depend on the grouping
