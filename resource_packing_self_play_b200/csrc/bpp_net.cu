@@ -1492,7 +1492,8 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             }
             G.w_bytes = off;
             G.arena_off = (off + G.nlay * 32 * 4 + 127) & ~127;
-            if (G.NT > bppgr::MAX_TILES || G.wp > 128) { ok = false; break; }
+            // the residual layers (and stage 2's conv) keep one accumulator slot per grid row: 16 slots of 16 or 8 of 32 columns
+            if (G.NT > bppgr::MAX_TILES || G.wp > 128 || (s >= 1 && G.NT > (s == 1 ? 16 : 8))) { ok = false; break; }
             const char* je = getenv(s == 0 ? "BPP_GR_J0" : s == 1 ? "BPP_GR_J1" : s == 2 ? "BPP_GR_J2" : "BPP_GR_J3");
             int jmax = std::min(128 / G.wp, s == 0 ? 8 : 255);
             if (je) jmax = std::max(1, std::min(jmax, atoi(je)));
@@ -1502,8 +1503,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             for (int J = jmax; J >= 1 && !fit; --J)
                 for (int ns = nsub_max; ns >= 1 && !fit; --ns) {
                     // prefer two groups in flight with slightly smaller groups over one full group
-                    if (ns == 1 && J > 1 && J * 4 > jmax * 3 && nsub_max == 2 && G.NT * cmax <= 256) continue;
-                    if (G.NT * cmax > 512 / ns) continue;
+                    if (ns == 1 && J > 1 && J * 4 > jmax * 3 && nsub_max == 2) continue;
                     G.J = J;
                     G.TS = (J * G.wp + 7) & ~7;
                     G.RT = bppgr::G0 + (G.NT - 1) * G.TS + 128 + 8;
@@ -1513,18 +1513,16 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                     fit = G.smem_bytes <= cap && G.RT < 16384;
                 }
             if (!fit) { ok = false; break; }
-            int cols = G.nsub * G.NT * cmax, tc = 32;
-            while (tc < cols) tc <<= 1;
-            G.col_sub = G.nsub == 2 ? tc / 2 : 0;
-            if (tc > 512) { ok = false; break; }
-            G.tmem_cols = tc;
+            // accumulators: a ring of 256 TMEM columns per group in flight (16 slots of 16 or 8 slots of 32 columns)
+            G.tmem_cols = G.nsub == 2 ? 512 : 256;
+            G.col_sub = 256;
+            (void)cmax;
             G.m_w = bpptc::fdiv_magic((uint32_t)G.w);
             G.m_w2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.w2));
             G.m_hw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.h2 * G.w2));
             G.m_php2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.h2 * G.w2));
             G.m_flat = bpptc::fdiv_magic((uint32_t)P.flat);
             G.m_pw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.w2));
-            G.dbg_serial = getenv("BPP_GR_SERIAL") ? atoi(getenv("BPP_GR_SERIAL")) : 0;
             if (getenv("BPP_TC_VERBOSE"))
                 fprintf(stderr, "bpp_net: grid-row stage %d: %dx%d, J = %d, tile stride %d, %d group(s) per CTA, %d TMEM columns, "
                         "%d B shared memory (weights %d)\n", s, G.h, G.w, G.J, G.TS, G.nsub, G.tmem_cols, G.smem_bytes, G.w_bytes);

@@ -59,7 +59,6 @@ struct GrStage {
     int arena_off, arena_bytes, smem_bytes;
     uint32_t m_w, m_w2, m_hw2, m_php2, m_flat, m_pw2;   // fdiv magics: w, w2, h2*w2, planes_out*h2*w2, flat, planes_out*w2
     int planes_out;                // planes of the pooled hand-over (stages 0..2)
-    int dbg_serial;                // experiments: 1 = drain the tensor pipe after every tile, 2 = after every MMA
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -99,47 +98,80 @@ __host__ __device__ constexpr uint32_t gr_idesc(int n) {   // kind::f16: D = f32
 // All MMAs of one layer, issued by one thread: straight-line code per tile (the issuing thread's own instruction stream is
 // what bounds the MMA rate of these small tiles: branches and address arithmetic per MMA cost more than the MMA).
 //   alo0 = descriptor low word of tile 0's dx = 0 window (it starts one row before the tile); wlo = descriptor low word of the
-//   layer's weights [dx][kc][k-half][3*COUT rows]; both advance in 16-byte units.  Input tile t feeds output tiles t+1, t,
-//   t-1 (column blocks c_next, +COUT, +2*COUT).  PRE: the epilogue warps have pre-loaded every accumulator column with the
-//   layer's bias (tcgen05.st), so all MMAs accumulate; else the first MMA of a tile is split because its dy = 0 block OPENS
-//   output tile t+1 and must overwrite.
-template <int CIN16, int COUT, bool PRE>
+//   layer's weights [dx][kc][k-half][3*COUT rows]; both advance in 16-byte units.
+// Accumulators: a RING of R slots of COUT columns; output tile Y owns slot Y mod R at columns cbase + (R-1 - Y mod R)*COUT,
+// so that the three blocks of input tile t (output tiles t+1, t, t-1) are consecutive ascending column blocks = ONE MMA of
+// N = 3*COUT, except where the ring wraps (two MMAs).  The epilogue warps pre-load every slot with the bias of the tile that
+// uses it next (tcgen05.st), so every MMA accumulates.  Waits: `ready` of the PREVIOUS layer (parity rpar) hands over tile t's
+// data and the drained slots when the layers are chained tile by tile (chain; needs NT <= R), and `ready` of THIS layer
+// (parity cpar) frees the slot of output tile t+1 when the image has more grid rows than the ring has slots.
+template <int CIN16, int COUT, int R, bool TALL, bool PRE>
 __device__ __forceinline__ void issue_layer(uint32_t alo0, uint32_t ahi, uint32_t a_kc, uint32_t TS, uint32_t wlo, uint32_t bhi,
-                                            int NT, uint32_t cbase, uint32_t full, uint32_t ready, uint32_t rpar,
-                                            bool wait_ready) {
+                                            int NT, uint32_t cbase, uint32_t full, uint32_t ready, uint32_t rpar, uint32_t cpar,
+                                            bool chain) {
     constexpr uint32_t id1 = gr_idesc(COUT), id2 = gr_idesc(2 * COUT), id3 = gr_idesc(3 * COUT);
     constexpr uint32_t blk = 6u * COUT;   // 16-byte units of one (dx, kc) block: 2 K halves x 3*COUT rows
+    constexpr uint32_t top = (uint32_t)(R - 1) * COUT;
+#define GR_MMAS(DCOL, BOFF, ID)                                                                                               \
+    _Pragma("unroll") for (int i = 0; i < 3 * CIN16; ++i)                                                                     \
+        umma_bf16_lh((DCOL), alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + (BOFF), bhi, (ID), 1u)
     for (int t = 0; t < NT; ++t) {
-        if (wait_ready && t + 1 < NT) {
-            mbar_wait(ready + 8u * (uint32_t)(t + 1), rpar);   // data of tile t (and t-1, t), columns of t+1 drained
+        if (chain && t + 1 < NT) {
+            mbar_wait(ready + 8u * (uint32_t)(t + 1), rpar);   // data of tile t (and t-1, t), slot of t+1 drained
             tc_fence_after();
         }
         const uint32_t alo = alo0 + (uint32_t)t * TS;
-        const uint32_t c_next = cbase + (uint32_t)(NT - 2 - t) * COUT;   // columns of output tile t+1; tile t follows
-        if (NT == 1) {
-#pragma unroll
-            for (int i = 0; i < 3 * CIN16; ++i)
-                umma_bf16_lh(cbase, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + COUT, bhi, id1, (PRE || i) ? 1u : 0u);
-        } else if (t == 0) {          // output tiles 1 and 0 open
-#pragma unroll
-            for (int i = 0; i < 3 * CIN16; ++i)
-                umma_bf16_lh(c_next, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id2, (PRE || i) ? 1u : 0u);
-        } else if (t == NT - 1) {     // no tile below: dy = 1, 2 only
-#pragma unroll
-            for (int i = 0; i < 3 * CIN16; ++i)
-                umma_bf16_lh(cbase, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + COUT, bhi, id2, 1u);
-        } else {
-            if (PRE) umma_bf16_lh(c_next, alo, ahi, wlo, bhi, id3, 1u);
-            else {
-                umma_bf16_lh(c_next, alo, ahi, wlo, bhi, id1, 0u);                    // dy = 0 opens output tile t+1
-                umma_bf16_lh(c_next + COUT, alo, ahi, wlo + COUT, bhi, id2, 1u);      // dy = 1, 2 accumulate onto t, t-1
+        if (!TALL) {   // every grid row has its own slot (NT <= R): no wrap, no slot is reused inside a layer
+            const uint32_t c_a = cbase + top - (uint32_t)(t + 1) * COUT;   // columns of output tile t+1
+            if (PRE) {
+                if (NT == 1) { GR_MMAS(cbase + top, COUT, id1); }
+                else if (t == 0) { GR_MMAS(c_a, 0u, id2); }                    // output tiles 1 and 0
+                else if (t == NT - 1) { GR_MMAS(c_a + COUT, COUT, id2); }      // no tile below: dy = 1, 2 only
+                else { GR_MMAS(c_a, 0u, id3); }
+            } else {
+                // accumulators not pre-loaded: the first MMA into a slot overwrites.  Tile 0 opens output tiles 1 and 0; a
+                // middle tile's dy = 0 block opens output tile t+1 while its other two blocks accumulate: its first MMA is split
+#define GR_MMAS0(DCOL, BOFF, ID, A0)                                                                                           \
+    _Pragma("unroll") for (int i = 0; i < 3 * CIN16; ++i)                                                                     \
+        umma_bf16_lh((DCOL), alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + (BOFF), bhi, (ID), (i || (A0)) ? 1u : 0u)
+                if (NT == 1) { GR_MMAS0(cbase + top, COUT, id1, 0); }
+                else if (t == 0) { GR_MMAS0(c_a, 0u, id2, 0); }
+                else if (t == NT - 1) { GR_MMAS0(c_a + COUT, COUT, id2, 1); }
+                else {
+                    umma_bf16_lh(c_a, alo, ahi, wlo, bhi, id1, 0u);
+                    umma_bf16_lh(c_a + COUT, alo, ahi, wlo + COUT, bhi, id2, 1u);
+                    _Pragma("unroll") for (int i = 1; i < 3 * CIN16; ++i)
+                        umma_bf16_lh(c_a, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id3, 1u);
+                }
+#undef GR_MMAS0
             }
-#pragma unroll
-            for (int i = 1; i < 3 * CIN16; ++i)
-                umma_bf16_lh(c_next, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id3, 1u);
+        } else {
+            if (t + 1 >= R && t + 1 < NT) {
+                mbar_wait(ready + 8u * (uint32_t)(t + 1 - R), cpar);   // the slot of output tile t+1 was tile t+1-R's
+                tc_fence_after();
+            }
+            const uint32_t sa = (uint32_t)(t + 1) & (uint32_t)(R - 1), sb = (uint32_t)t & (uint32_t)(R - 1);
+            const uint32_t c_a = cbase + top - sa * COUT;   // columns of output tile t+1
+            if (NT == 1) {
+                GR_MMAS(cbase + top, COUT, id1);
+            } else if (t == 0) {              // output tiles 1 and 0
+                GR_MMAS(c_a, 0u, id2);
+            } else if (t == NT - 1) {         // no tile below: dy = 1, 2 only
+                if (sb != 0) { GR_MMAS(cbase + top - sb * COUT, COUT, id2); }
+                else { GR_MMAS(cbase + top, COUT, id1); GR_MMAS(cbase, 2u * COUT, id1); }
+            } else if (sa == 0) {             // tile t+1 wrapped to the top slot; t and t-1 sit in the two lowest column blocks
+                GR_MMAS(cbase + top, 0u, id1);
+                GR_MMAS(cbase, COUT, id2);
+            } else if (sb == 0) {             // t+1 and t are consecutive, t-1 wrapped to the lowest block
+                GR_MMAS(c_a, 0u, id2);
+                GR_MMAS(cbase, 2u * COUT, id1);
+            } else {
+                GR_MMAS(c_a, 0u, id3);
+            }
         }
         umma_commit(full + 8u * (uint32_t)t);
     }
+#undef GR_MMAS
 }
 
 enum { GR_CONV = 0, GR_RES0 = 1, GR_RES1 = 2 };
@@ -233,14 +265,14 @@ __device__ __forceinline__ void epi_unit(const uint32_t* acc, const float* bias_
     }
 }
 
-// this warp's share of the accumulator columns of all tiles <- the bias of the group's first layer (start of a group)
-template <int NC>
-__device__ __forceinline__ void preload_bias(uint32_t tmem_sub, int NT, uint32_t cout, const float* bias_s, int quarter, int half) {
+// this warp's share of the first min(NT, R) accumulator slots <- the bias of the layer that is about to run
+template <int NC, int R>
+__device__ __forceinline__ void preload_bias(uint32_t tbase, int NT, uint32_t cout, const float* bias_s) {
     uint32_t bv[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) bv[i] = __float_as_uint(bias_s[half * NC + i]);
-    const uint32_t tbase = tmem_sub + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * NC);
-    for (int T = 0; T < NT; ++T) tmem_st<NC>(tbase + (uint32_t)T * cout, bv);
+    for (int i = 0; i < NC; ++i) bv[i] = __float_as_uint(bias_s[i]);
+    const int ns = NT < R ? NT : R;
+    for (int sl = 0; sl < ns; ++sl) tmem_st<NC>(tbase + (uint32_t)(R - 1 - sl) * cout, bv);
     tmem_wait_st();
     tc_fence_before();
 }
@@ -250,17 +282,17 @@ __device__ __forceinline__ void preload_bias(uint32_t tmem_sub, int NT, uint32_t
 #else
 #define GR_T(slot) do { } while (0)
 #endif
-// All epilogue units of one layer for this warp, in batches of TB tiles: one wait for the batch's last tile, the TMEM loads of
-// the whole batch in flight together, one cross-proxy fence per batch, then one arrival per tile on the tiles' "ready"
-// barriers.  `publish` = a later layer reads the stores through the tensor core's proxy.  bias_next != nullptr: the drained
-// columns are re-loaded with the NEXT layer's bias (same column map), whose MMAs then only accumulate; BIAS: this layer's
-// accumulators were not pre-loaded, the bias is added here.
-template <int NC, int KIND, int TB, bool BIAS>
+// All epilogue units of one layer for this warp, in batches of TB tiles (R % TB == 0: a batch never straddles the ring's
+// wrap): one wait for the batch's last tile, the TMEM loads of the whole batch in flight together, one cross-proxy fence per
+// batch, then one arrival per tile on the tiles' "ready" barriers.  `publish` = a later layer reads the stores through the
+// tensor core's proxy.  A drained slot is re-loaded with the bias of its next user: this layer's (bias_s) while the image
+// has tiles left for it (T + R < NT), else the next layer's (bias_next, nullptr = none).
+//   tbase = TMEM address of this warp's lane quarter and column part in slot R-1 (column block 0); out0 / raw0 = shared
+//   addresses of this thread's row in tile 0, first plane of its column part
+template <int NC, int KIND, int TB, int R, bool BIAS, bool TALL>
 __device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t PS, uint32_t tbase, uint32_t full, uint32_t ready,
                                           uint32_t par, uint32_t cout, const float* bias_s, const float* bias_next, bool interior,
                                           uint32_t out0, uint32_t raw0, int lane, bool publish, long long* tprof) {
-    // tbase = TMEM address of this warp's lane quarter and column part in the LAST tile's block (tile T sits (NT-1-T)*cout
-    // columns further); out0 / raw0 = shared addresses of this thread's row in tile 0, first plane of its column part
     uint32_t bn[NC];
     if (bias_next) {
 #pragma unroll
@@ -269,13 +301,14 @@ __device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t 
 #ifdef BPP_GR_PROF
     long long tq = tprof ? clock64() : 0;
 #endif
-    uint32_t tcol = tbase + (uint32_t)(NT - 1) * cout, orow = out0, rrow = raw0;
+    uint32_t orow = out0, rrow = raw0;
     for (int T0 = 0; T0 < NT; T0 += TB) {
         const int nb = min(TB, NT - T0);
         const int fb = min(T0 + nb, NT - 1);   // the MMAs of input tile T+1 complete output tile T
         mbar_wait(full + 8u * (uint32_t)fb, par);
         tc_fence_after();
         GR_T(0);
+        const uint32_t tcol = tbase + (uint32_t)(R - 1 - (T0 & (R - 1))) * cout;   // slot of tile T0; T0 + b sits b blocks lower
         uint32_t acc[TB][NC];
 #pragma unroll
         for (int b = 0; b < TB; ++b)
@@ -285,12 +318,17 @@ __device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t 
             if (b < nb) {
                 tmem_wait_dep<NC>(acc[b]);
                 if (b == 0) GR_T(1);
-                if (bias_next) tmem_st<NC>(tcol - (uint32_t)b * cout, bn);
+                if (TALL && T0 + b + R < NT) {   // the image is taller than the ring: this layer uses the slot again
+                    uint32_t bt[NC];
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) bt[i] = __float_as_uint(bias_s[i]);
+                    tmem_st<NC>(tcol - (uint32_t)b * cout, bt);
+                } else if (bias_next) tmem_st<NC>(tcol - (uint32_t)b * cout, bn);
                 epi_unit<NC, KIND, BIAS>(acc[b], bias_s, interior, orow + (uint32_t)b * tile_bytes, rrow + (uint32_t)b * tile_bytes, PS);
             }
         GR_T(2);
         if (publish) fence_proxy_async();   // this thread's stores -> visible to the tensor core's reads of the next layer
-        if (bias_next) tmem_wait_st();
+        if (bias_next || TALL) tmem_wait_st();
         GR_T(3);
         tc_fence_before();                  // its TMEM accesses are ordered before the MMAs that will use the columns
         __syncwarp();
@@ -300,7 +338,6 @@ __device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t 
                 if (b < nb) mbar_arrive(ready + 8u * (uint32_t)(T0 + b));
         }
         GR_T(4);
-        tcol -= (uint32_t)TB * cout;
         orow += (uint32_t)TB * tile_bytes;
         rrow += (uint32_t)TB * tile_bytes;
     }
@@ -316,7 +353,7 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
     __shared__ __align__(8) uint64_t s_full[2][MAX_TILES];
     __shared__ __align__(8) uint64_t s_ready[2][MAX_TILES];
     __shared__ __align__(8) uint64_t s_wbar;
-    __shared__ __align__(8) uint64_t s_dbar[2];
+    __shared__ __align__(8) uint64_t s_cbar[2];   // conv bias pre-loaded (8 warps), per sub
     __shared__ uint32_t s_tmem;
     __shared__ long long s_tprof[8];
     __shared__ uint16_t s_rowmap[128];   // row r of a tile -> leaf j | xp << 8 (0xffff: not a pixel row)
@@ -337,7 +374,7 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
         mbar_init(smem_u32(&s_full[0][0]) + 8u * (uint32_t)tid, 1);
         mbar_init(smem_u32(&s_ready[0][0]) + 8u * (uint32_t)tid, 8);
     }
-    if (tid == 0) { mbar_init(smem_u32(&s_wbar), 1); mbar_init(smem_u32(&s_dbar[0]), 1); mbar_init(smem_u32(&s_dbar[1]), 1); }
+    if (tid == 0) { mbar_init(smem_u32(&s_wbar), 1); mbar_init(smem_u32(&s_cbar[0]), 8); mbar_init(smem_u32(&s_cbar[1]), 8); }
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "r"((uint32_t)S.tmem_cols));
@@ -401,7 +438,7 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
     const uint32_t rm = s_rowmap[r];
     const int my_j = (int)(rm & 0xff);
     uint32_t lc = 0;   // layers this sub has run (parity of its barriers)
-    uint32_t dpar = 0;
+    uint32_t cbar_par = 0;
     const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
     long long* tprof = profiling ? s_tprof : nullptr;
     if (profiling) for (int i = 0; i < 8; ++i) s_tprof[i] = 0;
@@ -502,10 +539,12 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     }
             }
         }
-        if (warp_s < 8) {   // accumulator columns of the group's first layer <- its bias
-            if (STAGE <= 1) preload_bias<8>(tmem_sub, NT, 16u, s_bias, quarter, half);
-            else preload_bias<16>(tmem_sub, NT, 32u, s_bias, quarter, half);
-        }
+        constexpr int NCR = STAGE <= 1 ? 8 : 16;          // columns per warp in the residual layers (and stage 0's conv)
+        constexpr int RR = STAGE <= 1 ? 16 : 8;           // accumulator ring: 256 columns per sub
+        constexpr uint32_t CO = STAGE <= 1 ? 16u : 32u;
+        const uint32_t tq_ = tmem_sub + ((uint32_t)(quarter * 32) << 16);
+        if (warp_s < 8)   // accumulator slots of the group's first layer <- its bias
+            preload_bias<NCR, RR>(tq_ + half * NCR, NT, CO, s_bias + half * NCR);
         fence_proxy_async();
         sub_sync(sub);
         if (profiling) { const long long t_ = clock64(); t_in += t_ - tq; tq = t_; }
@@ -527,51 +566,76 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     const uint64_t bd = umma_desc(smem_u32(smem + S.w_soff[l]), 3u * (uint32_t)S.cout[l], 8u);
                     const uint32_t wlo = (uint32_t)bd, bhi = (uint32_t)(bd >> 32);
                     const uint32_t a_kc = 2u * (uint32_t)S.RT;
-                    const uint32_t rpar = (lcl - 1u) & 1u;
+                    const uint32_t rpar = (lcl - 1u) & 1u, cpar = lcl & 1u;
+                    // layers are chained tile by tile while every grid row has its own accumulator slot; the sequence's first
+                    // conv has another column map and starts when every slot of the last residual layer is drained: with up to
+                    // 8 grid rows its first MMAs overwrite the slots and the bias is added in the epilogue, a taller image
+                    // needs the ring (wraps) and gets the bias pre-loaded behind s_cbar
+                    const bool chain = l > 0 && !conv && NT <= RR;
                     if (l > 0) {
-                        if (conv) {   // other column map: every tile of the last residual layer must have been drained
+                        if (conv && NT > 8) {   // (a conv of at most 8 grid rows opens its slots itself, see below)
+                            mbar_wait(smem_u32(&s_cbar[sub]), cbar_par);
+                            cbar_par ^= 1u;
+                        } else if (chain) mbar_wait(ready, rpar);
+                        else
                             for (int t = 0; t < NT; ++t) mbar_wait(ready + 8u * (uint32_t)t, rpar);
-                        } else mbar_wait(ready, rpar);
                         tc_fence_after();
                     }
-                    const bool wr = l > 0 && !conv;
+#define GR_ISSUE(C16, CO_, R_, PRE_)                                                                                          \
+    do {                                                                                                                      \
+        if (NT <= (R_)) issue_layer<C16, CO_, R_, false, PRE_>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain); \
+        else issue_layer<C16, CO_, R_, true, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain);           \
+    } while (0)
+#define GR_ISSUE_FLAT(C16, CO_, R_, PRE_) /* layers whose grid rows always fit the ring (guaranteed by the plan) */            \
+    issue_layer<C16, CO_, R_, false, PRE_>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain)
                     if (STAGE == 0) {
-                        if (S.cin16[0] == 1) issue_layer<1, 16, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
-                        else issue_layer<2, 16, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                        if (S.cin16[0] == 1) GR_ISSUE(1, 16, 16, true);
+                        else GR_ISSUE(2, 16, 16, true);
                     } else if (STAGE == 1) {
-                        if (!conv) issue_layer<1, 16, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
-                        else issue_layer<1, 32, false>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
-                    } else if (!conv) issue_layer<2, 32, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
-                    else issue_layer<2, 32, false>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, wr);
+                        if (!conv) GR_ISSUE_FLAT(1, 16, 16, true);
+                        else GR_ISSUE(1, 32, 8, false);
+                    } else if (!conv) GR_ISSUE_FLAT(2, 32, 8, true);
+                    else GR_ISSUE_FLAT(2, 32, 8, false);
+#undef GR_ISSUE_FLAT
+#undef GR_ISSUE
                 }
             }
             __syncwarp();
         } else {
             const bool interior = rm != 0xffffu && my_j < nvalid;
             uint32_t lcl = lc;
-            // residual layers (and stage 0's conv): accumulators pre-loaded with the bias, drained columns re-loaded with the
-            // next layer's; the sequence's first conv at the end of stages 1, 2 has another column map: opening MMAs + bias here
-            constexpr int NCR = STAGE <= 1 ? 8 : 16;          // columns per warp in the residual layers (and stage 0's conv)
+            // every layer's accumulator slots are pre-loaded with its bias; a drained slot is re-loaded for its next user
             const uint32_t tile_bytes = (uint32_t)S.TS * 16u;
-            const uint32_t tq_ = tmem_sub + ((uint32_t)(quarter * 32) << 16);
             const uint32_t row_a = smem_u32(arena) + (uint32_t)(G0 + r) * 16u;
             const uint32_t raw_r = row_a + (uint32_t)(half * (NCR / 8)) * PS;            // raw planes of this warp's column part
             const uint32_t act_r = raw_r + (uint32_t)S.cp * PS;
             const float* bs = s_bias + half * NCR;
             if (STAGE == 0) {
-                epi_layer<8, GR_CONV, 2, false>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof);
+                if (NT <= RR) epi_layer<8, GR_CONV, 2, RR, false, false>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof);
+                else epi_layer<8, GR_CONV, 2, RR, false, true>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof);
             } else {
-                constexpr uint32_t CO = STAGE == 1 ? 16u : 32u;
                 constexpr int TBR = STAGE == 1 ? 2 : 1;
                 for (int blk = 0; blk < 2; ++blk) {
-                    epi_layer<NCR, GR_RES0, TBR, false>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk), bs + 32 * (2 * blk + 1), interior, act_r, raw_r, lane, true, tprof);
+                    epi_layer<NCR, GR_RES0, TBR, RR, false, false>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk), bs + 32 * (2 * blk + 1), interior, act_r, raw_r, lane, true, tprof);
                     ++lcl;
-                    epi_layer<NCR, GR_RES1, TBR, false>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk + 1), blk == 0 ? bs + 32 * 2 : nullptr, interior, act_r, raw_r, lane, STAGE != 3 || blk == 0, tprof);
+                    epi_layer<NCR, GR_RES1, TBR, RR, false, false>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk + 1), blk == 0 ? bs + 32 * 2 : nullptr, interior, act_r, raw_r, lane, STAGE != 3 || blk == 0, tprof);
                     ++lcl;
                 }
-                if (STAGE != 3) {   // 32 output channels: 16 columns = 2 planes per warp
+                if (STAGE != 3) {
+                    // the sequence's first conv: 32 output channels, 16 columns = 2 planes per warp, its own column map (ring
+                    // of 8 slots)
                     const uint32_t t_r = row_a + (uint32_t)(half * 2) * PS;
-                    epi_layer<16, GR_CONV, 1, true>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, s_bias + 32 * 4 + half * 16, nullptr, interior, t_r, t_r, lane, false, tprof);
+                    const float* bc = s_bias + 32 * 4 + half * 16;
+                    if (NT > 8) {
+                        // all eight warps must have drained the residual layers' slots before any of them pre-loads the
+                        // conv's bias; the issuer starts the conv behind s_cbar
+                        asm volatile("bar.sync %0, 256;" ::"r"(3 + sub) : "memory");
+                        preload_bias<16, 8>(tq_ + half * 16, NT, 32u, bc);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&s_cbar[sub]));
+                        epi_layer<16, GR_CONV, 1, 8, false, true>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, bc, nullptr, interior, t_r, t_r, lane, false, tprof);
+                    } else
+                        epi_layer<16, GR_CONV, 1, 8, true, false>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, bc, nullptr, interior, t_r, t_r, lane, false, tprof);
                 }
             }
         }
