@@ -331,7 +331,7 @@ int bpp_net_set_precision(bpp_net *n, int mode);
 int bpp_net_profile(bpp_net *n, int64_t cycles_host[8]);
 /* the same timers per role kernel of the split trunk (k_net_role<0..2>): cycles_host[8 * role + slot] */
 int bpp_net_profile_roles(bpp_net *n, int64_t cycles_host[32]);
-/* 1 when the bf16 mode of this handle runs the grid-row stage kernels (k_net_gr), else 0 */
+/* 1 when the handle's current precision mode (bf16 or split-bf16) runs the grid-row stage kernels (k_net_gr), else 0 */
 int bpp_net_grid_row(bpp_net *n);
 /* Forward for B compact states.  recs_dev uint32 [B][32], game_dev int32 [B] (index into items_wh_dev rows; may be
  * NULL for identity), items_wh_dev int32 [*][N][2]; if count_dev != NULL the batch size is read from device memory

@@ -1102,9 +1102,10 @@ struct bpp_net {
     uint4* d_x1 = nullptr;   // hand-over buffers between the roles (sized for the split mode: hi + lo)
     uint4* d_x2 = nullptr;
     // grid-row trunk (k_net_gr, bpp_net_gr.cuh): one plan per level
-    bppgr::GrStage Gr[4];
-    bool gr_ok = false;
+    bppgr::GrStage Gr[4], Gr3[4];   // bf16, split-bf16
+    bool gr_ok = false, gr3_ok = false;
     __nv_bfloat16* d_wts_gr = nullptr;
+    __nv_bfloat16* d_wts_gr_lo = nullptr;
     long long gr_elems = 0;
     uint4* d_g[3] = {nullptr, nullptr, nullptr};   // hand-over buffers x1, x2, x3
 };
@@ -1458,88 +1459,111 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         }
     }
 
-    // ---- grid-row trunk (bpp_net_gr.cuh): one plan per level.  J = leaves per group (J * (w+1) <= 128 rows = one MMA
-    // tile per grid row), two groups in flight per CTA where shared memory and the TMEM columns allow it
+    // ---- grid-row trunk (bpp_net_gr.cuh): one plan per level and arithmetic mode.  J = leaves per group (J * (w+1) <= 128
+    // rows = one MMA tile per grid row).  bf16: two groups in flight per CTA where shared memory allows it.  Split-bf16 (x3):
+    // arena and weights are doubled (hi + lo), one group per CTA, and where the level's weights do not fit next to the arena
+    // they stream through two slots.
     {
         const int cin16_0 = (P.Cin + 15) / 16;
         const int chans_in[4] = {16 * cin16_0, 16, 32, 32};
-        long long goff = 0;
-        bool ok = getenv("BPP_NO_GR") == nullptr && P.flat % 16 == 0 && n->heads_ok;
-        const int cap = 232448 - 7 * 1024;   // 227 KB per block minus the kernel's static shared memory
-        for (int s = 0; s < 4 && ok; ++s) {
-            bppgr::GrStage& G = n->Gr[s];
-            memset(&G, 0, sizeof(G));
-            G.h = P.hs[s]; G.w = P.ws[s]; G.wp = G.w + 1; G.NT = G.h;
-            G.h2 = s < 3 ? P.hs[s + 1] : 0; G.w2 = s < 3 ? P.ws[s + 1] : 0;
-            G.cp = chans_in[s] / 8;
-            G.arena_planes = s == 0 ? std::max(G.cp, 2) : 2 * G.cp;
-            G.planes_out = s < 3 ? chans[s] / 8 : 0;
-            // layers: stage 0 = conv 0; stage s = the four residual convs at this level, then the next sequence's conv
-            int first = s == 0 ? 0 : 5 * (s - 1) + 1;
-            G.nlay = s == 0 ? 1 : s == 3 ? 4 : 5;
-            int off = 0, cmax = 0;
-            for (int l = 0; l < G.nlay; ++l) {
-                const ConvDesc& d = P.conv[first + l];
-                G.cin16[l] = (d.ci + 15) / 16;
-                G.cout[l] = d.co;
-                G.w_len[l] = 9 * G.cin16[l] * 2 * d.co * 16;
-                G.w_soff[l] = off;
-                G.w_goff[l] = goff;
-                G.b_goff[l] = d.b_off;
-                off += G.w_len[l];
-                goff += G.w_len[l] / 2;
-                cmax = std::max(cmax, d.co);
-            }
-            G.w_bytes = off;
-            G.arena_off = (off + G.nlay * 32 * 4 + 127) & ~127;
-            // the residual layers (and stage 2's conv) keep one accumulator slot per grid row: 16 slots of 16 or 8 of 32 columns
-            if (G.NT > bppgr::MAX_TILES || G.wp > 128 || (s >= 1 && G.NT > (s == 1 ? 16 : 8))) { ok = false; break; }
-            const char* je = getenv(s == 0 ? "BPP_GR_J0" : s == 1 ? "BPP_GR_J1" : s == 2 ? "BPP_GR_J2" : "BPP_GR_J3");
-            int jmax = std::min(128 / G.wp, s == 0 ? 8 : 255);
-            if (je) jmax = std::max(1, std::min(jmax, atoi(je)));
-            const char* se = getenv("BPP_GR_NSUB");
-            const int nsub_max = se ? std::max(1, std::min(2, atoi(se))) : 2;
-            bool fit = false;
-            for (int J = jmax; J >= 1 && !fit; --J)
-                for (int ns = nsub_max; ns >= 1 && !fit; --ns) {
-                    // prefer two groups in flight with slightly smaller groups over one full group
-                    if (ns == 1 && J > 1 && J * 4 > jmax * 3 && nsub_max == 2) continue;
-                    G.J = J;
-                    G.TS = (J * G.wp + 7) & ~7;
-                    G.RT = bppgr::G0 + (G.NT - 1) * G.TS + 128 + 8;
-                    G.arena_bytes = G.arena_planes * G.RT * 16;
-                    G.nsub = ns;
-                    G.smem_bytes = G.arena_off + ns * G.arena_bytes;
-                    fit = G.smem_bytes <= cap && G.RT < 16384;
+        const int cap = 232448 - 8 * 1024;   // 227 KB per block minus the kernel's static shared memory
+        for (int x3 = 0; x3 < 2; ++x3) {
+            long long goff = 0;
+            bool ok = getenv(x3 ? "BPP_NO_GR3" : "BPP_NO_GR") == nullptr && P.flat % 16 == 0 && (x3 ? n->heads3_ok : n->heads_ok);
+            const int f = x3 ? 2 : 1;
+            for (int s = 0; s < 4 && ok; ++s) {
+                bppgr::GrStage& G = (x3 ? n->Gr3 : n->Gr)[s];
+                memset(&G, 0, sizeof(G));
+                G.h = P.hs[s]; G.w = P.ws[s]; G.wp = G.w + 1; G.NT = G.h;
+                G.h2 = s < 3 ? P.hs[s + 1] : 0; G.w2 = s < 3 ? P.ws[s + 1] : 0;
+                G.cp = chans_in[s] / 8;
+                G.arena_planes = s == 0 ? std::max(G.cp, 2) : 2 * G.cp;
+                G.planes_out = s < 3 ? chans[s] / 8 : 0;
+                // layers: stage 0 = conv 0; stage s = the four residual convs at this level, then the next sequence's conv
+                int first = s == 0 ? 0 : 5 * (s - 1) + 1;
+                G.nlay = s == 0 ? 1 : s == 3 ? 4 : 5;
+                int off = 0, wmax = 0;
+                for (int l = 0; l < G.nlay; ++l) {
+                    const ConvDesc& d = P.conv[first + l];
+                    G.cin16[l] = (d.ci + 15) / 16;
+                    G.cout[l] = d.co;
+                    G.w_len[l] = 9 * G.cin16[l] * 2 * d.co * 16;
+                    G.w_soff[l] = off;
+                    G.w_goff[l] = goff;
+                    G.b_goff[l] = d.b_off;
+                    off += f * G.w_len[l];
+                    goff += G.w_len[l] / 2;
+                    wmax = std::max(wmax, f * G.w_len[l]);
                 }
-            if (!fit) { ok = false; break; }
-            // accumulators: a ring of 256 TMEM columns per group in flight (16 slots of 16 or 8 slots of 32 columns)
-            G.tmem_cols = G.nsub == 2 ? 512 : 256;
-            G.col_sub = 256;
-            (void)cmax;
-            G.m_w = bpptc::fdiv_magic((uint32_t)G.w);
-            G.m_w2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.w2));
-            G.m_hw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.h2 * G.w2));
-            G.m_php2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.h2 * G.w2));
-            G.m_flat = bpptc::fdiv_magic((uint32_t)P.flat);
-            G.m_pw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.w2));
-            if (getenv("BPP_TC_VERBOSE"))
-                fprintf(stderr, "bpp_net: grid-row stage %d: %dx%d, J = %d, tile stride %d, %d group(s) per CTA, %d TMEM columns, "
-                        "%d B shared memory (weights %d)\n", s, G.h, G.w, G.J, G.TS, G.nsub, G.tmem_cols, G.smem_bytes, G.w_bytes);
+                // the residual layers (and stage 2's conv) keep one accumulator slot per grid row: 16 slots of 16 or 8 of 32 columns
+                if (G.NT > bppgr::MAX_TILES || G.wp > 128 || (s >= 1 && G.NT > (s == 1 ? 16 : 8))) { ok = false; break; }
+                const char* je = getenv(s == 0 ? "BPP_GR_J0" : s == 1 ? "BPP_GR_J1" : s == 2 ? "BPP_GR_J2" : "BPP_GR_J3");
+                int jmax = std::min(128 / G.wp, s == 0 ? 8 : 255);
+                if (je) jmax = std::max(1, std::min(jmax, atoi(je)));
+                const char* se = getenv("BPP_GR_NSUB");
+                const int nsub_max = x3 ? 1 : (se ? std::max(1, std::min(2, atoi(se))) : 2);
+                bool fit = false;
+                // every (J, groups per CTA, weights resident | streamed) that fits; the one with the most leaves in flight per
+                // SM wins (streamed weights count 10 % less: their layers are not chained tile by tile), ties go to larger groups
+                bppgr::GrStage best = G;
+                double best_score = -1.0;
+                for (int J = jmax; J >= 1; --J)
+                    for (int ns = nsub_max; ns >= 1; --ns)
+                        for (int stream = 0; stream < (x3 && G.nlay > 2 ? 2 : 1); ++stream) {
+                            G.J = J;
+                            G.TS = (J * G.wp + 7) & ~7;
+                            G.RT = bppgr::G0 + (G.NT - 1) * G.TS + 128 + 8;
+                            G.lo_off = G.arena_planes * G.RT * 16;
+                            G.arena_bytes = f * G.lo_off;
+                            G.nsub = ns;
+                            G.stream = stream;
+                            G.slot_bytes = (wmax + 127) & ~127;
+                            G.w_bytes = stream ? 2 * G.slot_bytes : off;
+                            G.arena_off = (G.w_bytes + G.nlay * 32 * 4 + 127) & ~127;
+                            G.smem_bytes = G.arena_off + ns * G.arena_bytes;
+                            if (G.smem_bytes > cap || G.RT >= 16384) continue;
+                            const double score = (double)J * ns * (stream ? 0.9 : 1.0) + 1e-3 * J;
+                            if (score > best_score) { best_score = score; best = G; fit = true; }
+                        }
+                G = best;
+                if (!fit) { ok = false; break; }
+                // accumulators: a ring of 256 TMEM columns per group in flight (16 slots of 16 or 8 slots of 32 columns)
+                G.tmem_cols = G.nsub == 2 ? 512 : 256;
+                G.col_sub = 256;
+                G.m_w = bpptc::fdiv_magic((uint32_t)G.w);
+                G.m_w2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.w2));
+                G.m_hw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.h2 * G.w2));
+                G.m_php2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.h2 * G.w2));
+                G.m_flat = bpptc::fdiv_magic((uint32_t)P.flat);
+                G.m_pw2 = bpptc::fdiv_magic((uint32_t)std::max(1, G.planes_out * G.w2));
+                if (getenv("BPP_TC_VERBOSE"))
+                    fprintf(stderr, "bpp_net: grid-row stage %d (%s): %dx%d, J = %d, tile stride %d, %d group(s) per CTA, weights %s, "
+                            "%d B shared memory (weights %d)\n", s, x3 ? "bf16x3" : "bf16", G.h, G.w, G.J, G.TS, G.nsub,
+                            G.stream ? "streamed" : "resident", G.smem_bytes, G.w_bytes);
+            }
+            n->gr_elems = goff;
+            (x3 ? n->gr3_ok : n->gr_ok) = ok;
         }
-        n->gr_elems = goff;
-        if (ok) {
-            const size_t x1 = (size_t)max_batch * 2 * P.hs[1] * P.ws[1] * 16, x2 = (size_t)max_batch * 4 * P.hs[2] * P.ws[2] * 16,
-                         x3 = (size_t)max_batch * 4 * P.hs[3] * P.ws[3] * 16;
-            ok = cudaMalloc(&n->d_wts_gr, (size_t)goff * 2) == cudaSuccess && cudaMalloc(&n->d_g[0], x1) == cudaSuccess &&
-                 cudaMalloc(&n->d_g[1], x2) == cudaSuccess && cudaMalloc(&n->d_g[2], x3) == cudaSuccess &&
-                 cudaFuncSetAttribute(bppgr::k_net_gr<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->Gr[0].smem_bytes) == cudaSuccess &&
-                 cudaFuncSetAttribute(bppgr::k_net_gr<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->Gr[1].smem_bytes) == cudaSuccess &&
-                 cudaFuncSetAttribute(bppgr::k_net_gr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->Gr[2].smem_bytes) == cudaSuccess &&
-                 cudaFuncSetAttribute(bppgr::k_net_gr<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, n->Gr[3].smem_bytes) == cudaSuccess;
-            if (!ok) cudaGetLastError();
+        if (n->gr_ok || n->gr3_ok) {   // weights in the grid-row layout (hi, lo) and the hand-over buffers x1..x3 (hi + lo)
+            const size_t x1 = (size_t)max_batch * 2 * 2 * P.hs[1] * P.ws[1] * 16, x2 = (size_t)max_batch * 2 * 4 * P.hs[2] * P.ws[2] * 16,
+                         x3b = (size_t)max_batch * 2 * 4 * P.hs[3] * P.ws[3] * 16;
+            bool ok = cudaMalloc(&n->d_wts_gr, (size_t)n->gr_elems * 2) == cudaSuccess &&
+                      cudaMalloc(&n->d_wts_gr_lo, (size_t)n->gr_elems * 2) == cudaSuccess && cudaMalloc(&n->d_g[0], x1) == cudaSuccess &&
+                      cudaMalloc(&n->d_g[1], x2) == cudaSuccess && cudaMalloc(&n->d_g[2], x3b) == cudaSuccess;
+            auto attr = [&](const void* fn, int bytes) {
+                return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+            };
+            if (ok && n->gr_ok)
+                ok = attr((const void*)bppgr::k_net_gr<0, false>, n->Gr[0].smem_bytes) && attr((const void*)bppgr::k_net_gr<1, false>, n->Gr[1].smem_bytes) &&
+                     attr((const void*)bppgr::k_net_gr<2, false>, n->Gr[2].smem_bytes) && attr((const void*)bppgr::k_net_gr<3, false>, n->Gr[3].smem_bytes);
+            if (ok && n->gr3_ok)
+                ok = attr((const void*)bppgr::k_net_gr<0, true>, n->Gr3[0].smem_bytes) && attr((const void*)bppgr::k_net_gr<1, true>, n->Gr3[1].smem_bytes) &&
+                     attr((const void*)bppgr::k_net_gr<2, true>, n->Gr3[2].smem_bytes) && attr((const void*)bppgr::k_net_gr<3, true>, n->Gr3[3].smem_bytes);
+            if (!ok) {
+                cudaGetLastError();
+                n->gr_ok = n->gr3_ok = false;
+            }
         }
-        n->gr_ok = ok;
     }
     if (cudaMalloc(&n->d_prof, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(n->d_prof, 0, 32 * sizeof(long long));
     *out = n;
@@ -1565,6 +1589,7 @@ extern "C" int bpp_net_destroy(bpp_net* n) {
     cudaFree(n->d_x1);
     cudaFree(n->d_x2);
     cudaFree(n->d_wts_gr);
+    cudaFree(n->d_wts_gr_lo);
     for (int i = 0; i < 3; ++i) cudaFree(n->d_g[i]);
     delete n;
     return BPP_OK;
@@ -1648,11 +1673,12 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
         }
     // conv weights for the grid-row kernels: per layer [dx][kc][k-half][dy * cout + co][8 cin] - the three vertical taps of
     // one horizontal tap are the N axis of one UMMA B operand (bpp_net_gr.cuh)
-    std::vector<uint16_t> wg;
-    if (n->gr_ok) {
+    std::vector<uint16_t> wg, wgl;
+    if (n->gr_ok || n->gr3_ok) {
         wg.assign((size_t)n->gr_elems, 0);
+        wgl.assign((size_t)n->gr_elems, 0);
         for (int s = 0; s < 4; ++s) {
-            const bppgr::GrStage& G = n->Gr[s];
+            const bppgr::GrStage& G = n->gr_ok ? n->Gr[s] : n->Gr3[s];   // (layer tables are the same in both plans)
             const int first = s == 0 ? 0 : 5 * (s - 1) + 1;
             for (int l = 0; l < G.nlay; ++l) {
                 const ConvDesc& d = P.conv[first + l];
@@ -1670,6 +1696,10 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
                                         const size_t ui = (size_t)G.w_goff[l] +
                                                           ((((size_t)dx * c16 + kc) * 2 + kh) * (3 * d.co) + dy * d.co + co) * 8 + j;
                                         wg[ui] = f32_to_bf16_rne(v);
+                                        uint32_t hb = (uint32_t)wg[ui] << 16;
+                                        float hf;
+                                        memcpy(&hf, &hb, 4);
+                                        wgl[ui] = f32_to_bf16_rne(v - hf);   // low half for the split-bf16 mode
                                     }
             }
         }
@@ -1734,7 +1764,9 @@ extern "C" int bpp_net_commit(bpp_net* n, void* stream) {
         for (int o = 0; o < P.A; ++o)
             for (int i = 0; i < HIDDEN; ++i) wlp[(size_t)i * n->T.A_pad + o] = f32_to_bf16_rne(src2[(size_t)o * HIDDEN + i]);
     }
-    if (n->gr_ok && cudaMemcpyAsync(n->d_wts_gr, wg.data(), wg.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    if ((n->gr_ok || n->gr3_ok) &&
+        (cudaMemcpyAsync(n->d_wts_gr, wg.data(), wg.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+         cudaMemcpyAsync(n->d_wts_gr_lo, wgl.data(), wgl.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess))
         return nerr(BPP_E_CUDA, "grid-row weight upload failed");
     if (cudaMemcpyAsync(n->d_wts_logits_pad, wlp.data(), wlp.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(n->d_wts_umma, wu.data(), wu.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -1759,7 +1791,9 @@ extern "C" int bpp_net_profile(bpp_net* n, int64_t cycles_host[8]) {
     for (int i = 0; i < 8; ++i) cycles_host[i] = roles ? all[i] + all[8 + i] + all[16 + i] : all[i];
     return BPP_OK;
 }
-extern "C" int bpp_net_grid_row(bpp_net* n) { return n && n->gr_ok ? 1 : 0; }
+extern "C" int bpp_net_grid_row(bpp_net* n) {
+    return n && ((n->precision == BPP_NET_BF16 && n->gr_ok) || (n->precision == BPP_NET_BF16X3 && n->gr3_ok)) ? 1 : 0;
+}
 extern "C" int bpp_net_profile_roles(bpp_net* n, int64_t cycles_host[32]) {
     if (!n || !cycles_host || !n->d_prof) return nerr(BPP_E_INVALID, "null argument");
     if (cudaMemcpy(cycles_host, n->d_prof, 32 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -1823,22 +1857,26 @@ static int launch_roles(bpp_net* n, int x3, int B, const int32_t* count_dev, con
 
 
 // grid-row trunk: four level kernels chained by programmatic launches (bpp_net_gr.cuh)
-static int launch_gr(bpp_net* n, int B, const int32_t* count_dev, const uint32_t* recs_dev, const int32_t* game_dev,
+static int launch_gr(bpp_net* n, int x3, int B, const int32_t* count_dev, const uint32_t* recs_dev, const int32_t* game_dev,
                      const int32_t* items_wh_dev, cudaStream_t st) {
     cudaError_t ce = cudaSuccess;
+    const long long flo = (long long)n->max_batch * n->P.flat;
     for (int s = 0; s < 4 && ce == cudaSuccess; ++s) {
-        const bppgr::GrStage& G = n->Gr[s];
+        const bppgr::GrStage& G = (x3 ? n->Gr3 : n->Gr)[s];
         const int groups = (B + G.J - 1) / G.J;
         const int gr = std::max(1, std::min((groups + G.nsub - 1) / G.nsub, n->num_sms));
         const uint4* xin = s == 0 ? nullptr : n->d_g[s - 1];
         uint4* xout = s < 3 ? n->d_g[s] : nullptr;
-#define GR_LAUNCH(SQ)                                                                                                      \
-    ce = launch_pdl(bppgr::k_net_gr<SQ>, gr, G.nsub * bppgr::SUB_THREADS, (size_t)G.smem_bytes, st, n->P, G, B, count_dev, \
-                    recs_dev, game_dev, items_wh_dev, xin, xout, n->d_feat, (const __nv_bfloat16*)n->d_wts_gr, n->d_prof)
-        if (s == 0) GR_LAUNCH(0);
-        else if (s == 1) GR_LAUNCH(1);
-        else if (s == 2) GR_LAUNCH(2);
-        else GR_LAUNCH(3);
+#define GR_LAUNCH(SQ, X)                                                                                                      \
+    ce = launch_pdl(bppgr::k_net_gr<SQ, X>, gr, G.nsub * bppgr::SUB_THREADS, (size_t)G.smem_bytes, st, n->P, G, B, count_dev, \
+                    recs_dev, game_dev, items_wh_dev, xin, xout, n->d_feat, flo, (const __nv_bfloat16*)n->d_wts_gr,          \
+                    (const __nv_bfloat16*)n->d_wts_gr_lo, n->d_prof)
+#define GR_PICK(SQ) do { if (x3) GR_LAUNCH(SQ, true); else GR_LAUNCH(SQ, false); } while (0)
+        if (s == 0) GR_PICK(0);
+        else if (s == 1) GR_PICK(1);
+        else if (s == 2) GR_PICK(2);
+        else GR_PICK(3);
+#undef GR_PICK
 #undef GR_LAUNCH
     }
     if (ce != cudaSuccess) return nerr(BPP_E_CUDA, std::string("grid-row kernel launch failed: ") + cudaGetErrorString(ce));
@@ -1861,7 +1899,7 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         const int g2 = groups < cap ? groups : cap;
         __nv_bfloat16* fo = n->heads_ok ? n->d_feat : nullptr;
         if (fo && n->gr_ok) {
-            int rc = launch_gr(n, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
+            int rc = launch_gr(n, 0, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
             if (rc) return rc;
         } else if (fo && n->roles_ok[0] && B >= n->roles_min_batch) {
             int rc = launch_roles(n, 0, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
@@ -1878,6 +1916,11 @@ extern "C" int bpp_net_forward(bpp_net* n, int B, const int32_t* count_dev, cons
         if (fo)
             launch_pdl(k_net_heads_tc<false>, (B + 127) / 128, HEAD_THREADS, (size_t)n->heads_smem, st, n->Hp, B, count_dev,
                        (const __nv_bfloat16*)n->d_feat, policy_out_dev, value_out_dev);
+    } else if (n->precision == BPP_NET_BF16X3 && n->gr3_ok && n->heads3_ok) {
+        int rc = launch_gr(n, 1, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
+        if (rc) return rc;
+        launch_pdl(k_net_heads_tc<true>, (B + 127) / 128, HEAD_THREADS, (size_t)n->heads_smem3, st, n->Hp, B, count_dev,
+                   (const __nv_bfloat16*)n->d_feat, policy_out_dev, value_out_dev);
     } else if (n->precision == BPP_NET_BF16X3 && n->roles_ok[1] && n->heads3_ok) {
         int rc = launch_roles(n, 1, B, count_dev, recs_dev, game_dev, items_wh_dev, st);
         if (rc) return rc;

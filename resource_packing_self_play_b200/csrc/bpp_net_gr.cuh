@@ -59,6 +59,10 @@ struct GrStage {
     int arena_off, arena_bytes, smem_bytes;
     uint32_t m_w, m_w2, m_hw2, m_php2, m_flat, m_pw2;   // fdiv magics: w, w2, h2*w2, planes_out*h2*w2, flat, planes_out*w2
     int planes_out;                // planes of the pooled hand-over (stages 0..2)
+    // split-bf16 mode (hi + lo halves, three MMAs per product): the lo planes of the arena sit lo_off bytes behind the hi
+    // planes, a layer's lo weights w_len bytes behind its hi weights; `stream`: the weights do not fit next to the arena and
+    // pass through two slots of slot_bytes, one layer ahead
+    int lo_off, stream, slot_bytes;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -105,16 +109,24 @@ __host__ __device__ constexpr uint32_t gr_idesc(int n) {   // kind::f16: D = f32
 // uses it next (tcgen05.st), so every MMA accumulates.  Waits: `ready` of the PREVIOUS layer (parity rpar) hands over tile t's
 // data and the drained slots when the layers are chained tile by tile (chain; needs NT <= R), and `ready` of THIS layer
 // (parity cpar) frees the slot of output tile t+1 when the image has more grid rows than the ring has slots.
-template <int CIN16, int COUT, int R, bool TALL, bool PRE>
+// XM: 0 = plain bf16; 1 = split-bf16, every product is a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (a_lo16 / w_lo16 = distance of the lo
+// operands in 16-byte units); 2 = split-bf16 with an exact bf16 A operand (the 0/1 input planes): no a_lo term
+template <int CIN16, int COUT, int R, bool TALL, bool PRE, int XM>
 __device__ __forceinline__ void issue_layer(uint32_t alo0, uint32_t ahi, uint32_t a_kc, uint32_t TS, uint32_t wlo, uint32_t bhi,
                                             int NT, uint32_t cbase, uint32_t full, uint32_t ready, uint32_t rpar, uint32_t cpar,
-                                            bool chain) {
+                                            bool chain, uint32_t a_lo16, uint32_t w_lo16) {
     constexpr uint32_t id1 = gr_idesc(COUT), id2 = gr_idesc(2 * COUT), id3 = gr_idesc(3 * COUT);
     constexpr uint32_t blk = 6u * COUT;   // 16-byte units of one (dx, kc) block: 2 K halves x 3*COUT rows
     constexpr uint32_t top = (uint32_t)(R - 1) * COUT;
+#define GR_MMA1(DCOL, AT, BT, ID, ACC)                                                                                         \
+    do {                                                                                                                      \
+        umma_bf16_lh((DCOL), (AT), ahi, (BT), bhi, (ID), (ACC));                                                              \
+        if (XM) umma_bf16_lh((DCOL), (AT), ahi, (BT) + w_lo16, bhi, (ID), 1u);                                                \
+        if (XM == 1) umma_bf16_lh((DCOL), (AT) + a_lo16, ahi, (BT), bhi, (ID), 1u);                                           \
+    } while (0)
 #define GR_MMAS(DCOL, BOFF, ID)                                                                                               \
     _Pragma("unroll") for (int i = 0; i < 3 * CIN16; ++i)                                                                     \
-        umma_bf16_lh((DCOL), alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + (BOFF), bhi, (ID), 1u)
+        GR_MMA1((DCOL), alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, wlo + (uint32_t)i * blk + (BOFF), (ID), 1u)
     for (int t = 0; t < NT; ++t) {
         if (chain && t + 1 < NT) {
             mbar_wait(ready + 8u * (uint32_t)(t + 1), rpar);   // data of tile t (and t-1, t), slot of t+1 drained
@@ -133,15 +145,17 @@ __device__ __forceinline__ void issue_layer(uint32_t alo0, uint32_t ahi, uint32_
                 // middle tile's dy = 0 block opens output tile t+1 while its other two blocks accumulate: its first MMA is split
 #define GR_MMAS0(DCOL, BOFF, ID, A0)                                                                                           \
     _Pragma("unroll") for (int i = 0; i < 3 * CIN16; ++i)                                                                     \
-        umma_bf16_lh((DCOL), alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk + (BOFF), bhi, (ID), (i || (A0)) ? 1u : 0u)
+        GR_MMA1((DCOL), alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, wlo + (uint32_t)i * blk + (BOFF), (ID), (i || (A0)) ? 1u : 0u)
                 if (NT == 1) { GR_MMAS0(cbase + top, COUT, id1, 0); }
                 else if (t == 0) { GR_MMAS0(c_a, 0u, id2, 0); }
                 else if (t == NT - 1) { GR_MMAS0(c_a + COUT, COUT, id2, 1); }
                 else {
                     umma_bf16_lh(c_a, alo, ahi, wlo, bhi, id1, 0u);
                     umma_bf16_lh(c_a + COUT, alo, ahi, wlo + COUT, bhi, id2, 1u);
+                    if (XM) umma_bf16_lh(c_a, alo, ahi, wlo + w_lo16, bhi, id3, 1u);
+                    if (XM == 1) umma_bf16_lh(c_a, alo + a_lo16, ahi, wlo, bhi, id3, 1u);
                     _Pragma("unroll") for (int i = 1; i < 3 * CIN16; ++i)
-                        umma_bf16_lh(c_a, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, ahi, wlo + (uint32_t)i * blk, bhi, id3, 1u);
+                        GR_MMA1(c_a, alo + (uint32_t)(i / CIN16) + (uint32_t)(i % CIN16) * a_kc, wlo + (uint32_t)i * blk, id3, 1u);
                 }
 #undef GR_MMAS0
             }
@@ -172,6 +186,7 @@ __device__ __forceinline__ void issue_layer(uint32_t alo0, uint32_t ahi, uint32_
         umma_commit(full + 8u * (uint32_t)t);
     }
 #undef GR_MMAS
+#undef GR_MMA1
 }
 
 enum { GR_CONV = 0, GR_RES0 = 1, GR_RES1 = 2 };
@@ -265,6 +280,40 @@ __device__ __forceinline__ void epi_unit(const uint32_t* acc, const float* bias_
     }
 }
 
+// split-bf16 variant: every stored value is hi + lo (the lo entry LO bytes behind the hi one)
+template <int NC, int KIND, bool BIAS>
+__device__ __forceinline__ void epi_unit_x3(const uint32_t* acc, const float* bias_s, bool interior, uint32_t out, uint32_t raw,
+                                            uint32_t PS, uint32_t LO) {
+#pragma unroll
+    for (int p = 0; p < NC / 8; ++p) {
+        float u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = __uint_as_float(acc[8 * p + i]) + (BIAS ? bias_s[8 * p + i] : 0.f);
+        uint4 h4, l4;
+        if (KIND == GR_RES1) {
+            const uint4 rh = lds128(raw + (uint32_t)p * PS), rl = lds128(raw + (uint32_t)p * PS + LO);
+            u[0] += bf16_lo(rh.x) + bf16_lo(rl.x); u[1] += bf16_hi(rh.x) + bf16_hi(rl.x);
+            u[2] += bf16_lo(rh.y) + bf16_lo(rl.y); u[3] += bf16_hi(rh.y) + bf16_hi(rl.y);
+            u[4] += bf16_lo(rh.z) + bf16_lo(rl.z); u[5] += bf16_hi(rh.z) + bf16_hi(rl.z);
+            u[6] += bf16_lo(rh.w) + bf16_lo(rl.w); u[7] += bf16_hi(rh.w) + bf16_hi(rl.w);
+            split8(u, h4, l4);
+            if (interior) {
+                sts128(raw + (uint32_t)p * PS, h4);
+                sts128(raw + (uint32_t)p * PS + LO, l4);
+            }
+        }
+        if (KIND != GR_CONV) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = fmaxf(u[i], 0.f);
+        }
+        split8(u, h4, l4);
+        if (interior) {
+            sts128(out + (uint32_t)p * PS, h4);
+            sts128(out + (uint32_t)p * PS + LO, l4);
+        }
+    }
+}
+
 // this warp's share of the first min(NT, R) accumulator slots <- the bias of the layer that is about to run
 template <int NC, int R>
 __device__ __forceinline__ void preload_bias(uint32_t tbase, int NT, uint32_t cout, const float* bias_s) {
@@ -289,10 +338,10 @@ __device__ __forceinline__ void preload_bias(uint32_t tbase, int NT, uint32_t co
 // has tiles left for it (T + R < NT), else the next layer's (bias_next, nullptr = none).
 //   tbase = TMEM address of this warp's lane quarter and column part in slot R-1 (column block 0); out0 / raw0 = shared
 //   addresses of this thread's row in tile 0, first plane of its column part
-template <int NC, int KIND, int TB, int R, bool BIAS, bool TALL>
+template <int NC, int KIND, int TB, int R, bool BIAS, bool TALL, bool X3 = false>
 __device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t PS, uint32_t tbase, uint32_t full, uint32_t ready,
                                           uint32_t par, uint32_t cout, const float* bias_s, const float* bias_next, bool interior,
-                                          uint32_t out0, uint32_t raw0, int lane, bool publish, long long* tprof) {
+                                          uint32_t out0, uint32_t raw0, int lane, bool publish, long long* tprof, uint32_t LO = 0) {
     uint32_t bn[NC];
     if (bias_next) {
 #pragma unroll
@@ -324,7 +373,8 @@ __device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t 
                     for (int i = 0; i < NC; ++i) bt[i] = __float_as_uint(bias_s[i]);
                     tmem_st<NC>(tcol - (uint32_t)b * cout, bt);
                 } else if (bias_next) tmem_st<NC>(tcol - (uint32_t)b * cout, bn);
-                epi_unit<NC, KIND, BIAS>(acc[b], bias_s, interior, orow + (uint32_t)b * tile_bytes, rrow + (uint32_t)b * tile_bytes, PS);
+                if (X3) epi_unit_x3<NC, KIND, BIAS>(acc[b], bias_s, interior, orow + (uint32_t)b * tile_bytes, rrow + (uint32_t)b * tile_bytes, PS, LO);
+                else epi_unit<NC, KIND, BIAS>(acc[b], bias_s, interior, orow + (uint32_t)b * tile_bytes, rrow + (uint32_t)b * tile_bytes, PS);
             }
         GR_T(2);
         if (publish) fence_proxy_async();   // this thread's stores -> visible to the tensor core's reads of the next layer
@@ -343,17 +393,20 @@ __device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t 
     }
 }
 
-template <int STAGE>
-__global__ void __launch_bounds__(2 * SUB_THREADS, 1)
+// X3 = split-bf16 mode: activations and weights as hi + lo bf16 halves, three MMAs per product, fp32-level accuracy for the
+// reference's trained checkpoints; one group per CTA (the doubled arena leaves no room for two)
+template <int STAGE, bool X3>
+__global__ void __launch_bounds__(X3 ? SUB_THREADS : 2 * SUB_THREADS, 1)
 k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev, const uint32_t* __restrict__ recs,
          const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh, const uint4* __restrict__ xin,
-         uint4* __restrict__ xout, __nv_bfloat16* __restrict__ feat_out, const __nv_bfloat16* __restrict__ wts_gr,
-         long long* prof) {
+         uint4* __restrict__ xout, __nv_bfloat16* __restrict__ feat_out, long long feat_lo_off,
+         const __nv_bfloat16* __restrict__ wts_gr, const __nv_bfloat16* __restrict__ wts_gr_lo, long long* prof) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_full[2][MAX_TILES];
     __shared__ __align__(8) uint64_t s_ready[2][MAX_TILES];
     __shared__ __align__(8) uint64_t s_wbar;
     __shared__ __align__(8) uint64_t s_cbar[2];   // conv bias pre-loaded (8 warps), per sub
+    __shared__ __align__(8) uint64_t s_wslot[2];  // streamed weights: slot filled
     __shared__ uint32_t s_tmem;
     __shared__ long long s_tprof[8];
     __shared__ uint16_t s_rowmap[128];   // row r of a tile -> leaf j | xp << 8 (0xffff: not a pixel row)
@@ -369,12 +422,16 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
     float* s_bias = reinterpret_cast<float*>(smem + S.w_bytes);   // [nlay][32]
     unsigned char* arena = smem + S.arena_off + (size_t)sub * S.arena_bytes;
     const uint32_t PS = (uint32_t)S.RT * 16u;
+    const uint32_t LO = (uint32_t)S.lo_off;   // split mode: lo planes behind the hi planes
 
     if (tid < 2 * MAX_TILES) {
         mbar_init(smem_u32(&s_full[0][0]) + 8u * (uint32_t)tid, 1);
         mbar_init(smem_u32(&s_ready[0][0]) + 8u * (uint32_t)tid, 8);
     }
-    if (tid == 0) { mbar_init(smem_u32(&s_wbar), 1); mbar_init(smem_u32(&s_cbar[0]), 8); mbar_init(smem_u32(&s_cbar[1]), 8); }
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_wbar), 1); mbar_init(smem_u32(&s_cbar[0]), 8); mbar_init(smem_u32(&s_cbar[1]), 8);
+        mbar_init(smem_u32(&s_wslot[0]), 1); mbar_init(smem_u32(&s_wslot[1]), 1);
+    }
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
                      "r"((uint32_t)S.tmem_cols));
@@ -406,16 +463,28 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {   // the stage's weights stay resident: one bulk async copy per layer
-        const uint32_t wb = smem_u32(&s_wbar);
-        mbar_expect_tx(wb, (uint32_t)S.w_bytes);
-        for (int l = 0; l < S.nlay; ++l)
-            bulk_g2s(smem_u32(smem + S.w_soff[l]), wts_gr + S.w_goff[l], (uint32_t)S.w_len[l], wb);
+    // weights: resident for the whole kernel (one bulk async copy per layer now), or - split mode, where they do not fit next
+    // to the doubled arena - streamed through two slots, one layer ahead (the issuing thread refills, see below)
+    auto fetch_layer = [&](int l, uint32_t dst, uint32_t bar) {   // one thread
+        bulk_g2s(dst, wts_gr + S.w_goff[l], (uint32_t)S.w_len[l], bar);
+        if (X3) bulk_g2s(dst + (uint32_t)S.w_len[l], wts_gr_lo + S.w_goff[l], (uint32_t)S.w_len[l], bar);
+    };
+    if (tid == 0) {
+        if (!S.stream) {
+            const uint32_t wb = smem_u32(&s_wbar);
+            mbar_expect_tx(wb, (uint32_t)S.w_bytes);
+            for (int l = 0; l < S.nlay; ++l) fetch_layer(l, smem_u32(smem + S.w_soff[l]), wb);
+        } else {
+            for (int g = 0; g < 2 && g < S.nlay; ++g) {
+                mbar_expect_tx(smem_u32(&s_wslot[g]), (uint32_t)S.w_len[g] * (X3 ? 2u : 1u));
+                fetch_layer(g, smem_u32(smem + g * S.slot_bytes), smem_u32(&s_wslot[g]));
+            }
+        }
     }
     // everything above is independent of the kernel that produced this stage's input
     pdl_launch_dependents();
     pdl_wait();
-    mbar_wait(smem_u32(&s_wbar), 0);
+    if (!S.stream) mbar_wait(smem_u32(&s_wbar), 0);
     const long long t_start = clock64();
     long long t_in = 0, t_cv = 0, t_out = 0;
 
@@ -504,26 +573,26 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                 }
             }
         } else {
-            // the previous stage's residual stream [leaf][plane][pixel] -> raw planes, relu(raw) -> activation planes; the
-            // loads of LR rows are in flight together
+            // the previous stage's residual stream [leaf][hi | lo][plane][pixel] -> raw planes, relu(raw) -> activation planes;
+            // the loads of LR rows are in flight together
             const int hw = S.h * S.w;
-            constexpr int CPX = STAGE == 1 ? 2 : 4, LR = STAGE == 1 ? 2 : 1;
+            constexpr int CPX = STAGE == 1 ? 2 : 4, LR = (STAGE == 1 && !X3) ? 2 : 1, FX = X3 ? 2 : 1;
             for (int i0 = st; i0 < NT * 128; i0 += LR * SUB_THREADS) {
-                uint4 v[LR][CPX];
-                uint4* dst[LR];
+                uint4 v[LR][FX * CPX];
+                uint32_t dst[LR];
 #pragma unroll
                 for (int k = 0; k < LR; ++k) {
                     const int idx = i0 + k * SUB_THREADS;
-                    dst[k] = nullptr;
+                    dst[k] = 0;
                     if (idx < NT * 128) {
                         const int t = idx >> 7;
                         const uint32_t m = s_rowmap[idx & 127];
                         const int j = (int)(m & 0xff);
                         if (m != 0xffffu && j < nvalid) {
-                            const uint4* src = xin + (size_t)(b0 + j) * CPX * hw + t * S.w + ((int)(m >> 8) - 1);
-                            dst[k] = reinterpret_cast<uint4*>(arena) + (G0 + t * S.TS + (idx & 127));
+                            const uint4* src = xin + (size_t)(b0 + j) * (FX * CPX) * hw + t * S.w + ((int)(m >> 8) - 1);
+                            dst[k] = smem_u32(arena) + (uint32_t)(G0 + t * S.TS + (idx & 127)) * 16u;
 #pragma unroll
-                            for (int p = 0; p < CPX; ++p) v[k][p] = __ldg(src + (size_t)p * hw);
+                            for (int p = 0; p < FX * CPX; ++p) v[k][p] = __ldg(src + (size_t)p * hw);
                         }
                     }
                 }
@@ -532,9 +601,24 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     if (dst[k]) {
 #pragma unroll
                         for (int p = 0; p < CPX; ++p) {
-                            dst[k][(size_t)p * S.RT] = v[k][p];
-                            dst[k][(size_t)(CPX + p) * S.RT] = make_uint4(relu_bf16x2(v[k][p].x), relu_bf16x2(v[k][p].y),
-                                                                          relu_bf16x2(v[k][p].z), relu_bf16x2(v[k][p].w));
+                            const uint32_t d = dst[k] + (uint32_t)p * PS;
+                            sts128(d, v[k][p]);
+                            if (!X3) {
+                                sts128(d + (uint32_t)CPX * PS, make_uint4(relu_bf16x2(v[k][p].x), relu_bf16x2(v[k][p].y),
+                                                                          relu_bf16x2(v[k][p].z), relu_bf16x2(v[k][p].w)));
+                            } else {
+                                const uint4 lo = v[k][CPX + p];
+                                sts128(d + LO, lo);
+                                float a[8], c[8];
+                                unpack8(v[k][p], a);
+                                unpack8(lo, c);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i] + c[i], 0.f);
+                                uint4 h4, l4;
+                                split8(a, h4, l4);
+                                sts128(d + (uint32_t)CPX * PS, h4);
+                                sts128(d + (uint32_t)CPX * PS + LO, l4);
+                            }
                         }
                     }
             }
@@ -558,20 +642,25 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                 const uint32_t a_lbo = ((uint32_t)S.RT & 0x3fffu) << 16;
                 const uint32_t arena_a = smem_u32(arena);
                 uint32_t lcl = lc;
+                const uint32_t a_lo16 = LO >> 4;
+                const uint32_t nl_total = (uint32_t)n_groups * (uint32_t)S.nlay;   // layers this CTA runs in all (streaming)
                 for (int l = 0; l < nres + (has_conv ? 1 : 0); ++l, ++lcl) {
                     const bool conv = l == nres;
                     // residual layers read the activation planes, the sequence's first conv the raw stream (stage 0: input)
                     const uint32_t abase = arena_a + ((conv || STAGE == 0) ? 0u : (uint32_t)S.cp * PS);
                     const uint32_t alo0 = (((abase + (uint32_t)(G0 - 1) * 16u) >> 4) & 0x3fffu) | a_lbo;
-                    const uint64_t bd = umma_desc(smem_u32(smem + S.w_soff[l]), 3u * (uint32_t)S.cout[l], 8u);
+                    const uint32_t w_sm = smem_u32(smem) + (S.stream ? (lcl & 1u) * (uint32_t)S.slot_bytes : (uint32_t)S.w_soff[l]);
+                    const uint64_t bd = umma_desc(w_sm, 3u * (uint32_t)S.cout[l], 8u);
                     const uint32_t wlo = (uint32_t)bd, bhi = (uint32_t)(bd >> 32);
+                    const uint32_t w_lo16 = (uint32_t)S.w_len[l] >> 4;
                     const uint32_t a_kc = 2u * (uint32_t)S.RT;
                     const uint32_t rpar = (lcl - 1u) & 1u, cpar = lcl & 1u;
                     // layers are chained tile by tile while every grid row has its own accumulator slot; the sequence's first
                     // conv has another column map and starts when every slot of the last residual layer is drained: with up to
                     // 8 grid rows its first MMAs overwrite the slots and the bias is added in the epilogue, a taller image
-                    // needs the ring (wraps) and gets the bias pre-loaded behind s_cbar
-                    const bool chain = l > 0 && !conv && NT <= RR;
+                    // needs the ring (wraps) and gets the bias pre-loaded behind s_cbar.  Streamed weights: no chaining, the
+                    // previous layer is complete when this one starts, so its slot is refilled with the layer after this one.
+                    const bool chain = l > 0 && !conv && NT <= RR && !S.stream;
                     if (l > 0) {
                         if (conv && NT > 8) {   // (a conv of at most 8 grid rows opens its slots itself, see below)
                             mbar_wait(smem_u32(&s_cbar[sub]), cbar_par);
@@ -581,21 +670,30 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                             for (int t = 0; t < NT; ++t) mbar_wait(ready + 8u * (uint32_t)t, rpar);
                         tc_fence_after();
                     }
-#define GR_ISSUE(C16, CO_, R_, PRE_)                                                                                          \
+                    if (S.stream) {
+                        if (lcl >= 1u && lcl + 1u < nl_total) {
+                            const uint32_t sl = (lcl + 1u) & 1u, nl = (lcl + 1u) % (uint32_t)S.nlay;
+                            mbar_expect_tx(smem_u32(&s_wslot[sl]), (uint32_t)S.w_len[nl] * (X3 ? 2u : 1u));
+                            fetch_layer((int)nl, smem_u32(smem) + sl * (uint32_t)S.slot_bytes, smem_u32(&s_wslot[sl]));
+                        }
+                        mbar_wait(smem_u32(&s_wslot[lcl & 1u]), (lcl >> 1) & 1u);
+                    }
+#define GR_ISSUE(C16, CO_, R_, PRE_, XM_)                                                                                     \
     do {                                                                                                                      \
-        if (NT <= (R_)) issue_layer<C16, CO_, R_, false, PRE_>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain); \
-        else issue_layer<C16, CO_, R_, true, true>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain);           \
+        if (NT <= (R_)) issue_layer<C16, CO_, R_, false, PRE_, XM_>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain, a_lo16, w_lo16); \
+        else issue_layer<C16, CO_, R_, true, true, XM_>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain, a_lo16, w_lo16);           \
     } while (0)
-#define GR_ISSUE_FLAT(C16, CO_, R_, PRE_) /* layers whose grid rows always fit the ring (guaranteed by the plan) */            \
-    issue_layer<C16, CO_, R_, false, PRE_>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain)
-                    if (STAGE == 0) {
-                        if (S.cin16[0] == 1) GR_ISSUE(1, 16, 16, true);
-                        else GR_ISSUE(2, 16, 16, true);
+#define GR_ISSUE_FLAT(C16, CO_, R_, PRE_, XM_) /* layers whose grid rows always fit the ring (guaranteed by the plan) */       \
+    issue_layer<C16, CO_, R_, false, PRE_, XM_>(alo0, ahi, a_kc, (uint32_t)S.TS, wlo, bhi, NT, tmem_sub, full, ready, rpar, cpar, chain, a_lo16, w_lo16)
+                    constexpr int XMR = X3 ? 1 : 0;
+                    if (STAGE == 0) {   // the 0/1 input planes are exact in bf16: no a_lo term in the network's first layer
+                        if (S.cin16[0] == 1) GR_ISSUE(1, 16, 16, true, (X3 ? 2 : 0));
+                        else GR_ISSUE(2, 16, 16, true, (X3 ? 2 : 0));
                     } else if (STAGE == 1) {
-                        if (!conv) GR_ISSUE_FLAT(1, 16, 16, true);
-                        else GR_ISSUE(1, 32, 8, false);
-                    } else if (!conv) GR_ISSUE_FLAT(2, 32, 8, true);
-                    else GR_ISSUE_FLAT(2, 32, 8, false);
+                        if (!conv) GR_ISSUE_FLAT(1, 16, 16, true, XMR);
+                        else GR_ISSUE(1, 32, 8, false, XMR);
+                    } else if (!conv) GR_ISSUE_FLAT(2, 32, 8, true, XMR);
+                    else GR_ISSUE_FLAT(2, 32, 8, false, XMR);
 #undef GR_ISSUE_FLAT
 #undef GR_ISSUE
                 }
@@ -611,14 +709,14 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
             const uint32_t act_r = raw_r + (uint32_t)S.cp * PS;
             const float* bs = s_bias + half * NCR;
             if (STAGE == 0) {
-                if (NT <= RR) epi_layer<8, GR_CONV, 2, RR, false, false>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof);
-                else epi_layer<8, GR_CONV, 2, RR, false, true>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof);
+                if (NT <= RR) epi_layer<8, GR_CONV, 2, RR, false, false, X3>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof, LO);
+                else epi_layer<8, GR_CONV, 2, RR, false, true, X3>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof, LO);
             } else {
                 constexpr int TBR = STAGE == 1 ? 2 : 1;
                 for (int blk = 0; blk < 2; ++blk) {
-                    epi_layer<NCR, GR_RES0, TBR, RR, false, false>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk), bs + 32 * (2 * blk + 1), interior, act_r, raw_r, lane, true, tprof);
+                    epi_layer<NCR, GR_RES0, TBR, RR, false, false, X3>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk), bs + 32 * (2 * blk + 1), interior, act_r, raw_r, lane, true, tprof, LO);
                     ++lcl;
-                    epi_layer<NCR, GR_RES1, TBR, RR, false, false>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk + 1), blk == 0 ? bs + 32 * 2 : nullptr, interior, act_r, raw_r, lane, STAGE != 3 || blk == 0, tprof);
+                    epi_layer<NCR, GR_RES1, TBR, RR, false, false, X3>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk + 1), blk == 0 ? bs + 32 * 2 : nullptr, interior, act_r, raw_r, lane, STAGE != 3 || blk == 0, tprof, LO);
                     ++lcl;
                 }
                 if (STAGE != 3) {
@@ -633,9 +731,9 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                         preload_bias<16, 8>(tq_ + half * 16, NT, 32u, bc);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&s_cbar[sub]));
-                        epi_layer<16, GR_CONV, 1, 8, false, true>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, bc, nullptr, interior, t_r, t_r, lane, false, tprof);
+                        epi_layer<16, GR_CONV, 1, 8, false, true, X3>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, bc, nullptr, interior, t_r, t_r, lane, false, tprof, LO);
                     } else
-                        epi_layer<16, GR_CONV, 1, 8, true, false>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, bc, nullptr, interior, t_r, t_r, lane, false, tprof);
+                        epi_layer<16, GR_CONV, 1, 8, true, false, X3>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, bc, nullptr, interior, t_r, t_r, lane, false, tprof, LO);
                 }
             }
         }
@@ -660,20 +758,55 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                 const uint32_t a0 = abase + (uint32_t)p * PS + (uint32_t)(j * S.wp) * 16u;
                 const uint32_t c0 = a0 + (uint32_t)max(2 * ox - 1, 0) * 16u, c1 = a0 + (uint32_t)(2 * ox) * 16u,
                                c2 = a0 + (uint32_t)min(2 * ox + 1, S.w - 1) * 16u;
-                auto hmax = [&](int y) {
-                    const uint32_t ro = (uint32_t)y * trow;
-                    const uint4 a = lds128(c0 + ro), b = lds128(c1 + ro), c = lds128(c2 + ro);
-                    return make_uint4(max_bf16x2(max_bf16x2(a.x, b.x), c.x), max_bf16x2(max_bf16x2(a.y, b.y), c.y),
-                                      max_bf16x2(max_bf16x2(a.z, b.z), c.z), max_bf16x2(max_bf16x2(a.w, b.w), c.w));
-                };
-                uint4* dst = xout + (size_t)(b0 + j) * per + p * hw2 + ox;
-                uint4 up = hmax(0);
-                for (int oy = 0; oy < S.h2; ++oy) {
-                    const uint4 mid = oy ? hmax(2 * oy) : up;
-                    const uint4 lo = hmax(min(2 * oy + 1, S.h - 1));
-                    dst[oy * S.w2] = make_uint4(max_bf16x2(max_bf16x2(up.x, mid.x), lo.x), max_bf16x2(max_bf16x2(up.y, mid.y), lo.y),
-                                                max_bf16x2(max_bf16x2(up.z, mid.z), lo.z), max_bf16x2(max_bf16x2(up.w, mid.w), lo.w));
-                    up = lo;
+                if (!X3) {
+                    auto hmax = [&](int y) {
+                        const uint32_t ro = (uint32_t)y * trow;
+                        const uint4 a = lds128(c0 + ro), b = lds128(c1 + ro), c = lds128(c2 + ro);
+                        return make_uint4(max_bf16x2(max_bf16x2(a.x, b.x), c.x), max_bf16x2(max_bf16x2(a.y, b.y), c.y),
+                                          max_bf16x2(max_bf16x2(a.z, b.z), c.z), max_bf16x2(max_bf16x2(a.w, b.w), c.w));
+                    };
+                    uint4* dst = xout + (size_t)(b0 + j) * per + p * hw2 + ox;
+                    uint4 up = hmax(0);
+                    for (int oy = 0; oy < S.h2; ++oy) {
+                        const uint4 mid = oy ? hmax(2 * oy) : up;
+                        const uint4 lo = hmax(min(2 * oy + 1, S.h - 1));
+                        dst[oy * S.w2] = make_uint4(max_bf16x2(max_bf16x2(up.x, mid.x), lo.x), max_bf16x2(max_bf16x2(up.y, mid.y), lo.y),
+                                                    max_bf16x2(max_bf16x2(up.z, mid.z), lo.z), max_bf16x2(max_bf16x2(up.w, mid.w), lo.w));
+                        up = lo;
+                    }
+                } else {
+                    // split mode: values are hi + lo; hand-over layout [leaf][hi | lo][plane][pixel]
+                    struct F8 { float f[8]; };
+                    auto ld8 = [&](uint32_t a) {
+                        F8 r, q2;
+                        unpack8(lds128(a), r.f);
+                        unpack8(lds128(a + LO), q2.f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) r.f[i] += q2.f[i];
+                        return r;
+                    };
+                    auto hmax = [&](int y) {
+                        const uint32_t ro = (uint32_t)y * trow;
+                        F8 a = ld8(c0 + ro);
+                        const F8 b = ld8(c1 + ro), c = ld8(c2 + ro);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a.f[i] = fmaxf(fmaxf(a.f[i], b.f[i]), c.f[i]);
+                        return a;
+                    };
+                    uint4* dst = xout + (size_t)(b0 + j) * (2 * per) + p * hw2 + ox;
+                    F8 up = hmax(0);
+                    for (int oy = 0; oy < S.h2; ++oy) {
+                        const F8 mid = oy ? hmax(2 * oy) : up;
+                        const F8 lo = hmax(min(2 * oy + 1, S.h - 1));
+                        float m[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) m[i] = fmaxf(fmaxf(up.f[i], mid.f[i]), lo.f[i]);
+                        uint4 h4, l4;
+                        split8(m, h4, l4);
+                        dst[oy * S.w2] = h4;
+                        dst[per + oy * S.w2] = l4;
+                        up = lo;
+                    }
                 }
             }
         } else {
@@ -685,8 +818,18 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                 const int c = fdiv(f, m_hw), q = f - c * hw;
                 const int y = fdiv(q, S.m_w), x = q - y * S.w;
                 const size_t row = (size_t)G0 + (size_t)y * S.TS + (size_t)j * S.wp + (x + 1);
-                const uint16_t e = *(reinterpret_cast<const uint16_t*>(arena + ((size_t)(c >> 3) * S.RT + row) * 16) + (c & 7));
-                reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (e & 0x8000u) ? (uint16_t)0 : e;
+                const size_t eoff = ((size_t)(c >> 3) * S.RT + row) * 16;
+                const uint16_t e = *(reinterpret_cast<const uint16_t*>(arena + eoff) + (c & 7));
+                if (!X3) {
+                    reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (e & 0x8000u) ? (uint16_t)0 : e;
+                } else {   // hi, and lo feat_lo_off elements behind it
+                    const uint16_t el = *(reinterpret_cast<const uint16_t*>(arena + LO + eoff) + (c & 7));
+                    const float v = fmaxf(__uint_as_float((uint32_t)e << 16) + __uint_as_float((uint32_t)el << 16), 0.f);
+                    const uint32_t hb = pack_bf16(v, 0.f) & 0xffffu;
+                    const uint32_t lb = pack_bf16(v - __uint_as_float(hb << 16), 0.f) & 0xffffu;
+                    reinterpret_cast<uint16_t*>(feat_out)[(size_t)(b0 + j) * P.flat + f] = (uint16_t)hb;
+                    reinterpret_cast<uint16_t*>(feat_out)[(size_t)feat_lo_off + (size_t)(b0 + j) * P.flat + f] = (uint16_t)lb;
+                }
             }
         }
         sub_sync(sub);

@@ -28,10 +28,11 @@ class G:
 
 
 def make(W, H, N, B, gr, precision="bf16", scale=1.0):
-    if gr:
-        os.environ.pop("BPP_NO_GR", None)
-    else:
-        os.environ["BPP_NO_GR"] = "1"
+    for k in ("BPP_NO_GR", "BPP_NO_GR3"):
+        if gr:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = "1"
     torch.manual_seed(4)
     net = NNetWrapper(G(W, H, N), dotdict(num_items=N, num_bins=1, cuda=True, epochs=1, batch_size=8), max_batch=B,
                       precision=precision)
@@ -77,9 +78,32 @@ def check(W, H, N, B):
     return ok and d_simt < max(5e-3, 4 * d_ref) and same
 
 
-def perf(W, H, N, B, gr, iters=20):
+def check_x3(W, H, N, B):
+    """split-bf16 grid-row kernels against the previous split-bf16 path and the fp32 CUDA-core kernel"""
     recs, items = data(W, H, N, B)
-    net = make(W, H, N, B, gr)
+    new = make(W, H, N, B, True, precision="bf16x3", scale=25.0)
+    old = make(W, H, N, B, False, precision="bf16x3", scale=25.0)
+    pn, vn = new.dnet.forward(recs, items)
+    po, vo = old.dnet.forward(recs, items)
+    old.dnet.set_precision("fp32")
+    pf, vf = old.dnet.forward(recs, items)
+    torch.cuda.synchronize()
+    k = max(1, B // 3)
+    cnt = torch.tensor([k], dtype=torch.int32, device="cuda")
+    p2, v2 = torch.zeros_like(pn), torch.zeros_like(vn)
+    new.dnet.forward(recs, items, count_dev=cnt, policy_out=p2, value_out=v2)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(p2[:k], pn[:k])) and not bool(p2[k:].any())
+    d_new, d_old = float((pn - pf).abs().max()), float((po - pf).abs().max())
+    print(f"check x3 {W}x{H} N={N} B={B}: grid_row {new.dnet.grid_row()} finite {bool(torch.isfinite(pn).all())}  |new-fp32| {d_new:.2e}  "
+          f"|old-fp32| {d_old:.2e}  |new-old| {float((pn - po).abs().max()):.2e}  |dv| {float((vn - vf).abs().max()):.2e}  "
+          f"count_dev ok {same}", flush=True)
+    return d_new < max(1e-3, 4 * d_old) and same
+
+
+def perf(W, H, N, B, gr, iters=20, precision="bf16"):
+    recs, items = data(W, H, N, B)
+    net = make(W, H, N, B, gr, precision=precision)
     pol = torch.empty((B, W * N), dtype=torch.float32, device="cuda")
     val = torch.empty(B, dtype=torch.float32, device="cuda")
     for _ in range(3):
@@ -98,7 +122,7 @@ def perf(W, H, N, B, gr, iters=20):
             extra = str(net.dnet.profile_roles())
         except Exception as err:  # noqa: BLE001
             extra = repr(err)
-    print(f"perf {W}x{H} B={B} {'grid-row' if gr else 'previous'}: {ms * 1e3:.1f} us  {B / ms / 1e3:.2f} M evals/s  "
+    print(f"perf {precision} {W}x{H} B={B} {'grid-row' if gr else 'previous'}: {ms * 1e3:.1f} us  {B / ms / 1e3:.2f} M evals/s  "
           f"{B * FLOPS[(W, H, N)] / ms / 1e9:.1f} TFLOP/s  {extra}", flush=True)
 
 
@@ -116,6 +140,17 @@ if __name__ == "__main__":
             print("== BPP_GR_SERIAL =", mode, flush=True)
             for c in cases[:3]:
                 check(*c)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "x3":
+        os.environ["BPP_TC_VERBOSE"] = "1"
+        for c in cases:
+            good = check_x3(*c) and good
+        os.environ.pop("BPP_TC_VERBOSE", None)
+        print("ALL X3 CHECKS", "PASS" if good else "FAIL", flush=True)
+        for (W, H) in [(15, 15), (20, 20)]:
+            for B in (2800, 8192):
+                perf(W, H, 10, B, True, precision="bf16x3")
+                perf(W, H, 10, B, False, precision="bf16x3")
         sys.exit(0)
     for c in cases:
         good = check(*c) and good
