@@ -1467,6 +1467,8 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
         const int cin16_0 = (P.Cin + 15) / 16;
         const int chans_in[4] = {16 * cin16_0, 16, 32, 32};
         const int cap = 232448 - 8 * 1024;   // 227 KB per block minus the kernel's static shared memory
+        n->gr_elems = 0;   // all 15 layers in the grid-row layout, whichever plans succeed
+        for (int l = 0; l < NCONV; ++l) n->gr_elems += 9LL * ((P.conv[l].ci + 15) / 16) * 2 * P.conv[l].co * 8;
         for (int x3 = 0; x3 < 2; ++x3) {
             long long goff = 0;
             bool ok = getenv(x3 ? "BPP_NO_GR3" : "BPP_NO_GR") == nullptr && P.flat % 16 == 0 && (x3 ? n->heads3_ok : n->heads_ok);
@@ -1541,7 +1543,6 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                             "%d B shared memory (weights %d)\n", s, x3 ? "bf16x3" : "bf16", G.h, G.w, G.J, G.TS, G.nsub,
                             G.stream ? "streamed" : "resident", G.smem_bytes, G.w_bytes);
             }
-            n->gr_elems = goff;
             (x3 ? n->gr3_ok : n->gr_ok) = ok;
         }
         if (n->gr_ok || n->gr3_ok) {   // weights in the grid-row layout (hi, lo) and the hand-over buffers x1..x3 (hi + lo)

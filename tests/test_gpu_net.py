@@ -276,3 +276,49 @@ def test_grid_row_stage_kernels_match_the_previous_tensor_core_path_and_the_simt
     assert np.abs(g[0] - sm[0]).max() <= max(5e-4, 4 * ref) and np.abs(g[1] - sm[1]).max() <= 2e-3
     assert np.abs(g[0] - p[0]).max() <= max(5e-4, 4 * ref)
     assert np.array_equal(g[2][:k], g[0][:k]) and not g[2][k:].any()   # results do not depend on the grouping
+
+
+@pytest.mark.parametrize("W,H,N,B", [(15, 15, 10, 333), (20, 20, 10, 150), (9, 12, 5, 64), (25, 28, 10, 40)])
+def test_split_bf16_grid_row_kernels_match_the_fp32_kernel_and_the_previous_split_path(W, H, N, B, monkeypatch):
+    """The split-bf16 mode of the grid-row stage kernels (hi + lo arena and weights, weights streamed through two slots
+    where they do not fit) against the CUDA-core fp32 kernel and the previous split-bf16 kernels (BPP_NO_GR3=1), with the
+    logits scaled up as in the reference's trained checkpoints; ragged batches and the device-side batch size."""
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+    rng = np.random.RandomState(5)
+    recs = np.zeros((B, 32), dtype=np.uint32)
+    recs[:, :H] = rng.randint(0, 1 << W, size=(B, H)) & rng.randint(0, 1 << W, size=(B, H))
+    recs[:, 28] = rng.randint(1, 1 << N, size=B)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(B) % 53 + 9, None)
+    outs = {}
+    for tag in ("gr", "prev"):
+        if tag == "gr":
+            monkeypatch.delenv("BPP_NO_GR3", raising=False)
+        else:
+            monkeypatch.setenv("BPP_NO_GR3", "1")
+        torch.manual_seed(4)
+        net = NNetWrapper(_Game(W, H, N), dotdict(num_items=N, num_bins=1, cuda=True, epochs=1, batch_size=8),
+                          max_batch=B, precision="bf16x3")
+        with torch.no_grad():
+            net.nnet.logits_fc.weight.mul_(25.0)
+        net.sync_weights()
+        assert net.dnet.grid_row() == (tag == "gr")
+        dev = net.device
+        r_t, i_t = torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev)
+        pol, val = net.dnet.forward(r_t, i_t)
+        k = max(1, B // 3)
+        count = torch.tensor([k], dtype=torch.int32, device=dev)
+        pol2, val2 = torch.zeros_like(pol), torch.zeros_like(val)
+        net.dnet.forward(r_t, i_t, count_dev=count, policy_out=pol2, value_out=val2)
+        if tag == "prev":
+            net.dnet.set_precision("fp32")
+            pf, vf = net.dnet.forward(r_t, i_t)
+            outs["fp32"] = (pf.cpu().numpy(), vf.cpu().numpy())
+        torch.cuda.synchronize()
+        outs[tag] = (pol.cpu().numpy(), val.cpu().numpy(), pol2.cpu().numpy())
+    g, p, f32 = outs["gr"], outs["prev"], outs["fp32"]
+    assert np.isfinite(g[0]).all() and abs(g[0].sum(axis=1) - 1).max() < 1e-4
+    assert np.abs(g[0] - f32[0]).max() <= 2e-4 and np.abs(g[1] - f32[1]).max() <= 2e-4   # fp32-level accuracy
+    assert np.abs(g[0] - p[0]).max() <= 2e-4
+    assert np.array_equal(g[2][:k], g[0][:k]) and not g[2][k:].any()
