@@ -35,6 +35,10 @@
 // (BinpackingNNet.py:29-48,72-81).
 #pragma once
 
+#ifndef BPP_GR_TB23
+#define BPP_GR_TB23 1   // tiles per epilogue batch in stages 2, 3 (16 columns per warp)
+#endif
+
 namespace bppgr {
 using namespace bpptc;
 
@@ -484,8 +488,7 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
     // everything above is independent of the kernel that produced this stage's input
     pdl_launch_dependents();
     pdl_wait();
-    if (!S.stream) mbar_wait(smem_u32(&s_wbar), 0);
-    const long long t_start = clock64();
+    const long long t_start = clock64();   // (only the issuing threads wait for the weights, before their first MMA)
     long long t_in = 0, t_cv = 0, t_out = 0;
 
     const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
@@ -643,6 +646,7 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                 const uint32_t arena_a = smem_u32(arena);
                 uint32_t lcl = lc;
                 const uint32_t a_lo16 = LO >> 4;
+                if (!S.stream && lc == 0) mbar_wait(smem_u32(&s_wbar), 0);   // resident weights have landed
                 const uint32_t nl_total = (uint32_t)n_groups * (uint32_t)S.nlay;   // layers this CTA runs in all (streaming)
                 for (int l = 0; l < nres + (has_conv ? 1 : 0); ++l, ++lcl) {
                     const bool conv = l == nres;
@@ -712,7 +716,7 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                 if (NT <= RR) epi_layer<8, GR_CONV, 2, RR, false, false, X3>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof, LO);
                 else epi_layer<8, GR_CONV, 2, RR, false, true, X3>(NT, tile_bytes, PS, tq_ + half * 8, full, ready, lcl & 1u, 16u, bs, nullptr, interior, raw_r, raw_r, lane, false, tprof, LO);
             } else {
-                constexpr int TBR = STAGE == 1 ? 2 : 1;
+                constexpr int TBR = STAGE == 1 ? 2 : BPP_GR_TB23;
                 for (int blk = 0; blk < 2; ++blk) {
                     epi_layer<NCR, GR_RES0, TBR, RR, false, false, X3>(NT, tile_bytes, PS, tq_ + half * NCR, full, ready, lcl & 1u, CO, bs + 32 * (2 * blk), bs + 32 * (2 * blk + 1), interior, act_r, raw_r, lane, true, tprof, LO);
                     ++lcl;

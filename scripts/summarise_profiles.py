@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Summarise the ncu reports of scripts/capture_profiles.sh (run here, no GPU needed: `ncu -i`): writes
-profiles/r02_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic) and one text summary per report."""
+"""Summarise the ncu reports of scripts/capture_profiles.sh (`ncu -i`, no GPU needed; the capture script runs it on the GPU
+box into gpurun_out/prof/ because the reports themselves exceed what gpurun copies back): writes r02_traffic.json (DRAM bytes
+per launch, read by bench.py for roofline.traffic) and one text summary per report.
+    python scripts/summarise_profiles.py [output directory, default profiles/]"""
 import csv
 import io
 import json
@@ -10,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-PROF = os.path.join(ROOT, "profiles")
+PROF = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles")   # summaries + r02_traffic.json go here
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -47,6 +49,7 @@ def raw(rep):
 
 
 def main():
+    os.makedirs(PROF, exist_ok=True)
     traffic = {}
     for rep in sorted(f for f in os.listdir(OUT) if f.startswith("r02_") and f.endswith(".ncu-rep")):
         ks = raw(os.path.join(OUT, rep))
