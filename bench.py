@@ -302,7 +302,9 @@ class Ctx:
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            # a rank that diverges must fail the run in minutes, not after NCCL's default 10-minute watchdog
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=240))
         self.sampler = ClockSampler(self.local)
         self.sampler.start()
         self.peaks = load_peaks()
@@ -656,7 +658,7 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
                                    "sample": f"{eps} episodes in {dt:.1f} s; {src} + fp32 torch net on CPU"}
     bm.close()
     net.dnet.close()
-    return rec
+    return rec if cx.rank == 0 else {"precision_mode": mode, "rank_stub": True}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -808,14 +810,16 @@ def main():
             return {"error": f"{type(err).__name__}: {err}"}
     if "real15" in todo:
         r = guarded("real15", lambda: run_real_arm(cx, 15, 15, args.precision))
+        # every rank must take the same branch (the arms contain collectives): the mode the calibration picked is a function
+        # of the weights and identical on all ranks; only rank 0 holds the full record
         if r is not None and "error" not in r and args.precision == "auto" and r["precision_mode"] != "bf16":
             b = guarded("real15_bf16", lambda: run_real_arm(cx, 15, 15, "bf16", with_e2e=False, with_cpu=False))
-            if b is not None and "error" not in b:
+            if b is not None and "error" not in b and not b.get("rank_stub"):
                 r["bf16"] = {"value": b["value"], "leaf_evals_per_sec": b["leaf_evals_per_sec"],
                              "roofline": b["roofline"], "lockstep_steps_per_batch": b["lockstep_steps_per_batch"],
                              "note": "plain bf16 on this trained checkpoint is OUT of the stated tolerance (|d pi| up to "
                                      "0.6, profiles/r02_precision_study.txt): throughput shown for comparison only"}
-            else:
+            elif not r.get("rank_stub"):
                 r["bf16"] = b
         sec["real15"] = r
     if "real20" in todo:
@@ -835,7 +839,7 @@ def main():
                     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": r.get("dtype"),
                     "data": "synthetic", "config": r.get("config"), "e2e": r.get("e2e"), "roofline": r.get("roofline"),
                     "clocks": r.get("clocks"), "gpu_launches": r.get("gpu_launches")}
-        line["secondary"] = {k: v for k, v in sec.items() if v is not None}
+        line["secondary"] = {k: v for k, v in sec.items() if v is not None and not (isinstance(v, dict) and v.get("rank_stub"))}
         line["bench_wall_s"] = time.perf_counter() - t_start
         print(json.dumps(line))
     cx.close()
