@@ -542,9 +542,9 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
 
     # episodes per step, streamed through the G resident games.  A game that needs the evaluator on every simulation (flat
     # prior) takes numMCTSSims x moves sequential lockstep steps whatever the batch does, so the stream must be long against
-    # that tail: 16 x G with the sharp trained policy (whose bulk of episodes is over in ~300 steps), 4 x G with the
-    # random-init net (all episodes alike)
-    mult = args.stream_mult or (16 if (Wb, Hb) == (15, 15) else 4)
+    # that tail: 16 x G with the sharp trained policy (whose bulk of episodes is over in ~300 steps), 8 x G with the
+    # random-init net (all episodes alike; 4 x G: fill 0.76, 8 x G: 0.81, 16 x G: 0.83)
+    mult = args.stream_mult or (16 if (Wb, Hb) == (15, 15) else 8)
     E = mult * G
 
     def instances(k):

@@ -322,3 +322,35 @@ def test_split_bf16_grid_row_kernels_match_the_fp32_kernel_and_the_previous_spli
     assert np.abs(g[0] - f32[0]).max() <= 2e-4 and np.abs(g[1] - f32[1]).max() <= 2e-4   # fp32-level accuracy
     assert np.abs(g[0] - p[0]).max() <= 2e-4
     assert np.array_equal(g[2][:k], g[0][:k]) and not g[2][k:].any()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_grid_row_kernels_reproduce_their_outputs_bit_for_bit(precision):
+    """Repeated launches on the same inputs give identical bits for many batch sizes (one group per SM, partial groups, more
+    groups than SMs): a race in the per-tile mbarrier hand-over between the MMA issuer and the epilogue warps, or between the
+    two groups of a CTA, would show up as a rare difference."""
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+    W, H, N, Bmax = 15, 15, 10, 5000
+    rng = np.random.RandomState(11)
+    recs = np.zeros((Bmax, 32), dtype=np.uint32)
+    recs[:, :H] = rng.randint(0, 1 << W, size=(Bmax, H)) & rng.randint(0, 1 << W, size=(Bmax, H))
+    recs[:, 28] = rng.randint(1, 1 << N, size=Bmax)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(Bmax) % 53 + 9, None)
+    torch.manual_seed(4)
+    net = NNetWrapper(_Game(W, H, N), dotdict(num_items=N, num_bins=1, cuda=True, epochs=1, batch_size=8), max_batch=Bmax,
+                      precision=precision)
+    assert net.dnet.grid_row()
+    dev = net.device
+    r_t, i_t = torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev)
+    for B in (1, 9, 148, 297, 1211, 2800, 4097, 5000):
+        p0, v0 = net.dnet.forward(r_t[:B].contiguous(), i_t[:B].contiguous())
+        p0, v0 = p0.clone(), v0.clone()
+        for _ in range(3):
+            p1, v1 = net.dnet.forward(r_t[:B].contiguous(), i_t[:B].contiguous())
+            assert torch.equal(p1, p0) and torch.equal(v1, v0), B
+    # a leaf's result does not depend on the batch it is evaluated in
+    pa, _ = net.dnet.forward(r_t[:2800].contiguous(), i_t[:2800].contiguous())
+    pb, _ = net.dnet.forward(r_t[:300].contiguous(), i_t[:300].contiguous())
+    assert torch.equal(pa[:300], pb)
