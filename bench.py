@@ -534,7 +534,7 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
     warmup = warmup if warmup is not None else max(3, args.warmup)
     net, weights = _make_net(cx, Wb, Hb, G, precision)
     mode = net.dnet.precision
-    net_kernels = 5 if net.dnet.grid_row() else 2   # evaluator kernels per lockstep step: four stage kernels + heads | trunk + heads
+    net_kernels = 2   # evaluator kernels per lockstep step: trunk (k_net_gr: the four levels in one launch) + heads
     bm = BatchedMCTS(_Gm(Wb, Hb), net, _margs(args.sims), G, device=cx.local)
     eng = bm.eng
     gen = ItemsGenerator(Wb, Hb, N)
@@ -626,7 +626,7 @@ def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, ste
                "lockstep_steps_per_batch": float(np.mean(lock_steps)),
                "leaf_batch_fill": exps / max(1.0, cx.world * sum(lock_steps) * G),
                "gpu_launches": int(launches),
-               "roofline": {"bound": "tensor", "kernel": ("k_net_gr<0..3> + k_net_heads_tc (four grid-row stage kernels + FC heads)" if net_kernels == 5 else "k_net_forward_tc / k_net_role + k_net_heads_tc (trunk + FC heads)"),
+               "roofline": {"bound": "tensor", "kernel": ("k_net_gr + k_net_heads_tc (grid-row trunk, four levels in one launch, + FC heads)" if net.dnet.grid_row() else "k_net_forward_tc / k_net_role + k_net_heads_tc (trunk + FC heads)"),
                             "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak if achieved else None,
                             "traffic": cap.get("dram_bytes_per_launch"),

@@ -1104,6 +1104,7 @@ struct bpp_net {
     // grid-row trunk (k_net_gr, bpp_net_gr.cuh): one plan per level
     bppgr::GrStage Gr[4], Gr3[4];   // bf16, split-bf16
     bool gr_ok = false, gr3_ok = false;
+    int gr_smem[2] = {0, 0}, gr_threads[2] = {0, 0};   // fused launch: dynamic shared memory, threads per CTA
     __nv_bfloat16* d_wts_gr = nullptr;
     __nv_bfloat16* d_wts_gr_lo = nullptr;
     long long gr_elems = 0;
@@ -1466,7 +1467,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
     {
         const int cin16_0 = (P.Cin + 15) / 16;
         const int chans_in[4] = {16 * cin16_0, 16, 32, 32};
-        const int cap = 232448 - 8 * 1024;   // 227 KB per block minus the kernel's static shared memory
+        const int cap = 232448 - 4608;   // 227 KB per block minus the kernel's static shared memory (barriers, row map, biases)
         n->gr_elems = 0;   // all 15 layers in the grid-row layout, whichever plans succeed
         for (int l = 0; l < NCONV; ++l) n->gr_elems += 9LL * ((P.conv[l].ci + 15) / 16) * 2 * P.conv[l].co * 8;
         for (int x3 = 0; x3 < 2; ++x3) {
@@ -1522,7 +1523,7 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
                             G.slot_bytes = (wmax + 127) & ~127;
                             G.w_bytes = stream ? 2 * G.slot_bytes : off;
                             G.arena_off = (G.w_bytes + G.nlay * 32 * 4 + 127) & ~127;
-                            G.smem_bytes = G.arena_off + ns * G.arena_bytes;
+                            G.smem_bytes = G.arena_off + ns * G.arena_bytes + (s == 0 ? (int)sizeof(bppgr::GrStage0Tables) : 0);
                             if (G.smem_bytes > cap || G.RT >= 16384) continue;
                             const double score = (double)J * ns * (stream ? 0.9 : 1.0) + 1e-3 * J;
                             if (score > best_score) { best_score = score; best = G; fit = true; }
@@ -1554,12 +1555,16 @@ extern "C" int bpp_net_create(int W, int H, int N, int max_batch, int device, bp
             auto attr = [&](const void* fn, int bytes) {
                 return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
             };
-            if (ok && n->gr_ok)
-                ok = attr((const void*)bppgr::k_net_gr<0, false>, n->Gr[0].smem_bytes) && attr((const void*)bppgr::k_net_gr<1, false>, n->Gr[1].smem_bytes) &&
-                     attr((const void*)bppgr::k_net_gr<2, false>, n->Gr[2].smem_bytes) && attr((const void*)bppgr::k_net_gr<3, false>, n->Gr[3].smem_bytes);
-            if (ok && n->gr3_ok)
-                ok = attr((const void*)bppgr::k_net_gr<0, true>, n->Gr3[0].smem_bytes) && attr((const void*)bppgr::k_net_gr<1, true>, n->Gr3[1].smem_bytes) &&
-                     attr((const void*)bppgr::k_net_gr<2, true>, n->Gr3[2].smem_bytes) && attr((const void*)bppgr::k_net_gr<3, true>, n->Gr3[3].smem_bytes);
+            for (int x3 = 0; x3 < 2; ++x3) {   // one launch runs the four stages: common TMEM allocation, largest footprint
+                bppgr::GrStage* G = x3 ? n->Gr3 : n->Gr;
+                int cols = 0, sm = 0, ns = 1;
+                for (int s2 = 0; s2 < 4; ++s2) { cols = std::max(cols, G[s2].tmem_cols); sm = std::max(sm, G[s2].smem_bytes); ns = std::max(ns, G[s2].nsub); }
+                for (int s2 = 0; s2 < 4; ++s2) G[s2].tmem_cols = cols;
+                n->gr_smem[x3] = sm;
+                n->gr_threads[x3] = ns * bppgr::SUB_THREADS;
+            }
+            if (ok && n->gr_ok) ok = attr((const void*)bppgr::k_net_gr<false>, n->gr_smem[0]);
+            if (ok && n->gr3_ok) ok = attr((const void*)bppgr::k_net_gr<true>, n->gr_smem[1]);
             if (!ok) {
                 cudaGetLastError();
                 n->gr_ok = n->gr3_ok = false;
@@ -1857,29 +1862,21 @@ static int launch_roles(bpp_net* n, int x3, int B, const int32_t* count_dev, con
 }
 
 
-// grid-row trunk: four level kernels chained by programmatic launches (bpp_net_gr.cuh)
+// grid-row trunk: the four levels in one launch (bpp_net_gr.cuh); every CTA takes its share of the batch through all of them
 static int launch_gr(bpp_net* n, int x3, int B, const int32_t* count_dev, const uint32_t* recs_dev, const int32_t* game_dev,
                      const int32_t* items_wh_dev, cudaStream_t st) {
-    cudaError_t ce = cudaSuccess;
+    const bppgr::GrStage* G = x3 ? n->Gr3 : n->Gr;
     const long long flo = (long long)n->max_batch * n->P.flat;
-    for (int s = 0; s < 4 && ce == cudaSuccess; ++s) {
-        const bppgr::GrStage& G = (x3 ? n->Gr3 : n->Gr)[s];
-        const int groups = (B + G.J - 1) / G.J;
-        const int gr = std::max(1, std::min((groups + G.nsub - 1) / G.nsub, n->num_sms));
-        const uint4* xin = s == 0 ? nullptr : n->d_g[s - 1];
-        uint4* xout = s < 3 ? n->d_g[s] : nullptr;
-#define GR_LAUNCH(SQ, X)                                                                                                      \
-    ce = launch_pdl(bppgr::k_net_gr<SQ, X>, gr, G.nsub * bppgr::SUB_THREADS, (size_t)G.smem_bytes, st, n->P, G, B, count_dev, \
-                    recs_dev, game_dev, items_wh_dev, xin, xout, n->d_feat, flo, (const __nv_bfloat16*)n->d_wts_gr,          \
-                    (const __nv_bfloat16*)n->d_wts_gr_lo, n->d_prof)
-#define GR_PICK(SQ) do { if (x3) GR_LAUNCH(SQ, true); else GR_LAUNCH(SQ, false); } while (0)
-        if (s == 0) GR_PICK(0);
-        else if (s == 1) GR_PICK(1);
-        else if (s == 2) GR_PICK(2);
-        else GR_PICK(3);
-#undef GR_PICK
-#undef GR_LAUNCH
-    }
+    const int grid = std::max(1, std::min((B + 7) / 8, n->num_sms));
+    cudaError_t ce;
+    if (x3)
+        ce = launch_pdl(bppgr::k_net_gr<true>, grid, n->gr_threads[1], (size_t)n->gr_smem[1], st, n->P, G[0], G[1], G[2], G[3], B,
+                        count_dev, recs_dev, game_dev, items_wh_dev, n->d_g[0], n->d_g[1], n->d_g[2], n->d_feat, flo,
+                        (const __nv_bfloat16*)n->d_wts_gr, (const __nv_bfloat16*)n->d_wts_gr_lo, n->d_prof);
+    else
+        ce = launch_pdl(bppgr::k_net_gr<false>, grid, n->gr_threads[0], (size_t)n->gr_smem[0], st, n->P, G[0], G[1], G[2], G[3], B,
+                        count_dev, recs_dev, game_dev, items_wh_dev, n->d_g[0], n->d_g[1], n->d_g[2], n->d_feat, flo,
+                        (const __nv_bfloat16*)n->d_wts_gr, (const __nv_bfloat16*)n->d_wts_gr_lo, n->d_prof);
     if (ce != cudaSuccess) return nerr(BPP_E_CUDA, std::string("grid-row kernel launch failed: ") + cudaGetErrorString(ce));
     return BPP_OK;
 }

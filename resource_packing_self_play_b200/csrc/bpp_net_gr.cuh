@@ -397,53 +397,76 @@ __device__ __forceinline__ void epi_layer(int NT, uint32_t tile_bytes, uint32_t 
     }
 }
 
-// X3 = split-bf16 mode: activations and weights as hi + lo bf16 halves, three MMAs per product, fp32-level accuracy for the
-// reference's trained checkpoints; one group per CTA (the doubled arena leaves no room for two)
+// barriers and small tables of a CTA (static shared memory, shared by the four stages of the fused kernel)
+struct GrShared {
+    uint64_t full[2][MAX_TILES];    // [sub][tile]: the MMAs of input tile t are complete
+    uint64_t ready[2][MAX_TILES];   // [sub][tile]: output tile t stored, its accumulator slot drained (8 warp arrivals)
+    uint64_t wbar;                  // resident weights have landed
+    uint64_t cbar[2];               // conv bias pre-loaded (8 warps), per sub
+    uint64_t wslot[2];              // streamed weights: slot filled
+    uint32_t tmem;
+    long long tprof[8];
+    uint16_t rowmap[128];           // row r of a tile -> leaf j | xp << 8 (0xffff: not a pixel row)
+    float bias[15][32];             // biases of all conv layers (fetched once per launch), global layer index
+};
+// stage 0's per-group tables live in dynamic shared memory behind its arenas (12.3 KB)
+struct GrStage0Tables {
+    uint32_t rec[2][8][32];                  // [sub][leaf]: compact record
+    uint32_t msk[2][8][2][32];               // [sub][leaf][rows | columns][index]: items reaching grid row y / column x
+    int it[2][8][2 * BPP_MAX_ITEMS];         // [sub][leaf][item: w, h]
+    uint4 lut[256];                          // 8 channel bits -> 8 x bf16 {0, 1}
+};
+
+// One level of the trunk for this CTA's share of the batch.  X3 = split-bf16 mode: activations and weights as hi + lo bf16
+// halves, three MMAs per product, fp32-level accuracy for the reference's trained checkpoints; one group per
+// CTA (the doubled arena leaves no room for two).  Called by every thread of the CTA; `first` = the CTA has not run a stage
+// yet (barriers are fresh, nothing to wait for).
 template <int STAGE, bool X3>
-__global__ void __launch_bounds__(X3 ? SUB_THREADS : 2 * SUB_THREADS, 1)
-k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev, const uint32_t* __restrict__ recs,
-         const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh, const uint4* __restrict__ xin,
-         uint4* __restrict__ xout, __nv_bfloat16* __restrict__ feat_out, long long feat_lo_off,
-         const __nv_bfloat16* __restrict__ wts_gr, const __nv_bfloat16* __restrict__ wts_gr_lo, long long* prof) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_full[2][MAX_TILES];
-    __shared__ __align__(8) uint64_t s_ready[2][MAX_TILES];
-    __shared__ __align__(8) uint64_t s_wbar;
-    __shared__ __align__(8) uint64_t s_cbar[2];   // conv bias pre-loaded (8 warps), per sub
-    __shared__ __align__(8) uint64_t s_wslot[2];  // streamed weights: slot filled
-    __shared__ uint32_t s_tmem;
-    __shared__ long long s_tprof[8];
-    __shared__ uint16_t s_rowmap[128];   // row r of a tile -> leaf j | xp << 8 (0xffff: not a pixel row)
-    __shared__ uint32_t s_rec[STAGE == 0 ? 2 : 1][STAGE == 0 ? 8 : 1][32];
-    __shared__ uint32_t s_msk[STAGE == 0 ? 2 : 1][STAGE == 0 ? 8 : 1][2][32];   // [sub][leaf][rows | columns][index]
-    __shared__ int s_it[STAGE == 0 ? 2 : 1][STAGE == 0 ? 8 : 1][2 * BPP_MAX_ITEMS];     // [sub][leaf][item: w, h]
-    __shared__ uint4 s_lut[STAGE == 0 ? 256 : 1];                                 // 8 channel bits -> 8 x bf16 {0, 1}
+__device__ __forceinline__ void gr_stage(const NetParams& P, const GrStage& S, int B, const uint32_t* __restrict__ recs,
+                                         const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh,
+                                         const uint4* xin, uint4* xout, __nv_bfloat16* __restrict__ feat_out,
+                                         long long feat_lo_off, const __nv_bfloat16* __restrict__ wts_gr,
+                                         const __nv_bfloat16* __restrict__ wts_gr_lo, long long* prof, unsigned char* smem,
+                                         GrShared& sh, bool first) {
+    GrStage0Tables& t0 = *reinterpret_cast<GrStage0Tables*>(smem + S.arena_off + (size_t)S.nsub * S.arena_bytes);
+    const long long t_enter = clock64();
     const int tid = threadIdx.x;
     const int sub = tid >= SUB_THREADS ? 1 : 0;
     const int st = tid - sub * SUB_THREADS;          // thread inside the sub
     const int warp_s = st >> 5, lane = tid & 31;
-    const int nthreads = S.nsub * SUB_THREADS;
-    float* s_bias = reinterpret_cast<float*>(smem + S.w_bytes);   // [nlay][32]
+    const int nthreads = (int)blockDim.x;   // (a stage that runs one group per CTA leaves the second sub idle)
+    float* s_bias = &sh.bias[STAGE == 0 ? 0 : 5 * (STAGE - 1) + 1][0];   // [nlay][32], this stage's layers
     unsigned char* arena = smem + S.arena_off + (size_t)sub * S.arena_bytes;
     const uint32_t PS = (uint32_t)S.RT * 16u;
     const uint32_t LO = (uint32_t)S.lo_off;   // split mode: lo planes behind the hi planes
 
+    // every stage starts with fresh barriers (its own phase counting)
+    if (!first) {
+        __syncthreads();
+        if (tid < 2 * MAX_TILES) {
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.full[0][0]) + 8u * (uint32_t)tid) : "memory");
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.ready[0][0]) + 8u * (uint32_t)tid) : "memory");
+        }
+        if (tid == 0) {
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.wbar)) : "memory");
+            for (int k = 0; k < 2; ++k) {
+                asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.cbar[k])) : "memory");
+                asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.wslot[k])) : "memory");
+            }
+        }
+        __syncthreads();
+    }
     if (tid < 2 * MAX_TILES) {
-        mbar_init(smem_u32(&s_full[0][0]) + 8u * (uint32_t)tid, 1);
-        mbar_init(smem_u32(&s_ready[0][0]) + 8u * (uint32_t)tid, 8);
+        mbar_init(smem_u32(&sh.full[0][0]) + 8u * (uint32_t)tid, 1);
+        mbar_init(smem_u32(&sh.ready[0][0]) + 8u * (uint32_t)tid, 8);
     }
     if (tid == 0) {
-        mbar_init(smem_u32(&s_wbar), 1); mbar_init(smem_u32(&s_cbar[0]), 8); mbar_init(smem_u32(&s_cbar[1]), 8);
-        mbar_init(smem_u32(&s_wslot[0]), 1); mbar_init(smem_u32(&s_wslot[1]), 1);
-    }
-    if (tid < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "r"((uint32_t)S.tmem_cols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        mbar_init(smem_u32(&sh.wbar), 1); mbar_init(smem_u32(&sh.cbar[0]), 8); mbar_init(smem_u32(&sh.cbar[1]), 8);
+        mbar_init(smem_u32(&sh.wslot[0]), 1); mbar_init(smem_u32(&sh.wslot[1]), 1);
     }
     if (tid < 128) {
         const int j = tid / S.wp, xp = tid - j * S.wp;
-        s_rowmap[tid] = (tid < S.J * S.wp && xp != 0) ? (uint16_t)(j | (xp << 8)) : (uint16_t)0xffff;
+        sh.rowmap[tid] = (tid < S.J * S.wp && xp != 0) ? (uint16_t)(j | (xp << 8)) : (uint16_t)0xffff;
     }
     if (STAGE == 0 && tid < 256) {
         const uint32_t b8 = (uint32_t)tid;
@@ -452,17 +475,13 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
         v.y = (((b8 >> 2) & 1u) | ((b8 & 8u) << 13)) * 0x3f80u;
         v.z = (((b8 >> 4) & 1u) | ((b8 & 32u) << 11)) * 0x3f80u;
         v.w = (((b8 >> 6) & 1u) | ((b8 & 128u) << 9)) * 0x3f80u;
-        s_lut[tid] = v;
+        t0.lut[tid] = v;
     }
     // halo rows, guards and padding rows are zero from here on: no epilogue, input or hand-over pass ever writes them
     {
         uint4* q = reinterpret_cast<uint4*>(smem + S.arena_off);
         const int n16 = S.nsub * S.arena_bytes / 16;
         for (int i = tid; i < n16; i += nthreads) q[i] = make_uint4(0, 0, 0, 0);
-    }
-    for (int i = tid; i < S.nlay * 32; i += nthreads) {
-        const int l = i >> 5, c = i & 31;
-        s_bias[i] = c < S.cout[l] ? P.bias[S.b_goff[l] + c] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -474,24 +493,23 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
         if (X3) bulk_g2s(dst + (uint32_t)S.w_len[l], wts_gr_lo + S.w_goff[l], (uint32_t)S.w_len[l], bar);
     };
     if (tid == 0) {
+        fence_proxy_async();   // the previous stage used this memory through the generic proxy
         if (!S.stream) {
-            const uint32_t wb = smem_u32(&s_wbar);
+            const uint32_t wb = smem_u32(&sh.wbar);
             mbar_expect_tx(wb, (uint32_t)S.w_bytes);
             for (int l = 0; l < S.nlay; ++l) fetch_layer(l, smem_u32(smem + S.w_soff[l]), wb);
         } else {
             for (int g = 0; g < 2 && g < S.nlay; ++g) {
-                mbar_expect_tx(smem_u32(&s_wslot[g]), (uint32_t)S.w_len[g] * (X3 ? 2u : 1u));
-                fetch_layer(g, smem_u32(smem + g * S.slot_bytes), smem_u32(&s_wslot[g]));
+                mbar_expect_tx(smem_u32(&sh.wslot[g]), (uint32_t)S.w_len[g] * (X3 ? 2u : 1u));
+                fetch_layer(g, smem_u32(smem + g * S.slot_bytes), smem_u32(&sh.wslot[g]));
             }
         }
     }
-    // everything above is independent of the kernel that produced this stage's input
-    pdl_launch_dependents();
-    pdl_wait();
     const long long t_start = clock64();   // (only the issuing threads wait for the weights, before their first MMA)
     long long t_in = 0, t_cv = 0, t_out = 0;
 
-    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
+    // this CTA's share of the batch is the same contiguous range of leaves in every stage (its subs split it), so a stage
+    // only ever reads hand-over data written by its own CTA
     const int nwork = gridDim.x * S.nsub, wid = blockIdx.x * S.nsub + sub;
     const int slice_lo = (int)(((long long)wid * B) / nwork);
     const int slice_hi = (int)(((long long)(wid + 1) * B) / nwork);
@@ -499,21 +517,21 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
     const int n_groups = (n_slice + S.J - 1) / S.J;
     const int gsz = n_groups > 0 ? (n_slice + n_groups - 1) / n_groups : S.J;
 
-    const uint32_t tmem_sub = s_tmem + (uint32_t)(sub * S.col_sub);
-    const uint32_t full = smem_u32(&s_full[sub][0]), ready = smem_u32(&s_ready[sub][0]);
+    const uint32_t tmem_sub = sh.tmem + (uint32_t)(sub * 256);
+    const uint32_t full = smem_u32(&sh.full[sub][0]), ready = smem_u32(&sh.ready[sub][0]);
     const int NT = S.NT;
     // epilogue warps: this thread's pixel row inside every tile
     // a warp reads the TMEM lane quarter of its CTA-wide warp index (sub 1 starts at warp 9): the eight epilogue warps of a
     // sub cover every (quarter, half) pair once either way
     const int quarter = (tid >> 5) & 3, half = (warp_s >> 2) & 1;
     const int r = quarter * 32 + lane;
-    const uint32_t rm = s_rowmap[r];
+    const uint32_t rm = sh.rowmap[r];
     const int my_j = (int)(rm & 0xff);
     uint32_t lc = 0;   // layers this sub has run (parity of its barriers)
     uint32_t cbar_par = 0;
     const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
-    long long* tprof = profiling ? s_tprof : nullptr;
-    if (profiling) for (int i = 0; i < 8; ++i) s_tprof[i] = 0;
+    long long* tprof = profiling ? sh.tprof : nullptr;
+    if (profiling) for (int i = 0; i < 8; ++i) sh.tprof[i] = 0;
 
     // stage 0: the compact record words and item-list entries this thread fetches ahead for its sub's next group
     uint32_t pf_rec = 0;
@@ -540,16 +558,16 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
             // grid row y, items that reach column x - make a pixel's channel bits one AND; an 8-channel plane entry (bf16 0/1)
             // comes from a 256-entry table.
             // (the records and item lists were fetched into registers while the previous group was being computed)
-            if (st < nvalid * 32) s_rec[sub][st >> 5][st & 31] = pf_rec;
-            if (st < nvalid * n2) s_it[sub][pf_j][pf_q] = pf_it;
+            if (st < nvalid * 32) t0.rec[sub][st >> 5][st & 31] = pf_rec;
+            if (st < nvalid * n2) t0.it[sub][pf_j][pf_q] = pf_it;
             sub_sync(sub);
             for (int i = st; i < nvalid * 64; i += SUB_THREADS) {
                 const int j = i >> 6, k = i & 31, isx = (i >> 5) & 1;   // k = grid row y (isx = 0) or column x (isx = 1)
-                const uint32_t rem = s_rec[sub][j][BPP_REC_REM];
+                const uint32_t rem = t0.rec[sub][j][BPP_REC_REM];
                 uint32_t m = 0;
                 for (int q = 0; q < P.N; ++q)
-                    if (((rem >> q) & 1u) && k < s_it[sub][j][2 * q + (isx ? 0 : 1)]) m |= 2u << q;
-                s_msk[sub][j][isx][k] = m;
+                    if (((rem >> q) & 1u) && k < t0.it[sub][j][2 * q + (isx ? 0 : 1)]) m |= 2u << q;
+                t0.msk[sub][j][isx][k] = m;
             }
             {   // next group's inputs: in flight during this group's layers
                 const int nb0 = b0 + gsz, nv = min(gsz, slice_hi - nb0);
@@ -562,17 +580,17 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
             sub_sync(sub);
             for (int idx = st; idx < NT * 128; idx += SUB_THREADS) {   // one pixel row entry of one tile per step
                 const int t = idx >> 7;
-                const uint32_t m = s_rowmap[idx & 127];
+                const uint32_t m = sh.rowmap[idx & 127];
                 const int j = (int)(m & 0xff);
                 if (m == 0xffffu || j >= nvalid) continue;
                 const int x = (int)(m >> 8) - 1;
-                const uint32_t bits = ((s_rec[sub][j][t] >> x) & 1u) | (s_msk[sub][j][0][t] & s_msk[sub][j][1][x]);
+                const uint32_t bits = ((t0.rec[sub][j][t] >> x) & 1u) | (t0.msk[sub][j][0][t] & t0.msk[sub][j][1][x]);
                 const uint32_t dst = smem_u32(arena) + (uint32_t)(G0 + t * S.TS + (idx & 127)) * 16u;
-                sts128(dst, s_lut[bits & 0xffu]);
-                sts128(dst + PS, s_lut[(bits >> 8) & 0xffu]);
+                sts128(dst, t0.lut[bits & 0xffu]);
+                sts128(dst + PS, t0.lut[(bits >> 8) & 0xffu]);
                 if (S.cp > 2) {
-                    sts128(dst + 2u * PS, s_lut[(bits >> 16) & 0xffu]);
-                    sts128(dst + 3u * PS, s_lut[0]);
+                    sts128(dst + 2u * PS, t0.lut[(bits >> 16) & 0xffu]);
+                    sts128(dst + 3u * PS, t0.lut[0]);
                 }
             }
         } else {
@@ -589,13 +607,13 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     dst[k] = 0;
                     if (idx < NT * 128) {
                         const int t = idx >> 7;
-                        const uint32_t m = s_rowmap[idx & 127];
+                        const uint32_t m = sh.rowmap[idx & 127];
                         const int j = (int)(m & 0xff);
                         if (m != 0xffffu && j < nvalid) {
                             const uint4* src = xin + (size_t)(b0 + j) * (FX * CPX) * hw + t * S.w + ((int)(m >> 8) - 1);
                             dst[k] = smem_u32(arena) + (uint32_t)(G0 + t * S.TS + (idx & 127)) * 16u;
 #pragma unroll
-                            for (int p = 0; p < FX * CPX; ++p) v[k][p] = __ldg(src + (size_t)p * hw);
+                            for (int p = 0; p < FX * CPX; ++p) v[k][p] = __ldcg(src + (size_t)p * hw);   // written by this kernel: L2, not the read-only path
                         }
                     }
                 }
@@ -646,7 +664,7 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                 const uint32_t arena_a = smem_u32(arena);
                 uint32_t lcl = lc;
                 const uint32_t a_lo16 = LO >> 4;
-                if (!S.stream && lc == 0) mbar_wait(smem_u32(&s_wbar), 0);   // resident weights have landed
+                if (!S.stream && lc == 0) mbar_wait(smem_u32(&sh.wbar), 0);   // resident weights have landed
                 const uint32_t nl_total = (uint32_t)n_groups * (uint32_t)S.nlay;   // layers this CTA runs in all (streaming)
                 for (int l = 0; l < nres + (has_conv ? 1 : 0); ++l, ++lcl) {
                     const bool conv = l == nres;
@@ -662,12 +680,12 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     // layers are chained tile by tile while every grid row has its own accumulator slot; the sequence's first
                     // conv has another column map and starts when every slot of the last residual layer is drained: with up to
                     // 8 grid rows its first MMAs overwrite the slots and the bias is added in the epilogue, a taller image
-                    // needs the ring (wraps) and gets the bias pre-loaded behind s_cbar.  Streamed weights: no chaining, the
+                    // needs the ring (wraps) and gets the bias pre-loaded behind sh.cbar.  Streamed weights: no chaining, the
                     // previous layer is complete when this one starts, so its slot is refilled with the layer after this one.
                     const bool chain = l > 0 && !conv && NT <= RR && !S.stream;
                     if (l > 0) {
                         if (conv && NT > 8) {   // (a conv of at most 8 grid rows opens its slots itself, see below)
-                            mbar_wait(smem_u32(&s_cbar[sub]), cbar_par);
+                            mbar_wait(smem_u32(&sh.cbar[sub]), cbar_par);
                             cbar_par ^= 1u;
                         } else if (chain) mbar_wait(ready, rpar);
                         else
@@ -677,10 +695,10 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     if (S.stream) {
                         if (lcl >= 1u && lcl + 1u < nl_total) {
                             const uint32_t sl = (lcl + 1u) & 1u, nl = (lcl + 1u) % (uint32_t)S.nlay;
-                            mbar_expect_tx(smem_u32(&s_wslot[sl]), (uint32_t)S.w_len[nl] * (X3 ? 2u : 1u));
-                            fetch_layer((int)nl, smem_u32(smem) + sl * (uint32_t)S.slot_bytes, smem_u32(&s_wslot[sl]));
+                            mbar_expect_tx(smem_u32(&sh.wslot[sl]), (uint32_t)S.w_len[nl] * (X3 ? 2u : 1u));
+                            fetch_layer((int)nl, smem_u32(smem) + sl * (uint32_t)S.slot_bytes, smem_u32(&sh.wslot[sl]));
                         }
-                        mbar_wait(smem_u32(&s_wslot[lcl & 1u]), (lcl >> 1) & 1u);
+                        mbar_wait(smem_u32(&sh.wslot[lcl & 1u]), (lcl >> 1) & 1u);
                     }
 #define GR_ISSUE(C16, CO_, R_, PRE_, XM_)                                                                                     \
     do {                                                                                                                      \
@@ -730,11 +748,11 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
                     const float* bc = s_bias + 32 * 4 + half * 16;
                     if (NT > 8) {
                         // all eight warps must have drained the residual layers' slots before any of them pre-loads the
-                        // conv's bias; the issuer starts the conv behind s_cbar
+                        // conv's bias; the issuer starts the conv behind sh.cbar
                         asm volatile("bar.sync %0, 256;" ::"r"(3 + sub) : "memory");
                         preload_bias<16, 8>(tq_ + half * 16, NT, 32u, bc);
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&s_cbar[sub]));
+                        if (lane == 0) mbar_arrive(smem_u32(&sh.cbar[sub]));
                         epi_layer<16, GR_CONV, 1, 8, false, true, X3>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, bc, nullptr, interior, t_r, t_r, lane, false, tprof, LO);
                     } else
                         epi_layer<16, GR_CONV, 1, 8, true, false, X3>(NT, tile_bytes, PS, tq_ + half * 16, full, ready, lcl & 1u, 32u, bc, nullptr, interior, t_r, t_r, lane, false, tprof, LO);
@@ -844,14 +862,50 @@ k_net_gr(NetParams P, GrStage S, int Bmax, const int32_t* __restrict__ count_dev
         prof[8 * STAGE + 1] = t_cv;
         prof[8 * STAGE + 2] = t_out;
 #ifdef BPP_GR_PROF
-        for (int i = 0; i < 4; ++i) prof[8 * STAGE + 3 + i] = s_tprof[i] + (i == 3 ? s_tprof[4] : 0);
+        for (int i = 0; i < 4; ++i) prof[8 * STAGE + 3 + i] = sh.tprof[i] + (i == 3 ? sh.tprof[4] : 0);
 #endif
         prof[8 * STAGE + 7] = clock64() - t_start;
+        prof[8 * STAGE + 3] = t_start - t_enter;   // the stage's prologue (barriers, tables, arena clear, weight fetch issue)
     }
+    __threadfence();   // the hand-over written by this stage is read by the CTA's next stage
     tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    if (profiling) prof[8 * STAGE + 4] = clock64() - t_enter;   // whole stage incl. prologue and the closing fence + barrier
+}
+
+// The whole trunk in ONE launch: every CTA takes the same contiguous share of the batch through the four levels (no
+// dependency between CTAs, hence no grid-wide barrier and no launch boundary between the levels: four launches cost ~4 us
+// each in prologue, tail imbalance and launch latency - 15 % of a forward at the lockstep batch sizes).  Each level re-plans
+// the shared memory (its weights, its arenas) and re-initialises the barriers; TMEM is allocated once.
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? SUB_THREADS : 2 * SUB_THREADS, 1)
+k_net_gr(NetParams P, GrStage S0, GrStage S1, GrStage S2, GrStage S3, int Bmax, const int32_t* __restrict__ count_dev,
+         const uint32_t* __restrict__ recs, const int32_t* __restrict__ game, const int32_t* __restrict__ items_wh, uint4* x1,
+         uint4* x2, uint4* x3, __nv_bfloat16* __restrict__ feat_out, long long feat_lo_off,
+         const __nv_bfloat16* __restrict__ wts_gr, const __nv_bfloat16* __restrict__ wts_gr_lo, long long* prof) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) GrShared sh;
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem)),
+                     "r"((uint32_t)S0.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    for (int i = tid; i < 15 * 32; i += (int)blockDim.x) {
+        const int l = i >> 5, c = i & 31;
+        sh.bias[l][c] = c < P.conv[l].co ? P.bias[P.conv[l].b_off + c] : 0.f;
+    }
+    // nothing above depends on the kernel that produced the leaf batch; the heads kernel behind us may start launching
+    pdl_launch_dependents();
+    pdl_wait();
+    const int B = count_dev ? min(*count_dev, Bmax) : Bmax;
+    gr_stage<0, X3>(P, S0, B, recs, game, items_wh, nullptr, x1, feat_out, feat_lo_off, wts_gr, wts_gr_lo, prof, smem, sh, true);
+    gr_stage<1, X3>(P, S1, B, recs, game, items_wh, x1, x2, feat_out, feat_lo_off, wts_gr, wts_gr_lo, prof, smem, sh, false);
+    gr_stage<2, X3>(P, S2, B, recs, game, items_wh, x2, x3, feat_out, feat_lo_off, wts_gr, wts_gr_lo, prof, smem, sh, false);
+    gr_stage<3, X3>(P, S3, B, recs, game, items_wh, x3, nullptr, feat_out, feat_lo_off, wts_gr, wts_gr_lo, prof, smem, sh, false);
     if (tid < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"((uint32_t)S.tmem_cols));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem), "r"((uint32_t)S0.tmem_cols));
 }
 
 }  // namespace bppgr

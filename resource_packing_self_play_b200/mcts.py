@@ -222,8 +222,7 @@ class BatchedMCTS:
             self._graphs[key] = graph
         if graph is not None:
             graph.replay()
-            nk = 5 if getattr(net, "grid_row", lambda: False)() else 2     # evaluator kernels: four stage kernels + heads | trunk + heads
-            self.graph_launches += (nk + (1 if self.fused else 2)) * chunk   # [k_search,] evaluator, k_expand_[backup|search]
+            self.graph_launches += (3 if self.fused else 4) * chunk   # [k_search,] trunk, heads, k_expand_[backup|search]
         else:
             body()
             self._eager_chunks += 1
