@@ -319,8 +319,9 @@ int bpp_net_commit(bpp_net *n, void *stream);
 /* Arithmetic of the forward.  BPP_NET_BF16 (default): bf16 weights and inter-layer activations, fp32 accumulation - within
  * 1e-3 of the fp32 reference for freshly initialised networks.  BPP_NET_FP32: fp32 weights and activations - needed for
  * the reference's TRAINED checkpoints, whose logits span ~3e3 so that bf16 rounding of the weights alone moves the
- * policy by up to 0.3 (measured, DESIGN.md "leaf evaluation"). */
-#define BPP_NET_BF16 0      /* tcgen05 tensor-core kernel (implicit GEMM, TMEM accumulators) */
+ * policy by up to 0.3 (measured, DESIGN.md "leaf evaluation"); BPP_NET_BF16X3 keeps fp32-level accuracy on the tensor cores
+ * and is what the Python wrapper's precision="auto" selects for such weights. */
+#define BPP_NET_BF16 0      /* tcgen05 tensor-core kernels (grid-row implicit GEMM, TMEM accumulators; bpp_net_gr.cuh) */
 #define BPP_NET_FP32 1      /* CUDA-core kernel, fp32 weights and activations */
 #define BPP_NET_BF16_SIMT 2 /* CUDA-core kernel with the bf16 roundings of mode 0 (cross-check of the tensor-core path) */
 #define BPP_NET_BF16X3 3    /* tcgen05 kernel in split-bf16: activations and weights as hi + lo bf16 halves, three MMAs per
@@ -329,7 +330,9 @@ int bpp_net_set_precision(bpp_net *n, int mode);
 /* Phase timers (SM clock cycles, CTA 0 of the last tensor-core forward; synchronises the device):
  * [0] input planes, [1] weight staging, [2] MMA issue, [3] MMA wait, [4] epilogue, [5] pooling, [6] heads, [7] total. */
 int bpp_net_profile(bpp_net *n, int64_t cycles_host[8]);
-/* the same timers per role kernel of the split trunk (k_net_role<0..2>): cycles_host[8 * role + slot] */
+/* Timers of the four level stages of the grid-row trunk (k_net_gr, CTA 0 / thread 0 of the last forward):
+ * cycles_host[8 * stage + slot], slots [0] input, [1] layers, [2] output (pooling / features), [3] stage prologue, [4] whole
+ * stage, [7] groups only.  (Fallback kernels: the phase timers above per role kernel k_net_role<0..2>.) */
 int bpp_net_profile_roles(bpp_net *n, int64_t cycles_host[32]);
 /* 1 when the handle's current precision mode (bf16 or split-bf16) runs the grid-row stage kernels (k_net_gr), else 0 */
 int bpp_net_grid_row(bpp_net *n);

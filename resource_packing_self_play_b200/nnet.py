@@ -120,8 +120,8 @@ class DeviceNet:
     def profile_roles(self):
         arr = (C.c_int64 * 32)()
         call("bpp_net_profile_roles", self._h, arr)
-        if self.grid_row():   # k_net_gr stages 0..3 (thread 0 of CTA 0): phases of a group, then epilogue-warp waits
-            keys = ["input", "layers", "output", "epi_wait_mma", "epi_tmem_ld", "epi_math_store", "epi_fence_arrive", "total"]
+        if self.grid_row():   # k_net_gr stages 0..3 (thread 0 of CTA 0): phases of its groups, prologue, whole stage
+            keys = ["input", "layers", "output", "prologue", "stage", "unused5", "unused6", "total"]
         else:
             keys = ["input", "weights", "mma_issue", "mma_wait", "epilogue", "pool", "output", "total"]
         return [{k: int(arr[8 * r + i]) for i, k in enumerate(keys)} for r in range(4 if self.grid_row() else 3)]
