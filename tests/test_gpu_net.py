@@ -354,3 +354,36 @@ def test_grid_row_kernels_reproduce_their_outputs_bit_for_bit(precision):
     pa, _ = net.dnet.forward(r_t[:2800].contiguous(), i_t[:2800].contiguous())
     pb, _ = net.dnet.forward(r_t[:300].contiguous(), i_t[:300].contiguous())
     assert torch.equal(pa[:300], pb)
+
+
+@pytest.mark.parametrize("W,H,N", [(3, 2, 2), (2, 28, 3), (32, 3, 4), (31, 1, 2), (5, 5, 16), (1, 9, 3), (24, 24, 10), (7, 13, 1)])
+def test_grid_row_kernels_on_odd_board_geometries(W, H, N):
+    """One-row / one-column boards, 28 grid rows (more than the 16 accumulator slots of the first layer), 17 input channels,
+    a single item: the tensor-core modes against the CUDA-core kernels with the same arithmetic (bf16 vs bf16_simt,
+    split-bf16 vs fp32) on batches of 1, 37 and 600 leaves."""
+    from resource_packing_self_play_b200.nnet import NNetWrapper
+    from resource_packing_self_play_b200.utils import dotdict
+    rng = np.random.RandomState(0)
+    for B in (1, 37, 600):
+        recs = np.zeros((B, 32), dtype=np.uint32)
+        recs[:, :H] = rng.randint(0, 1 << min(W, 30), size=(B, H))
+        recs[:, 28] = rng.randint(1, 1 << N, size=B)
+        items = np.stack([rng.randint(1, W + 1, size=(B, N)), rng.randint(1, H + 1, size=(B, N))], axis=2).astype(np.int32)
+        torch.manual_seed(1)
+        net = NNetWrapper(_Game(W, H, N), dotdict(num_items=N, num_bins=1, cuda=True, epochs=1, batch_size=8), max_batch=B,
+                          precision="bf16")
+        with torch.no_grad():
+            net.nnet.logits_fc.weight.mul_(10.0)
+        net.sync_weights()
+        dev = net.device
+        r_t, i_t = torch.from_numpy(recs.view(np.int32)).to(dev), torch.from_numpy(items).to(dev)
+        out = {}
+        for mode in ("bf16", "bf16_simt", "bf16x3", "fp32"):
+            net.dnet.set_precision(mode)
+            p, v = net.dnet.forward(r_t, i_t)
+            out[mode] = (p.clone(), v.clone())
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(out["bf16"][0]).all())
+        assert float((out["bf16"][0] - out["bf16_simt"][0]).abs().max()) < 2e-3
+        assert float((out["bf16x3"][0] - out["fp32"][0]).abs().max()) < 2e-4
+        assert float((out["bf16x3"][1] - out["fp32"][1]).abs().max()) < 2e-4
