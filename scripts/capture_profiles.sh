@@ -10,7 +10,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_episode -s 1 -
 for cfg in "15 15 8192 bf16" "15 15 8192 bf16x3" "20 20 8192 bf16" "15 15 2800 bf16 6"; do
   tag=$(echo $cfg | tr ' ' '_')
   python scripts/net_once.py $cfg > gpurun_out/r02_plain_net_$tag.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:k_net_ -s 10 -c 5 -o gpurun_out/r02_net_$tag python scripts/net_once.py $cfg > gpurun_out/r02_ncu_net_$tag.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_net_ -s 4 -c 2 -o gpurun_out/r02_net_$tag python scripts/net_once.py $cfg > gpurun_out/r02_ncu_net_$tag.log 2>&1
 done
 R="python bench.py --workload real20 --no-cpu --steps 2 --warmup 1 --stream-mult 1"
 $R > gpurun_out/r02_plain_real20.log 2>&1 &&
