@@ -867,7 +867,8 @@ __device__ __forceinline__ void gr_stage(const NetParams& P, const GrStage& S, i
         prof[8 * STAGE + 7] = clock64() - t_start;
         prof[8 * STAGE + 3] = t_start - t_enter;   // the stage's prologue (barriers, tables, arena clear, weight fetch issue)
     }
-    __threadfence();   // the hand-over written by this stage is read by the CTA's next stage
+    __threadfence();       // the hand-over written by this stage is read by the CTA's next stage
+    fence_proxy_async();   // this thread's shared-memory writes are ordered before the next stage's bulk weight copies
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
