@@ -11,28 +11,31 @@
 //
 //   * row axis of a level = [grid row y][leaf j][padded column xp], xp = 0 being the zero halo column shared by
 //     neighbouring leaves; one 128-row MMA tile = grid row y of the J leaves of a group (J*(w+1) <= 128: 8 leaves at 15x15,
-//     14 at 8x8, 25 at 4x4, 42 at 2x2 - hence one kernel per level, each with its own group size);
+//     14 at 8x8, 25 at 4x4, 42 at 2x2 - hence one STAGE per level, each with its own group size and shared-memory plan);
 //   * for INPUT tile t the three vertical taps are stacked along N: B = [W(dy=0,dx) | W(dy=1,dx) | W(dy=2,dx)], N = 3*Cout,
 //     accumulated over dx (A shifted by dx-1 rows, i.e. only the descriptor's start address moves) and the input-channel
-//     chunks; block dy belongs to OUTPUT tile t+1-dy.  Output tile Y owns TMEM columns base + (NT-1-Y)*Cout, so the three
-//     blocks of one MMA land in three consecutive column blocks = three consecutive output tiles, on the SAME lanes;
-//   * 3*cin16 (+1, see below) MMAs of N = 48 / 96 per tile instead of 9*cin16 of N = 16 / 32: ~2.3x fewer tensor cycles.
-//     The first MMA of a tile is split (its dy = 0 block opens a fresh output tile and must overwrite, the other two
-//     accumulate);
+//     chunks; block dy belongs to OUTPUT tile t+1-dy.  Output tile Y owns slot Y mod R of a ring of R accumulator slots of
+//     Cout TMEM columns (256 columns per group), laid out so that the three blocks of one MMA land in three consecutive
+//     column blocks = three consecutive output tiles, on the SAME lanes (two MMAs where the ring wraps);
+//   * 3*cin16 MMAs of N = 48 / 96 per tile instead of 9*cin16 of N = 16 / 32: ~2.3x fewer tensor cycles.  A stacked MMA
+//     cannot overwrite one block and accumulate into the other two, so the epilogue warps pre-load every slot they drain
+//     with the bias of its next user (tcgen05.st) and every MMA accumulates;
 //   * an input tile is read by ITS OWN MMAs only, so every layer runs IN PLACE: the epilogue of output tile Y (which waits
 //     for the MMAs of input tile Y+1) overwrites input tile Y.  A residual block needs two buffers (raw stream, relu'd
-//     activations) instead of three plus a pooling buffer; halo rows are never written and stay zero for the whole kernel;
-//   * the CTA is persistent, all weights of its level stay in shared memory (one bulk async copy per layer at kernel start),
-//     and the layers of a group are chained by per-tile mbarriers instead of CTA-wide barriers: the issuer starts layer l+1
-//     on tile t as soon as the epilogue warps have stored tiles <= t+1 of layer l, so the tensor pipe does not drain
-//     between layers;
+//     activations) instead of three plus a pooling buffer; halo rows are never written and stay zero for the whole stage;
+//   * all weights of a level stay in shared memory (one bulk async copy per layer at the start of the stage; split mode:
+//     streamed through two slots where they do not fit), and the layers of a group are chained by per-tile mbarriers
+//     instead of CTA-wide barriers: the issuer starts layer l+1 on tile t as soon as the epilogue warps have stored tiles
+//     <= t+1 of layer l, so the tensor pipe does not drain between layers;
 //   * a CTA runs up to two independent groups ("subs": 8 epilogue warps + 1 issuer warp each) that share the weights and
-//     split the 512 TMEM columns - one sub's epilogue / input / pooling phases overlap the other's MMAs.
+//     split the 512 TMEM columns - one sub's epilogue / input / pooling phases overlap the other's MMAs;
+//   * the four stages run in ONE launch (k_net_gr): every CTA takes the same contiguous share of the batch through all
+//     levels, so a stage only reads hand-over data written by its own CTA and no grid-wide barrier is needed.
 //
 // Stages: 0 = input planes from the compact records -> conv -> max-pool -> x1;  1 = x1 -> two residual blocks -> conv ->
 // max-pool -> x2;  2 = the same one level down -> x3;  3 = x3 -> two residual blocks -> relu(flatten) -> feat (the FC heads
-// run in k_net_heads_tc).  Hand-over layout: [leaf][plane of 8 channels][pixel] 16-byte units, interior pixels only
-// (BinpackingNNet.py:29-48,72-81).
+// run in k_net_heads_tc).  Hand-over layout: [leaf][hi | lo (split mode)][plane of 8 channels][pixel] 16-byte units,
+// interior pixels only (BinpackingNNet.py:29-48,72-81).
 #pragma once
 
 #ifndef BPP_GR_TB23
