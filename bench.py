@@ -69,9 +69,11 @@ def workload(first_episode, count, Wb=W, Hb=H):
     return seeds, heights, (Wb * heights).astype(np.int32)
 
 
-def config_dict(args, extra=None):
+def config_dict(args, extra=None, mult=1):
     c = {"workload": "configs[1]: main_bpp default instance (15x15 bin, 10 items, numMCTSSims=200, cpuct=1), "
-                     f"{args.games} lockstep games per GPU, stub uniform-prior net, whole self-play episodes",
+                     f"{args.games} lockstep games per GPU, stub uniform-prior net, whole self-play episodes" +
+                     (f"; a step = {mult} x {args.games} episodes streamed through the resident games (a game whose "
+                      "episode ends takes the next instance inside the kernel)" if mult > 1 else ""),
          "games_per_gpu": args.games, "num_mcts_sims": args.sims, "bin": [W, H], "items": N,
          "action_choice": "sample ~ visit counts (greedy=False)",
          "cache": "working set (search graphs of all games, several GB per step) is far larger than the 126 MB L2; "
@@ -346,21 +348,27 @@ class Ctx:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def run_stub_arm(cx):
-    """headline: whole episodes with the in-kernel stub evaluator (one k_episode launch per step)"""
+def run_stub_arm(cx, mult=None, steps=None, with_e2e=True):
+    """headline: whole episodes with the in-kernel stub evaluator (one k_episode launch per step).  mult > 1: a step is
+    mult x G episodes streamed through the G resident games (bpp_engine_play_stub_stream), mult == 1: one episode per
+    game (bpp_engine_reset + bpp_engine_play_stub)."""
     torch, args = cx.torch, cx.args
+    mult = mult or max(1, args.stub_stream_mult)
+    if steps is not None:
+        args = argparse.Namespace(**{**vars(args), "steps": steps})
     from resource_packing_self_play_b200 import _lib
     from resource_packing_self_play_b200.engine import SearchEngine, algorithmic_bytes_per_sim
     from resource_packing_self_play_b200.game import ItemsGenerator
     dev, rank, world, local = cx.dev, cx.rank, cx.world, cx.local
     G = args.games
+    E = mult * G   # episodes per step
     n_steps_total = args.warmup + args.steps
     gen = ItemsGenerator(W, H, N)
     # synthetic instances for every step of this rank (host generation is setup, not part of the timed path)
     inst = []
     for k in range(2 * n_steps_total):  # first half: device-resident arm, second half: e2e arm
-        first = ((k * world) + rank) * G
-        seeds, heights, areas = workload(first, G)
+        first = ((k * world) + rank) * E
+        seeds, heights, areas = workload(first, E)
         # the package's device-side generator (bit-identical to numpy's legacy RNG path, tests/test_gpu_env.py)
         inst.append((gen.items_batch_device(seeds, heights, device=local).cpu().numpy(), areas))
     edge_cap = 0
@@ -368,10 +376,14 @@ def run_stub_arm(cx):
     if args.edge_frac < 1.0:  # profiling runs: a smaller edge pool keeps ncu's save/restore cheap
         edge_cap = int((args.sims * N + N + 2) * worst_units_per_node * args.edge_frac)
     eng = SearchEngine(W, H, N, G, args.sims, CPUCT, device=local, edge_cap=edge_cap)
-    nan_bl = np.full(G, np.nan)
+    nan_bl = np.full(E, np.nan)
     bl_dev = torch.from_numpy(nan_bl).to(dev)
-    counts_buf = torch.zeros((N, G, W * N), dtype=torch.int32, device=dev)
-    actions_buf = torch.empty((N, G), dtype=torch.int32, device=dev)
+    counts_buf = torch.zeros((N, E, W * N), dtype=torch.int32, device=dev)
+    actions_buf = torch.empty((N, E), dtype=torch.int32, device=dev)
+    r_buf = torch.empty(E, dtype=torch.int32, device=dev)
+    score_buf = torch.empty(E, dtype=torch.float64, device=dev)
+    moves_buf = torch.zeros(E, dtype=torch.int32, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
     # ---- arm 1: inputs resident in HBM ------------------------------------------------------------------------------
     dev_inst = [(torch.from_numpy(i).to(dev), torch.from_numpy(a).to(dev)) for i, a in inst[:n_steps_total]]
@@ -383,12 +395,18 @@ def run_stub_arm(cx):
     def step_resident(k, timed):
         """reset + ONE launch of the whole-episode kernel (search -> counts -> choose -> play, N moves)"""
         items, area = dev_inst[k]
-        eng.reset(items, area, bl_dev)
+        if mult == 1:
+            eng.reset(items, area, bl_dev)
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.call("bpp_engine_play_stub", eng._h, _lib.STUB["U"], _lib.CHOOSE_SAMPLE, C.c_uint64(1234 + k), 0,
-                  C.c_void_p(counts_buf.data_ptr()), C.c_void_p(actions_buf.data_ptr()), None, eng_stream())
+        if mult == 1:
+            _lib.call("bpp_engine_play_stub", eng._h, _lib.STUB["U"], _lib.CHOOSE_SAMPLE, C.c_uint64(1234 + k), 0,
+                      vp(counts_buf), vp(actions_buf), None, eng_stream())
+        else:   # the stream's own set-up (queue counter, k_stream_begin, output clears) is inside the events
+            _lib.call("bpp_engine_play_stub_stream", eng._h, _lib.STUB["U"], _lib.CHOOSE_SAMPLE, C.c_uint64(1234 + k), E,
+                      vp(items), vp(area), vp(bl_dev), None, vp(counts_buf), vp(actions_buf), vp(r_buf), vp(score_buf),
+                      vp(moves_buf), eng_stream())
         if timed:
             e1.record()
             search_events.append((e0, e1))
@@ -402,6 +420,8 @@ def run_stub_arm(cx):
     st = eng.stats(reset=True)
     done = eng.status()["done"]
     assert bool((done == 1).all()), "some games did not finish their episode"
+    if mult > 1:
+        assert int(moves_buf.min()) >= 1, "some episodes of the stream were not played"
     g_nodes, g_units = eng.graph_sizes()
     graph = {"max_nodes_per_game": int(g_nodes.max()), "max_edge_units_per_game": int(g_units.max()),
              "mean_edge_units_per_game": float(g_units.double().mean()), "engine_device_bytes": eng.device_bytes,
@@ -412,30 +432,36 @@ def run_stub_arm(cx):
     # ---- arm 2: end to end through the host-buffer C ABI --------------------------------------------------------------
     pinned_items = [torch.from_numpy(i).pin_memory() for i, _ in inst[n_steps_total:]]
     pinned_area = [torch.from_numpy(a).pin_memory() for _, a in inst[n_steps_total:]]
-    out = {"counts": torch.empty((N, G, W * N), dtype=torch.int32).pin_memory().numpy(),
-           "actions": torch.empty((N, G), dtype=torch.int32).pin_memory().numpy(),
-           "r": torch.empty(G, dtype=torch.int32).pin_memory().numpy(),
-           "score": torch.empty(G, dtype=torch.float64).pin_memory().numpy(),
-           "moves": torch.empty(G, dtype=torch.int32).pin_memory().numpy()}
+    out = {"counts": torch.empty((N, E, W * N), dtype=torch.int32).pin_memory().numpy(),
+           "actions": torch.empty((N, E), dtype=torch.int32).pin_memory().numpy(),
+           "r": torch.empty(E, dtype=torch.int32).pin_memory().numpy(),
+           "score": torch.empty(E, dtype=torch.float64).pin_memory().numpy(),
+           "moves": torch.empty(E, dtype=torch.int32).pin_memory().numpy()}
     pinned_bl = torch.from_numpy(nan_bl).pin_memory().numpy()
 
     def step_e2e(k):
-        eng.play_stub_host("U", pinned_items[k].numpy(), pinned_area[k].numpy(), pinned_bl,
-                           choose_mode=_lib.CHOOSE_SAMPLE, seed=99 + k, out=out)
+        if mult == 1:
+            eng.play_stub_host("U", pinned_items[k].numpy(), pinned_area[k].numpy(), pinned_bl,
+                               choose_mode=_lib.CHOOSE_SAMPLE, seed=99 + k, out=out)
+        else:
+            eng.play_stub_stream_host("U", pinned_items[k].numpy(), pinned_area[k].numpy(), pinned_bl,
+                                      choose_mode=_lib.CHOOSE_SAMPLE, seed=99 + k, out=out)
         return int(out["moves"].sum())
 
-    for k in range(args.warmup):
-        step_e2e(k)
-    eng.stats(reset=True)
-    e2e_dev_ms, e2e_wall_ms, _, _ = cx.timed(lambda k: step_e2e(args.warmup + k), args.steps)
-    e2e_ms = max(e2e_dev_ms, e2e_wall_ms)  # conservative: device events vs wall clock
-    st2 = eng.stats(reset=True)
+    e2e_ms, st2 = 0.0, {"sims": 0, "launches": 0}
+    if with_e2e:
+        for k in range(args.warmup):
+            step_e2e(k)
+        eng.stats(reset=True)
+        e2e_dev_ms, e2e_wall_ms, _, _ = cx.timed(lambda k: step_e2e(args.warmup + k), args.steps)
+        e2e_ms = max(e2e_dev_ms, e2e_wall_ms)  # conservative: device events vs wall clock
+        st2 = eng.stats(reset=True)
     h2d = inst[0][0].nbytes + inst[0][1].nbytes + nan_bl.nbytes
     d2h = sum(v.nbytes for v in out.values())
     eng.close()
 
     (ms, e2e_ms, search_ms_max), (sims, sims2, launches, episodes) = cx.reduce(
-        [ms, e2e_ms, search_ms], [st["sims"], st2["sims"], st["launches"] + st2["launches"], args.steps * G])
+        [ms, e2e_ms, search_ms], [st["sims"], st2["sims"], st["launches"] + st2["launches"], args.steps * E])
     if rank != 0:
         return None
     peak = float(cx.peaks.get("hbm_gbs", 6650.0))
@@ -452,17 +478,23 @@ def run_stub_arm(cx):
     achieved = bytes_per_sim * sims_per_launch / kernel_s / 1e9
     cap = cx.traffic.get("k_episode", {})
     traffic = cap.get("dram_bytes_per_launch") if (cap.get("games") == G and cap.get("sims") == args.sims) else None
+    if traffic and mult > 1:
+        traffic *= mult   # the capture is of one episode per game; a streamed launch plays mult of them per game
+    api = "bpp_engine_play_stub_host" if mult == 1 else "bpp_engine_play_stub_stream_host"
     line = {
         "metric": METRIC, "value": sims / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, {"parallelism": f"games sharded over {world} GPU(s), no data-path collective"}),
+        "config": config_dict(args, {"parallelism": f"games sharded over {world} GPU(s), no data-path collective",
+                                     "episodes_per_step": E}, mult),
         "episodes_per_sec": episodes / (ms * 1e-3),
         "e2e": {"value": sims2 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "episodes_per_sec": episodes / (e2e_ms * 1e-3),
-                "api": "bpp_engine_play_stub_host (pinned host buffers)"},
+                "api": api + " (pinned host buffers)"} if with_e2e else None,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_episode<STUB_U,15> (whole episodes, one launch per step)",
+                     "traffic_source": "ncu capture of one episode per game (profiles/r02_traffic.json)" +
+                                       (f" x {mult} episodes per game" if mult > 1 else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json (measured)" if cx.peaks else "fallback 6650 GB/s",
                      # DRAM read+write bytes of one k_episode launch: ncu --set full capture of THIS round and THIS
@@ -480,7 +512,7 @@ def run_stub_arm(cx):
                      },
         "clocks": clocks, "graph": graph,
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and with_e2e:
         v, eps, dt = cpu_single_core(args.cpu_seconds, args.sims)
         kind, _, _, _, _, src = _cpu_impl()
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
@@ -522,14 +554,14 @@ def _make_net(cx, Wb, Hb, G, precision):
     return net, weights
 
 
-def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, steps=None, warmup=None):
+def run_real_arm(cx, Wb, Hb, precision="auto", with_e2e=True, with_cpu=True, steps=None, warmup=None, games=None):
     """whole self-play episodes with the real net as leaf evaluator (bpp_engine_play_net: asynchronous per game)"""
     torch, args = cx.torch, cx.args
     from resource_packing_self_play_b200 import _lib
     from resource_packing_self_play_b200.game import ItemsGenerator
     from resource_packing_self_play_b200.mcts import BatchedMCTS
     from resource_packing_self_play_b200.nnet import BinPackingNNet
-    G = args.games
+    G = games or args.games
     steps = steps or max(3, args.steps // 5)
     warmup = warmup if warmup is not None else max(3, args.warmup)
     net, weights = _make_net(cx, Wb, Hb, G, precision)
@@ -780,8 +812,14 @@ def main():
     ap.add_argument("--workload", default="all",
                     help="comma list of: stub (headline), real15, real20, iteration, arena, checksum; all = every one")
     ap.add_argument("--precision", default="auto", help="precision mode of a single real15/real20 run")
+    ap.add_argument("--stub-stream-mult", type=int, default=8,
+                    help="headline workload: episodes per step = mult x games, streamed through the resident games "
+                         "(1 = one episode per game and step, bpp_engine_play_stub)")
     ap.add_argument("--stream-mult", type=int, default=0,
                     help="real-net workloads: episodes per step = stream-mult x games, streamed through the resident games")
+    ap.add_argument("--real20-large-games", type=int, default=16384,
+                    help="resident games per GPU of the second real20 record (0 = skip): the 20x20 evaluator runs at 190 "
+                         "TFLOP/s on 2,800 leaves, 285 on 8,192 and more, and this arm is evaluator-bound")
     ap.add_argument("--iteration-games", type=int, default=8192)
     ap.add_argument("--arena-seeds", type=int, default=8192)
     args = ap.parse_args()
@@ -796,6 +834,13 @@ def main():
     line, sec = None, {}
     if "stub" in todo:
         line = run_stub_arm(cx)
+        if args.stub_stream_mult > 1:
+            # the same games with ONE episode per game and step (the launch ends with an idle tail while the longest
+            # episodes finish): the figure of round 1 and of the ncu captures, for comparison
+            one = run_stub_arm(cx, mult=1, steps=max(5, args.steps // 2), with_e2e=False)
+            if line is not None and one is not None:
+                line["one_episode_per_game"] = {k: one[k] for k in ("value", "ms_per_step", "steps", "episodes_per_sec")}
+                line["one_episode_per_game"]["kernel_ms_per_launch"] = one["roofline"]["kernel_ms_per_launch"]
 
     def guarded(name, fn):
         """a failing secondary workload must not take the headline line with it: its record carries the error"""
@@ -825,6 +870,9 @@ def main():
         sec["real15"] = r
     if "real20" in todo:
         sec["real20"] = guarded("real20", lambda: run_real_arm(cx, 20, 20, args.precision))
+        if args.real20_large_games and args.real20_large_games != args.games:
+            sec[f"real20_g{args.real20_large_games}"] = guarded("real20_large", lambda: run_real_arm(
+                cx, 20, 20, args.precision, with_cpu=False, steps=3, games=args.real20_large_games))
     if "iteration" in todo:
         sec["iteration"] = guarded("iteration", lambda: run_iteration_arm(cx, args.iteration_games))
     if "arena" in todo:

@@ -227,6 +227,24 @@ int bpp_engine_play_stub_host(bpp_engine *e, int stub_kind, int choose_mode, uin
                               const int8_t *tie_host, int32_t *counts_out_host, int32_t *actions_out_host,
                               int32_t *r_out_host, double *score_out_host, int32_t *moves_out_host, void *stream);
 
+/* Episode STREAM with a stub evaluator (CoachBPP.executeEpisode x num_episodes, CoachBPP.py:50-99, in ONE launch):
+ * num_episodes >= 1 instances played through the G resident games.  Games 0..G-1 start with episodes 0..G-1; a game whose
+ * episode ends latches the outcome and takes the next instance of the queue inside the episode kernel, so the launch has
+ * no idle tail but the end of the whole stream.  Inputs are indexed by episode: items_wh int32 [E][N][2], total_area int32
+ * [E], bl float64 [E], tie int8 [E] or NULL; outputs too: counts int32 [N][E][A], actions int32 [N][E], r int32 [E], score
+ * float64 [E], moves int32 [E]; any output may be NULL.  The action stream is keyed by (seed, episode, move): results do
+ * not depend on G, and with num_episodes == G they equal bpp_engine_reset + bpp_engine_play_stub.  No bpp_engine_reset is
+ * needed before the call.  The _host form takes / fills HOST buffers (pinned result buffers are written by the kernel
+ * itself while the episodes run), synchronises and fails with BPP_E_CAPACITY if a game overflowed its pools. */
+int bpp_engine_play_stub_stream(bpp_engine *e, int stub_kind, int choose_mode, uint64_t seed, int num_episodes,
+                                const int32_t *items_wh_dev, const int32_t *total_area_dev, const double *bl_dev,
+                                const int8_t *tie_dev, int32_t *counts_out_dev, int32_t *actions_out_dev,
+                                int32_t *r_out_dev, double *score_out_dev, int32_t *moves_out_dev, void *stream);
+int bpp_engine_play_stub_stream_host(bpp_engine *e, int stub_kind, int choose_mode, uint64_t seed, int num_episodes,
+                                     const int32_t *items_wh_host, const int32_t *total_area_host, const double *bl_host,
+                                     const int8_t *tie_host, int32_t *counts_out_host, int32_t *actions_out_host,
+                                     int32_t *r_out_host, double *score_out_host, int32_t *moves_out_host, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Asynchronous self-play episodes with the batched device evaluator (CoachBPP.executeEpisode, CoachBPP.py:50-99, for
  * all G games at once; the real-net counterpart of bpp_engine_play_stub).

@@ -69,6 +69,8 @@ SIGNATURES = {
     "bpp_engine_roots": [_vp, _vp, _vp],
     "bpp_engine_play_stub": [_vp, _i32, _i32, _u64, _i32, _vp, _vp, C.POINTER(_i32), _vp],
     "bpp_engine_play_stub_host": [_vp, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "bpp_engine_play_stub_stream": [_vp, _i32, _i32, _u64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "bpp_engine_play_stub_stream_host": [_vp, _i32, _i32, _u64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "bpp_engine_set_auto_play": [_vp, _i32, _u64, _vp, _vp, _vp],
     "bpp_engine_progress_async": [_vp, _vp, _vp],
     "bpp_engine_play_net": [_vp, _vp, _i32, _u64, _vp, _vp, _vp, C.POINTER(_i32), _vp],

@@ -806,7 +806,7 @@ k_episode(Params P, int mode, unsigned long long seed, int max_moves, int32_t* c
     const int g = blockIdx.x * WARPS_PER_CTA + wid;
     if (g >= P.G) return;
     if (P.status[g] != 0) {
-        if (counts_host) fill_unplayed(counts_host, actions_out, g, P.G, P.geom.A, 0, max_moves, lane);
+        if (counts_host && !P.q_total) fill_unplayed(counts_host, actions_out, g, P.G, P.geom.A, 0, max_moves, lane);
         return;
     }
     WarpSmem& sm = smem[wid];
@@ -816,9 +816,15 @@ k_episode(Params P, int mode, unsigned long long seed, int max_moves, int32_t* c
     uint32_t rec = P.root_rec[(size_t)g * REC_WORDS + lane];
     int move_no = P.moves_done[g];
     int done = P.sims_done[g];
-    const size_t GA = (size_t)P.G * P.geom.A;
+    // rows of the outputs: [move][game] or, with an episode stream (q_total > 0, bpp_engine_play_stub_stream),
+    // [move][episode]: a game whose episode ends takes the next instance of the queue, so the launch has no idle tail
+    // but the end of the whole stream
+    const int rows = P.q_total ? P.q_total : P.G;
+    int ep = P.q_total ? P.slot_ep[g] : g;
+    const size_t RA = (size_t)rows * P.geom.A;
     int m = 0;
-    for (; m < max_moves; ++m) {
+    bool open = true;   // an episode is in progress in this game (its unplayed rows are still to be written)
+    while (m < max_moves) {
         while (done < P.num_sims) {
             if (simulate<STUB, HC>(P, gm, sm, lane, st) != 0) break;
             done++;
@@ -826,21 +832,42 @@ k_episode(Params P, int mode, unsigned long long seed, int max_moves, int32_t* c
         }
         if (gm.err) break;
         if (counts_out) {
-            int32_t* row = counts_out + m * GA + (size_t)g * P.geom.A;
+            int32_t* row = counts_out + m * RA + (size_t)ep * P.geom.A;
             root_counts_warp(P, g, gm.root_node, lane, row);
-            if (counts_host) mirror_row(row, counts_host + m * GA + (size_t)g * P.geom.A, P.geom.A, lane);
+            if (counts_host) mirror_row(row, counts_host + m * RA + (size_t)ep * P.geom.A, P.geom.A, lane);
         }
-        int a = lane == 0 ? choose_action(P, g, gm.root_node, move_no, mode, seed) : 0;
+        int a = lane == 0 ? choose_action(P, g, gm.root_node, move_no, mode, seed, ep) : 0;
         a = __shfl_sync(FULL, a, 0);
-        if (actions_out && lane == 0) actions_out[(size_t)m * P.G + g] = a;
+        if (actions_out && lane == 0) actions_out[(size_t)m * rows + ep] = a;
         const int status = advance_game(P, gm, sm, lane, a, rec, st);
         move_no++;
+        ++m;
         done = 0;
-        if (status != 0) { ++m; break; }
+        if (status == 0) continue;
+        if (!P.q_total || status != 1) break;
+        // the episode has ended: latch its outcome and take the next instance of the queue into this game
+        if (counts_host) fill_unplayed(counts_host, actions_out, ep, rows, P.geom.A, m, max_moves, lane);
+        open = false;
+        int nxt = 0;
+        if (lane == 0) {
+            if (P.epq_r) P.epq_r[ep] = P.ep_r[g];
+            if (P.epq_score) P.epq_score[ep] = P.ep_score[g];
+            if (P.epq_moves) P.epq_moves[ep] = P.moves_done[g];
+            nxt = atomicAdd(P.q_next, 1);
+        }
+        nxt = __shfl_sync(FULL, nxt, 0);
+        if (nxt >= P.q_total) break;
+        load_episode(P, g, nxt, lane);
+        load_ctx(P, g, lane, gm, sm);
+        rec = P.root_rec[(size_t)g * REC_WORDS + lane];
+        ep = nxt;
+        move_no = 0;
+        m = 0;
+        open = true;
     }
     store_ctx(P, gm, lane);
     flush_stats(P, st, lane);
-    if (counts_host) fill_unplayed(counts_host, actions_out, g, P.G, P.geom.A, m, max_moves, lane);
+    if (counts_host && open) fill_unplayed(counts_host, actions_out, ep, rows, P.geom.A, m, max_moves, lane);
 }
 
 // dense evaluator input: planes [B][N+1][H][W] float32 (getBinItem, BinPackingGame.py:118-120)
@@ -1562,7 +1589,7 @@ static int play_stub_impl(bpp_engine* e, int stub_kind, int choose_mode, uint64_
     if (choose_mode < 0 || choose_mode > 2) return set_err(BPP_E_INVALID, "unknown choose mode %d", choose_mode);
     // every move places exactly one item, so an episode has at most N moves
     const int moves = max_moves > 0 && max_moves < e->P.geom.N ? max_moves : e->P.geom.N;
-    const size_t G = (size_t)e->P.G, GA = G * e->P.geom.A;
+    const size_t G = e->P.q_total ? (size_t)e->P.q_total : (size_t)e->P.G, GA = G * e->P.geom.A;  // rows per move
     // rows of moves a game does not play: counts 0, action -1
     if (!counts_host_map) {
         if (counts_out_dev) CUDA_TRY(cudaMemsetAsync(counts_out_dev, 0, (size_t)moves * GA * sizeof(int32_t), S(stream)));
@@ -1641,6 +1668,114 @@ extern "C" int bpp_engine_play_stub_host(bpp_engine* e, int stub_kind, int choos
         CUDA_TRY(cudaMemcpyAsync(score_out_host, e->P.ep_score, G * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
     if (moves_out_host)
         CUDA_TRY(cudaMemcpyAsync(moves_out_host, e->P.moves_done, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    return bpp_engine_check(e, stream);
+}
+
+// queue / result staging of the *_stream_host entry points, grown on demand
+template <typename T>
+static int ensure(bpp_engine* e, T** p, size_t* have, size_t need) {
+    if (*p && *have >= need) return BPP_OK;
+    *have = need;
+    return dev_alloc(e, p, need);  // the old block stays owned by the handle until destroy (rare: sizes repeat)
+}
+
+// E >= 1 episodes streamed through the G resident games with a stub evaluator, ONE launch: a game whose episode ends
+// latches its outcome and takes the next instance of the queue inside k_episode (CoachBPP.executeEpisode x E; the action
+// stream is keyed by (seed, episode, move), so the results do not depend on G).  Outputs have E rows per move.
+static int play_stub_stream_impl(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed, int num_episodes,
+                                 const int32_t* items_wh_dev, const int32_t* total_area_dev, const double* bl_dev,
+                                 const int8_t* tie_dev, int32_t* counts_out_dev, int32_t* actions_out_dev,
+                                 int32_t* r_out_dev, double* score_out_dev, int32_t* moves_out_dev,
+                                 int32_t* counts_host_map, void* stream) {
+    if (!e || !items_wh_dev || !total_area_dev || !bl_dev) return set_err(BPP_E_INVALID, "null argument");
+    if (num_episodes < 1) return set_err(BPP_E_INVALID, "num_episodes = %d", num_episodes);
+    Params& P = e->P;
+    P.q_total = num_episodes;
+    P.q_items = items_wh_dev;
+    P.q_area = total_area_dev;
+    P.q_bl = bl_dev;
+    P.q_tie = tie_dev;
+    P.epq_r = r_out_dev;
+    P.epq_score = score_out_dev;
+    P.epq_moves = moves_out_dev;
+    const int first = P.G;  // episodes 0..G-1 start in the games, the queue hands out the rest
+    cudaError_t ce = cudaMemcpyAsync(P.q_next, &first, sizeof(int), cudaMemcpyHostToDevice, S(stream));
+    int rc = BPP_OK;
+    if (ce != cudaSuccess) {
+        rc = set_err(BPP_E_CUDA, "bpp_engine_play_stub_stream: %s", cudaGetErrorString(ce));
+    } else {
+        k_stream_begin<<<grid_warps(P.G), WARPS_PER_CTA * 32, 0, S(stream)>>>(P);
+        e->launches++;
+        e->leaf_parked = false;
+        e->items_ref = e->d_items;
+        rc = play_stub_impl(e, stub_kind, choose_mode, seed, 0, counts_out_dev, actions_out_dev, nullptr, counts_host_map,
+                            stream);
+    }
+    P.q_total = 0;
+    P.q_items = nullptr; P.q_area = nullptr; P.q_bl = nullptr; P.q_tie = nullptr;
+    P.epq_r = nullptr; P.epq_score = nullptr; P.epq_moves = nullptr;
+    return rc;
+}
+
+extern "C" int bpp_engine_play_stub_stream(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed, int num_episodes,
+                                           const int32_t* items_wh_dev, const int32_t* total_area_dev, const double* bl_dev,
+                                           const int8_t* tie_dev, int32_t* counts_out_dev, int32_t* actions_out_dev,
+                                           int32_t* r_out_dev, double* score_out_dev, int32_t* moves_out_dev, void* stream) {
+    return play_stub_stream_impl(e, stub_kind, choose_mode, seed, num_episodes, items_wh_dev, total_area_dev, bl_dev, tie_dev,
+                                 counts_out_dev, actions_out_dev, r_out_dev, score_out_dev, moves_out_dev, nullptr, stream);
+}
+
+extern "C" int bpp_engine_play_stub_stream_host(bpp_engine* e, int stub_kind, int choose_mode, uint64_t seed,
+                                                int num_episodes, const int32_t* items_wh_host,
+                                                const int32_t* total_area_host, const double* bl_host, const int8_t* tie_host,
+                                                int32_t* counts_out_host, int32_t* actions_out_host, int32_t* r_out_host,
+                                                double* score_out_host, int32_t* moves_out_host, void* stream) {
+    if (!e || !items_wh_host || !total_area_host || !bl_host) return set_err(BPP_E_INVALID, "null argument");
+    if (num_episodes < 1) return set_err(BPP_E_INVALID, "num_episodes = %d", num_episodes);
+    const size_t E = (size_t)num_episodes, G = (size_t)e->P.G, A = (size_t)e->P.geom.A, N = (size_t)e->P.geom.N;
+    int rc;
+    if ((rc = ensure(e, &e->q_items, &e->q_items_n, E * N * 2)) || (rc = ensure(e, &e->q_area, &e->q_area_n, E)) ||
+        (rc = ensure(e, &e->q_bl, &e->q_bl_n, E)) || (rc = ensure(e, &e->q_tie, &e->q_tie_n, E)) ||
+        (rc = ensure(e, &e->q_r, &e->q_r_n, E)) || (rc = ensure(e, &e->q_score, &e->q_score_n, E)) ||
+        (rc = ensure(e, &e->q_moves, &e->q_moves_n, E)))
+        return rc;
+    // Pinned (mapped) result buffers are written by the episode kernel itself, row by row while the games run (the rows
+    // are built in a per-game device scratch of N x G x A); pageable buffers take the staged path.
+    int32_t* counts_map = static_cast<int32_t*>(mapped_alias(counts_out_host));
+    int32_t* actions_map = static_cast<int32_t*>(mapped_alias(actions_out_host));
+    const bool direct = counts_map && (!actions_out_host || actions_map) && getenv("BPP_NO_ZERO_COPY") == nullptr;
+    if (counts_out_host && (rc = ensure(e, &e->q_counts, &e->q_counts_n, N * E * A))) return rc;
+    if (!direct && actions_out_host && (rc = ensure(e, &e->q_actions, &e->q_actions_n, N * E))) return rc;
+    (void)G;
+    CUDA_TRY(cudaMemcpyAsync(e->q_items, items_wh_host, E * N * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, S(stream)));
+    CUDA_TRY(cudaMemcpyAsync(e->q_area, total_area_host, E * sizeof(int32_t), cudaMemcpyHostToDevice, S(stream)));
+    CUDA_TRY(cudaMemcpyAsync(e->q_bl, bl_host, E * sizeof(double), cudaMemcpyHostToDevice, S(stream)));
+    if (tie_host) CUDA_TRY(cudaMemcpyAsync(e->q_tie, tie_host, E * sizeof(int8_t), cudaMemcpyHostToDevice, S(stream)));
+    CUDA_TRY(cudaMemsetAsync(e->q_moves, 0, E * sizeof(int32_t), S(stream)));
+    if (direct) {
+        rc = play_stub_stream_impl(e, stub_kind, choose_mode, seed, num_episodes, e->q_items, e->q_area, e->q_bl,
+                                   tie_host ? e->q_tie : nullptr, e->q_counts, actions_map, e->q_r, e->q_score, e->q_moves,
+                                   counts_map, stream);
+        if (rc) return rc;
+    } else {
+        rc = play_stub_stream_impl(e, stub_kind, choose_mode, seed, num_episodes, e->q_items, e->q_area, e->q_bl,
+                                   tie_host ? e->q_tie : nullptr, counts_out_host ? e->q_counts : nullptr,
+                                   actions_out_host ? e->q_actions : nullptr, e->q_r, e->q_score, e->q_moves, nullptr,
+                                   stream);
+        if (rc) return rc;
+        if (counts_out_host)
+            CUDA_TRY(cudaMemcpyAsync(counts_out_host, e->q_counts, N * E * A * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     S(stream)));
+        if (actions_out_host)
+            CUDA_TRY(cudaMemcpyAsync(actions_out_host, e->q_actions, N * E * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     S(stream)));
+    }
+    if (r_out_host) CUDA_TRY(cudaMemcpyAsync(r_out_host, e->q_r, E * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
+    if (score_out_host)
+        CUDA_TRY(cudaMemcpyAsync(score_out_host, e->q_score, E * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
+    if (moves_out_host)
+        CUDA_TRY(cudaMemcpyAsync(moves_out_host, e->q_moves, E * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
     return bpp_engine_check(e, stream);
 }
@@ -1912,14 +2047,6 @@ extern "C" int bpp_engine_play_net_host(bpp_engine* e, bpp_net* net, int choose_
         CUDA_TRY(cudaMemcpyAsync(moves_out_host, e->P.moves_done, G * sizeof(int32_t), cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
     return bpp_engine_check(e, stream);
-}
-
-// queue / result staging of bpp_engine_play_net_stream_host, grown on demand
-template <typename T>
-static int ensure(bpp_engine* e, T** p, size_t* have, size_t need) {
-    if (*p && *have >= need) return BPP_OK;
-    *have = need;
-    return dev_alloc(e, p, need);  // the old block stays owned by the handle until destroy (rare: sizes repeat)
 }
 
 extern "C" int bpp_engine_play_net_stream_host(bpp_engine* e, bpp_net* net, int choose_mode, uint64_t seed, int num_episodes,

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -255,6 +256,280 @@ __global__ void __launch_bounds__(THREADS, 2) k_lr_conv(ConvArgs a) {
         for (int q = 0; q < a.KS; ++q) v += sp[q * items];
         a.out[o] = (mk > 0.f ? v : 0.f) + ad;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One launch per ConvSequence and direction: a CTA takes G samples through the stage's five convolutions and its pooling
+// with the activations of the running layer in shared memory (zero halos), so that a layer costs its FMAs and one weight
+// fetch instead of a launch, a staging pass over global memory and a tail.  Every tensor the backward pass or the weight
+// gradient needs is still written to global memory (c, p, arg-max codes, a0, q, a1, o / da1, dq, da0, dp, dc, dout).
+// The per-layer arithmetic is conv_tile's, with the same work decomposition as k_lr_conv (row segments of TP positions x 8
+// output channels, input channels split over KS threads when a layer has fewer work items than the CTA has threads).
+struct StageLayer {
+    const float* wt;    // [cin*9][cout] (forward) or the transposed + rotated layout (data gradient)
+    const float* bias;  // nullable
+    const float* mask;  // nullable [B][cout][hw]: stashed activation whose sign gates the gradient
+    const float* add;   // nullable [B][cout][hw]: residual / gradient of the skip connection
+    float* out;         // [B][cout][hw]
+    int cin, cout, h, w, wp, TP, KS, relu_in;
+};
+struct StageArgs {
+    StageLayer L[5];    // forward: conv, res0.conv0, res0.conv1, res1.conv0, res1.conv1; backward: the reverse order
+    const float* in;    // forward: the stage's input [B][cin][h0*w0]; backward: d(stage output) [B][ch][h1*w1]
+    float* p;           // forward: pooled activation out           backward: unused
+    uint8_t* amax;      // arg-max codes of the pooling (written forward, read backward)
+    float* dc;          // backward: gradient w.r.t. the conv output (input resolution)
+    int B, G, ch, h0, w0, h1, w1, wp0, wp1;
+    int l0_dgrad;       // backward: the stage has a predecessor, its output gradient is L[4] (dgrad of the stage's conv)
+    int off_a, off_x, off_y, off_part, n_act;   // float offsets into dynamic shared memory (weights at 0)
+};
+
+__device__ __forceinline__ void stage_weights(float* s_w, const StageLayer& L, int tid) {
+    const int n4 = L.cin * 9 * L.cout / 4;
+    for (int idx = tid; idx < n4; idx += THREADS) cp_async16(s_w + 4 * idx, L.wt + 4 * idx);
+}
+
+// global [B][C][h*w] planes of samples b0 .. b0 + gmax - 1 -> shared [C][G][PP] with halo (buffer zeroed before)
+__device__ __forceinline__ void stage_planes(float* s_dst, const float* src_base, int C, int h, int w, int wp, int G, int gmax,
+                                             int b0, int tid) {
+    const int hw = h * w, PP = (h + 2) * wp, per = C * hw;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned magic = (65536u + w - 1) / w;
+    for (int pl = warp; pl < gmax * C; pl += THREADS / 32) {
+        const int g = pl / C, ci = pl - g * C;
+        const float* src = src_base + (size_t)(b0 + g) * per + ci * hw;
+        float* dst = s_dst + (ci * G + g) * PP + wp + 1;
+        for (int pos = lane; pos < hw; pos += 32) {
+            const int y = (int)(((unsigned)pos * magic) >> 16);
+            cp_async4(dst + pos + y * (wp - w), src + pos);
+        }
+    }
+}
+
+// one convolution of the stage: input in shared memory (s_in, [cin][G][PP]), weights in s_w; result to global memory and,
+// when s_out != nullptr, into the interior of the next layer's shared input ([cout][G][PP], same resolution).
+// Ends with a CTA barrier.
+template <int TP>
+__device__ __noinline__ void stage_conv(const StageLayer& a, const float* s_w, const float* s_in, float* s_out,
+                                        float* s_part, int B, int G, int b0, int tid) {
+    const int hw = a.h * a.w, wp = a.wp, PP = (a.h + 2) * wp;
+    const float lo = a.relu_in ? 0.f : -INFINITY;
+    const int nseg = (a.w + TP - 1) / TP;
+    const int rows = G * a.h * nseg, items = rows * (a.cout >> 3);
+    const int cstride = G * PP;
+    if (a.KS == 1) {
+        for (int item = tid; item < items; item += THREADS) {
+            const int cb = item / rows;
+            int r = item - cb * rows;
+            const int g = r / (a.h * nseg);
+            r -= g * a.h * nseg;
+            const int y = r / nseg, x0 = (r - y * nseg) * TP;
+            const int b = b0 + g;
+            if (b >= B) continue;
+            float acc[8][TP];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float bj = a.bias ? __ldg(a.bias + cb * 8 + j) : 0.f;
+#pragma unroll
+                for (int k = 0; k < TP; ++k) acc[j][k] = bj;
+            }
+            conv_tile<TP>(acc, s_in + g * PP + y * wp + x0, s_w + cb * 8, 0, a.cin, cstride, wp, a.cout, lo);
+#pragma unroll
+            for (int j0 = 0; j0 < 8; j0 += 2) {
+                float mk[2][TP], ad[2][TP];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const size_t o0 = ((size_t)b * a.cout + cb * 8 + j0 + j) * hw + y * a.w + x0;
+#pragma unroll
+                    for (int k = 0; k < TP; ++k) {
+                        const bool in_row = x0 + k < a.w;
+                        mk[j][k] = (a.mask && in_row) ? a.mask[o0 + k] : 1.f;
+                        ad[j][k] = (a.add && in_row) ? a.add[o0 + k] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const size_t o0 = ((size_t)b * a.cout + cb * 8 + j0 + j) * hw + y * a.w + x0;
+                    float* so = s_out ? s_out + ((cb * 8 + j0 + j) * G + g) * PP + (y + 1) * wp + x0 + 1 : nullptr;
+#pragma unroll
+                    for (int k = 0; k < TP; ++k)
+                        if (x0 + k < a.w) {
+                            const float v = (mk[j][k] > 0.f ? acc[j0 + j][k] : 0.f) + ad[j][k];
+                            a.out[o0 + k] = v;
+                            if (so) so[k] = v;
+                        }
+                }
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    {
+        const int slots = items * a.KS;
+        const bool live = tid < slots;
+        const int item = live ? tid % items : 0, ks = live ? tid / items : 0;
+        const int cb = item / rows;
+        int r = item - cb * rows;
+        const int g = r / (a.h * nseg);
+        r -= g * a.h * nseg;
+        const int y = r / nseg, x0 = (r - y * nseg) * TP;
+        const int b = b0 + g;
+        if (live) {
+            const int cpk = (a.cin + a.KS - 1) / a.KS;
+            float acc[8][TP];
+    #pragma unroll
+            for (int j = 0; j < 8; ++j)
+    #pragma unroll
+                for (int k = 0; k < TP; ++k) acc[j][k] = 0.f;
+            conv_tile<TP>(acc, s_in + g * PP + y * wp + x0, s_w + cb * 8, ks * cpk, min(a.cin, (ks + 1) * cpk), cstride, wp,
+                          a.cout, lo);
+    #pragma unroll
+            for (int j = 0; j < 8; ++j)
+    #pragma unroll
+                for (int k = 0; k < TP; ++k) s_part[(j * TP + k) * slots + tid] = acc[j][k];
+        }
+        __syncthreads();
+        if (live && b < B) {
+            const size_t obase = ((size_t)b * a.cout + cb * 8) * hw + y * a.w + x0;
+            for (int jk = ks; jk < 8 * TP; jk += a.KS) {
+                const int j = jk / TP, k = jk % TP;  // TP is a compile-time power of two
+                if (x0 + k >= a.w) continue;
+                const size_t o = obase + (size_t)j * hw + k;
+                const float mk = a.mask ? a.mask[o] : 1.f;
+                const float ad = a.add ? a.add[o] : 0.f;
+                float v = a.bias ? __ldg(a.bias + cb * 8 + j) : 0.f;
+                const float* sp = s_part + jk * slots + item;
+                for (int q = 0; q < a.KS; ++q) v += sp[q * items];
+                v = (mk > 0.f ? v : 0.f) + ad;
+                a.out[o] = v;
+                if (s_out) s_out[((cb * 8 + j) * G + g) * PP + (y + 1) * wp + x0 + k + 1] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void stage_conv_any(const StageLayer& a, const float* s_w, const float* s_in, float* s_out,
+                                               float* s_part, int B, int G, int b0, int tid) {
+    if (a.TP == 8) stage_conv<8>(a, s_w, s_in, s_out, s_part, B, G, b0, tid);
+    else if (a.TP == 4) stage_conv<4>(a, s_w, s_in, s_out, s_part, B, G, b0, tid);
+    else stage_conv<2>(a, s_w, s_in, s_out, s_part, B, G, b0, tid);
+}
+
+__global__ void __launch_bounds__(THREADS, 2) k_lr_stage_fwd(StageArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float *s_w = sm, *s_a = sm + a.off_a, *s_x = sm + a.off_x, *s_y = sm + a.off_y, *s_part = sm + a.off_part;
+    const int tid = threadIdx.x, b0 = blockIdx.x * a.G, gmax = min(a.G, a.B - b0);
+    stage_weights(s_w, a.L[0], tid);
+    for (int idx = tid; idx < a.n_act; idx += THREADS) s_a[idx] = 0.f;  // all activation buffers: the halos stay zero
+    __syncthreads();
+    stage_planes(s_a, a.in, a.L[0].cin, a.h0, a.w0, a.wp0, a.G, gmax, b0, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    stage_conv_any(a.L[0], s_w, s_a, nullptr, s_part, a.B, a.G, b0, tid);   // c (global), barrier
+    stage_weights(s_w, a.L[1], tid);   // arrive behind the pooling
+    {   // max_pool2d(3, 2, 1) with torch's arg-max rule (k_lr_pool_fwd) -> p, codes, and the first residual conv's input
+        const int h = a.h0, w = a.w0, oh = a.h1, ow = a.w1, PP1 = (oh + 2) * a.wp1;
+        const int per = a.ch * oh * ow;
+        const float* cbuf = a.L[0].out;
+        for (int i = tid; i < gmax * per; i += THREADS) {
+            const int g = i / per;
+            int r = i - g * per;
+            const int c = r / (oh * ow);
+            r -= c * oh * ow;
+            const int oy = r / ow, ox = r - oy * ow;
+            const float* pl = cbuf + ((size_t)(b0 + g) * a.ch + c) * h * w;
+            float best = -INFINITY;
+            int code = 0;
+            bool first = true;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = 2 * oy - 1 + ky;
+                if (iy < 0 || iy >= h) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = 2 * ox - 1 + kx;
+                    if (ix < 0 || ix >= w) continue;
+                    const float v = pl[iy * w + ix];
+                    if (first || v > best || v != v) {
+                        best = v;
+                        code = ky * 3 + kx;
+                        first = false;
+                    }
+                }
+            }
+            const size_t o = ((size_t)(b0 + g) * a.ch + c) * oh * ow + r;
+            a.p[o] = best;
+            a.amax[o] = (uint8_t)code;
+            s_x[(c * a.G + g) * PP1 + (oy + 1) * a.wp1 + ox + 1] = best;
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float *cur = s_x, *nxt = s_y;
+    for (int k = 1; k < 5; ++k) {
+        stage_conv_any(a.L[k], s_w, cur, k < 4 ? nxt : nullptr, s_part, a.B, a.G, b0, tid);
+        if (k < 4) {
+            stage_weights(s_w, a.L[k + 1], tid);
+            cp_async_wait_all();
+            __syncthreads();
+        }
+        float* t = cur; cur = nxt; nxt = t;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 2) k_lr_stage_bwd(StageArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float *s_w = sm, *s_a = sm + a.off_a, *s_x = sm + a.off_x, *s_y = sm + a.off_y, *s_part = sm + a.off_part;
+    const int tid = threadIdx.x, b0 = blockIdx.x * a.G, gmax = min(a.G, a.B - b0);
+    stage_weights(s_w, a.L[0], tid);
+    for (int idx = tid; idx < a.n_act; idx += THREADS) s_a[idx] = 0.f;
+    __syncthreads();
+    stage_planes(s_x, a.in, a.ch, a.h1, a.w1, a.wp1, a.G, gmax, b0, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    float *cur = s_x, *nxt = s_y;
+    for (int k = 0; k < 4; ++k) {   // da1, dq, da0, dp
+        stage_conv_any(a.L[k], s_w, cur, k < 3 ? nxt : nullptr, s_part, a.B, a.G, b0, tid);
+        if (k < 3 || a.l0_dgrad) {
+            stage_weights(s_w, a.L[k + 1], tid);   // the conv's own data-gradient weights arrive behind the pooling
+            if (k < 3) {
+                cp_async_wait_all();
+                __syncthreads();
+            }
+        }
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    {   // pooling backward (k_lr_pool_bwd): dp, codes -> dc (global) and the conv's data-gradient input
+        const int h = a.h0, w = a.w0, oh = a.h1, ow = a.w1, PP0 = (h + 2) * a.wp0;
+        const int per = a.ch * h * w;
+        const float* dpb = a.L[3].out;
+        for (int i = tid; i < gmax * per; i += THREADS) {
+            const int g = i / per;
+            int r = i - g * per;
+            const int c = r / (h * w);
+            r -= c * h * w;
+            const int iy = r / w, ix = r - iy * w;
+            const size_t pb = ((size_t)(b0 + g) * a.ch + c) * oh * ow;
+            const float* dp = dpb + pb;
+            const uint8_t* am = a.amax + pb;
+            const int oy0 = iy >> 1, oy1 = (iy + 1) >> 1, ox0 = ix >> 1, ox1 = (ix + 1) >> 1;
+            const bool vy1 = oy1 != oy0 && oy1 < oh, vx1 = ox1 != ox0 && ox1 < ow;
+            const int cy1 = vy1 ? oy1 : oy0, cx1 = vx1 ? ox1 : ox0;
+            const int i00 = oy0 * ow + ox0, i01 = oy0 * ow + cx1, i10 = cy1 * ow + ox0, i11 = cy1 * ow + cx1;
+            const int a00 = am[i00], a01 = am[i01], a10 = am[i10], a11 = am[i11];
+            const float d00 = dp[i00], d01 = dp[i01], d10 = dp[i10], d11 = dp[i11];
+            const int ky0 = iy - (2 * oy0 - 1), ky1 = iy - (2 * cy1 - 1), kx0 = ix - (2 * ox0 - 1), kx1 = ix - (2 * cx1 - 1);
+            float gsum = (a00 == ky0 * 3 + kx0) ? d00 : 0.f;
+            if (vx1 && a01 == ky0 * 3 + kx1) gsum += d01;
+            if (vy1 && a10 == ky1 * 3 + kx0) gsum += d10;
+            if (vy1 && vx1 && a11 == ky1 * 3 + kx1) gsum += d11;
+            a.dc[((size_t)(b0 + g) * a.ch + c) * h * w + r] = gsum;
+            s_a[(c * a.G + g) * PP0 + (iy + 1) * a.wp0 + ix + 1] = gsum;
+        }
+    }
+    if (!a.l0_dgrad) return;
+    cp_async_wait_all();
+    __syncthreads();
+    stage_conv_any(a.L[4], s_w, s_a, nullptr, s_part, a.B, a.G, b0, tid);   // gradient of the previous stage's output
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -737,6 +1012,7 @@ struct bpp_learner {
     int max_chunks = 0;
     int sms = 148;
     int smem_cap = 0;
+    int fused_max_batch = 128;   // one kernel per stage and direction up to this batch size, one per layer beyond
     std::vector<void*> allocs;
 };
 
@@ -784,6 +1060,67 @@ int launch_conv(bpp_learner* l, cudaStream_t st, int B, const float* in, const f
         return lerr(BPP_E_CUDA, std::string("convolution launch failed: ") + cudaGetErrorString(e) + " (smem " +
                                     std::to_string(smem) + ", G " + std::to_string(G) + ", TP " + std::to_string(TP) + ")");
     return BPP_OK;
+}
+
+// plan and launch one fused stage kernel (k_lr_stage_fwd / k_lr_stage_bwd); L[] = the five layers in execution order with
+// their global pointers filled in, geometry taken from the stage
+int launch_stage(bpp_learner* l, cudaStream_t st, int B, int s, bool fwd, StageArgs& a) {
+    a.B = B;
+    a.ch = l->chans[s];
+    a.h0 = l->hs[s]; a.w0 = l->ws[s]; a.h1 = l->hs[s + 1]; a.w1 = l->ws[s + 1];
+    a.wp0 = (a.w0 + 2) | 1; a.wp1 = (a.w1 + 2) | 1;
+    const int PP0 = (a.h0 + 2) * a.wp0, PP1 = (a.h1 + 2) * a.wp1;
+    const int nl = fwd ? 5 : (a.l0_dgrad ? 5 : 4);
+    size_t wfl = 0;
+    for (int k = 0; k < nl; ++k) {
+        a.L[k].wp = (a.L[k].w + 2) | 1;
+        wfl = std::max(wfl, (size_t)a.L[k].cin * 9 * a.L[k].cout);
+    }
+    const int cin_a = fwd ? a.L[0].cin : a.ch;   // channels of the input-resolution buffer
+    auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
+    auto plan = [&](int G, bool commit) {
+        const size_t na = r4((size_t)cin_a * G * PP0 + 8), nx = r4((size_t)a.ch * G * PP1 + 8);
+        size_t npart = 0;
+        for (int k = 0; k < nl; ++k) {
+            StageLayer& L = a.L[k];
+            auto items = [&](int TP) { return G * L.h * ((L.w + TP - 1) / TP) * (L.cout / 8); };
+            const int TP = L.w >= 7 ? 8 : (L.w >= 3 ? 4 : 2);   // output positions per work item (row segment), as k_lr_conv
+            const int KS = items(TP) >= THREADS ? 1 : std::max(1, std::min(L.cin, THREADS / items(TP)));
+            if (commit) {
+                L.TP = TP;
+                L.KS = KS;
+            }
+            if (KS > 1) npart = std::max(npart, (size_t)THREADS * 8 * TP);
+        }
+        if (commit) {
+            a.G = G;
+            a.off_a = (int)r4(wfl);
+            a.off_x = a.off_a + (int)na;
+            a.off_y = a.off_x + (int)nx;
+            a.off_part = a.off_y + (int)nx;
+            a.n_act = (int)(na + 2 * nx);
+        }
+        return (r4(wfl) + na + 2 * nx + npart) * 4;
+    };
+    int G = std::max(1, std::min(4, (B + 2 * l->sms - 1) / (2 * l->sms)));
+    while (G > 1 && plan(G, false) > (size_t)l->smem_cap) --G;
+    const size_t smem = plan(G, true);
+    if (smem > (size_t)l->smem_cap) return lerr(BPP_E_INVALID, "stage does not fit in shared memory");
+    const int grid = (B + G - 1) / G;
+    if (fwd) k_lr_stage_fwd<<<grid, THREADS, smem, st>>>(a);
+    else k_lr_stage_bwd<<<grid, THREADS, smem, st>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return lerr(BPP_E_CUDA, std::string("stage kernel launch failed: ") + cudaGetErrorString(e) + " (smem " +
+                                    std::to_string(smem) + ", G " + std::to_string(G) + ")");
+    return BPP_OK;
+}
+
+void stage_layer(StageLayer& L, const float* wt, const float* bias, const float* mask, const float* add, float* out, int cin,
+                 int cout, int h, int w, int relu_in) {
+    L.wt = wt; L.bias = bias; L.mask = mask; L.add = add; L.out = out;
+    L.cin = cin; L.cout = cout; L.h = h; L.w = w; L.relu_in = relu_in;
+    L.wp = 0; L.TP = 0; L.KS = 1;
 }
 
 }  // namespace
@@ -841,10 +1178,18 @@ extern "C" int bpp_learner_create(int W, int H, int N, int max_batch, int device
     l->smem_cap = std::min(smem_optin, 200 * 1024);
     cudaDeviceGetAttribute(&l->sms, cudaDevAttrMultiProcessorCount, device);
     if (l->sms < 1) l->sms = 148;
+    {   // fused stage kernels: measured faster than one launch per layer up to ~128 samples (one sample group per CTA),
+        // slower beyond (profiles/r02_notes.md); BPP_LEARNER_FUSED=0 / 1 forces the choice
+        const char* e = std::getenv("BPP_LEARNER_FUSED");
+        l->fused_max_batch = e ? (e[0] == '1' ? 0x7fffffff : 0) : 128;
+        if (std::getenv("BPP_LEARNER_UNFUSED")) l->fused_max_batch = 0;
+    }
     const cudaFuncAttribute dyn = cudaFuncAttributeMaxDynamicSharedMemorySize;
     if (cudaFuncSetAttribute(k_lr_conv<8>, dyn, l->smem_cap) != cudaSuccess ||
         cudaFuncSetAttribute(k_lr_conv<4>, dyn, l->smem_cap) != cudaSuccess ||
         cudaFuncSetAttribute(k_lr_conv<2>, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_stage_fwd, dyn, l->smem_cap) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lr_stage_bwd, dyn, l->smem_cap) != cudaSuccess ||
         cudaFuncSetAttribute(k_lr_wgrad, dyn, l->smem_cap) != cudaSuccess ||
         cudaFuncSetAttribute(k_lr_heads<1>, dyn, l->smem_cap) != cudaSuccess ||
         cudaFuncSetAttribute(k_lr_heads<2>, dyn, l->smem_cap) != cudaSuccess ||
@@ -913,6 +1258,7 @@ extern "C" int bpp_learner_grad(bpp_learner* l, int B, const float* params_dev, 
     if (B < 1 || B > l->max_batch) return lerr(BPP_E_INVALID, "batch size out of range");
     cudaStream_t st = (cudaStream_t)stream;
     const bool train = grads_out_dev != nullptr;
+    const bool fused = B <= l->fused_max_batch;
     const float* P = params_dev;
     int rc;
     {
@@ -932,6 +1278,18 @@ extern "C" int bpp_learner_grad(bpp_learner* l, int B, const float* params_dev, 
     for (int s = 0; s < NSTAGE; ++s) {
         const ConvL* L = &l->conv[s * 5];
         const int ch = l->chans[s], h1 = l->hs[s + 1], w1 = l->ws[s + 1];
+        if (fused) {   // one launch per stage: conv -> pool -> two residual blocks
+            StageArgs a;
+            a.in = u; a.p = l->p[s]; a.amax = l->amax[s]; a.dc = nullptr; a.l0_dgrad = 0;
+            stage_layer(a.L[0], l->wfwd + L[0].w_off, P + L[0].b_off, nullptr, nullptr, l->c[s], L[0].cin, ch, L[0].h, L[0].w, 0);
+            stage_layer(a.L[1], l->wfwd + L[1].w_off, P + L[1].b_off, nullptr, nullptr, l->a0[s], ch, ch, h1, w1, 1);
+            stage_layer(a.L[2], l->wfwd + L[2].w_off, P + L[2].b_off, nullptr, l->p[s], l->q[s], ch, ch, h1, w1, 1);
+            stage_layer(a.L[3], l->wfwd + L[3].w_off, P + L[3].b_off, nullptr, nullptr, l->a1[s], ch, ch, h1, w1, 1);
+            stage_layer(a.L[4], l->wfwd + L[4].w_off, P + L[4].b_off, nullptr, l->q[s], l->o[s], ch, ch, h1, w1, 1);
+            if ((rc = launch_stage(l, st, B, s, true, a))) return rc;
+            u = l->o[s];
+            continue;
+        }
         if ((rc = launch_conv(l, st, B, u, l->wfwd + L[0].w_off, P + L[0].b_off, nullptr, nullptr, l->c[s], L[0].cin, ch,
                               L[0].h, L[0].w, 0)))
             return rc;
@@ -987,6 +1345,18 @@ extern "C" int bpp_learner_grad(bpp_learner* l, int B, const float* params_dev, 
     for (int s = NSTAGE - 1; s >= 0; --s) {
         const ConvL* L = &l->conv[s * 5];
         const int ch = l->chans[s], h1 = l->hs[s + 1], w1 = l->ws[s + 1];
+        if (fused) {   // one launch per stage: four data gradients, pooling backward, the conv's data gradient
+            StageArgs a;
+            a.in = l->dout[s]; a.p = nullptr; a.amax = l->amax[s]; a.dc = l->dc[s]; a.l0_dgrad = s > 0;
+            stage_layer(a.L[0], l->wbwd + L[4].w_off, nullptr, l->a1[s], nullptr, l->da1[s], ch, ch, h1, w1, 0);
+            stage_layer(a.L[1], l->wbwd + L[3].w_off, nullptr, l->q[s], l->dout[s], l->dq[s], ch, ch, h1, w1, 0);
+            stage_layer(a.L[2], l->wbwd + L[2].w_off, nullptr, l->a0[s], nullptr, l->da0[s], ch, ch, h1, w1, 0);
+            stage_layer(a.L[3], l->wbwd + L[1].w_off, nullptr, l->p[s], l->dq[s], l->dp[s], ch, ch, h1, w1, 0);
+            stage_layer(a.L[4], l->wbwd + L[0].w_off, nullptr, nullptr, nullptr, s > 0 ? l->dout[s - 1] : nullptr, ch,
+                        s > 0 ? L[0].cin : 8, L[0].h, L[0].w, 0);
+            if ((rc = launch_stage(l, st, B, s, false, a))) return rc;
+            continue;
+        }
         // da1 = dgrad(res1.conv1, do) * (a1 > 0)
         if ((rc = launch_conv(l, st, B, l->dout[s], l->wbwd + L[4].w_off, nullptr, l->a1[s], nullptr, l->da1[s], ch, ch, h1,
                               w1, 0)) ||

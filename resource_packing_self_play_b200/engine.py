@@ -328,6 +328,55 @@ class SearchEngine:
              vp(out["r"]), vp(out["score"]), vp(out["moves"]), _stream())
         return out
 
+    def play_stub_stream(self, kind, items_wh, total_area, bl, tie=None, choose_mode=_lib.CHOOSE_ARGMAX_FIRST, seed=0,
+                         record=True):
+        """E >= 1 episodes streamed through the G resident games with a stub evaluator, one launch
+        (bpp_engine_play_stub_stream): a game whose episode ends takes the next instance of the queue inside the episode
+        kernel.  items_wh (E, N, 2), total_area (E,), bl (E,) float64 (NaN = empty rewards list), tie (E,) int8 or None.
+        Returns device tensors indexed by EPISODE: counts (N, E, A), actions (N, E) (None unless record), r, score, moves."""
+        items = _dev(items_wh, torch.int32, self.device)
+        E = items.shape[0]
+        items = items.reshape(E, self.N, 2)
+        area = _dev(total_area, torch.int32, self.device).reshape(E)
+        blt = _dev(bl, torch.float64, self.device).reshape(E)
+        tiet = _dev(tie, torch.int8, self.device).reshape(E) if tie is not None else None
+        counts = actions = None
+        if record:
+            counts = torch.empty((self.N, E, self.A), dtype=torch.int32, device=self.device)
+            actions = torch.empty((self.N, E), dtype=torch.int32, device=self.device)
+        r = torch.zeros(E, dtype=torch.int32, device=self.device)
+        score = torch.zeros(E, dtype=torch.float64, device=self.device)
+        moves = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self.items_wh = items[:self.G] if E >= self.G else items
+        call("bpp_engine_play_stub_stream", self._h, STUB[kind] if isinstance(kind, str) else int(kind), int(choose_mode),
+             C.c_uint64(seed), int(E), _ptr(items), _ptr(area), _ptr(blt), _ptr(tiet), _ptr(counts), _ptr(actions), _ptr(r),
+             _ptr(score), _ptr(moves), _stream())
+        return {"counts": counts, "actions": actions, "r": r, "score": score, "moves": moves}
+
+    def play_stub_stream_host(self, kind, items_wh, total_area, bl, tie=None, choose_mode=_lib.CHOOSE_ARGMAX_FIRST, seed=0,
+                              out=None):
+        """the same from / to HOST buffers through the C ABI (uploads the queue, plays, downloads, synchronises).
+        `out` may hold preallocated (ideally pinned) numpy arrays: counts (N,E,A) i32, actions (N,E) i32, r (E,) i32,
+        score (E,) f64, moves (E,) i32."""
+        items = np.ascontiguousarray(items_wh, dtype=np.int32)
+        E = items.shape[0]
+        area = np.ascontiguousarray(total_area, dtype=np.int32)
+        blh = np.ascontiguousarray(bl, dtype=np.float64)
+        tieh = np.ascontiguousarray(tie, dtype=np.int8) if tie is not None else None
+        if out is None:
+            out = {}
+        out.setdefault("counts", np.empty((self.N, E, self.A), dtype=np.int32))
+        out.setdefault("actions", np.empty((self.N, E), dtype=np.int32))
+        out.setdefault("r", np.empty(E, dtype=np.int32))
+        out.setdefault("score", np.empty(E, dtype=np.float64))
+        out.setdefault("moves", np.empty(E, dtype=np.int32))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        call("bpp_engine_play_stub_stream_host", self._h, STUB[kind] if isinstance(kind, str) else int(kind),
+             int(choose_mode), C.c_uint64(seed), int(E), vp(items), vp(area), vp(blh),
+             vp(tieh) if tieh is not None else C.c_void_p(0), vp(out["counts"]), vp(out["actions"]), vp(out["r"]),
+             vp(out["score"]), vp(out["moves"]), _stream())
+        return out
+
     # -- asynchronous whole episodes with the batched device evaluator ---------------------------------------------------
     def set_auto_play(self, mode, seed=0, counts=None, actions=None, roots=None):
         """arm (mode = CHOOSE_*) / disarm (mode = -1) per-game move completion inside expand_select"""

@@ -306,3 +306,52 @@ def test_streamed_episodes_do_not_depend_on_the_number_of_resident_games(W, H, E
         assert np.array_equal(out[k], a[k]), k
     assert np.array_equal(out["roots"].view(np.int32), a["roots"])
     bm.close()
+
+
+@pytest.mark.parametrize("W,H,E,G,SIMS,stub,mode", [(15, 15, 150, 32, 40, "U", 1), (20, 20, 61, 7, 25, "V", 2),
+                                                    (15, 15, 40, 64, 30, "H", 0)])
+def test_streamed_stub_episodes_equal_one_game_per_episode(W, H, E, G, SIMS, stub, mode):
+    """bpp_engine_play_stub_stream: E instances through G resident games in one launch of the episode kernel (a game whose
+    episode ends takes the next instance) == reset + play_stub with one game per instance: identical visit counts,
+    actions and outcomes per episode (the action stream is keyed by (seed, episode, move)); G > E leaves games idle.
+    The host-buffer form (pinned buffers: written by the kernel itself; pageable: staged) returns the same."""
+    from resource_packing_self_play_b200.engine import SearchEngine
+    from resource_packing_self_play_b200.game import ItemsGenerator
+    N = 10
+    rng = np.random.RandomState(11)
+    heights = rng.randint(2, H + 1, size=E).astype(np.int32)
+    items = ItemsGenerator(W, H, N).items_batch(np.arange(E) + 400, heights)
+    area = (W * heights).astype(np.int32)
+    bl = np.full(E, np.nan) if stub == "U" else np.full(E, 0.7001)
+    ref = SearchEngine(W, H, N, E, SIMS, 1.0)
+    ref.reset(items, area, bl)
+    counts, actions = ref.play_stub(stub, choose_mode=mode, seed=21)
+    ref.check()
+    st = {k: v.cpu().numpy() for k, v in ref.status().items()}
+    counts, actions = counts.cpu().numpy(), actions.cpu().numpy()
+    ref.close()
+    assert (st["done"] == 1).all() and st["moves"].min() >= 1
+
+    eng = SearchEngine(W, H, N, G, SIMS, 1.0)
+    out = eng.play_stub_stream(stub, items, area, bl, choose_mode=mode, seed=21)
+    eng.check()
+    assert np.array_equal(out["counts"].cpu().numpy(), counts)
+    assert np.array_equal(out["actions"].cpu().numpy(), actions)
+    for k in ("r", "score", "moves"):
+        assert np.array_equal(out[k].cpu().numpy(), st[k]), k
+    # a second stream on the same handle (pools and hash tables of the games are reused), without recording
+    out2 = eng.play_stub_stream(stub, items[::-1].copy(), area[::-1].copy(), bl, choose_mode=0, seed=21, record=False)
+    eng.check()
+    assert out2["counts"] is None and (out2["moves"].cpu().numpy() >= 1).all()
+    # host buffers: pageable (staged copies) and pinned (zero-copy rows written by the episode kernel)
+    host = eng.play_stub_stream_host(stub, items, area, bl, choose_mode=mode, seed=21)
+    pinned = {"counts": torch.empty((N, E, W * N), dtype=torch.int32).pin_memory().numpy(),
+              "actions": torch.empty((N, E), dtype=torch.int32).pin_memory().numpy()}
+    pinned["counts"][:] = 7
+    pinned["actions"][:] = 7
+    hostp = eng.play_stub_stream_host(stub, items, area, bl, choose_mode=mode, seed=21, out=pinned)
+    for o in (host, hostp):
+        assert np.array_equal(o["counts"], counts) and np.array_equal(o["actions"], actions)
+        for k in ("r", "score", "moves"):
+            assert np.array_equal(o[k], st[k]), k
+    eng.close()

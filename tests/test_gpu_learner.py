@@ -89,6 +89,32 @@ def test_gradients_match_autograd(W, H, N, B):
     L.close()
 
 
+@pytest.mark.parametrize("W,H,N,B", [(15, 15, 10, 64), (15, 15, 10, 300), (20, 20, 10, 48), (9, 12, 5, 130), (15, 15, 10, 1201),
+                                     (32, 28, 16, 20), (3, 2, 2, 9)])
+def test_fused_stage_kernels_match_the_per_layer_kernels(W, H, N, B, monkeypatch):
+    """one launch per ConvSequence and direction (k_lr_stage_fwd / k_lr_stage_bwd, the default up to 128 samples) against
+    one launch per layer: the same work decomposition per layer, so the results agree to fp32 summation noise (bit for
+    bit where both paths pick the same number of samples per CTA)"""
+    from resource_packing_self_play_b200.nnet import DeviceLearner
+    ops, recs, items, pis, vs = _examples(B, W, H, N, seed=9)
+    m = _module(W, H, N, scale=1.5)
+    out = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("BPP_LEARNER_FUSED", fused)
+        L = DeviceLearner(W, H, N, max_batch=B)
+        L.load_state_dict(m.state_dict())
+        logp = torch.empty((B, W * N), device="cuda")
+        v = torch.empty(B, device="cuda")
+        losses = L.grad(recs, items, pis, vs, logp_out=logp, v_out=v).clone()
+        out.append((losses, L.grads.clone(), logp, v))
+        L.close()
+    (l1, g1, p1, v1), (l0, g0, p0, v0) = out
+    assert bool(torch.isfinite(g1).all())
+    assert float((l1 - l0).abs().max()) < 1e-5
+    assert float((g1 - g0).abs().max()) <= 2e-5 * float(g0.abs().max())
+    assert float((p1 - p0).abs().max()) < 1e-5 and float((v1 - v0).abs().max()) < 1e-5
+
+
 def test_gather_index_and_determinism():
     from resource_packing_self_play_b200.nnet import DeviceLearner
     W, H, N, M, B = 15, 15, 10, 200, 64
