@@ -179,34 +179,45 @@ __device__ __forceinline__ void flush_stats(const Params& P, const Stats& st, in
 // Find the node of a state (full-key equality, like the dict lookup of MCTS_bpp.py:76-85) or create it.
 // (scalars instead of `const Params&`: a reference into kernel-parameter space from a non-inlined function would force
 // a 480-byte local copy of Params in every kernel)
-__device__ __noinline__ int lookup_or_insert(int H, int node_cap, uint32_t table_mask, GameCtx& gm, uint32_t rec, int lane,
-                                             Stats& st) {
+// The context fields travel by value and the counters come back packed (bits 0..31 node index or -1, bits 32..47 probes,
+// bit 48 created): a reference into the caller's GameCtx / Stats would pin both structures in local memory for the whole
+// search loop (LDL / STL on the critical path of every level).
+__device__ __noinline__ long long lookup_or_insert_v(int H, int node_cap, uint32_t table_mask, uint32_t* table, uint32_t* nodes,
+                                                     int n_nodes, uint32_t rec, int lane) {
     const uint32_t h = hash_state(rec, lane, H);
     const uint32_t tag = h >> 20;
     uint32_t slot = h & table_mask;
+    long long probes = 0;
     for (;;) {
-        st.probes++;
-        const uint32_t ent = gm.table[slot];
+        probes++;
+        const uint32_t ent = table[slot];
         if (ent == 0u) {
-            if (gm.n_nodes >= node_cap) {
-                gm.err = 4;
-                return -1;
-            }
-            const int idx = gm.n_nodes++;
-            gm.nodes[(size_t)idx * REC_WORDS + lane] = state_lane(lane, H) ? rec : 0u;
-            if (lane == 0) gm.table[slot] = (tag << 20) | (uint32_t)(idx + 1);
+            if (n_nodes >= node_cap) return (probes << 32) | 0xffffffffll;
+            const int idx = n_nodes;
+            nodes[(size_t)idx * REC_WORDS + lane] = state_lane(lane, H) ? rec : 0u;
+            if (lane == 0) table[slot] = (tag << 20) | (uint32_t)(idx + 1);
             __syncwarp();
-            st.created++;
-            return idx;
+            return (1ll << 48) | (probes << 32) | (long long)idx;
         }
         if ((ent >> 20) == tag) {
             const int cand = (int)(ent & 0xfffffu) - 1;
-            const uint32_t o = gm.nodes[(size_t)cand * REC_WORDS + lane];
+            const uint32_t o = nodes[(size_t)cand * REC_WORDS + lane];
             const bool same = !state_lane(lane, H) || o == rec;
-            if (__all_sync(FULL, same)) return cand;
+            if (__all_sync(FULL, same)) return (probes << 32) | (long long)cand;
         }
         slot = (slot + 1u) & table_mask;
     }
+}
+__device__ __forceinline__ int lookup_or_insert(int H, int node_cap, uint32_t table_mask, GameCtx& gm, uint32_t rec, int lane,
+                                                Stats& st) {
+    const long long r = lookup_or_insert_v(H, node_cap, table_mask, gm.table, gm.nodes, gm.n_nodes, rec, lane);
+    const int idx = (int)(uint32_t)r;
+    const unsigned created = (unsigned)(r >> 48) & 1u;
+    st.probes += (unsigned)(r >> 32) & 0xffffu;
+    st.created += created;
+    gm.n_nodes += (int)created;
+    if (idx < 0) gm.err = 4;
+    return idx;
 }
 
 // Leaf expansion, MCTS_bpp.py:85-104.  sm.vw holds the valid mask.  prior(a) is the evaluator's p[a] as float64.
