@@ -70,32 +70,73 @@ __device__ __forceinline__ uint32_t strip_mask(int w, int x, unsigned wmask) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Valid-move mask.  s_occ[0..H) = occupancy rows (shared, this warp's 16-byte aligned strip), s_items[i] = w | h << 8,
-// s_tab = 16-entry scratch.  The (remaining item, column x) pairs are enumerated densely: pair p = k*W + x, k = rank of
-// the item among the remaining ones, so late in an episode (few items left) only ceil(nrem*W/32) rounds run.
+// s_tab = 16-entry scratch, s_col = VW_SCRATCH words of scratch.  The (remaining item, column x) pairs are enumerated
+// densely: pair p = k*W + x, k = rank of the item among the remaining ones, so late in an episode (few items left) only
+// ceil(nrem*W/32) rounds run.
 //   (A) cell-count test (BinPackingLogic.py:89): occupied cells of the strip [:, x:x+w] <= w*(H-h);
 //   (B) left adjacency (BinPackingLogic.py:63-70): x == 0, or the cell left of the strip is occupied in the first strip
 //       row that is completely empty (row H-1 if none: the reference's loop variable keeps its last value).
-// HC > 0 = compile-time bin height: the rows are held in registers (vector shared loads) and the row sweep is fully
-// unrolled; HC == 0 = generic.  The sweep carries no cross-lane dependency, which keeps the per-warp latency short
-// (an item-major variant with prefix sums and early-exit votes executed fewer instructions but ran 10 % slower).
+// COLUMN view (round 2; the row sweep per pair - H x {and, popc, add, compare, or} - was 40 % of k_episode's
+// instructions): lane c builds col[c] = the H-bit occupancy of column c once per call; then per pair
+//   occupied rows of the strip = OR of col[x .. x+w)  -> two look-ups in a sparse table of range ORs (level k covers 2^k
+//                                                       columns, built with one shuffle per level),
+//   cell count                 = pre[x+w] - pre[x]      (prefix sums of popc(col), one warp scan),
+//   left neighbour             = bit t of col[x-1].
+// HC > 0 = compile-time bin height (the column build is unrolled over vector loads of the rows); HC == 0 = generic.
 // Returns word k of the A-bit mask in lane k (0 elsewhere); also leaves the words in s_vw[0..MAX_AW).
+constexpr int VW_LEVELS = 6;                       // range ORs over 1, 2, 4, 8, 16, 32 columns
+constexpr int VW_PRE = VW_LEVELS * 32;             // prefix sums pre[0..32] behind the table
+constexpr int VW_SCRATCH = VW_PRE + 36;            // 32-bit words
 template <int HC>
 __device__ __forceinline__ uint32_t valid_words(const Geom& g, const uint32_t* s_occ, const uint16_t* s_items,
-                                                uint32_t rem, int lane, uint32_t* s_vw, uint8_t* s_tab) {
+                                                uint32_t rem, int lane, uint32_t* s_vw, uint8_t* s_tab, uint32_t* s_col) {
     const int H = HC ? HC : g.H;
-    constexpr int NR = HC ? ((HC + 3) & ~3) : 4;
-    uint32_t occ[NR];
+    uint32_t col = 0;
     if (HC) {
+        constexpr int NR = (HC + 3) & ~3;
 #pragma unroll
         for (int r4 = 0; r4 < NR; r4 += 4) {
             const uint4 v = *reinterpret_cast<const uint4*>(s_occ + r4);
-            occ[r4] = v.x; occ[r4 + 1] = v.y; occ[r4 + 2] = v.z; occ[r4 + 3] = v.w;
+            col |= ((v.x >> lane) & 1u) << r4;
+            if (r4 + 1 < HC) col |= ((v.y >> lane) & 1u) << (r4 + 1);
+            if (r4 + 2 < HC) col |= ((v.z >> lane) & 1u) << (r4 + 2);
+            if (r4 + 3 < HC) col |= ((v.w >> lane) & 1u) << (r4 + 3);
         }
+    } else {
+        for (int r = 0; r < H; ++r) col |= ((s_occ[r] >> lane) & 1u) << r;
     }
+    if (lane >= g.W) col = 0u;
     rem &= (g.N >= 32) ? 0xffffffffu : ((1u << g.N) - 1u);
     if (lane < MAX_AW) s_vw[lane] = 0u;
     if ((rem >> lane) & 1u) s_tab[__popc(rem & ((1u << lane) - 1u))] = (uint8_t)lane;  // rank -> item index
+    {   // sparse table of range ORs: level k, entry c = OR of col[c .. c + 2^k) (clipped at the last lane)
+        uint32_t t = col;
+        s_col[lane] = t;
+        t |= __shfl_down_sync(FULL, t, 1);
+        s_col[32 + lane] = t;
+        t |= __shfl_down_sync(FULL, t, 2);
+        s_col[64 + lane] = t;
+        t |= __shfl_down_sync(FULL, t, 4);
+        s_col[96 + lane] = t;
+        if (g.W > 15) {   // items at least 16 (32) wide exist only in bins that wide
+            t |= __shfl_down_sync(FULL, t, 8);
+            s_col[128 + lane] = t;
+            if (g.W > 31) {
+                t |= __shfl_down_sync(FULL, t, 16);
+                s_col[160 + lane] = t;
+            }
+        }
+        int inc = __popc(col);   // inclusive scan of the column counts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        s_col[VW_PRE + 1 + lane] = (uint32_t)inc;
+        if (lane == 0) s_col[VW_PRE] = 0u;
+    }
     __syncwarp();
+    const uint32_t hmask = (1u << H) - 1u;   // H <= 28
     const int npairs = __popc(rem) * g.W;
     for (int p0 = 0; p0 < npairs; p0 += 32) {
         const int p = p0 + lane;
@@ -105,25 +146,13 @@ __device__ __forceinline__ uint32_t valid_words(const Geom& g, const uint32_t* s
             const int i = s_tab[k];
             const int w = s_items[i] & 0xff, h = s_items[i] >> 8;
             if (x + w <= g.W) {
-                const uint32_t m = strip_mask(w, x, g.wmask);
-                int cnt = 0;
-                uint32_t emp = 0;  // bit r: strip row r is completely empty
-                if (HC) {
-#pragma unroll
-                    for (int r = 0; r < HC; ++r) {
-                        const uint32_t c = occ[r] & m;
-                        cnt += __popc(c);
-                        emp |= (c == 0u ? 1u : 0u) << r;
-                    }
-                } else {
-                    for (int r = 0; r < H; ++r) {
-                        const uint32_t c = s_occ[r] & m;
-                        cnt += __popc(c);
-                        emp |= (c == 0u ? 1u : 0u) << r;
-                    }
-                }
+                const int lv = 31 - __clz(w | 1);
+                const uint32_t* tk = s_col + lv * 32;
+                const uint32_t occ_rows = w > 0 ? (tk[x] | tk[x + w - (1 << lv)]) : 0u;  // rows with a cell in the strip
+                const uint32_t emp = ~occ_rows & hmask;                                  // strip rows completely empty
+                const int cnt = (int)s_col[VW_PRE + x + w] - (int)s_col[VW_PRE + x];
                 const int t = emp ? __ffs(emp) - 1 : H - 1;
-                if ((cnt <= w * (H - h)) && (x == 0 || ((s_occ[t] >> (x - 1)) & 1u))) {
+                if ((cnt <= w * (H - h)) && (x == 0 || ((s_col[x - 1] >> t) & 1u))) {
                     const int a = i * g.W + x;
                     atomicOr(&s_vw[a >> 5], 1u << (a & 31));
                 }

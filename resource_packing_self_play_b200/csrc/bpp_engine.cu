@@ -120,6 +120,7 @@ struct Params {
 
 struct __align__(16) WarpSmem {
     uint32_t occ[32];
+    uint32_t col[VW_SCRATCH];   // valid_words: range-OR table over the columns + prefix sums of the column counts
     uint32_t vw[MAX_AW];
     uint16_t items[BPP_MAX_ITEMS];
     uint8_t tab[16];
@@ -297,7 +298,7 @@ __device__ __forceinline__ int simulate(const Params& P, GameCtx& gm, WarpSmem& 
             // first visit of this state: Es (getGameEnded) then, if not terminal, expansion
             sm.occ[lane] = rec;
             __syncwarp();
-            const uint32_t mine = valid_words<HC>(ge, sm.occ, sm.items, rem, lane, sm.vw, sm.tab);
+            const uint32_t mine = valid_words<HC>(ge, sm.occ, sm.items, rem, lane, sm.vw, sm.tab, sm.col);
             if (!__any_sync(FULL, mine != 0u)) {
                 double score;
                 const int r = terminal_value(ge, gm.rc, rec, lane, &score);
@@ -658,7 +659,7 @@ __device__ __forceinline__ int advance_game(const Params& P, GameCtx& gm, WarpSm
     sm.occ[lane] = rec;
     __syncwarp();
     const uint32_t nrem = __shfl_sync(FULL, rec, REC_REM);
-    const uint32_t mine = valid_words<0>(ge, sm.occ, sm.items, nrem, lane, sm.vw, sm.tab);
+    const uint32_t mine = valid_words<0>(ge, sm.occ, sm.items, nrem, lane, sm.vw, sm.tab, sm.col);
     int status = 0;
     if (!__any_sync(FULL, mine != 0u)) {
         double score;
@@ -940,7 +941,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_env_valid(EnvArgs E, uin
     uint32_t rec;
     env_load(E, s, lane, sm, rec);
     const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
-    valid_words<0>(E.geom, sm.occ, sm.items, rem, lane, sm.vw, sm.tab);
+    valid_words<0>(E.geom, sm.occ, sm.items, rem, lane, sm.vw, sm.tab, sm.col);
     for (int a = lane; a < E.geom.A; a += 32) out[(size_t)s * E.geom.A + a] = (uint8_t)((sm.vw[a >> 5] >> (a & 31)) & 1u);
 }
 
@@ -971,7 +972,7 @@ k_env_ended(EnvArgs E, const int32_t* total_area, const int32_t* max_h, const do
     uint32_t rec;
     env_load(E, s, lane, sm, rec);
     const uint32_t rem = __shfl_sync(FULL, rec, REC_REM);
-    const uint32_t mine = valid_words<0>(E.geom, sm.occ, sm.items, rem, lane, sm.vw, sm.tab);
+    const uint32_t mine = valid_words<0>(E.geom, sm.occ, sm.items, rem, lane, sm.vw, sm.tab, sm.col);
     int res = 0;
     double score = 0.0;
     if (!__any_sync(FULL, mine != 0u)) {
