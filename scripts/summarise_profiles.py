@@ -51,6 +51,12 @@ def raw(rep):
 def main():
     os.makedirs(PROF, exist_ok=True)
     traffic = {}
+    for d in (PROF, os.path.join(ROOT, "profiles")):   # entries of reports that are not re-captured are kept
+        try:
+            traffic = json.load(open(os.path.join(d, "r02_traffic.json")))
+            break
+        except Exception:
+            pass
     for rep in sorted(f for f in os.listdir(OUT) if f.startswith("r02_") and f.endswith(".ncu-rep")):
         ks = raw(os.path.join(OUT, rep))
         if not ks:
