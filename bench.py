@@ -832,8 +832,21 @@ def main():
     cx = Ctx(args)
     t_start = time.perf_counter()
     line, sec = None, {}
+
+    def release():
+        """hand the finished workload's buffers back to the driver (device blocks and pinned host blocks that torch's caching
+        allocators would otherwise keep for the rest of the process): every workload starts from the same memory state"""
+        import gc
+        gc.collect()
+        cx.torch.cuda.empty_cache()
+        try:
+            cx.torch._C._host_emptyCache()
+        except Exception:  # noqa: BLE001
+            pass
+
     if "stub" in todo:
         line = run_stub_arm(cx)
+        release()
         if args.stub_stream_mult > 1:
             # the same games with ONE episode per game and step (the launch ends with an idle tail while the longest
             # episodes finish): the figure of round 1 and of the ncu captures, for comparison
@@ -849,6 +862,7 @@ def main():
             r = fn()
             if r is not None:
                 r["wall_s"] = time.perf_counter() - t0
+            release()
             return r
         except Exception as err:  # noqa: BLE001
             if cx.world > 1:
