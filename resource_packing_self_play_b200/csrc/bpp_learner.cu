@@ -7,6 +7,10 @@
 // checkpoints reach logits of -3e3, which bf16 operands cannot represent, DESIGN.md "leaf evaluation"), and the net is
 // 4.4 MFLOP per sample, so a minibatch step is ~7 GFLOP: launch- and latency-bound, not FLOP-bound.
 //
+// Launches per step: up to 128 samples one kernel per ConvSequence and direction (k_lr_stage_fwd / k_lr_stage_bwd: the
+// running activation stays in shared memory across the stage's five layers; 13 launches), beyond that one kernel per layer
+// (k_lr_conv / k_lr_pool_*; 41 launches) - the fused form measured slower from 256 samples on (profiles/r02_notes.md).
+//
 // Layout: activations fp32 [B][C][h*w] per tensor in one device buffer.  Parameters, gradients and Adam moments are
 // flat caller-owned fp32 device buffers in state_dict order (bpp_learner_param_offset).  Per-chunk partial gradients
 // [chunk][param] are summed in a fixed order (no atomics): the step is run-to-run deterministic.
