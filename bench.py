@@ -220,7 +220,10 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, {"parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective"}),
+            # the same workload description as the B200 arm's line (each CPU step is a bounded sample of it: cpu_baseline.sample)
+            "config": config_dict(args, {"parallelism": f"games sharded over {args.gpus} GPU(s), no data-path collective",
+                                         "episodes_per_step": max(1, args.stub_stream_mult) * args.games},
+                                  max(1, args.stub_stream_mult)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "episodes_per_sec": args.steps * eps_per_step / dt, "gpu_launches": 0}
